@@ -1,0 +1,705 @@
+// mitc4_math.h — per-lane arithmetic of the MITC4 director-shell assembly kernel.
+//
+// One warp owns one element.  The warp walks through a fixed sequence of
+// phases; inside a phase every lane executes the same straight-line code on its
+// own slice of the element (a node, a Gauss point, three columns of the strain
+// matrix, a pair of nodes ...) and the phases communicate through an
+// ElemScratch record that lives in shared memory.  The functions below are the
+// phase bodies.  They are written against plain pointers so that the very same
+// code can be stepped lane by lane on the host (tests/host_emul.cpp) — the CUDA
+// kernel in assemble.cu only adds the warp synchronisation between phases, the
+// DMMA contraction and the scatter.
+//
+// What is computed (reference: TACSShellElement<Quad2x2, QuadBasis<2>,
+// LinearizedRotation, Linear|NonlinearModel>, src/elements/shell/
+// TACSShellElement.h:303-771).  With q the 24 element DOFs, every strain of the
+// element is a polynomial of degree <= 2 in q:
+//       e(q) = B0 q + 1/2 B1(q) q,          B(q) = de/dq = B0 + B1(q)
+// and the reference's hand-differentiated code evaluates the exact gradient and
+// Hessian of U = 1/2 sum_qp w (e - T eth)^T C (e - T eth).  We form those
+// directly:
+//       r  = sum_qp w B^T s                      s = C (e - T eth)
+//       K  = sum_qp w B^T C B + Kgeo(s)          (B = B0 for the linear model)
+//       G  = sum_qp w (B1^T C B0 + B0^T C B1) + Kgeo(s0),  s0 = C (B0 q - T eth)
+// G is the part of the nonlinear tangent that is linear in (q, T): exactly what
+// the reference's central difference (TACSShellElement.h:705-751) converges to,
+// without its cancellation noise.
+//
+// Strain rows per Gauss point (TACSShellElementModel.h:440-455):
+//   0,1,2 membrane (e11, e22, 2e12)   6,7 transverse shear (2e23, 2e13)
+//   3,4,5 bending                     8   drilling penalty strain
+// Rows 0,1,2,6,7 come from the 9 MITC tying strains (QuadBasis.h:530-672).
+#ifndef A2DS_MITC4_MATH_H
+#define A2DS_MITC4_MATH_H
+
+#include <math.h>
+
+#ifdef __CUDACC__
+#define A2DS_HD __host__ __device__ __forceinline__
+#else
+#define A2DS_HD inline
+#endif
+
+namespace a2ds {
+
+// Products and sums that must not be contracted into FMAs: used where the
+// reference's own rounding has to be reproduced (see drill_strain_state).
+#ifdef __CUDA_ARCH__
+#define A2DS_MUL(a, b) __dmul_rn((a), (b))
+#define A2DS_ADD(a, b) __dadd_rn((a), (b))
+#else
+// host build (tests/host_emul.cpp): a volatile temporary keeps the compiler from
+// fusing, so the emulation can be built with -mfma -ffp-contract=fast to mimic nvcc
+static inline double a2ds_host_mul(double a, double b) { volatile double r = a * b; return r; }
+static inline double a2ds_host_add(double a, double b) { volatile double r = a + b; return r; }
+#define A2DS_MUL(a, b) a2ds_host_mul((a), (b))
+#define A2DS_ADD(a, b) a2ds_host_add((a), (b))
+#endif
+
+// Component (constitutive + element class) record, device resident.
+// Cs/eth are produced on the host by the reference's own constitutive object
+// (TACSShellConstitutive.h:34; TACSIsoShellConstitutive.cpp:192-226, 438-456).
+struct CompData {
+  double Cs[22];       // A[6] B[6] D[6] As[3] drill
+  double eth[9];       // thermal strain per unit temperature
+  double temperature;  // TACSShellElement::temperature
+  double axis[3];      // normalised reference axis (transform == 1)
+  int model;           // 0 linear strain model, 1 nonlinear
+  int transform;       // 0 natural, 1 reference axis
+};
+
+// operand arrays for the contraction are stored [dof column][strain row] with a
+// leading dimension of 36 doubles: conflict-free for the DMMA fragment loads
+static const int LDS_ROWS = 36;
+
+struct ElemScratch {
+  double X[12], q[24];
+  double fn[12];   // unit node normals            (TacsShellComputeNodeNormals)
+  double dr[12];   // directors d_m = theta_m x fn_m (TACSDirector.h:244-267)
+  double t0n[12], t1n[12], wn[12];  // node frames: T columns 0,1 and t0 x t1
+  double Sn[16];   // per node: (Xd^-1 T)[0..1][0..1]
+  double etn[4];   // nodal drill strain of the state, evaluated in the reference's order
+  double Pq[4][6]; // per Gauss point: T T^T (symmetric)
+  double ca[4][8][2], cb[4][8][2];  // per Gauss point, per generalised node
+                                    // (u_0..u_3, d_0..d_3): coefficient pairs
+  double sg[4][3]; // per Gauss point: w*s3, w*s4, w*s5 (bending resultants)
+  double sig[4][9];    // per Gauss point contribution to the tying-point stresses
+  double rpart[4][24]; // per Gauss point contribution to the residual
+  double epart[32][9]; // per lane contribution to the Gauss point strains
+  double BA[24 * LDS_ROWS];  // strain matrix B (A operand)
+  double W[24 * LDS_ROWS];   // w C B
+  double B1[24 * LDS_ROWS];  // state dependent part B1(q)
+};
+
+A2DS_HD void cross(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+A2DS_HD double dot(const double a[3], const double b[3]) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+
+// 3x3 inverse, adjugate form as TACSElementAlgebra.h:1980 (row major)
+A2DS_HD double inv3(const double A[9], double Ai[9]) {
+  double det = (A[8] * (A[0] * A[4] - A[3] * A[1]) - A[7] * (A[0] * A[5] - A[3] * A[2]) +
+                A[6] * (A[1] * A[5] - A[2] * A[4]));
+  double di = 1.0 / det;
+  Ai[0] = (A[4] * A[8] - A[5] * A[7]) * di;
+  Ai[1] = -(A[1] * A[8] - A[2] * A[7]) * di;
+  Ai[2] = (A[1] * A[5] - A[2] * A[4]) * di;
+  Ai[3] = -(A[3] * A[8] - A[5] * A[6]) * di;
+  Ai[4] = (A[0] * A[8] - A[2] * A[6]) * di;
+  Ai[5] = -(A[0] * A[5] - A[2] * A[3]) * di;
+  Ai[6] = (A[3] * A[7] - A[4] * A[6]) * di;
+  Ai[7] = -(A[0] * A[7] - A[1] * A[6]) * di;
+  Ai[8] = (A[0] * A[4] - A[1] * A[3]) * di;
+  return det;
+}
+
+// Local frame T = [t1 | t2 | n] (columns) from X,xi and the normal.
+// Natural transform reproduces TACSShellElementTransform.h:25-92 including the
+// projection that only updates the first component (lines 42-44, three
+// successive subtractions); reference-axis transform follows :116-213.
+A2DS_HD void shell_transform(const CompData &c, const double Xxi[3], const double n0[3],
+                             double t1[3], double t2[3], double n[3]) {
+  double inv = 1.0 / sqrt(dot(n0, n0));
+  n[0] = n0[0] * inv; n[1] = n0[1] * inv; n[2] = n0[2] * inv;
+  if (c.transform == 0) {
+    t1[0] = Xxi[0]; t1[1] = Xxi[1]; t1[2] = Xxi[2];
+    double d = dot(n, t1);
+    t1[0] = t1[0] - d * n[0];
+    t1[0] = t1[0] - d * n[0];
+    t1[0] = t1[0] - d * n[0];
+  } else {
+    double an = dot(c.axis, n);
+    t1[0] = c.axis[0] - an * n[0];
+    t1[1] = c.axis[1] - an * n[1];
+    t1[2] = c.axis[2] - an * n[2];
+  }
+  inv = 1.0 / sqrt(dot(t1, t1));
+  t1[0] *= inv; t1[1] *= inv; t1[2] *= inv;
+  cross(n, t1, t2);
+}
+
+// half edge vectors of a nodal field with stride `ld`:
+//   a[i] = d/dxi at eta = -1,+1     b[i] = d/deta at xi = -1,+1
+A2DS_HD void edge_vectors(const double *v, int ld, double a0[3], double a1[3], double b0[3],
+                          double b1[3]) {
+  for (int k = 0; k < 3; k++) {
+    a0[k] = 0.5 * (v[ld + k] - v[k]);
+    a1[k] = 0.5 * (v[3 * ld + k] - v[2 * ld + k]);
+    b0[k] = 0.5 * (v[2 * ld + k] - v[k]);
+    b1[k] = 0.5 * (v[3 * ld + k] - v[ld + k]);
+  }
+}
+
+// Drill strain of the state at node m, in the operation order of the reference
+// (TacsShellComputeDrillStrain, TACSShellUtilities.h:651-693; evalDrillStrain,
+// TACSDirector.h:560-564):  et = 1/2 (Ct[3] + u0x[3] - Ct[1] - u0x[1]) with
+// Ct = (T^T C) T, C = I - theta^x and u0x = T^T ([u,xi | u,eta | 0] (Xd^-1 T)).
+// Ct[3] and Ct[1] carry the O(1) entries of T^T T (T is not orthonormal, see
+// shell_transform), so their difference loses digits relative to the rotation
+// size.  The residual inherits that rounding noise; evaluating the value the same
+// way keeps our residual within 1e-12 of the reference instead of 1e-12 of the
+// exact value.  The derivative rows (strain_columns) do not need this.
+A2DS_HD double drill_strain_state(const double T[9], const double S[9], const double uxi[3],
+                                  const double ueta[3], const double th[3]) {
+  // C = I - theta^x  (setMatSkew(-1, q, C), TACSElementAlgebra.h:1518)
+  const double C[9] = {1.0, th[2], -th[1], -th[2], 1.0, th[0], th[1], -th[0], 1.0};
+  // tmp = T^T C  (rows 0,1 only), mat3x3TransMatMult: C[3i+j] = A[i]B[j]+A[3+i]B[3+j]+A[6+i]B[6+j]
+  double tc[6];
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 3; j++)
+      tc[3 * i + j] = A2DS_ADD(A2DS_ADD(A2DS_MUL(T[i], C[j]), A2DS_MUL(T[3 + i], C[3 + j])),
+                               A2DS_MUL(T[6 + i], C[6 + j]));
+  // Ct = tmp T, entries [1] = (0,1) and [3] = (1,0), mat3x3MatMult
+  const double ct1 = A2DS_ADD(A2DS_ADD(A2DS_MUL(tc[0], T[1]), A2DS_MUL(tc[1], T[4])),
+                              A2DS_MUL(tc[2], T[7]));
+  const double ct3 = A2DS_ADD(A2DS_ADD(A2DS_MUL(tc[3], T[0]), A2DS_MUL(tc[4], T[3])),
+                              A2DS_MUL(tc[5], T[6]));
+  // tmp2 = u0d S with u0d = [u,xi | u,eta | 0] (columns); columns 0,1 needed
+  double us[6];
+  for (int k = 0; k < 3; k++)
+    for (int j = 0; j < 2; j++)
+      us[2 * k + j] = A2DS_ADD(A2DS_ADD(A2DS_MUL(uxi[k], S[j]), A2DS_MUL(ueta[k], S[3 + j])),
+                               A2DS_MUL(0.0, S[6 + j]));
+  // u0x = T^T tmp2, entries [1] = (0,1), [3] = (1,0)
+  const double u1 = A2DS_ADD(A2DS_ADD(A2DS_MUL(T[0], us[1]), A2DS_MUL(T[3], us[3])),
+                             A2DS_MUL(T[6], us[5]));
+  const double u3 = A2DS_ADD(A2DS_ADD(A2DS_MUL(T[1], us[0]), A2DS_MUL(T[4], us[2])),
+                             A2DS_MUL(T[7], us[4]));
+  return A2DS_MUL(0.5, A2DS_ADD(A2DS_ADD(A2DS_ADD(ct3, u3), -ct1), -u1));
+}
+
+// ---- phase 1: node m (lane & 3) ---------------------------------------------
+// Node normal, node frame T_m, S_m = Xd^-1 T_m, director, and the drill strain of
+// the state (TACSShellUtilities.h:301-342, 651-693).  This phase is written with
+// non-contracted products/sums in the reference's operation order so that T_m and
+// S_m — and with them the rounding of drill_strain_state — are reproduced to the
+// bit (see the note there).  It is ~200 flops per node; everything downstream is
+// free to use FMAs.
+A2DS_HD double sdot(const double x[3], const double y[3]) {
+  return A2DS_ADD(A2DS_ADD(A2DS_MUL(x[0], y[0]), A2DS_MUL(x[1], y[1])), A2DS_MUL(x[2], y[2]));
+}
+A2DS_HD void scross(const double x[3], const double y[3], double o[3]) {
+  o[0] = A2DS_ADD(A2DS_MUL(x[1], y[2]), -A2DS_MUL(x[2], y[1]));
+  o[1] = A2DS_ADD(A2DS_MUL(x[2], y[0]), -A2DS_MUL(x[0], y[2]));
+  o[2] = A2DS_ADD(A2DS_MUL(x[0], y[1]), -A2DS_MUL(x[1], y[0]));
+}
+A2DS_HD double sdet2(double a, double b, double c, double d) {  // a*b - c*d
+  return A2DS_ADD(A2DS_MUL(a, b), -A2DS_MUL(c, d));
+}
+
+A2DS_HD void phase_node(const CompData &c, ElemScratch &s, int m) {
+  double a0[3], a1[3], b0[3], b1[3];
+  edge_vectors(s.X, 3, a0, a1, b0, b1);
+  const double *Xxi = (m / 2) ? a1 : a0;   // X,xi at the node (eta = +-1)
+  const double *Xeta = (m % 2) ? b1 : b0;  // X,eta at the node (xi = +-1)
+  double fn[3];
+  scross(Xxi, Xeta, fn);
+  double nrm = sqrt(sdot(fn, fn));
+  if (nrm != 0.0) {
+    double inv = 1.0 / nrm;
+    fn[0] = A2DS_MUL(fn[0], inv); fn[1] = A2DS_MUL(fn[1], inv); fn[2] = A2DS_MUL(fn[2], inv);
+  }
+  // transform (TACSShellElementTransform.h:25-92 / :116-213), strict order
+  double t1[3], t2[3], n[3];
+  {
+    double inv = 1.0 / sqrt(sdot(fn, fn));
+    n[0] = A2DS_MUL(fn[0], inv); n[1] = A2DS_MUL(fn[1], inv); n[2] = A2DS_MUL(fn[2], inv);
+    if (c.transform == 0) {
+      t1[0] = Xxi[0]; t1[1] = Xxi[1]; t1[2] = Xxi[2];
+      double d = sdot(n, t1);
+      t1[0] = A2DS_ADD(t1[0], -A2DS_MUL(d, n[0]));
+      t1[0] = A2DS_ADD(t1[0], -A2DS_MUL(d, n[0]));
+      t1[0] = A2DS_ADD(t1[0], -A2DS_MUL(d, n[0]));
+    } else {
+      double an = sdot(c.axis, n);
+      t1[0] = A2DS_ADD(c.axis[0], -A2DS_MUL(an, n[0]));
+      t1[1] = A2DS_ADD(c.axis[1], -A2DS_MUL(an, n[1]));
+      t1[2] = A2DS_ADD(c.axis[2], -A2DS_MUL(an, n[2]));
+    }
+    inv = 1.0 / sqrt(sdot(t1, t1));
+    t1[0] = A2DS_MUL(t1[0], inv); t1[1] = A2DS_MUL(t1[1], inv); t1[2] = A2DS_MUL(t1[2], inv);
+    scross(n, t1, t2);
+  }
+  // Xd = [Xxi | Xeta | fn] (columns), row major; inverse as inv3x3
+  // (TACSElementAlgebra.h:1980)
+  const double A[9] = {Xxi[0], Xeta[0], fn[0], Xxi[1], Xeta[1], fn[1], Xxi[2], Xeta[2], fn[2]};
+  double Xi[9];
+  {
+    double det = A2DS_ADD(A2DS_ADD(A2DS_MUL(A[8], sdet2(A[0], A[4], A[3], A[1])),
+                                   -A2DS_MUL(A[7], sdet2(A[0], A[5], A[3], A[2]))),
+                          A2DS_MUL(A[6], sdet2(A[1], A[5], A[2], A[4])));
+    double di = 1.0 / det;
+    Xi[0] = A2DS_MUL(sdet2(A[4], A[8], A[5], A[7]), di);
+    Xi[1] = A2DS_MUL(-sdet2(A[1], A[8], A[2], A[7]), di);
+    Xi[2] = A2DS_MUL(sdet2(A[1], A[5], A[2], A[4]), di);
+    Xi[3] = A2DS_MUL(-sdet2(A[3], A[8], A[5], A[6]), di);
+    Xi[4] = A2DS_MUL(sdet2(A[0], A[8], A[2], A[6]), di);
+    Xi[5] = A2DS_MUL(-sdet2(A[0], A[5], A[2], A[3]), di);
+    Xi[6] = A2DS_MUL(sdet2(A[3], A[7], A[4], A[6]), di);
+    Xi[7] = A2DS_MUL(-sdet2(A[0], A[7], A[1], A[6]), di);
+    Xi[8] = A2DS_MUL(sdet2(A[0], A[4], A[1], A[3]), di);
+  }
+  // S = Xd^-1 T (mat3x3MatMult), T row major with columns t1, t2, n
+  const double T[9] = {t1[0], t2[0], n[0], t1[1], t2[1], n[1], t1[2], t2[2], n[2]};
+  double S[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      S[3 * i + j] = A2DS_ADD(A2DS_ADD(A2DS_MUL(Xi[3 * i], T[j]), A2DS_MUL(Xi[3 * i + 1], T[3 + j])),
+                              A2DS_MUL(Xi[3 * i + 2], T[6 + j]));
+  s.Sn[4 * m] = S[0]; s.Sn[4 * m + 1] = S[1]; s.Sn[4 * m + 2] = S[3]; s.Sn[4 * m + 3] = S[4];
+  {
+    double ua0[3], ua1[3], ub0[3], ub1[3];
+    edge_vectors(s.q, 6, ua0, ua1, ub0, ub1);
+    s.etn[m] = drill_strain_state(T, S, (m / 2) ? ua1 : ua0, (m % 2) ? ub1 : ub0, &s.q[6 * m + 3]);
+  }
+  double w[3], d[3];
+  cross(t1, t2, w);
+  scross(&s.q[6 * m + 3], fn, d);
+  for (int k = 0; k < 3; k++) {
+    s.fn[3 * m + k] = fn[k];
+    s.t0n[3 * m + k] = t1[k];
+    s.t1n[3 * m + k] = t2[k];
+    s.wn[3 * m + k] = w[k];
+    s.dr[3 * m + k] = d[k];
+  }
+}
+
+// Gauss point geometry kept in registers by the lanes of a Gauss point
+struct QpGeom {
+  double na[2], nb[2];      // 1D shape functions at the point
+  double t0[3], t1[3], tn[3];
+  double S[9], Sz[9];       // Xd^-1 T and -Xd^-1 Xdz Xd^-1 T
+  double M[25];             // (e0,e1,e2,e6,e7) = M (g11,g12,g13,g22,g23)
+  double w;                 // det(Xd) * quadrature weight
+  double P0[6], P1[6];      // T u0x[:,j], T u1x[:,j] (j = 0,1) for the state
+};
+
+// 2-point Gauss rule, 15-digit abscissa as the reference (TACSGaussQuadrature.h:26)
+#define A2DS_GAUSS_PT 0.577350269189626
+
+// ---- phase 2a: Gauss point geometry (lane >> 3) ------------------------------
+// TACSShellElement.h:520-534 and TacsShellComputeDispGrad (TACSShellUtilities.h:361-421)
+A2DS_HD void qp_geometry(const CompData &c, const ElemScratch &s, int qp, bool need_state,
+                         QpGeom &g) {
+  const double xi = (qp & 1) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
+  const double eta = (qp & 2) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
+  g.na[0] = 0.5 * (1.0 - xi); g.na[1] = 0.5 * (1.0 + xi);
+  g.nb[0] = 0.5 * (1.0 - eta); g.nb[1] = 0.5 * (1.0 + eta);
+  double a0[3], a1[3], b0[3], b1[3];
+  edge_vectors(s.X, 3, a0, a1, b0, b1);
+  double Xxi[3], Xeta[3], n0[3], nxi[3], neta[3];
+  double f0[3], f1[3], h0[3], h1[3];
+  edge_vectors(s.fn, 3, f0, f1, h0, h1);
+  const double N[4] = {g.na[0] * g.nb[0], g.na[1] * g.nb[0], g.na[0] * g.nb[1],
+                       g.na[1] * g.nb[1]};
+  for (int k = 0; k < 3; k++) {
+    Xxi[k] = g.nb[0] * a0[k] + g.nb[1] * a1[k];
+    Xeta[k] = g.na[0] * b0[k] + g.na[1] * b1[k];
+    nxi[k] = g.nb[0] * f0[k] + g.nb[1] * f1[k];
+    neta[k] = g.na[0] * h0[k] + g.na[1] * h1[k];
+    n0[k] = N[0] * s.fn[k] + N[1] * s.fn[3 + k] + N[2] * s.fn[6 + k] + N[3] * s.fn[9 + k];
+  }
+  shell_transform(c, Xxi, n0, g.t0, g.t1, g.tn);
+  double Xd[9] = {Xxi[0], Xeta[0], n0[0], Xxi[1], Xeta[1], n0[1], Xxi[2], Xeta[2], n0[2]};
+  double Xi[9];
+  g.w = inv3(Xd, Xi);
+  // S = Xd^-1 T
+  for (int i = 0; i < 3; i++) {
+    g.S[3 * i] = Xi[3 * i] * g.t0[0] + Xi[3 * i + 1] * g.t0[1] + Xi[3 * i + 2] * g.t0[2];
+    g.S[3 * i + 1] = Xi[3 * i] * g.t1[0] + Xi[3 * i + 1] * g.t1[1] + Xi[3 * i + 2] * g.t1[2];
+    g.S[3 * i + 2] = Xi[3 * i] * g.tn[0] + Xi[3 * i + 1] * g.tn[1] + Xi[3 * i + 2] * g.tn[2];
+  }
+  // Sz = -(Xd^-1 Xdz) S with Xdz = [n,xi | n,eta | 0]
+  double Z[9];
+  for (int i = 0; i < 3; i++) {
+    Z[3 * i] = Xi[3 * i] * nxi[0] + Xi[3 * i + 1] * nxi[1] + Xi[3 * i + 2] * nxi[2];
+    Z[3 * i + 1] = Xi[3 * i] * neta[0] + Xi[3 * i + 1] * neta[1] + Xi[3 * i + 2] * neta[2];
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      g.Sz[3 * i + j] = -(Z[3 * i] * g.S[j] + Z[3 * i + 1] * g.S[3 + j]);
+  // M: e0ty = S^T gty S (mat3x3SymmTransformTranspose, TACSElementAlgebra.h:1094),
+  // e = (e0ty[00], e0ty[11], 2 e0ty[01], 2 e0ty[12], 2 e0ty[02]); columns ordered
+  // (g11, g12, g13, g22, g23) with gty symmetric, g33 = 0.
+  const int ra[5] = {0, 1, 0, 1, 0}, rb[5] = {0, 1, 1, 2, 2};
+  const double fac[5] = {1.0, 1.0, 2.0, 2.0, 2.0};
+  for (int r = 0; r < 5; r++) {
+    const int a = ra[r], b = rb[r];
+    const double f = fac[r];
+    const double *S = g.S;
+    g.M[5 * r + 0] = f * (S[a] * S[b]);
+    g.M[5 * r + 1] = f * (S[a] * S[3 + b] + S[3 + a] * S[b]);
+    g.M[5 * r + 2] = f * (S[a] * S[6 + b] + S[6 + a] * S[b]);
+    g.M[5 * r + 3] = f * (S[3 + a] * S[3 + b]);
+    g.M[5 * r + 4] = f * (S[3 + a] * S[6 + b] + S[6 + a] * S[3 + b]);
+  }
+  if (need_state) {
+    // u0d = [u,xi | u,eta | d0], u1d = [d,xi | d,eta | 0] at the point
+    double ua0[3], ua1[3], ub0[3], ub1[3], da0[3], da1[3], db0[3], db1[3];
+    edge_vectors(s.q, 6, ua0, ua1, ub0, ub1);
+    edge_vectors(s.dr, 3, da0, da1, db0, db1);
+    double Y0[6], Y1[6];  // (u0d S)[:,0..1], (u1d S + u0d Sz)[:,0..1], row major 3x2
+    for (int k = 0; k < 3; k++) {
+      double uxi = g.nb[0] * ua0[k] + g.nb[1] * ua1[k];
+      double ueta = g.na[0] * ub0[k] + g.na[1] * ub1[k];
+      double dxi = g.nb[0] * da0[k] + g.nb[1] * da1[k];
+      double deta = g.na[0] * db0[k] + g.na[1] * db1[k];
+      double d0 = N[0] * s.dr[k] + N[1] * s.dr[3 + k] + N[2] * s.dr[6 + k] + N[3] * s.dr[9 + k];
+      for (int j = 0; j < 2; j++) {
+        Y0[2 * k + j] = uxi * g.S[j] + ueta * g.S[3 + j] + d0 * g.S[6 + j];
+        Y1[2 * k + j] = dxi * g.S[j] + deta * g.S[3 + j] + uxi * g.Sz[j] + ueta * g.Sz[3 + j] +
+                        d0 * g.Sz[6 + j];
+      }
+    }
+    // P = T (T^T Y): T is not orthonormal in general, keep both factors
+    for (int j = 0; j < 2; j++) {
+      double y0[3] = {Y0[j], Y0[2 + j], Y0[4 + j]}, y1[3] = {Y1[j], Y1[2 + j], Y1[4 + j]};
+      double c00 = dot(g.t0, y0), c01 = dot(g.t1, y0), c02 = dot(g.tn, y0);
+      double c10 = dot(g.t0, y1), c11 = dot(g.t1, y1), c12 = dot(g.tn, y1);
+      for (int k = 0; k < 3; k++) {
+        g.P0[3 * j + k] = g.t0[k] * c00 + g.t1[k] * c01 + g.tn[k] * c02;
+        g.P1[3 * j + k] = g.t0[k] * c10 + g.t1[k] * c11 + g.tn[k] * c12;
+      }
+    }
+  }
+}
+
+// publish the per Gauss point data the geometric-stiffness phase needs
+A2DS_HD void qp_publish(ElemScratch &s, int qp, const QpGeom &g) {
+  const double *t0 = g.t0, *t1 = g.t1, *tn = g.tn;
+  s.Pq[qp][0] = t0[0] * t0[0] + t1[0] * t1[0] + tn[0] * tn[0];
+  s.Pq[qp][1] = t0[0] * t0[1] + t1[0] * t1[1] + tn[0] * tn[1];
+  s.Pq[qp][2] = t0[0] * t0[2] + t1[0] * t1[2] + tn[0] * tn[2];
+  s.Pq[qp][3] = t0[1] * t0[1] + t1[1] * t1[1] + tn[1] * tn[1];
+  s.Pq[qp][4] = t0[1] * t0[2] + t1[1] * t1[2] + tn[1] * tn[2];
+  s.Pq[qp][5] = t0[2] * t0[2] + t1[2] * t1[2] + tn[2] * tn[2];
+}
+
+// Coefficients of node m at a Gauss point: derivative of the local displacement
+// gradients w.r.t. the node's displacement / director:
+//   d u0x[i][j] / d u_mk = T[k][i] a[j]     d u1x[i][j] / d u_mk = T[k][i] az[j]
+//   d u0x[i][j] / d d_mk = T[k][i] b[j]     d u1x[i][j] / d d_mk = T[k][i] cc[j]
+struct NodeCoef { double a[2], az[2], b[2], cc[2]; };
+
+A2DS_HD void node_coef(const QpGeom &g, int m, NodeCoef &n) {
+  const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
+  const double Nxi = dN * g.nb[m / 2], Neta = g.na[m % 2] * dM, N = g.na[m % 2] * g.nb[m / 2];
+  for (int j = 0; j < 2; j++) {
+    n.a[j] = Nxi * g.S[j] + Neta * g.S[3 + j];
+    n.az[j] = Nxi * g.Sz[j] + Neta * g.Sz[3 + j];
+    n.b[j] = N * g.S[6 + j];
+    n.cc[j] = n.a[j] + N * g.Sz[6 + j];
+  }
+}
+
+// Three columns (node m, h = 0: displacements, h = 1: rotations) of the 9-row
+// strain matrix at one Gauss point.  `lin` selects B0 (geometry vectors) or, with
+// the state vectors passed instead, B1(q).
+//   va[2], vb[2]   : field,xi at eta = -+1 / field,eta at xi = -+1  (X or u)
+//   vn23[2], vn13[2]: normal-like field at the g23 / g13 tying points (fn or d)
+//   p0, p1         : for the bending rows: B0 uses (0, T columns); B1 uses
+//                    (T u1x[:,j], T u0x[:,j])
+A2DS_HD void strain_columns(const ElemScratch &s, const QpGeom &g, const NodeCoef &nc, int m,
+                            int h, const double va[2][3], const double vb[2][3],
+                            const double vn23[2][3], const double vn13[2][3],
+                            const double *pa0, const double *pa1, const double *pz0,
+                            const double *pz1, bool drill, double B[9][3]) {
+  const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
+  const double *fn = &s.fn[3 * m];
+  double G5[5][3];  // columns of (g11, g12, g13, g22, g23) interpolated to the point
+  if (h == 0) {
+    const double c11 = g.nb[m / 2] * dN;          // g11 tying point on this node's eta edge
+    const double c22 = g.na[m % 2] * dM;          // g22 tying point on this node's xi edge
+    const double c12x = 0.5 * (0.5 * dN), c12e = 0.5 * (0.5 * dM);  // centre point
+    const double c23 = g.na[m % 2] * (0.5 * dM);  // g23: 1/2 N,eta n0
+    const double c13 = g.nb[m / 2] * (0.5 * dN);  // g13: 1/2 N,xi n0
+    for (int k = 0; k < 3; k++) {
+      G5[0][k] = c11 * va[m / 2][k];
+      G5[3][k] = c22 * vb[m % 2][k];
+      G5[1][k] = c12x * (0.5 * (vb[0][k] + vb[1][k])) + c12e * (0.5 * (va[0][k] + va[1][k]));
+      G5[4][k] = c23 * vn23[m % 2][k];
+      G5[2][k] = c13 * vn13[m / 2][k];
+    }
+  } else {
+    // 1/2 N_m(tying point) (fn_m x field,eta|xi); N_m = 1/2 at the edge mid points
+    double x23[3], x13[3];
+    cross(fn, vb[m % 2], x23);
+    cross(fn, va[m / 2], x13);
+    const double c23 = g.na[m % 2] * 0.25, c13 = g.nb[m / 2] * 0.25;
+    for (int k = 0; k < 3; k++) {
+      G5[0][k] = 0.0; G5[1][k] = 0.0; G5[3][k] = 0.0;
+      G5[4][k] = c23 * x23[k];
+      G5[2][k] = c13 * x13[k];
+    }
+  }
+  const int row[5] = {0, 1, 2, 6, 7};
+  for (int r = 0; r < 5; r++)
+    for (int k = 0; k < 3; k++)
+      B[row[r]][k] = g.M[5 * r] * G5[0][k] + g.M[5 * r + 1] * G5[1][k] +
+                     g.M[5 * r + 2] * G5[2][k] + g.M[5 * r + 3] * G5[3][k] +
+                     g.M[5 * r + 4] * G5[4][k];
+  // bending rows: e3 = u1x[0][0], e4 = u1x[1][1], e5 = u1x[0][1] + u1x[1][0]
+  // (+ u0x/u1x products for the nonlinear part)
+  const double *ca = (h == 0) ? nc.a : nc.b;    // multiplies the "u0x" partner
+  const double *cz = (h == 0) ? nc.az : nc.cc;  // multiplies the "u1x" partner
+  double A0[3], A1[3], Z0[3], Z1[3];
+  if (h == 0) {
+    for (int k = 0; k < 3; k++) {
+      A0[k] = pa0 ? pa0[k] : 0.0; A1[k] = pa1 ? pa1[k] : 0.0;
+      Z0[k] = pz0[k]; Z1[k] = pz1[k];
+    }
+  } else {
+    double zero[3] = {0.0, 0.0, 0.0};
+    cross(fn, pa0 ? pa0 : zero, A0);
+    cross(fn, pa1 ? pa1 : zero, A1);
+    cross(fn, pz0, Z0);
+    cross(fn, pz1, Z1);
+  }
+  for (int k = 0; k < 3; k++) {
+    B[3][k] = ca[0] * A0[k] + cz[0] * Z0[k];
+    B[4][k] = ca[1] * A1[k] + cz[1] * Z1[k];
+    B[5][k] = ca[0] * A1[k] + cz[1] * Z0[k] + ca[1] * A0[k] + cz[0] * Z1[k];
+  }
+  // drilling strain row: et = sum_n N_n etn_n,
+  // etn_n = 1/2 (u0x[1][0] - u0x[0][1]) - theta_n . (t0n x t1n)   (TACSDirector.h:560-564)
+  if (!drill) {
+    B[8][0] = B[8][1] = B[8][2] = 0.0;
+  } else if (h == 0) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int n = 0; n < 4; n++) {
+      // shape function derivatives of node m evaluated at node n
+      const double Nxi = (m / 2 == n / 2) ? dN : 0.0;
+      const double Neta = (m % 2 == n % 2) ? dM : 0.0;
+      const double a0 = Nxi * s.Sn[4 * n] + Neta * s.Sn[4 * n + 2];
+      const double a1 = Nxi * s.Sn[4 * n + 1] + Neta * s.Sn[4 * n + 3];
+      const double Nq = g.na[n % 2] * g.nb[n / 2];
+      for (int k = 0; k < 3; k++)
+        acc[k] += Nq * (0.5 * (a0 * s.t1n[3 * n + k] - a1 * s.t0n[3 * n + k]));
+    }
+    B[8][0] = acc[0]; B[8][1] = acc[1]; B[8][2] = acc[2];
+  } else {
+    const double Nq = g.na[m % 2] * g.nb[m / 2];
+    for (int k = 0; k < 3; k++) B[8][k] = -Nq * s.wn[3 * m + k];
+  }
+}
+
+// vectors feeding strain_columns for B0 (geometry) and B1 (state)
+struct ColVecs { double va[2][3], vb[2][3], vn23[2][3], vn13[2][3]; };
+
+A2DS_HD void col_vectors(const double *field, int ld, const double *normal, ColVecs &v) {
+  edge_vectors(field, ld, v.va[0], v.va[1], v.vb[0], v.vb[1]);
+  for (int k = 0; k < 3; k++) {
+    v.vn23[0][k] = 0.5 * (normal[k] + normal[6 + k]);      // xi = -1 edge: nodes 0,2
+    v.vn23[1][k] = 0.5 * (normal[3 + k] + normal[9 + k]);  // xi = +1 edge: nodes 1,3
+    v.vn13[0][k] = 0.5 * (normal[k] + normal[3 + k]);      // eta = -1 edge: nodes 0,1
+    v.vn13[1][k] = 0.5 * (normal[6 + k] + normal[9 + k]);  // eta = +1 edge: nodes 2,3
+  }
+}
+
+// s = C e (TACSShellConstitutive::computeStress, TACSShellConstitutive.h:125-147)
+A2DS_HD void apply_C(const double Cs[22], const double e[9], double s[9]) {
+  const double *A = &Cs[0], *B = &Cs[6], *D = &Cs[12], *As = &Cs[18];
+  s[0] = A[0] * e[0] + A[1] * e[1] + A[2] * e[2] + B[0] * e[3] + B[1] * e[4] + B[2] * e[5];
+  s[1] = A[1] * e[0] + A[3] * e[1] + A[4] * e[2] + B[1] * e[3] + B[3] * e[4] + B[4] * e[5];
+  s[2] = A[2] * e[0] + A[4] * e[1] + A[5] * e[2] + B[2] * e[3] + B[4] * e[4] + B[5] * e[5];
+  s[3] = B[0] * e[0] + B[1] * e[1] + B[2] * e[2] + D[0] * e[3] + D[1] * e[4] + D[2] * e[5];
+  s[4] = B[1] * e[0] + B[3] * e[1] + B[4] * e[2] + D[1] * e[3] + D[3] * e[4] + D[4] * e[5];
+  s[5] = B[2] * e[0] + B[4] * e[1] + B[5] * e[2] + D[2] * e[3] + D[4] * e[4] + D[5] * e[5];
+  s[6] = As[0] * e[6] + As[1] * e[7];
+  s[7] = As[1] * e[6] + As[2] * e[7];
+  s[8] = Cs[21] * e[8];
+}
+
+// What the launch is asked to produce
+struct Want {
+  bool res, kmat, gmat;  // residual, tangent, geometric stiffness
+  bool nonlinear;        // element uses the nonlinear strain model (tangent/residual)
+};
+
+// ---- phase 2: lane = (qp, m, h): strain matrix columns + strain partial sums ---
+// Fills BA (= B0, or B0 + B1 for the nonlinear model) and B1 columns in scratch and
+// the lane's contribution to the Gauss point strains.
+A2DS_HD void phase_columns(const CompData &c, ElemScratch &s, int lane, const Want &w,
+                           QpGeom &g) {
+  const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
+  const bool need_b1 = w.gmat || w.nonlinear;
+  qp_geometry(c, s, qp, need_b1, g);
+  if (m == 0 && h == 0) qp_publish(s, qp, g);
+  NodeCoef nc;
+  node_coef(g, m, nc);
+  // coefficient pairs for the geometric stiffness phase (generalised nodes u_m, d_m)
+  if (h == 0) {
+    s.ca[qp][m][0] = nc.a[0]; s.ca[qp][m][1] = nc.a[1];
+    s.cb[qp][m][0] = nc.az[0]; s.cb[qp][m][1] = nc.az[1];
+  } else {
+    s.ca[qp][4 + m][0] = nc.b[0]; s.ca[qp][4 + m][1] = nc.b[1];
+    s.cb[qp][4 + m][0] = nc.cc[0]; s.cb[qp][4 + m][1] = nc.cc[1];
+  }
+  ColVecs v;
+  double B0[9][3], Bq[9][3];
+  col_vectors(s.X, 3, s.fn, v);
+  strain_columns(s, g, nc, m, h, v.va, v.vb, v.vn23, v.vn13, (const double *)0,
+                 (const double *)0, g.t0, g.t1, true, B0);
+  if (need_b1) {
+    col_vectors(s.q, 6, s.dr, v);
+    strain_columns(s, g, nc, m, h, v.va, v.vb, v.vn23, v.vn13, &g.P1[0], &g.P1[3], &g.P0[0],
+                   &g.P0[3], false, Bq);
+  }
+  const double *qc = &s.q[6 * m + 3 * h];
+  const int col = 6 * m + 3 * h;
+  for (int r = 0; r < 9; r++) {
+    double e = B0[r][0] * qc[0] + B0[r][1] * qc[1] + B0[r][2] * qc[2];
+    if (need_b1) {
+      // nonlinear strain: e = B0 q + 1/2 B1 q.  For the geometric stiffness of a
+      // linear-model element only the linear strain enters the stress.
+      if (w.nonlinear) e += 0.5 * (Bq[r][0] * qc[0] + Bq[r][1] * qc[1] + Bq[r][2] * qc[2]);
+      for (int k = 0; k < 3; k++) s.B1[(col + k) * LDS_ROWS + 9 * qp + r] = Bq[r][k];
+    }
+    s.epart[lane][r] = e;
+    for (int k = 0; k < 3; k++) {
+      double b = B0[r][k];
+      if (w.nonlinear) b += Bq[r][k];
+      s.BA[(col + k) * LDS_ROWS + 9 * qp + r] = b;
+    }
+  }
+}
+
+// ---- phase 3: lane = (qp, m, h): stresses, W = w C B columns, residual partials ---
+A2DS_HD void phase_stress(const CompData &c, ElemScratch &s, int lane, const Want &w,
+                          const QpGeom &g) {
+  const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
+  double e[9], st[9];
+  for (int r = 0; r < 9; r++) {
+    double acc = 0.0;
+    for (int l = 0; l < 8; l++) acc += s.epart[8 * qp + l][r];
+    e[r] = acc - c.temperature * c.eth[r];
+  }
+  {
+    // drilling strain of the state: interpolate the nodal values evaluated in the
+    // reference's order (interpFields<1,1>, TACSShellElement.h:350)
+    double et = 0.0;
+    for (int n = 0; n < 4; n++) et = A2DS_ADD(et, A2DS_MUL(A2DS_MUL(g.na[n % 2], g.nb[n / 2]), s.etn[n]));
+    e[8] = et - c.temperature * c.eth[8];
+  }
+  apply_C(c.Cs, e, st);
+  const int col = 6 * m + 3 * h;
+  for (int k = 0; k < 3; k++) {
+    double b[9], cb[9];
+    for (int r = 0; r < 9; r++) b[r] = s.BA[(col + k) * LDS_ROWS + 9 * qp + r];
+    apply_C(c.Cs, b, cb);
+    double rr = 0.0;
+    for (int r = 0; r < 9; r++) {
+      s.W[(col + k) * LDS_ROWS + 9 * qp + r] = g.w * cb[r];
+      rr += b[r] * st[r];
+    }
+    s.rpart[qp][col + k] = g.w * rr;
+  }
+  if (m == 0 && h == 0) {
+    // stresses feeding the geometric terms
+    s.sg[qp][0] = g.w * st[3]; s.sg[qp][1] = g.w * st[4]; s.sg[qp][2] = g.w * st[5];
+    // pull the membrane/shear stresses back to the tying points:
+    // dU/dg5 = M^T (w s_ms), then the tying interpolation transposed
+    const double sm[5] = {g.w * st[0], g.w * st[1], g.w * st[2], g.w * st[6], g.w * st[7]};
+    double dg[5];
+    for (int cidx = 0; cidx < 5; cidx++)
+      dg[cidx] = g.M[cidx] * sm[0] + g.M[5 + cidx] * sm[1] + g.M[10 + cidx] * sm[2] +
+                 g.M[15 + cidx] * sm[3] + g.M[20 + cidx] * sm[4];
+    // tying point order (QuadBasis.h:530-564): g11 @eta=-+1, g22 @xi=-+1, g12 centre,
+    // g23 @xi=-+1, g13 @eta=-+1; dg order (g11, g12, g13, g22, g23)
+    s.sig[qp][0] = g.nb[0] * dg[0]; s.sig[qp][1] = g.nb[1] * dg[0];
+    s.sig[qp][2] = g.na[0] * dg[3]; s.sig[qp][3] = g.na[1] * dg[3];
+    s.sig[qp][4] = dg[1];
+    s.sig[qp][5] = g.na[0] * dg[4]; s.sig[qp][6] = g.na[1] * dg[4];
+    s.sig[qp][7] = g.nb[0] * dg[2]; s.sig[qp][8] = g.nb[1] * dg[2];
+  }
+}
+
+// ---- geometric stiffness: one 3x3 block for the generalised node pair (p, pp) ---
+// p, pp in 0..7: 0..3 displacement of node p, 4..7 director of node p-4.
+// Returns the block already folded onto the rotation DOFs:
+//   rows of a director node:    skew(fn_m) * blk      (d = theta x fn)
+//   columns of a director node: blk * skew(fn_m)^T
+// (TACSLinearizedRotation::addDirectorJacobian, TACSDirector.h:369-486)
+A2DS_HD void geo_block(const ElemScratch &s, int p, int pp, double out[9]) {
+  // tying point stresses (sum over Gauss points)
+  double sig[9];
+  for (int t = 0; t < 9; t++) sig[t] = s.sig[0][t] + s.sig[1][t] + s.sig[2][t] + s.sig[3][t];
+  const int m = p & 3, mm = pp & 3;
+  const bool pd = p >= 4, ppd = pp >= 4;
+  const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
+  const double dNN = (mm % 2) ? 0.5 : -0.5, dMM = (mm / 2) ? 0.5 : -0.5;
+  double sc = 0.0;  // scalar multiplying the identity (tying part)
+  if (!pd && !ppd) {
+    // g11: N,xi N,xi at eta = -+1 ; g22: N,eta N,eta at xi = -+1 ; g12 at the centre
+    if (m / 2 == mm / 2) sc += sig[m / 2] * dN * dNN;
+    if (m % 2 == mm % 2) sc += sig[2 + m % 2] * dM * dMM;
+    sc += sig[4] * 0.5 * ((0.5 * dN) * (0.5 * dMM) + (0.5 * dM) * (0.5 * dNN));
+  } else if (pd != ppd) {
+    // g23 = 1/2 d0 . u,eta (xi = -+1), g13 = 1/2 d0 . u,xi (eta = -+1)
+    const int md = pd ? m : mm, mu = pd ? mm : m;
+    const double dNu = (mu % 2) ? 0.5 : -0.5, dMu = (mu / 2) ? 0.5 : -0.5;
+    if (md % 2 == mu % 2) sc += sig[5 + md % 2] * 0.5 * 0.5 * dMu;
+    if (md / 2 == mu / 2) sc += sig[7 + md / 2] * 0.5 * 0.5 * dNu;
+  }
+  double blk[9] = {sc, 0.0, 0.0, 0.0, sc, 0.0, 0.0, 0.0, sc};
+  // bending part: sum_qp (alpha_p^T Sigma beta_pp + beta_p^T Sigma alpha_pp) T T^T
+  for (int qp = 0; qp < 4; qp++) {
+    const double *ap = s.ca[qp][p], *bp = s.cb[qp][p], *app = s.ca[qp][pp], *bpp = s.cb[qp][pp];
+    const double s3 = s.sg[qp][0], s4 = s.sg[qp][1], s5 = s.sg[qp][2];
+    const double mq = ap[0] * (s3 * bpp[0] + s5 * bpp[1]) + ap[1] * (s5 * bpp[0] + s4 * bpp[1]) +
+                      bp[0] * (s3 * app[0] + s5 * app[1]) + bp[1] * (s5 * app[0] + s4 * app[1]);
+    const double *P = s.Pq[qp];
+    blk[0] += mq * P[0]; blk[1] += mq * P[1]; blk[2] += mq * P[2];
+    blk[3] += mq * P[1]; blk[4] += mq * P[3]; blk[5] += mq * P[4];
+    blk[6] += mq * P[2]; blk[7] += mq * P[4]; blk[8] += mq * P[5];
+  }
+  if (pd) {  // rows: skew(fn_m) * blk
+    const double *f = &s.fn[3 * m];
+    double t[9];
+    for (int j = 0; j < 3; j++) {
+      t[j] = f[1] * blk[6 + j] - f[2] * blk[3 + j];
+      t[3 + j] = f[2] * blk[j] - f[0] * blk[6 + j];
+      t[6 + j] = f[0] * blk[3 + j] - f[1] * blk[j];
+    }
+    for (int i = 0; i < 9; i++) blk[i] = t[i];
+  }
+  if (ppd) {  // columns: blk * skew(fn_mm)^T, i.e. row_i -> fn x row_i
+    const double *f = &s.fn[3 * mm];
+    double t[9];
+    for (int i = 0; i < 3; i++) {
+      const double *r = &blk[3 * i];
+      t[3 * i] = f[1] * r[2] - f[2] * r[1];
+      t[3 * i + 1] = f[2] * r[0] - f[0] * r[2];
+      t[3 * i + 2] = f[0] * r[1] - f[1] * r[0];
+    }
+    for (int i = 0; i < 9; i++) blk[i] = t[i];
+  }
+  for (int i = 0; i < 9; i++) out[i] = blk[i];
+}
+
+}  // namespace a2ds
+#endif

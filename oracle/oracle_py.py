@@ -1,0 +1,110 @@
+"""ctypes binding for oracle/liboracle_shell.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may import this.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Comp(C.Structure):
+    _fields_ = [("model", C.c_int), ("transform", C.c_int), ("axis", C.c_double * 3),
+                ("Cs", C.c_double * 22), ("eth", C.c_double * 9), ("mom", C.c_double * 3),
+                ("temperature", C.c_double)]
+
+
+def make_comp(model, Cs, eth, mom=(0, 0, 0), temperature=0.0, transform=0, axis=(1.0, 0.0, 0.0)):
+    c = Comp()
+    c.model = int(model); c.transform = int(transform)
+    ax = np.asarray(axis, dtype=np.float64)
+    if transform == 1:
+        ax = ax / np.sqrt(ax @ ax)
+    for i in range(3):
+        c.axis[i] = ax[i]; c.mom[i] = mom[i]
+    for i in range(22):
+        c.Cs[i] = Cs[i]
+    for i in range(9):
+        c.eth[i] = eth[i]
+    c.temperature = float(temperature)
+    return c
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle_shell.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", _HERE, "oracle"])
+        _LIB = C.CDLL(path)
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def strain(comp, X, q):
+    e = np.zeros(36); det = np.zeros(4)
+    lib().oracle_strain(C.byref(comp), _p(np.ascontiguousarray(X, dtype=np.float64)),
+                        _p(np.ascontiguousarray(q, dtype=np.float64)), _p(e), _p(det))
+    return e.reshape(4, 9), det
+
+
+def residual(comp, X, q):
+    r = np.zeros(24)
+    lib().oracle_residual(C.byref(comp), _p(np.ascontiguousarray(X, dtype=np.float64)),
+                          _p(np.ascontiguousarray(q, dtype=np.float64)), _p(r))
+    return r
+
+
+def jacobian(comp, X, q, alpha=1.0):
+    r = np.zeros(24); m = np.zeros(576)
+    lib().oracle_jacobian(C.byref(comp), C.c_double(alpha),
+                          _p(np.ascontiguousarray(X, dtype=np.float64)),
+                          _p(np.ascontiguousarray(q, dtype=np.float64)), _p(r), _p(m))
+    return r, m.reshape(24, 24)
+
+
+def mat_type(comp, type_, X, q):
+    m = np.zeros(576)
+    lib().oracle_mat_type(C.byref(comp), C.c_int(type_),
+                          _p(np.ascontiguousarray(X, dtype=np.float64)),
+                          _p(np.ascontiguousarray(q, dtype=np.float64)), _p(m))
+    return m.reshape(24, 24)
+
+
+def pattern(n_nodes, conn):
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
+    rowp = np.zeros(n_nodes + 1, dtype=np.int32)
+    nnz = lib().oracle_pattern(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), None)
+    cols = np.zeros(nnz, dtype=np.int32)
+    lib().oracle_pattern(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), _p(cols))
+    return rowp, cols
+
+
+def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_vars=None,
+             bc_vals=None, alpha=1.0):
+    """op 0 res, 1 jacobian, 2 K, 3 G -> (res[n,6] or None, A[nnz,6,6] or None)."""
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 6)
+    n = X.shape[0]
+    arr = (Comp * len(comps))(*comps)
+    ec = np.ascontiguousarray(elem_comp, dtype=np.int32)
+    nb = 0 if bc_nodes is None else len(bc_nodes)
+    bn = np.ascontiguousarray(bc_nodes if nb else np.zeros(0), dtype=np.int32)
+    bv = np.ascontiguousarray(bc_vars if nb else np.zeros(0), dtype=np.int32)
+    bx = np.ascontiguousarray(bc_vals if nb else np.zeros(0), dtype=np.float64)
+    res = np.zeros((n, 6)) if op <= 1 else None
+    A = np.zeros((len(cols), 6, 6)) if op >= 1 else None
+    miss = lib().oracle_assemble(C.c_int(op), C.c_double(alpha), C.c_int(n), C.c_int(conn.shape[0]),
+                                 _p(conn), _p(ec), arr, _p(X), _p(u), C.c_int(nb), _p(bn), _p(bv),
+                                 _p(bx), _p(np.ascontiguousarray(rowp, dtype=np.int32)),
+                                 _p(np.ascontiguousarray(cols, dtype=np.int32)), _p(res), _p(A))
+    assert miss == 0, "element block missing from the pattern"
+    return res, A

@@ -1,0 +1,72 @@
+/*
+ * shell_oracle.h — CPU restatement of the reference's MITC4 shell assembly path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (a2d-shells_b200/, include/,
+ * bench.py's GPU arm) may link, import or call this.  Allowed callers: tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs,
+ * and there only as the checker.
+ *
+ * Parity status: PINNED against the reference itself — the unmodified reference
+ * is compiled into oracle/_ref (oracle/Makefile) and tests/test_oracle.py checks
+ * every function here against it on seeded inputs, plus against the fixtures in
+ * tests/golden/ that were generated from it (tests/golden/make_golden.py).
+ * The reference ships no golden vectors or known-answer tests of its own
+ * (SURVEY.md §4).
+ */
+#ifndef A2DS_SHELL_ORACLE_H
+#define A2DS_SHELL_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int model;          /* 0 = TACSShellLinearModel, 1 = TACSShellNonlinearModel */
+  int transform;      /* 0 = TACSShellNaturalTransform, 1 = TACSShellRefAxisTransform */
+  double axis[3];     /* normalised reference axis (transform == 1) */
+  double Cs[22];      /* A[6] B[6] D[6] As[3] drill  (TACSShellConstitutive.h:34) */
+  double eth[9];      /* thermal strain per unit temperature */
+  double mom[3];      /* mass moments (unused by the static path) */
+  double temperature; /* TACSShellElement::temperature (TACSShellElement.h:35) */
+} oracle_comp_t;
+
+/* strains e[4][9] and detXd*weight at the 4 Gauss points for state q[24] */
+void oracle_strain(const oracle_comp_t *c, const double X[12], const double q[24],
+                   double e[36], double detXd[4]);
+
+/* TACSShellElement::addResidual (static terms): res[24] (overwritten) */
+void oracle_residual(const oracle_comp_t *c, const double X[12], const double q[24],
+                     double res[24]);
+
+/* TACSShellElement::addJacobian with beta = gamma = 0: res[24], mat[576] = alpha*dR/dq
+   (both overwritten; either may be NULL) */
+void oracle_jacobian(const oracle_comp_t *c, double alpha, const double X[12],
+                     const double q[24], double res[24], double mat[576]);
+
+/* TACSShellElement::getMatType: type 0 = stiffness, 1 = geometric stiffness */
+void oracle_mat_type(const oracle_comp_t *c, int type, const double X[12],
+                     const double q[24], double mat[576]);
+
+/* Non-zero pattern of the node-to-node matrix, columns sorted per row
+   (TACSAssembler::computeLocalNodeToNodeCSR).  Two-pass: call with cols == NULL
+   to fill rowp[n_nodes+1] and get the block count, then again with cols. */
+int oracle_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int *cols);
+
+/*
+ * Assembly over a mesh (TACSAssembler::assembleRes / assembleJacobian /
+ * assembleMatType, single rank): op 0 = residual, 1 = Jacobian (res + alpha*K),
+ * 2 = matType(K), 3 = matType(G).  res[6*n_nodes] and A[36*nnz] are zeroed first
+ * (may be NULL when the op does not produce them); boundary conditions are
+ * applied exactly as the reference does (TACSBVec::applyBCs, BCSRMat::zeroRow).
+ * Returns 0, or the number of element blocks not found in the pattern.
+ */
+int oracle_assemble(int op, double alpha, int n_nodes, int n_elems, const int *conn,
+                    const int *elem_comp, const oracle_comp_t *comps, const double *X,
+                    const double *u, int n_bc, const int *bc_nodes, const int *bc_vars,
+                    const double *bc_vals, const int *rowp, const int *cols, double *res,
+                    double *A);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

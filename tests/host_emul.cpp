@@ -1,0 +1,56 @@
+// host_emul.cpp — steps the kernel's per-lane phase functions (mitc4_math.h) lane by
+// lane on the CPU so the arithmetic can be checked without a GPU.  Test-only: the
+// product never builds or loads this; the DMMA contraction and the scatter of the
+// real kernel are replaced by plain loops over the same operand arrays.
+#include <string.h>
+
+#include "../a2d-shells_b200/csrc/mitc4_math.h"
+
+using namespace a2ds;
+
+extern "C" int emul_element(const double *Cs, const double *eth, double temperature, int model,
+                            int transform, const double *axis, const double *X, const double *q,
+                            int want_gmat, double *res, double *K, double *G) {
+  CompData c;
+  memcpy(c.Cs, Cs, sizeof(c.Cs));
+  memcpy(c.eth, eth, sizeof(c.eth));
+  c.temperature = temperature;
+  c.model = model;
+  c.transform = transform;
+  memcpy(c.axis, axis, sizeof(c.axis));
+  static ElemScratch s;
+  memset(&s, 0, sizeof(s));
+  memcpy(s.X, X, sizeof(s.X));
+  memcpy(s.q, q, sizeof(s.q));
+  Want w;
+  w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1;
+  for (int lane = 0; lane < 32; lane++) phase_node(c, s, lane & 3);
+  static QpGeom g[32];
+  for (int lane = 0; lane < 32; lane++) phase_columns(c, s, lane, w, g[lane]);
+  for (int lane = 0; lane < 32; lane++) phase_stress(c, s, lane, w, g[lane]);
+  for (int a = 0; a < 24; a++)
+    res[a] = s.rpart[0][a] + s.rpart[1][a] + s.rpart[2][a] + s.rpart[3][a];
+  double geo[576];
+  memset(geo, 0, sizeof(geo));
+  for (int p = 0; p < 8; p++)
+    for (int pp = 0; pp < 8; pp++) {
+      double blk[9];
+      geo_block(s, p, pp, blk);
+      int r0 = 6 * (p & 3) + (p >= 4 ? 3 : 0), c0 = 6 * (pp & 3) + (pp >= 4 ? 3 : 0);
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) geo[24 * (r0 + i) + c0 + j] += blk[3 * i + j];
+    }
+  for (int r = 0; r < 24; r++)
+    for (int cc = 0; cc < 24; cc++) {
+      double k = 0.0, gm = 0.0;
+      for (int t = 0; t < 36; t++) {
+        k += s.BA[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t];
+        gm += s.B1[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t] +
+              s.W[r * LDS_ROWS + t] * s.B1[cc * LDS_ROWS + t];
+      }
+      if (w.nonlinear) k += geo[24 * r + cc];
+      K[24 * r + cc] = k;
+      if (G) G[24 * r + cc] = gm + geo[24 * r + cc];
+    }
+  return 0;
+}
