@@ -1,0 +1,297 @@
+"""ctypes face of include/a2ds.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+STIFFNESS_MATRIX = 0
+GEOMETRIC_STIFFNESS_MATRIX = 1
+QUAD4_SHELL = 0
+QUAD4_NONLINEAR_SHELL = 1
+TRANSFORM_NATURAL = 0
+TRANSFORM_REF_AXIS = 1
+SCATTER_ATOMIC = 0
+SCATTER_COLORED = 1
+
+# every symbol include/a2ds.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "a2ds_last_error", "a2ds_version", "a2ds_create", "a2ds_destroy", "a2ds_synchronize",
+    "a2ds_set_mesh", "a2ds_set_nodes", "a2ds_set_components", "a2ds_set_state",
+    "a2ds_set_state_dev", "a2ds_set_bcs", "a2ds_set_scatter_mode", "a2ds_mat_create",
+    "a2ds_mat_create_natural", "a2ds_mat_pattern", "a2ds_mat_nnz", "a2ds_mat_zero",
+    "a2ds_mat_download", "a2ds_mat_values_dev", "a2ds_assemble_res", "a2ds_assemble_jacobian",
+    "a2ds_assemble_mat_type", "a2ds_assemble_all", "a2ds_res_dev", "a2ds_state_dev",
+    "a2ds_comm_unique_id", "a2ds_comm_init", "a2ds_set_halo", "a2ds_halo_forward",
+    "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
+]
+
+_LIB = None
+
+
+class A2dsError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(HERE, "lib", "liba2ds_b200.so")
+
+
+def load_library():
+    """Load the CUDA library.  Fails loudly if it has not been built — there is no
+    fallback implementation."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise A2dsError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(path)
+        L.a2ds_last_error.restype = C.c_char_p
+        L.a2ds_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def host_pattern(n_nodes, conn):
+    """natural-order BCSR pattern (rowp, cols) — host only, no device needed"""
+    L = load_library()
+    conn = _i32(conn).reshape(-1, 4)
+    rowp = np.zeros(n_nodes + 1, dtype=np.int32)
+    nnz = C.c_longlong()
+    if L.a2ds_host_pattern(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), None,
+                           C.byref(nnz)):
+        raise A2dsError(L.a2ds_last_error().decode())
+    cols = np.zeros(nnz.value, dtype=np.int32)
+    L.a2ds_host_pattern(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), _p(cols),
+                        C.byref(nnz))
+    return rowp, cols
+
+
+def host_color_elements(n_nodes, conn):
+    L = load_library()
+    conn = _i32(conn).reshape(-1, 4)
+    color = np.zeros(conn.shape[0], dtype=np.int32)
+    nc = C.c_int()
+    if L.a2ds_host_color_elements(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(color),
+                                  C.byref(nc)):
+        raise A2dsError(L.a2ds_last_error().decode())
+    return color, nc.value
+
+
+class Assembler:
+    """One device context = one rank's sub-mesh on one GPU.  Method names follow
+    TACSAssembler (src/TACSAssembler.h:213-220)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        self._chk(self.L.a2ds_create(C.c_int(device), C.byref(self.ctx)))
+        self.n_nodes = self.n_owned = self.n_elems = 0
+        self._keep = []
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise A2dsError(self.L.a2ds_last_error().decode())
+
+    def close(self):
+        if self.ctx:
+            self.L.a2ds_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- mesh -------------------------------------------------------------------
+    def set_mesh(self, conn, n_nodes, n_owned=None, elem_comp=None):
+        conn = _i32(conn).reshape(-1, 4)
+        self.n_elems = conn.shape[0]
+        self.n_nodes = int(n_nodes)
+        self.n_owned = self.n_nodes if n_owned is None else int(n_owned)
+        ec = None if elem_comp is None else _i32(elem_comp)
+        self._chk(self.L.a2ds_set_mesh(self.ctx, C.c_int(self.n_nodes), C.c_int(self.n_owned),
+                                       C.c_int(self.n_elems), _p(conn), _p(ec)))
+
+    def set_nodes(self, X):
+        X = _f64(X).reshape(-1, 3)
+        assert X.shape[0] == self.n_nodes
+        self._chk(self.L.a2ds_set_nodes(self.ctx, _p(X)))
+
+    def set_components(self, Cs, eth, temperature=None, elem_class=None,
+                       transform=TRANSFORM_NATURAL, ref_axis=None):
+        Cs = _f64(Cs).reshape(-1, 22)
+        eth = _f64(eth).reshape(-1, 9)
+        n = Cs.shape[0]
+        T = _f64(np.zeros(n) if temperature is None else np.broadcast_to(temperature, (n,)))
+        cl = _i32(np.zeros(n) if elem_class is None else np.broadcast_to(elem_class, (n,)))
+        ax = None if ref_axis is None else _f64(ref_axis)
+        self._chk(self.L.a2ds_set_components(self.ctx, C.c_int(n), _p(Cs), _p(eth), _p(T), _p(cl),
+                                             C.c_int(transform), _p(ax)))
+
+    def set_state(self, u):
+        u = _f64(u).reshape(-1, 6)
+        self._chk(self.L.a2ds_set_state(self.ctx, C.c_int(u.shape[0]), _p(u)))
+        self._keep = [u]  # the copy is asynchronous
+
+    def set_state_ptr(self, n_given, host_ptr):
+        """state from a raw (pinned) host pointer; asynchronous"""
+        self._chk(self.L.a2ds_set_state(self.ctx, C.c_int(n_given), C.c_void_p(host_ptr)))
+
+    def set_state_dev(self, n_given, dev_ptr):
+        self._chk(self.L.a2ds_set_state_dev(self.ctx, C.c_int(n_given), C.c_void_p(dev_ptr)))
+
+    def set_bcs(self, nodes, vars_mask, vals=None):
+        nodes = _i32(nodes)
+        vm = _i32(np.broadcast_to(vars_mask, nodes.shape))
+        vals = _f64(np.zeros((len(nodes), 6)) if vals is None else vals).reshape(-1, 6)
+        self._chk(self.L.a2ds_set_bcs(self.ctx, C.c_int(len(nodes)), _p(nodes), _p(vm), _p(vals)))
+
+    def set_scatter_mode(self, mode):
+        self._chk(self.L.a2ds_set_scatter_mode(self.ctx, C.c_int(mode)))
+
+    # -- matrices -----------------------------------------------------------------
+    def create_mat(self):
+        """natural-order BCSR over the local nodes (TACSAssembler::createMat pattern)"""
+        m = C.c_int()
+        self._chk(self.L.a2ds_mat_create_natural(self.ctx, C.byref(m)))
+        return m.value
+
+    def create_mat_from_pattern(self, blocks):
+        """blocks: list of dicts with nrows,rowp,cols and optional row_map,col_map,ident —
+        the pattern of a host matrix (e.g. the B/E/F/C blocks of a TACSSchurMat)"""
+        nb = len(blocks)
+        keep = []
+        IntP = C.POINTER(C.c_int)
+
+        def arr(key, b):
+            a = b.get(key)
+            if a is None:
+                return IntP()
+            a = _i32(a)
+            keep.append(a)
+            return a.ctypes.data_as(IntP)
+
+        nrows = _i32([b["nrows"] for b in blocks])
+        rowp = (IntP * nb)(*[arr("rowp", b) for b in blocks])
+        cols = (IntP * nb)(*[arr("cols", b) for b in blocks])
+        rmap = (IntP * nb)(*[arr("row_map", b) for b in blocks])
+        cmap = (IntP * nb)(*[arr("col_map", b) for b in blocks])
+        ident = _i32([b.get("ident", 1 if i == 0 else 0) for i, b in enumerate(blocks)])
+        m = C.c_int()
+        self._chk(self.L.a2ds_mat_create(self.ctx, C.c_int(nb), _p(nrows), rowp, cols, rmap, cmap,
+                                         _p(ident), C.byref(m)))
+        return m.value
+
+    def mat_pattern(self, mat, block=0):
+        nr = C.c_int(); nnz = C.c_longlong()
+        self._chk(self.L.a2ds_mat_pattern(self.ctx, C.c_int(mat), C.c_int(block), C.byref(nr),
+                                          None, None))
+        self._chk(self.L.a2ds_mat_nnz(self.ctx, C.c_int(mat), C.c_int(block), C.byref(nnz)))
+        rowp = np.zeros(nr.value + 1, dtype=np.int32); cols = np.zeros(nnz.value, dtype=np.int32)
+        self._chk(self.L.a2ds_mat_pattern(self.ctx, C.c_int(mat), C.c_int(block), C.byref(nr),
+                                          _p(rowp), _p(cols)))
+        return rowp, cols
+
+    def mat_nnz(self, mat, block=0):
+        nnz = C.c_longlong()
+        self._chk(self.L.a2ds_mat_nnz(self.ctx, C.c_int(mat), C.c_int(block), C.byref(nnz)))
+        return nnz.value
+
+    def mat_zero(self, mat):
+        self._chk(self.L.a2ds_mat_zero(self.ctx, C.c_int(mat)))
+
+    def mat_values(self, mat, block=0, out=None):
+        n = self.mat_nnz(mat, block)
+        A = np.empty((n, 6, 6)) if out is None else out
+        self._chk(self.L.a2ds_mat_download(self.ctx, C.c_int(mat), C.c_int(block), _p(A)))
+        return A
+
+    def mat_values_dev(self, mat, block=0):
+        p = C.c_void_p()
+        self._chk(self.L.a2ds_mat_values_dev(self.ctx, C.c_int(mat), C.c_int(block), C.byref(p)))
+        return p.value
+
+    # -- assembly (TACSAssembler names) ------------------------------------------------
+    def _res_out(self, want):
+        return np.empty((self.n_owned, 6)) if want else None
+
+    def assembleRes(self, download=True):
+        r = self._res_out(download)
+        self._chk(self.L.a2ds_assemble_res(self.ctx, _p(r)))
+        return r
+
+    def assembleJacobian(self, alpha, beta, gamma, mat, download=True):
+        r = self._res_out(download)
+        self._chk(self.L.a2ds_assemble_jacobian(self.ctx, C.c_double(alpha), C.c_double(beta),
+                                                C.c_double(gamma), _p(r), C.c_int(mat)))
+        return r
+
+    def assembleMatType(self, mat_type, mat):
+        self._chk(self.L.a2ds_assemble_mat_type(self.ctx, C.c_int(mat_type), C.c_int(mat)))
+
+    def assembleAll(self, kmat, gmat, download=True, out_ptr=None):
+        """residual + K + G in one pass; out_ptr: raw (pinned) host pointer for the residual"""
+        if out_ptr is not None:
+            self._chk(self.L.a2ds_assemble_all(self.ctx, C.c_void_p(out_ptr), C.c_int(kmat),
+                                               C.c_int(gmat)))
+            return None
+        r = self._res_out(download)
+        self._chk(self.L.a2ds_assemble_all(self.ctx, _p(r), C.c_int(kmat), C.c_int(gmat)))
+        return r
+
+    def res_dev(self):
+        p = C.c_void_p()
+        self._chk(self.L.a2ds_res_dev(self.ctx, C.byref(p)))
+        return p.value
+
+    def state_dev(self):
+        p = C.c_void_p()
+        self._chk(self.L.a2ds_state_dev(self.ctx, C.byref(p)))
+        return p.value
+
+    def synchronize(self):
+        self._chk(self.L.a2ds_synchronize(self.ctx))
+
+    def last_timing(self):
+        ms = C.c_float(); n = C.c_int()
+        self._chk(self.L.a2ds_last_timing(self.ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- multi-GPU ---------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._chk(self.L.a2ds_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, n_ranks, rank, uid):
+        self._chk(self.L.a2ds_comm_init(self.ctx, C.c_int(n_ranks), C.c_int(rank),
+                                        C.c_char_p(uid)))
+
+    def set_halo(self, peers, send_lists, recv_lists):
+        peers = _i32(peers)
+        sp = _i32(np.concatenate([[0], np.cumsum([len(x) for x in send_lists])]))
+        rp = _i32(np.concatenate([[0], np.cumsum([len(x) for x in recv_lists])]))
+        sn = _i32(np.concatenate(send_lists)) if len(send_lists) else _i32([])
+        rn = _i32(np.concatenate(recv_lists)) if len(recv_lists) else _i32([])
+        self._chk(self.L.a2ds_set_halo(self.ctx, C.c_int(len(peers)), _p(peers), _p(sp), _p(sn),
+                                       _p(rp), _p(rn)))
+
+    def halo_forward(self):
+        self._chk(self.L.a2ds_halo_forward(self.ctx))

@@ -1,0 +1,976 @@
+// a2ds.cu — CUDA kernels (sm_100a) and the C ABI of liba2ds_b200.so.
+//
+// Hot kernel: k_assemble<RES, KMAT, GMAT, NL>.  One warp owns one MITC4 element:
+//   1. gather the 4 nodes' coordinates and state (coalesced by node, 24/48 B rows)
+//   2. node phase, column phase, stress phase: mitc4_math.h, FP64 FMA pipe
+//   3. the 24x24 contractions  K = B^T (w C B),  G = B1^T W + W^T B1  as FP64
+//      tensor-core MMAs (mma.sync m8n8k4 f64 -> DMMA.8x8x4), operands staged in
+//      shared memory [dof][36] (conflict-free fragment loads), accumulators in
+//      registers, only the upper block triangle is computed
+//   4. stage the element matrices in shared memory, add the geometric-stiffness
+//      3x3 blocks, then scatter with coalesced RED.E.ADD.F64 through a
+//      precomputed element -> BCSR block offset table (16 offsets per element)
+// Roofline notes live in DESIGN.md.
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/a2ds.h"
+#include "mitc4_math.h"
+
+using namespace a2ds;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string &m) {
+  g_err = m;
+  return 1;
+}
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+  } while (0)
+#define NC(call)                                                                       \
+  do {                                                                                 \
+    ncclResult_t r_ = (call);                                                          \
+    if (r_ != ncclSuccess) return fail(std::string(#call) + ": " + ncclGetErrorString(r_)); \
+  } while (0)
+
+extern "C" const char *a2ds_last_error(void) { return g_err.c_str(); }
+extern "C" const char *a2ds_version(void) { return "a2ds-b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------
+struct KParams {
+  const int *elem_list;  // elements to process (NULL: 0..n_list-1)
+  int n_list;
+  const int *conn;       // 4 local nodes per element
+  const int *elem_comp;
+  const CompData *comps;
+  const double *X;       // 3 per node
+  const double *u;       // 6 per node
+  double *res;           // 6 per node
+  double *Kval;          // concatenated block values of the tangent matrix
+  const int *Koff;       // 16 block offsets per element (-1: not stored here)
+  double *Gval;
+  const int *Goff;
+  double alpha;
+  int scratch_bytes;
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+static const int WARPS_PER_BLOCK = 4;
+static const int KE_LD = 24;  // leading dimension of the staged element matrices
+
+template <bool RES, bool KMAT, bool GMAT, bool NL>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+    k_assemble(const KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ElemScratch &s = *reinterpret_cast<ElemScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  const unsigned FULL = 0xffffffffu;
+  Want w;
+  w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL;
+
+  for (int it = blockIdx.x * WARPS_PER_BLOCK + warp; it < p.n_list;
+       it += gridDim.x * WARPS_PER_BLOCK) {
+    const int e = p.elem_list ? __ldg(&p.elem_list[it]) : it;
+    const CompData &c = p.comps[__ldg(&p.elem_comp[e])];
+
+    // ---- gather -----------------------------------------------------------
+    const int nd = __ldg(&p.conn[4 * e + (lane & 3)]);  // lane l holds node l & 3
+    {
+      const int nx = __shfl_sync(FULL, nd, lane / 3);
+      const int nq = __shfl_sync(FULL, nd, lane / 6);
+      if (lane < 12) s.X[lane] = __ldg(&p.X[3 * (size_t)nx + lane % 3]);
+      if (lane < 24) s.q[lane] = __ldg(&p.u[6 * (size_t)nq + lane % 6]);
+    }
+    int koff = -1, goff = -1;
+    if (KMAT && lane < 16) koff = __ldg(&p.Koff[16 * (size_t)e + lane]);
+    if (GMAT && lane < 16) goff = __ldg(&p.Goff[16 * (size_t)e + lane]);
+    __syncwarp();
+
+    // ---- node phase ---------------------------------------------------------
+    phase_node(c, s, lane & 3);
+    __syncwarp();
+
+    // ---- column phase (+ strain reduction over the 8 lanes of a Gauss point) ---
+    {
+      double ep[9], qw, na[2], nb[2];
+      lane_columns(c, s, lane, w, ep, qw, na, nb);
+      if (RES || GMAT || NL) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          ep[r] += __shfl_xor_sync(FULL, ep[r], 1);
+          ep[r] += __shfl_xor_sync(FULL, ep[r], 2);
+          ep[r] += __shfl_xor_sync(FULL, ep[r], 4);
+        }
+        double r3[3];
+        lane_stress(c, s, lane, w, ep, qw, na, nb, r3);
+        if (RES) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 8);
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 16);
+          }
+          const int nm = __shfl_sync(FULL, nd, (lane >> 1) & 3);
+          if (lane < 8) {
+            double *r = &p.res[6 * (size_t)nm + 3 * (lane & 1)];
+            atomicAdd(r, r3[0]);
+            atomicAdd(r + 1, r3[1]);
+            atomicAdd(r + 2, r3[2]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    if (KMAT || GMAT) {
+      // ---- contraction on the FP64 tensor path ---------------------------------
+      // fragment address: row (lane >> 2) of the 8-wide tile, k index (lane & 3)
+      double kacc[6][2], gacc[6][2];
+#pragma unroll
+      for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = gacc[t][0] = gacc[t][1] = 0.0;
+      const int fr = (lane >> 2) * LDS_ROWS + (lane & 3);
+#pragma unroll
+      for (int ks = 0; ks < 9; ks++) {
+        double a[3], wv[3], b1[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          wv[t] = s.W[8 * t * LDS_ROWS + fr + 4 * ks];
+          if (KMAT) a[t] = s.BA[8 * t * LDS_ROWS + fr + 4 * ks];
+          if (GMAT) b1[t] = s.B1[8 * t * LDS_ROWS + fr + 4 * ks];
+        }
+        int idx = 0;
+#pragma unroll
+        for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+          for (int tj = ti; tj < 3; tj++, idx++) {
+            if (KMAT) dmma884(kacc[idx], a[ti], wv[tj]);
+            if (GMAT) {
+              dmma884(gacc[idx], b1[ti], wv[tj]);
+              dmma884(gacc[idx], wv[ti], b1[tj]);
+            }
+          }
+      }
+      __syncwarp();
+
+      // ---- stage the element matrices (upper tiles + mirrored lower tiles) ------
+      double *Ke = s.BA, *Ge = s.B1;
+      {
+        const int r = lane >> 2, cpair = 2 * (lane & 3);
+        int idx = 0;
+#pragma unroll
+        for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+          for (int tj = ti; tj < 3; tj++, idx++) {
+            const int row = 8 * ti + r, col = 8 * tj + cpair;
+            if (KMAT) {
+              Ke[row * KE_LD + col] = kacc[idx][0];
+              Ke[row * KE_LD + col + 1] = kacc[idx][1];
+              if (ti != tj) {
+                Ke[col * KE_LD + row] = kacc[idx][0];
+                Ke[(col + 1) * KE_LD + row] = kacc[idx][1];
+              }
+            }
+            if (GMAT) {
+              Ge[row * KE_LD + col] = gacc[idx][0];
+              Ge[row * KE_LD + col + 1] = gacc[idx][1];
+              if (ti != tj) {
+                Ge[col * KE_LD + row] = gacc[idx][0];
+                Ge[(col + 1) * KE_LD + row] = gacc[idx][1];
+              }
+            }
+          }
+      }
+      __syncwarp();
+
+      // ---- geometric stiffness blocks: 64 generalised node pairs, 2 per lane -----
+      if (GMAT || (NL && KMAT)) {
+        double *dst = GMAT ? Ge : Ke;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+          const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+          double blk[9];
+          geo_block(s, pr, pc, blk);
+          const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) dst[(r0 + i) * KE_LD + c0 + j] += blk[3 * i + j];
+        }
+        __syncwarp();
+      }
+
+      // ---- scatter: 576 entries = 16 blocks x 36, consecutive lanes -> consecutive
+      //      doubles of a block (coalesced RED.E.ADD.F64) --------------------------
+#pragma unroll 1
+      for (int ch = 0; ch < 18; ch++) {
+        const int idx = ch * 32 + lane;
+        const int blk = idx / 36, wi = idx - 36 * blk;
+        const int r = wi / 6, cc = wi - 6 * r;
+        const int src = (6 * (blk >> 2) + r) * KE_LD + 6 * (blk & 3) + cc;
+        if (KMAT) {
+          const int off = __shfl_sync(FULL, koff, blk);
+          if (off >= 0) atomicAdd(&p.Kval[36 * (size_t)off + wi], p.alpha * Ke[src]);
+        }
+        if (GMAT) {
+          const int off = __shfl_sync(FULL, goff, blk);
+          if (off >= 0) atomicAdd(&p.Gval[36 * (size_t)off + wi], Ge[src]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// One BCSR block of a matrix as the kernels see it
+struct BlockDev {
+  const int *rowp, *cols, *row_map, *col_map;
+  long long base;  // first 6x6 block of this BCSR block in the concatenated array
+  int nrows, ident;
+};
+
+// element -> block offset table; replaces TACSSchurMat::addValues' findIndex +
+// BCSRMat::addRowValues' bsearch (TACSSchurMat.cpp:453-531, BCSRMat.cpp:1778-1827)
+__global__ void k_build_offsets(int n_elems, const int *conn, int n_blocks, const BlockDev *blk,
+                                int *off, int *missing) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= 16 * (size_t)n_elems) return;
+  const int e = (int)(t >> 4), slot = (int)(t & 15);
+  const int rn = conn[4 * e + (slot >> 2)], cn = conn[4 * e + (slot & 3)];
+  int found = -1;
+  for (int b = 0; b < n_blocks && found < 0; b++) {
+    const int rr = blk[b].row_map ? blk[b].row_map[rn] : (rn < blk[b].nrows ? rn : -1);
+    const int cc = blk[b].col_map ? blk[b].col_map[cn] : cn;
+    if (rr < 0 || cc < 0) continue;
+    int lo = blk[b].rowp[rr], hi = blk[b].rowp[rr + 1] - 1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1, v = blk[b].cols[mid];
+      if (v == cc) { found = (int)(blk[b].base + mid); break; }
+      if (v < cc) lo = mid + 1; else hi = mid - 1;
+    }
+  }
+  off[t] = found;
+  if (found < 0) atomicAdd(missing, 1);
+}
+
+// residual BC rows: r = u - ubar on owned nodes (TACSBVec::applyBCs, TACSBVec.cpp:546-585)
+__global__ void k_res_bcs(int n_bc, const int *nodes, const int *vars, const double *vals,
+                          const double *u, double *res, int n_owned) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n_bc) return;
+  const int b = t / 6, k = t - 6 * b, n = nodes[b];
+  if (n < n_owned && (vars[b] & (1 << k))) res[6 * (size_t)n + k] = u[6 * (size_t)n + k] - vals[t];
+}
+
+// matrix BC rows: zero the constrained DOF rows of every block in the block row, 1.0 on
+// the diagonal entry of the diagonal block (BCSRMat::zeroRow, BCSRMat.cpp:2005-2030;
+// columns untouched, as the reference)
+__global__ void k_mat_bcs(int n_bc, const int *nodes, const int *vars, int n_blocks,
+                          const BlockDev *blk, double *A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_bc * n_blocks) return;
+  const int b = t / n_blocks, ib = t - b * n_blocks;
+  const BlockDev B = blk[ib];
+  const int n = nodes[b], mask = vars[b];
+  const int row = B.row_map ? B.row_map[n] : (n < B.nrows ? n : -1);
+  if (row < 0) return;
+  const int diag_col = B.col_map ? B.col_map[n] : n;
+  for (int j = B.rowp[row]; j < B.rowp[row + 1]; j++) {
+    double *a = &A[36 * (size_t)(B.base + j)];
+    for (int ii = 0; ii < 6; ii++)
+      if (mask & (1 << ii))
+        for (int jj = 0; jj < 6; jj++) a[6 * ii + jj] = 0.0;
+    if (B.ident && B.cols[j] == diag_col)
+      for (int ii = 0; ii < 6; ii++)
+        if (mask & (1 << ii)) a[7 * ii] = 1.0;
+  }
+}
+
+// halo pack / unpack (VecDistGetVars6 and the TACS_ADD_VALUES scatter of
+// TACSBVecDistribute.cpp:543-747)
+__global__ void k_pack6(int n, const int *nodes, const double *v, double *buf) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 6 * n) buf[t] = v[6 * (size_t)nodes[t / 6] + t % 6];
+}
+__global__ void k_unpack6(int n, const int *nodes, const double *buf, double *v, int add) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n) return;
+  double *d = &v[6 * (size_t)nodes[t / 6] + t % 6];
+  if (add) *d += buf[t]; else *d = buf[t];
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct MatrixRec {
+  int n_blocks = 0;
+  std::vector<long long> nnz, base;
+  std::vector<int> nrows;
+  long long total = 0;
+  double *A = nullptr;
+  int *off = nullptr;          // 16 per element
+  BlockDev *blk_dev = nullptr;
+  std::vector<void *> owned;   // device allocations to free
+  std::vector<std::vector<int>> h_rowp, h_cols;  // host copy of the patterns
+};
+
+struct a2ds_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int n_sm = 0;
+  int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
+  int *conn = nullptr, *elem_comp = nullptr;
+  std::vector<int> h_conn, h_elem_comp, h_class;
+  double *X = nullptr, *u = nullptr, *res = nullptr;
+  CompData *comps = nullptr;
+  int *bc_nodes = nullptr, *bc_vars = nullptr;
+  double *bc_vals = nullptr;
+  std::vector<MatrixRec> mats;
+  int scatter_mode = A2DS_SCATTER_ATOMIC;
+  // element lists: [class][colour]; colour list 0 of the atomic mode holds everything
+  bool lists_ready = false;
+  int n_colors = 0;
+  std::vector<int *> list_dev[2];
+  std::vector<int> list_len[2];
+  // halo
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  std::vector<int> peers, send_ptr, recv_ptr;
+  int *send_nodes = nullptr, *recv_nodes = nullptr;
+  double *send_buf = nullptr, *recv_buf = nullptr;
+  bool has_halo = false;
+  // instrumentation
+  float last_ms = 0.f;
+  int last_launches = 0;
+};
+
+template <class T>
+static int upload(T **dst, const T *src, size_t n, cudaStream_t st) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  if (n == 0) return 0;
+  CU(cudaMalloc((void **)dst, n * sizeof(T)));
+  CU(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int a2ds_create(int device, a2ds_ctx **out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail("a2ds_create: no CUDA device available (there is no CPU path)");
+  if (device < 0 || device >= n) return fail("a2ds_create: bad device index");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail("a2ds_create: kernels are built for sm_100a only, device is sm_" +
+                std::to_string(prop.major) + std::to_string(prop.minor));
+  a2ds_ctx *c = new a2ds_ctx();
+  c->device = device;
+  c->n_sm = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  *out = c;
+  return 0;
+}
+
+static void free_lists(a2ds_ctx *c) {
+  for (int k = 0; k < 2; k++) {
+    for (int *p : c->list_dev[k])
+      if (p) cudaFree(p);
+    c->list_dev[k].clear();
+    c->list_len[k].clear();
+  }
+  c->lists_ready = false;
+}
+
+extern "C" int a2ds_destroy(a2ds_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &m : c->mats)
+    for (void *p : m.owned) cudaFree(p);
+  free_lists(c);
+  cudaFree(c->conn); cudaFree(c->elem_comp); cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
+  cudaFree(c->comps); cudaFree(c->bc_nodes); cudaFree(c->bc_vars); cudaFree(c->bc_vals);
+  cudaFree(c->send_nodes); cudaFree(c->recv_nodes); cudaFree(c->send_buf); cudaFree(c->recv_buf);
+  if (c->comm) ncclCommDestroy(c->comm);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int a2ds_synchronize(a2ds_ctx *c) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems, const int *conn,
+                             const int *elem_comp) {
+  CU(cudaSetDevice(c->device));
+  if (n_owned > n_nodes || n_nodes < 0 || n_elems < 0) return fail("a2ds_set_mesh: bad sizes");
+  for (size_t i = 0; i < 4 * (size_t)n_elems; i++)
+    if (conn[i] < 0 || conn[i] >= n_nodes)
+      return fail("a2ds_set_mesh: connectivity refers to a node outside [0, n_nodes) "
+                  "(dependent nodes are not supported)");
+  c->n_nodes = n_nodes; c->n_owned = n_owned; c->n_elems = n_elems;
+  c->h_conn.assign(conn, conn + 4 * (size_t)n_elems);
+  if (elem_comp) c->h_elem_comp.assign(elem_comp, elem_comp + n_elems);
+  else c->h_elem_comp.assign(n_elems, 0);
+  if (upload(&c->conn, conn, 4 * (size_t)n_elems, c->stream)) return 1;
+  if (upload(&c->elem_comp, c->h_elem_comp.data(), (size_t)n_elems, c->stream)) return 1;
+  cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
+  c->X = c->u = c->res = nullptr;
+  CU(cudaMalloc((void **)&c->X, 3 * (size_t)n_nodes * sizeof(double)));
+  CU(cudaMalloc((void **)&c->u, 6 * (size_t)n_nodes * sizeof(double)));
+  CU(cudaMalloc((void **)&c->res, 6 * (size_t)n_nodes * sizeof(double)));
+  CU(cudaMemsetAsync(c->u, 0, 6 * (size_t)n_nodes * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)n_nodes * sizeof(double), c->stream));
+  free_lists(c);
+  return 0;
+}
+
+extern "C" int a2ds_set_nodes(a2ds_ctx *c, const double *X) {
+  CU(cudaSetDevice(c->device));
+  if (!c->X) return fail("a2ds_set_nodes: call a2ds_set_mesh first");
+  CU(cudaMemcpyAsync(c->X, X, 3 * (size_t)c->n_nodes * sizeof(double), cudaMemcpyHostToDevice,
+                     c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_set_components(a2ds_ctx *c, int n_comp, const double *Cs, const double *eth,
+                                   const double *temperature, const int *elem_class,
+                                   int transform, const double *ref_axis) {
+  CU(cudaSetDevice(c->device));
+  if (n_comp <= 0) return fail("a2ds_set_components: need at least one component");
+  if (transform != A2DS_TRANSFORM_NATURAL && transform != A2DS_TRANSFORM_REF_AXIS)
+    return fail("a2ds_set_components: unknown transform kind");
+  std::vector<CompData> h(n_comp);
+  c->h_class.resize(n_comp);
+  for (int i = 0; i < n_comp; i++) {
+    memcpy(h[i].Cs, &Cs[22 * i], 22 * sizeof(double));
+    memcpy(h[i].eth, &eth[9 * i], 9 * sizeof(double));
+    h[i].temperature = temperature ? temperature[i] : 0.0;
+    h[i].model = elem_class ? elem_class[i] : 0;
+    if (h[i].model != A2DS_QUAD4_SHELL && h[i].model != A2DS_QUAD4_NONLINEAR_SHELL)
+      return fail("a2ds_set_components: unsupported element class (only TACSQuad4Shell and "
+                  "TACSQuad4NonlinearShell are implemented)");
+    c->h_class[i] = h[i].model;
+    h[i].transform = transform;
+    h[i].axis[0] = h[i].axis[1] = h[i].axis[2] = 0.0;
+    if (transform == A2DS_TRANSFORM_REF_AXIS) {
+      if (!ref_axis) return fail("a2ds_set_components: reference axis missing");
+      // normalised as TACSShellRefAxisTransform's constructor does (Transform.h:97-108)
+      double nrm = sqrt(ref_axis[0] * ref_axis[0] + ref_axis[1] * ref_axis[1] +
+                        ref_axis[2] * ref_axis[2]);
+      double inv = nrm != 0.0 ? 1.0 / nrm : 0.0;
+      for (int k = 0; k < 3; k++) h[i].axis[k] = ref_axis[k] * inv;
+    }
+  }
+  c->n_comp = n_comp;
+  if (upload(&c->comps, h.data(), (size_t)n_comp, c->stream)) return 1;
+  free_lists(c);
+  return 0;
+}
+
+extern "C" int a2ds_set_state_dev(a2ds_ctx *c, int n_given, const double *u_dev) {
+  CU(cudaSetDevice(c->device));
+  if (n_given != c->n_nodes && n_given != c->n_owned)
+    return fail("a2ds_set_state: n_given must be n_nodes or n_owned");
+  CU(cudaMemcpyAsync(c->u, u_dev, 6 * (size_t)n_given * sizeof(double), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_set_state(a2ds_ctx *c, int n_given, const double *u) {
+  CU(cudaSetDevice(c->device));
+  if (n_given != c->n_nodes && n_given != c->n_owned)
+    return fail("a2ds_set_state: n_given must be n_nodes or n_owned");
+  CU(cudaMemcpyAsync(c->u, u, 6 * (size_t)n_given * sizeof(double), cudaMemcpyHostToDevice,
+                     c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_set_bcs(a2ds_ctx *c, int n_bc, const int *nodes, const int *vars,
+                            const double *vals) {
+  CU(cudaSetDevice(c->device));
+  c->n_bc = n_bc;
+  if (upload(&c->bc_nodes, nodes, (size_t)n_bc, c->stream)) return 1;
+  if (upload(&c->bc_vars, vars, (size_t)n_bc, c->stream)) return 1;
+  if (upload(&c->bc_vals, vals, 6 * (size_t)n_bc, c->stream)) return 1;
+  return 0;
+}
+
+extern "C" int a2ds_set_scatter_mode(a2ds_ctx *c, int mode) {
+  if (mode != A2DS_SCATTER_ATOMIC && mode != A2DS_SCATTER_COLORED)
+    return fail("a2ds_set_scatter_mode: unknown mode");
+  if (mode != c->scatter_mode) free_lists(c);
+  c->scatter_mode = mode;
+  return 0;
+}
+
+// Greedy element colouring: two elements that share a node get different colours, so
+// within a colour every BCSR block and every residual row receives at most one
+// contribution -> the sum order is fixed by the colour order.
+static void color_elements(int nn, int ne, const int *conn, std::vector<int> &color,
+                           int &n_colors) {
+  std::vector<int> ptr(nn + 1, 0);
+  for (size_t i = 0; i < 4 * (size_t)ne; i++) ptr[conn[i] + 1]++;
+  for (int i = 0; i < nn; i++) ptr[i + 1] += ptr[i];
+  std::vector<int> adj(ptr[nn]), fill(ptr.begin(), ptr.end() - 1);
+  for (int e = 0; e < ne; e++)
+    for (int i = 0; i < 4; i++) adj[fill[conn[4 * e + i]]++] = e;
+  color.assign(ne, -1);
+  n_colors = 0;
+  for (int e = 0; e < ne; e++) {
+    unsigned long long used = 0ull;
+    for (int i = 0; i < 4; i++) {
+      const int n = conn[4 * e + i];
+      for (int k = ptr[n]; k < ptr[n + 1]; k++) {
+        const int o = adj[k];
+        if (color[o] >= 0 && color[o] < 64) used |= 1ull << color[o];
+      }
+    }
+    int col = 0;
+    while (used & (1ull << col)) col++;
+    color[e] = col;
+    n_colors = std::max(n_colors, col + 1);
+  }
+}
+
+static int build_lists(a2ds_ctx *c) {
+  if (c->lists_ready) return 0;
+  if (c->n_comp == 0) return fail("assemble: a2ds_set_components has not been called");
+  for (int e = 0; e < c->n_elems; e++)
+    if (c->h_elem_comp[e] < 0 || c->h_elem_comp[e] >= c->n_comp)
+      return fail("assemble: element component index out of range");
+  std::vector<int> color;
+  int ncol = 1;
+  if (c->scatter_mode == A2DS_SCATTER_COLORED)
+    color_elements(c->n_nodes, c->n_elems, c->h_conn.data(), color, ncol);
+  c->n_colors = ncol;
+  for (int k = 0; k < 2; k++) {
+    std::vector<std::vector<int>> lists(ncol);
+    for (int e = 0; e < c->n_elems; e++)
+      if (c->h_class[c->h_elem_comp[e]] == k)
+        lists[c->scatter_mode == A2DS_SCATTER_COLORED ? color[e] : 0].push_back(e);
+    c->list_dev[k].assign(ncol, nullptr);
+    c->list_len[k].assign(ncol, 0);
+    for (int col = 0; col < ncol; col++) {
+      c->list_len[k][col] = (int)lists[col].size();
+      if (lists[col].empty()) continue;
+      // the identity list needs no indirection
+      if ((int)lists[col].size() == c->n_elems) continue;
+      if (upload(&c->list_dev[k][col], lists[col].data(), lists[col].size(), c->stream)) return 1;
+    }
+  }
+  c->lists_ready = true;
+  return 0;
+}
+
+extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
+                               const int *const *rowp, const int *const *cols,
+                               const int *const *row_map, const int *const *col_map,
+                               const int *bc_ident, int *mat) {
+  CU(cudaSetDevice(c->device));
+  if (n_blocks < 1 || n_blocks > 4) return fail("a2ds_mat_create: 1..4 BCSR blocks");
+  if (!c->conn) return fail("a2ds_mat_create: call a2ds_set_mesh first");
+  MatrixRec m;
+  m.n_blocks = n_blocks;
+  std::vector<BlockDev> hb(n_blocks);
+  long long total = 0;
+  for (int b = 0; b < n_blocks; b++) {
+    const long long nnz = nrows[b] > 0 ? rowp[b][nrows[b]] : 0;
+    m.nnz.push_back(nnz); m.base.push_back(total); m.nrows.push_back(nrows[b]);
+    m.h_rowp.emplace_back(nrows[b] > 0 ? std::vector<int>(rowp[b], rowp[b] + nrows[b] + 1)
+                                       : std::vector<int>(1, 0));
+    m.h_cols.emplace_back(cols[b], cols[b] + nnz);
+    int *d_rowp = nullptr, *d_cols = nullptr, *d_rm = nullptr, *d_cm = nullptr;
+    std::vector<int> zero_rowp(1, 0);
+    if (upload(&d_rowp, nrows[b] > 0 ? rowp[b] : zero_rowp.data(), (size_t)nrows[b] + 1, c->stream)) return 1;
+    if (upload(&d_cols, cols[b], (size_t)nnz, c->stream)) return 1;
+    if (row_map && row_map[b] && upload(&d_rm, row_map[b], (size_t)c->n_nodes, c->stream)) return 1;
+    if (col_map && col_map[b] && upload(&d_cm, col_map[b], (size_t)c->n_nodes, c->stream)) return 1;
+    m.owned.push_back(d_rowp); m.owned.push_back(d_cols);
+    if (d_rm) m.owned.push_back(d_rm);
+    if (d_cm) m.owned.push_back(d_cm);
+    hb[b].rowp = d_rowp; hb[b].cols = d_cols; hb[b].row_map = d_rm; hb[b].col_map = d_cm;
+    hb[b].base = total; hb[b].nrows = nrows[b];
+    hb[b].ident = bc_ident ? bc_ident[b] : (b == 0);
+    total += nnz;
+  }
+  if (total >= (1ll << 31)) return fail("a2ds_mat_create: more than 2^31 blocks on one GPU");
+  m.total = total;
+  CU(cudaMalloc((void **)&m.A, std::max<long long>(total, 1) * 36 * sizeof(double)));
+  m.owned.push_back(m.A);
+  CU(cudaMemsetAsync(m.A, 0, total * 36 * sizeof(double), c->stream));
+  CU(cudaMalloc((void **)&m.blk_dev, n_blocks * sizeof(BlockDev)));
+  m.owned.push_back(m.blk_dev);
+  CU(cudaMemcpyAsync(m.blk_dev, hb.data(), n_blocks * sizeof(BlockDev), cudaMemcpyHostToDevice,
+                     c->stream));
+  CU(cudaMalloc((void **)&m.off, std::max<size_t>(16 * (size_t)c->n_elems, 1) * sizeof(int)));
+  m.owned.push_back(m.off);
+  int *d_missing = nullptr;
+  CU(cudaMalloc((void **)&d_missing, sizeof(int)));
+  CU(cudaMemsetAsync(d_missing, 0, sizeof(int), c->stream));
+  if (c->n_elems > 0) {
+    const size_t nt = 16 * (size_t)c->n_elems;
+    k_build_offsets<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(
+        c->n_elems, c->conn, n_blocks, m.blk_dev, m.off, d_missing);
+    CU(cudaGetLastError());
+  }
+  int missing = 0;
+  CU(cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_missing);
+  if (missing) {
+    for (void *p : m.owned) cudaFree(p);
+    return fail("a2ds_mat_create: " + std::to_string(missing) +
+                " element blocks have no entry in the supplied non-zero pattern");
+  }
+  c->mats.push_back(m);
+  *mat = (int)c->mats.size() - 1;
+  return 0;
+}
+
+static int check_mat(a2ds_ctx *c, int mat, int block = 0) {
+  if (mat < 0 || mat >= (int)c->mats.size()) return fail("bad matrix id");
+  if (block < 0 || block >= c->mats[mat].n_blocks) return fail("bad BCSR block index");
+  return 0;
+}
+
+// node -> nodes of its elements (4 per incidence), then sort + unique per row
+static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &rowp,
+                           std::vector<int> &cols) {
+  std::vector<int> ptr(nn + 1, 0);
+  for (size_t i = 0; i < 4 * (size_t)ne; i++) {
+    if (conn[i] < 0 || conn[i] >= nn) return fail("pattern: node index out of range");
+    ptr[conn[i] + 1] += 4;
+  }
+  for (int i = 0; i < nn; i++) {
+    if ((long long)ptr[i] + ptr[i + 1] > 0x7fffffffll) return fail("pattern too large");
+    ptr[i + 1] += ptr[i];
+  }
+  std::vector<int> tmp(ptr[nn]), fill(ptr.begin(), ptr.end() - 1);
+  for (int e = 0; e < ne; e++)
+    for (int i = 0; i < 4; i++) {
+      const int r = conn[4 * e + i];
+      for (int j = 0; j < 4; j++) tmp[fill[r]++] = conn[4 * e + j];
+    }
+  rowp.assign(nn + 1, 0);
+  cols.clear();
+  cols.reserve((size_t)9 * nn + 16);
+  for (int r = 0; r < nn; r++) {
+    std::sort(tmp.begin() + ptr[r], tmp.begin() + ptr[r + 1]);
+    int last = -1;
+    for (int k = ptr[r]; k < ptr[r + 1]; k++)
+      if (k == ptr[r] || tmp[k] != last) { cols.push_back(tmp[k]); last = tmp[k]; }
+    rowp[r + 1] = (int)cols.size();
+  }
+  return 0;
+}
+
+extern "C" int a2ds_host_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int *cols,
+                                 long long *nnz) {
+  std::vector<int> rp, cl;
+  if (natural_pattern(n_nodes, n_elems, conn, rp, cl)) return 1;
+  if (rowp) memcpy(rowp, rp.data(), rp.size() * sizeof(int));
+  if (cols) memcpy(cols, cl.data(), cl.size() * sizeof(int));
+  if (nnz) *nnz = (long long)cl.size();
+  return 0;
+}
+
+extern "C" int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *color,
+                                        int *n_colors) {
+  std::vector<int> col;
+  int nc = 0;
+  color_elements(n_nodes, n_elems, conn, col, nc);
+  memcpy(color, col.data(), col.size() * sizeof(int));
+  *n_colors = nc;
+  return 0;
+}
+
+extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
+  if (!c->conn) return fail("a2ds_mat_create_natural: call a2ds_set_mesh first");
+  std::vector<int> rowp, cols;
+  if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), rowp, cols)) return 1;
+  const int nrows = c->n_nodes;
+  const int *rp = rowp.data(), *cp = cols.data();
+  const int ident = 1;
+  return a2ds_mat_create(c, 1, &nrows, &rp, &cp, nullptr, nullptr, &ident, mat);
+}
+
+extern "C" int a2ds_mat_pattern(a2ds_ctx *c, int mat, int block, int *nrows, int *rowp, int *cols) {
+  if (check_mat(c, mat, block)) return 1;
+  MatrixRec &m = c->mats[mat];
+  if (nrows) *nrows = m.nrows[block];
+  if (rowp) memcpy(rowp, m.h_rowp[block].data(), m.h_rowp[block].size() * sizeof(int));
+  if (cols) memcpy(cols, m.h_cols[block].data(), m.h_cols[block].size() * sizeof(int));
+  return 0;
+}
+
+extern "C" int a2ds_mat_nnz(a2ds_ctx *c, int mat, int block, long long *nnz) {
+  if (check_mat(c, mat, block)) return 1;
+  *nnz = c->mats[mat].nnz[block];
+  return 0;
+}
+
+extern "C" int a2ds_mat_zero(a2ds_ctx *c, int mat) {
+  if (check_mat(c, mat)) return 1;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->mats[mat].A, 0, c->mats[mat].total * 36 * sizeof(double), c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_mat_download(a2ds_ctx *c, int mat, int block, double *A) {
+  if (check_mat(c, mat, block)) return 1;
+  CU(cudaSetDevice(c->device));
+  MatrixRec &m = c->mats[mat];
+  CU(cudaMemcpyAsync(A, m.A + 36 * m.base[block], m.nnz[block] * 36 * sizeof(double),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_mat_values_dev(a2ds_ctx *c, int mat, int block, double **A_dev) {
+  if (check_mat(c, mat, block)) return 1;
+  *A_dev = c->mats[mat].A + 36 * c->mats[mat].base[block];
+  return 0;
+}
+
+extern "C" int a2ds_res_dev(a2ds_ctx *c, double **r) { *r = c->res; return 0; }
+extern "C" int a2ds_state_dev(a2ds_ctx *c, double **u) { *u = c->u; return 0; }
+
+// ---- halo -------------------------------------------------------------------
+extern "C" int a2ds_comm_unique_id(char id[128]) {
+  ncclUniqueId uid;
+  NC(ncclGetUniqueId(&uid));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id, &uid, 128);
+  return 0;
+}
+
+extern "C" int a2ds_comm_init(a2ds_ctx *c, int n_ranks, int rank, const char id[128]) {
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  NC(ncclCommInitRank(&c->comm, n_ranks, uid, rank));
+  c->n_ranks = n_ranks; c->rank = rank;
+  return 0;
+}
+
+extern "C" int a2ds_set_halo(a2ds_ctx *c, int n_peers, const int *peer_rank, const int *send_ptr,
+                             const int *send_nodes, const int *recv_ptr, const int *recv_nodes) {
+  CU(cudaSetDevice(c->device));
+  c->peers.assign(peer_rank, peer_rank + n_peers);
+  c->send_ptr.assign(send_ptr, send_ptr + n_peers + 1);
+  c->recv_ptr.assign(recv_ptr, recv_ptr + n_peers + 1);
+  const size_t ns = send_ptr[n_peers], nr = recv_ptr[n_peers];
+  if (upload(&c->send_nodes, send_nodes, ns, c->stream)) return 1;
+  if (upload(&c->recv_nodes, recv_nodes, nr, c->stream)) return 1;
+  cudaFree(c->send_buf); cudaFree(c->recv_buf);
+  c->send_buf = c->recv_buf = nullptr;
+  // the same buffers serve both directions: size for the larger side
+  const size_t nb = std::max(ns, nr);
+  CU(cudaMalloc((void **)&c->send_buf, std::max<size_t>(nb, 1) * 6 * sizeof(double)));
+  CU(cudaMalloc((void **)&c->recv_buf, std::max<size_t>(nb, 1) * 6 * sizeof(double)));
+  c->has_halo = n_peers > 0;
+  return 0;
+}
+
+// forward: owners send the values of send_nodes, ghosts receive into recv_nodes
+static int halo_exchange(a2ds_ctx *c, double *vec, bool reverse) {
+  if (!c->has_halo) return 0;
+  if (!c->comm) return fail("halo exchange: a2ds_comm_init has not been called");
+  const int np = (int)c->peers.size();
+  // forward packs the owned side, reverse packs the ghost side
+  const std::vector<int> &pk_ptr = reverse ? c->recv_ptr : c->send_ptr;
+  const std::vector<int> &up_ptr = reverse ? c->send_ptr : c->recv_ptr;
+  const int *pk_nodes = reverse ? c->recv_nodes : c->send_nodes;
+  const int *up_nodes = reverse ? c->send_nodes : c->recv_nodes;
+  const int n_pk = pk_ptr[np], n_up = up_ptr[np];
+  if (n_pk) k_pack6<<<(6 * n_pk + 255) / 256, 256, 0, c->stream>>>(n_pk, pk_nodes, vec, c->send_buf);
+  NC(ncclGroupStart());
+  for (int p = 0; p < np; p++) {
+    const int ns = pk_ptr[p + 1] - pk_ptr[p], nr = up_ptr[p + 1] - up_ptr[p];
+    if (ns) NC(ncclSend(c->send_buf + 6 * (size_t)pk_ptr[p], 6 * (size_t)ns, ncclDouble, c->peers[p], c->comm, c->stream));
+    if (nr) NC(ncclRecv(c->recv_buf + 6 * (size_t)up_ptr[p], 6 * (size_t)nr, ncclDouble, c->peers[p], c->comm, c->stream));
+  }
+  NC(ncclGroupEnd());
+  // reverse: contributions are added in peer order (fixed -> deterministic)
+  if (n_up)
+    k_unpack6<<<(6 * n_up + 255) / 256, 256, 0, c->stream>>>(n_up, up_nodes, c->recv_buf, vec, reverse ? 1 : 0);
+  CU(cudaGetLastError());
+  c->last_launches += (n_pk ? 1 : 0) + (n_up ? 1 : 0);
+  return 0;
+}
+
+extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
+  CU(cudaSetDevice(c->device));
+  return halo_exchange(c, c->u, false);
+}
+
+// ---- assembly ------------------------------------------------------------------
+template <bool RES, bool KMAT, bool GMAT, bool NL>
+static int launch_one(a2ds_ctx *c, KParams &p) {
+  const size_t per_warp = GMAT ? sizeof(ElemScratch) : offsetof(ElemScratch, B1);
+  p.scratch_bytes = (int)((per_warp + 15) & ~size_t(15));
+  const size_t smem = p.scratch_bytes * (size_t)WARPS_PER_BLOCK;
+  auto kern = k_assemble<RES, KMAT, GMAT, NL>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  int per_sm = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_BLOCK * 32, smem));
+  if (per_sm < 1) return fail("k_assemble does not fit on an SM");
+  const int want = (p.n_list + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
+  kern<<<grid, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  CU(cudaGetLastError());
+  c->last_launches++;
+  return 0;
+}
+
+// what: bit 0 residual, bit 1 tangent, bit 2 geometric stiffness
+static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat, double *res_host) {
+  CU(cudaSetDevice(c->device));
+  if (!c->conn || !c->X) return fail("assemble: mesh or nodes not set");
+  if (build_lists(c)) return 1;
+  const bool RES = what & 1, KM = (what & 2) != 0, GM = (what & 4) != 0;
+  if (KM && check_mat(c, kmat)) return 1;
+  if (GM && check_mat(c, gmat)) return 1;
+  if (KM && GM && kmat == gmat) return fail("assemble: tangent and geometric matrices must differ");
+  c->last_launches = 0;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  if (RES) CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)c->n_nodes * sizeof(double), c->stream));
+  if (KM) CU(cudaMemsetAsync(c->mats[kmat].A, 0, c->mats[kmat].total * 36 * sizeof(double), c->stream));
+  if (GM) CU(cudaMemsetAsync(c->mats[gmat].A, 0, c->mats[gmat].total * 36 * sizeof(double), c->stream));
+  c->last_launches += (RES ? 1 : 0) + (KM ? 1 : 0) + (GM ? 1 : 0);
+
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.conn = c->conn; p.elem_comp = c->elem_comp; p.comps = c->comps;
+  p.X = c->X; p.u = c->u; p.res = c->res; p.alpha = alpha;
+  if (KM) { p.Kval = c->mats[kmat].A; p.Koff = c->mats[kmat].off; }
+  if (GM) { p.Gval = c->mats[gmat].A; p.Goff = c->mats[gmat].off; }
+
+  for (int col = 0; col < c->n_colors; col++) {
+    for (int cls = 0; cls < 2; cls++) {
+      p.n_list = c->list_len[cls][col];
+      p.elem_list = c->list_dev[cls][col];
+      if (p.n_list == 0) continue;
+      int rc = 0;
+      if (cls == 0) {
+        switch (what) {
+          case 1: rc = launch_one<true, false, false, false>(c, p); break;
+          case 2: rc = launch_one<false, true, false, false>(c, p); break;
+          case 3: rc = launch_one<true, true, false, false>(c, p); break;
+          case 4: rc = launch_one<false, false, true, false>(c, p); break;
+          case 7: rc = launch_one<true, true, true, false>(c, p); break;
+          default: return fail("assemble: unsupported output combination");
+        }
+      } else {
+        // nonlinear strain model: residual and tangent about the current state.
+        // Its geometric stiffness (a finite difference about the ZERO state in the
+        // reference, TACSShellElement.h:705-751) is the same linear-in-state term as
+        // for the linear model and is evaluated with the linear-model kernel.
+        switch (what) {
+          case 1: rc = launch_one<true, false, false, true>(c, p); break;
+          case 2: rc = launch_one<false, true, false, true>(c, p); break;
+          case 3: rc = launch_one<true, true, false, true>(c, p); break;
+          case 4: rc = launch_one<false, false, true, false>(c, p); break;
+          case 7:
+            rc = launch_one<true, true, false, true>(c, p);
+            if (!rc) rc = launch_one<false, false, true, false>(c, p);
+            break;
+          default: return fail("assemble: unsupported output combination");
+        }
+      }
+      if (rc) return rc;
+    }
+  }
+  // ghost residual contributions -> owners (TACSBVec::beginSetValues/endSetValues, ADD)
+  if (RES && halo_exchange(c, c->res, true)) return 1;
+  if (RES && c->n_bc) {
+    k_res_bcs<<<(6 * c->n_bc + 255) / 256, 256, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars,
+                                                                c->bc_vals, c->u, c->res, c->n_owned);
+    c->last_launches++;
+  }
+  for (int pass = 0; pass < 2; pass++) {
+    const bool on = pass == 0 ? KM : GM;
+    if (!on || !c->n_bc) continue;
+    MatrixRec &m = c->mats[pass == 0 ? kmat : gmat];
+    const int nt = c->n_bc * m.n_blocks;
+    k_mat_bcs<<<(nt + 127) / 128, 128, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars, m.n_blocks,
+                                                       m.blk_dev, m.A);
+    c->last_launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev1, c->stream));
+  if (res_host) {
+    CU(cudaMemcpyAsync(res_host, c->res, 6 * (size_t)c->n_owned * sizeof(double),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+extern "C" int a2ds_assemble_res(a2ds_ctx *c, double *res) {
+  return run_assembly(c, 1, 1.0, -1, -1, res);
+}
+
+extern "C" int a2ds_assemble_jacobian(a2ds_ctx *c, double alpha, double beta, double gamma,
+                                      double *res, int mat) {
+  if (beta != 0.0 || gamma != 0.0)
+    return fail("a2ds_assemble_jacobian: only the static path (beta = gamma = 0) is implemented");
+  int rc = run_assembly(c, 3, alpha, mat, -1, res);
+  if (rc) return rc;
+  if (!res) return 0;
+  return 0;
+}
+
+extern "C" int a2ds_assemble_mat_type(a2ds_ctx *c, int mat_type, int mat) {
+  if (mat_type == A2DS_STIFFNESS_MATRIX) return run_assembly(c, 2, 1.0, mat, -1, nullptr);
+  if (mat_type == A2DS_GEOMETRIC_STIFFNESS_MATRIX) return run_assembly(c, 4, 1.0, -1, mat, nullptr);
+  return fail("a2ds_assemble_mat_type: only stiffness and geometric stiffness are implemented");
+}
+
+extern "C" int a2ds_assemble_all(a2ds_ctx *c, double *res, int kmat, int gmat) {
+  return run_assembly(c, 7, 1.0, kmat, gmat, res);
+}
+
+extern "C" int a2ds_last_timing(a2ds_ctx *c, float *ms, int *launches) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  if (ms) *ms = c->last_ms;
+  if (launches) *launches = c->last_launches;
+  return 0;
+}

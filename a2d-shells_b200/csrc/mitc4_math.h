@@ -84,8 +84,7 @@ struct ElemScratch {
                                     // (u_0..u_3, d_0..d_3): coefficient pairs
   double sg[4][3]; // per Gauss point: w*s3, w*s4, w*s5 (bending resultants)
   double sig[4][9];    // per Gauss point contribution to the tying-point stresses
-  double rpart[4][24]; // per Gauss point contribution to the residual
-  double epart[32][9]; // per lane contribution to the Gauss point strains
+  double Mq[4][25];    // per Gauss point: tying strain -> membrane/shear strain map
   double BA[24 * LDS_ROWS];  // strain matrix B (A operand)
   double W[24 * LDS_ROWS];   // w C B
   double B1[24 * LDS_ROWS];  // state dependent part B1(q)
@@ -540,15 +539,24 @@ struct Want {
   bool nonlinear;        // element uses the nonlinear strain model (tangent/residual)
 };
 
-// ---- phase 2: lane = (qp, m, h): strain matrix columns + strain partial sums ---
-// Fills BA (= B0, or B0 + B1 for the nonlinear model) and B1 columns in scratch and
-// the lane's contribution to the Gauss point strains.
-A2DS_HD void phase_columns(const CompData &c, ElemScratch &s, int lane, const Want &w,
-                           QpGeom &g) {
+// ---- phase 2: lane = (qp, m, h): three columns of B, w C B and B1 ---------------
+// Writes the lane's columns of BA (= B0, or B0 + B1 for the nonlinear model), of
+// W = w C BA and of B1 into the scratch operand arrays, publishes the per Gauss
+// point data of the geometric phase, and returns in e_part[9] the lane's
+// contribution to the Gauss point strains (to be summed over the 8 lanes of the
+// Gauss point: warp shuffles on the device, a loop in the host emulation).
+A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Want &w,
+                          double e_part[9], double &qp_w, double na[2], double nb[2]) {
   const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
   const bool need_b1 = w.gmat || w.nonlinear;
+  QpGeom g;
   qp_geometry(c, s, qp, need_b1, g);
-  if (m == 0 && h == 0) qp_publish(s, qp, g);
+  qp_w = g.w;
+  na[0] = g.na[0]; na[1] = g.na[1]; nb[0] = g.nb[0]; nb[1] = g.nb[1];
+  if (m == 0 && h == 0) {
+    qp_publish(s, qp, g);
+    for (int i = 0; i < 25; i++) s.Mq[qp][i] = g.M[i];
+  }
   NodeCoef nc;
   node_coef(g, m, nc);
   // coefficient pairs for the geometric stiffness phase (generalised nodes u_m, d_m)
@@ -573,68 +581,76 @@ A2DS_HD void phase_columns(const CompData &c, ElemScratch &s, int lane, const Wa
   const int col = 6 * m + 3 * h;
   for (int r = 0; r < 9; r++) {
     double e = B0[r][0] * qc[0] + B0[r][1] * qc[1] + B0[r][2] * qc[2];
-    if (need_b1) {
-      // nonlinear strain: e = B0 q + 1/2 B1 q.  For the geometric stiffness of a
-      // linear-model element only the linear strain enters the stress.
-      if (w.nonlinear) e += 0.5 * (Bq[r][0] * qc[0] + Bq[r][1] * qc[1] + Bq[r][2] * qc[2]);
-      for (int k = 0; k < 3; k++) s.B1[(col + k) * LDS_ROWS + 9 * qp + r] = Bq[r][k];
+    // nonlinear strain: e = B0 q + 1/2 B1 q.  For the geometric stiffness of a
+    // linear-model element only the linear strain enters the stress.
+    if (w.nonlinear) e += 0.5 * (Bq[r][0] * qc[0] + Bq[r][1] * qc[1] + Bq[r][2] * qc[2]);
+    e_part[r] = e;
+  }
+  for (int k = 0; k < 3; k++) {
+    double b[9], cb[9];
+    for (int r = 0; r < 9; r++) {
+      b[r] = B0[r][k];
+      if (w.nonlinear) b[r] += Bq[r][k];
     }
-    s.epart[lane][r] = e;
-    for (int k = 0; k < 3; k++) {
-      double b = B0[r][k];
-      if (w.nonlinear) b += Bq[r][k];
-      s.BA[(col + k) * LDS_ROWS + 9 * qp + r] = b;
+    apply_C(c.Cs, b, cb);
+    double *pa = &s.BA[(col + k) * LDS_ROWS + 9 * qp];
+    double *pw = &s.W[(col + k) * LDS_ROWS + 9 * qp];
+    for (int r = 0; r < 9; r++) {
+      pa[r] = b[r];
+      pw[r] = g.w * cb[r];
+    }
+    if (w.gmat) {
+      double *p1 = &s.B1[(col + k) * LDS_ROWS + 9 * qp];
+      for (int r = 0; r < 9; r++) p1[r] = Bq[r][k];
     }
   }
 }
 
-// ---- phase 3: lane = (qp, m, h): stresses, W = w C B columns, residual partials ---
-A2DS_HD void phase_stress(const CompData &c, ElemScratch &s, int lane, const Want &w,
-                          const QpGeom &g) {
+// ---- phase 3: lane = (qp, m, h): mechanical strain -> residual partials, stresses ---
+// e_qp[9] is the Gauss point strain summed over the lanes of the point.  Returns the
+// lane's three residual entries for this Gauss point, r = W^T (e - T eth) (to be summed
+// over the four Gauss points), and publishes the stresses of the geometric phase.
+A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want &w,
+                         const double e_qp[9], double qp_w, const double na[2],
+                         const double nb[2], double r3[3]) {
   const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
-  double e[9], st[9];
-  for (int r = 0; r < 9; r++) {
-    double acc = 0.0;
-    for (int l = 0; l < 8; l++) acc += s.epart[8 * qp + l][r];
-    e[r] = acc - c.temperature * c.eth[r];
-  }
+  double e[9];
+  for (int r = 0; r < 9; r++) e[r] = e_qp[r] - c.temperature * c.eth[r];
   {
     // drilling strain of the state: interpolate the nodal values evaluated in the
     // reference's order (interpFields<1,1>, TACSShellElement.h:350)
     double et = 0.0;
-    for (int n = 0; n < 4; n++) et = A2DS_ADD(et, A2DS_MUL(A2DS_MUL(g.na[n % 2], g.nb[n / 2]), s.etn[n]));
+    for (int n = 0; n < 4; n++)
+      et = A2DS_ADD(et, A2DS_MUL(A2DS_MUL(na[n % 2], nb[n / 2]), s.etn[n]));
     e[8] = et - c.temperature * c.eth[8];
   }
-  apply_C(c.Cs, e, st);
   const int col = 6 * m + 3 * h;
   for (int k = 0; k < 3; k++) {
-    double b[9], cb[9];
-    for (int r = 0; r < 9; r++) b[r] = s.BA[(col + k) * LDS_ROWS + 9 * qp + r];
-    apply_C(c.Cs, b, cb);
+    const double *pw = &s.W[(col + k) * LDS_ROWS + 9 * qp];
     double rr = 0.0;
-    for (int r = 0; r < 9; r++) {
-      s.W[(col + k) * LDS_ROWS + 9 * qp + r] = g.w * cb[r];
-      rr += b[r] * st[r];
-    }
-    s.rpart[qp][col + k] = g.w * rr;
+    for (int r = 0; r < 9; r++) rr += pw[r] * e[r];
+    r3[k] = rr;
   }
-  if (m == 0 && h == 0) {
+  if ((w.gmat || w.nonlinear) && m == 0 && h == 0) {
+    double st[9];
+    apply_C(c.Cs, e, st);
     // stresses feeding the geometric terms
-    s.sg[qp][0] = g.w * st[3]; s.sg[qp][1] = g.w * st[4]; s.sg[qp][2] = g.w * st[5];
+    s.sg[qp][0] = qp_w * st[3]; s.sg[qp][1] = qp_w * st[4]; s.sg[qp][2] = qp_w * st[5];
     // pull the membrane/shear stresses back to the tying points:
     // dU/dg5 = M^T (w s_ms), then the tying interpolation transposed
-    const double sm[5] = {g.w * st[0], g.w * st[1], g.w * st[2], g.w * st[6], g.w * st[7]};
+    const double sm[5] = {qp_w * st[0], qp_w * st[1], qp_w * st[2], qp_w * st[6], qp_w * st[7]};
+    const double *M = s.Mq[qp];
     double dg[5];
     for (int cidx = 0; cidx < 5; cidx++)
-      dg[cidx] = g.M[cidx] * sm[0] + g.M[5 + cidx] * sm[1] + g.M[10 + cidx] * sm[2] +
-                 g.M[15 + cidx] * sm[3] + g.M[20 + cidx] * sm[4];
+      dg[cidx] = M[cidx] * sm[0] + M[5 + cidx] * sm[1] + M[10 + cidx] * sm[2] +
+                 M[15 + cidx] * sm[3] + M[20 + cidx] * sm[4];
     // tying point order (QuadBasis.h:530-564): g11 @eta=-+1, g22 @xi=-+1, g12 centre,
     // g23 @xi=-+1, g13 @eta=-+1; dg order (g11, g12, g13, g22, g23)
-    s.sig[qp][0] = g.nb[0] * dg[0]; s.sig[qp][1] = g.nb[1] * dg[0];
-    s.sig[qp][2] = g.na[0] * dg[3]; s.sig[qp][3] = g.na[1] * dg[3];
+    s.sig[qp][0] = nb[0] * dg[0]; s.sig[qp][1] = nb[1] * dg[0];
+    s.sig[qp][2] = na[0] * dg[3]; s.sig[qp][3] = na[1] * dg[3];
     s.sig[qp][4] = dg[1];
-    s.sig[qp][5] = g.na[0] * dg[4]; s.sig[qp][6] = g.na[1] * dg[4];
-    s.sig[qp][7] = g.nb[0] * dg[2]; s.sig[qp][8] = g.nb[1] * dg[2];
+    s.sig[qp][5] = na[0] * dg[4]; s.sig[qp][6] = na[1] * dg[4];
+    s.sig[qp][7] = nb[0] * dg[2]; s.sig[qp][8] = nb[1] * dg[2];
   }
 }
 

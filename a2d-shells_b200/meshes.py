@@ -1,0 +1,114 @@
+"""Synthetic structured shell meshes and seeded states.
+
+Node order inside an element is the reference's tensor order
+[(i,j),(i+1,j),(i,j+1),(i+1,j+1)] (TACSShellElementQuadBasis.h:147-150; the BDF
+reader maps CQUAD4 n1,n2,n3,n4 to this as [n1,n2,n4,n3], TACSMeshLoader.cpp:932-937).
+"""
+import numpy as np
+
+
+def plate(nx, ny, lx=1.0, ly=1.0, bump=1e-3):
+    """Flat (bump=0) or slightly doubly-curved plate of nx x ny elements.
+    Returns conn[ne,4], X[nn,3], clamped-edge BC nodes (edge i = 0)."""
+    i = np.arange(nx + 1); j = np.arange(ny + 1)
+    ii, jj = np.meshgrid(i, j, indexing="xy")          # node id = j*(nx+1) + i
+    x = ii.ravel() * (lx / nx); y = jj.ravel() * (ly / ny)
+    z = bump * np.sin(2 * np.pi * x / lx) * np.sin(2 * np.pi * y / ly)
+    X = np.stack([x, y, z], axis=1)
+    ei, ej = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    n0 = (ej * (nx + 1) + ei).ravel()
+    conn = np.stack([n0, n0 + 1, n0 + nx + 1, n0 + nx + 2], axis=1).astype(np.int32)
+    bc_nodes = (np.arange(ny + 1) * (nx + 1)).astype(np.int32)
+    return conn, X, bc_nodes
+
+
+def cylinder(ntheta, nx, radius=0.2, length=0.4, x0=0.0):
+    """Closed cylinder, periodic in theta: ntheta x nx elements, X = (x, -R sin t, -R cos t)
+    as examples/cylinder-buckling/mech-cylinder.bdf:7-10.  Node id = ix*ntheta + it.
+    Returns conn, X, nodes of the two end rings."""
+    it = np.arange(ntheta); ix = np.arange(nx + 1)
+    tt, xx = np.meshgrid(it, ix, indexing="xy")
+    th = tt.ravel() * (2 * np.pi / ntheta)
+    x = x0 + xx.ravel() * (length / nx)
+    X = np.stack([x, -radius * np.sin(th), -radius * np.cos(th)], axis=1)
+    et, ex = np.meshgrid(np.arange(ntheta), np.arange(nx), indexing="xy")
+    et = et.ravel(); ex = ex.ravel()
+    etp = (et + 1) % ntheta
+    conn = np.stack([ex * ntheta + et, ex * ntheta + etp, (ex + 1) * ntheta + et,
+                     (ex + 1) * ntheta + etp], axis=1).astype(np.int32)
+    ends = np.concatenate([np.arange(ntheta), nx * ntheta + np.arange(ntheta)]).astype(np.int32)
+    return conn, X, ends
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def seeded_state(global_node_ids, scale=1e-5, seed=12345):
+    """u[n,6] = scale * U(-1,1) from a counter-based hash keyed on the GLOBAL node id
+    and dof (partition independent, no RNG state): splitmix64(seed ^ (6*id + dof))."""
+    ids = np.asarray(global_node_ids, dtype=np.uint64)
+    key = (ids[:, None] * np.uint64(6) + np.arange(6, dtype=np.uint64)[None, :]) ^ np.uint64(seed)
+    with np.errstate(over="ignore"):
+        h = _splitmix64(key)
+    u01 = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return scale * (2.0 * u01 - 1.0)
+
+
+def slab_partition(n_slabs, conn, X, axis_index, n_per_layer):
+    """Not used by the single-GPU path; see partition_structured()."""
+    raise NotImplementedError
+
+
+def partition_rows(conn, n_nodes, elem_rank):
+    """Element-wise partition -> per-rank local meshes with TACSCreator's node ownership
+    rule: a node belongs to the rank of the first element (in global order) touching it
+    (src/TACSCreator.cpp:1156-1205).  Returns a list of dicts per rank:
+      conn_local, owned (global ids), ghosts (global ids), elems (global element ids),
+      peers / send_lists / recv_lists (local indices) for the halo exchange."""
+    conn = np.asarray(conn)
+    elem_rank = np.asarray(elem_rank)
+    n_ranks = int(elem_rank.max()) + 1
+    owner = np.full(n_nodes, -1, dtype=np.int64)
+    # first touch in global element order
+    flat_nodes = conn.ravel()
+    flat_rank = np.repeat(elem_rank, 4)
+    first = np.full(n_nodes, len(flat_nodes), dtype=np.int64)
+    np.minimum.at(first, flat_nodes, np.arange(len(flat_nodes)))
+    touched = first < len(flat_nodes)
+    owner[touched] = flat_rank[first[touched]]
+    parts = []
+    for r in range(n_ranks):
+        elems = np.nonzero(elem_rank == r)[0]
+        used = np.unique(conn[elems].ravel())
+        owned = used[owner[used] == r]
+        # owned nodes this rank never references still belong to it
+        extra = np.nonzero(owner == r)[0]
+        owned = np.union1d(owned, extra)
+        ghosts = used[owner[used] != r]
+        glob = np.concatenate([owned, ghosts])
+        lookup = {}
+        local_of = np.full(n_nodes, -1, dtype=np.int64)
+        local_of[glob] = np.arange(len(glob))
+        parts.append(dict(rank=r, elems=elems, owned=owned, ghosts=ghosts, glob=glob,
+                          conn_local=local_of[conn[elems]].astype(np.int32),
+                          local_of=local_of, ghost_owner=owner[ghosts]))
+    # halo lists: for each (r, p): ghosts of r owned by p, sorted by global id on both sides
+    for r in range(n_ranks):
+        P = parts[r]
+        peers = sorted(set(P["ghost_owner"].tolist()) |
+                       {q for q in range(n_ranks) if q != r and np.any(parts[q]["ghost_owner"] == r)})
+        send_lists, recv_lists = [], []
+        for p in peers:
+            mine = np.sort(P["ghosts"][P["ghost_owner"] == p])              # I receive these
+            theirs = np.sort(parts[p]["ghosts"][parts[p]["ghost_owner"] == r])  # I send these
+            recv_lists.append(P["local_of"][mine].astype(np.int32))
+            send_lists.append(P["local_of"][theirs].astype(np.int32))
+        P["peers"] = np.asarray(peers, dtype=np.int32)
+        P["send_lists"] = send_lists
+        P["recv_lists"] = recv_lists
+    return parts

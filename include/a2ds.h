@@ -1,0 +1,185 @@
+/*
+ * a2ds.h — C ABI of the B200 shell-assembly library (liba2ds_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of the reference (a2d-shells, a TACS
+ * mini-app): assembly of the residual, tangent stiffness and geometric stiffness
+ * of MITC4 director shells into 6x6-block BCSR matrices.  Every entry point
+ * below names the reference interface it stands in for (paths relative to the
+ * reference root).  Plain pointers and sizes only; all `const double*` / `const
+ * int*` arguments are HOST pointers unless the name ends in `_dev`.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error;
+ *     a2ds_last_error() returns a description of the last failure of the calling
+ *     thread (the reference prints to stderr and carries on,
+ *     src/bpmat/BCSRMat.cpp:1803; a C ABI cannot, so it reports);
+ *   - one context per GPU, driven by one host thread; work is enqueued on the
+ *     context's stream; calls that hand data back to the host synchronise;
+ *   - node indices are LOCAL indices of this rank: owned nodes first
+ *     [0, n_owned), then ghost nodes (TACSBVec x / x_ext split,
+ *     src/bpmat/TACSBVec.h:141-158);
+ *   - DOF layout per node [u v w rx ry rz]; element matrix blocks are 6x6,
+ *     row-major inside the block, block k at A[36 k]
+ *     (src/bpmat/BCSRMatImpl.h:27-46, BCSRMat.cpp:1806-1817).
+ *   - there is no CPU fallback: if no CUDA device is usable a2ds_create fails.
+ */
+#ifndef A2DS_H
+#define A2DS_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct a2ds_ctx a2ds_ctx;
+
+/* ElementMatrixType, src/elements/TACSElementTypes.h:101-107 */
+#define A2DS_STIFFNESS_MATRIX 0
+#define A2DS_GEOMETRIC_STIFFNESS_MATRIX 1
+
+/* element class of a component: TACSQuad4Shell / TACSQuad4NonlinearShell
+   (src/elements/shell/TACSShellElementDefs.h:12-14, 27-29) */
+#define A2DS_QUAD4_SHELL 0
+#define A2DS_QUAD4_NONLINEAR_SHELL 1
+
+/* TACSShellNaturalTransform / TACSShellRefAxisTransform
+   (src/elements/shell/TACSShellElementTransform.h:22, 95) */
+#define A2DS_TRANSFORM_NATURAL 0
+#define A2DS_TRANSFORM_REF_AXIS 1
+
+/* scatter mode: atomics in launch order, or one launch per element colour with a
+   fixed colour order (bit-reproducible run to run) */
+#define A2DS_SCATTER_ATOMIC 0
+#define A2DS_SCATTER_COLORED 1
+
+const char *a2ds_last_error(void);
+const char *a2ds_version(void);
+
+/* ---- context --------------------------------------------------------------- */
+int a2ds_create(int device, a2ds_ctx **ctx);
+int a2ds_destroy(a2ds_ctx *ctx);
+int a2ds_synchronize(a2ds_ctx *ctx);
+
+/* ---- mesh, replaces the element loops' inputs ---------------------------------
+ * TACSAssembler::setElementConnectivity / setElements (src/TACSAssembler.h:89-91):
+ * conn[4 e + i] is the local node of corner i of element e in the reference's
+ * tensor order (src/elements/shell/TACSShellElementQuadBasis.h:147-150);
+ * elem_comp[e] selects the component record below. */
+int a2ds_set_mesh(a2ds_ctx *ctx, int n_nodes, int n_owned, int n_elems, const int *conn,
+                  const int *elem_comp);
+
+/* TACSAssembler::setNodes (src/TACSAssembler.cpp:912): X[3 n + k], all local nodes */
+int a2ds_set_nodes(a2ds_ctx *ctx, const double *X);
+
+/* Per-component tables.  Replaces the virtual calls made per quadrature point:
+ *   con->evalTangentStiffness -> Cs[22 c + .]   (src/constitutive/TACSShellConstitutive.h:34)
+ *   con->evalThermalStrain(theta = 1) -> eth[9 c + .]  (TACSIsoShellConstitutive.cpp:438-456)
+ *   element->temperature -> temperature[c]      (src/elements/shell/TACSShellElement.h:35)
+ *   element class -> elem_class[c];  transform kind + reference axis (common to all) */
+int a2ds_set_components(a2ds_ctx *ctx, int n_comp, const double *Cs, const double *eth,
+                        const double *temperature, const int *elem_class, int transform,
+                        const double *ref_axis);
+
+/* TACSAssembler::setVariables (src/TACSAssembler.cpp:3825-3857): u[6 n + k] for all
+ * local nodes when n_given == n_nodes, or for the owned nodes only when
+ * n_given == n_owned (ghost values then come from a2ds_halo_forward). */
+int a2ds_set_state(a2ds_ctx *ctx, int n_given, const double *u);
+int a2ds_set_state_dev(a2ds_ctx *ctx, int n_given, const double *u_dev);
+
+/* TACSBcMap (src/bpmat/KSM.h:43-75): bc_nodes[b] local node, bc_vars[b] bit mask of
+ * constrained DOFs, bc_vals[6 b + k] prescribed values */
+int a2ds_set_bcs(a2ds_ctx *ctx, int n_bc, const int *bc_nodes, const int *bc_vars,
+                 const double *bc_vals);
+
+/* A2DS_SCATTER_* ; colouring is computed on the host when first needed */
+int a2ds_set_scatter_mode(a2ds_ctx *ctx, int mode);
+
+/* ---- matrices ---------------------------------------------------------------
+ * A matrix is 1..4 BCSR blocks that share one device allocation, mirroring
+ * TACSParallelMat {Aloc, Bext} (src/bpmat/TACSParallelMat.h:103) and TACSSchurMat
+ * {B, E, F, C} (src/bpmat/TACSSchurMat.h:98).  The non-zero pattern is TAKEN from the
+ * host matrices (BCSRMat::getArrays, src/bpmat/BCSRMat.h:82), never recomputed.
+ * For block b: row_map[b][n] / col_map[b][n] give the block-local row / column of
+ * local node n, or -1 when the node is not in that block's row / column set (NULL =
+ * identity); this replaces the two-level search of TACSSchurMat::addValues
+ * (src/bpmat/TACSSchurMat.cpp:453-531) + BCSRMat::addRowValues (BCSRMat.cpp:1778).
+ * bc_ident[b] != 0: the block holds the diagonal — BC rows get 1.0 there
+ * (TACSSchurMat::applyBCs, TACSSchurMat.cpp:662-703).
+ * Returns a matrix id >= 0 in *mat. */
+int a2ds_mat_create(a2ds_ctx *ctx, int n_blocks, const int *nrows, const int *const *rowp,
+                    const int *const *cols, const int *const *row_map,
+                    const int *const *col_map, const int *bc_ident, int *mat);
+/* Same, with the pattern computed here from the element connectivity: one block,
+ * one row per local node, columns = all nodes sharing an element with the row
+ * node, sorted ascending.  This is the pattern TACSAssembler::createMat builds
+ * (computeLocalNodeToNodeCSR, src/TACSAssembler.cpp:1839 + TacsSortAndUniquifyCSR,
+ * src/utils/TacsUtilities.cpp:280) for natural ordering; tests check it is
+ * identical to the reference's, bit for bit. */
+int a2ds_mat_create_natural(a2ds_ctx *ctx, int *mat);
+/* copy the pattern of a block to the host: rowp[nrows + 1], cols[nnz] (either may be NULL) */
+int a2ds_mat_pattern(a2ds_ctx *ctx, int mat, int block, int *nrows, int *rowp, int *cols);
+/* number of 6x6 blocks stored in BCSR block `block` */
+int a2ds_mat_nnz(a2ds_ctx *ctx, int mat, int block, long long *nnz);
+/* TACSMat::zeroEntries (src/bpmat/BCSRMat.cpp:1745) */
+int a2ds_mat_zero(a2ds_ctx *ctx, int mat);
+/* copy block values to the host array A[36 nnz] (the "hand K and G back to the
+ * reference solver" path: BCSRMat::getArrays) / borrow the device pointer */
+int a2ds_mat_download(a2ds_ctx *ctx, int mat, int block, double *A);
+int a2ds_mat_values_dev(a2ds_ctx *ctx, int mat, int block, double **A_dev);
+
+/* ---- assembly: the three reference entry points -------------------------------
+ * TACSAssembler::assembleRes (src/TACSAssembler.cpp:4000-4063): res[6 n + k] for the
+ * owned nodes, boundary rows r = u - ubar.  res may be NULL (result stays on device,
+ * see a2ds_res_dev). */
+int a2ds_assemble_res(a2ds_ctx *ctx, double *res);
+/* TACSAssembler::assembleJacobian (src/TACSAssembler.cpp:4084-4174) with
+ * beta = gamma = 0 (static path): zero res and A, add alpha * dR/du, apply BCs to
+ * both.  res may be NULL. */
+int a2ds_assemble_jacobian(a2ds_ctx *ctx, double alpha, double beta, double gamma,
+                           double *res, int mat);
+/* TACSAssembler::assembleMatType (src/TACSAssembler.cpp:4186-4249) */
+int a2ds_assemble_mat_type(a2ds_ctx *ctx, int mat_type, int mat);
+/* residual + tangent + geometric stiffness in one pass over the elements (what the
+ * buckling flow asks for in three calls, src/TACSBuckling.cpp:239-266) */
+int a2ds_assemble_all(a2ds_ctx *ctx, double *res, int kmat, int gmat);
+
+/* device-resident residual of the last assembly, 6 * n_nodes doubles */
+int a2ds_res_dev(a2ds_ctx *ctx, double **res_dev);
+/* device-resident state, 6 * n_nodes doubles */
+int a2ds_state_dev(a2ds_ctx *ctx, double **u_dev);
+
+/* ---- multi-GPU: ghost exchange ------------------------------------------------
+ * TACSBVecDistribute (src/bpmat/TACSBVecDistribute.cpp:543-747).  Peers are the other
+ * ranks of an NCCL communicator; the 128-byte unique id is created on rank 0 with
+ * a2ds_comm_unique_id and broadcast by the caller (torch.distributed / MPI).
+ * send_ptr/send_nodes: for peer p, the owned local nodes whose values that peer
+ * reads as ghosts; recv_ptr/recv_nodes: the local ghost nodes owned by peer p. */
+int a2ds_comm_unique_id(char id[128]);
+int a2ds_comm_init(a2ds_ctx *ctx, int n_ranks, int rank, const char id[128]);
+int a2ds_set_halo(a2ds_ctx *ctx, int n_peers, const int *peer_rank, const int *send_ptr,
+                  const int *send_nodes, const int *recv_ptr, const int *recv_nodes);
+/* forward: owner -> ghost copies of the state (beginForward/endForward) */
+int a2ds_halo_forward(a2ds_ctx *ctx);
+/* reverse: ghost residual contributions added to their owners, done inside
+ * a2ds_assemble_* when a halo is set (beginReverse/endReverse, TACS_ADD_VALUES) */
+
+/* ---- host-only helpers (no device needed) ---------------------------------------
+ * The natural-order non-zero pattern used by a2ds_mat_create_natural: two-pass, call
+ * with cols == NULL to fill rowp[n_nodes + 1] and obtain *nnz, then again with cols. */
+int a2ds_host_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int *cols,
+                      long long *nnz);
+/* Greedy element colouring used by A2DS_SCATTER_COLORED: color[e] in [0, *n_colors);
+ * elements sharing a node never share a colour. */
+int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *color,
+                             int *n_colors);
+
+/* ---- instrumentation ------------------------------------------------------------
+ * device time of the last assemble call in milliseconds (CUDA events on the context
+ * stream) and the number of kernels it launched */
+int a2ds_last_timing(a2ds_ctx *ctx, float *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

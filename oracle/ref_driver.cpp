@@ -431,11 +431,13 @@ double refdrv_time(void *h, int op, int mat) {
  * mode 1: kmat and gmat already hold externally assembled values (set with
  *         refdrv_mat_set); only the tail of solve() is run
  *         (src/TACSBuckling.cpp:240,262-263,269-277).
- * u0 (reference numbering) is the load-path state, as the shipped examples pass.
+ * u0 (reference numbering) is the load-path state, as the shipped examples pass;
+ * NULL in mode 0 lets the reference solve for the path.  path_out (optional)
+ * receives the load path actually used (after setBCs).
  */
 int refdrv_buckling(void *h, int kmat, int gmat, int aux, int mode, double sigma,
                     int max_lanczos, int num_eigs, double tol, const double *u0,
-                    double *eigs, double *errs) {
+                    double *eigs, double *errs, double *path_out) {
   RefCtx *c = (RefCtx *)h;
   TACSSchurMat *K = (TACSSchurMat *)c->mats[kmat].mat;
   TACSSchurMat *G = (TACSSchurMat *)c->mats[gmat].mat;
@@ -456,7 +458,9 @@ int refdrv_buckling(void *h, int kmat, int gmat, int aux, int mode, double sigma
     memcpy(a, u0, n * sizeof(double));
   }
   if (mode == 0) {
-    b->solve(f, u, NULL);
+    /* u0 == NULL: the reference computes the load path itself by a linear static
+       solve, path = -K^{-1} r (src/TACSBuckling.cpp:244-258) */
+    b->solve(f, u0 ? u : NULL, NULL);
   } else {
     c->assembler->zeroVariables();
     A->copyValues(K);
@@ -467,6 +471,11 @@ int refdrv_buckling(void *h, int kmat, int gmat, int aux, int mode, double sigma
     A->applyBCs(c->assembler->getBcMap());
     b->pc->factor();
     b->sep->solve(NULL);
+  }
+  if (path_out) {
+    TacsScalar *a;
+    int n = b->path->getArray(&a);
+    memcpy(path_out, a, n * sizeof(double));
   }
   for (int i = 0; i < num_eigs; i++) {
     TacsScalar err;

@@ -214,9 +214,10 @@ class RefAssembler:
                  tol=1e-12, u0=None):
         eigs = np.zeros(num_eigs); errs = np.zeros(num_eigs)
         u0a = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        self.path = np.zeros((self.n_nodes, 6))
         lib().refdrv_buckling(self.h, C.c_int(kmat), C.c_int(gmat), C.c_int(aux), C.c_int(mode),
                               C.c_double(sigma), C.c_int(max_lanczos), C.c_int(num_eigs),
-                              C.c_double(tol), _p(u0a), _p(eigs), _p(errs))
+                              C.c_double(tol), _p(u0a), _p(eigs), _p(errs), _p(self.path))
         return eigs, errs
 
     def close(self):

@@ -1,0 +1,99 @@
+"""Generate the golden fixtures in tests/golden/ from the UNMODIFIED reference
+(oracle/_ref, built by oracle/Makefile from /root/reference).  Run in the build
+container:  python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own, so these are outputs
+of the reference itself on seeded inputs:
+  elements.npz : 12 random elements x {linear, nonlinear} x {natural, ref-axis}
+                 x {T=0 & no offset, T=10 & offset}: addJacobian res/K and, for the
+                 linear class, getMatType(G)
+  plate.npz, cylinder.npz : small assembled meshes (reference numbering): pattern,
+                 res, K, G of assembleJacobian / assembleMatType, with BCs
+  buckling.npz : lowest 6 buckling eigenvalues of a 40x20 cylinder
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import refdrv  # noqa: E402
+from helpers import random_elements  # noqa: E402
+
+a2ds = importlib.import_module("a2d-shells_b200")
+AXIS = np.array([0.3, 1.0, 0.2])
+
+
+def elements():
+    X, q = random_elements(12, seed=2024)
+    out = dict(X=X, q=q, axis=AXIS)
+    for kind in (0, 1):
+        for tr in (0, 1):
+            for ci, (T, off) in enumerate(((0.0, 0.0), (10.0, 0.3))):
+                p = refdrv.iso_props(kind=kind, temperature=T, t_offset=off)
+                Cs, eth, _ = refdrv.con_tables(p)
+                r, k, _ = refdrv.element_batch(p, 1, X.reshape(-1, 12), q.reshape(-1, 24),
+                                               transform=tr, axis=AXIS)
+                key = f"k{kind}_t{tr}_c{ci}"
+                out[key + "_res"] = r; out[key + "_K"] = k
+                out[key + "_Cs"] = Cs; out[key + "_eth"] = eth; out[key + "_T"] = T
+                if kind == 0:
+                    _, g, _ = refdrv.element_batch(p, 3, X.reshape(-1, 12), q.reshape(-1, 24),
+                                                   transform=tr, axis=AXIS)
+                    out[key + "_G"] = g
+    np.savez_compressed(os.path.join(HERE, "elements.npz"), **out)
+
+
+def mesh(name):
+    if name == "plate":
+        conn, X, bcn = a2ds.meshes.plate(7, 5, bump=2e-2)
+    else:
+        conn, X, bcn = a2ds.meshes.cylinder(12, 4)
+    n = len(X)
+    bc_vars = [list(range(6)) if i % 2 else [0, 1, 2] for i in range(len(bcn))]
+    bc_vals = [[-1e-5] + [0.0] * (len(v) - 1) for v in bc_vars]
+    props = refdrv.iso_props()
+    ra = refdrv.RefAssembler(conn, X, np.zeros(len(conn), dtype=np.int32), props[None], bcn,
+                             bc_vars, bc_vals)
+    u = np.zeros((n, 6))
+    u[ra.new_nodes] = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)
+    ra.set_state(u)
+    pm = ra.mat_create(0)
+    res = ra.assemble_jacobian(pm)
+    blk = ra.mat_block(pm, 0)
+    ra.assemble_mat_type(1, pm)
+    G = ra.mat_block(pm, 0)["A"]
+    res_only = ra.assemble_res()
+    nodes_b, vars_b, vals_b = ra.bcs()
+    Cs, eth, _ = refdrv.con_tables(props)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), conn=ra.conn(), X=ra.nodes(), u=u,
+                        bc_nodes=nodes_b, bc_vars=vars_b, bc_vals=vals_b, rowp=blk["rowp"],
+                        cols=blk["cols"], K=blk["A"], G=G, res=res, res_only=res_only, Cs=Cs,
+                        eth=eth, new_nodes=ra.new_nodes)
+    ra.close()
+
+
+def buckling():
+    """cylinder 40x20 under end shortening; the reference solves for the load path itself
+    (u0 = NULL) and runs Lanczos with the shipped example's settings (100 vectors, 50
+    eigenvalues, mechBuckling.cpp:136-138); shift 12 is close to the lowest cluster."""
+    conn, X, ends = a2ds.meshes.cylinder(40, 20)
+    bc_vars = [[0, 1, 2, 5]] * len(ends)
+    bc_vals = [[-1e-3 if i >= 40 else 0.0, 0.0, 0.0, 0.0] for i in range(len(ends))]
+    ra = refdrv.RefAssembler(conn, X, np.zeros(len(conn), dtype=np.int32),
+                             refdrv.iso_props()[None], ends, bc_vars, bc_vals)
+    km, gm, am = ra.mat_create(1), ra.mat_create(1), ra.mat_create(1)
+    eig, err = ra.buckling(km, gm, am, 0, sigma=12.0, num_eigs=50, max_lanczos=100, u0=None)
+    np.savez_compressed(os.path.join(HERE, "buckling.npz"), eig=eig[:8], err=err[:8],
+                        path=ra.path)
+    print("buckling eigenvalues", eig[:8], err[:8])
+    ra.close()
+
+
+if __name__ == "__main__":
+    elements(); mesh("plate"); mesh("cylinder"); buckling()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))

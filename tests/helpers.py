@@ -1,0 +1,74 @@
+"""Shared helpers for the parity tests."""
+import ctypes as C
+
+import numpy as np
+
+
+def relmax(a, b):
+    """norm-relative error max|a-b| / max|b| (SURVEY.md §7 hard part 2)"""
+    d = np.abs(np.asarray(a) - np.asarray(b)).max()
+    s = np.abs(np.asarray(b)).max()
+    return d / s if s > 0 else d
+
+
+def random_elements(n, seed, h_range=(-3, 0), state_range=(-6, -3), flat=False):
+    """n random distorted, curved, arbitrarily oriented quads with random states.
+    Returns X[n,4,3], q[n,4,6]."""
+    rng = np.random.default_rng(seed)
+    base = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], float)
+    X = np.zeros((n, 4, 3)); q = np.zeros((n, 4, 6))
+    for e in range(n):
+        h = 10.0 ** rng.uniform(*h_range)
+        pert = 0.2 * rng.uniform(-1, 1, (4, 3))
+        if flat:
+            pert[:, 2] = 0.0
+        Xe = h * (base + pert)
+        R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        X[e] = Xe @ R.T + rng.uniform(-1, 1, 3)
+        sc = 10.0 ** rng.uniform(*state_range)
+        q[e, :, :3] = sc * h * rng.uniform(-1, 1, (4, 3))
+        q[e, :, 3:] = sc * rng.uniform(-1, 1, (4, 3))
+    return X, q
+
+
+def emul_element(L, Cs, eth, T, model, transform, axis, X, q, want_g):
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    res = np.zeros(24); K = np.zeros(576); G = np.zeros(576)
+    ax = np.asarray(axis, float)
+    ax = np.ascontiguousarray(ax / np.linalg.norm(ax))
+    Cs = np.ascontiguousarray(Cs, dtype=np.float64); eth = np.ascontiguousarray(eth, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64).ravel()
+    q = np.ascontiguousarray(q, dtype=np.float64).ravel()
+    L.emul_element(p(Cs), p(eth), C.c_double(T), C.c_int(model), C.c_int(transform), p(ax), p(X),
+                   p(q), C.c_int(want_g), p(res), p(K), p(G))
+    return res, K.reshape(24, 24), G.reshape(24, 24)
+
+
+def element_blocks(A, rowp, cols, nodes):
+    """extract the 24x24 of one element (4 node ids) from BCSR values A[nnz,6,6]"""
+    out = np.zeros((24, 24))
+    for i, r in enumerate(nodes):
+        row = cols[rowp[r]:rowp[r + 1]]
+        for j, c in enumerate(nodes):
+            k = rowp[r] + int(np.searchsorted(row, c))
+            assert cols[k] == c
+            out[6 * i:6 * i + 6, 6 * j:6 * j + 6] = A[k]
+    return out
+
+
+def bcsr_to_dense(A, rowp, cols, n):
+    M = np.zeros((6 * n, 6 * n))
+    for r in range(n):
+        for k in range(rowp[r], rowp[r + 1]):
+            c = cols[k]
+            M[6 * r:6 * r + 6, 6 * c:6 * c + 6] = A[k]
+    return M
+
+
+def bcsr_matvec(A, rowp, cols, x):
+    """y = A x for x[n,6] without forming the dense matrix"""
+    n = len(rowp) - 1
+    rows = np.repeat(np.arange(n), np.diff(rowp))
+    y = np.zeros((n, 6))
+    np.add.at(y, rows, np.einsum("kij,kj->ki", A, x[cols]))
+    return y

@@ -25,11 +25,20 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   Want w;
   w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1;
   for (int lane = 0; lane < 32; lane++) phase_node(c, s, lane & 3);
-  static QpGeom g[32];
-  for (int lane = 0; lane < 32; lane++) phase_columns(c, s, lane, w, g[lane]);
-  for (int lane = 0; lane < 32; lane++) phase_stress(c, s, lane, w, g[lane]);
-  for (int a = 0; a < 24; a++)
-    res[a] = s.rpart[0][a] + s.rpart[1][a] + s.rpart[2][a] + s.rpart[3][a];
+  static double ep[32][9], qw[32], na[32][2], nb[32][2];
+  for (int lane = 0; lane < 32; lane++) lane_columns(c, s, lane, w, ep[lane], qw[lane], na[lane], nb[lane]);
+  memset(res, 0, 24 * sizeof(double));
+  for (int lane = 0; lane < 32; lane++) {
+    int qp = lane >> 3;
+    double e[9], r3[3];
+    for (int r = 0; r < 9; r++) {
+      e[r] = 0.0;
+      for (int l = 0; l < 8; l++) e[r] += ep[8 * qp + l][r];
+    }
+    lane_stress(c, s, lane, w, e, qw[lane], na[lane], nb[lane], r3);
+    int col = 6 * ((lane >> 1) & 3) + 3 * (lane & 1);
+    for (int k = 0; k < 3; k++) res[col + k] += r3[k];
+  }
   double geo[576];
   memset(geo, 0, sizeof(geo));
   for (int p = 0; p < 8; p++)

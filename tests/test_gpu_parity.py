@@ -1,0 +1,280 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/a2ds.h), against
+the oracle (oracle/shell_oracle.c) and — when oracle/_ref is present — against the
+unmodified reference itself, on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star), all norm-relative max|d| / max|ref|:
+  residual 1e-12, matrix entries 1e-10, sparsity pattern bit-exact,
+  thermal geometric stiffness at the reference's own finite-difference noise (1e-6).
+"""
+import numpy as np
+import pytest
+
+from conftest import has_gpu
+from helpers import bcsr_matvec, element_blocks, random_elements, relmax
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_gpu(), reason="no CUDA device")]
+
+RES_TOL = 1e-12
+MAT_TOL = 1e-10
+THERMAL_G_TOL = 1e-6
+
+
+def _props(ref_or_none, a2ds, kind=0, T=0.0, t_offset=0.0):
+    Cs, eth = a2ds.iso_shell_tables(t_offset=t_offset)
+    return Cs, eth
+
+
+def _disconnected(a2ds, X, q, Cs, eth, T, kind, transform, axis):
+    """every element gets its own 4 nodes; returns assembler + matrices"""
+    n = X.shape[0]
+    conn = np.arange(4 * n, dtype=np.int32).reshape(n, 4)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, 4 * n)
+    asm.set_nodes(X.reshape(-1, 3))
+    asm.set_components(Cs[None], eth[None], temperature=[T], elem_class=[kind],
+                       transform=transform, ref_axis=axis)
+    asm.set_state(q.reshape(-1, 6))
+    return asm, conn
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("transform", [0, 1])
+@pytest.mark.parametrize("T,t_offset", [(0.0, 0.0), (10.0, 0.3)])
+def test_element_level_vs_oracle(a2ds, orc, kind, transform, T, t_offset):
+    n = 64
+    X, q = random_elements(n, seed=100 + 10 * kind + transform)
+    Cs, eth = a2ds.iso_shell_tables(t_offset=t_offset)
+    axis = np.array([0.3, 1.0, 0.2])
+    asm, conn = _disconnected(a2ds, X, q, Cs, eth, T, kind, transform, axis)
+    kmat = asm.create_mat(); gmat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(kmat)
+    res = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
+    K = asm.mat_values(kmat)
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gmat)
+    G = asm.mat_values(gmat)
+    comp = orc.make_comp(kind, Cs, eth, (0, 0, 0), T, transform, axis)
+    worst = [0.0, 0.0, 0.0]
+    for e in range(n):
+        r_o, k_o = orc.jacobian(comp, X[e].ravel(), q[e].ravel())
+        g_o = orc.mat_type(comp, 1, X[e].ravel(), q[e].ravel())
+        worst[0] = max(worst[0], relmax(res[conn[e]].ravel(), r_o))
+        worst[1] = max(worst[1], relmax(element_blocks(K, rowp, cols, conn[e]), k_o))
+        if not (kind == 1 and T != 0.0):  # nonlinear class + temperature: reference quirk, see oracle
+            worst[2] = max(worst[2], relmax(element_blocks(G, rowp, cols, conn[e]), g_o))
+    assert worst[0] < RES_TOL, worst
+    assert worst[1] < MAT_TOL, worst
+    assert worst[2] < (THERMAL_G_TOL if T != 0.0 else MAT_TOL), worst
+    asm.close()
+
+
+def test_element_level_vs_reference(a2ds, ref):
+    n = 48
+    X, q = random_elements(n, seed=7)
+    axis = np.array([0.3, 1.0, 0.2])
+    for kind in (0, 1):
+        for transform in (0, 1):
+            p = ref.iso_props(kind=kind, temperature=0.0, t_offset=0.1)
+            Cs, eth, _ = ref.con_tables(p)
+            asm, conn = _disconnected(a2ds, X, q, Cs, eth, 0.0, kind, transform, axis)
+            kmat = asm.create_mat(); gmat = asm.create_mat()
+            rowp, cols = asm.mat_pattern(kmat)
+            res = asm.assembleAll(kmat, gmat)
+            K = asm.mat_values(kmat); G = asm.mat_values(gmat)
+            r_ref, k_ref, _ = ref.element_batch(p, 1, X.reshape(n, 12), q.reshape(n, 24),
+                                                transform=transform, axis=axis)
+            _, g_ref, _ = ref.element_batch(p, 3, X.reshape(n, 12), q.reshape(n, 24),
+                                            transform=transform, axis=axis)
+            for e in range(n):
+                assert relmax(res[conn[e]].ravel(), r_ref[e]) < RES_TOL
+                assert relmax(element_blocks(K, rowp, cols, conn[e]), k_ref[e]) < MAT_TOL
+                assert relmax(element_blocks(G, rowp, cols, conn[e]), g_ref[e]) < MAT_TOL
+            asm.close()
+
+
+def _mesh_case(a2ds, name):
+    if name == "plate":
+        conn, X, bcn = a2ds.meshes.plate(14, 9, bump=2e-2)
+    else:
+        conn, X, bcn = a2ds.meshes.cylinder(24, 7)
+    return conn, X, bcn
+
+
+@pytest.mark.parametrize("name", ["plate", "cylinder"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_assembly_vs_oracle(a2ds, orc, name, mode):
+    conn, X, bcn = _mesh_case(a2ds, name)
+    n = len(X)
+    u = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)
+    u[:, 3:] *= 10.0
+    Cs, eth = a2ds.iso_shell_tables()
+    bc_vars = np.full(len(bcn), 63, dtype=np.int32); bc_vars[::2] = 0b000111
+    bc_vals = np.zeros((len(bcn), 6)); bc_vals[:, 0] = -1e-5
+    asm = a2ds.Assembler(0)
+    asm.set_scatter_mode(mode)
+    asm.set_mesh(conn, n)
+    asm.set_nodes(X)
+    asm.set_components(Cs[None], eth[None])
+    asm.set_bcs(bcn, bc_vars, bc_vals)
+    asm.set_state(u)
+    kmat = asm.create_mat(); gmat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(kmat)
+    rowp_o, cols_o = orc.pattern(n, conn)
+    assert np.array_equal(rowp, rowp_o) and np.array_equal(cols, cols_o)
+    comp = orc.make_comp(0, Cs, eth)
+    ec = np.zeros(len(conn), dtype=np.int32)
+    r_o, k_o = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    _, g_o = orc.assemble(3, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    r0_o, _ = orc.assemble(0, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    # the three reference entry points
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gmat)
+    assert relmax(asm.mat_values(gmat), g_o) < MAT_TOL
+    asm.assembleMatType(a2ds.STIFFNESS_MATRIX, gmat)
+    assert relmax(asm.mat_values(gmat), k_o) < MAT_TOL
+    assert relmax(asm.assembleRes(), r0_o) < RES_TOL
+    # the fused pass gives the same three results
+    r = asm.assembleAll(kmat, gmat)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL
+    assert relmax(asm.mat_values(gmat), g_o) < MAT_TOL
+    # alpha scales the tangent only
+    asm.assembleJacobian(2.5, 0.0, 0.0, kmat)
+    k25 = asm.mat_values(kmat)
+    _, k25_o = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals, alpha=2.5)
+    assert relmax(k25, k25_o) < MAT_TOL
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["plate", "cylinder"])
+def test_assembly_vs_reference_schur_and_parallel(a2ds, ref, name):
+    """drop-in style: connectivity, nodes, BCs and BOTH matrix patterns are taken from the
+    reference assembler; values must match block for block."""
+    conn, X, bcn = _mesh_case(a2ds, name)
+    n = len(X)
+    props = ref.iso_props()
+    bc_vars = [list(range(6)) if i % 2 else [0, 1, 2] for i in range(len(bcn))]
+    bc_vals = [[-1e-5] + [0.0] * (len(v) - 1) for v in bc_vars]
+    ra = ref.RefAssembler(conn, X, np.zeros(len(conn), dtype=np.int32), props[None], bcn, bc_vars,
+                          bc_vals)
+    u = np.zeros((n, 6))
+    u[ra.new_nodes] = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)  # keyed on original ids
+    ra.set_state(u)
+    Cs, eth, _ = ref.con_tables(props)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(ra.conn(), n)
+    asm.set_nodes(ra.nodes())
+    asm.set_components(Cs[None], eth[None])
+    nodes_b, vars_b, vals_b = ra.bcs()
+    asm.set_bcs(nodes_b, vars_b, vals_b)
+    asm.set_state(u)
+    # ParallelMat flavour: our own natural pattern must equal the reference's, bit for bit
+    pm = ra.mat_create(0)
+    aloc = ra.mat_block(pm, 0, values=False)
+    kmat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(kmat)
+    assert rowp.tobytes() == aloc["rowp"].tobytes() and cols.tobytes() == aloc["cols"].tobytes()
+    r_ref = ra.assemble_jacobian(pm)
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
+    assert relmax(r, r_ref) < RES_TOL
+    assert relmax(asm.mat_values(kmat), ra.mat_block(pm, 0)["A"]) < MAT_TOL
+    # SchurMat flavour: AMD-permuted B block, pattern and row map from the host matrix
+    sm = ra.mat_create(1)
+    B = ra.mat_block(sm, 0, values=False)
+    bidx = ra.schur_index(sm, 0)
+    rmap = np.full(n, -1, dtype=np.int32); rmap[bidx] = np.arange(len(bidx), dtype=np.int32)
+    smat = asm.create_mat_from_pattern([dict(nrows=B["nrows"], rowp=B["rowp"], cols=B["cols"],
+                                             row_map=rmap, col_map=rmap, ident=1)])
+    for typ, ours in ((0, a2ds.STIFFNESS_MATRIX), (1, a2ds.GEOMETRIC_STIFFNESS_MATRIX)):
+        ra.assemble_mat_type(typ, sm)
+        asm.assembleMatType(ours, smat)
+        assert relmax(asm.mat_values(smat), ra.mat_block(sm, 0)["A"]) < MAT_TOL
+    asm.close(); ra.close()
+
+
+def test_deterministic_mode_is_bit_reproducible(a2ds):
+    conn, X, bcn = a2ds.meshes.cylinder(64, 40)
+    n = len(X)
+    u = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)
+    Cs, eth = a2ds.iso_shell_tables()
+    outs = []
+    for rep in range(3):
+        asm = a2ds.Assembler(0)
+        asm.set_scatter_mode(a2ds.SCATTER_COLORED)
+        asm.set_mesh(conn, n); asm.set_nodes(X); asm.set_components(Cs[None], eth[None])
+        asm.set_state(u)
+        k = asm.create_mat(); g = asm.create_mat()
+        r = asm.assembleAll(k, g)
+        outs.append((r.tobytes(), asm.mat_values(k).tobytes(), asm.mat_values(g).tobytes()))
+        asm.close()
+    assert outs[0] == outs[1] == outs[2]
+
+
+def test_properties_at_size(a2ds):
+    """size-independent properties on a mesh far beyond what the oracle can check:
+    K symmetric (before BCs), K u = r for the linear element, G linear in u."""
+    nx = 300
+    conn, X, _ = a2ds.meshes.plate(nx, nx, bump=1e-2)
+    n = len(X)
+    u = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)
+    Cs, eth = a2ds.iso_shell_tables()
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n); asm.set_nodes(X); asm.set_components(Cs[None], eth[None])
+    asm.set_state(u)
+    k = asm.create_mat(); g = asm.create_mat()
+    rowp, cols = asm.mat_pattern(k)
+    r = asm.assembleAll(k, g)
+    K = asm.mat_values(k); G = asm.mat_values(g)
+    assert relmax(bcsr_matvec(K, rowp, cols, u), r) < 1e-11
+    # symmetry through random probes: x^T K y == y^T K x
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(n, 6)); y = rng.normal(size=(n, 6))
+    for M in (K, G):
+        a = np.sum(x * bcsr_matvec(M, rowp, cols, y)); b = np.sum(y * bcsr_matvec(M, rowp, cols, x))
+        assert abs(a - b) < 1e-10 * (abs(a) + abs(b) + 1e-300) + 1e-9 * np.abs(M).max()
+    asm.set_state(2.0 * u)
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, k)
+    assert relmax(asm.mat_values(k), 2.0 * G) < 1e-12
+    asm.close()
+
+
+def test_buckling_eigenvalues_with_reference_solver(a2ds, ref):
+    """K and G assembled on the GPU, handed to the reference's TACSSchurPc/SEP stack, against
+    the reference doing everything itself: lowest eigenvalues within 1e-8 (north_star).
+    Flow of TACSLinearBuckling::solve (src/TACSBuckling.cpp:197-277): K at zero state,
+    load path = -K^-1 r (the reference's own static solve), G about the path."""
+    import os
+    conn, X, ends = a2ds.meshes.cylinder(40, 20)
+    n = len(X)
+    bc_vars = [[0, 1, 2, 5]] * len(ends)
+    bc_vals = [[-1e-3 if i >= 40 else 0.0, 0.0, 0.0, 0.0] for i in range(len(ends))]
+    props = ref.iso_props()
+    ra = ref.RefAssembler(conn, X, np.zeros(len(conn), dtype=np.int32), props[None], ends,
+                          bc_vars, bc_vals)
+    km, gm, am = ra.mat_create(1), ra.mat_create(1), ra.mat_create(1)
+    kw = dict(sigma=12.0, num_eigs=50, max_lanczos=100)
+    eig_ref, err_ref = ra.buckling(km, gm, am, 0, u0=None, **kw)
+    path = ra.path.copy()  # after setBCs, i.e. the state G is assembled about
+    assert np.all(err_ref[:6] < 1e-6)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "buckling.npz"))
+    assert np.allclose(eig_ref[:6], gold["eig"][:6], rtol=1e-9, atol=0)
+    # GPU assembly with the reference's numbering, patterns and BCs
+    Cs, eth, _ = ref.con_tables(props)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(ra.conn(), n); asm.set_nodes(ra.nodes()); asm.set_components(Cs[None], eth[None])
+    nodes_b, vars_b, vals_b = ra.bcs()
+    asm.set_bcs(nodes_b, vars_b, vals_b)
+    B = ra.mat_block(km, 0, values=False)
+    bidx = ra.schur_index(km, 0)
+    rmap = np.full(n, -1, dtype=np.int32); rmap[bidx] = np.arange(len(bidx), dtype=np.int32)
+    blk = dict(nrows=B["nrows"], rowp=B["rowp"], cols=B["cols"], row_map=rmap, col_map=rmap, ident=1)
+    kd = asm.create_mat_from_pattern([blk]); gd = asm.create_mat_from_pattern([blk])
+    asm.set_state(np.zeros((n, 6)))
+    asm.assembleMatType(a2ds.STIFFNESS_MATRIX, kd)
+    asm.set_state(path)
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gd)
+    ra.mat_set(km, 0, asm.mat_values(kd)); ra.mat_set(gm, 0, asm.mat_values(gd))
+    eig_gpu, _ = ra.buckling(km, gm, am, 1, u0=path, **kw)
+    assert np.all(np.abs(eig_gpu[:6] - eig_ref[:6]) <= 1e-8 * np.abs(eig_ref[:6])), (eig_gpu[:6], eig_ref[:6])
+    asm.close(); ra.close()

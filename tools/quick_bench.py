@@ -1,0 +1,27 @@
+"""quick device-time probe of the assembly kernels (development aid, not bench.py)"""
+import importlib, sys, time
+import numpy as np
+sys.path.insert(0, ".")
+a2ds = importlib.import_module("a2d-shells_b200")
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 500
+conn, X, bcn = a2ds.meshes.plate(nx, nx, bump=1e-3)
+n = len(X)
+u = a2ds.meshes.seeded_state(np.arange(n), 1e-5)
+Cs, eth = a2ds.iso_shell_tables()
+asm = a2ds.Assembler(0)
+asm.set_mesh(conn, n); asm.set_nodes(X); asm.set_components(Cs[None], eth[None]); asm.set_state(u)
+asm.set_bcs(bcn, 63)
+t0 = time.time(); k = asm.create_mat(); g = asm.create_mat(); print("mat create s", time.time() - t0)
+ne = len(conn)
+for name, fn in (("res", lambda: asm.assembleRes(False)),
+                 ("jac(res+K)", lambda: asm.assembleJacobian(1.0, 0, 0, k, False)),
+                 ("K", lambda: asm.assembleMatType(0, k)),
+                 ("G", lambda: asm.assembleMatType(1, g)),
+                 ("all(res+K+G)", lambda: asm.assembleAll(k, g, False))):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(5):
+        fn(); ts.append(asm.last_timing()[0])
+    ms = np.median(ts)
+    print(f"{name:14s} {ms:8.3f} ms  {ne / ms * 1e-3:8.2f} M elem/s  launches {asm.last_timing()[1]}")
