@@ -25,6 +25,7 @@ SYMBOLS = [
     "a2ds_assemble_mat_type", "a2ds_assemble_all", "a2ds_res_dev", "a2ds_state_dev",
     "a2ds_comm_unique_id", "a2ds_comm_init", "a2ds_set_halo", "a2ds_halo_forward",
     "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
+    "a2ds_last_kernel_ms", "a2ds_region_begin", "a2ds_region_end",
 ]
 
 _LIB = None
@@ -273,6 +274,19 @@ class Assembler:
         ms = C.c_float(); n = C.c_int()
         self._chk(self.L.a2ds_last_timing(self.ctx, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._chk(self.L.a2ds_last_kernel_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def region_begin(self):
+        self._chk(self.L.a2ds_region_begin(self.ctx))
+
+    def region_end(self):
+        ms = C.c_float()
+        self._chk(self.L.a2ds_region_end(self.ctx, C.byref(ms)))
+        return ms.value
 
     # -- multi-GPU ---------------------------------------------------------------------
     def comm_unique_id(self):

@@ -335,7 +335,7 @@ struct MatrixRec {
 struct a2ds_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   int n_sm = 0;
   int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
   int *conn = nullptr, *elem_comp = nullptr;
@@ -392,6 +392,10 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreate(&c->evk0));
+  CU(cudaEventCreate(&c->evk1));
+  CU(cudaEventCreate(&c->evr0));
+  CU(cudaEventCreate(&c->evr1));
   *out = c;
   return 0;
 }
@@ -417,7 +421,8 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   cudaFree(c->comps); cudaFree(c->bc_nodes); cudaFree(c->bc_vars); cudaFree(c->bc_vals);
   cudaFree(c->send_nodes); cudaFree(c->recv_nodes); cudaFree(c->send_buf); cudaFree(c->recv_buf);
   if (c->comm) ncclCommDestroy(c->comm);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0);
+  cudaEventDestroy(c->evk1); cudaEventDestroy(c->evr0); cudaEventDestroy(c->evr1);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -881,6 +886,7 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
   if (KM) { p.Kval = c->mats[kmat].A; p.Koff = c->mats[kmat].off; }
   if (GM) { p.Gval = c->mats[gmat].A; p.Goff = c->mats[gmat].off; }
 
+  CU(cudaEventRecord(c->evk0, c->stream));
   for (int col = 0; col < c->n_colors; col++) {
     for (int cls = 0; cls < 2; cls++) {
       p.n_list = c->list_len[cls][col];
@@ -916,6 +922,7 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
       if (rc) return rc;
     }
   }
+  CU(cudaEventRecord(c->evk1, c->stream));
   // ghost residual contributions -> owners (TACSBVec::beginSetValues/endSetValues, ADD)
   if (RES && halo_exchange(c, c->res, true)) return 1;
   if (RES && c->n_bc) {
@@ -972,5 +979,26 @@ extern "C" int a2ds_last_timing(a2ds_ctx *c, float *ms, int *launches) {
   CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   if (ms) *ms = c->last_ms;
   if (launches) *launches = c->last_launches;
+  return 0;
+}
+
+extern "C" int a2ds_last_kernel_ms(a2ds_ctx *c, float *ms) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->evk1));
+  CU(cudaEventElapsedTime(ms, c->evk0, c->evk1));
+  return 0;
+}
+
+extern "C" int a2ds_region_begin(a2ds_ctx *c) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->evr0, c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_region_end(a2ds_ctx *c, float *ms) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->evr1, c->stream));
+  CU(cudaEventSynchronize(c->evr1));
+  CU(cudaEventElapsedTime(ms, c->evr0, c->evr1));
   return 0;
 }

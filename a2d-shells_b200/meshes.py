@@ -59,9 +59,50 @@ def seeded_state(global_node_ids, scale=1e-5, seed=12345):
     return scale * (2.0 * u01 - 1.0)
 
 
-def slab_partition(n_slabs, conn, X, axis_index, n_per_layer):
-    """Not used by the single-GPU path; see partition_structured()."""
-    raise NotImplementedError
+def plate_slab(rank, n_ranks, nx, ny, lx=1.0, ly=1.0, bump=1e-3):
+    """Rank `rank`'s slab of a plate of nx x (n_ranks*ny) elements partitioned by element
+    rows, built directly (no global mesh): the weak-scaling workload of bench.py.
+    Ownership is TACSCreator's first-touch rule (src/TACSCreator.cpp:1156-1205): the
+    node row shared by slabs r-1 and r belongs to r-1, so rank r > 0 sees it as ghosts.
+    Local numbering: owned nodes in global order, then ghosts.  Returns a dict with
+    conn, X, n_owned, glob (global node ids), bc_nodes (edge i = 0), peers, send_lists,
+    recv_lists (local indices)."""
+    npr = nx + 1
+    j0 = rank * ny
+    first_owned_row = j0 if rank == 0 else j0 + 1
+    owned_rows = np.arange(first_owned_row, j0 + ny + 1)
+    n_owned = len(owned_rows) * npr
+    glob_owned = (owned_rows[:, None] * npr + np.arange(npr)[None, :]).ravel()
+    glob_ghost = (j0 * npr + np.arange(npr)) if rank > 0 else np.zeros(0, dtype=np.int64)
+    glob = np.concatenate([glob_owned, glob_ghost]).astype(np.int64)
+
+    def local(row, i):
+        row = np.asarray(row); i = np.asarray(i)
+        own = (row - first_owned_row) * npr + i
+        return np.where(row >= first_owned_row, own, n_owned + i)
+
+    ei, ej = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    ei = ei.ravel(); ej = ej.ravel() + j0
+    conn = np.stack([local(ej, ei), local(ej, ei + 1), local(ej + 1, ei), local(ej + 1, ei + 1)],
+                    axis=1).astype(np.int32)
+    gi = glob % npr; gj = glob // npr
+    Ly = ly * n_ranks
+    x = gi * (lx / nx); y = gj * (Ly / (ny * n_ranks))
+    z = bump * np.sin(2 * np.pi * x / lx) * np.sin(2 * np.pi * y / ly)
+    X = np.stack([x, y, z], axis=1)
+    bc_nodes = np.nonzero(gi[:n_owned] == 0)[0].astype(np.int32)
+    peers, send_lists, recv_lists = [], [], []
+    if rank > 0:      # ghost row comes from the slab below; nothing is sent to it
+        peers.append(rank - 1)
+        send_lists.append(np.zeros(0, dtype=np.int32))
+        recv_lists.append((n_owned + np.arange(npr)).astype(np.int32))
+    if rank < n_ranks - 1:  # our top row is the next slab's ghost row
+        peers.append(rank + 1)
+        send_lists.append(local(np.full(npr, j0 + ny), np.arange(npr)).astype(np.int32))
+        recv_lists.append(np.zeros(0, dtype=np.int32))
+    return dict(conn=conn, X=X, n_owned=n_owned, n_nodes=len(glob), glob=glob, bc_nodes=bc_nodes,
+                peers=np.asarray(peers, dtype=np.int32), send_lists=send_lists,
+                recv_lists=recv_lists)
 
 
 def partition_rows(conn, n_nodes, elem_rank):

@@ -178,6 +178,13 @@ int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *col
  * device time of the last assemble call in milliseconds (CUDA events on the context
  * stream) and the number of kernels it launched */
 int a2ds_last_timing(a2ds_ctx *ctx, float *ms, int *launches);
+/* device time of the element kernel(s) alone in the last assemble call (the memsets,
+ * halo and BC kernels excluded) */
+int a2ds_last_kernel_ms(a2ds_ctx *ctx, float *ms);
+/* bracket an arbitrary region of calls with CUDA events on the context stream;
+ * a2ds_region_end waits for the region to finish and returns its device time */
+int a2ds_region_begin(a2ds_ctx *ctx);
+int a2ds_region_end(a2ds_ctx *ctx, float *ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,104 @@
+"""Host-side logic and the C-ABI surface.  CPU only: no compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "a2ds.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(a2ds_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(a2ds):
+    L = a2ds.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(a2ds.capi.SYMBOLS) == declared
+    assert b"sm_100a" in L.a2ds_version()
+
+
+def test_no_gpu_means_loud_failure(a2ds):
+    from conftest import has_gpu
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(a2ds.A2dsError, match="no CUDA device"):
+        a2ds.Assembler(0)
+
+
+def test_product_does_not_reference_the_oracle():
+    """the product tree must never import, link or execute anything under oracle/"""
+    pkg = os.path.join(ROOT, "a2d-shells_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and False, (dirpath, f)
+    hdr = open(os.path.join(ROOT, "include", "a2ds.h")).read()
+    assert "oracle" not in hdr.lower()
+
+
+def test_host_pattern_matches_oracle_pattern(a2ds, orc):
+    for conn, X, _ in (a2ds.meshes.plate(9, 6), a2ds.meshes.cylinder(10, 5)):
+        rp, cl = a2ds.host_pattern(len(X), conn)
+        rpo, clo = orc.pattern(len(X), conn)
+        assert rp.tobytes() == rpo.tobytes() and cl.tobytes() == clo.tobytes()
+    rp, cl = a2ds.host_pattern(4, np.zeros((0, 4), dtype=np.int32))
+    assert rp.tolist() == [0] * 5 and len(cl) == 0
+
+
+def test_host_pattern_matches_golden(a2ds):
+    for name in ("plate", "cylinder"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        rp, cl = a2ds.host_pattern(len(g["X"]), g["conn"])
+        assert rp.tobytes() == g["rowp"].tobytes() and cl.tobytes() == g["cols"].tobytes()
+
+
+def test_coloring_is_valid(a2ds):
+    for conn, X, _ in (a2ds.meshes.plate(11, 7), a2ds.meshes.cylinder(9, 4),
+                       a2ds.meshes.cylinder(8, 3)):
+        color, nc = a2ds.host_color_elements(len(X), conn)
+        assert color.min() == 0 and color.max() == nc - 1 and nc <= 9
+        for c in range(nc):
+            nodes = conn[color == c].ravel()
+            assert len(nodes) == len(np.unique(nodes))  # no node shared inside a colour
+
+
+def test_structured_plate_needs_four_colors(a2ds):
+    conn, X, _ = a2ds.meshes.plate(20, 20)
+    _, nc = a2ds.host_color_elements(len(X), conn)
+    assert nc == 4
+
+
+def test_seeded_state_is_partition_independent(a2ds):
+    ids = np.arange(1000)
+    u = a2ds.meshes.seeded_state(ids, 1e-5)
+    perm = np.random.default_rng(0).permutation(1000)
+    assert np.array_equal(a2ds.meshes.seeded_state(ids[perm], 1e-5), u[perm])
+    assert np.abs(u).max() <= 1e-5 and abs(u.mean()) < 1e-6
+    assert not np.array_equal(u, a2ds.meshes.seeded_state(ids, 1e-5, seed=1))
+
+
+def test_partition_ownership_follows_first_touch(a2ds):
+    conn, X, _ = a2ds.meshes.cylinder(12, 8)
+    ne = len(conn)
+    elem_rank = (np.arange(ne) * 4) // ne
+    parts = a2ds.meshes.partition_rows(conn, len(X), elem_rank)
+    owned_all = np.concatenate([p["owned"] for p in parts])
+    assert len(owned_all) == len(X) and len(np.unique(owned_all)) == len(X)
+    for p in parts:
+        glob = p["glob"]
+        assert np.array_equal(glob[p["conn_local"]], conn[p["elems"]])
+        # halo plans pair up: what r sends to q is what q receives from r
+        for k, q in enumerate(p["peers"]):
+            other = parts[q]
+            kk = list(other["peers"]).index(p["rank"])
+            assert np.array_equal(glob[p["send_lists"][k]], other["glob"][other["recv_lists"][kk]])
+            assert np.all(p["send_lists"][k] < len(p["owned"]))
+            assert np.all(p["recv_lists"][k] >= len(p["owned"]))

@@ -1,0 +1,65 @@
+"""The kernel's per-lane arithmetic (a2d-shells_b200/csrc/mitc4_math.h) stepped on the host
+(tests/host_emul.cpp, compiled with FMA contraction like nvcc) against the golden
+fixtures and the oracle.  CPU only — the GPU tests check the same code on the device."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import emul_element, random_elements, relmax
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("tr", [0, 1])
+@pytest.mark.parametrize("ci", [0, 1])
+def test_kernel_math_against_golden(emul, kind, tr, ci):
+    g = np.load(os.path.join(GOLD, "elements.npz"))
+    key = f"k{kind}_t{tr}_c{ci}"
+    T = float(g[key + "_T"])
+    for e in range(g["X"].shape[0]):
+        r, K, G = emul_element(emul, g[key + "_Cs"], g[key + "_eth"], T, kind, tr, g["axis"],
+                               g["X"][e], g["q"][e], 1 if kind == 0 else 0)
+        assert relmax(r, g[key + "_res"][e]) < 1e-12      # north_star residual tolerance
+        assert relmax(K, g[key + "_K"][e]) < 1e-10        # north_star matrix tolerance
+        if kind == 0:
+            assert relmax(G, g[key + "_G"][e]) < (1e-10 if T == 0.0 else 1e-6)
+            assert np.abs(G - G.T).max() <= 1e-13 * np.abs(G).max()
+
+
+def test_kernel_math_against_oracle_many(emul, orc, a2ds):
+    """400 random elements: tight agreement with the oracle (same exact-derivative
+    definition), including the residual whose rounding follows the reference's order"""
+    X, q = random_elements(400, seed=11)
+    axis = np.array([0.3, 1.0, 0.2])
+    Cs, eth = a2ds.iso_shell_tables(t_offset=0.25)
+    for kind in (0, 1):
+        for tr in (0, 1):
+            comp = orc.make_comp(kind, Cs, eth, (0, 0, 0), 0.0, tr, axis)
+            worst = [0.0, 0.0]
+            for e in range(X.shape[0]):
+                r, K, _ = emul_element(emul, Cs, eth, 0.0, kind, tr, axis, X[e], q[e], 0)
+                ro, ko = orc.jacobian(comp, X[e].ravel(), q[e].ravel())
+                worst[0] = max(worst[0], relmax(r, ro)); worst[1] = max(worst[1], relmax(K, ko))
+            assert worst[0] < 1e-12 and worst[1] < 1e-11, worst  # badly conditioned quads included
+
+
+def test_geometric_stiffness_is_exact_linear_part(emul, orc, a2ds):
+    """our G is the linear-in-state part of the nonlinear tangent:
+    G(u) = 1/2 (K_nl(u) - K_nl(-u)) exactly, where the reference takes a noisy difference"""
+    X, q = random_elements(20, seed=5, state_range=(-4, -3))
+    Cs, eth = a2ds.iso_shell_tables()
+    comp_nl = orc.make_comp(1, Cs, eth)
+    for e in range(X.shape[0]):
+        _, _, G = emul_element(emul, Cs, eth, 0.0, 0, 0, (1, 0, 0), X[e], q[e], 1)
+        kp = orc.mat_type(comp_nl, 0, X[e].ravel(), q[e].ravel())
+        km = orc.mat_type(comp_nl, 0, X[e].ravel(), -q[e].ravel())
+        assert relmax(G, 0.5 * (kp - km)) < 1e-10
+
+
+def test_iso_tables_match_reference(a2ds, ref):
+    for off in (0.0, 0.3):
+        Cs, eth = a2ds.iso_shell_tables(t_offset=off)
+        Cr, er, _ = ref.con_tables(ref.iso_props(t_offset=off))
+        assert relmax(Cs, Cr) < 1e-15 and np.array_equal(eth, er)

@@ -1,0 +1,99 @@
+"""The oracle (oracle/shell_oracle.c) against the golden fixtures generated from the
+unmodified reference (tests/golden/make_golden.py) and, where oracle/_ref is present,
+against the reference itself.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import random_elements, relmax
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cases():
+    for kind in (0, 1):
+        for tr in (0, 1):
+            for ci in (0, 1):
+                yield kind, tr, ci
+
+
+@pytest.mark.parametrize("kind,tr,ci", list(_cases()))
+def test_elements_against_golden(orc, kind, tr, ci):
+    g = np.load(os.path.join(GOLD, "elements.npz"))
+    key = f"k{kind}_t{tr}_c{ci}"
+    T = float(g[key + "_T"])
+    comp = orc.make_comp(kind, g[key + "_Cs"], g[key + "_eth"], (0, 0, 0), T, tr, g["axis"])
+    for e in range(g["X"].shape[0]):
+        X = g["X"][e].ravel(); q = g["q"][e].ravel()
+        r, k = orc.jacobian(comp, X, q)
+        assert relmax(r, g[key + "_res"][e]) < 1e-13
+        assert relmax(k, g[key + "_K"][e]) < 1e-13
+        assert relmax(orc.residual(comp, X, q), g[key + "_res"][e]) < 1e-13
+        assert relmax(orc.mat_type(comp, 0, X, q), g[key + "_K"][e]) < 1e-13
+        if kind == 0:
+            # G is a finite difference in the reference: agreement is limited by its
+            # cancellation noise (1e-12 at T = 0, ~1e-7 with a temperature)
+            tol = 1e-10 if T == 0.0 else 1e-6
+            assert relmax(orc.mat_type(comp, 1, X, q), g[key + "_G"][e]) < tol
+
+
+@pytest.mark.parametrize("name", ["plate", "cylinder"])
+def test_assembly_against_golden(orc, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    conn, X, u = g["conn"], g["X"], g["u"]
+    n = len(X)
+    rowp, cols = orc.pattern(n, conn)
+    # bit-exact sparsity pattern (TACSAssembler::createMat, natural order)
+    assert rowp.tobytes() == g["rowp"].tobytes() and cols.tobytes() == g["cols"].tobytes()
+    comp = orc.make_comp(0, g["Cs"], g["eth"])
+    ec = np.zeros(len(conn), dtype=np.int32)
+    args = (conn, ec, [comp], X, u, rowp, cols, g["bc_nodes"], g["bc_vars"], g["bc_vals"])
+    r, K = orc.assemble(1, *args)
+    assert relmax(r, g["res"]) < 1e-13 and relmax(K, g["K"]) < 1e-13
+    r0, _ = orc.assemble(0, *args)
+    assert relmax(r0, g["res_only"]) < 1e-13
+    _, G = orc.assemble(3, *args)
+    assert relmax(G, g["G"]) < 1e-10
+    # BC rows: zero except 1 on the diagonal; residual rows u - ubar
+    for b, nd in enumerate(g["bc_nodes"]):
+        for k in range(6):
+            if g["bc_vars"][b] & (1 << k):
+                assert r[nd, k] == u[nd, k] - g["bc_vals"][b, k]
+                for j in range(rowp[nd], rowp[nd + 1]):
+                    row = K[j, k].copy()
+                    if cols[j] == nd:
+                        assert row[k] == 1.0
+                        row[k] = 0.0
+                    assert not row.any()
+
+
+def test_oracle_against_reference_live(orc, ref):
+    """random elements beyond the fixtures, all model/transform combinations"""
+    X, q = random_elements(40, seed=99)
+    axis = np.array([0.3, 1.0, 0.2])
+    for kind in (0, 1):
+        for tr in (0, 1):
+            p = ref.iso_props(kind=kind, temperature=0.0, t_offset=0.2)
+            Cs, eth, mom = ref.con_tables(p)
+            comp = orc.make_comp(kind, Cs, eth, mom, 0.0, tr, axis)
+            r_ref, k_ref, _ = ref.element_batch(p, 1, X.reshape(-1, 12), q.reshape(-1, 24),
+                                                transform=tr, axis=axis)
+            _, g_ref, _ = ref.element_batch(p, 3, X.reshape(-1, 12), q.reshape(-1, 24),
+                                            transform=tr, axis=axis)
+            for e in range(X.shape[0]):
+                r, k = orc.jacobian(comp, X[e].ravel(), q[e].ravel())
+                assert relmax(r, r_ref[e]) < 1e-13 and relmax(k, k_ref[e]) < 1e-13
+                assert relmax(orc.mat_type(comp, 1, X[e].ravel(), q[e].ravel()), g_ref[e]) < 1e-10
+
+
+def test_empty_and_degenerate_inputs(orc):
+    rowp, cols = orc.pattern(3, np.zeros((0, 4), dtype=np.int32))
+    assert rowp.tolist() == [0, 0, 0, 0] and len(cols) == 0
+    # zero state: zero residual; G of a zero state is exactly zero in the oracle's
+    # central difference (both evaluations coincide)
+    X, _ = random_elements(1, seed=3)
+    Cs = np.ones(22); Cs[6:12] = 0.0
+    comp = orc.make_comp(0, Cs, np.zeros(9))
+    r, k = orc.jacobian(comp, X[0].ravel(), np.zeros(24))
+    assert not r.any() and np.abs(k - k.T).max() <= 1e-12 * np.abs(k).max()
