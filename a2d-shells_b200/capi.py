@@ -36,7 +36,8 @@ class A2dsError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(HERE, "lib", "liba2ds_b200.so")
+    # A2DS_LIB: development switch to try an alternative build of the same library
+    return os.environ.get("A2DS_LIB") or os.path.join(HERE, "lib", "liba2ds_b200.so")
 
 
 def load_library():

@@ -15,6 +15,7 @@
 #include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -75,21 +76,66 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-static const int WARPS_PER_BLOCK = 4;
-static const int KE_LD = 24;  // leading dimension of the staged element matrices
+static const int MAX_WARPS_PER_BLOCK = 2;
+// Register budget (measured on B200, 490 k elements): the residual / tangent kernels run
+// fastest at 12 warps per SM (168 registers, no spills); the variants that carry the
+// B1(q) columns across the tangent pass (geometric stiffness, nonlinear model) spill at
+// 168 and run faster at 8 warps per SM with the full 255 registers.
+#define A2DS_MIN_BLOCKS(GMAT, NL) (((GMAT) || (NL)) ? 4 : 6)
+static const int KE_LD = 26;  // leading dimension of the staged element matrices (24 + pad)
+
+// scatter one staged 24x24 element matrix: for each of the 16 node-pair blocks the 36
+// entries leave as one full-warp RED (entries 0..31) + one 4-lane RED (32..35), i.e.
+// consecutive lanes hit consecutive doubles of a BCSR block
+__device__ __forceinline__ void scatter_matrix(const double *E, double *vals, int off16,
+                                               double scale, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const int r0 = lane / 6, c0 = lane - 6 * r0;   // entry `lane` of a 6x6 block
+  const int src0 = r0 * KE_LD + c0;
+  const int src1 = 5 * KE_LD + 2 + lane;         // entries 32..35: row 5, columns 2..5
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    const int off = __shfl_sync(FULL, off16, b);
+    if (off >= 0) {
+      const double *Eb = E + 6 * (b >> 2) * KE_LD + 6 * (b & 3);
+      double *dst = vals + 36 * (size_t)off;
+      atomicAdd(dst + lane, scale * Eb[src0]);
+      if (lane < 4) atomicAdd(dst + 32 + lane, scale * Eb[src1]);
+    }
+  }
+}
+
+// upper-triangle tiles of a symmetric 24x24 from DMMA accumulators into the staging area
+__device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2], int lane) {
+  const int r = lane >> 2, cpair = 2 * (lane & 3);
+  int idx = 0;
+#pragma unroll
+  for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+    for (int tj = ti; tj < 3; tj++, idx++) {
+      const int row = 8 * ti + r, col = 8 * tj + cpair;
+      E[row * KE_LD + col] = acc[idx][0];
+      E[row * KE_LD + col + 1] = acc[idx][1];
+      if (ti != tj) {
+        E[col * KE_LD + row] = acc[idx][0];
+        E[(col + 1) * KE_LD + row] = acc[idx][1];
+      }
+    }
+}
 
 template <bool RES, bool KMAT, bool GMAT, bool NL>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT, NL))
     k_assemble(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
   ElemScratch &s = *reinterpret_cast<ElemScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
   const unsigned FULL = 0xffffffffu;
   Want w;
   w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL;
 
-  for (int it = blockIdx.x * WARPS_PER_BLOCK + warp; it < p.n_list;
-       it += gridDim.x * WARPS_PER_BLOCK) {
+  for (int it = blockIdx.x * warps_per_block + warp; it < p.n_list;
+       it += gridDim.x * warps_per_block) {
     const int e = p.elem_list ? __ldg(&p.elem_list[it]) : it;
     const CompData &c = p.comps[__ldg(&p.elem_comp[e])];
 
@@ -111,9 +157,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     __syncwarp();
 
     // ---- column phase (+ strain reduction over the 8 lanes of a Gauss point) ---
+    double Bq[9][3];
     {
       double ep[9], qw, na[2], nb[2];
-      lane_columns(c, s, lane, w, ep, qw, na, nb);
+      lane_columns(c, s, lane, w, ep, qw, na, nb, Bq);
       if (RES || GMAT || NL) {
 #pragma unroll
         for (int r = 0; r < 9; r++) {
@@ -140,65 +187,66 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
       }
     }
     __syncwarp();
+    if ((GMAT || NL) && lane < 9) sum_tying_stress(s, lane);
 
     if (KMAT || GMAT) {
-      // ---- contraction on the FP64 tensor path ---------------------------------
-      // fragment address: row (lane >> 2) of the 8-wide tile, k index (lane & 3)
-      double kacc[6][2], gacc[6][2];
-#pragma unroll
-      for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = gacc[t][0] = gacc[t][1] = 0.0;
+      // ---- contractions on the FP64 tensor path --------------------------------
+      // fragment address: row (lane >> 2) of the 8-wide tile, k index (lane & 3);
+      // the two passes share the A-operand array (B, then B1)
       const int fr = (lane >> 2) * LDS_ROWS + (lane & 3);
+      double kacc[6][2], gacc[6][2];
+      if (KMAT) {
 #pragma unroll
-      for (int ks = 0; ks < 9; ks++) {
-        double a[3], wv[3], b1[3];
+        for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = 0.0;
 #pragma unroll
-        for (int t = 0; t < 3; t++) {
-          wv[t] = s.W[8 * t * LDS_ROWS + fr + 4 * ks];
-          if (KMAT) a[t] = s.BA[8 * t * LDS_ROWS + fr + 4 * ks];
-          if (GMAT) b1[t] = s.B1[8 * t * LDS_ROWS + fr + 4 * ks];
-        }
-        int idx = 0;
+        for (int ks = 0; ks < 9; ks++) {
+          double a[3], wv[3];
 #pragma unroll
-        for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-          for (int tj = ti; tj < 3; tj++, idx++) {
-            if (KMAT) dmma884(kacc[idx], a[ti], wv[tj]);
-            if (GMAT) {
-              dmma884(gacc[idx], b1[ti], wv[tj]);
-              dmma884(gacc[idx], wv[ti], b1[tj]);
-            }
+          for (int t = 0; t < 3; t++) {
+            wv[t] = s.W[8 * t * LDS_ROWS + fr + 4 * ks];
+            a[t] = s.BA[8 * t * LDS_ROWS + fr + 4 * ks];
           }
+          int idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], a[ti], wv[tj]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
+      if (GMAT) {
+        store_b1_columns(s, lane, Bq);
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 9; ks++) {
+          double b1[3], wv[3];
+#pragma unroll
+          for (int t = 0; t < 3; t++) {
+            wv[t] = s.W[8 * t * LDS_ROWS + fr + 4 * ks];
+            b1[t] = s.BA[8 * t * LDS_ROWS + fr + 4 * ks];
+          }
+          // two products per tile; issue all first products, then all second ones, so
+          // that consecutive DMMAs never wait on the same accumulator
+          int idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], b1[ti], wv[tj]);
+          idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], wv[ti], b1[tj]);
+        }
+        __syncwarp();
+      }
 
       // ---- stage the element matrices (upper tiles + mirrored lower tiles) ------
-      double *Ke = s.BA, *Ge = s.B1;
-      {
-        const int r = lane >> 2, cpair = 2 * (lane & 3);
-        int idx = 0;
-#pragma unroll
-        for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-          for (int tj = ti; tj < 3; tj++, idx++) {
-            const int row = 8 * ti + r, col = 8 * tj + cpair;
-            if (KMAT) {
-              Ke[row * KE_LD + col] = kacc[idx][0];
-              Ke[row * KE_LD + col + 1] = kacc[idx][1];
-              if (ti != tj) {
-                Ke[col * KE_LD + row] = kacc[idx][0];
-                Ke[(col + 1) * KE_LD + row] = kacc[idx][1];
-              }
-            }
-            if (GMAT) {
-              Ge[row * KE_LD + col] = gacc[idx][0];
-              Ge[row * KE_LD + col + 1] = gacc[idx][1];
-              if (ti != tj) {
-                Ge[col * KE_LD + row] = gacc[idx][0];
-                Ge[(col + 1) * KE_LD + row] = gacc[idx][1];
-              }
-            }
-          }
-      }
+      double *Ke = s.BA, *Ge = s.W;
+      if (KMAT) stage_tiles(Ke, kacc, lane);
+      if (GMAT) stage_tiles(Ge, gacc, lane);
       __syncwarp();
 
       // ---- geometric stiffness blocks: 64 generalised node pairs, 2 per lane -----
@@ -218,23 +266,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
         __syncwarp();
       }
 
-      // ---- scatter: 576 entries = 16 blocks x 36, consecutive lanes -> consecutive
-      //      doubles of a block (coalesced RED.E.ADD.F64) --------------------------
-#pragma unroll 1
-      for (int ch = 0; ch < 18; ch++) {
-        const int idx = ch * 32 + lane;
-        const int blk = idx / 36, wi = idx - 36 * blk;
-        const int r = wi / 6, cc = wi - 6 * r;
-        const int src = (6 * (blk >> 2) + r) * KE_LD + 6 * (blk & 3) + cc;
-        if (KMAT) {
-          const int off = __shfl_sync(FULL, koff, blk);
-          if (off >= 0) atomicAdd(&p.Kval[36 * (size_t)off + wi], p.alpha * Ke[src]);
-        }
-        if (GMAT) {
-          const int off = __shfl_sync(FULL, goff, blk);
-          if (off >= 0) atomicAdd(&p.Gval[36 * (size_t)off + wi], Ge[src]);
-        }
-      }
+      // ---- scatter (coalesced RED.E.ADD.F64) --------------------------------------
+      if (KMAT) scatter_matrix(Ke, p.Kval, koff, p.alpha, lane);
+      if (GMAT) scatter_matrix(Ge, p.Gval, goff, 1.0, lane);
     }
     __syncwarp();
   }
@@ -346,6 +380,7 @@ struct a2ds_ctx {
   double *bc_vals = nullptr;
   std::vector<MatrixRec> mats;
   int scatter_mode = A2DS_SCATTER_ATOMIC;
+  int warps_per_block = 2;  // one warp = one element; 17 KB of scratch per warp
   // element lists: [class][colour]; colour list 0 of the atomic mode holds everything
   bool lists_ready = false;
   int n_colors = 0;
@@ -389,6 +424,10 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   a2ds_ctx *c = new a2ds_ctx();
   c->device = device;
   c->n_sm = prop.multiProcessorCount;
+  if (const char *env = getenv("A2DS_WARPS_PER_BLOCK")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= MAX_WARPS_PER_BLOCK) c->warps_per_block = v;
+  }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
@@ -843,21 +882,24 @@ extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
 // ---- assembly ------------------------------------------------------------------
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_one(a2ds_ctx *c, KParams &p) {
-  const size_t per_warp = GMAT ? sizeof(ElemScratch) : offsetof(ElemScratch, B1);
-  p.scratch_bytes = (int)((per_warp + 15) & ~size_t(15));
-  const size_t smem = p.scratch_bytes * (size_t)WARPS_PER_BLOCK;
+  const size_t per_warp = (sizeof(ElemScratch) + 15) & ~size_t(15);
+  p.scratch_bytes = (int)per_warp;
+  const int wpb = c->warps_per_block;
+  const size_t smem = per_warp * (size_t)wpb;
   auto kern = k_assemble<RES, KMAT, GMAT, NL>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static size_t attr_smem = 0;  // per instantiation
+  if (attr_smem < smem) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    attr_smem = smem;
   }
   int per_sm = 1;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_BLOCK * 32, smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
   if (per_sm < 1) return fail("k_assemble does not fit on an SM");
-  const int want = (p.n_list + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  const int want = (p.n_list + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
-  kern<<<grid, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  kern<<<grid, wpb * 32, smem, c->stream>>>(p);
   CU(cudaGetLastError());
   c->last_launches++;
   return 0;

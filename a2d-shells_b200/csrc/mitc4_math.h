@@ -85,9 +85,12 @@ struct ElemScratch {
   double sg[4][3]; // per Gauss point: w*s3, w*s4, w*s5 (bending resultants)
   double sig[4][9];    // per Gauss point contribution to the tying-point stresses
   double Mq[4][25];    // per Gauss point: tying strain -> membrane/shear strain map
-  double BA[24 * LDS_ROWS];  // strain matrix B (A operand)
+  double sigsum[9];    // tying-point stresses summed over the Gauss points
+  // Operand arrays of the contraction.  BA first holds B (tangent pass), then is
+  // overwritten with B1(q) (geometric pass); afterwards BA / W are reused to stage the
+  // element matrices for the scatter.
+  double BA[24 * LDS_ROWS];
   double W[24 * LDS_ROWS];   // w C B
-  double B1[24 * LDS_ROWS];  // state dependent part B1(q)
 };
 
 A2DS_HD void cross(const double a[3], const double b[3], double o[3]) {
@@ -153,6 +156,18 @@ A2DS_HD void edge_vectors(const double *v, int ld, double a0[3], double a1[3], d
   }
 }
 
+// d/dxi of a nodal field on the edge eta = -1 (side 0) / +1 (side 1), and d/deta on the
+// edge xi = -1 / +1.  The side is lane dependent: read the two nodes straight from
+// (shared) memory so that no register array is indexed dynamically.
+A2DS_HD void edge_xi(const double *v, int ld, int side, double o[3]) {
+  const double *lo = v + 2 * side * ld, *hi = lo + ld;
+  o[0] = 0.5 * (hi[0] - lo[0]); o[1] = 0.5 * (hi[1] - lo[1]); o[2] = 0.5 * (hi[2] - lo[2]);
+}
+A2DS_HD void edge_eta(const double *v, int ld, int side, double o[3]) {
+  const double *lo = v + side * ld, *hi = lo + 2 * ld;
+  o[0] = 0.5 * (hi[0] - lo[0]); o[1] = 0.5 * (hi[1] - lo[1]); o[2] = 0.5 * (hi[2] - lo[2]);
+}
+
 // Drill strain of the state at node m, in the operation order of the reference
 // (TacsShellComputeDrillStrain, TACSShellUtilities.h:651-693; evalDrillStrain,
 // TACSDirector.h:560-564):  et = 1/2 (Ct[3] + u0x[3] - Ct[1] - u0x[1]) with
@@ -211,10 +226,9 @@ A2DS_HD double sdet2(double a, double b, double c, double d) {  // a*b - c*d
 }
 
 A2DS_HD void phase_node(const CompData &c, ElemScratch &s, int m) {
-  double a0[3], a1[3], b0[3], b1[3];
-  edge_vectors(s.X, 3, a0, a1, b0, b1);
-  const double *Xxi = (m / 2) ? a1 : a0;   // X,xi at the node (eta = +-1)
-  const double *Xeta = (m % 2) ? b1 : b0;  // X,eta at the node (xi = +-1)
+  double Xxi[3], Xeta[3];
+  edge_xi(s.X, 3, m / 2, Xxi);    // X,xi at the node (eta = +-1)
+  edge_eta(s.X, 3, m % 2, Xeta);  // X,eta at the node (xi = +-1)
   double fn[3];
   scross(Xxi, Xeta, fn);
   double nrm = sqrt(sdot(fn, fn));
@@ -271,9 +285,11 @@ A2DS_HD void phase_node(const CompData &c, ElemScratch &s, int m) {
                               A2DS_MUL(Xi[3 * i + 2], T[6 + j]));
   s.Sn[4 * m] = S[0]; s.Sn[4 * m + 1] = S[1]; s.Sn[4 * m + 2] = S[3]; s.Sn[4 * m + 3] = S[4];
   {
-    double ua0[3], ua1[3], ub0[3], ub1[3];
-    edge_vectors(s.q, 6, ua0, ua1, ub0, ub1);
-    s.etn[m] = drill_strain_state(T, S, (m / 2) ? ua1 : ua0, (m % 2) ? ub1 : ub0, &s.q[6 * m + 3]);
+    double uxi[3], ueta[3];
+    edge_xi(s.q, 6, m / 2, uxi);
+    edge_eta(s.q, 6, m % 2, ueta);
+    const double th[3] = {s.q[6 * m + 3], s.q[6 * m + 4], s.q[6 * m + 5]};
+    s.etn[m] = drill_strain_state(T, S, uxi, ueta, th);
   }
   double w[3], d[3];
   cross(t1, t2, w);
@@ -406,7 +422,9 @@ struct NodeCoef { double a[2], az[2], b[2], cc[2]; };
 
 A2DS_HD void node_coef(const QpGeom &g, int m, NodeCoef &n) {
   const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
-  const double Nxi = dN * g.nb[m / 2], Neta = g.na[m % 2] * dM, N = g.na[m % 2] * g.nb[m / 2];
+  const double nam = (m % 2) ? g.na[1] : g.na[0], nbm = (m / 2) ? g.nb[1] : g.nb[0];
+  const double Nxi = dN * nbm, Neta = nam * dM, N = nam * nbm;
+#pragma unroll
   for (int j = 0; j < 2; j++) {
     n.a[j] = Nxi * g.S[j] + Neta * g.S[3 + j];
     n.az[j] = Nxi * g.Sz[j] + Neta * g.Sz[3 + j];
@@ -416,72 +434,85 @@ A2DS_HD void node_coef(const QpGeom &g, int m, NodeCoef &n) {
 }
 
 // Three columns (node m, h = 0: displacements, h = 1: rotations) of the 9-row
-// strain matrix at one Gauss point.  `lin` selects B0 (geometry vectors) or, with
-// the state vectors passed instead, B1(q).
-//   va[2], vb[2]   : field,xi at eta = -+1 / field,eta at xi = -+1  (X or u)
-//   vn23[2], vn13[2]: normal-like field at the g23 / g13 tying points (fn or d)
-//   p0, p1         : for the bending rows: B0 uses (0, T columns); B1 uses
-//                    (T u1x[:,j], T u0x[:,j])
+// strain matrix at one Gauss point.  With (field, normal) = (X, fn) this is B0; with
+// (u, director) it is the state dependent part B1(q):
+//   field,xi / field,eta on the node's two edges and at the centre feed the tying rows,
+//   `normal` averaged on the edges feeds the transverse-shear tying rows,
+//   bending rows:  B0 uses the T columns, B1 uses T u1x[:,j] / T u0x[:,j].
 A2DS_HD void strain_columns(const ElemScratch &s, const QpGeom &g, const NodeCoef &nc, int m,
-                            int h, const double va[2][3], const double vb[2][3],
-                            const double vn23[2][3], const double vn13[2][3],
-                            const double *pa0, const double *pa1, const double *pz0,
+                            int h, const double *field, int ld, const double *normal,
+                            bool has_a, const double *pa0, const double *pa1, const double *pz0,
                             const double *pz1, bool drill, double B[9][3]) {
-  const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
-  const double *fn = &s.fn[3 * m];
+  const int sx = m % 2, sy = m / 2;  // which xi / eta side the node sits on
+  const double dN = sx ? 0.5 : -0.5, dM = sy ? 0.5 : -0.5;
+  const double nas = sx ? g.na[1] : g.na[0], nbs = sy ? g.nb[1] : g.nb[0];
+  const double fn[3] = {s.fn[3 * m], s.fn[3 * m + 1], s.fn[3 * m + 2]};
+  double fxi[3], feta[3];  // field,xi on the node's eta edge; field,eta on its xi edge
+  edge_xi(field, ld, sy, fxi);
+  edge_eta(field, ld, sx, feta);
   double G5[5][3];  // columns of (g11, g12, g13, g22, g23) interpolated to the point
   if (h == 0) {
-    const double c11 = g.nb[m / 2] * dN;          // g11 tying point on this node's eta edge
-    const double c22 = g.na[m % 2] * dM;          // g22 tying point on this node's xi edge
+    const double c11 = nbs * dN;          // g11 tying point on this node's eta edge
+    const double c22 = nas * dM;          // g22 tying point on this node's xi edge
     const double c12x = 0.5 * (0.5 * dN), c12e = 0.5 * (0.5 * dM);  // centre point
-    const double c23 = g.na[m % 2] * (0.5 * dM);  // g23: 1/2 N,eta n0
-    const double c13 = g.nb[m / 2] * (0.5 * dN);  // g13: 1/2 N,xi n0
+    const double c23 = nas * (0.5 * dM);  // g23: 1/2 N,eta n0 on the xi edge
+    const double c13 = nbs * (0.5 * dN);  // g13: 1/2 N,xi n0 on the eta edge
+    // edge-averaged normals: xi edge -> nodes (sx, sx+2); eta edge -> nodes (2 sy, 2 sy + 1)
+    const double *n23a = normal + 3 * sx, *n13a = normal + 6 * sy;
+#pragma unroll
     for (int k = 0; k < 3; k++) {
-      G5[0][k] = c11 * va[m / 2][k];
-      G5[3][k] = c22 * vb[m % 2][k];
-      G5[1][k] = c12x * (0.5 * (vb[0][k] + vb[1][k])) + c12e * (0.5 * (va[0][k] + va[1][k]));
-      G5[4][k] = c23 * vn23[m % 2][k];
-      G5[2][k] = c13 * vn13[m / 2][k];
+      // field,xi / field,eta at the element centre
+      const double cxi = 0.25 * (field[ld + k] - field[k] + field[3 * ld + k] - field[2 * ld + k]);
+      const double ceta = 0.25 * (field[2 * ld + k] - field[k] + field[3 * ld + k] - field[ld + k]);
+      G5[0][k] = c11 * fxi[k];
+      G5[3][k] = c22 * feta[k];
+      G5[1][k] = c12x * ceta + c12e * cxi;
+      G5[4][k] = c23 * (0.5 * (n23a[k] + n23a[6 + k]));
+      G5[2][k] = c13 * (0.5 * (n13a[k] + n13a[3 + k]));
     }
   } else {
     // 1/2 N_m(tying point) (fn_m x field,eta|xi); N_m = 1/2 at the edge mid points
     double x23[3], x13[3];
-    cross(fn, vb[m % 2], x23);
-    cross(fn, va[m / 2], x13);
-    const double c23 = g.na[m % 2] * 0.25, c13 = g.nb[m / 2] * 0.25;
+    cross(fn, feta, x23);
+    cross(fn, fxi, x13);
+    const double c23 = nas * 0.25, c13 = nbs * 0.25;
+#pragma unroll
     for (int k = 0; k < 3; k++) {
       G5[0][k] = 0.0; G5[1][k] = 0.0; G5[3][k] = 0.0;
       G5[4][k] = c23 * x23[k];
       G5[2][k] = c13 * x13[k];
     }
   }
-  const int row[5] = {0, 1, 2, 6, 7};
-  for (int r = 0; r < 5; r++)
+#pragma unroll
+  for (int r = 0; r < 5; r++) {
+    const int row = (r < 3) ? r : r + 3;  // strain rows 0,1,2,6,7
+#pragma unroll
     for (int k = 0; k < 3; k++)
-      B[row[r]][k] = g.M[5 * r] * G5[0][k] + g.M[5 * r + 1] * G5[1][k] +
-                     g.M[5 * r + 2] * G5[2][k] + g.M[5 * r + 3] * G5[3][k] +
-                     g.M[5 * r + 4] * G5[4][k];
+      B[row][k] = g.M[5 * r] * G5[0][k] + g.M[5 * r + 1] * G5[1][k] +
+                  g.M[5 * r + 2] * G5[2][k] + g.M[5 * r + 3] * G5[3][k] +
+                  g.M[5 * r + 4] * G5[4][k];
+  }
   // bending rows: e3 = u1x[0][0], e4 = u1x[1][1], e5 = u1x[0][1] + u1x[1][0]
   // (+ u0x/u1x products for the nonlinear part)
-  const double *ca = (h == 0) ? nc.a : nc.b;    // multiplies the "u0x" partner
-  const double *cz = (h == 0) ? nc.az : nc.cc;  // multiplies the "u1x" partner
-  double A0[3], A1[3], Z0[3], Z1[3];
+  const double ca0 = h ? nc.b[0] : nc.a[0], ca1 = h ? nc.b[1] : nc.a[1];      // "u0x" partner
+  const double cz0 = h ? nc.cc[0] : nc.az[0], cz1 = h ? nc.cc[1] : nc.az[1];  // "u1x" partner
+  double A0[3] = {0.0, 0.0, 0.0}, A1[3] = {0.0, 0.0, 0.0}, Z0[3], Z1[3];
   if (h == 0) {
+#pragma unroll
     for (int k = 0; k < 3; k++) {
-      A0[k] = pa0 ? pa0[k] : 0.0; A1[k] = pa1 ? pa1[k] : 0.0;
+      if (has_a) { A0[k] = pa0[k]; A1[k] = pa1[k]; }
       Z0[k] = pz0[k]; Z1[k] = pz1[k];
     }
   } else {
-    double zero[3] = {0.0, 0.0, 0.0};
-    cross(fn, pa0 ? pa0 : zero, A0);
-    cross(fn, pa1 ? pa1 : zero, A1);
+    if (has_a) { cross(fn, pa0, A0); cross(fn, pa1, A1); }
     cross(fn, pz0, Z0);
     cross(fn, pz1, Z1);
   }
+#pragma unroll
   for (int k = 0; k < 3; k++) {
-    B[3][k] = ca[0] * A0[k] + cz[0] * Z0[k];
-    B[4][k] = ca[1] * A1[k] + cz[1] * Z1[k];
-    B[5][k] = ca[0] * A1[k] + cz[1] * Z0[k] + ca[1] * A0[k] + cz[0] * Z1[k];
+    B[3][k] = ca0 * A0[k] + cz0 * Z0[k];
+    B[4][k] = ca1 * A1[k] + cz1 * Z1[k];
+    B[5][k] = ca0 * A1[k] + cz1 * Z0[k] + ca1 * A0[k] + cz0 * Z1[k];
   }
   // drilling strain row: et = sum_n N_n etn_n,
   // etn_n = 1/2 (u0x[1][0] - u0x[0][1]) - theta_n . (t0n x t1n)   (TACSDirector.h:560-564)
@@ -489,33 +520,23 @@ A2DS_HD void strain_columns(const ElemScratch &s, const QpGeom &g, const NodeCoe
     B[8][0] = B[8][1] = B[8][2] = 0.0;
   } else if (h == 0) {
     double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
     for (int n = 0; n < 4; n++) {
       // shape function derivatives of node m evaluated at node n
-      const double Nxi = (m / 2 == n / 2) ? dN : 0.0;
-      const double Neta = (m % 2 == n % 2) ? dM : 0.0;
+      const double Nxi = (sy == n / 2) ? dN : 0.0;
+      const double Neta = (sx == n % 2) ? dM : 0.0;
       const double a0 = Nxi * s.Sn[4 * n] + Neta * s.Sn[4 * n + 2];
       const double a1 = Nxi * s.Sn[4 * n + 1] + Neta * s.Sn[4 * n + 3];
       const double Nq = g.na[n % 2] * g.nb[n / 2];
+#pragma unroll
       for (int k = 0; k < 3; k++)
         acc[k] += Nq * (0.5 * (a0 * s.t1n[3 * n + k] - a1 * s.t0n[3 * n + k]));
     }
     B[8][0] = acc[0]; B[8][1] = acc[1]; B[8][2] = acc[2];
   } else {
-    const double Nq = g.na[m % 2] * g.nb[m / 2];
+    const double Nq = nas * nbs;
+#pragma unroll
     for (int k = 0; k < 3; k++) B[8][k] = -Nq * s.wn[3 * m + k];
-  }
-}
-
-// vectors feeding strain_columns for B0 (geometry) and B1 (state)
-struct ColVecs { double va[2][3], vb[2][3], vn23[2][3], vn13[2][3]; };
-
-A2DS_HD void col_vectors(const double *field, int ld, const double *normal, ColVecs &v) {
-  edge_vectors(field, ld, v.va[0], v.va[1], v.vb[0], v.vb[1]);
-  for (int k = 0; k < 3; k++) {
-    v.vn23[0][k] = 0.5 * (normal[k] + normal[6 + k]);      // xi = -1 edge: nodes 0,2
-    v.vn23[1][k] = 0.5 * (normal[3 + k] + normal[9 + k]);  // xi = +1 edge: nodes 1,3
-    v.vn13[0][k] = 0.5 * (normal[k] + normal[3 + k]);      // eta = -1 edge: nodes 0,1
-    v.vn13[1][k] = 0.5 * (normal[6 + k] + normal[9 + k]);  // eta = +1 edge: nodes 2,3
   }
 }
 
@@ -540,13 +561,15 @@ struct Want {
 };
 
 // ---- phase 2: lane = (qp, m, h): three columns of B, w C B and B1 ---------------
-// Writes the lane's columns of BA (= B0, or B0 + B1 for the nonlinear model), of
-// W = w C BA and of B1 into the scratch operand arrays, publishes the per Gauss
-// point data of the geometric phase, and returns in e_part[9] the lane's
+// Writes the lane's columns of BA (= B0, or B0 + B1 for the nonlinear model) and of
+// W = w C BA into the scratch operand arrays, hands back the B1(q) columns in
+// registers (Bq, for the geometric pass), publishes the per Gauss point data of the
+// geometric phase, and returns in e_part[9] the lane's
 // contribution to the Gauss point strains (to be summed over the 8 lanes of the
 // Gauss point: warp shuffles on the device, a loop in the host emulation).
 A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Want &w,
-                          double e_part[9], double &qp_w, double na[2], double nb[2]) {
+                          double e_part[9], double &qp_w, double na[2], double nb[2],
+                          double Bq[9][3]) {
   const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
   const bool need_b1 = w.gmat || w.nonlinear;
   QpGeom g;
@@ -567,16 +590,11 @@ A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Wan
     s.ca[qp][4 + m][0] = nc.b[0]; s.ca[qp][4 + m][1] = nc.b[1];
     s.cb[qp][4 + m][0] = nc.cc[0]; s.cb[qp][4 + m][1] = nc.cc[1];
   }
-  ColVecs v;
-  double B0[9][3], Bq[9][3];
-  col_vectors(s.X, 3, s.fn, v);
-  strain_columns(s, g, nc, m, h, v.va, v.vb, v.vn23, v.vn13, (const double *)0,
-                 (const double *)0, g.t0, g.t1, true, B0);
-  if (need_b1) {
-    col_vectors(s.q, 6, s.dr, v);
-    strain_columns(s, g, nc, m, h, v.va, v.vb, v.vn23, v.vn13, &g.P1[0], &g.P1[3], &g.P0[0],
-                   &g.P0[3], false, Bq);
-  }
+  double B0[9][3];
+  strain_columns(s, g, nc, m, h, s.X, 3, s.fn, false, g.t0, g.t1, g.t0, g.t1, true, B0);
+  if (need_b1)
+    strain_columns(s, g, nc, m, h, s.q, 6, s.dr, true, &g.P1[0], &g.P1[3], &g.P0[0], &g.P0[3],
+                   false, Bq);
   const double *qc = &s.q[6 * m + 3 * h];
   const int col = 6 * m + 3 * h;
   for (int r = 0; r < 9; r++) {
@@ -599,10 +617,18 @@ A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Wan
       pa[r] = b[r];
       pw[r] = g.w * cb[r];
     }
-    if (w.gmat) {
-      double *p1 = &s.B1[(col + k) * LDS_ROWS + 9 * qp];
-      for (int r = 0; r < 9; r++) p1[r] = Bq[r][k];
-    }
+  }
+}
+
+// the lane's three B1(q) columns into the A-operand array (geometric pass)
+A2DS_HD void store_b1_columns(ElemScratch &s, int lane, const double Bq[9][3]) {
+  const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
+  const int col = 6 * m + 3 * h;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double *p1 = &s.BA[(col + k) * LDS_ROWS + 9 * qp];
+#pragma unroll
+    for (int r = 0; r < 9; r++) p1[r] = Bq[r][k];
   }
 }
 
@@ -654,6 +680,11 @@ A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want
   }
 }
 
+// tying-point stresses summed over the Gauss points (lanes 0..8, after lane_stress)
+A2DS_HD void sum_tying_stress(ElemScratch &s, int t) {
+  s.sigsum[t] = s.sig[0][t] + s.sig[1][t] + s.sig[2][t] + s.sig[3][t];
+}
+
 // ---- geometric stiffness: one 3x3 block for the generalised node pair (p, pp) ---
 // p, pp in 0..7: 0..3 displacement of node p, 4..7 director of node p-4.
 // Returns the block already folded onto the rotation DOFs:
@@ -661,9 +692,7 @@ A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want
 //   columns of a director node: blk * skew(fn_m)^T
 // (TACSLinearizedRotation::addDirectorJacobian, TACSDirector.h:369-486)
 A2DS_HD void geo_block(const ElemScratch &s, int p, int pp, double out[9]) {
-  // tying point stresses (sum over Gauss points)
-  double sig[9];
-  for (int t = 0; t < 9; t++) sig[t] = s.sig[0][t] + s.sig[1][t] + s.sig[2][t] + s.sig[3][t];
+  const double *sig = s.sigsum;  // tying point stresses (summed over the Gauss points)
   const int m = p & 3, mm = pp & 3;
   const bool pd = p >= 4, ppd = pp >= 4;
   const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
@@ -683,6 +712,7 @@ A2DS_HD void geo_block(const ElemScratch &s, int p, int pp, double out[9]) {
   }
   double blk[9] = {sc, 0.0, 0.0, 0.0, sc, 0.0, 0.0, 0.0, sc};
   // bending part: sum_qp (alpha_p^T Sigma beta_pp + beta_p^T Sigma alpha_pp) T T^T
+#pragma unroll
   for (int qp = 0; qp < 4; qp++) {
     const double *ap = s.ca[qp][p], *bp = s.cb[qp][p], *app = s.ca[qp][pp], *bpp = s.cb[qp][pp];
     const double s3 = s.sg[qp][0], s4 = s.sg[qp][1], s5 = s.sg[qp][2];
@@ -696,24 +726,29 @@ A2DS_HD void geo_block(const ElemScratch &s, int p, int pp, double out[9]) {
   if (pd) {  // rows: skew(fn_m) * blk
     const double *f = &s.fn[3 * m];
     double t[9];
+#pragma unroll
     for (int j = 0; j < 3; j++) {
       t[j] = f[1] * blk[6 + j] - f[2] * blk[3 + j];
       t[3 + j] = f[2] * blk[j] - f[0] * blk[6 + j];
       t[6 + j] = f[0] * blk[3 + j] - f[1] * blk[j];
     }
+#pragma unroll
     for (int i = 0; i < 9; i++) blk[i] = t[i];
   }
   if (ppd) {  // columns: blk * skew(fn_mm)^T, i.e. row_i -> fn x row_i
     const double *f = &s.fn[3 * mm];
     double t[9];
+#pragma unroll
     for (int i = 0; i < 3; i++) {
       const double *r = &blk[3 * i];
       t[3 * i] = f[1] * r[2] - f[2] * r[1];
       t[3 * i + 1] = f[2] * r[0] - f[0] * r[2];
       t[3 * i + 2] = f[0] * r[1] - f[1] * r[0];
     }
+#pragma unroll
     for (int i = 0; i < 9; i++) blk[i] = t[i];
   }
+#pragma unroll
   for (int i = 0; i < 9; i++) out[i] = blk[i];
 }
 

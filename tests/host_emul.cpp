@@ -25,8 +25,9 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   Want w;
   w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1;
   for (int lane = 0; lane < 32; lane++) phase_node(c, s, lane & 3);
-  static double ep[32][9], qw[32], na[32][2], nb[32][2];
-  for (int lane = 0; lane < 32; lane++) lane_columns(c, s, lane, w, ep[lane], qw[lane], na[lane], nb[lane]);
+  static double ep[32][9], qw[32], na[32][2], nb[32][2], Bq[32][9][3];
+  for (int lane = 0; lane < 32; lane++)
+    lane_columns(c, s, lane, w, ep[lane], qw[lane], na[lane], nb[lane], Bq[lane]);
   memset(res, 0, 24 * sizeof(double));
   for (int lane = 0; lane < 32; lane++) {
     int qp = lane >> 3;
@@ -38,6 +39,15 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
     lane_stress(c, s, lane, w, e, qw[lane], na[lane], nb[lane], r3);
     int col = 6 * ((lane >> 1) & 3) + 3 * (lane & 1);
     for (int k = 0; k < 3; k++) res[col + k] += r3[k];
+  }
+  for (int t = 0; t < 9; t++) sum_tying_stress(s, t);
+  // tangent pass operands, then the geometric pass overwrites BA with B1(q)
+  static double BAk[24 * LDS_ROWS], B1[24 * LDS_ROWS];
+  memcpy(BAk, s.BA, sizeof(BAk));
+  memset(B1, 0, sizeof(B1));
+  if (w.gmat || w.nonlinear) {
+    for (int lane = 0; lane < 32; lane++) store_b1_columns(s, lane, Bq[lane]);
+    memcpy(B1, s.BA, sizeof(B1));
   }
   double geo[576];
   memset(geo, 0, sizeof(geo));
@@ -53,9 +63,9 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
     for (int cc = 0; cc < 24; cc++) {
       double k = 0.0, gm = 0.0;
       for (int t = 0; t < 36; t++) {
-        k += s.BA[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t];
-        gm += s.B1[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t] +
-              s.W[r * LDS_ROWS + t] * s.B1[cc * LDS_ROWS + t];
+        k += BAk[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t];
+        gm += B1[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t] +
+              s.W[r * LDS_ROWS + t] * B1[cc * LDS_ROWS + t];
       }
       if (w.nonlinear) k += geo[24 * r + cc];
       K[24 * r + cc] = k;

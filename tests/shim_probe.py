@@ -1,0 +1,31 @@
+"""Run the reference's buckling flow (TACSLinearBuckling::solve) on a synthetic cylinder and
+print the lowest eigenvalues.  With LD_PRELOAD=libtacs_a2ds_shim.so the three TACSAssembler
+assembly entry points inside that flow run on the GPU; without it they are the reference's."""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import refdrv  # noqa: E402
+
+a2ds_meshes = importlib.import_module("a2d-shells_b200.meshes")
+conn, X, ends = a2ds_meshes.cylinder(40, 20)
+bc_vars = [[0, 1, 2, 5]] * len(ends)
+bc_vals = [[-1e-3 if i >= 40 else 0.0, 0.0, 0.0, 0.0] for i in range(len(ends))]
+ra = refdrv.RefAssembler(conn, X, np.zeros(len(conn), dtype=np.int32), refdrv.iso_props()[None],
+                         ends, bc_vars, bc_vals)
+km, gm, am = ra.mat_create(1), ra.mat_create(1), ra.mat_create(1)
+eig, err = ra.buckling(km, gm, am, 0, sigma=12.0, num_eigs=50, max_lanczos=100, u0=None)
+# also one plain Jacobian assembly into a TACSParallelMat
+pm = ra.mat_create(0)
+u = np.zeros((len(X), 6)); u[ra.new_nodes] = a2ds_meshes.seeded_state(np.arange(len(X)), 1e-5)
+ra.set_state(u)
+r = ra.assemble_jacobian(pm)
+A = ra.mat_block(pm, 0)["A"]
+print("SHIM_PROBE " + json.dumps(dict(eig=eig[:6].tolist(), err=err[:6].tolist(),
+                                     res_norm=float(np.abs(r).max()), res_sum=float(r.sum()),
+                                     a_max=float(np.abs(A).max()), a_sum=float(A.sum()))))

@@ -1,0 +1,43 @@
+"""The link-time drop-in: the UNMODIFIED reference buckling flow with
+libtacs_a2ds_shim.so preloaded (its TACSAssembler::assembleRes/Jacobian/MatType run on the
+GPU) against the same flow without it."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import has_gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "a2d-shells_b200", "lib", "libtacs_a2ds_shim.so")
+
+
+def _run(preload):
+    env = dict(os.environ)
+    env["OPENBLAS_NUM_THREADS"] = "1"
+    if preload:
+        env["LD_PRELOAD"] = SHIM
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shim_probe.py")], env=env,
+                         capture_output=True, text=True, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("SHIM_PROBE ")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    return json.loads(line[0][len("SHIM_PROBE "):]), out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_gpu(), reason="no CUDA device")
+def test_reference_buckling_flow_runs_on_gpu_through_the_shim(ref):
+    if not os.path.exists(SHIM):
+        pytest.skip("shim not built (needs the reference headers)")
+    base, _ = _run(False)
+    gpu, log = _run(True)
+    assert "[a2ds shim]" in log and "device assembly" in log   # the GPU path really ran
+    e0, e1 = np.array(base["eig"]), np.array(gpu["eig"])
+    assert np.all(np.array(base["err"]) < 1e-6)
+    assert np.all(np.abs(e1 - e0) <= 1e-8 * np.abs(e0)), (e0, e1)
+    assert abs(gpu["res_norm"] - base["res_norm"]) <= 1e-12 * base["res_norm"]
+    assert abs(gpu["a_max"] - base["a_max"]) <= 1e-10 * base["a_max"]
+    assert abs(gpu["a_sum"] - base["a_sum"]) <= 1e-9 * base["a_max"]
