@@ -86,27 +86,39 @@ static const int KE_LD = 26;  // leading dimension of the staged element matrice
 
 // scatter one staged 24x24 element matrix: for each of the 16 node-pair blocks the 36
 // entries leave as one full-warp RED (entries 0..31) + one 4-lane RED (32..35), i.e.
-// consecutive lanes hit consecutive doubles of a BCSR block
+// consecutive lanes hit consecutive doubles of a BCSR block.  Every slot has a block
+// (a2ds_mat_create refuses patterns with missing blocks), so there is no validity
+// branch; loads are batched 8 blocks at a time so the REDs do not wait on shared memory
+// one by one.
 __device__ __forceinline__ void scatter_matrix(const double *E, double *vals, int off16,
-                                               double scale, int lane) {
+                                               int lane) {
   const unsigned FULL = 0xffffffffu;
   const int r0 = lane / 6, c0 = lane - 6 * r0;   // entry `lane` of a 6x6 block
   const int src0 = r0 * KE_LD + c0;
-  const int src1 = 5 * KE_LD + 2 + lane;         // entries 32..35: row 5, columns 2..5
+  const int src1 = 5 * KE_LD + 2 + (lane & 3);   // entries 32..35: row 5, columns 2..5
 #pragma unroll
-  for (int b = 0; b < 16; b++) {
-    const int off = __shfl_sync(FULL, off16, b);
-    if (off >= 0) {
+  for (int half = 0; half < 2; half++) {
+    double v0[8], v1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int b = 8 * half + k;
       const double *Eb = E + 6 * (b >> 2) * KE_LD + 6 * (b & 3);
+      v0[k] = Eb[src0];
+      v1[k] = Eb[src1];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int off = __shfl_sync(FULL, off16, 8 * half + k);
       double *dst = vals + 36 * (size_t)off;
-      atomicAdd(dst + lane, scale * Eb[src0]);
-      if (lane < 4) atomicAdd(dst + 32 + lane, scale * Eb[src1]);
+      atomicAdd(dst + lane, v0[k]);
+      if (lane < 4) atomicAdd(dst + 32 + lane, v1[k]);
     }
   }
 }
 
 // upper-triangle tiles of a symmetric 24x24 from DMMA accumulators into the staging area
-__device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2], int lane) {
+__device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2], double scale,
+                                            int lane) {
   const int r = lane >> 2, cpair = 2 * (lane & 3);
   int idx = 0;
 #pragma unroll
@@ -114,11 +126,12 @@ __device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2]
 #pragma unroll
     for (int tj = ti; tj < 3; tj++, idx++) {
       const int row = 8 * ti + r, col = 8 * tj + cpair;
-      E[row * KE_LD + col] = acc[idx][0];
-      E[row * KE_LD + col + 1] = acc[idx][1];
+      const double a0 = scale * acc[idx][0], a1 = scale * acc[idx][1];
+      E[row * KE_LD + col] = a0;
+      E[row * KE_LD + col + 1] = a1;
       if (ti != tj) {
-        E[col * KE_LD + row] = acc[idx][0];
-        E[(col + 1) * KE_LD + row] = acc[idx][1];
+        E[col * KE_LD + row] = a0;
+        E[(col + 1) * KE_LD + row] = a1;
       }
     }
 }
@@ -134,22 +147,33 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
   Want w;
   w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL;
 
-  for (int it = blockIdx.x * warps_per_block + warp; it < p.n_list;
-       it += gridDim.x * warps_per_block) {
-    const int e = p.elem_list ? __ldg(&p.elem_list[it]) : it;
-    const CompData &c = p.comps[__ldg(&p.elem_comp[e])];
-
-    // ---- gather -----------------------------------------------------------
-    const int nd = __ldg(&p.conn[4 * e + (lane & 3)]);  // lane l holds node l & 3
-    {
-      const int nx = __shfl_sync(FULL, nd, lane / 3);
-      const int nq = __shfl_sync(FULL, nd, lane / 6);
-      if (lane < 12) s.X[lane] = __ldg(&p.X[3 * (size_t)nx + lane % 3]);
-      if (lane < 24) s.q[lane] = __ldg(&p.u[6 * (size_t)nq + lane % 6]);
-    }
-    int koff = -1, goff = -1;
-    if (KMAT && lane < 16) koff = __ldg(&p.Koff[16 * (size_t)e + lane]);
-    if (GMAT && lane < 16) goff = __ldg(&p.Goff[16 * (size_t)e + lane]);
+  // Gather of element i+1 is issued while element i is being processed (the loads only
+  // land in registers; they are written to the scratch at the top of the next trip).
+  struct Fetch { int comp, nd, koff, goff; double x, q; };
+  auto fetch = [&](int it_) {
+    Fetch f;
+    const int e = p.elem_list ? __ldg(&p.elem_list[it_]) : it_;
+    f.comp = __ldg(&p.elem_comp[e]);
+    f.nd = __ldg(&p.conn[4 * e + (lane & 3)]);  // lane l holds node l & 3
+    const int nx = __shfl_sync(FULL, f.nd, lane / 3);
+    const int nq = __shfl_sync(FULL, f.nd, lane / 6);
+    f.x = (lane < 12) ? __ldg(&p.X[3 * (size_t)nx + lane % 3]) : 0.0;
+    f.q = (lane < 24) ? __ldg(&p.u[6 * (size_t)nq + lane % 6]) : 0.0;
+    f.koff = (KMAT && lane < 16) ? __ldg(&p.Koff[16 * (size_t)e + lane]) : -1;
+    f.goff = (GMAT && lane < 16) ? __ldg(&p.Goff[16 * (size_t)e + lane]) : -1;
+    return f;
+  };
+  const int stride = gridDim.x * warps_per_block;
+  int it = blockIdx.x * warps_per_block + warp;
+  Fetch nxt;
+  if (it < p.n_list) nxt = fetch(it);
+  for (; it < p.n_list; it += stride) {
+    const Fetch cur = nxt;
+    if (it + stride < p.n_list) nxt = fetch(it + stride);
+    const CompData &c = p.comps[cur.comp];
+    const int nd = cur.nd, koff = cur.koff, goff = cur.goff;
+    if (lane < 12) s.X[lane] = cur.x;
+    if (lane < 24) s.q[lane] = cur.q;
     __syncwarp();
 
     // ---- node phase ---------------------------------------------------------
@@ -245,14 +269,16 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
 
       // ---- stage the element matrices (upper tiles + mirrored lower tiles) ------
       double *Ke = s.BA, *Ge = s.W;
-      if (KMAT) stage_tiles(Ke, kacc, lane);
-      if (GMAT) stage_tiles(Ge, gacc, lane);
+      if (KMAT) stage_tiles(Ke, kacc, p.alpha, lane);
+      if (GMAT) stage_tiles(Ge, gacc, 1.0, lane);
       __syncwarp();
 
       // ---- geometric stiffness blocks: 64 generalised node pairs, 2 per lane -----
+      // (for the nonlinear tangent they belong to K and carry its alpha)
       if (GMAT || (NL && KMAT)) {
         double *dst = GMAT ? Ge : Ke;
-#pragma unroll 1
+        const double gs = GMAT ? 1.0 : p.alpha;
+#pragma unroll
         for (int pass = 0; pass < 2; pass++) {
           const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
           double blk[9];
@@ -261,14 +287,14 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++) dst[(r0 + i) * KE_LD + c0 + j] += blk[3 * i + j];
+            for (int j = 0; j < 3; j++) dst[(r0 + i) * KE_LD + c0 + j] += gs * blk[3 * i + j];
         }
         __syncwarp();
       }
 
       // ---- scatter (coalesced RED.E.ADD.F64) --------------------------------------
-      if (KMAT) scatter_matrix(Ke, p.Kval, koff, p.alpha, lane);
-      if (GMAT) scatter_matrix(Ge, p.Gval, goff, 1.0, lane);
+      if (KMAT) scatter_matrix(Ke, p.Kval, koff, lane);
+      if (GMAT) scatter_matrix(Ge, p.Gval, goff, lane);
     }
     __syncwarp();
   }

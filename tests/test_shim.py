@@ -19,6 +19,11 @@ def _run(preload):
     env = dict(os.environ)
     env["OPENBLAS_NUM_THREADS"] = "1"
     if preload:
+        # the shim pulls in the reference library, whose bundled OpenBLAS needs its sibling
+        # libgfortran on the loader path
+        import sysconfig
+        blas = os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs")
+        env["LD_LIBRARY_PATH"] = blas + os.pathsep + env.get("LD_LIBRARY_PATH", "")
         env["LD_PRELOAD"] = SHIM
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shim_probe.py")], env=env,
                          capture_output=True, text=True, timeout=600)
