@@ -29,35 +29,5 @@ def build(force=False, verbose=False):
     return LIB
 
 
-SHIM = os.path.join(HERE, "lib", "libtacs_a2ds_shim.so")
-
-
-def build_shim(reference="/root/reference", ref_lib_dir=None):
-    """The link-time replacement of TACSAssembler::assembleRes/Jacobian/MatType
-    (host/tacs_shim.cpp).  Needs the reference's headers, so it is only built where the
-    reference tree is present (the build container); the .so travels with the snapshot.
-    It is linked against the reference library it interposes on (here: the single-rank
-    build under oracle/_ref) — in a deployment that is the user's liba2dshells.so."""
-    src = os.path.join(HERE, "host", "tacs_shim.cpp")
-    if not os.path.exists(os.path.join(reference, "src", "TACSAssembler.h")):
-        return None
-    ref_lib_dir = ref_lib_dir or os.path.join(HERE, "..", "oracle", "_ref")
-    if not os.path.exists(os.path.join(ref_lib_dir, "liba2dshells_ref.so")):
-        return None
-    if os.path.exists(SHIM) and os.path.getmtime(SHIM) >= max(os.path.getmtime(src),
-                                                              os.path.getmtime(LIB)):
-        return SHIM
-    inc = ["-I" + os.path.join(HERE, "..", "oracle", "stubs"), "-I" + os.path.join(HERE, "..", "include")]
-    for d in ("", "bpmat", "elements", "elements/basis", "elements/shell", "constitutive", "io", "utils"):
-        inc.append("-I" + os.path.join(reference, "src", d))
-    cmd = (["g++", "-std=c++11", "-O2", "-fPIC", "-w", "-fno-access-control", "-shared"] + inc +
-           ["-o", SHIM, src, "-L" + os.path.dirname(LIB), "-la2ds_b200",
-            "-L" + ref_lib_dir, "-la2dshells_ref",
-            "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../oracle/_ref"])
-    subprocess.check_call(cmd)
-    return SHIM
-
-
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
-    print(build_shim())

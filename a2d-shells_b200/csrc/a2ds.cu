@@ -76,13 +76,17 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-static const int MAX_WARPS_PER_BLOCK = 2;
-// Register budget (measured on B200, 490 k elements): the residual / tangent kernels run
-// fastest at 12 warps per SM (168 registers, no spills); the variants that carry the
-// B1(q) columns across the tangent pass (geometric stiffness, nonlinear model) spill at
-// 168 and run faster at 8 warps per SM with the full 255 registers.
-#define A2DS_MIN_BLOCKS(GMAT, NL) (((GMAT) || (NL)) ? 4 : 6)
-static const int KE_LD = 26;  // leading dimension of the staged element matrices (24 + pad)
+static const int MAX_WARPS_PER_BLOCK = 4;
+// Register budget: the residual / tangent kernels run at 12 warps per SM (168
+// registers); the variants that carry the B1(q) fragments across the tangent pass
+// (geometric stiffness, nonlinear model) need the full 255 registers (8 warps per SM).
+#ifndef A2DS_MB_G
+#define A2DS_MB_G 2
+#endif
+#ifndef A2DS_MB_K
+#define A2DS_MB_K 3
+#endif
+#define A2DS_MIN_BLOCKS(GMAT, NL) (((GMAT) || (NL)) ? A2DS_MB_G : A2DS_MB_K)
 
 // scatter one staged 24x24 element matrix: for each of the 16 node-pair blocks the 36
 // entries leave as one full-warp RED (entries 0..31) + one 4-lane RED (32..35), i.e.
@@ -116,24 +120,41 @@ __device__ __forceinline__ void scatter_matrix(const double *E, double *vals, in
   }
 }
 
-// upper-triangle tiles of a symmetric 24x24 from DMMA accumulators into the staging area
+// DMMA accumulators of the 6 upper tiles -> staged symmetric 24x24.  In the fragment
+// layout of mitc4_math.h the accumulator of tile (ti, tj) holds, on lane (c, qp'),
+// K[3 c + ti][6 qp' + tj] and K[3 c + ti][6 qp' + 3 + tj]  (c = lane >> 2, qp' = lane & 3).
 __device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2], double scale,
                                             int lane) {
-  const int r = lane >> 2, cpair = 2 * (lane & 3);
+  const int rowb = 3 * (lane >> 2), colb = 6 * (lane & 3);
   int idx = 0;
 #pragma unroll
   for (int ti = 0; ti < 3; ti++)
 #pragma unroll
     for (int tj = ti; tj < 3; tj++, idx++) {
-      const int row = 8 * ti + r, col = 8 * tj + cpair;
+      const int row = rowb + ti, col0 = colb + tj, col1 = colb + 3 + tj;
       const double a0 = scale * acc[idx][0], a1 = scale * acc[idx][1];
-      E[row * KE_LD + col] = a0;
-      E[row * KE_LD + col + 1] = a1;
+      E[row * KE_LD + col0] = a0;
+      E[row * KE_LD + col1] = a1;
       if (ti != tj) {
-        E[col * KE_LD + row] = a0;
-        E[(col + 1) * KE_LD + row] = a1;
+        E[col0 * KE_LD + row] = a0;
+        E[col1 * KE_LD + row] = a1;
       }
     }
+}
+
+// 64 geometric-stiffness 3x3 blocks (generalised node pairs), 2 per lane, added in place
+__device__ __forceinline__ void add_geo_blocks(ElemScratch &s, double *E, double scale, int lane) {
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+    double blk[9];
+    geo_block(s, pr, pc, blk);
+    const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) E[(r0 + i) * KE_LD + c0 + j] += scale * blk[3 * i + j];
+  }
 }
 
 template <bool RES, bool KMAT, bool GMAT, bool NL>
@@ -180,29 +201,31 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     phase_node(c, s, lane & 3);
     __syncwarp();
 
-    // ---- column phase (+ strain reduction over the 8 lanes of a Gauss point) ---
-    double Bq[9][3];
+    // ---- column phase: the lane's fragments of B, w C B and B1(q) -----------------
+    double Bc[9][3], Wc[9][3], Bq[9][3];
     {
       double ep[9], qw, na[2], nb[2];
-      lane_columns(c, s, lane, w, ep, qw, na, nb, Bq);
+      lane_columns(c, s, lane, w, ep, qw, na, nb, Bc, Wc, Bq);
       if (RES || GMAT || NL) {
+        // strains: sum over the 8 lanes of a Gauss point (lane bits 2..4)
 #pragma unroll
         for (int r = 0; r < 9; r++) {
-          ep[r] += __shfl_xor_sync(FULL, ep[r], 1);
-          ep[r] += __shfl_xor_sync(FULL, ep[r], 2);
           ep[r] += __shfl_xor_sync(FULL, ep[r], 4);
+          ep[r] += __shfl_xor_sync(FULL, ep[r], 8);
+          ep[r] += __shfl_xor_sync(FULL, ep[r], 16);
         }
         double r3[3];
-        lane_stress(c, s, lane, w, ep, qw, na, nb, r3);
+        lane_stress(c, s, lane, w, ep, qw, na, nb, Wc, r3);
         if (RES) {
+          // residual: sum over the 4 Gauss points (lane bits 0..1)
 #pragma unroll
           for (int k = 0; k < 3; k++) {
-            r3[k] += __shfl_xor_sync(FULL, r3[k], 8);
-            r3[k] += __shfl_xor_sync(FULL, r3[k], 16);
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 1);
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 2);
           }
-          const int nm = __shfl_sync(FULL, nd, (lane >> 1) & 3);
-          if (lane < 8) {
-            double *r = &p.res[6 * (size_t)nm + 3 * (lane & 1)];
+          const int nm = __shfl_sync(FULL, nd, lane_m(lane));
+          if ((lane & 3) == 0) {
+            double *r = &p.res[6 * (size_t)nm + 3 * lane_h(lane)];
             atomicAdd(r, r3[0]);
             atomicAdd(r + 1, r3[1]);
             atomicAdd(r + 2, r3[2]);
@@ -210,92 +233,51 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
         }
       }
     }
-    __syncwarp();
-    if ((GMAT || NL) && lane < 9) sum_tying_stress(s, lane);
 
-    if (KMAT || GMAT) {
-      // ---- contractions on the FP64 tensor path --------------------------------
-      // fragment address: row (lane >> 2) of the 8-wide tile, k index (lane & 3);
-      // the two passes share the A-operand array (B, then B1)
-      const int fr = (lane >> 2) * LDS_ROWS + (lane & 3);
-      double kacc[6][2], gacc[6][2];
-      if (KMAT) {
+    // ---- contractions on the FP64 tensor path, operands straight from registers ------
+    //      K = B^T (w C B),   G = B1^T W + W^T B1  (upper tiles only)
+    double kacc[6][2], gacc[6][2];
+    if (KMAT) {
 #pragma unroll
-        for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = 0.0;
+      for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = 0.0;
 #pragma unroll
-        for (int ks = 0; ks < 9; ks++) {
-          double a[3], wv[3];
+      for (int ks = 0; ks < 9; ks++) {
+        int idx = 0;
 #pragma unroll
-          for (int t = 0; t < 3; t++) {
-            wv[t] = s.W[8 * t * LDS_ROWS + fr + 4 * ks];
-            a[t] = s.BA[8 * t * LDS_ROWS + fr + 4 * ks];
-          }
-          int idx = 0;
+        for (int ti = 0; ti < 3; ti++)
 #pragma unroll
-          for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-            for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], a[ti], wv[tj]);
-        }
-        __syncwarp();
+          for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], Bc[ks][ti], Wc[ks][tj]);
       }
-      if (GMAT) {
-        store_b1_columns(s, lane, Bq);
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < 9; ks++) {
-          double b1[3], wv[3];
-#pragma unroll
-          for (int t = 0; t < 3; t++) {
-            wv[t] = s.W[8 * t * LDS_ROWS + fr + 4 * ks];
-            b1[t] = s.BA[8 * t * LDS_ROWS + fr + 4 * ks];
-          }
-          // two products per tile; issue all first products, then all second ones, so
-          // that consecutive DMMAs never wait on the same accumulator
-          int idx = 0;
-#pragma unroll
-          for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], b1[ti], wv[tj]);
-          idx = 0;
-#pragma unroll
-          for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], wv[ti], b1[tj]);
-        }
-        __syncwarp();
-      }
-
-      // ---- stage the element matrices (upper tiles + mirrored lower tiles) ------
-      double *Ke = s.BA, *Ge = s.W;
-      if (KMAT) stage_tiles(Ke, kacc, p.alpha, lane);
-      if (GMAT) stage_tiles(Ge, gacc, 1.0, lane);
-      __syncwarp();
-
-      // ---- geometric stiffness blocks: 64 generalised node pairs, 2 per lane -----
-      // (for the nonlinear tangent they belong to K and carry its alpha)
-      if (GMAT || (NL && KMAT)) {
-        double *dst = GMAT ? Ge : Ke;
-        const double gs = GMAT ? 1.0 : p.alpha;
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-          const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
-          double blk[9];
-          geo_block(s, pr, pc, blk);
-          const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
-#pragma unroll
-          for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) dst[(r0 + i) * KE_LD + c0 + j] += gs * blk[3 * i + j];
-        }
-        __syncwarp();
-      }
-
-      // ---- scatter (coalesced RED.E.ADD.F64) --------------------------------------
-      if (KMAT) scatter_matrix(Ke, p.Kval, koff, lane);
-      if (GMAT) scatter_matrix(Ge, p.Gval, goff, lane);
     }
+    if (GMAT) {
+#pragma unroll
+      for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 9; ks++) {
+        // two products per tile; all first products, then all second ones, so that
+        // consecutive DMMAs never wait on the same accumulator
+        int idx = 0;
+#pragma unroll
+        for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+          for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Bq[ks][ti], Wc[ks][tj]);
+        idx = 0;
+#pragma unroll
+        for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+          for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Wc[ks][ti], Bq[ks][tj]);
+      }
+    }
+    // ---- stage, add the geometric blocks, scatter -----------------------------------
+    if (KMAT) stage_tiles(s.E, kacc, p.alpha, lane);
+    if (GMAT) stage_tiles(s.E2, gacc, 1.0, lane);
+    if ((GMAT || NL) && lane < 9) sum_tying_stress(s, lane);
+    __syncwarp();
+    if (GMAT) add_geo_blocks(s, s.E2, 1.0, lane);
+    else if (NL && KMAT) add_geo_blocks(s, s.E, p.alpha, lane);
+    if (GMAT || NL) __syncwarp();
+    if (KMAT) scatter_matrix(s.E, p.Kval, koff, lane);
+    if (GMAT) scatter_matrix(s.E2, p.Gval, goff, lane);
     __syncwarp();
   }
 }
@@ -406,7 +388,7 @@ struct a2ds_ctx {
   double *bc_vals = nullptr;
   std::vector<MatrixRec> mats;
   int scatter_mode = A2DS_SCATTER_ATOMIC;
-  int warps_per_block = 2;  // one warp = one element; 17 KB of scratch per warp
+  int warps_per_block = 4;  // one warp = one element; 8 KB of scratch per warp
   // element lists: [class][colour]; colour list 0 of the atomic mode holds everything
   bool lists_ready = false;
   int n_colors = 0;

@@ -68,9 +68,20 @@ struct CompData {
   int transform;       // 0 natural, 1 reference axis
 };
 
-// operand arrays for the contraction are stored [dof column][strain row] with a
-// leading dimension of 36 doubles: conflict-free for the DMMA fragment loads
-static const int LDS_ROWS = 36;
+// leading dimension of the staged 24x24 element matrix (24 + pad against bank conflicts)
+static const int KE_LD = 26;
+
+// Lane -> work item.  lane = 4 c + qp with c = 2 m + h:
+//   qp = lane & 3   Gauss point,  m = (lane >> 3) & 3   node,  h = (lane >> 2) & 1   0: u, 1: theta
+// This is the m8n8k4 DMMA fragment layout read backwards: with the contraction index
+// ordered k = 4 s + qp (s = strain row) and matrix row/column  8 t + c  standing for
+// DOF 6 m + 3 h + t, lane (c, qp) of an A or B fragment for tile t, k-step s holds exactly
+// B_qp[s][6 m + 3 h + t] — an entry of the three columns this lane computes.  The
+// operands of the contraction therefore never leave the registers of the lane that made
+// them.
+A2DS_HD int lane_qp(int lane) { return lane & 3; }
+A2DS_HD int lane_m(int lane) { return (lane >> 3) & 3; }
+A2DS_HD int lane_h(int lane) { return (lane >> 2) & 1; }
 
 struct ElemScratch {
   double X[12], q[24];
@@ -86,11 +97,8 @@ struct ElemScratch {
   double sig[4][9];    // per Gauss point contribution to the tying-point stresses
   double Mq[4][25];    // per Gauss point: tying strain -> membrane/shear strain map
   double sigsum[9];    // tying-point stresses summed over the Gauss points
-  // Operand arrays of the contraction.  BA first holds B (tangent pass), then is
-  // overwritten with B1(q) (geometric pass); afterwards BA / W are reused to stage the
-  // element matrices for the scatter.
-  double BA[24 * LDS_ROWS];
-  double W[24 * LDS_ROWS];   // w C B
+  double E[24 * KE_LD];   // staging of a 24x24 element matrix for the scatter (tangent)
+  double E2[24 * KE_LD];  // second staging buffer (geometric stiffness)
 };
 
 A2DS_HD void cross(const double a[3], const double b[3], double o[3]) {
@@ -561,16 +569,16 @@ struct Want {
 };
 
 // ---- phase 2: lane = (qp, m, h): three columns of B, w C B and B1 ---------------
-// Writes the lane's columns of BA (= B0, or B0 + B1 for the nonlinear model) and of
-// W = w C BA into the scratch operand arrays, hands back the B1(q) columns in
-// registers (Bq, for the geometric pass), publishes the per Gauss point data of the
-// geometric phase, and returns in e_part[9] the lane's
-// contribution to the Gauss point strains (to be summed over the 8 lanes of the
-// Gauss point: warp shuffles on the device, a loop in the host emulation).
+// Returns the lane's columns IN REGISTERS, indexed [strain row][component]:
+//   Bc = B0 (or B0 + B1 for the nonlinear model),  Wc = w C Bc,  Bq = B1(q)
+// (they are the DMMA fragments, see lane_qp above), publishes the per Gauss point data
+// of the geometric phase, and returns in e_part[9] the lane's contribution to the Gauss
+// point strains (to be summed over the 8 lanes of the Gauss point: warp shuffles on the
+// device, a loop in the host emulation).
 A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Want &w,
                           double e_part[9], double &qp_w, double na[2], double nb[2],
-                          double Bq[9][3]) {
-  const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
+                          double Bc[9][3], double Wc[9][3], double Bq[9][3]) {
+  const int qp = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
   const bool need_b1 = w.gmat || w.nonlinear;
   QpGeom g;
   qp_geometry(c, s, qp, need_b1, g);
@@ -578,57 +586,43 @@ A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Wan
   na[0] = g.na[0]; na[1] = g.na[1]; nb[0] = g.nb[0]; nb[1] = g.nb[1];
   if (m == 0 && h == 0) {
     qp_publish(s, qp, g);
+#pragma unroll
     for (int i = 0; i < 25; i++) s.Mq[qp][i] = g.M[i];
   }
   NodeCoef nc;
   node_coef(g, m, nc);
   // coefficient pairs for the geometric stiffness phase (generalised nodes u_m, d_m)
-  if (h == 0) {
-    s.ca[qp][m][0] = nc.a[0]; s.ca[qp][m][1] = nc.a[1];
-    s.cb[qp][m][0] = nc.az[0]; s.cb[qp][m][1] = nc.az[1];
-  } else {
-    s.ca[qp][4 + m][0] = nc.b[0]; s.ca[qp][4 + m][1] = nc.b[1];
-    s.cb[qp][4 + m][0] = nc.cc[0]; s.cb[qp][4 + m][1] = nc.cc[1];
+  if (need_b1) {
+    const int p = 4 * h + m;
+    s.ca[qp][p][0] = h ? nc.b[0] : nc.a[0]; s.ca[qp][p][1] = h ? nc.b[1] : nc.a[1];
+    s.cb[qp][p][0] = h ? nc.cc[0] : nc.az[0]; s.cb[qp][p][1] = h ? nc.cc[1] : nc.az[1];
   }
-  double B0[9][3];
-  strain_columns(s, g, nc, m, h, s.X, 3, s.fn, false, g.t0, g.t1, g.t0, g.t1, true, B0);
+  strain_columns(s, g, nc, m, h, s.X, 3, s.fn, false, g.t0, g.t1, g.t0, g.t1, true, Bc);
   if (need_b1)
     strain_columns(s, g, nc, m, h, s.q, 6, s.dr, true, &g.P1[0], &g.P1[3], &g.P0[0], &g.P0[3],
                    false, Bq);
   const double *qc = &s.q[6 * m + 3 * h];
-  const int col = 6 * m + 3 * h;
+  const double q0 = qc[0], q1 = qc[1], q2 = qc[2];
+#pragma unroll
   for (int r = 0; r < 9; r++) {
-    double e = B0[r][0] * qc[0] + B0[r][1] * qc[1] + B0[r][2] * qc[2];
+    double e = Bc[r][0] * q0 + Bc[r][1] * q1 + Bc[r][2] * q2;
     // nonlinear strain: e = B0 q + 1/2 B1 q.  For the geometric stiffness of a
     // linear-model element only the linear strain enters the stress.
-    if (w.nonlinear) e += 0.5 * (Bq[r][0] * qc[0] + Bq[r][1] * qc[1] + Bq[r][2] * qc[2]);
+    if (w.nonlinear) {
+      e += 0.5 * (Bq[r][0] * q0 + Bq[r][1] * q1 + Bq[r][2] * q2);
+#pragma unroll
+      for (int k = 0; k < 3; k++) Bc[r][k] += Bq[r][k];
+    }
     e_part[r] = e;
   }
+#pragma unroll
   for (int k = 0; k < 3; k++) {
     double b[9], cb[9];
-    for (int r = 0; r < 9; r++) {
-      b[r] = B0[r][k];
-      if (w.nonlinear) b[r] += Bq[r][k];
-    }
+#pragma unroll
+    for (int r = 0; r < 9; r++) b[r] = Bc[r][k];
     apply_C(c.Cs, b, cb);
-    double *pa = &s.BA[(col + k) * LDS_ROWS + 9 * qp];
-    double *pw = &s.W[(col + k) * LDS_ROWS + 9 * qp];
-    for (int r = 0; r < 9; r++) {
-      pa[r] = b[r];
-      pw[r] = g.w * cb[r];
-    }
-  }
-}
-
-// the lane's three B1(q) columns into the A-operand array (geometric pass)
-A2DS_HD void store_b1_columns(ElemScratch &s, int lane, const double Bq[9][3]) {
-  const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
-  const int col = 6 * m + 3 * h;
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    double *p1 = &s.BA[(col + k) * LDS_ROWS + 9 * qp];
-#pragma unroll
-    for (int r = 0; r < 9; r++) p1[r] = Bq[r][k];
+    for (int r = 0; r < 9; r++) Wc[r][k] = g.w * cb[r];
   }
 }
 
@@ -638,23 +632,25 @@ A2DS_HD void store_b1_columns(ElemScratch &s, int lane, const double Bq[9][3]) {
 // over the four Gauss points), and publishes the stresses of the geometric phase.
 A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want &w,
                          const double e_qp[9], double qp_w, const double na[2],
-                         const double nb[2], double r3[3]) {
-  const int qp = lane >> 3, m = (lane >> 1) & 3, h = lane & 1;
+                         const double nb[2], const double Wc[9][3], double r3[3]) {
+  const int qp = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
   double e[9];
+#pragma unroll
   for (int r = 0; r < 9; r++) e[r] = e_qp[r] - c.temperature * c.eth[r];
   {
     // drilling strain of the state: interpolate the nodal values evaluated in the
     // reference's order (interpFields<1,1>, TACSShellElement.h:350)
     double et = 0.0;
+#pragma unroll
     for (int n = 0; n < 4; n++)
       et = A2DS_ADD(et, A2DS_MUL(A2DS_MUL(na[n % 2], nb[n / 2]), s.etn[n]));
     e[8] = et - c.temperature * c.eth[8];
   }
-  const int col = 6 * m + 3 * h;
+#pragma unroll
   for (int k = 0; k < 3; k++) {
-    const double *pw = &s.W[(col + k) * LDS_ROWS + 9 * qp];
     double rr = 0.0;
-    for (int r = 0; r < 9; r++) rr += pw[r] * e[r];
+#pragma unroll
+    for (int r = 0; r < 9; r++) rr += Wc[r][k] * e[r];
     r3[k] = rr;
   }
   if ((w.gmat || w.nonlinear) && m == 0 && h == 0) {
@@ -667,6 +663,7 @@ A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want
     const double sm[5] = {qp_w * st[0], qp_w * st[1], qp_w * st[2], qp_w * st[6], qp_w * st[7]};
     const double *M = s.Mq[qp];
     double dg[5];
+#pragma unroll
     for (int cidx = 0; cidx < 5; cidx++)
       dg[cidx] = M[cidx] * sm[0] + M[5 + cidx] * sm[1] + M[10 + cidx] * sm[2] +
                  M[15 + cidx] * sm[3] + M[20 + cidx] * sm[4];

@@ -1,7 +1,8 @@
 // host_emul.cpp — steps the kernel's per-lane phase functions (mitc4_math.h) lane by
 // lane on the CPU so the arithmetic can be checked without a GPU.  Test-only: the
-// product never builds or loads this; the DMMA contraction and the scatter of the
-// real kernel are replaced by plain loops over the same operand arrays.
+// product never builds or loads this.  The DMMA contraction of the real kernel is
+// replaced by plain loops over the SAME per-lane fragments, using the same
+// (lane -> Gauss point, node, u/theta) mapping; the scatter is replaced by dense output.
 #include <string.h>
 
 #include "../a2d-shells_b200/csrc/mitc4_math.h"
@@ -25,47 +26,53 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   Want w;
   w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1;
   for (int lane = 0; lane < 32; lane++) phase_node(c, s, lane & 3);
-  static double ep[32][9], qw[32], na[32][2], nb[32][2], Bq[32][9][3];
+  static double ep[32][9], qw[32], na[32][2], nb[32][2];
+  static double Bc[32][9][3], Wc[32][9][3], Bq[32][9][3];
+  memset(Bq, 0, sizeof(Bq));
   for (int lane = 0; lane < 32; lane++)
-    lane_columns(c, s, lane, w, ep[lane], qw[lane], na[lane], nb[lane], Bq[lane]);
+    lane_columns(c, s, lane, w, ep[lane], qw[lane], na[lane], nb[lane], Bc[lane], Wc[lane], Bq[lane]);
   memset(res, 0, 24 * sizeof(double));
   for (int lane = 0; lane < 32; lane++) {
-    int qp = lane >> 3;
+    const int qp = lane_qp(lane);
     double e[9], r3[3];
     for (int r = 0; r < 9; r++) {
       e[r] = 0.0;
-      for (int l = 0; l < 8; l++) e[r] += ep[8 * qp + l][r];
+      for (int l = 0; l < 32; l++)
+        if (lane_qp(l) == qp) e[r] += ep[l][r];
     }
-    lane_stress(c, s, lane, w, e, qw[lane], na[lane], nb[lane], r3);
-    int col = 6 * ((lane >> 1) & 3) + 3 * (lane & 1);
+    lane_stress(c, s, lane, w, e, qw[lane], na[lane], nb[lane], Wc[lane], r3);
+    const int col = 6 * lane_m(lane) + 3 * lane_h(lane);
     for (int k = 0; k < 3; k++) res[col + k] += r3[k];
   }
   for (int t = 0; t < 9; t++) sum_tying_stress(s, t);
-  // tangent pass operands, then the geometric pass overwrites BA with B1(q)
-  static double BAk[24 * LDS_ROWS], B1[24 * LDS_ROWS];
-  memcpy(BAk, s.BA, sizeof(BAk));
-  memset(B1, 0, sizeof(B1));
-  if (w.gmat || w.nonlinear) {
-    for (int lane = 0; lane < 32; lane++) store_b1_columns(s, lane, Bq[lane]);
-    memcpy(B1, s.BA, sizeof(B1));
+  // dense operands [dof][k = (strain, qp)] assembled from the per-lane fragments
+  static double BA[24][36], W[24][36], B1[24][36];
+  for (int lane = 0; lane < 32; lane++) {
+    const int qp = lane_qp(lane), col = 6 * lane_m(lane) + 3 * lane_h(lane);
+    for (int r = 0; r < 9; r++)
+      for (int k = 0; k < 3; k++) {
+        BA[col + k][4 * r + qp] = Bc[lane][r][k];
+        W[col + k][4 * r + qp] = Wc[lane][r][k];
+        B1[col + k][4 * r + qp] = Bq[lane][r][k];
+      }
   }
   double geo[576];
   memset(geo, 0, sizeof(geo));
-  for (int p = 0; p < 8; p++)
-    for (int pp = 0; pp < 8; pp++) {
-      double blk[9];
-      geo_block(s, p, pp, blk);
-      int r0 = 6 * (p & 3) + (p >= 4 ? 3 : 0), c0 = 6 * (pp & 3) + (pp >= 4 ? 3 : 0);
-      for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) geo[24 * (r0 + i) + c0 + j] += blk[3 * i + j];
-    }
+  if (w.gmat || w.nonlinear)
+    for (int p = 0; p < 8; p++)
+      for (int pp = 0; pp < 8; pp++) {
+        double blk[9];
+        geo_block(s, p, pp, blk);
+        int r0 = 6 * (p & 3) + (p >= 4 ? 3 : 0), c0 = 6 * (pp & 3) + (pp >= 4 ? 3 : 0);
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) geo[24 * (r0 + i) + c0 + j] += blk[3 * i + j];
+      }
   for (int r = 0; r < 24; r++)
     for (int cc = 0; cc < 24; cc++) {
       double k = 0.0, gm = 0.0;
       for (int t = 0; t < 36; t++) {
-        k += BAk[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t];
-        gm += B1[r * LDS_ROWS + t] * s.W[cc * LDS_ROWS + t] +
-              s.W[r * LDS_ROWS + t] * B1[cc * LDS_ROWS + t];
+        k += BA[r][t] * W[cc][t];
+        gm += B1[r][t] * W[cc][t] + W[r][t] * B1[cc][t];
       }
       if (w.nonlinear) k += geo[24 * r + cc];
       K[24 * r + cc] = k;

@@ -39,7 +39,7 @@ def test_product_does_not_reference_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".h", ".cpp", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower() or f == "__init__.py" and False, (dirpath, f)
+                assert "oracle" not in txt.lower(), (dirpath, f)
     hdr = open(os.path.join(ROOT, "include", "a2ds.h")).read()
     assert "oracle" not in hdr.lower()
 

@@ -12,7 +12,7 @@ import pytest
 from conftest import has_gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SHIM = os.path.join(ROOT, "a2d-shells_b200", "lib", "libtacs_a2ds_shim.so")
+SHIM = os.path.join(ROOT, "tests", "_shim", "libtacs_a2ds_shim.so")
 
 
 def _run(preload):
