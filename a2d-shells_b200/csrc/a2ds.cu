@@ -143,12 +143,13 @@ __device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2]
 }
 
 // 64 geometric-stiffness 3x3 blocks (generalised node pairs), 2 per lane, added in place
-__device__ __forceinline__ void add_geo_blocks(ElemScratch &s, double *E, double scale, int lane) {
+__device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWork &wk, double *E,
+                                               double scale, int lane) {
 #pragma unroll
   for (int pass = 0; pass < 2; pass++) {
     const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
     double blk[9];
-    geo_block(s, pr, pc, blk);
+    geo_block(gm, wk, pr, pc, blk);
     const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -157,128 +158,152 @@ __device__ __forceinline__ void add_geo_blocks(ElemScratch &s, double *E, double
   }
 }
 
+// A warp prepares NB elements at a time: the node phase and the Gauss-point phase then run
+// on NB*4 distinct work items (one lane each) instead of 8 redundant copies per element.
+static const int NB = 4;
+struct WarpScratch {
+  int comp[NB], nodes[NB][4], koff[NB][16], goff[NB][16];
+  ElemGeom geo[NB];
+  ElemWork work;  // last: its second staging buffer is dropped when no G is assembled
+};
+
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT, NL))
     k_assemble(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  ElemScratch &s = *reinterpret_cast<ElemScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  ElemWork &wk = ws.work;
   const unsigned FULL = 0xffffffffu;
   Want w;
   w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL;
+  const bool need_state = GMAT || NL;
 
-  // Gather of element i+1 is issued while element i is being processed (the loads only
-  // land in registers; they are written to the scratch at the top of the next trip).
-  struct Fetch { int comp, nd, koff, goff; double x, q; };
-  auto fetch = [&](int it_) {
-    Fetch f;
-    const int e = p.elem_list ? __ldg(&p.elem_list[it_]) : it_;
-    f.comp = __ldg(&p.elem_comp[e]);
-    f.nd = __ldg(&p.conn[4 * e + (lane & 3)]);  // lane l holds node l & 3
-    const int nx = __shfl_sync(FULL, f.nd, lane / 3);
-    const int nq = __shfl_sync(FULL, f.nd, lane / 6);
-    f.x = (lane < 12) ? __ldg(&p.X[3 * (size_t)nx + lane % 3]) : 0.0;
-    f.q = (lane < 24) ? __ldg(&p.u[6 * (size_t)nq + lane % 6]) : 0.0;
-    f.koff = (KMAT && lane < 16) ? __ldg(&p.Koff[16 * (size_t)e + lane]) : -1;
-    f.goff = (GMAT && lane < 16) ? __ldg(&p.Goff[16 * (size_t)e + lane]) : -1;
-    return f;
-  };
-  const int stride = gridDim.x * warps_per_block;
-  int it = blockIdx.x * warps_per_block + warp;
-  Fetch nxt;
-  if (it < p.n_list) nxt = fetch(it);
-  for (; it < p.n_list; it += stride) {
-    const Fetch cur = nxt;
-    if (it + stride < p.n_list) nxt = fetch(it + stride);
-    const CompData &c = p.comps[cur.comp];
-    const int nd = cur.nd, koff = cur.koff, goff = cur.goff;
-    if (lane < 12) s.X[lane] = cur.x;
-    if (lane < 24) s.q[lane] = cur.q;
+  const int n_groups = (p.n_list + NB - 1) / NB;
+  for (int grp = blockIdx.x * warps_per_block + warp; grp < n_groups;
+       grp += gridDim.x * warps_per_block) {
+    const int base = grp * NB;
+    const int cnt = min(NB, p.n_list - base);
+
+    // ---- gather the batch: coordinates, state, block offsets --------------------------
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      if (j < cnt) {
+        const int e = p.elem_list ? __ldg(&p.elem_list[base + j]) : base + j;
+        const int nd = __ldg(&p.conn[4 * e + (lane & 3)]);  // lane l holds node l & 3
+        const int nx = __shfl_sync(FULL, nd, lane / 3);
+        const int nq = __shfl_sync(FULL, nd, lane / 6);
+        if (lane < 12) ws.geo[j].X[lane] = __ldg(&p.X[3 * (size_t)nx + lane % 3]);
+        if (lane < 24) ws.geo[j].q[lane] = __ldg(&p.u[6 * (size_t)nq + lane % 6]);
+        if (lane < 4) ws.nodes[j][lane] = nd;
+        if (lane == 4) ws.comp[j] = __ldg(&p.elem_comp[e]);
+        if (KMAT && lane < 16) ws.koff[j][lane] = __ldg(&p.Koff[16 * (size_t)e + lane]);
+        if (GMAT && lane >= 16) ws.goff[j][lane - 16] = __ldg(&p.Goff[16 * (size_t)e + lane - 16]);
+      }
+    }
     __syncwarp();
 
-    // ---- node phase ---------------------------------------------------------
-    phase_node(c, s, lane & 3);
-    __syncwarp();
-
-    // ---- column phase: the lane's fragments of B, w C B and B1(q) -----------------
-    double Bc[9][3], Wc[9][3], Bq[9][3];
+    // ---- node phase: lane = (element of the batch, node) --------------------------------
     {
-      double ep[9], qw, na[2], nb[2];
-      lane_columns(c, s, lane, w, ep, qw, na, nb, Bc, Wc, Bq);
-      if (RES || GMAT || NL) {
-        // strains: sum over the 8 lanes of a Gauss point (lane bits 2..4)
-#pragma unroll
-        for (int r = 0; r < 9; r++) {
-          ep[r] += __shfl_xor_sync(FULL, ep[r], 4);
-          ep[r] += __shfl_xor_sync(FULL, ep[r], 8);
-          ep[r] += __shfl_xor_sync(FULL, ep[r], 16);
-        }
-        double r3[3];
-        lane_stress(c, s, lane, w, ep, qw, na, nb, Wc, r3);
-        if (RES) {
-          // residual: sum over the 4 Gauss points (lane bits 0..1)
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            r3[k] += __shfl_xor_sync(FULL, r3[k], 1);
-            r3[k] += __shfl_xor_sync(FULL, r3[k], 2);
-          }
-          const int nm = __shfl_sync(FULL, nd, lane_m(lane));
-          if ((lane & 3) == 0) {
-            double *r = &p.res[6 * (size_t)nm + 3 * lane_h(lane)];
-            atomicAdd(r, r3[0]);
-            atomicAdd(r + 1, r3[1]);
-            atomicAdd(r + 2, r3[2]);
-          }
-        }
-      }
+      const int j = (lane >> 2) & (NB - 1);
+      if (lane < 4 * NB && j < cnt) phase_node(p.comps[ws.comp[j]], ws.geo[j], lane & 3);
     }
+    __syncwarp();
+    // ---- Gauss point phase: lane = (element of the batch, Gauss point) ------------------
+    {
+      const int j = (lane >> 2) & (NB - 1);
+      if (lane < 4 * NB && j < cnt) phase_qp(p.comps[ws.comp[j]], ws.geo[j], lane & 3, need_state);
+    }
+    __syncwarp();
 
-    // ---- contractions on the FP64 tensor path, operands straight from registers ------
-    //      K = B^T (w C B),   G = B1^T W + W^T B1  (upper tiles only)
-    double kacc[6][2], gacc[6][2];
-    if (KMAT) {
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+      const ElemGeom &gm = ws.geo[j];
+      const CompData &c = p.comps[ws.comp[j]];
+
+      // ---- column phase + contractions on the FP64 tensor path ----------------------
+      // The lane's columns of B, w C B and B1(q) ARE the DMMA fragments (mitc4_math.h), so
+      // operands go from the FMA pipe to the tensor path without leaving registers.
+      //      K = B^T (w C B),   G = B1^T W + W^T B1      (upper tiles only)
+      // Order: B0/W -> strains, residual -> K pass -> B1 -> G pass, so that B0 and B1 are
+      // never live together (the nonlinear model needs B1 first: B = B0 + B1).
+      double Bc[9][3], Wc[9][3], Bq[9][3];
+      double kacc[6][2], gacc[6][2];
+      if (NL) lane_b1(gm, wk, lane, Bq);
+      {
+        double ep[9];
+        lane_b0w(c, gm, lane, w, Bq, ep, Bc, Wc);
+        if (RES || GMAT || NL) {
+          // strains: sum over the 8 lanes of a Gauss point (lane bits 2..4)
 #pragma unroll
-      for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = 0.0;
+          for (int r = 0; r < 9; r++) {
+            ep[r] += __shfl_xor_sync(FULL, ep[r], 4);
+            ep[r] += __shfl_xor_sync(FULL, ep[r], 8);
+            ep[r] += __shfl_xor_sync(FULL, ep[r], 16);
+          }
+          double r3[3];
+          lane_stress(c, gm, wk, lane, w, ep, Wc, r3);
+          if (RES) {
+            // residual: sum over the 4 Gauss points (lane bits 0..1)
 #pragma unroll
-      for (int ks = 0; ks < 9; ks++) {
-        int idx = 0;
-#pragma unroll
-        for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-          for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], Bc[ks][ti], Wc[ks][tj]);
+            for (int k = 0; k < 3; k++) {
+              r3[k] += __shfl_xor_sync(FULL, r3[k], 1);
+              r3[k] += __shfl_xor_sync(FULL, r3[k], 2);
+            }
+            if ((lane & 3) == 0) {
+              double *r = &p.res[6 * (size_t)ws.nodes[j][lane_m(lane)] + 3 * lane_h(lane)];
+              atomicAdd(r, r3[0]);
+              atomicAdd(r + 1, r3[1]);
+              atomicAdd(r + 2, r3[2]);
+            }
+          }
+        }
       }
-    }
-    if (GMAT) {
+      if (KMAT) {
 #pragma unroll
-      for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
+        for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = 0.0;
 #pragma unroll
-      for (int ks = 0; ks < 9; ks++) {
-        // two products per tile; all first products, then all second ones, so that
-        // consecutive DMMAs never wait on the same accumulator
-        int idx = 0;
+        for (int ks = 0; ks < 9; ks++) {
+          int idx = 0;
 #pragma unroll
-        for (int ti = 0; ti < 3; ti++)
+          for (int ti = 0; ti < 3; ti++)
 #pragma unroll
-          for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Bq[ks][ti], Wc[ks][tj]);
-        idx = 0;
-#pragma unroll
-        for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-          for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Wc[ks][ti], Bq[ks][tj]);
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], Bc[ks][ti], Wc[ks][tj]);
+        }
       }
+      if (GMAT) {
+        lane_b1(gm, wk, lane, Bq);
+#pragma unroll
+        for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 9; ks++) {
+          // two products per tile; all first products, then all second ones, so that
+          // consecutive DMMAs never wait on the same accumulator
+          int idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Bq[ks][ti], Wc[ks][tj]);
+          idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Wc[ks][ti], Bq[ks][tj]);
+        }
+      }
+      // ---- stage, add the geometric blocks, scatter -------------------------------------
+      if (KMAT) stage_tiles(wk.E, kacc, p.alpha, lane);
+      if (GMAT) stage_tiles(wk.E2, gacc, 1.0, lane);
+      if ((GMAT || NL) && lane < 9) sum_tying_stress(wk, lane);
+      __syncwarp();
+      if (GMAT) add_geo_blocks(gm, wk, wk.E2, 1.0, lane);
+      else if (NL && KMAT) add_geo_blocks(gm, wk, wk.E, p.alpha, lane);
+      if (GMAT || NL) __syncwarp();
+      if (KMAT) scatter_matrix(wk.E, p.Kval, ws.koff[j][lane & 15], lane);
+      if (GMAT) scatter_matrix(wk.E2, p.Gval, ws.goff[j][lane & 15], lane);
+      __syncwarp();
     }
-    // ---- stage, add the geometric blocks, scatter -----------------------------------
-    if (KMAT) stage_tiles(s.E, kacc, p.alpha, lane);
-    if (GMAT) stage_tiles(s.E2, gacc, 1.0, lane);
-    if ((GMAT || NL) && lane < 9) sum_tying_stress(s, lane);
-    __syncwarp();
-    if (GMAT) add_geo_blocks(s, s.E2, 1.0, lane);
-    else if (NL && KMAT) add_geo_blocks(s, s.E, p.alpha, lane);
-    if (GMAT || NL) __syncwarp();
-    if (KMAT) scatter_matrix(s.E, p.Kval, koff, lane);
-    if (GMAT) scatter_matrix(s.E2, p.Gval, goff, lane);
-    __syncwarp();
   }
 }
 
@@ -890,7 +915,8 @@ extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
 // ---- assembly ------------------------------------------------------------------
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_one(a2ds_ctx *c, KParams &p) {
-  const size_t per_warp = (sizeof(ElemScratch) + 15) & ~size_t(15);
+  const size_t raw = GMAT ? sizeof(WarpScratch) : sizeof(WarpScratch) - sizeof(ElemWork::E2);
+  const size_t per_warp = (raw + 15) & ~size_t(15);
   p.scratch_bytes = (int)per_warp;
   const int wpb = c->warps_per_block;
   const size_t smem = per_warp * (size_t)wpb;
@@ -905,7 +931,7 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   int per_sm = 1;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
   if (per_sm < 1) return fail("k_assemble does not fit on an SM");
-  const int want = (p.n_list + wpb - 1) / wpb;
+  const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
   kern<<<grid, wpb * 32, smem, c->stream>>>(p);
   CU(cudaGetLastError());

@@ -1,11 +1,12 @@
 // mitc4_math.h — per-lane arithmetic of the MITC4 director-shell assembly kernel.
 //
-// One warp owns one element.  The warp walks through a fixed sequence of
-// phases; inside a phase every lane executes the same straight-line code on its
-// own slice of the element (a node, a Gauss point, three columns of the strain
-// matrix, a pair of nodes ...) and the phases communicate through an
-// ElemScratch record that lives in shared memory.  The functions below are the
-// phase bodies.  They are written against plain pointers so that the very same
+// A warp walks through a fixed sequence of phases; inside a phase every lane executes
+// the same straight-line code on its own work item (a node, a Gauss point, three columns
+// of the strain matrix, a pair of nodes ...) and the phases communicate through ElemGeom /
+// ElemWork records that live in shared memory.  Node and Gauss-point phases are run for a
+// small batch of elements at once (one lane per node / per Gauss point), the column,
+// contraction and scatter phases then take the elements of the batch one at a time with
+// all 32 lanes.  The functions below are the phase bodies.  They are written against plain pointers so that the very same
 // code can be stepped lane by lane on the host (tests/host_emul.cpp) — the CUDA
 // kernel in assemble.cu only adds the warp synchronisation between phases, the
 // DMMA contraction and the scatter.
@@ -68,8 +69,8 @@ struct CompData {
   int transform;       // 0 natural, 1 reference axis
 };
 
-// leading dimension of the staged 24x24 element matrix (24 + pad against bank conflicts)
-static const int KE_LD = 26;
+// leading dimension of the staged 24x24 element matrix (odd: conflict-free rows and columns)
+static const int KE_LD = 25;
 
 // Lane -> work item.  lane = 4 c + qp with c = 2 m + h:
 //   qp = lane & 3   Gauss point,  m = (lane >> 3) & 3   node,  h = (lane >> 2) & 1   0: u, 1: theta
@@ -83,19 +84,36 @@ A2DS_HD int lane_qp(int lane) { return lane & 3; }
 A2DS_HD int lane_m(int lane) { return (lane >> 3) & 3; }
 A2DS_HD int lane_h(int lane) { return (lane >> 2) & 1; }
 
-struct ElemScratch {
+// Per Gauss point data, produced once per element by phase_qp and read by the lanes of
+// that Gauss point in the column phase.
+struct QpData {
+  double t0[3], t1[3];  // T columns 0, 1
+  double S[6], Sz[6];   // (Xd^-1 T)[i][j] and its thickness derivative, i = 0..2, j = 0..1
+  double M[25];         // (e0,e1,e2,e6,e7) = M (g11,g12,g13,g22,g23)
+  double w;             // det(Xd) * quadrature weight
+  double P0[6], P1[6];  // T u0x[:,j], T u1x[:,j] (j = 0,1) for the state
+  double Pq[6];         // T T^T (symmetric)
+};
+
+// Element geometry: filled by the node phase (one lane per node) and the Gauss point
+// phase (one lane per Gauss point).  A warp prepares a small batch of elements at once so
+// that those phases run on distinct work items instead of 8 redundant copies.
+struct ElemGeom {
   double X[12], q[24];
   double fn[12];   // unit node normals            (TacsShellComputeNodeNormals)
   double dr[12];   // directors d_m = theta_m x fn_m (TACSDirector.h:244-267)
   double t0n[12], t1n[12], wn[12];  // node frames: T columns 0,1 and t0 x t1
   double Sn[16];   // per node: (Xd^-1 T)[0..1][0..1]
   double etn[4];   // nodal drill strain of the state, evaluated in the reference's order
-  double Pq[4][6]; // per Gauss point: T T^T (symmetric)
+  QpData qp[4];
+};
+
+// Working set of the element currently being contracted / scattered
+struct ElemWork {
   double ca[4][8][2], cb[4][8][2];  // per Gauss point, per generalised node
                                     // (u_0..u_3, d_0..d_3): coefficient pairs
-  double sg[4][3]; // per Gauss point: w*s3, w*s4, w*s5 (bending resultants)
+  double sg[4][3];     // per Gauss point: w*s3, w*s4, w*s5 (bending resultants)
   double sig[4][9];    // per Gauss point contribution to the tying-point stresses
-  double Mq[4][25];    // per Gauss point: tying strain -> membrane/shear strain map
   double sigsum[9];    // tying-point stresses summed over the Gauss points
   double E[24 * KE_LD];   // staging of a 24x24 element matrix for the scatter (tangent)
   double E2[24 * KE_LD];  // second staging buffer (geometric stiffness)
@@ -233,7 +251,7 @@ A2DS_HD double sdet2(double a, double b, double c, double d) {  // a*b - c*d
   return A2DS_ADD(A2DS_MUL(a, b), -A2DS_MUL(c, d));
 }
 
-A2DS_HD void phase_node(const CompData &c, ElemScratch &s, int m) {
+A2DS_HD void phase_node(const CompData &c, ElemGeom &s, int m) {
   double Xxi[3], Xeta[3];
   edge_xi(s.X, 3, m / 2, Xxi);    // X,xi at the node (eta = +-1)
   edge_eta(s.X, 3, m % 2, Xeta);  // X,eta at the node (xi = +-1)
@@ -326,7 +344,7 @@ struct QpGeom {
 
 // ---- phase 2a: Gauss point geometry (lane >> 3) ------------------------------
 // TACSShellElement.h:520-534 and TacsShellComputeDispGrad (TACSShellUtilities.h:361-421)
-A2DS_HD void qp_geometry(const CompData &c, const ElemScratch &s, int qp, bool need_state,
+A2DS_HD void qp_geometry(const CompData &c, const ElemGeom &s, int qp, bool need_state,
                          QpGeom &g) {
   const double xi = (qp & 1) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
   const double eta = (qp & 2) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
@@ -411,15 +429,39 @@ A2DS_HD void qp_geometry(const CompData &c, const ElemScratch &s, int qp, bool n
   }
 }
 
-// publish the per Gauss point data the geometric-stiffness phase needs
-A2DS_HD void qp_publish(ElemScratch &s, int qp, const QpGeom &g) {
+// ---- phase 2: Gauss point qp of one element (one lane per Gauss point) -------------
+A2DS_HD void phase_qp(const CompData &c, ElemGeom &s, int qp, bool need_state) {
+  QpGeom g;
+  qp_geometry(c, s, qp, need_state, g);
+  QpData &d = s.qp[qp];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { d.t0[k] = g.t0[k]; d.t1[k] = g.t1[k]; }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) { d.S[2 * i + j] = g.S[3 * i + j]; d.Sz[2 * i + j] = g.Sz[3 * i + j]; }
+#pragma unroll
+  for (int i = 0; i < 25; i++) d.M[i] = g.M[i];
+  d.w = g.w;
+  if (need_state) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) { d.P0[i] = g.P0[i]; d.P1[i] = g.P1[i]; }
+  }
   const double *t0 = g.t0, *t1 = g.t1, *tn = g.tn;
-  s.Pq[qp][0] = t0[0] * t0[0] + t1[0] * t1[0] + tn[0] * tn[0];
-  s.Pq[qp][1] = t0[0] * t0[1] + t1[0] * t1[1] + tn[0] * tn[1];
-  s.Pq[qp][2] = t0[0] * t0[2] + t1[0] * t1[2] + tn[0] * tn[2];
-  s.Pq[qp][3] = t0[1] * t0[1] + t1[1] * t1[1] + tn[1] * tn[1];
-  s.Pq[qp][4] = t0[1] * t0[2] + t1[1] * t1[2] + tn[1] * tn[2];
-  s.Pq[qp][5] = t0[2] * t0[2] + t1[2] * t1[2] + tn[2] * tn[2];
+  d.Pq[0] = t0[0] * t0[0] + t1[0] * t1[0] + tn[0] * tn[0];
+  d.Pq[1] = t0[0] * t0[1] + t1[0] * t1[1] + tn[0] * tn[1];
+  d.Pq[2] = t0[0] * t0[2] + t1[0] * t1[2] + tn[0] * tn[2];
+  d.Pq[3] = t0[1] * t0[1] + t1[1] * t1[1] + tn[1] * tn[1];
+  d.Pq[4] = t0[1] * t0[2] + t1[1] * t1[2] + tn[1] * tn[2];
+  d.Pq[5] = t0[2] * t0[2] + t1[2] * t1[2] + tn[2] * tn[2];
+}
+
+// 1D shape functions at Gauss point qp
+A2DS_HD void qp_shape(int qp, double na[2], double nb[2]) {
+  const double xi = (qp & 1) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
+  const double eta = (qp & 2) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
+  na[0] = 0.5 * (1.0 - xi); na[1] = 0.5 * (1.0 + xi);
+  nb[0] = 0.5 * (1.0 - eta); nb[1] = 0.5 * (1.0 + eta);
 }
 
 // Coefficients of node m at a Gauss point: derivative of the local displacement
@@ -428,16 +470,17 @@ A2DS_HD void qp_publish(ElemScratch &s, int qp, const QpGeom &g) {
 //   d u0x[i][j] / d d_mk = T[k][i] b[j]     d u1x[i][j] / d d_mk = T[k][i] cc[j]
 struct NodeCoef { double a[2], az[2], b[2], cc[2]; };
 
-A2DS_HD void node_coef(const QpGeom &g, int m, NodeCoef &n) {
+A2DS_HD void node_coef(const QpData &g, const double na[2], const double nb[2], int m,
+                       NodeCoef &n) {
   const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
-  const double nam = (m % 2) ? g.na[1] : g.na[0], nbm = (m / 2) ? g.nb[1] : g.nb[0];
+  const double nam = (m % 2) ? na[1] : na[0], nbm = (m / 2) ? nb[1] : nb[0];
   const double Nxi = dN * nbm, Neta = nam * dM, N = nam * nbm;
 #pragma unroll
   for (int j = 0; j < 2; j++) {
-    n.a[j] = Nxi * g.S[j] + Neta * g.S[3 + j];
-    n.az[j] = Nxi * g.Sz[j] + Neta * g.Sz[3 + j];
-    n.b[j] = N * g.S[6 + j];
-    n.cc[j] = n.a[j] + N * g.Sz[6 + j];
+    n.a[j] = Nxi * g.S[j] + Neta * g.S[2 + j];
+    n.az[j] = Nxi * g.Sz[j] + Neta * g.Sz[2 + j];
+    n.b[j] = N * g.S[4 + j];
+    n.cc[j] = n.a[j] + N * g.Sz[4 + j];
   }
 }
 
@@ -447,13 +490,14 @@ A2DS_HD void node_coef(const QpGeom &g, int m, NodeCoef &n) {
 //   field,xi / field,eta on the node's two edges and at the centre feed the tying rows,
 //   `normal` averaged on the edges feeds the transverse-shear tying rows,
 //   bending rows:  B0 uses the T columns, B1 uses T u1x[:,j] / T u0x[:,j].
-A2DS_HD void strain_columns(const ElemScratch &s, const QpGeom &g, const NodeCoef &nc, int m,
-                            int h, const double *field, int ld, const double *normal,
+A2DS_HD void strain_columns(const ElemGeom &s, const QpData &g, const double na[2],
+                            const double nb[2], const NodeCoef &nc, int m, int h,
+                            const double *field, int ld, const double *normal,
                             bool has_a, const double *pa0, const double *pa1, const double *pz0,
                             const double *pz1, bool drill, double B[9][3]) {
   const int sx = m % 2, sy = m / 2;  // which xi / eta side the node sits on
   const double dN = sx ? 0.5 : -0.5, dM = sy ? 0.5 : -0.5;
-  const double nas = sx ? g.na[1] : g.na[0], nbs = sy ? g.nb[1] : g.nb[0];
+  const double nas = sx ? na[1] : na[0], nbs = sy ? nb[1] : nb[0];
   const double fn[3] = {s.fn[3 * m], s.fn[3 * m + 1], s.fn[3 * m + 2]};
   double fxi[3], feta[3];  // field,xi on the node's eta edge; field,eta on its xi edge
   edge_xi(field, ld, sy, fxi);
@@ -535,7 +579,7 @@ A2DS_HD void strain_columns(const ElemScratch &s, const QpGeom &g, const NodeCoe
       const double Neta = (sx == n % 2) ? dM : 0.0;
       const double a0 = Nxi * s.Sn[4 * n] + Neta * s.Sn[4 * n + 2];
       const double a1 = Nxi * s.Sn[4 * n + 1] + Neta * s.Sn[4 * n + 3];
-      const double Nq = g.na[n % 2] * g.nb[n / 2];
+      const double Nq = na[n % 2] * nb[n / 2];
 #pragma unroll
       for (int k = 0; k < 3; k++)
         acc[k] += Nq * (0.5 * (a0 * s.t1n[3 * n + k] - a1 * s.t0n[3 * n + k]));
@@ -568,39 +612,41 @@ struct Want {
   bool nonlinear;        // element uses the nonlinear strain model (tangent/residual)
 };
 
-// ---- phase 2: lane = (qp, m, h): three columns of B, w C B and B1 ---------------
-// Returns the lane's columns IN REGISTERS, indexed [strain row][component]:
-//   Bc = B0 (or B0 + B1 for the nonlinear model),  Wc = w C Bc,  Bq = B1(q)
-// (they are the DMMA fragments, see lane_qp above), publishes the per Gauss point data
-// of the geometric phase, and returns in e_part[9] the lane's contribution to the Gauss
-// point strains (to be summed over the 8 lanes of the Gauss point: warp shuffles on the
-// device, a loop in the host emulation).
-A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Want &w,
-                          double e_part[9], double &qp_w, double na[2], double nb[2],
-                          double Bc[9][3], double Wc[9][3], double Bq[9][3]) {
+// ---- column phase: lane = (qp, m, h) ------------------------------------------------
+// The lane's three columns are returned IN REGISTERS, indexed [strain row][component]
+// (they are the DMMA fragments, see lane_qp above):
+//   lane_b1 : Bq = B1(q), the state dependent part (only when G or the nonlinear model is
+//             asked for); also publishes the coefficient pairs of the geometric phase
+//   lane_b0w: Bc = B0 (+ Bq for the nonlinear model), Wc = w C Bc, and the lane's
+//             contribution e_part[9] to the Gauss point strains (summed over the 8 lanes
+//             of the Gauss point with warp shuffles / a loop in the host emulation)
+// They are separate so that the kernel can run the tangent contraction between them and
+// never holds B0, W and B1 at the same time.
+A2DS_HD void lane_b1(const ElemGeom &s, ElemWork &wk, int lane, double Bq[9][3]) {
   const int qp = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
-  const bool need_b1 = w.gmat || w.nonlinear;
-  QpGeom g;
-  qp_geometry(c, s, qp, need_b1, g);
-  qp_w = g.w;
-  na[0] = g.na[0]; na[1] = g.na[1]; nb[0] = g.nb[0]; nb[1] = g.nb[1];
-  if (m == 0 && h == 0) {
-    qp_publish(s, qp, g);
-#pragma unroll
-    for (int i = 0; i < 25; i++) s.Mq[qp][i] = g.M[i];
-  }
+  const QpData &g = s.qp[qp];
+  double na[2], nb[2];
+  qp_shape(qp, na, nb);
   NodeCoef nc;
-  node_coef(g, m, nc);
+  node_coef(g, na, nb, m, nc);
   // coefficient pairs for the geometric stiffness phase (generalised nodes u_m, d_m)
-  if (need_b1) {
-    const int p = 4 * h + m;
-    s.ca[qp][p][0] = h ? nc.b[0] : nc.a[0]; s.ca[qp][p][1] = h ? nc.b[1] : nc.a[1];
-    s.cb[qp][p][0] = h ? nc.cc[0] : nc.az[0]; s.cb[qp][p][1] = h ? nc.cc[1] : nc.az[1];
-  }
-  strain_columns(s, g, nc, m, h, s.X, 3, s.fn, false, g.t0, g.t1, g.t0, g.t1, true, Bc);
-  if (need_b1)
-    strain_columns(s, g, nc, m, h, s.q, 6, s.dr, true, &g.P1[0], &g.P1[3], &g.P0[0], &g.P0[3],
-                   false, Bq);
+  const int p = 4 * h + m;
+  wk.ca[qp][p][0] = h ? nc.b[0] : nc.a[0]; wk.ca[qp][p][1] = h ? nc.b[1] : nc.a[1];
+  wk.cb[qp][p][0] = h ? nc.cc[0] : nc.az[0]; wk.cb[qp][p][1] = h ? nc.cc[1] : nc.az[1];
+  strain_columns(s, g, na, nb, nc, m, h, s.q, 6, s.dr, true, &g.P1[0], &g.P1[3], &g.P0[0],
+                 &g.P0[3], false, Bq);
+}
+
+A2DS_HD void lane_b0w(const CompData &c, const ElemGeom &s, int lane, const Want &w,
+                      const double Bq[9][3], double e_part[9], double Bc[9][3],
+                      double Wc[9][3]) {
+  const int qp = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
+  const QpData &g = s.qp[qp];
+  double na[2], nb[2];
+  qp_shape(qp, na, nb);
+  NodeCoef nc;
+  node_coef(g, na, nb, m, nc);
+  strain_columns(s, g, na, nb, nc, m, h, s.X, 3, s.fn, false, g.t0, g.t1, g.t0, g.t1, true, Bc);
   const double *qc = &s.q[6 * m + 3 * h];
   const double q0 = qc[0], q1 = qc[1], q2 = qc[2];
 #pragma unroll
@@ -615,6 +661,7 @@ A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Wan
     }
     e_part[r] = e;
   }
+  const double gw = g.w;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     double b[9], cb[9];
@@ -622,7 +669,7 @@ A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Wan
     for (int r = 0; r < 9; r++) b[r] = Bc[r][k];
     apply_C(c.Cs, b, cb);
 #pragma unroll
-    for (int r = 0; r < 9; r++) Wc[r][k] = g.w * cb[r];
+    for (int r = 0; r < 9; r++) Wc[r][k] = gw * cb[r];
   }
 }
 
@@ -630,10 +677,13 @@ A2DS_HD void lane_columns(const CompData &c, ElemScratch &s, int lane, const Wan
 // e_qp[9] is the Gauss point strain summed over the lanes of the point.  Returns the
 // lane's three residual entries for this Gauss point, r = W^T (e - T eth) (to be summed
 // over the four Gauss points), and publishes the stresses of the geometric phase.
-A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want &w,
-                         const double e_qp[9], double qp_w, const double na[2],
-                         const double nb[2], const double Wc[9][3], double r3[3]) {
+A2DS_HD void lane_stress(const CompData &c, const ElemGeom &s, ElemWork &wk, int lane,
+                         const Want &w, const double e_qp[9], const double Wc[9][3],
+                         double r3[3]) {
   const int qp = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
+  double na[2], nb[2];
+  qp_shape(qp, na, nb);
+  const double qp_w = s.qp[qp].w;
   double e[9];
 #pragma unroll
   for (int r = 0; r < 9; r++) e[r] = e_qp[r] - c.temperature * c.eth[r];
@@ -657,11 +707,11 @@ A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want
     double st[9];
     apply_C(c.Cs, e, st);
     // stresses feeding the geometric terms
-    s.sg[qp][0] = qp_w * st[3]; s.sg[qp][1] = qp_w * st[4]; s.sg[qp][2] = qp_w * st[5];
+    wk.sg[qp][0] = qp_w * st[3]; wk.sg[qp][1] = qp_w * st[4]; wk.sg[qp][2] = qp_w * st[5];
     // pull the membrane/shear stresses back to the tying points:
     // dU/dg5 = M^T (w s_ms), then the tying interpolation transposed
     const double sm[5] = {qp_w * st[0], qp_w * st[1], qp_w * st[2], qp_w * st[6], qp_w * st[7]};
-    const double *M = s.Mq[qp];
+    const double *M = s.qp[qp].M;
     double dg[5];
 #pragma unroll
     for (int cidx = 0; cidx < 5; cidx++)
@@ -669,16 +719,16 @@ A2DS_HD void lane_stress(const CompData &c, ElemScratch &s, int lane, const Want
                  M[15 + cidx] * sm[3] + M[20 + cidx] * sm[4];
     // tying point order (QuadBasis.h:530-564): g11 @eta=-+1, g22 @xi=-+1, g12 centre,
     // g23 @xi=-+1, g13 @eta=-+1; dg order (g11, g12, g13, g22, g23)
-    s.sig[qp][0] = nb[0] * dg[0]; s.sig[qp][1] = nb[1] * dg[0];
-    s.sig[qp][2] = na[0] * dg[3]; s.sig[qp][3] = na[1] * dg[3];
-    s.sig[qp][4] = dg[1];
-    s.sig[qp][5] = na[0] * dg[4]; s.sig[qp][6] = na[1] * dg[4];
-    s.sig[qp][7] = nb[0] * dg[2]; s.sig[qp][8] = nb[1] * dg[2];
+    wk.sig[qp][0] = nb[0] * dg[0]; wk.sig[qp][1] = nb[1] * dg[0];
+    wk.sig[qp][2] = na[0] * dg[3]; wk.sig[qp][3] = na[1] * dg[3];
+    wk.sig[qp][4] = dg[1];
+    wk.sig[qp][5] = na[0] * dg[4]; wk.sig[qp][6] = na[1] * dg[4];
+    wk.sig[qp][7] = nb[0] * dg[2]; wk.sig[qp][8] = nb[1] * dg[2];
   }
 }
 
 // tying-point stresses summed over the Gauss points (lanes 0..8, after lane_stress)
-A2DS_HD void sum_tying_stress(ElemScratch &s, int t) {
+A2DS_HD void sum_tying_stress(ElemWork &s, int t) {
   s.sigsum[t] = s.sig[0][t] + s.sig[1][t] + s.sig[2][t] + s.sig[3][t];
 }
 
@@ -688,7 +738,7 @@ A2DS_HD void sum_tying_stress(ElemScratch &s, int t) {
 //   rows of a director node:    skew(fn_m) * blk      (d = theta x fn)
 //   columns of a director node: blk * skew(fn_m)^T
 // (TACSLinearizedRotation::addDirectorJacobian, TACSDirector.h:369-486)
-A2DS_HD void geo_block(const ElemScratch &s, int p, int pp, double out[9]) {
+A2DS_HD void geo_block(const ElemGeom &gm, const ElemWork &s, int p, int pp, double out[9]) {
   const double *sig = s.sigsum;  // tying point stresses (summed over the Gauss points)
   const int m = p & 3, mm = pp & 3;
   const bool pd = p >= 4, ppd = pp >= 4;
@@ -715,13 +765,13 @@ A2DS_HD void geo_block(const ElemScratch &s, int p, int pp, double out[9]) {
     const double s3 = s.sg[qp][0], s4 = s.sg[qp][1], s5 = s.sg[qp][2];
     const double mq = ap[0] * (s3 * bpp[0] + s5 * bpp[1]) + ap[1] * (s5 * bpp[0] + s4 * bpp[1]) +
                       bp[0] * (s3 * app[0] + s5 * app[1]) + bp[1] * (s5 * app[0] + s4 * app[1]);
-    const double *P = s.Pq[qp];
+    const double *P = gm.qp[qp].Pq;
     blk[0] += mq * P[0]; blk[1] += mq * P[1]; blk[2] += mq * P[2];
     blk[3] += mq * P[1]; blk[4] += mq * P[3]; blk[5] += mq * P[4];
     blk[6] += mq * P[2]; blk[7] += mq * P[4]; blk[8] += mq * P[5];
   }
   if (pd) {  // rows: skew(fn_m) * blk
-    const double *f = &s.fn[3 * m];
+    const double *f = &gm.fn[3 * m];
     double t[9];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -733,7 +783,7 @@ A2DS_HD void geo_block(const ElemScratch &s, int p, int pp, double out[9]) {
     for (int i = 0; i < 9; i++) blk[i] = t[i];
   }
   if (ppd) {  // columns: blk * skew(fn_mm)^T, i.e. row_i -> fn x row_i
-    const double *f = &s.fn[3 * mm];
+    const double *f = &gm.fn[3 * mm];
     double t[9];
 #pragma unroll
     for (int i = 0; i < 3; i++) {

@@ -19,18 +19,23 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   c.model = model;
   c.transform = transform;
   memcpy(c.axis, axis, sizeof(c.axis));
-  static ElemScratch s;
+  static ElemGeom s;
+  static ElemWork wk;
   memset(&s, 0, sizeof(s));
+  memset(&wk, 0, sizeof(wk));
   memcpy(s.X, X, sizeof(s.X));
   memcpy(s.q, q, sizeof(s.q));
   Want w;
   w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1;
-  for (int lane = 0; lane < 32; lane++) phase_node(c, s, lane & 3);
-  static double ep[32][9], qw[32], na[32][2], nb[32][2];
+  for (int m = 0; m < 4; m++) phase_node(c, s, m);
+  for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, w.gmat || w.nonlinear);
+  static double ep[32][9];
   static double Bc[32][9][3], Wc[32][9][3], Bq[32][9][3];
   memset(Bq, 0, sizeof(Bq));
-  for (int lane = 0; lane < 32; lane++)
-    lane_columns(c, s, lane, w, ep[lane], qw[lane], na[lane], nb[lane], Bc[lane], Wc[lane], Bq[lane]);
+  for (int lane = 0; lane < 32; lane++) {
+    if (w.gmat || w.nonlinear) lane_b1(s, wk, lane, Bq[lane]);
+    lane_b0w(c, s, lane, w, Bq[lane], ep[lane], Bc[lane], Wc[lane]);
+  }
   memset(res, 0, 24 * sizeof(double));
   for (int lane = 0; lane < 32; lane++) {
     const int qp = lane_qp(lane);
@@ -40,11 +45,11 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
       for (int l = 0; l < 32; l++)
         if (lane_qp(l) == qp) e[r] += ep[l][r];
     }
-    lane_stress(c, s, lane, w, e, qw[lane], na[lane], nb[lane], Wc[lane], r3);
+    lane_stress(c, s, wk, lane, w, e, Wc[lane], r3);
     const int col = 6 * lane_m(lane) + 3 * lane_h(lane);
     for (int k = 0; k < 3; k++) res[col + k] += r3[k];
   }
-  for (int t = 0; t < 9; t++) sum_tying_stress(s, t);
+  for (int t = 0; t < 9; t++) sum_tying_stress(wk, t);
   // dense operands [dof][k = (strain, qp)] assembled from the per-lane fragments
   static double BA[24][36], W[24][36], B1[24][36];
   for (int lane = 0; lane < 32; lane++) {
@@ -62,7 +67,7 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
     for (int p = 0; p < 8; p++)
       for (int pp = 0; pp < 8; pp++) {
         double blk[9];
-        geo_block(s, p, pp, blk);
+        geo_block(s, wk, p, pp, blk);
         int r0 = 6 * (p & 3) + (p >= 4 ? 3 : 0), c0 = 6 * (pp & 3) + (pp >= 4 ? 3 : 0);
         for (int i = 0; i < 3; i++)
           for (int j = 0; j < 3; j++) geo[24 * (r0 + i) + c0 + j] += blk[3 * i + j];
