@@ -143,13 +143,14 @@ __device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2]
 }
 
 // 64 geometric-stiffness 3x3 blocks (generalised node pairs), 2 per lane, added in place
-__device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWork &wk, double *E,
-                                               double scale, int lane) {
+__device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWork &wk,
+                                               const double *Pq4, double *E, double scale,
+                                               int lane) {
 #pragma unroll
   for (int pass = 0; pass < 2; pass++) {
     const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
     double blk[9];
-    geo_block(gm, wk, pr, pc, blk);
+    geo_block(gm, wk, Pq4, pr, pc, blk);
     const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -161,11 +162,35 @@ __device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWor
 // A warp prepares NB elements at a time: the node phase and the Gauss-point phase then run
 // on NB*4 distinct work items (one lane each) instead of 8 redundant copies per element.
 static const int NB = 4;
-struct WarpScratch {
-  int comp[NB], nodes[NB][4], koff[NB][16], goff[NB][16];
-  ElemGeom geo[NB];
-  ElemWork work;  // last: its second staging buffer is dropped when no G is assembled
+struct RawBatch {          // gathered inputs of one batch, filled by cp.async
+  double xq[NB][36];       // per element: X[12] then q[24]
+  int koff[NB][16], goff[NB][16];
+  int comp[NB];
 };
+struct WarpScratch {
+  RawBatch raw0;
+  int nodes[NB][4];
+  ElemGeom geo[NB];
+  double E[24 * KE_LD];   // staging of a 24x24 element matrix for the scatter (tangent)
+  // ---- only the geometric-stiffness / nonlinear variants use what follows; the linear
+  //      residual / tangent kernels allocate up to here (12 instead of 8 warps per SM) ----
+  double E2[24 * KE_LD];  // second staging buffer (geometric stiffness)
+  ElemWork work;
+  double Pq[NB][4][6];    // per Gauss point T T^T
+  RawBatch raw1;          // double buffer: batch i+1 lands (cp.async) while batch i is processed
+};
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT, NL))
@@ -175,31 +200,80 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
   const int warps_per_block = blockDim.x >> 5;
   WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
   ElemWork &wk = ws.work;
+  const bool PF = GMAT || NL;  // full scratch + asynchronous prefetch of the next batch
   const unsigned FULL = 0xffffffffu;
   Want w;
   w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL;
   const bool need_state = GMAT || NL;
 
   const int n_groups = (p.n_list + NB - 1) / NB;
-  for (int grp = blockIdx.x * warps_per_block + warp; grp < n_groups;
-       grp += gridDim.x * warps_per_block) {
+  const int stride = gridDim.x * warps_per_block;
+
+  // element id and node id this lane is responsible for in a batch: lane = 4 j + m
+  auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
+    const int j = (lane >> 2) & (NB - 1);
+    const int idx = grp_ * NB + j;
+    e_out = -1; nd_out = 0;
+    if (grp_ < n_groups && idx < p.n_list) {
+      e_out = p.elem_list ? __ldg(&p.elem_list[idx]) : idx;
+      nd_out = __ldg(&p.conn[4 * e_out + (lane & 3)]);
+    }
+  };
+  // asynchronous gather of a batch into raw buffer `rb` (addresses from the ids above)
+  auto issue_gather = [&](RawBatch &rb, int e_l, int nd_l) {
+#pragma unroll
+    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx / 36, k = sidx - 36 * j;
+      const bool isx = k < 12;
+      const int node = isx ? k / 3 : (k - 12) / 6;
+      const int comp_k = isx ? k - 3 * node : (k - 12) - 6 * node;
+      const int src_lane = (4 * j + node) & 31;
+      const int nd = __shfl_sync(FULL, nd_l, src_lane);
+      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+      if (sidx < NB * 36 && ej >= 0) {
+        const double *src = isx ? &p.X[3 * (size_t)nd + comp_k] : &p.u[6 * (size_t)nd + comp_k];
+        cp_async8(&rb.xq[j][k], src);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NB * 16 / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx >> 4, k = sidx & 15;
+      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+      if (ej >= 0) {
+        if (KMAT) cp_async4(&rb.koff[j][k], &p.Koff[16 * (size_t)ej + k]);
+        if (GMAT) cp_async4(&rb.goff[j][k], &p.Goff[16 * (size_t)ej + k]);
+      }
+    }
+    if ((lane & 3) == 0 && lane < 4 * NB && e_l >= 0) cp_async4(&rb.comp[lane >> 2], &p.elem_comp[e_l]);
+  };
+
+  int grp = blockIdx.x * warps_per_block + warp;
+  int buf = 0;
+  int e_cur, nd_cur;
+  batch_ids(grp, e_cur, nd_cur);
+  if (PF && grp < n_groups) issue_gather(ws.raw0, e_cur, nd_cur);
+  for (; grp < n_groups; grp += stride, buf ^= 1) {
     const int base = grp * NB;
     const int cnt = min(NB, p.n_list - base);
+    // ids of the NEXT batch: requested now, consumed after the geometry phases
+    int e_nxt = -1, nd_nxt = 0;
+    if (PF) batch_ids(grp + stride, e_nxt, nd_nxt);
 
-    // ---- gather the batch: coordinates, state, block offsets --------------------------
+    // ---- the batch gathered during the previous trip (or right now without prefetch) -----
+    if (!PF) issue_gather(ws.raw0, e_cur, nd_cur);
+    cp_async_wait_all();
+    __syncwarp();
+    const RawBatch &rb = (PF && buf) ? ws.raw1 : ws.raw0;
+    if (lane < 4 * NB) ws.nodes[lane >> 2][lane & 3] = nd_cur;
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-      if (j < cnt) {
-        const int e = p.elem_list ? __ldg(&p.elem_list[base + j]) : base + j;
-        const int nd = __ldg(&p.conn[4 * e + (lane & 3)]);  // lane l holds node l & 3
-        const int nx = __shfl_sync(FULL, nd, lane / 3);
-        const int nq = __shfl_sync(FULL, nd, lane / 6);
-        if (lane < 12) ws.geo[j].X[lane] = __ldg(&p.X[3 * (size_t)nx + lane % 3]);
-        if (lane < 24) ws.geo[j].q[lane] = __ldg(&p.u[6 * (size_t)nq + lane % 6]);
-        if (lane < 4) ws.nodes[j][lane] = nd;
-        if (lane == 4) ws.comp[j] = __ldg(&p.elem_comp[e]);
-        if (KMAT && lane < 16) ws.koff[j][lane] = __ldg(&p.Koff[16 * (size_t)e + lane]);
-        if (GMAT && lane >= 16) ws.goff[j][lane - 16] = __ldg(&p.Goff[16 * (size_t)e + lane - 16]);
+    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx / 36, k = sidx - 36 * j;
+      if (sidx < NB * 36) {
+        const double v = rb.xq[j][k];
+        if (k < 12) ws.geo[j].X[k] = v; else ws.geo[j].q[k - 12] = v;
       }
     }
     __syncwarp();
@@ -207,20 +281,25 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     // ---- node phase: lane = (element of the batch, node) --------------------------------
     {
       const int j = (lane >> 2) & (NB - 1);
-      if (lane < 4 * NB && j < cnt) phase_node(p.comps[ws.comp[j]], ws.geo[j], lane & 3);
+      if (lane < 4 * NB && j < cnt) phase_node(p.comps[rb.comp[j]], ws.geo[j], lane & 3);
     }
     __syncwarp();
     // ---- Gauss point phase: lane = (element of the batch, Gauss point) ------------------
     {
       const int j = (lane >> 2) & (NB - 1);
-      if (lane < 4 * NB && j < cnt) phase_qp(p.comps[ws.comp[j]], ws.geo[j], lane & 3, need_state);
+      if (lane < 4 * NB && j < cnt)
+        phase_qp(p.comps[rb.comp[j]], ws.geo[j], lane & 3, need_state,
+                 need_state ? &ws.Pq[j][lane & 3][0] : (double *)0);
     }
+    // start the gather of the next batch into the other raw buffer
+    if (PF && grp + stride < n_groups) issue_gather(buf ? ws.raw0 : ws.raw1, e_nxt, nd_nxt);
+    if (PF) { e_cur = e_nxt; nd_cur = nd_nxt; }
     __syncwarp();
 
 #pragma unroll 1
     for (int j = 0; j < cnt; j++) {
       const ElemGeom &gm = ws.geo[j];
-      const CompData &c = p.comps[ws.comp[j]];
+      const CompData &c = p.comps[rb.comp[j]];
 
       // ---- column phase + contractions on the FP64 tensor path ----------------------
       // The lane's columns of B, w C B and B1(q) ARE the DMMA fragments (mitc4_math.h), so
@@ -293,17 +372,18 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
         }
       }
       // ---- stage, add the geometric blocks, scatter -------------------------------------
-      if (KMAT) stage_tiles(wk.E, kacc, p.alpha, lane);
-      if (GMAT) stage_tiles(wk.E2, gacc, 1.0, lane);
+      if (KMAT) stage_tiles(ws.E, kacc, p.alpha, lane);
+      if (GMAT) stage_tiles(ws.E2, gacc, 1.0, lane);
       if ((GMAT || NL) && lane < 9) sum_tying_stress(wk, lane);
       __syncwarp();
-      if (GMAT) add_geo_blocks(gm, wk, wk.E2, 1.0, lane);
-      else if (NL && KMAT) add_geo_blocks(gm, wk, wk.E, p.alpha, lane);
+      if (GMAT) add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E2, 1.0, lane);
+      else if (NL && KMAT) add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E, p.alpha, lane);
       if (GMAT || NL) __syncwarp();
-      if (KMAT) scatter_matrix(wk.E, p.Kval, ws.koff[j][lane & 15], lane);
-      if (GMAT) scatter_matrix(wk.E2, p.Gval, ws.goff[j][lane & 15], lane);
+      if (KMAT) scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
+      if (GMAT) scatter_matrix(ws.E2, p.Gval, rb.goff[j][lane & 15], lane);
       __syncwarp();
     }
+    if (!PF) batch_ids(grp + stride, e_cur, nd_cur);
   }
 }
 
@@ -413,7 +493,7 @@ struct a2ds_ctx {
   double *bc_vals = nullptr;
   std::vector<MatrixRec> mats;
   int scatter_mode = A2DS_SCATTER_ATOMIC;
-  int warps_per_block = 4;  // one warp = one element; 8 KB of scratch per warp
+  int warps_per_block_forced = 0;  // A2DS_WARPS_PER_BLOCK: development override
   // element lists: [class][colour]; colour list 0 of the atomic mode holds everything
   bool lists_ready = false;
   int n_colors = 0;
@@ -459,7 +539,7 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   c->n_sm = prop.multiProcessorCount;
   if (const char *env = getenv("A2DS_WARPS_PER_BLOCK")) {
     const int v = atoi(env);
-    if (v >= 1 && v <= MAX_WARPS_PER_BLOCK) c->warps_per_block = v;
+    if (v >= 1 && v <= MAX_WARPS_PER_BLOCK) c->warps_per_block_forced = v;
   }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));
@@ -915,22 +995,32 @@ extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
 // ---- assembly ------------------------------------------------------------------
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_one(a2ds_ctx *c, KParams &p) {
-  const size_t raw = GMAT ? sizeof(WarpScratch) : sizeof(WarpScratch) - sizeof(ElemWork::E2);
+  const size_t raw = (GMAT || NL) ? sizeof(WarpScratch) : offsetof(WarpScratch, E2);
   const size_t per_warp = (raw + 15) & ~size_t(15);
   p.scratch_bytes = (int)per_warp;
-  const int wpb = c->warps_per_block;
-  const size_t smem = per_warp * (size_t)wpb;
   auto kern = k_assemble<RES, KMAT, GMAT, NL>;
-  static size_t attr_smem = 0;  // per instantiation
-  if (attr_smem < smem) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // pick the block size (1..4 warps) that keeps the most warps resident per SM: shared
+  // memory is allocated per block, so smaller blocks pack better when it is the limiter
+  static int best_wpb = 0, best_per_sm = 0;  // per instantiation
+  if (best_wpb == 0 || c->warps_per_block_forced) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(per_warp * MAX_WARPS_PER_BLOCK)));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
-    attr_smem = smem;
+    int best = 0;
+    for (int wv = MAX_WARPS_PER_BLOCK; wv >= 1; wv--) {
+      if (c->warps_per_block_forced && wv != c->warps_per_block_forced) continue;
+      int per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wv * 32, per_warp * wv));
+      if (per_sm * wv > best) { best = per_sm * wv; best_wpb = wv; best_per_sm = per_sm; }
+    }
+    if (best == 0) return fail("k_assemble does not fit on an SM");
+    if (getenv("A2DS_VERBOSE"))
+      fprintf(stderr, "[a2ds] k_assemble<%d,%d,%d,%d>: %zu B scratch/warp, %d warps/block x %d blocks/SM\n",
+              (int)RES, (int)KMAT, (int)GMAT, (int)NL, per_warp, best_wpb, best_per_sm);
   }
-  int per_sm = 1;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
-  if (per_sm < 1) return fail("k_assemble does not fit on an SM");
+  const int wpb = best_wpb, per_sm = best_per_sm;
+  const size_t smem = per_warp * (size_t)wpb;
   const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
   kern<<<grid, wpb * 32, smem, c->stream>>>(p);

@@ -92,7 +92,7 @@ struct QpData {
   double M[25];         // (e0,e1,e2,e6,e7) = M (g11,g12,g13,g22,g23)
   double w;             // det(Xd) * quadrature weight
   double P0[6], P1[6];  // T u0x[:,j], T u1x[:,j] (j = 0,1) for the state
-  double Pq[6];         // T T^T (symmetric)
+  double pad_;          // 57 doubles: see the bank note in ElemGeom
 };
 
 // Element geometry: filled by the node phase (one lane per node) and the Gauss point
@@ -106,17 +106,20 @@ struct ElemGeom {
   double Sn[16];   // per node: (Xd^-1 T)[0..1][0..1]
   double etn[4];   // nodal drill strain of the state, evaluated in the reference's order
   QpData qp[4];
+  // sizeof(QpData) = 57 doubles = 9 (mod 16) and sizeof(ElemGeom) = 356 doubles = 4
+  // (mod 16): the 16 (element, node) / (element, Gauss point) lanes of the batched phases
+  // then fall into 16 different 8-byte shared-memory banks (measured: 8 % on the residual
+  // kernel against an unlucky stride)
+  double pad_[12];
 };
 
-// Working set of the element currently being contracted / scattered
+// Working set of the geometric-stiffness phase of the element currently being processed
 struct ElemWork {
   double ca[4][8][2], cb[4][8][2];  // per Gauss point, per generalised node
                                     // (u_0..u_3, d_0..d_3): coefficient pairs
   double sg[4][3];     // per Gauss point: w*s3, w*s4, w*s5 (bending resultants)
   double sig[4][9];    // per Gauss point contribution to the tying-point stresses
   double sigsum[9];    // tying-point stresses summed over the Gauss points
-  double E[24 * KE_LD];   // staging of a 24x24 element matrix for the scatter (tangent)
-  double E2[24 * KE_LD];  // second staging buffer (geometric stiffness)
 };
 
 A2DS_HD void cross(const double a[3], const double b[3], double o[3]) {
@@ -430,7 +433,7 @@ A2DS_HD void qp_geometry(const CompData &c, const ElemGeom &s, int qp, bool need
 }
 
 // ---- phase 2: Gauss point qp of one element (one lane per Gauss point) -------------
-A2DS_HD void phase_qp(const CompData &c, ElemGeom &s, int qp, bool need_state) {
+A2DS_HD void phase_qp(const CompData &c, ElemGeom &s, int qp, bool need_state, double *Pq) {
   QpGeom g;
   qp_geometry(c, s, qp, need_state, g);
   QpData &d = s.qp[qp];
@@ -447,13 +450,15 @@ A2DS_HD void phase_qp(const CompData &c, ElemGeom &s, int qp, bool need_state) {
 #pragma unroll
     for (int i = 0; i < 6; i++) { d.P0[i] = g.P0[i]; d.P1[i] = g.P1[i]; }
   }
-  const double *t0 = g.t0, *t1 = g.t1, *tn = g.tn;
-  d.Pq[0] = t0[0] * t0[0] + t1[0] * t1[0] + tn[0] * tn[0];
-  d.Pq[1] = t0[0] * t0[1] + t1[0] * t1[1] + tn[0] * tn[1];
-  d.Pq[2] = t0[0] * t0[2] + t1[0] * t1[2] + tn[0] * tn[2];
-  d.Pq[3] = t0[1] * t0[1] + t1[1] * t1[1] + tn[1] * tn[1];
-  d.Pq[4] = t0[1] * t0[2] + t1[1] * t1[2] + tn[1] * tn[2];
-  d.Pq[5] = t0[2] * t0[2] + t1[2] * t1[2] + tn[2] * tn[2];
+  if (Pq) {  // T T^T (symmetric 6) for the geometric-stiffness phase
+    const double *t0 = g.t0, *t1 = g.t1, *tn = g.tn;
+    Pq[0] = t0[0] * t0[0] + t1[0] * t1[0] + tn[0] * tn[0];
+    Pq[1] = t0[0] * t0[1] + t1[0] * t1[1] + tn[0] * tn[1];
+    Pq[2] = t0[0] * t0[2] + t1[0] * t1[2] + tn[0] * tn[2];
+    Pq[3] = t0[1] * t0[1] + t1[1] * t1[1] + tn[1] * tn[1];
+    Pq[4] = t0[1] * t0[2] + t1[1] * t1[2] + tn[1] * tn[2];
+    Pq[5] = t0[2] * t0[2] + t1[2] * t1[2] + tn[2] * tn[2];
+  }
 }
 
 // 1D shape functions at Gauss point qp
@@ -738,7 +743,8 @@ A2DS_HD void sum_tying_stress(ElemWork &s, int t) {
 //   rows of a director node:    skew(fn_m) * blk      (d = theta x fn)
 //   columns of a director node: blk * skew(fn_m)^T
 // (TACSLinearizedRotation::addDirectorJacobian, TACSDirector.h:369-486)
-A2DS_HD void geo_block(const ElemGeom &gm, const ElemWork &s, int p, int pp, double out[9]) {
+A2DS_HD void geo_block(const ElemGeom &gm, const ElemWork &s, const double *Pq4, int p, int pp,
+                       double out[9]) {
   const double *sig = s.sigsum;  // tying point stresses (summed over the Gauss points)
   const int m = p & 3, mm = pp & 3;
   const bool pd = p >= 4, ppd = pp >= 4;
@@ -765,7 +771,7 @@ A2DS_HD void geo_block(const ElemGeom &gm, const ElemWork &s, int p, int pp, dou
     const double s3 = s.sg[qp][0], s4 = s.sg[qp][1], s5 = s.sg[qp][2];
     const double mq = ap[0] * (s3 * bpp[0] + s5 * bpp[1]) + ap[1] * (s5 * bpp[0] + s4 * bpp[1]) +
                       bp[0] * (s3 * app[0] + s5 * app[1]) + bp[1] * (s5 * app[0] + s4 * app[1]);
-    const double *P = gm.qp[qp].Pq;
+    const double *P = Pq4 + 6 * qp;
     blk[0] += mq * P[0]; blk[1] += mq * P[1]; blk[2] += mq * P[2];
     blk[3] += mq * P[1]; blk[4] += mq * P[3]; blk[5] += mq * P[4];
     blk[6] += mq * P[2]; blk[7] += mq * P[4]; blk[8] += mq * P[5];

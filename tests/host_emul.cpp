@@ -28,7 +28,8 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   Want w;
   w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1;
   for (int m = 0; m < 4; m++) phase_node(c, s, m);
-  for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, w.gmat || w.nonlinear);
+  static double Pq[4][6];
+  for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, w.gmat || w.nonlinear, Pq[qp]);
   static double ep[32][9];
   static double Bc[32][9][3], Wc[32][9][3], Bq[32][9][3];
   memset(Bq, 0, sizeof(Bq));
@@ -67,7 +68,7 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
     for (int p = 0; p < 8; p++)
       for (int pp = 0; pp < 8; pp++) {
         double blk[9];
-        geo_block(s, wk, p, pp, blk);
+        geo_block(s, wk, &Pq[0][0], p, pp, blk);
         int r0 = 6 * (p & 3) + (p >= 4 ? 3 : 0), c0 = 6 * (pp & 3) + (pp >= 4 ? 3 : 0);
         for (int i = 0; i < 3; i++)
           for (int j = 0; j < 3; j++) geo[24 * (r0 + i) + c0 + j] += blk[3 * i + j];

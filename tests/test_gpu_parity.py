@@ -278,3 +278,67 @@ def test_buckling_eigenvalues_with_reference_solver(a2ds, ref):
     eig_gpu, _ = ra.buckling(km, gm, am, 1, u0=path, **kw)
     assert np.all(np.abs(eig_gpu[:6] - eig_ref[:6]) <= 1e-8 * np.abs(eig_ref[:6])), (eig_gpu[:6], eig_ref[:6])
     asm.close(); ra.close()
+
+
+def test_many_components_mixed_classes_vs_oracle(a2ds, orc):
+    """BASELINE config 4 stand-in: a mesh with 120 components, each with its own full
+    22-entry tangent (non-zero B coupling, As[1]), own temperature, and a mix of linear and
+    nonlinear element classes in one assembler (separate element lists per class)."""
+    conn, X, bcn = a2ds.meshes.cylinder(30, 9)
+    n = len(X); ne = len(conn)
+    rng = np.random.default_rng(42)
+    ncomp = 120
+    Cs = np.zeros((ncomp, 22)); eth = np.zeros((ncomp, 9))
+    for c in range(ncomp):
+        base, e = a2ds.iso_shell_tables(E=72e9 * rng.uniform(0.5, 2), nu=rng.uniform(0.2, 0.4),
+                                        t=rng.uniform(0.005, 0.02), t_offset=rng.uniform(-0.4, 0.4))
+        base[7] *= 1.0 + 0.1 * rng.uniform()          # a little anisotropy in B
+        base[19] = 0.05 * base[18] * rng.uniform(-1, 1)   # As[1] != 0
+        Cs[c] = base; eth[c] = e
+    temperature = np.zeros(ncomp)                      # (T != 0 for nonlinear-class G is a quirk)
+    cls = (rng.uniform(size=ncomp) < 0.4).astype(np.int32)
+    elem_comp = rng.integers(0, ncomp, ne).astype(np.int32)
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-4)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n, elem_comp=elem_comp); asm.set_nodes(X)
+    asm.set_components(Cs, eth, temperature=temperature, elem_class=cls)
+    asm.set_bcs(bcn, 63); asm.set_state(u)
+    k = asm.create_mat(); g = asm.create_mat()
+    rowp, cols = asm.mat_pattern(k)
+    comps = [orc.make_comp(int(cls[c]), Cs[c], eth[c], (0, 0, 0), temperature[c]) for c in range(ncomp)]
+    bc_vars = np.full(len(bcn), 63, dtype=np.int32); bc_vals = np.zeros((len(bcn), 6))
+    r_o, k_o = orc.assemble(1, conn, elem_comp, comps, X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    _, g_o = orc.assemble(3, conn, elem_comp, comps, X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    for mode in (a2ds.SCATTER_ATOMIC, a2ds.SCATTER_COLORED):
+        asm.set_scatter_mode(mode)
+        r = asm.assembleAll(k, g)
+        assert relmax(r, r_o) < RES_TOL
+        assert relmax(asm.mat_values(k), k_o) < MAT_TOL
+        assert relmax(asm.mat_values(g), g_o) < MAT_TOL
+    asm.close()
+
+
+def test_empty_and_tiny_meshes(a2ds):
+    """edge cases: no elements at all, and a single element (ragged batch)"""
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(np.zeros((0, 4), dtype=np.int32), 4)
+    asm.set_nodes(np.zeros((4, 3)))
+    Cs, eth = a2ds.iso_shell_tables()
+    asm.set_components(Cs[None], eth[None])
+    k = asm.create_mat()
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, k)
+    assert not r.any() and asm.mat_nnz(k) == 0
+    asm.close()
+    X, q = random_elements(1, seed=1)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(np.arange(4, dtype=np.int32)[None], 4); asm.set_nodes(X[0])
+    asm.set_components(Cs[None], eth[None]); asm.set_state(q[0])
+    k = asm.create_mat(); g = asm.create_mat()
+    r = asm.assembleAll(k, g)
+    K = asm.mat_values(k)
+    assert np.isfinite(r).all() and np.isfinite(K).all() and np.abs(K).max() > 0
+    with pytest.raises(a2ds.A2dsError):
+        asm.assembleJacobian(1.0, 0.5, 0.0, k)   # inertial terms are not on the device path
+    with pytest.raises(a2ds.A2dsError):
+        asm.assembleAll(k, k)
+    asm.close()
