@@ -26,6 +26,7 @@ SYMBOLS = [
     "a2ds_comm_unique_id", "a2ds_comm_init", "a2ds_set_halo", "a2ds_halo_forward",
     "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
     "a2ds_last_kernel_ms", "a2ds_region_begin", "a2ds_region_end",
+    "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
 ]
 
 _LIB = None
@@ -229,6 +230,30 @@ class Assembler:
         p = C.c_void_p()
         self._chk(self.L.a2ds_mat_values_dev(self.ctx, C.c_int(mat), C.c_int(block), C.byref(p)))
         return p.value
+
+    # -- matrix algebra on the device values (TACSMat names) ------------------------------
+    def mat_copy(self, dst, src):
+        self._chk(self.L.a2ds_mat_copy(self.ctx, C.c_int(dst), C.c_int(src)))
+
+    def mat_axpy(self, alpha, x, y):
+        self._chk(self.L.a2ds_mat_axpy(self.ctx, C.c_double(alpha), C.c_int(x), C.c_int(y)))
+
+    def mat_apply_bcs(self, mat):
+        self._chk(self.L.a2ds_mat_apply_bcs(self.ctx, C.c_int(mat)))
+
+    def mat_mult(self, mat, x, block=0):
+        x = _f64(x).reshape(-1, 6)
+        nr = C.c_int()
+        self._chk(self.L.a2ds_mat_pattern(self.ctx, C.c_int(mat), C.c_int(block), C.byref(nr),
+                                          None, None))
+        y = np.empty((nr.value, 6))
+        self._chk(self.L.a2ds_mat_mult(self.ctx, C.c_int(mat), C.c_int(block), C.c_int(x.shape[0]),
+                                       _p(x), _p(y)))
+        return y
+
+    def mat_mult_dev(self, mat, x_dev, y_dev, block=0):
+        self._chk(self.L.a2ds_mat_mult_dev(self.ctx, C.c_int(mat), C.c_int(block),
+                                           C.c_void_p(x_dev), C.c_void_p(y_dev)))
 
     # -- assembly (TACSAssembler names) ------------------------------------------------
     def _res_out(self, want):

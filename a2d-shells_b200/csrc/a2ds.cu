@@ -464,6 +464,34 @@ __global__ void k_unpack6(int n, const int *nodes, const double *buf, double *v,
   if (add) *d += buf[t]; else *d = buf[t];
 }
 
+// y <- y + alpha x over all stored values (BCSRMat::axpy, BCSRMat.cpp:2430)
+__global__ void k_axpy(size_t n, double alpha, const double *__restrict__ x, double *__restrict__ y) {
+  const size_t stride = gridDim.x * (size_t)blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] += alpha * x[i];
+}
+
+// 6x6 BCSR mat-vec (BCSRMatVecMult6, BCSRMatMult6.cpp:82): one thread per scalar row, the six
+// threads of a block row read the 288 contiguous bytes of each block between them.
+// HBM bound: 288 B of values + 4 B of column index per block; x is reused through L1/L2.
+__global__ void k_spmv6(int nrows, const int *__restrict__ rowp, const int *__restrict__ cols,
+                        const double *__restrict__ A, const double *__restrict__ x,
+                        double *__restrict__ y) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int row = (int)(t / 6), r = (int)(t - 6 * (size_t)row);
+  if (row >= nrows) return;
+  double acc = 0.0;
+  const int end = rowp[row + 1];
+  for (int k = rowp[row]; k < end; k++) {
+    const double2 *a = reinterpret_cast<const double2 *>(A + 36 * (size_t)k + 6 * r);
+    const double2 *xv = reinterpret_cast<const double2 *>(x + 6 * (size_t)__ldg(&cols[k]));
+    const double2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+    const double2 x0 = __ldg(xv), x1 = __ldg(xv + 1), x2 = __ldg(xv + 2);
+    acc += a0.x * x0.x + a0.y * x0.y + a1.x * x1.x + a1.y * x1.y + a2.x * x2.x + a2.y * x2.y;
+  }
+  y[t] = acc;
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -477,6 +505,7 @@ struct MatrixRec {
   BlockDev *blk_dev = nullptr;
   std::vector<void *> owned;   // device allocations to free
   std::vector<std::vector<int>> h_rowp, h_cols;  // host copy of the patterns
+  std::vector<const int *> d_rowp, d_cols;       // device copy, per block
 };
 
 struct a2ds_ctx {
@@ -485,6 +514,7 @@ struct a2ds_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   int n_sm = 0;
   int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
+  bool mesh_set = false;
   int *conn = nullptr, *elem_comp = nullptr;
   std::vector<int> h_conn, h_elem_comp, h_class;
   double *X = nullptr, *u = nullptr, *res = nullptr;
@@ -608,6 +638,7 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
   CU(cudaMemsetAsync(c->u, 0, 6 * (size_t)n_nodes * sizeof(double), c->stream));
   CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)n_nodes * sizeof(double), c->stream));
   free_lists(c);
+  c->mesh_set = true;
   return 0;
 }
 
@@ -756,7 +787,7 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
                                const int *bc_ident, int *mat) {
   CU(cudaSetDevice(c->device));
   if (n_blocks < 1 || n_blocks > 4) return fail("a2ds_mat_create: 1..4 BCSR blocks");
-  if (!c->conn) return fail("a2ds_mat_create: call a2ds_set_mesh first");
+  if (!c->mesh_set) return fail("a2ds_mat_create: call a2ds_set_mesh first");
   MatrixRec m;
   m.n_blocks = n_blocks;
   std::vector<BlockDev> hb(n_blocks);
@@ -777,6 +808,7 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
     if (d_rm) m.owned.push_back(d_rm);
     if (d_cm) m.owned.push_back(d_cm);
     hb[b].rowp = d_rowp; hb[b].cols = d_cols; hb[b].row_map = d_rm; hb[b].col_map = d_cm;
+    m.d_rowp.push_back(d_rowp); m.d_cols.push_back(d_cols);
     hb[b].base = total; hb[b].nrows = nrows[b];
     hb[b].ident = bc_ident ? bc_ident[b] : (b == 0);
     total += nnz;
@@ -873,7 +905,7 @@ extern "C" int a2ds_host_color_elements(int n_nodes, int n_elems, const int *con
 }
 
 extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
-  if (!c->conn) return fail("a2ds_mat_create_natural: call a2ds_set_mesh first");
+  if (!c->mesh_set) return fail("a2ds_mat_create_natural: call a2ds_set_mesh first");
   std::vector<int> rowp, cols;
   if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), rowp, cols)) return 1;
   const int nrows = c->n_nodes;
@@ -918,6 +950,75 @@ extern "C" int a2ds_mat_values_dev(a2ds_ctx *c, int mat, int block, double **A_d
   if (check_mat(c, mat, block)) return 1;
   *A_dev = c->mats[mat].A + 36 * c->mats[mat].base[block];
   return 0;
+}
+
+static int same_pattern(a2ds_ctx *c, int a, int b) {
+  if (check_mat(c, a) || check_mat(c, b)) return 1;
+  const MatrixRec &A = c->mats[a], &B = c->mats[b];
+  if (A.n_blocks != B.n_blocks || A.total != B.total || A.h_rowp != B.h_rowp || A.h_cols != B.h_cols)
+    return fail("matrix operation: the two matrices do not share one non-zero pattern");
+  return 0;
+}
+
+extern "C" int a2ds_mat_copy(a2ds_ctx *c, int dst, int src) {
+  if (same_pattern(c, dst, src)) return 1;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->mats[dst].A, c->mats[src].A, c->mats[src].total * 36 * sizeof(double),
+                     cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_mat_axpy(a2ds_ctx *c, double alpha, int x, int y) {
+  if (same_pattern(c, x, y)) return 1;
+  CU(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->mats[x].total * 36;
+  if (n) k_axpy<<<c->n_sm * 8, 256, 0, c->stream>>>(n, alpha, c->mats[x].A, c->mats[y].A);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int a2ds_mat_apply_bcs(a2ds_ctx *c, int mat) {
+  if (check_mat(c, mat)) return 1;
+  CU(cudaSetDevice(c->device));
+  if (!c->n_bc) return 0;
+  MatrixRec &m = c->mats[mat];
+  const int nt = c->n_bc * m.n_blocks;
+  k_mat_bcs<<<(nt + 127) / 128, 128, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars, m.n_blocks,
+                                                     m.blk_dev, m.A);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int a2ds_mat_mult_dev(a2ds_ctx *c, int mat, int block, const double *x_dev,
+                                 double *y_dev) {
+  if (check_mat(c, mat, block)) return 1;
+  CU(cudaSetDevice(c->device));
+  MatrixRec &m = c->mats[mat];
+  const int nrows = m.nrows[block];
+  if (nrows == 0) return 0;
+  const size_t nt = 6 * (size_t)nrows;
+  k_spmv6<<<(unsigned)((nt + 191) / 192), 192, 0, c->stream>>>(
+      nrows, m.d_rowp[block], m.d_cols[block], m.A + 36 * m.base[block], x_dev, y_dev);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int a2ds_mat_mult(a2ds_ctx *c, int mat, int block, int ncols, const double *x,
+                             double *y) {
+  if (check_mat(c, mat, block)) return 1;
+  CU(cudaSetDevice(c->device));
+  const int nrows = c->mats[mat].nrows[block];
+  double *dx = nullptr, *dy = nullptr;
+  CU(cudaMalloc((void **)&dx, std::max<size_t>(6 * (size_t)ncols, 1) * sizeof(double)));
+  CU(cudaMalloc((void **)&dy, std::max<size_t>(6 * (size_t)nrows, 1) * sizeof(double)));
+  CU(cudaMemcpyAsync(dx, x, 6 * (size_t)ncols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int rc = a2ds_mat_mult_dev(c, mat, block, dx, dy);
+  if (!rc) {
+    CU(cudaMemcpyAsync(y, dy, 6 * (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(dx); cudaFree(dy);
+  return rc;
 }
 
 extern "C" int a2ds_res_dev(a2ds_ctx *c, double **r) { *r = c->res; return 0; }
@@ -1032,7 +1133,7 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
 // what: bit 0 residual, bit 1 tangent, bit 2 geometric stiffness
 static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat, double *res_host) {
   CU(cudaSetDevice(c->device));
-  if (!c->conn || !c->X) return fail("assemble: mesh or nodes not set");
+  if (!c->mesh_set) return fail("assemble: mesh or nodes not set");
   if (build_lists(c)) return 1;
   const bool RES = what & 1, KM = (what & 2) != 0, GM = (what & 4) != 0;
   if (KM && check_mat(c, kmat)) return 1;

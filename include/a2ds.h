@@ -128,6 +128,20 @@ int a2ds_mat_zero(a2ds_ctx *ctx, int mat);
 int a2ds_mat_download(a2ds_ctx *ctx, int mat, int block, double *A);
 int a2ds_mat_values_dev(a2ds_ctx *ctx, int mat, int block, double **A_dev);
 
+/* ---- matrix algebra on the device-resident values (the buckling flow's K/G handling) ----
+ * TACSMat::copyValues (src/bpmat/BCSRMat.cpp:2375): dst <- src, same pattern required */
+int a2ds_mat_copy(a2ds_ctx *ctx, int dst, int src);
+/* TACSMat::axpy (src/bpmat/BCSRMat.cpp:2430): y <- y + alpha x, same pattern required
+ * (aux = K + sigma G, src/TACSBuckling.cpp:269) */
+int a2ds_mat_axpy(a2ds_ctx *ctx, double alpha, int x, int y);
+/* TACSMat::applyBCs (src/bpmat/TACSSchurMat.cpp:662-703, BCSRMat::zeroRow) */
+int a2ds_mat_apply_bcs(a2ds_ctx *ctx, int mat);
+/* 6x6 BCSR mat-vec y = A x for one BCSR block (BCSRMatVecMult6,
+ * src/bpmat/BCSRMatMult6.cpp:82): x has 6*ncols, y 6*nrows entries in the block's own
+ * row/column numbering.  _dev: device pointers; the other takes host pointers. */
+int a2ds_mat_mult_dev(a2ds_ctx *ctx, int mat, int block, const double *x_dev, double *y_dev);
+int a2ds_mat_mult(a2ds_ctx *ctx, int mat, int block, int ncols, const double *x, double *y);
+
 /* ---- assembly: the three reference entry points -------------------------------
  * TACSAssembler::assembleRes (src/TACSAssembler.cpp:4000-4063): res[6 n + k] for the
  * owned nodes, boundary rows r = u - ubar.  res may be NULL (result stays on device,

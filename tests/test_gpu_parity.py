@@ -342,3 +342,45 @@ def test_empty_and_tiny_meshes(a2ds):
     with pytest.raises(a2ds.A2dsError):
         asm.assembleAll(k, k)
     asm.close()
+
+
+def test_device_matrix_algebra_and_spmv(a2ds):
+    """the buckling flow's matrix handling on the device values: copyValues, axpy, applyBCs
+    (src/TACSBuckling.cpp:240,269-270) and the 6x6 BCSR mat-vec (BCSRMatMult6.cpp:82)"""
+    conn, X, bcn = a2ds.meshes.cylinder(36, 11)
+    n = len(X)
+    Cs, eth = a2ds.iso_shell_tables()
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n); asm.set_nodes(X); asm.set_components(Cs[None], eth[None])
+    asm.set_state(a2ds.meshes.seeded_state(np.arange(n), 1e-5))
+    k = asm.create_mat(); g = asm.create_mat(); aux = asm.create_mat()
+    rowp, cols = asm.mat_pattern(k)
+    asm.assembleAll(k, g, download=False)      # no BCs set yet
+    K = asm.mat_values(k); G = asm.mat_values(g)
+    asm.mat_copy(aux, k)
+    assert np.array_equal(asm.mat_values(aux), K)
+    asm.mat_axpy(10.0, g, aux)
+    assert relmax(asm.mat_values(aux), K + 10.0 * G) < 1e-15
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(n, 6))
+    for m, M in ((k, K), (g, G), (aux, K + 10.0 * G)):
+        assert relmax(asm.mat_mult(m, x), bcsr_matvec(M, rowp, cols, x)) < 1e-13
+    # applyBCs afterwards: BC rows zero, 1 on the diagonal entry, columns untouched
+    asm.set_bcs(bcn, 0b100111)
+    asm.mat_apply_bcs(aux)
+    A = asm.mat_values(aux)
+    ref = K + 10.0 * G
+    for nd in bcn:
+        for j in range(rowp[nd], rowp[nd + 1]):
+            for kk in range(6):
+                if 0b100111 & (1 << kk):
+                    row = A[j, kk].copy()
+                    if cols[j] == nd:
+                        assert row[kk] == 1.0
+                        row[kk] = 0.0
+                    assert not row.any()
+                else:
+                    assert np.abs(A[j, kk] - ref[j, kk]).max() <= 1e-15 * np.abs(ref).max()
+    with pytest.raises(a2ds.A2dsError):
+        asm.mat_axpy(1.0, k, 99)
+    asm.close()
