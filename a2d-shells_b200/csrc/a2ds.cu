@@ -464,11 +464,35 @@ __global__ void k_unpack6(int n, const int *nodes, const double *buf, double *v,
   if (add) *d += buf[t]; else *d = buf[t];
 }
 
-// y <- y + alpha x over all stored values (BCSRMat::axpy, BCSRMat.cpp:2430)
-__global__ void k_axpy(size_t n, double alpha, const double *__restrict__ x, double *__restrict__ y) {
+// y <- beta y + alpha x over all stored values (BCSRMat::axpy / copyValues, BCSRMat.cpp:2375,
+// 2430).  Pure HBM streaming: 128-bit accesses, four independent loads in flight per thread.
+// n2 = number of double2 (block values come in multiples of 36 doubles, 16-byte aligned).
+template <bool COPY>
+__global__ void __launch_bounds__(256) k_axpy(size_t n2, double alpha, const double2 *__restrict__ x,
+                                              double2 *__restrict__ y) {
   const size_t stride = gridDim.x * (size_t)blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride)
-    y[i] += alpha * x[i];
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n2; i += 4 * stride) {
+    double2 xv[4], yv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      xv[k] = __ldcs(&x[i + k * stride]);
+      if (!COPY) yv[k] = __ldcs(&y[i + k * stride]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      double2 r;
+      if (COPY) r = xv[k];
+      else { r.x = yv[k].x + alpha * xv[k].x; r.y = yv[k].y + alpha * xv[k].y; }
+      __stcs(&y[i + k * stride], r);
+    }
+  }
+  for (; i < n2; i += stride) {
+    double2 xv = x[i], r;
+    if (COPY) r = xv;
+    else { double2 yv = y[i]; r.x = yv.x + alpha * xv.x; r.y = yv.y + alpha * xv.y; }
+    y[i] = r;
+  }
 }
 
 // 6x6 BCSR mat-vec (BCSRMatVecMult6, BCSRMatMult6.cpp:82): one thread per scalar row, the six
@@ -963,16 +987,23 @@ static int same_pattern(a2ds_ctx *c, int a, int b) {
 extern "C" int a2ds_mat_copy(a2ds_ctx *c, int dst, int src) {
   if (same_pattern(c, dst, src)) return 1;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(c->mats[dst].A, c->mats[src].A, c->mats[src].total * 36 * sizeof(double),
-                     cudaMemcpyDeviceToDevice, c->stream));
+  const size_t n2 = (size_t)c->mats[src].total * 18;
+  if (n2)
+    k_axpy<true><<<c->n_sm * 16, 256, 0, c->stream>>>(
+        n2, 1.0, reinterpret_cast<const double2 *>(c->mats[src].A),
+        reinterpret_cast<double2 *>(c->mats[dst].A));
+  CU(cudaGetLastError());
   return 0;
 }
 
 extern "C" int a2ds_mat_axpy(a2ds_ctx *c, double alpha, int x, int y) {
   if (same_pattern(c, x, y)) return 1;
   CU(cudaSetDevice(c->device));
-  const size_t n = (size_t)c->mats[x].total * 36;
-  if (n) k_axpy<<<c->n_sm * 8, 256, 0, c->stream>>>(n, alpha, c->mats[x].A, c->mats[y].A);
+  const size_t n2 = (size_t)c->mats[x].total * 18;
+  if (n2)
+    k_axpy<false><<<c->n_sm * 16, 256, 0, c->stream>>>(
+        n2, alpha, reinterpret_cast<const double2 *>(c->mats[x].A),
+        reinterpret_cast<double2 *>(c->mats[y].A));
   CU(cudaGetLastError());
   return 0;
 }

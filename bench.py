@@ -38,6 +38,11 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_PER_ELEM = 5320.0      # conn 16 + X 24 + u 48 + res 48 + K 2592 + G 2592
 REF_FLOPS_PER_ELEM = 508437.0    # reference operation count, res + K + G
 DFMA_PEAK_TFLOPS = 34.1          # measured on this pool's B200 (tools/fp64_peak.cu, profiles/)
+# dram__bytes_read.sum + dram__bytes_write.sum of k_assemble<res,K,G> per element, from the
+# ncu --set full capture at 1 M elements (profiles/r01e_ncu_k_assemble_resKG_1M.txt):
+# 6.05 GB read + 6.18 GB written per launch = 2.3 x the algorithmic bytes (the RED
+# read-modify-write re-reads the zeroed matrices once)
+DRAM_TRAFFIC_PER_ELEM = 12227.8
 
 
 def measured_peaks():
@@ -308,7 +313,9 @@ def main():
                 "l2": "outputs (2 x 2.6 GB BCSR) and inputs exceed the 126 MB L2 every step",
                 "scatter": "atomic"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": which,
+                         "frac": achieved / hbm, "traffic": DRAM_TRAFFIC_PER_ELEM * n_elems,
+                         "traffic_source": "ncu capture at 1M elements, profiles/r01e_*",
+                         "peak_source": which,
                          "kernel": "k_assemble<res,K,G>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEM},
             "fp64": {"note": "the FP64 pipe, not HBM, bounds this kernel (SURVEY.md §8(d))",
