@@ -1,0 +1,100 @@
+// DeviceAssembler.h — C++ side-car over the C ABI of include/a2ds.h for drivers that own
+// their loop (route 2 of INTEGRATION.md).  Method names, argument order and meaning follow
+// TACSAssembler (src/TACSAssembler.h:213-220); the error convention does not — the
+// reference prints and carries on, this throws std::runtime_error with a2ds_last_error().
+// Header only; link with -la2ds_b200.
+#ifndef A2DS_DEVICE_ASSEMBLER_H
+#define A2DS_DEVICE_ASSEMBLER_H
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "a2ds.h"
+
+namespace a2ds {
+
+class DeviceAssembler {
+ public:
+  explicit DeviceAssembler(int device = 0) : ctx_(nullptr), n_nodes_(0), n_owned_(0) {
+    check(a2ds_create(device, &ctx_), "a2ds_create");
+  }
+  ~DeviceAssembler() { if (ctx_) a2ds_destroy(ctx_); }
+  DeviceAssembler(const DeviceAssembler &) = delete;
+  DeviceAssembler &operator=(const DeviceAssembler &) = delete;
+
+  // TACSAssembler::setElementConnectivity / setElements / setNodes / addBCs
+  void setMesh(int n_nodes, int n_owned, int n_elems, const int *conn, const int *elem_comp) {
+    check(a2ds_set_mesh(ctx_, n_nodes, n_owned, n_elems, conn, elem_comp), "a2ds_set_mesh");
+    n_nodes_ = n_nodes; n_owned_ = n_owned;
+  }
+  void setNodes(const double *X) { check(a2ds_set_nodes(ctx_, X), "a2ds_set_nodes"); }
+  void setComponents(int n_comp, const double *Cs, const double *eth, const double *temperature,
+                     const int *elem_class, int transform, const double *ref_axis) {
+    check(a2ds_set_components(ctx_, n_comp, Cs, eth, temperature, elem_class, transform, ref_axis),
+          "a2ds_set_components");
+  }
+  void addBCs(int n_bc, const int *nodes, const int *var_masks, const double *vals) {
+    check(a2ds_set_bcs(ctx_, n_bc, nodes, var_masks, vals), "a2ds_set_bcs");
+  }
+  // TACSAssembler::setVariables (all local nodes, or the owned ones followed by haloForward)
+  void setVariables(const double *u, bool owned_only = false) {
+    check(a2ds_set_state(ctx_, owned_only ? n_owned_ : n_nodes_, u), "a2ds_set_state");
+  }
+  void haloForward() { check(a2ds_halo_forward(ctx_), "a2ds_halo_forward"); }
+
+  // TACSAssembler::createMat (natural order) / matrices whose pattern comes from a host object
+  int createMat() {
+    int m = -1;
+    check(a2ds_mat_create_natural(ctx_, &m), "a2ds_mat_create_natural");
+    return m;
+  }
+  int createMatFromPattern(int n_blocks, const int *nrows, const int *const *rowp,
+                           const int *const *cols, const int *const *row_map,
+                           const int *const *col_map, const int *bc_ident) {
+    int m = -1;
+    check(a2ds_mat_create(ctx_, n_blocks, nrows, rowp, cols, row_map, col_map, bc_ident, &m),
+          "a2ds_mat_create");
+    return m;
+  }
+
+  // the three reference entry points; residual: 6 * n_owned doubles or NULL
+  void assembleRes(double *residual) { check(a2ds_assemble_res(ctx_, residual), "assembleRes"); }
+  void assembleJacobian(double alpha, double beta, double gamma, double *residual, int mat) {
+    check(a2ds_assemble_jacobian(ctx_, alpha, beta, gamma, residual, mat), "assembleJacobian");
+  }
+  void assembleMatType(int mat_type, int mat) {
+    check(a2ds_assemble_mat_type(ctx_, mat_type, mat), "assembleMatType");
+  }
+  // residual + K + G in one pass
+  void assembleAll(double *residual, int kmat, int gmat) {
+    check(a2ds_assemble_all(ctx_, residual, kmat, gmat), "assembleAll");
+  }
+
+  // TACSMat::copyValues / axpy / applyBCs / mult on the device-resident values
+  void copyValues(int dst, int src) { check(a2ds_mat_copy(ctx_, dst, src), "copyValues"); }
+  void axpy(double alpha, int x, int y) { check(a2ds_mat_axpy(ctx_, alpha, x, y), "axpy"); }
+  void applyBCs(int mat) { check(a2ds_mat_apply_bcs(ctx_, mat), "applyBCs"); }
+  void mult(int mat, int block, int ncols, const double *x, double *y) {
+    check(a2ds_mat_mult(ctx_, mat, block, ncols, x, y), "mult");
+  }
+  // BCSRMat::getArrays analogue: values of one BCSR block, A[36 k + 6 r + c]
+  std::vector<double> getValues(int mat, int block = 0) {
+    long long nnz = 0;
+    check(a2ds_mat_nnz(ctx_, mat, block, &nnz), "a2ds_mat_nnz");
+    std::vector<double> A(36 * (size_t)nnz);
+    check(a2ds_mat_download(ctx_, mat, block, A.data()), "a2ds_mat_download");
+    return A;
+  }
+  a2ds_ctx *context() { return ctx_; }
+
+ private:
+  static void check(int rc, const char *what) {
+    if (rc) throw std::runtime_error(std::string(what) + ": " + a2ds_last_error());
+  }
+  a2ds_ctx *ctx_;
+  int n_nodes_, n_owned_;
+};
+
+}  // namespace a2ds
+#endif

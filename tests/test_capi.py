@@ -102,3 +102,27 @@ def test_partition_ownership_follows_first_touch(a2ds):
             assert np.array_equal(glob[p["send_lists"][k]], other["glob"][other["recv_lists"][kk]])
             assert np.all(p["send_lists"][k] < len(p["owned"]))
             assert np.all(p["recv_lists"][k] >= len(p["owned"]))
+
+
+def _build_probe():
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_device_assembler_probe")
+    src = os.path.join(ROOT, "tests", "device_assembler_probe.cpp")
+    lib = os.path.join(ROOT, "a2d-shells_b200", "lib")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-std=c++11", "-O1", "-I" + os.path.join(ROOT, "include"), src,
+                               "-o", exe, "-L" + lib, "-la2ds_b200", "-Wl,-rpath," + lib])
+    return exe
+
+
+def test_cpp_sidecar_compiles_and_fails_loudly_without_gpu(a2ds):
+    """a2ds::DeviceAssembler (host/DeviceAssembler.h): header-only C++ mirror of the three
+    TACSAssembler entry points over the C ABI"""
+    import subprocess
+    from conftest import has_gpu
+    exe = _build_probe()
+    out = subprocess.run([exe], capture_output=True, text=True)
+    if has_gpu():
+        assert "DEVICE_ASSEMBLER_OK" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 1 and "no CUDA device" in out.stdout

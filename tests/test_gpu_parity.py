@@ -384,3 +384,11 @@ def test_device_matrix_algebra_and_spmv(a2ds):
     with pytest.raises(a2ds.A2dsError):
         asm.mat_axpy(1.0, k, 99)
     asm.close()
+
+
+def test_cpp_sidecar_runs(a2ds):
+    """the header-only C++ mirror (host/DeviceAssembler.h) end to end: K u = r on a small plate"""
+    import subprocess
+    from test_capi import _build_probe
+    out = subprocess.run([_build_probe()], capture_output=True, text=True)
+    assert out.returncode == 0 and "DEVICE_ASSEMBLER_OK" in out.stdout, out.stdout + out.stderr
