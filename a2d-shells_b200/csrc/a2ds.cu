@@ -142,6 +142,38 @@ __device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2]
     }
 }
 
+// all 9 tiles of an unsymmetric 24x24 (Z = B1^T W) into the staging area
+__device__ __forceinline__ void stage_tiles_full(double *E, const double (&acc)[9][2], int lane) {
+  const int rowb = 3 * (lane >> 2), colb = 6 * (lane & 3);
+#pragma unroll
+  for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+    for (int tj = 0; tj < 3; tj++) {
+      E[(rowb + ti) * KE_LD + colb + tj] = acc[3 * ti + tj][0];
+      E[(rowb + ti) * KE_LD + colb + 3 + tj] = acc[3 * ti + tj][1];
+    }
+}
+
+// G = Z + Z^T + geometric blocks, written block by block (64 generalised node pairs, 2 per
+// lane) from the staged Z into a second buffer
+__device__ __forceinline__ void symmetrize_add_geo(const ElemGeom &gm, const ElemWork &wk,
+                                                   const double *Pq4, const double *Z, double *G,
+                                                   int lane) {
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+    double blk[9];
+    geo_block(gm, wk, Pq4, pr, pc, blk);
+    const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        G[(r0 + i) * KE_LD + c0 + j] =
+            blk[3 * i + j] + Z[(r0 + i) * KE_LD + c0 + j] + Z[(c0 + j) * KE_LD + r0 + i];
+  }
+}
+
 // 64 geometric-stiffness 3x3 blocks (generalised node pairs), 2 per lane, added in place
 __device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWork &wk,
                                                const double *Pq4, double *E, double scale,
@@ -308,7 +340,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       // Order: B0/W -> strains, residual -> K pass -> B1 -> G pass, so that B0 and B1 are
       // never live together (the nonlinear model needs B1 first: B = B0 + B1).
       double Bc[9][3], Wc[9][3], Bq[9][3];
-      double kacc[6][2], gacc[6][2];
+      double kacc[6][2], zacc[9][2];
       if (NL) lane_b1(gm, wk, lane, Bq);
       {
         double ep[9];
@@ -352,35 +384,34 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
         }
       }
       if (GMAT) {
+        // Z = B1^T W over all 9 tiles (not symmetric); G = Z + Z^T is formed when the tiles
+        // are staged: 9 instead of 12 DMMAs per k-step
         lane_b1(gm, wk, lane, Bq);
 #pragma unroll
-        for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
+        for (int t = 0; t < 9; t++) zacc[t][0] = zacc[t][1] = 0.0;
 #pragma unroll
-        for (int ks = 0; ks < 9; ks++) {
-          // two products per tile; all first products, then all second ones, so that
-          // consecutive DMMAs never wait on the same accumulator
-          int idx = 0;
+        for (int ks = 0; ks < 9; ks++)
 #pragma unroll
           for (int ti = 0; ti < 3; ti++)
 #pragma unroll
-            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Bq[ks][ti], Wc[ks][tj]);
-          idx = 0;
-#pragma unroll
-          for (int ti = 0; ti < 3; ti++)
-#pragma unroll
-            for (int tj = ti; tj < 3; tj++, idx++) dmma884(gacc[idx], Wc[ks][ti], Bq[ks][tj]);
-        }
+            for (int tj = 0; tj < 3; tj++) dmma884(zacc[3 * ti + tj], Bq[ks][ti], Wc[ks][tj]);
       }
       // ---- stage, add the geometric blocks, scatter -------------------------------------
       if (KMAT) stage_tiles(ws.E, kacc, p.alpha, lane);
-      if (GMAT) stage_tiles(ws.E2, gacc, 1.0, lane);
+      if (GMAT) stage_tiles_full(ws.E2, zacc, lane);
       if ((GMAT || NL) && lane < 9) sum_tying_stress(wk, lane);
       __syncwarp();
-      if (GMAT) add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E2, 1.0, lane);
-      else if (NL && KMAT) add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E, p.alpha, lane);
-      if (GMAT || NL) __syncwarp();
+      if (NL && KMAT) {
+        add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E, p.alpha, lane);
+        __syncwarp();
+      }
       if (KMAT) scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
-      if (GMAT) scatter_matrix(ws.E2, p.Gval, rb.goff[j][lane & 15], lane);
+      if (GMAT) {
+        if (KMAT) __syncwarp();  // E is reused for G once K has left
+        symmetrize_add_geo(gm, wk, &ws.Pq[j][0][0], ws.E2, ws.E, lane);
+        __syncwarp();
+        scatter_matrix(ws.E, p.Gval, rb.goff[j][lane & 15], lane);
+      }
       __syncwarp();
     }
     if (!PF) batch_ids(grp + stride, e_cur, nd_cur);
