@@ -724,6 +724,10 @@ extern "C" int a2ds_set_components(a2ds_ctx *c, int n_comp, const double *Cs, co
       return fail("a2ds_set_components: unsupported element class (only TACSQuad4Shell and "
                   "TACSQuad4NonlinearShell are implemented)");
     c->h_class[i] = h[i].model;
+    h[i].coupled = 0;
+    for (int k = 6; k < 12; k++)
+      if (h[i].Cs[k] != 0.0) h[i].coupled = 1;
+    h[i].pad_ = 0;
     h[i].transform = transform;
     h[i].axis[0] = h[i].axis[1] = h[i].axis[2] = 0.0;
     if (transform == A2DS_TRANSFORM_REF_AXIS) {

@@ -67,6 +67,8 @@ struct CompData {
   double axis[3];      // normalised reference axis (transform == 1)
   int model;           // 0 linear strain model, 1 nonlinear
   int transform;       // 0 natural, 1 reference axis
+  int coupled;         // 0: the B block of Cs is identically zero
+  int pad_;
 };
 
 // leading dimension of the staged 24x24 element matrix (odd: conflict-free rows and columns)
@@ -102,11 +104,11 @@ struct ElemGeom {
   double X[12], q[24];
   double fn[12];   // unit node normals            (TacsShellComputeNodeNormals)
   double dr[12];   // directors d_m = theta_m x fn_m (TACSDirector.h:244-267)
-  double t0n[12], t1n[12], wn[12];  // node frames: T columns 0,1 and t0 x t1
-  double Sn[16];   // per node: (Xd^-1 T)[0..1][0..1]
+  double wn[12];   // per node: t0 x t1 of the node frame (rotation part of the drill row)
+  double cdr[48];  // per node n, per node m: d(drill strain at n)/d(u_m), a 3-vector
   double etn[4];   // nodal drill strain of the state, evaluated in the reference's order
   QpData qp[4];
-  // sizeof(QpData) = 57 doubles = 9 (mod 16) and sizeof(ElemGeom) = 356 doubles = 4
+  // sizeof(QpData) = 57 doubles = 9 (mod 16) and sizeof(ElemGeom) = 364 doubles = 12
   // (mod 16): the 16 (element, node) / (element, Gauss point) lanes of the batched phases
   // then fall into 16 different 8-byte shared-memory banks (measured: 8 % on the residual
   // kernel against an unlucky stride)
@@ -312,7 +314,17 @@ A2DS_HD void phase_node(const CompData &c, ElemGeom &s, int m) {
     for (int j = 0; j < 3; j++)
       S[3 * i + j] = A2DS_ADD(A2DS_ADD(A2DS_MUL(Xi[3 * i], T[j]), A2DS_MUL(Xi[3 * i + 1], T[3 + j])),
                               A2DS_MUL(Xi[3 * i + 2], T[6 + j]));
-  s.Sn[4 * m] = S[0]; s.Sn[4 * m + 1] = S[1]; s.Sn[4 * m + 2] = S[3]; s.Sn[4 * m + 3] = S[4];
+  // derivative of this node's drill strain w.r.t. the displacements of node mm:
+  //   1/2 (a0 t2 - a1 t1),  a_j = N_mm,xi(node) S[0][j] + N_mm,eta(node) S[1][j]
+  // (TacsShellComputeDrillStrain + evalDrillStrainSens, TACSShellUtilities.h:651-693, 780-818)
+#pragma unroll
+  for (int mm = 0; mm < 4; mm++) {
+    const double Nxi = (mm / 2 == m / 2) ? ((mm % 2) ? 0.5 : -0.5) : 0.0;
+    const double Neta = (mm % 2 == m % 2) ? ((mm / 2) ? 0.5 : -0.5) : 0.0;
+    const double a0 = Nxi * S[0] + Neta * S[3], a1 = Nxi * S[1] + Neta * S[4];
+#pragma unroll
+    for (int k = 0; k < 3; k++) s.cdr[12 * m + 3 * mm + k] = 0.5 * (a0 * t2[k] - a1 * t1[k]);
+  }
   {
     double uxi[3], ueta[3];
     edge_xi(s.q, 6, m / 2, uxi);
@@ -325,8 +337,6 @@ A2DS_HD void phase_node(const CompData &c, ElemGeom &s, int m) {
   scross(&s.q[6 * m + 3], fn, d);
   for (int k = 0; k < 3; k++) {
     s.fn[3 * m + k] = fn[k];
-    s.t0n[3 * m + k] = t1[k];
-    s.t1n[3 * m + k] = t2[k];
     s.wn[3 * m + k] = w[k];
     s.dr[3 * m + k] = d[k];
   }
@@ -579,15 +589,10 @@ A2DS_HD void strain_columns(const ElemGeom &s, const QpData &g, const double na[
     double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int n = 0; n < 4; n++) {
-      // shape function derivatives of node m evaluated at node n
-      const double Nxi = (sy == n / 2) ? dN : 0.0;
-      const double Neta = (sx == n % 2) ? dM : 0.0;
-      const double a0 = Nxi * s.Sn[4 * n] + Neta * s.Sn[4 * n + 2];
-      const double a1 = Nxi * s.Sn[4 * n + 1] + Neta * s.Sn[4 * n + 3];
       const double Nq = na[n % 2] * nb[n / 2];
+      const double *cd = &s.cdr[12 * n + 3 * m];
 #pragma unroll
-      for (int k = 0; k < 3; k++)
-        acc[k] += Nq * (0.5 * (a0 * s.t1n[3 * n + k] - a1 * s.t0n[3 * n + k]));
+      for (int k = 0; k < 3; k++) acc[k] += Nq * cd[k];
     }
     B[8][0] = acc[0]; B[8][1] = acc[1]; B[8][2] = acc[2];
   } else {
@@ -598,8 +603,22 @@ A2DS_HD void strain_columns(const ElemGeom &s, const QpData &g, const double na[
 }
 
 // s = C e (TACSShellConstitutive::computeStress, TACSShellConstitutive.h:125-147)
-A2DS_HD void apply_C(const double Cs[22], const double e[9], double s[9]) {
+// `coupled` == false: the B (membrane-bending coupling) block is identically zero (isotropic
+// shell without offset) and its 18 products are skipped; the flag is uniform over a warp.
+A2DS_HD void apply_C(const double Cs[22], const double e[9], double s[9], bool coupled = true) {
   const double *A = &Cs[0], *B = &Cs[6], *D = &Cs[12], *As = &Cs[18];
+  if (!coupled) {
+    s[0] = A[0] * e[0] + A[1] * e[1] + A[2] * e[2];
+    s[1] = A[1] * e[0] + A[3] * e[1] + A[4] * e[2];
+    s[2] = A[2] * e[0] + A[4] * e[1] + A[5] * e[2];
+    s[3] = D[0] * e[3] + D[1] * e[4] + D[2] * e[5];
+    s[4] = D[1] * e[3] + D[3] * e[4] + D[4] * e[5];
+    s[5] = D[2] * e[3] + D[4] * e[4] + D[5] * e[5];
+    s[6] = As[0] * e[6] + As[1] * e[7];
+    s[7] = As[1] * e[6] + As[2] * e[7];
+    s[8] = Cs[21] * e[8];
+    return;
+  }
   s[0] = A[0] * e[0] + A[1] * e[1] + A[2] * e[2] + B[0] * e[3] + B[1] * e[4] + B[2] * e[5];
   s[1] = A[1] * e[0] + A[3] * e[1] + A[4] * e[2] + B[1] * e[3] + B[3] * e[4] + B[4] * e[5];
   s[2] = A[2] * e[0] + A[4] * e[1] + A[5] * e[2] + B[2] * e[3] + B[4] * e[4] + B[5] * e[5];
@@ -672,7 +691,7 @@ A2DS_HD void lane_b0w(const CompData &c, const ElemGeom &s, int lane, const Want
     double b[9], cb[9];
 #pragma unroll
     for (int r = 0; r < 9; r++) b[r] = Bc[r][k];
-    apply_C(c.Cs, b, cb);
+    apply_C(c.Cs, b, cb, c.coupled != 0);
 #pragma unroll
     for (int r = 0; r < 9; r++) Wc[r][k] = gw * cb[r];
   }

@@ -18,6 +18,9 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   c.temperature = temperature;
   c.model = model;
   c.transform = transform;
+  c.coupled = 0;
+  for (int k = 6; k < 12; k++)
+    if (c.Cs[k] != 0.0) c.coupled = 1;
   memcpy(c.axis, axis, sizeof(c.axis));
   static ElemGeom s;
   static ElemWork wk;
