@@ -27,6 +27,7 @@ SYMBOLS = [
     "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
     "a2ds_last_kernel_ms", "a2ds_region_begin", "a2ds_region_end",
     "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
+    "a2ds_add_jacobian_vec_product", "a2ds_add_jacobian_vec_product_dev",
 ]
 
 _LIB = None
@@ -282,6 +283,20 @@ class Assembler:
         r = self._res_out(download)
         self._chk(self.L.a2ds_assemble_all(self.ctx, _p(r), C.c_int(kmat), C.c_int(gmat)))
         return r
+
+    def addJacobianVecProduct(self, scale, alpha, x, y):
+        """y <- y + scale * alpha * K x (matrix free), BC rows zeroed; returns the new y"""
+        x = _f64(x).reshape(-1, 6)
+        y = np.array(y, dtype=np.float64).reshape(-1, 6)
+        assert x.shape[0] == self.n_nodes and y.shape[0] == self.n_nodes
+        self._chk(self.L.a2ds_add_jacobian_vec_product(self.ctx, C.c_double(scale),
+                                                       C.c_double(alpha), _p(x), _p(y)))
+        return y
+
+    def addJacobianVecProduct_dev(self, scale, alpha, x_dev, y_dev):
+        self._chk(self.L.a2ds_add_jacobian_vec_product_dev(self.ctx, C.c_double(scale),
+                                                           C.c_double(alpha), C.c_void_p(x_dev),
+                                                           C.c_void_p(y_dev)))
 
     def res_dev(self):
         p = C.c_void_p()

@@ -67,6 +67,8 @@ struct KParams {
   double *Gval;
   const int *Goff;
   double alpha;
+  double res_scale;      // residual entries are multiplied by this before the RED
+  double thermal;        // 1: residual of the state;  0: matrix-free product K x (u := x)
   int scratch_bytes;
 };
 
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
   const bool PF = GMAT || NL;  // full scratch + asynchronous prefetch of the next batch
   const unsigned FULL = 0xffffffffu;
   Want w;
-  w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL;
+  w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL; w.thermal = p.thermal;
   const bool need_state = GMAT || NL;
 
   const int n_groups = (p.n_list + NB - 1) / NB;
@@ -364,9 +366,9 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
             }
             if ((lane & 3) == 0) {
               double *r = &p.res[6 * (size_t)ws.nodes[j][lane_m(lane)] + 3 * lane_h(lane)];
-              atomicAdd(r, r3[0]);
-              atomicAdd(r + 1, r3[1]);
-              atomicAdd(r + 2, r3[2]);
+              atomicAdd(r, p.res_scale * r3[0]);
+              atomicAdd(r + 1, p.res_scale * r3[1]);
+              atomicAdd(r + 2, p.res_scale * r3[2]);
             }
           }
         }
@@ -456,6 +458,14 @@ __global__ void k_res_bcs(int n_bc, const int *nodes, const int *vars, const dou
   if (t >= 6 * n_bc) return;
   const int b = t / 6, k = t - 6 * b, n = nodes[b];
   if (n < n_owned && (vars[b] & (1 << k))) res[6 * (size_t)n + k] = u[6 * (size_t)n + k] - vals[t];
+}
+
+// vector BC rows set to zero (TACSBVec::applyBCs without a state vector, TACSBVec.cpp:570-584)
+__global__ void k_vec_zero_bcs(int n_bc, const int *nodes, const int *vars, double *y, int n_owned) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n_bc) return;
+  const int b = t / 6, k = t - 6 * b, n = nodes[b];
+  if (n < n_owned && (vars[b] & (1 << k))) y[6 * (size_t)n + k] = 0.0;
 }
 
 // matrix BC rows: zero the constrained DOF rows of every block in the block row, 1.0 on
@@ -1216,6 +1226,7 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
   memset(&p, 0, sizeof(p));
   p.conn = c->conn; p.elem_comp = c->elem_comp; p.comps = c->comps;
   p.X = c->X; p.u = c->u; p.res = c->res; p.alpha = alpha;
+  p.res_scale = 1.0; p.thermal = 1.0;
   if (KM) { p.Kval = c->mats[kmat].A; p.Koff = c->mats[kmat].off; }
   if (GM) { p.Gval = c->mats[gmat].A; p.Goff = c->mats[gmat].off; }
 
@@ -1304,6 +1315,63 @@ extern "C" int a2ds_assemble_mat_type(a2ds_ctx *c, int mat_type, int mat) {
 
 extern "C" int a2ds_assemble_all(a2ds_ctx *c, double *res, int kmat, int gmat) {
   return run_assembly(c, 7, 1.0, kmat, gmat, res);
+}
+
+// TACSAssembler::addJacobianVecProduct (src/TACSAssembler.cpp:4331-4391), matrix free:
+// y <- y + scale * (alpha K) x, then the BC rows of y are zeroed.  For the linear strain
+// model K does not depend on the state and K x is the element residual evaluated at x
+// without thermal strain: r(x) = sum w B^T C B x — the residual kernel with u := x.
+extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, double alpha,
+                                                 const double *x_dev, double *y_dev) {
+  CU(cudaSetDevice(c->device));
+  if (!c->mesh_set) return fail("addJacobianVecProduct: mesh or nodes not set");
+  if (build_lists(c)) return 1;
+  for (int col = 0; col < c->n_colors; col++)
+    if (c->list_len[1][col] > 0)
+      return fail("addJacobianVecProduct: only linear-strain elements (TACSQuad4Shell) are "
+                  "supported matrix-free; assemble the tangent of nonlinear elements instead");
+  c->last_launches = 0;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.conn = c->conn; p.elem_comp = c->elem_comp; p.comps = c->comps;
+  p.X = c->X; p.u = x_dev; p.res = y_dev; p.alpha = 1.0;
+  p.res_scale = scale * alpha; p.thermal = 0.0;
+  CU(cudaEventRecord(c->evk0, c->stream));
+  for (int col = 0; col < c->n_colors; col++) {
+    p.n_list = c->list_len[0][col];
+    p.elem_list = c->list_dev[0][col];
+    if (p.n_list == 0) continue;
+    if (launch_one<true, false, false, false>(c, p)) return 1;
+  }
+  CU(cudaEventRecord(c->evk1, c->stream));
+  if (halo_exchange(c, y_dev, true)) return 1;
+  if (c->n_bc) {
+    k_vec_zero_bcs<<<(6 * c->n_bc + 255) / 256, 256, 0, c->stream>>>(c->n_bc, c->bc_nodes,
+                                                                     c->bc_vars, y_dev, c->n_owned);
+    c->last_launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev1, c->stream));
+  return 0;
+}
+
+extern "C" int a2ds_add_jacobian_vec_product(a2ds_ctx *c, double scale, double alpha,
+                                             const double *x, double *y) {
+  CU(cudaSetDevice(c->device));
+  const size_t nb = 6 * (size_t)c->n_nodes * sizeof(double);
+  double *dx = nullptr, *dy = nullptr;
+  CU(cudaMalloc((void **)&dx, std::max<size_t>(nb, 8)));
+  CU(cudaMalloc((void **)&dy, std::max<size_t>(nb, 8)));
+  CU(cudaMemcpyAsync(dx, x, nb, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(dy, y, nb, cudaMemcpyHostToDevice, c->stream));
+  int rc = a2ds_add_jacobian_vec_product_dev(c, scale, alpha, dx, dy);
+  if (!rc) {
+    CU(cudaMemcpyAsync(y, dy, nb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(dx); cudaFree(dy);
+  return rc;
 }
 
 extern "C" int a2ds_last_timing(a2ds_ctx *c, float *ms, int *launches) {

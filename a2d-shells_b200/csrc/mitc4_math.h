@@ -634,6 +634,7 @@ A2DS_HD void apply_C(const double Cs[22], const double e[9], double s[9], bool c
 struct Want {
   bool res, kmat, gmat;  // residual, tangent, geometric stiffness
   bool nonlinear;        // element uses the nonlinear strain model (tangent/residual)
+  double thermal;        // 1: mechanical strain e - T eth;  0: plain B q (matrix-free product)
 };
 
 // ---- column phase: lane = (qp, m, h) ------------------------------------------------
@@ -710,7 +711,9 @@ A2DS_HD void lane_stress(const CompData &c, const ElemGeom &s, ElemWork &wk, int
   const double qp_w = s.qp[qp].w;
   double e[9];
 #pragma unroll
-  for (int r = 0; r < 9; r++) e[r] = e_qp[r] - c.temperature * c.eth[r];
+  const double Tth = w.thermal * c.temperature;
+#pragma unroll
+  for (int r = 0; r < 9; r++) e[r] = e_qp[r] - Tth * c.eth[r];
   {
     // drilling strain of the state: interpolate the nodal values evaluated in the
     // reference's order (interpFields<1,1>, TACSShellElement.h:350)
@@ -718,7 +721,7 @@ A2DS_HD void lane_stress(const CompData &c, const ElemGeom &s, ElemWork &wk, int
 #pragma unroll
     for (int n = 0; n < 4; n++)
       et = A2DS_ADD(et, A2DS_MUL(A2DS_MUL(na[n % 2], nb[n / 2]), s.etn[n]));
-    e[8] = et - c.temperature * c.eth[8];
+    e[8] = (w.thermal != 0.0 ? et : e_qp[8]) - Tth * c.eth[8];
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) {

@@ -105,6 +105,48 @@ def plate_slab(rank, n_ranks, nx, ny, lx=1.0, ly=1.0, bump=1e-3):
                 recv_lists=recv_lists)
 
 
+def cylinder_slab(rank, n_ranks, ntheta, nx, radius=0.2, length=0.4):
+    """Rank `rank`'s slab of a closed cylinder of ntheta x (n_ranks*nx) elements cut into
+    axial slabs (BASELINE configs[2]/[4]: 2000x2000 on 1-8 GPUs, 4000x4000 = 16 M elements
+    on 8).  Same conventions as plate_slab / cylinder: node id = ring*ntheta + it, periodic in
+    theta, first-touch ownership (the ring shared with the slab below belongs to it)."""
+    i0 = rank * nx
+    first_owned = i0 if rank == 0 else i0 + 1
+    rings = np.arange(first_owned, i0 + nx + 1)
+    n_owned = len(rings) * ntheta
+    glob_owned = (rings[:, None] * ntheta + np.arange(ntheta)[None, :]).ravel()
+    glob_ghost = (i0 * ntheta + np.arange(ntheta)) if rank > 0 else np.zeros(0, dtype=np.int64)
+    glob = np.concatenate([glob_owned, glob_ghost]).astype(np.int64)
+
+    def local(ring, it):
+        ring = np.asarray(ring); it = np.asarray(it)
+        own = (ring - first_owned) * ntheta + it
+        return np.where(ring >= first_owned, own, n_owned + it)
+
+    et, ex = np.meshgrid(np.arange(ntheta), np.arange(nx), indexing="xy")
+    et = et.ravel(); ex = ex.ravel() + i0
+    etp = (et + 1) % ntheta
+    conn = np.stack([local(ex, et), local(ex, etp), local(ex + 1, et), local(ex + 1, etp)],
+                    axis=1).astype(np.int32)
+    it = glob % ntheta; ix = glob // ntheta
+    th = it * (2 * np.pi / ntheta)
+    x = ix * (length / (nx * n_ranks))
+    X = np.stack([x, -radius * np.sin(th), -radius * np.cos(th)], axis=1)
+    ends = np.nonzero((ix[:n_owned] == 0) | (ix[:n_owned] == nx * n_ranks))[0].astype(np.int32)
+    peers, send_lists, recv_lists = [], [], []
+    if rank > 0:
+        peers.append(rank - 1)
+        send_lists.append(np.zeros(0, dtype=np.int32))
+        recv_lists.append((n_owned + np.arange(ntheta)).astype(np.int32))
+    if rank < n_ranks - 1:
+        peers.append(rank + 1)
+        send_lists.append(local(np.full(ntheta, i0 + nx), np.arange(ntheta)).astype(np.int32))
+        recv_lists.append(np.zeros(0, dtype=np.int32))
+    return dict(conn=conn, X=X, n_owned=n_owned, n_nodes=len(glob), glob=glob, bc_nodes=ends,
+                peers=np.asarray(peers, dtype=np.int32), send_lists=send_lists,
+                recv_lists=recv_lists)
+
+
 def partition_rows(conn, n_nodes, elem_rank):
     """Element-wise partition -> per-rank local meshes with TACSCreator's node ownership
     rule: a node belongs to the rank of the first element (in global order) touching it

@@ -22,6 +22,7 @@ kernel: algorithmic bytes / kernel time against the measured copy bandwidth), `f
 on a bounded sample of the same workload).
 """
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
@@ -190,6 +191,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=1000, help="elements per side of a rank's slab")
+    ap.add_argument("--workload", default="plate", choices=["plate", "cylinder", "cylinder-nl"],
+                    help="plate: BASELINE configs[1] per GPU (default, the judged line); "
+                         "cylinder: 4000 x 500 elements per GPU (= the 16 M-element cylinder of "
+                         "configs[4] on 8 GPUs), fused res+K+G; cylinder-nl: 2000 x (2000/N) "
+                         "per GPU, nonlinear Newton tangent res+K (configs[2], strong scaling)")
     ap.add_argument("--ref-nx", type=int, default=250, help="plate side of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -211,14 +217,28 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     nx = ny = args.nx
-    slab = a2ds.meshes.plate_slab(rank, world, nx, ny, bump=0.0)
+    nonlinear = args.workload == "cylinder-nl"
+    if args.workload == "plate":
+        slab = a2ds.meshes.plate_slab(rank, world, nx, ny, bump=0.0)
+        wl = (f"flat plate {nx}x{ny * world} MITC4 quads (BASELINE configs[1] per GPU), fused "
+              f"residual+Kmat+Gmat, linear elastic iso shell")
+    elif args.workload == "cylinder":
+        nx, ny = 4000, 500
+        slab = a2ds.meshes.cylinder_slab(rank, world, nx, ny)
+        wl = (f"cylinder {nx}x{ny * world} MITC4 quads ({nx * ny * world / 1e6:.0f} M elements, "
+              f"BASELINE configs[4] at 8 GPUs), fused residual+Kmat+Gmat")
+    else:
+        nx, ny = 2000, 2000 // world
+        slab = a2ds.meshes.cylinder_slab(rank, world, nx, ny)
+        wl = (f"cylinder {nx}x{ny * world} MITC4 quads, geometrically nonlinear Newton tangent "
+              f"(TACSQuad4NonlinearShell): residual+Kmat about a state of 1e-3 (BASELINE configs[2])")
     n_nodes, n_owned, conn = slab["n_nodes"], slab["n_owned"], slab["conn"]
     n_elems = len(conn)
     Cs, eth = a2ds.iso_shell_tables()
     asm = a2ds.Assembler(local_rank)
     asm.set_mesh(conn, n_nodes, n_owned)
     asm.set_nodes(slab["X"])
-    asm.set_components(Cs[None], eth[None])
+    asm.set_components(Cs[None], eth[None], elem_class=[1 if nonlinear else 0])
     asm.set_bcs(slab["bc_nodes"], 63)
     if world > 1:
         uid = [asm.comm_unique_id() if rank == 0 else None]
@@ -229,7 +249,7 @@ def main():
 
     # pinned host buffers: the state comes from the host each e2e step, the residual goes back
     u_host = torch.empty((n_owned, 6), dtype=torch.float64, pin_memory=True)
-    u_host.numpy()[:] = a2ds.meshes.seeded_state(slab["glob"][:n_owned], 1e-5)
+    u_host.numpy()[:] = a2ds.meshes.seeded_state(slab["glob"][:n_owned], 1e-3 if nonlinear else 1e-5)
     r_host = torch.empty((n_owned, 6), dtype=torch.float64, pin_memory=True)
 
     def barrier():
@@ -239,16 +259,24 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def assemble(out_ptr=None):
+        if nonlinear:   # Newton tangent: residual + K of the nonlinear model
+            asm._chk(asm.L.a2ds_assemble_jacobian(asm.ctx, C.c_double(1.0), C.c_double(0.0),
+                                                  C.c_double(0.0), C.c_void_p(out_ptr), C.c_int(kmat)))
+        else:
+            asm._chk(asm.L.a2ds_assemble_all(asm.ctx, C.c_void_p(out_ptr), C.c_int(kmat),
+                                             C.c_int(gmat)))
+
     def step_resident():
         if world > 1:
             asm.halo_forward()
-        asm.assembleAll(kmat, gmat, download=False)
+        assemble(None)
 
     def step_e2e():
         asm.set_state_ptr(n_owned, u_host.data_ptr())
         if world > 1:
             asm.halo_forward()
-        asm.assembleAll(kmat, gmat, out_ptr=r_host.data_ptr())
+        assemble(r_host.data_ptr())
 
     # state resident in HBM for the kernel-level number
     asm.set_state_ptr(n_owned, u_host.data_ptr())
@@ -300,28 +328,32 @@ def main():
         peaks, which = measured_peaks()
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         value = total_elems / (ms_step * 1e-3)
-        achieved = ALG_BYTES_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e9
+        alg_bytes = 2728.0 if nonlinear else ALG_BYTES_PER_ELEM   # res+K only for the Newton tangent
+        achieved = alg_bytes * n_elems / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "shell elements/sec (res+Kmat+Gmat into BCSR6)",
             "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if nonlinear else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {
-                "workload": f"flat plate {nx}x{ny * world} MITC4 quads (BASELINE configs[1] per "
-                            f"GPU), fused residual+Kmat+Gmat, linear elastic iso shell",
+                "workload": wl,
                 "elements_per_gpu": n_elems, "partition": f"{world} row slabs, first-touch ownership",
                 "l2": "outputs (2 x 2.6 GB BCSR) and inputs exceed the 126 MB L2 every step",
                 "scatter": "atomic"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": DRAM_TRAFFIC_PER_ELEM * n_elems,
+                         "frac": achieved / hbm,
+                         "traffic": DRAM_TRAFFIC_PER_ELEM * n_elems if args.workload == "plate" else None,
                          "traffic_source": "ncu capture at 1M elements, profiles/r01e_*",
                          "peak_source": which,
-                         "kernel": "k_assemble<res,K,G>", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEM},
+                         "kernel": "k_assemble<res,K,nonlinear>" if nonlinear else "k_assemble<res,K,G>",
+                         "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_element": alg_bytes},
             "fp64": {"note": "the FP64 pipe, not HBM, bounds this kernel (SURVEY.md §8(d))",
                      "dfma_peak_tflops_measured": DFMA_PEAK_TFLOPS,
-                     "reference_flops_per_element": REF_FLOPS_PER_ELEM,
-                     "reference_count_tflops": REF_FLOPS_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12},
+                     "reference_flops_per_element": 171290.0 if nonlinear else REF_FLOPS_PER_ELEM,
+                     "reference_count_tflops": (171290.0 if nonlinear else REF_FLOPS_PER_ELEM) *
+                     n_elems / (k_ms * 1e-3) / 1e12},
             "e2e": {"value": total_elems / (e2e_ms * 1e-3), "unit": "elements/s",
                     "h2d_bytes_per_step": int(u_host.numel() * 8 * world),
                     "d2h_bytes_per_step": int(r_host.numel() * 8 * world),

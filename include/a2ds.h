@@ -158,6 +158,14 @@ int a2ds_assemble_mat_type(a2ds_ctx *ctx, int mat_type, int mat);
  * buckling flow asks for in three calls, src/TACSBuckling.cpp:239-266) */
 int a2ds_assemble_all(a2ds_ctx *ctx, double *res, int kmat, int gmat);
 
+/* TACSAssembler::addJacobianVecProduct (src/TACSAssembler.cpp:4331-4391), matrix free:
+ * y <- y + scale * (alpha K) x, BC rows of y zeroed; x, y hold 6 * n_nodes doubles (all
+ * local nodes; ghost entries of x must be current).  Linear-strain elements only. */
+int a2ds_add_jacobian_vec_product(a2ds_ctx *ctx, double scale, double alpha, const double *x,
+                                  double *y);
+int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *ctx, double scale, double alpha,
+                                      const double *x_dev, double *y_dev);
+
 /* device-resident residual of the last assembly, 6 * n_nodes doubles */
 int a2ds_res_dev(a2ds_ctx *ctx, double **res_dev);
 /* device-resident state, 6 * n_nodes doubles */

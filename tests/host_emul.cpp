@@ -29,7 +29,7 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   memcpy(s.X, X, sizeof(s.X));
   memcpy(s.q, q, sizeof(s.q));
   Want w;
-  w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1;
+  w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1; w.thermal = 1.0;
   for (int m = 0; m < 4; m++) phase_node(c, s, m);
   static double Pq[4][6];
   for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, w.gmat || w.nonlinear, Pq[qp]);

@@ -126,3 +126,25 @@ def test_cpp_sidecar_compiles_and_fails_loudly_without_gpu(a2ds):
         assert "DEVICE_ASSEMBLER_OK" in out.stdout, out.stdout + out.stderr
     else:
         assert out.returncode == 1 and "no CUDA device" in out.stdout
+
+
+def test_structured_slabs_match_generic_partition(a2ds):
+    """plate_slab / cylinder_slab (built per rank, no global mesh) against partition_rows"""
+    nx, ny, N = 5, 3, 3
+    conn, X, _ = a2ds.meshes.plate(nx, ny * N, ly=float(N))
+    parts = a2ds.meshes.partition_rows(conn, len(X), np.arange(len(conn)) // (nx * ny))
+    for r in range(N):
+        s, p = a2ds.meshes.plate_slab(r, N, nx, ny), parts[r]
+        assert np.array_equal(s["glob"], p["glob"]) and np.array_equal(s["conn"], p["conn_local"])
+        assert s["n_owned"] == len(p["owned"]) and list(s["peers"]) == list(p["peers"])
+        for a, b in zip(s["send_lists"] + s["recv_lists"], p["send_lists"] + p["recv_lists"]):
+            assert np.array_equal(a, b)
+    nt, nxp = 6, 2
+    conn, X, _ = a2ds.meshes.cylinder(nt, nxp * N)
+    parts = a2ds.meshes.partition_rows(conn, len(X), np.arange(len(conn)) // (nt * nxp))
+    for r in range(N):
+        s, p = a2ds.meshes.cylinder_slab(r, N, nt, nxp), parts[r]
+        assert np.array_equal(s["glob"], p["glob"]) and np.array_equal(s["conn"], p["conn_local"])
+        assert np.allclose(s["X"], X[s["glob"]])
+        for a, b in zip(s["send_lists"] + s["recv_lists"], p["send_lists"] + p["recv_lists"]):
+            assert np.array_equal(a, b)

@@ -392,3 +392,29 @@ def test_cpp_sidecar_runs(a2ds):
     from test_capi import _build_probe
     out = subprocess.run([_build_probe()], capture_output=True, text=True)
     assert out.returncode == 0 and "DEVICE_ASSEMBLER_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_matrix_free_jacobian_vec_product(a2ds, orc):
+    """TACSAssembler::addJacobianVecProduct (src/TACSAssembler.cpp:4331): y += scale alpha K x
+    without forming K, against the assembled oracle matrix; BC rows of y are zeroed."""
+    conn, X, bcn = a2ds.meshes.plate(13, 8, bump=3e-2)
+    n = len(X)
+    Cs, eth = a2ds.iso_shell_tables(t_offset=0.2)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n); asm.set_nodes(X)
+    asm.set_components(Cs[None], eth[None], temperature=[25.0])   # thermal strain must not enter
+    asm.set_bcs(bcn, 0b011011)
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(n, 6)); y0 = rng.normal(size=(n, 6))
+    y = asm.addJacobianVecProduct(0.7, 2.0, x, y0)
+    rowp, cols = orc.pattern(n, conn)
+    comp = orc.make_comp(0, Cs, eth, (0, 0, 0), 25.0)
+    _, K = orc.assemble(2, conn, np.zeros(len(conn), dtype=np.int32), [comp], X, np.zeros((n, 6)),
+                        rowp, cols)          # no BCs: raw K
+    ref = y0 + 0.7 * 2.0 * bcsr_matvec(K, rowp, cols, x)
+    for nd in bcn:
+        for k in range(6):
+            if 0b011011 & (1 << k):
+                ref[nd, k] = 0.0
+    assert relmax(y, ref) < 1e-12
+    asm.close()
