@@ -90,35 +90,35 @@ static const int MAX_WARPS_PER_BLOCK = 4;
 #endif
 #define A2DS_MIN_BLOCKS(GMAT, NL) (((GMAT) || (NL)) ? A2DS_MB_G : A2DS_MB_K)
 
-// scatter one staged 24x24 element matrix: for each of the 16 node-pair blocks the 36
-// entries leave as one full-warp RED (entries 0..31) + one 4-lane RED (32..35), i.e.
-// consecutive lanes hit consecutive doubles of a BCSR block.  Every slot has a block
-// (a2ds_mat_create refuses patterns with missing blocks), so there is no validity
-// branch; loads are batched 8 blocks at a time so the REDs do not wait on shared memory
-// one by one.
+// scatter one staged 24x24 element matrix.  Per 8 of the 16 node-pair blocks: 8 full-warp
+// REDs carry entries 0..31 of one block each (consecutive lanes -> consecutive doubles) and
+// ONE more full-warp RED carries the four remaining entries 32..35 of all 8 blocks (lane =
+// 4 * block + entry): 18 REDs per matrix, no divergent tail.  Every slot has a block
+// (a2ds_mat_create refuses patterns with missing blocks), so there is no validity branch;
+// loads are batched so the REDs do not wait on shared memory one by one.
 __device__ __forceinline__ void scatter_matrix(const double *E, double *vals, int off16,
                                                int lane) {
   const unsigned FULL = 0xffffffffu;
   const int r0 = lane / 6, c0 = lane - 6 * r0;   // entry `lane` of a 6x6 block
   const int src0 = r0 * KE_LD + c0;
-  const int src1 = 5 * KE_LD + 2 + (lane & 3);   // entries 32..35: row 5, columns 2..5
+  const int tb = lane >> 2;                      // tail RED: block tb of the current 8
+  const int src1 = 6 * (tb >> 2) * KE_LD + 6 * (tb & 3) + 5 * KE_LD + 2 + (lane & 3);
 #pragma unroll
   for (int half = 0; half < 2; half++) {
-    double v0[8], v1[8];
+    double v0[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int b = 8 * half + k;
-      const double *Eb = E + 6 * (b >> 2) * KE_LD + 6 * (b & 3);
-      v0[k] = Eb[src0];
-      v1[k] = Eb[src1];
+      v0[k] = E[6 * (b >> 2) * KE_LD + 6 * (b & 3) + src0];
     }
+    const double v1 = E[12 * half * KE_LD + src1];   // blocks 8..15 start two block rows down
+    const int offt = __shfl_sync(FULL, off16, 8 * half + tb);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int off = __shfl_sync(FULL, off16, 8 * half + k);
-      double *dst = vals + 36 * (size_t)off;
-      atomicAdd(dst + lane, v0[k]);
-      if (lane < 4) atomicAdd(dst + 32 + lane, v1[k]);
+      atomicAdd(vals + 36 * (size_t)off + lane, v0[k]);
     }
+    atomicAdd(vals + 36 * (size_t)offt + 32 + (lane & 3), v1);
   }
 }
 
@@ -198,7 +198,7 @@ __device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWor
 static const int NB = 4;
 struct RawBatch {          // gathered inputs of one batch, filled by cp.async
   double xq[NB][36];       // per element: X[12] then q[24]
-  int koff[NB][16], goff[NB][16];
+  int koff[NB][16];
   int comp[NB];
 };
 struct WarpScratch {
@@ -212,6 +212,7 @@ struct WarpScratch {
   ElemWork work;
   double Pq[NB][4][6];    // per Gauss point T T^T
   RawBatch raw1;          // double buffer: batch i+1 lands (cp.async) while batch i is processed
+  int goff[2][NB][16];    // block offsets of the geometric stiffness matrix (per raw buffer)
 };
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     }
   };
   // asynchronous gather of a batch into raw buffer `rb` (addresses from the ids above)
-  auto issue_gather = [&](RawBatch &rb, int e_l, int nd_l) {
+  auto issue_gather = [&](RawBatch &rb, int (*goffb)[16], int e_l, int nd_l) {
 #pragma unroll
     for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
       const int sidx = lane + 32 * r;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
       if (ej >= 0) {
         if (KMAT) cp_async4(&rb.koff[j][k], &p.Koff[16 * (size_t)ej + k]);
-        if (GMAT) cp_async4(&rb.goff[j][k], &p.Goff[16 * (size_t)ej + k]);
+        if (GMAT) cp_async4(&goffb[j][k], &p.Goff[16 * (size_t)ej + k]);
       }
     }
     if ((lane & 3) == 0 && lane < 4 * NB && e_l >= 0) cp_async4(&rb.comp[lane >> 2], &p.elem_comp[e_l]);
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
   int buf = 0;
   int e_cur, nd_cur;
   batch_ids(grp, e_cur, nd_cur);
-  if (PF && grp < n_groups) issue_gather(ws.raw0, e_cur, nd_cur);
+  if (PF && grp < n_groups) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
   for (; grp < n_groups; grp += stride, buf ^= 1) {
     const int base = grp * NB;
     const int cnt = min(NB, p.n_list - base);
@@ -296,10 +297,11 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     if (PF) batch_ids(grp + stride, e_nxt, nd_nxt);
 
     // ---- the batch gathered during the previous trip (or right now without prefetch) -----
-    if (!PF) issue_gather(ws.raw0, e_cur, nd_cur);
+    if (!PF) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
     cp_async_wait_all();
     __syncwarp();
     const RawBatch &rb = (PF && buf) ? ws.raw1 : ws.raw0;
+    const int (*goffb)[16] = ws.goff[(PF && buf) ? 1 : 0];
     if (lane < 4 * NB) ws.nodes[lane >> 2][lane & 3] = nd_cur;
 #pragma unroll
     for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
@@ -322,11 +324,12 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     {
       const int j = (lane >> 2) & (NB - 1);
       if (lane < 4 * NB && j < cnt)
-        phase_qp(p.comps[rb.comp[j]], ws.geo[j], lane & 3, need_state,
+        phase_qp(p.comps[rb.comp[j]], ws.geo[j], lane & 3, RES || GMAT || NL, need_state, NL,
                  need_state ? &ws.Pq[j][lane & 3][0] : (double *)0);
     }
     // start the gather of the next batch into the other raw buffer
-    if (PF && grp + stride < n_groups) issue_gather(buf ? ws.raw0 : ws.raw1, e_nxt, nd_nxt);
+    if (PF && grp + stride < n_groups)
+      issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ? 0 : 1], e_nxt, nd_nxt);
     if (PF) { e_cur = e_nxt; nd_cur = nd_nxt; }
     __syncwarp();
 
@@ -344,32 +347,22 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       double Bc[9][3], Wc[9][3], Bq[9][3];
       double kacc[6][2], zacc[9][2];
       if (NL) lane_b1(gm, wk, lane, Bq);
-      {
-        double ep[9];
-        lane_b0w(c, gm, lane, w, Bq, ep, Bc, Wc);
-        if (RES || GMAT || NL) {
-          // strains: sum over the 8 lanes of a Gauss point (lane bits 2..4)
+      lane_b0w(c, gm, lane, w, Bq, Bc, Wc);
+      if (RES || GMAT || NL) {
+        double r3[3];
+        lane_stress(c, gm, wk, lane, w, Wc, r3);
+        if (RES) {
+          // residual: sum over the 4 Gauss points (lane bits 0..1)
 #pragma unroll
-          for (int r = 0; r < 9; r++) {
-            ep[r] += __shfl_xor_sync(FULL, ep[r], 4);
-            ep[r] += __shfl_xor_sync(FULL, ep[r], 8);
-            ep[r] += __shfl_xor_sync(FULL, ep[r], 16);
+          for (int k = 0; k < 3; k++) {
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 1);
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 2);
           }
-          double r3[3];
-          lane_stress(c, gm, wk, lane, w, ep, Wc, r3);
-          if (RES) {
-            // residual: sum over the 4 Gauss points (lane bits 0..1)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-              r3[k] += __shfl_xor_sync(FULL, r3[k], 1);
-              r3[k] += __shfl_xor_sync(FULL, r3[k], 2);
-            }
-            if ((lane & 3) == 0) {
-              double *r = &p.res[6 * (size_t)ws.nodes[j][lane_m(lane)] + 3 * lane_h(lane)];
-              atomicAdd(r, p.res_scale * r3[0]);
-              atomicAdd(r + 1, p.res_scale * r3[1]);
-              atomicAdd(r + 2, p.res_scale * r3[2]);
-            }
+          if ((lane & 3) == 0) {
+            double *r = &p.res[6 * (size_t)ws.nodes[j][lane_m(lane)] + 3 * lane_h(lane)];
+            atomicAdd(r, p.res_scale * r3[0]);
+            atomicAdd(r + 1, p.res_scale * r3[1]);
+            atomicAdd(r + 2, p.res_scale * r3[2]);
           }
         }
       }
@@ -412,7 +405,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
         if (KMAT) __syncwarp();  // E is reused for G once K has left
         symmetrize_add_geo(gm, wk, &ws.Pq[j][0][0], ws.E2, ws.E, lane);
         __syncwarp();
-        scatter_matrix(ws.E, p.Gval, rb.goff[j][lane & 15], lane);
+        scatter_matrix(ws.E, p.Gval, goffb[j][lane & 15], lane);
       }
       __syncwarp();
     }

@@ -94,7 +94,8 @@ struct QpData {
   double M[25];         // (e0,e1,e2,e6,e7) = M (g11,g12,g13,g22,g23)
   double w;             // det(Xd) * quadrature weight
   double P0[6], P1[6];  // T u0x[:,j], T u1x[:,j] (j = 0,1) for the state
-  double pad_;          // 57 doubles: see the bank note in ElemGeom
+  double e[9];          // strains of the state at this point (e[8]: drilling strain)
+  double pad_[4];       // 69 doubles = 5 (mod 16): see the bank note in ElemGeom
 };
 
 // Element geometry: filled by the node phase (one lane per node) and the Gauss point
@@ -105,14 +106,14 @@ struct ElemGeom {
   double fn[12];   // unit node normals            (TacsShellComputeNodeNormals)
   double dr[12];   // directors d_m = theta_m x fn_m (TACSDirector.h:244-267)
   double wn[12];   // per node: t0 x t1 of the node frame (rotation part of the drill row)
-  double cdr[48];  // per node n, per node m: d(drill strain at n)/d(u_m), a 3-vector
+  double cdr[36];  // per node n, slot (m ^ n) in 0..2: d(drill strain at n)/d(u_m), a 3-vector
+                   // (zero for the diagonally opposite node, slot 3, which is not stored)
   double etn[4];   // nodal drill strain of the state, evaluated in the reference's order
   QpData qp[4];
-  // sizeof(QpData) = 57 doubles = 9 (mod 16) and sizeof(ElemGeom) = 364 doubles = 12
+  // sizeof(QpData) = 69 doubles = 5 (mod 16) and sizeof(ElemGeom) = 388 doubles = 4
   // (mod 16): the 16 (element, node) / (element, Gauss point) lanes of the batched phases
   // then fall into 16 different 8-byte shared-memory banks (measured: 8 % on the residual
   // kernel against an unlucky stride)
-  double pad_[12];
 };
 
 // Working set of the geometric-stiffness phase of the element currently being processed
@@ -318,12 +319,13 @@ A2DS_HD void phase_node(const CompData &c, ElemGeom &s, int m) {
   //   1/2 (a0 t2 - a1 t1),  a_j = N_mm,xi(node) S[0][j] + N_mm,eta(node) S[1][j]
   // (TacsShellComputeDrillStrain + evalDrillStrainSens, TACSShellUtilities.h:651-693, 780-818)
 #pragma unroll
-  for (int mm = 0; mm < 4; mm++) {
+  for (int slot = 0; slot < 3; slot++) {
+    const int mm = m ^ slot;  // the node itself, its xi neighbour, its eta neighbour
     const double Nxi = (mm / 2 == m / 2) ? ((mm % 2) ? 0.5 : -0.5) : 0.0;
     const double Neta = (mm % 2 == m % 2) ? ((mm / 2) ? 0.5 : -0.5) : 0.0;
     const double a0 = Nxi * S[0] + Neta * S[3], a1 = Nxi * S[1] + Neta * S[4];
 #pragma unroll
-    for (int k = 0; k < 3; k++) s.cdr[12 * m + 3 * mm + k] = 0.5 * (a0 * t2[k] - a1 * t1[k]);
+    for (int k = 0; k < 3; k++) s.cdr[9 * m + 3 * slot + k] = 0.5 * (a0 * t2[k] - a1 * t1[k]);
   }
   {
     double uxi[3], ueta[3];
@@ -350,6 +352,7 @@ struct QpGeom {
   double M[25];             // (e0,e1,e2,e6,e7) = M (g11,g12,g13,g22,g23)
   double w;                 // det(Xd) * quadrature weight
   double P0[6], P1[6];      // T u0x[:,j], T u1x[:,j] (j = 0,1) for the state
+  double e[9];              // strains of the state
 };
 
 // 2-point Gauss rule, 15-digit abscissa as the reference (TACSGaussQuadrature.h:26)
@@ -357,8 +360,8 @@ struct QpGeom {
 
 // ---- phase 2a: Gauss point geometry (lane >> 3) ------------------------------
 // TACSShellElement.h:520-534 and TacsShellComputeDispGrad (TACSShellUtilities.h:361-421)
-A2DS_HD void qp_geometry(const CompData &c, const ElemGeom &s, int qp, bool need_state,
-                         QpGeom &g) {
+A2DS_HD void qp_geometry(const CompData &c, const ElemGeom &s, int qp, bool want_e, bool want_P,
+                         bool nonlinear, QpGeom &g) {
   const double xi = (qp & 1) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
   const double eta = (qp & 2) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
   g.na[0] = 0.5 * (1.0 - xi); g.na[1] = 0.5 * (1.0 + xi);
@@ -411,41 +414,112 @@ A2DS_HD void qp_geometry(const CompData &c, const ElemGeom &s, int qp, bool need
     g.M[5 * r + 3] = f * (S[3 + a] * S[3 + b]);
     g.M[5 * r + 4] = f * (S[3 + a] * S[6 + b] + S[6 + a] * S[3 + b]);
   }
-  if (need_state) {
+  if (want_e || want_P) {
     // u0d = [u,xi | u,eta | d0], u1d = [d,xi | d,eta | 0] at the point
     double ua0[3], ua1[3], ub0[3], ub1[3], da0[3], da1[3], db0[3], db1[3];
     edge_vectors(s.q, 6, ua0, ua1, ub0, ub1);
     edge_vectors(s.dr, 3, da0, da1, db0, db1);
     double Y0[6], Y1[6];  // (u0d S)[:,0..1], (u1d S + u0d Sz)[:,0..1], row major 3x2
+#pragma unroll
     for (int k = 0; k < 3; k++) {
       double uxi = g.nb[0] * ua0[k] + g.nb[1] * ua1[k];
       double ueta = g.na[0] * ub0[k] + g.na[1] * ub1[k];
       double dxi = g.nb[0] * da0[k] + g.nb[1] * da1[k];
       double deta = g.na[0] * db0[k] + g.na[1] * db1[k];
       double d0 = N[0] * s.dr[k] + N[1] * s.dr[3 + k] + N[2] * s.dr[6 + k] + N[3] * s.dr[9 + k];
+#pragma unroll
       for (int j = 0; j < 2; j++) {
         Y0[2 * k + j] = uxi * g.S[j] + ueta * g.S[3 + j] + d0 * g.S[6 + j];
         Y1[2 * k + j] = dxi * g.S[j] + deta * g.S[3 + j] + uxi * g.Sz[j] + ueta * g.Sz[3 + j] +
                         d0 * g.Sz[6 + j];
       }
     }
-    // P = T (T^T Y): T is not orthonormal in general, keep both factors
+    // local displacement gradients u0x = T^T Y0, u1x = T^T Y1 (columns j = 0,1)
+    double u0x[3][2], u1x[3][2];
+#pragma unroll
     for (int j = 0; j < 2; j++) {
-      double y0[3] = {Y0[j], Y0[2 + j], Y0[4 + j]}, y1[3] = {Y1[j], Y1[2 + j], Y1[4 + j]};
-      double c00 = dot(g.t0, y0), c01 = dot(g.t1, y0), c02 = dot(g.tn, y0);
-      double c10 = dot(g.t0, y1), c11 = dot(g.t1, y1), c12 = dot(g.tn, y1);
-      for (int k = 0; k < 3; k++) {
-        g.P0[3 * j + k] = g.t0[k] * c00 + g.t1[k] * c01 + g.tn[k] * c02;
-        g.P1[3 * j + k] = g.t0[k] * c10 + g.t1[k] * c11 + g.tn[k] * c12;
+      const double y0[3] = {Y0[j], Y0[2 + j], Y0[4 + j]}, y1[3] = {Y1[j], Y1[2 + j], Y1[4 + j]};
+      u0x[0][j] = dot(g.t0, y0); u0x[1][j] = dot(g.t1, y0); u0x[2][j] = dot(g.tn, y0);
+      u1x[0][j] = dot(g.t0, y1); u1x[1][j] = dot(g.t1, y1); u1x[2][j] = dot(g.tn, y1);
+      // P = T (T^T Y): T is not orthonormal in general, keep both factors
+      if (want_P) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          g.P0[3 * j + k] = g.t0[k] * u0x[0][j] + g.t1[k] * u0x[1][j] + g.tn[k] * u0x[2][j];
+          g.P1[3 * j + k] = g.t0[k] * u1x[0][j] + g.t1[k] * u1x[1][j] + g.tn[k] * u1x[2][j];
+        }
       }
+    }
+    if (want_e) {
+      // Strains of the state, evaluated forward as the reference does (computeTyingStrain
+      // TACSShellElementModel.h:33/:644, interpTyingStrain, e0ty = S^T gty S, evalStrain
+      // :440/:1115).  Tying strains at the 9 MITC points from the edge / centre vectors:
+      double fa0[3], fa1[3], fb0[3], fb1[3];  // director averaged on the four edges
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        fa0[k] = 0.5 * (s.dr[k] + s.dr[3 + k]);      // eta = -1: nodes 0,1
+        fa1[k] = 0.5 * (s.dr[6 + k] + s.dr[9 + k]);  // eta = +1: nodes 2,3
+        fb0[k] = 0.5 * (s.dr[k] + s.dr[6 + k]);      // xi = -1: nodes 0,2
+        fb1[k] = 0.5 * (s.dr[3 + k] + s.dr[9 + k]);  // xi = +1: nodes 1,3
+      }
+      double nA0[3], nA1[3], nB0[3], nB1[3];  // node normal averaged on the four edges
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        nA0[k] = 0.5 * (s.fn[k] + s.fn[3 + k]);
+        nA1[k] = 0.5 * (s.fn[6 + k] + s.fn[9 + k]);
+        nB0[k] = 0.5 * (s.fn[k] + s.fn[6 + k]);
+        nB1[k] = 0.5 * (s.fn[3 + k] + s.fn[9 + k]);
+      }
+      double xc[3], yc[3], uxc[3], uyc[3];  // X,xi  X,eta  u,xi  u,eta at the centre
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        xc[k] = 0.5 * (a0[k] + a1[k]); yc[k] = 0.5 * (b0[k] + b1[k]);
+        uxc[k] = 0.5 * (ua0[k] + ua1[k]); uyc[k] = 0.5 * (ub0[k] + ub1[k]);
+      }
+      double g11a = dot(ua0, a0), g11b = dot(ua1, a1);
+      double g22a = dot(ub0, b0), g22b = dot(ub1, b1);
+      double g12c = 0.5 * (dot(uxc, yc) + dot(uyc, xc));
+      double g23a = 0.5 * (dot(b0, fb0) + dot(nB0, ub0)), g23b = 0.5 * (dot(b1, fb1) + dot(nB1, ub1));
+      double g13a = 0.5 * (dot(a0, fa0) + dot(nA0, ua0)), g13b = 0.5 * (dot(a1, fa1) + dot(nA1, ua1));
+      if (nonlinear) {
+        g11a += 0.5 * dot(ua0, ua0); g11b += 0.5 * dot(ua1, ua1);
+        g22a += 0.5 * dot(ub0, ub0); g22b += 0.5 * dot(ub1, ub1);
+        g12c += 0.5 * dot(uxc, uyc);
+        g23a += 0.5 * dot(fb0, ub0); g23b += 0.5 * dot(fb1, ub1);
+        g13a += 0.5 * dot(fa0, ua0); g13b += 0.5 * dot(fa1, ua1);
+      }
+      const double g5[5] = {g.nb[0] * g11a + g.nb[1] * g11b, g12c, g.nb[0] * g13a + g.nb[1] * g13b,
+                            g.na[0] * g22a + g.na[1] * g22b, g.na[0] * g23a + g.na[1] * g23b};
+      const int row[5] = {0, 1, 2, 6, 7};
+#pragma unroll
+      for (int r = 0; r < 5; r++)
+        g.e[row[r]] = g.M[5 * r] * g5[0] + g.M[5 * r + 1] * g5[1] + g.M[5 * r + 2] * g5[2] +
+                      g.M[5 * r + 3] * g5[3] + g.M[5 * r + 4] * g5[4];
+      g.e[3] = u1x[0][0];
+      g.e[4] = u1x[1][1];
+      g.e[5] = u1x[0][1] + u1x[1][0];
+      if (nonlinear) {
+        g.e[3] += u0x[0][0] * u1x[0][0] + u0x[1][0] * u1x[1][0] + u0x[2][0] * u1x[2][0];
+        g.e[4] += u0x[0][1] * u1x[0][1] + u0x[1][1] * u1x[1][1] + u0x[2][1] * u1x[2][1];
+        g.e[5] += u0x[0][0] * u1x[0][1] + u0x[1][0] * u1x[1][1] + u0x[2][0] * u1x[2][1] +
+                  u1x[0][0] * u0x[0][1] + u1x[1][0] * u0x[1][1] + u1x[2][0] * u0x[2][1];
+      }
+      // drilling strain: nodal values (reference operation order) interpolated as
+      // interpFields<1,1> does (TACSShellElement.h:350)
+      double et = 0.0;
+#pragma unroll
+      for (int n = 0; n < 4; n++)
+        et = A2DS_ADD(et, A2DS_MUL(A2DS_MUL(g.na[n % 2], g.nb[n / 2]), s.etn[n]));
+      g.e[8] = et;
     }
   }
 }
 
 // ---- phase 2: Gauss point qp of one element (one lane per Gauss point) -------------
-A2DS_HD void phase_qp(const CompData &c, ElemGeom &s, int qp, bool need_state, double *Pq) {
+A2DS_HD void phase_qp(const CompData &c, ElemGeom &s, int qp, bool want_e, bool want_P,
+                      bool nonlinear, double *Pq) {
   QpGeom g;
-  qp_geometry(c, s, qp, need_state, g);
+  qp_geometry(c, s, qp, want_e, want_P, nonlinear, g);
   QpData &d = s.qp[qp];
 #pragma unroll
   for (int k = 0; k < 3; k++) { d.t0[k] = g.t0[k]; d.t1[k] = g.t1[k]; }
@@ -456,9 +530,13 @@ A2DS_HD void phase_qp(const CompData &c, ElemGeom &s, int qp, bool need_state, d
 #pragma unroll
   for (int i = 0; i < 25; i++) d.M[i] = g.M[i];
   d.w = g.w;
-  if (need_state) {
+  if (want_P) {
 #pragma unroll
     for (int i = 0; i < 6; i++) { d.P0[i] = g.P0[i]; d.P1[i] = g.P1[i]; }
+  }
+  if (want_e) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) d.e[i] = g.e[i];
   }
   if (Pq) {  // T T^T (symmetric 6) for the geometric-stiffness phase
     const double *t0 = g.t0, *t1 = g.t1, *tn = g.tn;
@@ -589,8 +667,9 @@ A2DS_HD void strain_columns(const ElemGeom &s, const QpData &g, const double na[
     double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int n = 0; n < 4; n++) {
-      const double Nq = na[n % 2] * nb[n / 2];
-      const double *cd = &s.cdr[12 * n + 3 * m];
+      const int slot = m ^ n;  // 3: diagonally opposite node, no contribution
+      const double Nq = (slot == 3) ? 0.0 : na[n % 2] * nb[n / 2];
+      const double *cd = &s.cdr[9 * n + 3 * (slot & ~(slot >> 1))];  // slot 3 -> any valid slot
 #pragma unroll
       for (int k = 0; k < 3; k++) acc[k] += Nq * cd[k];
     }
@@ -642,9 +721,7 @@ struct Want {
 // (they are the DMMA fragments, see lane_qp above):
 //   lane_b1 : Bq = B1(q), the state dependent part (only when G or the nonlinear model is
 //             asked for); also publishes the coefficient pairs of the geometric phase
-//   lane_b0w: Bc = B0 (+ Bq for the nonlinear model), Wc = w C Bc, and the lane's
-//             contribution e_part[9] to the Gauss point strains (summed over the 8 lanes
-//             of the Gauss point with warp shuffles / a loop in the host emulation)
+//   lane_b0w: Bc = B0 (+ Bq for the nonlinear model) and Wc = w C Bc
 // They are separate so that the kernel can run the tangent contraction between them and
 // never holds B0, W and B1 at the same time.
 A2DS_HD void lane_b1(const ElemGeom &s, ElemWork &wk, int lane, double Bq[9][3]) {
@@ -663,8 +740,7 @@ A2DS_HD void lane_b1(const ElemGeom &s, ElemWork &wk, int lane, double Bq[9][3])
 }
 
 A2DS_HD void lane_b0w(const CompData &c, const ElemGeom &s, int lane, const Want &w,
-                      const double Bq[9][3], double e_part[9], double Bc[9][3],
-                      double Wc[9][3]) {
+                      const double Bq[9][3], double Bc[9][3], double Wc[9][3]) {
   const int qp = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
   const QpData &g = s.qp[qp];
   double na[2], nb[2];
@@ -672,19 +748,11 @@ A2DS_HD void lane_b0w(const CompData &c, const ElemGeom &s, int lane, const Want
   NodeCoef nc;
   node_coef(g, na, nb, m, nc);
   strain_columns(s, g, na, nb, nc, m, h, s.X, 3, s.fn, false, g.t0, g.t1, g.t0, g.t1, true, Bc);
-  const double *qc = &s.q[6 * m + 3 * h];
-  const double q0 = qc[0], q1 = qc[1], q2 = qc[2];
+  if (w.nonlinear) {  // B = B0 + B1(q)
 #pragma unroll
-  for (int r = 0; r < 9; r++) {
-    double e = Bc[r][0] * q0 + Bc[r][1] * q1 + Bc[r][2] * q2;
-    // nonlinear strain: e = B0 q + 1/2 B1 q.  For the geometric stiffness of a
-    // linear-model element only the linear strain enters the stress.
-    if (w.nonlinear) {
-      e += 0.5 * (Bq[r][0] * q0 + Bq[r][1] * q1 + Bq[r][2] * q2);
+    for (int r = 0; r < 9; r++)
 #pragma unroll
       for (int k = 0; k < 3; k++) Bc[r][k] += Bq[r][k];
-    }
-    e_part[r] = e;
   }
   const double gw = g.w;
 #pragma unroll
@@ -699,30 +767,19 @@ A2DS_HD void lane_b0w(const CompData &c, const ElemGeom &s, int lane, const Want
 }
 
 // ---- phase 3: lane = (qp, m, h): mechanical strain -> residual partials, stresses ---
-// e_qp[9] is the Gauss point strain summed over the lanes of the point.  Returns the
-// lane's three residual entries for this Gauss point, r = W^T (e - T eth) (to be summed
-// over the four Gauss points), and publishes the stresses of the geometric phase.
+// The strains of the state at the Gauss point come from phase_qp.  Returns the lane's three
+// residual entries for this Gauss point, r = W^T (e - T eth) (to be summed over the four
+// Gauss points), and publishes the stresses of the geometric phase.
 A2DS_HD void lane_stress(const CompData &c, const ElemGeom &s, ElemWork &wk, int lane,
-                         const Want &w, const double e_qp[9], const double Wc[9][3],
-                         double r3[3]) {
+                         const Want &w, const double Wc[9][3], double r3[3]) {
   const int qp = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
   double na[2], nb[2];
   qp_shape(qp, na, nb);
   const double qp_w = s.qp[qp].w;
+  const double Tth = w.thermal * c.temperature;
   double e[9];
 #pragma unroll
-  const double Tth = w.thermal * c.temperature;
-#pragma unroll
-  for (int r = 0; r < 9; r++) e[r] = e_qp[r] - Tth * c.eth[r];
-  {
-    // drilling strain of the state: interpolate the nodal values evaluated in the
-    // reference's order (interpFields<1,1>, TACSShellElement.h:350)
-    double et = 0.0;
-#pragma unroll
-    for (int n = 0; n < 4; n++)
-      et = A2DS_ADD(et, A2DS_MUL(A2DS_MUL(na[n % 2], nb[n / 2]), s.etn[n]));
-    e[8] = (w.thermal != 0.0 ? et : e_qp[8]) - Tth * c.eth[8];
-  }
+  for (int r = 0; r < 9; r++) e[r] = s.qp[qp].e[r] - Tth * c.eth[r];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     double rr = 0.0;

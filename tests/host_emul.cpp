@@ -32,24 +32,18 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
   w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1; w.thermal = 1.0;
   for (int m = 0; m < 4; m++) phase_node(c, s, m);
   static double Pq[4][6];
-  for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, w.gmat || w.nonlinear, Pq[qp]);
-  static double ep[32][9];
+  for (int qp = 0; qp < 4; qp++)
+    phase_qp(c, s, qp, true, w.gmat || w.nonlinear, w.nonlinear, Pq[qp]);
   static double Bc[32][9][3], Wc[32][9][3], Bq[32][9][3];
   memset(Bq, 0, sizeof(Bq));
   for (int lane = 0; lane < 32; lane++) {
     if (w.gmat || w.nonlinear) lane_b1(s, wk, lane, Bq[lane]);
-    lane_b0w(c, s, lane, w, Bq[lane], ep[lane], Bc[lane], Wc[lane]);
+    lane_b0w(c, s, lane, w, Bq[lane], Bc[lane], Wc[lane]);
   }
   memset(res, 0, 24 * sizeof(double));
   for (int lane = 0; lane < 32; lane++) {
-    const int qp = lane_qp(lane);
-    double e[9], r3[3];
-    for (int r = 0; r < 9; r++) {
-      e[r] = 0.0;
-      for (int l = 0; l < 32; l++)
-        if (lane_qp(l) == qp) e[r] += ep[l][r];
-    }
-    lane_stress(c, s, wk, lane, w, e, Wc[lane], r3);
+    double r3[3];
+    lane_stress(c, s, wk, lane, w, Wc[lane], r3);
     const int col = 6 * lane_m(lane) + 3 * lane_h(lane);
     for (int k = 0; k < 3; k++) res[col + k] += r3[k];
   }
