@@ -384,8 +384,9 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
         lane_b1(gm, wk, lane, Bq);
 #pragma unroll
         for (int t = 0; t < 9; t++) zacc[t][0] = zacc[t][1] = 0.0;
+        // the drilling strain is linear in the state: row 8 of B1 is zero, 8 k-steps suffice
 #pragma unroll
-        for (int ks = 0; ks < 9; ks++)
+        for (int ks = 0; ks < 8; ks++)
 #pragma unroll
           for (int ti = 0; ti < 3; ti++)
 #pragma unroll
@@ -394,7 +395,10 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       // ---- stage, add the geometric blocks, scatter -------------------------------------
       if (KMAT) stage_tiles(ws.E, kacc, p.alpha, lane);
       if (GMAT) stage_tiles_full(ws.E2, zacc, lane);
-      if ((GMAT || NL) && lane < 9) sum_tying_stress(wk, lane);
+      if (GMAT || NL) {
+        __syncwarp();  // the per Gauss point stresses (lane_stress) are published
+        if (lane < 9) sum_tying_stress(wk, lane);
+      }
       __syncwarp();
       if (NL && KMAT) {
         add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E, p.alpha, lane);

@@ -45,6 +45,28 @@ for r in data:
     if "DMMA" in s: mma += 1
     if "WARPSYNC" in s: flush("WARPSYNC")
 flush("end")
+# per source function (needs the library that was profiled still built in-tree):
+# samples, executed warp instructions, FP64-pipe warp instructions (DFMA/DMUL/DADD, DMMA)
+if len(sys.argv) > 2:
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import sass_account
+    table = sass_account.line_table(sys.argv[2])
+    if len(table) == len(data):
+        agg = collections.defaultdict(lambda: [0, 0, 0, 0])
+        for (off, fn, text), r in zip(table, data):
+            a = agg[fn]
+            ex = int(r[ix["Instructions Executed"]])
+            a[0] += int(r[ix["# Samples"]]); a[1] += ex
+            cl = sass_account.classify(text)
+            if cl in ("DFMA", "DMUL", "DADD"): a[2] += ex
+            if cl == "DMMA": a[3] += ex
+        tot_ex = sum(a[1] for a in agg.values())
+        print("\nby source function: % samples | % warp instructions | FP64 warp instr | DMMA")
+        for fn, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {fn:28s} {100*a[0]/max(n,1):5.1f}%  {100*a[1]/max(tot_ex,1):5.1f}%  {a[2]:10d} {a[3]:9d}")
+    else:
+        print(f"\n(per-function table skipped: library has {len(table)} SASS lines, report {len(data)})")
 top = sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:12]
 print("\nhottest SASS instructions:")
 for r in top: print(f"  {int(r[ix['# Samples']]):6d}  {r[ix['Source']][:80]}")
