@@ -31,20 +31,6 @@ for r in data:
         if r[ix[c]].isdigit(): tot[c] += int(r[ix[c]])
 print("\nwarp-state samples:", n)
 for c, v in tot.most_common(10): print(f"  {c:26s} {100*v/max(n,1):5.1f}%")
-# phase split by marker instructions (WARPSYNC boundaries)
-print("\nsamples between warp-sync points (kernel phases in program order):")
-acc = 0; insts = 0; seg = 0; fp = 0; mma = 0
-def flush(tag):
-    global acc, insts, seg, fp, mma
-    print(f"  segment {seg:2d}: {100*acc/max(n,1):5.1f}% of samples, {insts:5d} SASS instrs ({fp} FP64, {mma} DMMA) ends at {tag}")
-    acc = 0; insts = 0; fp = 0; mma = 0; seg += 1
-for r in data:
-    s = r[ix["Source"]]
-    acc += int(r[ix["# Samples"]]); insts += 1
-    if any(x in s for x in ("DFMA", "DMUL", "DADD")): fp += 1
-    if "DMMA" in s: mma += 1
-    if "WARPSYNC" in s: flush("WARPSYNC")
-flush("end")
 # per source function (needs the library that was profiled still built in-tree):
 # samples, executed warp instructions, FP64-pipe warp instructions (DFMA/DMUL/DADD, DMMA)
 if len(sys.argv) > 2:
