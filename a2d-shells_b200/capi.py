@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 STIFFNESS_MATRIX = 0
 GEOMETRIC_STIFFNESS_MATRIX = 1
+MASS_MATRIX = 2
 QUAD4_SHELL = 0
 QUAD4_NONLINEAR_SHELL = 1
 TRANSFORM_NATURAL = 0
@@ -28,6 +29,7 @@ SYMBOLS = [
     "a2ds_last_kernel_ms", "a2ds_region_begin", "a2ds_region_end",
     "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
     "a2ds_add_jacobian_vec_product", "a2ds_add_jacobian_vec_product_dev",
+    "a2ds_set_mass_moments", "a2ds_set_state_rates", "a2ds_assemble_mat_combo",
 ]
 
 _LIB = None
@@ -154,6 +156,21 @@ class Assembler:
         self._chk(self.L.a2ds_set_state(self.ctx, C.c_int(u.shape[0]), _p(u)))
         self._keep = [u]  # the copy is asynchronous
 
+    def set_mass_moments(self, moments):
+        """mass moments per component (TACSShellConstitutive::evalMassMoments)"""
+        m = _f64(moments).reshape(-1, 3)
+        self._chk(self.L.a2ds_set_mass_moments(self.ctx, C.c_int(m.shape[0]), _p(m)))
+
+    def set_state_rates(self, udot=None, uddot=None):
+        """qdot, qddot of TACSAssembler::setVariables; uddot=None removes the inertial term"""
+        n = self.n_nodes
+        ud = None if udot is None else _f64(udot).reshape(-1, 6)
+        udd = None if uddot is None else _f64(uddot).reshape(-1, 6)
+        if udd is not None:
+            n = udd.shape[0]
+        self._chk(self.L.a2ds_set_state_rates(self.ctx, C.c_int(n), _p(ud), _p(udd)))
+        self.synchronize()
+
     def set_state_ptr(self, n_given, host_ptr):
         """state from a raw (pinned) host pointer; asynchronous"""
         self._chk(self.L.a2ds_set_state(self.ctx, C.c_int(n_given), C.c_void_p(host_ptr)))
@@ -273,6 +290,14 @@ class Assembler:
 
     def assembleMatType(self, mat_type, mat):
         self._chk(self.L.a2ds_assemble_mat_type(self.ctx, C.c_int(mat_type), C.c_int(mat)))
+
+    def assembleMatCombo(self, mat_types, scales, mat):
+        """A = sum_i scales[i] * matType(mat_types[i])  (TACSAssembler::assembleMatCombo)"""
+        t = _i32(mat_types)
+        sc = _f64(scales)
+        assert len(t) == len(sc)
+        self._chk(self.L.a2ds_assemble_mat_combo(self.ctx, C.c_int(len(t)), _p(t), _p(sc),
+                                                 C.c_int(mat)))
 
     def assembleAll(self, kmat, gmat, download=True, out_ptr=None):
         """residual + K + G in one pass; out_ptr: raw (pinned) host pointer for the residual"""

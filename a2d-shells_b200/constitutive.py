@@ -34,3 +34,10 @@ def iso_shell_tables(E=72e9, nu=0.33, t=0.010, t_offset=0.0, cte=10e-6, kcorr=5.
     eth = np.zeros(9)
     eth[0] = cte; eth[1] = cte
     return Cs, eth
+
+
+def iso_mass_moments(rho=2718.0, t=0.010, t_offset=0.0):
+    """[m0, m1, m2] of TACSIsoShellConstitutive::evalMassMoments
+    (src/constitutive/TACSIsoShellConstitutive.cpp:120-129)."""
+    return np.array([rho * t, -rho * t * t * t_offset,
+                     rho * t * t * t * (t_offset * t_offset + 1.0 / 12.0)])

@@ -66,7 +66,8 @@ struct KParams {
   const int *Koff;       // 16 block offsets per element (-1: not stored here)
   double *Gval;
   const int *Goff;
-  double alpha;
+  double alpha;          // scale of the tangent (and of the mass matrix in k_mass)
+  double gscale;         // scale of the geometric stiffness (assembleMatCombo; 1 otherwise)
   double res_scale;      // residual entries are multiplied by this before the RED
   double thermal;        // 1: residual of the state;  0: matrix-free product K x (u := x)
   int scratch_bytes;
@@ -96,8 +97,9 @@ static const int MAX_WARPS_PER_BLOCK = 4;
 // 4 * block + entry): 18 REDs per matrix, no divergent tail.  Every slot has a block
 // (a2ds_mat_create refuses patterns with missing blocks), so there is no validity branch;
 // loads are batched so the REDs do not wait on shared memory one by one.
+template <bool SCALED = false>
 __device__ __forceinline__ void scatter_matrix(const double *E, double *vals, int off16,
-                                               int lane) {
+                                               int lane, double scale = 1.0) {
   const unsigned FULL = 0xffffffffu;
   const int r0 = lane / 6, c0 = lane - 6 * r0;   // entry `lane` of a 6x6 block
   const int src0 = r0 * KE_LD + c0;
@@ -110,8 +112,10 @@ __device__ __forceinline__ void scatter_matrix(const double *E, double *vals, in
     for (int k = 0; k < 8; k++) {
       const int b = 8 * half + k;
       v0[k] = E[6 * (b >> 2) * KE_LD + 6 * (b & 3) + src0];
+      if (SCALED) v0[k] *= scale;
     }
-    const double v1 = E[12 * half * KE_LD + src1];   // blocks 8..15 start two block rows down
+    double v1 = E[12 * half * KE_LD + src1];   // blocks 8..15 start two block rows down
+    if (SCALED) v1 *= scale;
     const int offt = __shfl_sync(FULL, off16, 8 * half + tb);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -160,7 +164,7 @@ __device__ __forceinline__ void stage_tiles_full(double *E, const double (&acc)[
 // lane) from the staged Z into a second buffer
 __device__ __forceinline__ void symmetrize_add_geo(const ElemGeom &gm, const ElemWork &wk,
                                                    const double *Pq4, const double *Z, double *G,
-                                                   int lane) {
+                                                   double scale, int lane) {
 #pragma unroll
   for (int pass = 0; pass < 2; pass++) {
     const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
@@ -172,7 +176,7 @@ __device__ __forceinline__ void symmetrize_add_geo(const ElemGeom &gm, const Ele
 #pragma unroll
       for (int j = 0; j < 3; j++)
         G[(r0 + i) * KE_LD + c0 + j] =
-            blk[3 * i + j] + Z[(r0 + i) * KE_LD + c0 + j] + Z[(c0 + j) * KE_LD + r0 + i];
+            scale * (blk[3 * i + j] + Z[(r0 + i) * KE_LD + c0 + j] + Z[(c0 + j) * KE_LD + r0 + i]);
   }
 }
 
@@ -407,13 +411,90 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       if (KMAT) scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
       if (GMAT) {
         if (KMAT) __syncwarp();  // E is reused for G once K has left
-        symmetrize_add_geo(gm, wk, &ws.Pq[j][0][0], ws.E2, ws.E, lane);
+        symmetrize_add_geo(gm, wk, &ws.Pq[j][0][0], ws.E2, ws.E, p.gscale, lane);
         __syncwarp();
         scatter_matrix(ws.E, p.Gval, goffb[j][lane & 15], lane);
       }
       __syncwarp();
     }
     if (!PF) batch_ids(grp + stride, e_cur, nd_cur);
+  }
+}
+
+// ---- mass path (gamma terms of assembleJacobian, TACS_MASS_MATRIX, inertial residual) ----
+// M_e = sum_qp w (m0 N^T N on u, m1 on u-d, m2 on d-d) folded onto the rotations
+// (TACSShellElement.h:410-447, 614-648); RES adds M_e * p.u (p.u = second time derivative
+// of the state) to the residual, MAT adds p.alpha * M_e to the matrix p.Kval.
+// Memory-bound (2.6 kB of matrix per element, a few hundred flops): same batched geometry
+// phases and scatter as k_assemble, no tensor-core part.
+template <bool RES, bool MAT>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 3) k_mass(const KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  const unsigned FULL = 0xffffffffu;
+  const int n_groups = (p.n_list + NB - 1) / NB;
+  for (int grp = blockIdx.x * warps_per_block + warp; grp < n_groups;
+       grp += gridDim.x * warps_per_block) {
+    const int base = grp * NB, cnt = min(NB, p.n_list - base);
+    // lane = 4 j + m: node m of element j
+    const int jl = (lane >> 2) & (NB - 1);
+    int e_l = -1, nd_l = 0;
+    if (jl < cnt) {
+      e_l = p.elem_list ? __ldg(&p.elem_list[base + jl]) : base + jl;
+      nd_l = __ldg(&p.conn[4 * e_l + (lane & 3)]);
+    }
+    if (lane < 4 * NB && e_l >= 0) {
+      const int m = lane & 3;
+#pragma unroll
+      for (int k = 0; k < 3; k++) ws.geo[jl].X[3 * m + k] = p.X[3 * (size_t)nd_l + k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) ws.geo[jl].q[6 * m + k] = RES ? p.u[6 * (size_t)nd_l + k] : 0.0;
+      if (m == 0) ws.raw0.comp[jl] = __ldg(&p.elem_comp[e_l]);
+    }
+    if (MAT) {
+#pragma unroll
+      for (int r = 0; r < NB * 16 / 32; r++) {
+        const int sidx = lane + 32 * r, j = sidx >> 4, k = sidx & 15;
+        const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+        if (ej >= 0) ws.raw0.koff[j][k] = __ldg(&p.Koff[16 * (size_t)ej + k]);
+      }
+    }
+    __syncwarp();
+    if (lane < 4 * NB && jl < cnt) phase_node(p.comps[ws.raw0.comp[jl]], ws.geo[jl], lane & 3);
+    __syncwarp();
+    if (lane < 4 * NB && jl < cnt)
+      phase_qp(p.comps[ws.raw0.comp[jl]], ws.geo[jl], lane & 3, false, false, false, (double *)0);
+    __syncwarp();
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+      const ElemGeom &gm = ws.geo[j];
+      const CompData &c = p.comps[ws.raw0.comp[j]];
+#pragma unroll
+      for (int pass = 0; pass < 2; pass++) {
+        const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+        double blk[9];
+        mass_block(c, gm, pr, pc, blk);
+        const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) ws.E[(r0 + i) * KE_LD + c0 + k] = blk[3 * i + k];
+      }
+      __syncwarp();
+      if (RES) {
+        const int node = __shfl_sync(FULL, nd_l, 4 * j + (lane / 6 & 3));
+        if (lane < 24) {
+          double r = 0.0;
+#pragma unroll
+          for (int k = 0; k < 24; k++) r += ws.E[lane * KE_LD + k] * gm.q[k];
+          atomicAdd(&p.res[6 * (size_t)node + lane % 6], p.res_scale * r);
+        }
+      }
+      if (MAT) scatter_matrix<true>(ws.E, p.Kval, ws.raw0.koff[j][lane & 15], lane, p.alpha);
+      __syncwarp();
+    }
   }
 }
 
@@ -579,7 +660,10 @@ struct a2ds_ctx {
   bool mesh_set = false;
   int *conn = nullptr, *elem_comp = nullptr;
   std::vector<int> h_conn, h_elem_comp, h_class;
+  std::vector<double> h_mom;          // mass moments per component (a2ds_set_mass_moments)
+  std::vector<CompData> h_comps;
   double *X = nullptr, *u = nullptr, *res = nullptr;
+  double *udd = nullptr;  // second time derivative of the state (null until set)
   CompData *comps = nullptr;
   int *bc_nodes = nullptr, *bc_vars = nullptr;
   double *bc_vals = nullptr;
@@ -602,6 +686,8 @@ struct a2ds_ctx {
   float last_ms = 0.f;
   int last_launches = 0;
 };
+
+static int halo_exchange(a2ds_ctx *c, double *vec, bool reverse);
 
 template <class T>
 static int upload(T **dst, const T *src, size_t n, cudaStream_t st) {
@@ -662,6 +748,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
     for (void *p : m.owned) cudaFree(p);
   free_lists(c);
   cudaFree(c->conn); cudaFree(c->elem_comp); cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
+  cudaFree(c->udd);
   cudaFree(c->comps); cudaFree(c->bc_nodes); cudaFree(c->bc_vars); cudaFree(c->bc_vals);
   cudaFree(c->send_nodes); cudaFree(c->recv_nodes); cudaFree(c->send_buf); cudaFree(c->recv_buf);
   if (c->comm) ncclCommDestroy(c->comm);
@@ -692,7 +779,8 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
   else c->h_elem_comp.assign(n_elems, 0);
   if (upload(&c->conn, conn, 4 * (size_t)n_elems, c->stream)) return 1;
   if (upload(&c->elem_comp, c->h_elem_comp.data(), (size_t)n_elems, c->stream)) return 1;
-  cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
+  cudaFree(c->X); cudaFree(c->u); cudaFree(c->res); cudaFree(c->udd);
+  c->udd = nullptr;
   c->X = c->u = c->res = nullptr;
   CU(cudaMalloc((void **)&c->X, 3 * (size_t)n_nodes * sizeof(double)));
   CU(cudaMalloc((void **)&c->u, 6 * (size_t)n_nodes * sizeof(double)));
@@ -726,6 +814,8 @@ extern "C" int a2ds_set_components(a2ds_ctx *c, int n_comp, const double *Cs, co
     memcpy(h[i].Cs, &Cs[22 * i], 22 * sizeof(double));
     memcpy(h[i].eth, &eth[9 * i], 9 * sizeof(double));
     h[i].temperature = temperature ? temperature[i] : 0.0;
+    h[i].mom[0] = h[i].mom[1] = h[i].mom[2] = 0.0;
+    if (i < (int)c->h_mom.size() / 3) memcpy(h[i].mom, &c->h_mom[3 * i], 3 * sizeof(double));
     h[i].model = elem_class ? elem_class[i] : 0;
     if (h[i].model != A2DS_QUAD4_SHELL && h[i].model != A2DS_QUAD4_NONLINEAR_SHELL)
       return fail("a2ds_set_components: unsupported element class (only TACSQuad4Shell and "
@@ -747,8 +837,51 @@ extern "C" int a2ds_set_components(a2ds_ctx *c, int n_comp, const double *Cs, co
     }
   }
   c->n_comp = n_comp;
+  c->h_comps = h;
   if (upload(&c->comps, h.data(), (size_t)n_comp, c->stream)) return 1;
   free_lists(c);
+  return 0;
+}
+
+// mass moments per component, as TACSShellConstitutive::evalMassMoments returns them
+// (TACSIsoShellConstitutive.cpp:120-129); may be called before or after
+// a2ds_set_components
+extern "C" int a2ds_set_mass_moments(a2ds_ctx *c, int n_comp, const double *moments) {
+  CU(cudaSetDevice(c->device));
+  if (n_comp <= 0 || !moments) return fail("a2ds_set_mass_moments: bad arguments");
+  c->h_mom.assign(moments, moments + 3 * (size_t)n_comp);
+  if (!c->h_comps.empty()) {
+    if ((int)c->h_comps.size() != n_comp)
+      return fail("a2ds_set_mass_moments: component count differs from a2ds_set_components");
+    for (int i = 0; i < n_comp; i++) memcpy(c->h_comps[i].mom, &moments[3 * i], 3 * sizeof(double));
+    CU(cudaStreamSynchronize(c->stream));
+    if (upload(&c->comps, c->h_comps.data(), (size_t)n_comp, c->stream)) return 1;
+  }
+  return 0;
+}
+
+// time derivatives of the state (TACSAssembler::setVariables(q, qdot, qddot),
+// src/TACSAssembler.cpp:3825-3857).  Only the second derivative enters this element class
+// (inertial term); udot is accepted for signature parity and ignored.  uddot == NULL
+// removes the inertial term again.
+extern "C" int a2ds_set_state_rates(a2ds_ctx *c, int n_given, const double *udot,
+                                    const double *uddot) {
+  (void)udot;
+  CU(cudaSetDevice(c->device));
+  if (!c->mesh_set) return fail("a2ds_set_state_rates: mesh not set");
+  if (!uddot) {
+    if (c->udd) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->udd); c->udd = nullptr; }
+    return 0;
+  }
+  if (n_given != c->n_nodes && n_given != c->n_owned)
+    return fail("a2ds_set_state_rates: n_given must be n_nodes or n_owned");
+  if (!c->udd) {
+    CU(cudaMalloc((void **)&c->udd, std::max<size_t>(6 * (size_t)c->n_nodes * sizeof(double), 8)));
+    CU(cudaMemsetAsync(c->udd, 0, 6 * (size_t)c->n_nodes * sizeof(double), c->stream));
+  }
+  CU(cudaMemcpyAsync(c->udd, uddot, 6 * (size_t)n_given * sizeof(double), cudaMemcpyHostToDevice,
+                     c->stream));
+  if (c->has_halo && n_given == c->n_owned && halo_exchange(c, c->udd, false)) return 1;
   return 0;
 }
 
@@ -1203,26 +1336,80 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   return 0;
 }
 
-// what: bit 0 residual, bit 1 tangent, bit 2 geometric stiffness
-static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat, double *res_host) {
+// launch the mass kernel over one element list
+template <bool RES, bool MAT>
+static int launch_mass(a2ds_ctx *c, KParams &p) {
+  const size_t per_warp = (offsetof(WarpScratch, E2) + 15) & ~size_t(15);
+  p.scratch_bytes = (int)per_warp;
+  auto kern = k_mass<RES, MAT>;
+  static int per_sm = 0;
+  const int wpb = MAX_WARPS_PER_BLOCK;
+  if (per_sm == 0) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, per_warp * wpb));
+    if (per_sm == 0) return fail("k_mass does not fit on an SM");
+  }
+  const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
+  const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
+  kern<<<grid, wpb * 32, per_warp * wpb, c->stream>>>(p);
+  CU(cudaGetLastError());
+  c->last_launches++;
+  return 0;
+}
+
+// One assembly request.  what: bit 0 residual, bit 1 tangent, bit 2 geometric stiffness,
+// bit 3 mass matrix (into mmat, which may be the tangent matrix: gamma term of the Jacobian).
+struct AsmReq {
+  int what = 0;
+  double alpha = 1.0, gscale = 1.0, mscale = 1.0;
+  int kmat = -1, gmat = -1, mmat = -1;
+  bool zero = true;    // zero the outputs first
+  bool finish = true;  // halo reverse exchange of the residual and boundary conditions
+  double *res_host = nullptr;
+};
+
+static int apply_mat_bcs(a2ds_ctx *c, int mat) {
+  if (!c->n_bc) return 0;
+  MatrixRec &m = c->mats[mat];
+  const int nt = c->n_bc * m.n_blocks;
+  k_mat_bcs<<<(nt + 127) / 128, 128, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars, m.n_blocks,
+                                                     m.blk_dev, m.A);
+  c->last_launches++;
+  return 0;
+}
+
+static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("assemble: mesh or nodes not set");
   if (build_lists(c)) return 1;
-  const bool RES = what & 1, KM = (what & 2) != 0, GM = (what & 4) != 0;
+  const int what = rq.what & 7;
+  const bool RES = rq.what & 1, KM = (rq.what & 2) != 0, GM = (rq.what & 4) != 0,
+             MM = (rq.what & 8) != 0;
+  const int kmat = rq.kmat, gmat = rq.gmat, mmat = rq.mmat;
+  // inertial residual M * uddot (TACSShellElement.h:410-447) once second derivatives are set
+  const bool MRES = RES && c->udd != nullptr;
   if (KM && check_mat(c, kmat)) return 1;
   if (GM && check_mat(c, gmat)) return 1;
-  if (KM && GM && kmat == gmat) return fail("assemble: tangent and geometric matrices must differ");
-  c->last_launches = 0;
-  CU(cudaEventRecord(c->ev0, c->stream));
-  if (RES) CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)c->n_nodes * sizeof(double), c->stream));
-  if (KM) CU(cudaMemsetAsync(c->mats[kmat].A, 0, c->mats[kmat].total * 36 * sizeof(double), c->stream));
-  if (GM) CU(cudaMemsetAsync(c->mats[gmat].A, 0, c->mats[gmat].total * 36 * sizeof(double), c->stream));
-  c->last_launches += (RES ? 1 : 0) + (KM ? 1 : 0) + (GM ? 1 : 0);
+  if (MM && check_mat(c, mmat)) return 1;
+  if (KM && GM && kmat == gmat && what == 7)
+    return fail("assemble: tangent and geometric matrices must differ");
+  if (rq.zero) {
+    c->last_launches = 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    if (RES) CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)c->n_nodes * sizeof(double), c->stream));
+    if (KM) CU(cudaMemsetAsync(c->mats[kmat].A, 0, c->mats[kmat].total * 36 * sizeof(double), c->stream));
+    if (GM) CU(cudaMemsetAsync(c->mats[gmat].A, 0, c->mats[gmat].total * 36 * sizeof(double), c->stream));
+    if (MM && !(KM && mmat == kmat))
+      CU(cudaMemsetAsync(c->mats[mmat].A, 0, c->mats[mmat].total * 36 * sizeof(double), c->stream));
+    c->last_launches += (RES ? 1 : 0) + (KM ? 1 : 0) + (GM ? 1 : 0) + (MM && !(KM && mmat == kmat) ? 1 : 0);
+  }
 
   KParams p;
   memset(&p, 0, sizeof(p));
   p.conn = c->conn; p.elem_comp = c->elem_comp; p.comps = c->comps;
-  p.X = c->X; p.u = c->u; p.res = c->res; p.alpha = alpha;
+  p.X = c->X; p.u = c->u; p.res = c->res; p.alpha = rq.alpha; p.gscale = rq.gscale;
   p.res_scale = 1.0; p.thermal = 1.0;
   if (KM) { p.Kval = c->mats[kmat].A; p.Koff = c->mats[kmat].off; }
   if (GM) { p.Gval = c->mats[gmat].A; p.Goff = c->mats[gmat].off; }
@@ -1236,6 +1423,7 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
       int rc = 0;
       if (cls == 0) {
         switch (what) {
+          case 0: break;
           case 1: rc = launch_one<true, false, false, false>(c, p); break;
           case 2: rc = launch_one<false, true, false, false>(c, p); break;
           case 3: rc = launch_one<true, true, false, false>(c, p); break;
@@ -1249,6 +1437,7 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
         // reference, TACSShellElement.h:705-751) is the same linear-in-state term as
         // for the linear model and is evaluated with the linear-model kernel.
         switch (what) {
+          case 0: break;
           case 1: rc = launch_one<true, false, false, true>(c, p); break;
           case 2: rc = launch_one<false, true, false, true>(c, p); break;
           case 3: rc = launch_one<true, true, false, true>(c, p); break;
@@ -1261,9 +1450,20 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
         }
       }
       if (rc) return rc;
+      if (MM || MRES) {
+        // mass path: same element lists (and colours), both element classes alike
+        KParams pm = p;
+        pm.u = c->udd; pm.alpha = rq.mscale;
+        if (MM) { pm.Kval = c->mats[mmat].A; pm.Koff = c->mats[mmat].off; }
+        if (MM && MRES) rc = launch_mass<true, true>(c, pm);
+        else if (MM) rc = launch_mass<false, true>(c, pm);
+        else rc = launch_mass<true, false>(c, pm);
+        if (rc) return rc;
+      }
     }
   }
   CU(cudaEventRecord(c->evk1, c->stream));
+  if (!rq.finish) return 0;
   // ghost residual contributions -> owners (TACSBVec::beginSetValues/endSetValues, ADD)
   if (RES && halo_exchange(c, c->res, true)) return 1;
   if (RES && c->n_bc) {
@@ -1271,43 +1471,68 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
                                                                 c->bc_vals, c->u, c->res, c->n_owned);
     c->last_launches++;
   }
-  for (int pass = 0; pass < 2; pass++) {
-    const bool on = pass == 0 ? KM : GM;
-    if (!on || !c->n_bc) continue;
-    MatrixRec &m = c->mats[pass == 0 ? kmat : gmat];
-    const int nt = c->n_bc * m.n_blocks;
-    k_mat_bcs<<<(nt + 127) / 128, 128, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars, m.n_blocks,
-                                                       m.blk_dev, m.A);
-    c->last_launches++;
-  }
+  if (KM && apply_mat_bcs(c, kmat)) return 1;
+  if (GM && !(KM && gmat == kmat) && apply_mat_bcs(c, gmat)) return 1;
+  if (MM && !(KM && mmat == kmat) && !(GM && mmat == gmat) && apply_mat_bcs(c, mmat)) return 1;
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, c->stream));
-  if (res_host) {
-    CU(cudaMemcpyAsync(res_host, c->res, 6 * (size_t)c->n_owned * sizeof(double),
+  if (rq.res_host) {
+    CU(cudaMemcpyAsync(rq.res_host, c->res, 6 * (size_t)c->n_owned * sizeof(double),
                        cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
   return 0;
 }
 
+static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat, double *res_host) {
+  AsmReq rq;
+  rq.what = what; rq.alpha = alpha; rq.kmat = kmat; rq.gmat = gmat; rq.res_host = res_host;
+  return run_assembly(c, rq);
+}
+
 extern "C" int a2ds_assemble_res(a2ds_ctx *c, double *res) {
   return run_assembly(c, 1, 1.0, -1, -1, res);
 }
 
+// beta multiplies dR/d(udot): this element class has no velocity dependent term (the
+// reference passes beta on to the director, where TACSLinearizedRotation ignores it,
+// TACSDirector.h:369-486), so any beta is accepted and has no effect.
 extern "C" int a2ds_assemble_jacobian(a2ds_ctx *c, double alpha, double beta, double gamma,
                                       double *res, int mat) {
-  if (beta != 0.0 || gamma != 0.0)
-    return fail("a2ds_assemble_jacobian: only the static path (beta = gamma = 0) is implemented");
-  int rc = run_assembly(c, 3, alpha, mat, -1, res);
-  if (rc) return rc;
-  if (!res) return 0;
-  return 0;
+  (void)beta;
+  AsmReq rq;
+  rq.what = 3 | (gamma != 0.0 ? 8 : 0);
+  rq.alpha = alpha; rq.mscale = gamma; rq.kmat = mat; rq.mmat = mat; rq.res_host = res;
+  return run_assembly(c, rq);
 }
 
 extern "C" int a2ds_assemble_mat_type(a2ds_ctx *c, int mat_type, int mat) {
   if (mat_type == A2DS_STIFFNESS_MATRIX) return run_assembly(c, 2, 1.0, mat, -1, nullptr);
   if (mat_type == A2DS_GEOMETRIC_STIFFNESS_MATRIX) return run_assembly(c, 4, 1.0, -1, mat, nullptr);
-  return fail("a2ds_assemble_mat_type: only stiffness and geometric stiffness are implemented");
+  if (mat_type == A2DS_MASS_MATRIX) {
+    AsmReq rq;
+    rq.what = 8; rq.mmat = mat;
+    return run_assembly(c, rq);
+  }
+  return fail("a2ds_assemble_mat_type: unknown matrix type");
+}
+
+// TACSAssembler::assembleMatCombo (src/TACSAssembler.cpp:4264-4318): A = sum_i scale[i] *
+// matType[i], boundary conditions applied once at the end.
+extern "C" int a2ds_assemble_mat_combo(a2ds_ctx *c, int n, const int *mat_types,
+                                       const double *scales, int mat) {
+  if (n <= 0) return fail("a2ds_assemble_mat_combo: need at least one matrix type");
+  if (check_mat(c, mat)) return 1;
+  for (int i = 0; i < n; i++) {
+    AsmReq rq;
+    rq.zero = (i == 0); rq.finish = (i == n - 1);
+    if (mat_types[i] == A2DS_STIFFNESS_MATRIX) { rq.what = 2; rq.kmat = mat; rq.alpha = scales[i]; }
+    else if (mat_types[i] == A2DS_GEOMETRIC_STIFFNESS_MATRIX) { rq.what = 4; rq.gmat = mat; rq.gscale = scales[i]; }
+    else if (mat_types[i] == A2DS_MASS_MATRIX) { rq.what = 8; rq.mmat = mat; rq.mscale = scales[i]; }
+    else return fail("a2ds_assemble_mat_combo: unknown matrix type");
+    if (run_assembly(c, rq)) return 1;
+  }
+  return 0;
 }
 
 extern "C" int a2ds_assemble_all(a2ds_ctx *c, double *res, int kmat, int gmat) {

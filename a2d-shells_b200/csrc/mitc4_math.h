@@ -65,6 +65,7 @@ struct CompData {
   double eth[9];       // thermal strain per unit temperature
   double temperature;  // TACSShellElement::temperature
   double axis[3];      // normalised reference axis (transform == 1)
+  double mom[3];       // mass moments (TACSShellConstitutive::evalMassMoments)
   int model;           // 0 linear strain model, 1 nonlinear
   int transform;       // 0 natural, 1 reference axis
   int coupled;         // 0: the B block of Cs is identically zero
@@ -816,6 +817,40 @@ A2DS_HD void sum_tying_stress(ElemWork &s, int t) {
   s.sigsum[t] = s.sig[0][t] + s.sig[1][t] + s.sig[2][t] + s.sig[3][t];
 }
 
+// Fold a 3x3 block given in terms of the generalised nodes (u_m, d_m) onto the rotation
+// DOFs of the linearised rotation d = theta x fn:
+//   rows of a director node:    skew(fn_m) * blk
+//   columns of a director node: blk * skew(fn_mm)^T
+// (TACSLinearizedRotation::addDirectorJacobian, TACSDirector.h:369-486)
+A2DS_HD void fold_director_block(const ElemGeom &gm, bool pd, int m, bool ppd, int mm,
+                                 double blk[9]) {
+  if (pd) {  // rows: skew(fn_m) * blk
+    const double *f = &gm.fn[3 * m];
+    double t[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      t[j] = f[1] * blk[6 + j] - f[2] * blk[3 + j];
+      t[3 + j] = f[2] * blk[j] - f[0] * blk[6 + j];
+      t[6 + j] = f[0] * blk[3 + j] - f[1] * blk[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) blk[i] = t[i];
+  }
+  if (ppd) {  // columns: blk * skew(fn_mm)^T, i.e. row_i -> fn x row_i
+    const double *f = &gm.fn[3 * mm];
+    double t[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double *r = &blk[3 * i];
+      t[3 * i] = f[1] * r[2] - f[2] * r[1];
+      t[3 * i + 1] = f[2] * r[0] - f[0] * r[2];
+      t[3 * i + 2] = f[0] * r[1] - f[1] * r[0];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) blk[i] = t[i];
+  }
+}
+
 // ---- geometric stiffness: one 3x3 block for the generalised node pair (p, pp) ---
 // p, pp in 0..7: 0..3 displacement of node p, 4..7 director of node p-4.
 // Returns the block already folded onto the rotation DOFs:
@@ -855,31 +890,28 @@ A2DS_HD void geo_block(const ElemGeom &gm, const ElemWork &s, const double *Pq4,
     blk[3] += mq * P[1]; blk[4] += mq * P[3]; blk[5] += mq * P[4];
     blk[6] += mq * P[2]; blk[7] += mq * P[4]; blk[8] += mq * P[5];
   }
-  if (pd) {  // rows: skew(fn_m) * blk
-    const double *f = &gm.fn[3 * m];
-    double t[9];
+  fold_director_block(gm, pd, m, ppd, mm, blk);
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-      t[j] = f[1] * blk[6 + j] - f[2] * blk[3 + j];
-      t[3 + j] = f[2] * blk[j] - f[0] * blk[6 + j];
-      t[6 + j] = f[0] * blk[3 + j] - f[1] * blk[j];
-    }
+  for (int i = 0; i < 9; i++) out[i] = blk[i];
+}
+
+// ---- mass matrix: one 3x3 block for the generalised node pair (p, pp) -----------
+// Kinetic energy density 1/2 (m0 u'.u' + 2 m1 u'.d' + m2 d'.d') with u and d interpolated
+// bilinearly (TACSShellElement.h:614-648): the block is (sum_qp w N_m N_mm) m_k I with
+// k = number of directors in the pair, folded onto the rotations like the geometric blocks.
+A2DS_HD void mass_block(const CompData &c, const ElemGeom &gm, int p, int pp, double out[9]) {
+  const int m = p & 3, mm = pp & 3;
+  const bool pd = p >= 4, ppd = pp >= 4;
+  double cc = 0.0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) blk[i] = t[i];
+  for (int qp = 0; qp < 4; qp++) {
+    double na[2], nb[2];
+    qp_shape(qp, na, nb);
+    cc += gm.qp[qp].w * (na[m % 2] * nb[m / 2]) * (na[mm % 2] * nb[mm / 2]);
   }
-  if (ppd) {  // columns: blk * skew(fn_mm)^T, i.e. row_i -> fn x row_i
-    const double *f = &gm.fn[3 * mm];
-    double t[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      const double *r = &blk[3 * i];
-      t[3 * i] = f[1] * r[2] - f[2] * r[1];
-      t[3 * i + 1] = f[2] * r[0] - f[0] * r[2];
-      t[3 * i + 2] = f[0] * r[1] - f[1] * r[0];
-    }
-#pragma unroll
-    for (int i = 0; i < 9; i++) blk[i] = t[i];
-  }
+  cc *= c.mom[(pd ? 1 : 0) + (ppd ? 1 : 0)];
+  double blk[9] = {cc, 0.0, 0.0, 0.0, cc, 0.0, 0.0, 0.0, cc};
+  fold_director_block(gm, pd, m, ppd, mm, blk);
 #pragma unroll
   for (int i = 0; i < 9; i++) out[i] = blk[i];
 }

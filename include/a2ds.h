@@ -37,6 +37,7 @@ typedef struct a2ds_ctx a2ds_ctx;
 /* ElementMatrixType, src/elements/TACSElementTypes.h:101-107 */
 #define A2DS_STIFFNESS_MATRIX 0
 #define A2DS_GEOMETRIC_STIFFNESS_MATRIX 1
+#define A2DS_MASS_MATRIX 2
 
 /* element class of a component: TACSQuad4Shell / TACSQuad4NonlinearShell
    (src/elements/shell/TACSShellElementDefs.h:12-14, 27-29) */
@@ -81,11 +82,22 @@ int a2ds_set_components(a2ds_ctx *ctx, int n_comp, const double *Cs, const doubl
                         const double *temperature, const int *elem_class, int transform,
                         const double *ref_axis);
 
+/* Mass moments of every component, moments[3 c + k], as the host constitutive object
+ * returns them (TACSShellConstitutive::evalMassMoments,
+ * src/constitutive/TACSIsoShellConstitutive.cpp:120-129).  Only the mass path needs them;
+ * may be called before or after a2ds_set_components (default: zero). */
+int a2ds_set_mass_moments(a2ds_ctx *ctx, int n_comp, const double *moments);
+
 /* TACSAssembler::setVariables (src/TACSAssembler.cpp:3825-3857): u[6 n + k] for all
  * local nodes when n_given == n_nodes, or for the owned nodes only when
  * n_given == n_owned (ghost values then come from a2ds_halo_forward). */
 int a2ds_set_state(a2ds_ctx *ctx, int n_given, const double *u);
 int a2ds_set_state_dev(a2ds_ctx *ctx, int n_given, const double *u_dev);
+/* the qdot / qddot arguments of TACSAssembler::setVariables.  Only uddot enters this element
+ * class (inertial term M * uddot of the residual, TACSShellElement.h:410-447); udot is
+ * accepted for signature parity.  uddot == NULL removes the inertial term again.  With a
+ * halo and n_given == n_owned the ghost values are exchanged here. */
+int a2ds_set_state_rates(a2ds_ctx *ctx, int n_given, const double *udot, const double *uddot);
 
 /* TACSBcMap (src/bpmat/KSM.h:43-75): bc_nodes[b] local node, bc_vars[b] bit mask of
  * constrained DOFs, bc_vals[6 b + k] prescribed values */
@@ -147,13 +159,18 @@ int a2ds_mat_mult(a2ds_ctx *ctx, int mat, int block, int ncols, const double *x,
  * owned nodes, boundary rows r = u - ubar.  res may be NULL (result stays on device,
  * see a2ds_res_dev). */
 int a2ds_assemble_res(a2ds_ctx *ctx, double *res);
-/* TACSAssembler::assembleJacobian (src/TACSAssembler.cpp:4084-4174) with
- * beta = gamma = 0 (static path): zero res and A, add alpha * dR/du, apply BCs to
- * both.  res may be NULL. */
+/* TACSAssembler::assembleJacobian (src/TACSAssembler.cpp:4084-4174): zero res and A, add
+ * the residual and alpha * dR/du + gamma * dR/d(uddot) (the mass matrix,
+ * src/elements/shell/TACSShellElement.h:614-648), apply BCs to both.  beta is accepted and
+ * has no effect: this element class has no velocity dependent term.  res may be NULL. */
 int a2ds_assemble_jacobian(a2ds_ctx *ctx, double alpha, double beta, double gamma,
                            double *res, int mat);
-/* TACSAssembler::assembleMatType (src/TACSAssembler.cpp:4186-4249) */
+/* TACSAssembler::assembleMatType (src/TACSAssembler.cpp:4186-4249), A2DS_*_MATRIX */
 int a2ds_assemble_mat_type(a2ds_ctx *ctx, int mat_type, int mat);
+/* TACSAssembler::assembleMatCombo (src/TACSAssembler.cpp:4264-4318):
+ * A = sum_i scales[i] * matType(mat_types[i]), BCs applied once at the end */
+int a2ds_assemble_mat_combo(a2ds_ctx *ctx, int n, const int *mat_types, const double *scales,
+                            int mat);
 /* residual + tangent + geometric stiffness in one pass over the elements (what the
  * buckling flow asks for in three calls, src/TACSBuckling.cpp:239-266) */
 int a2ds_assemble_all(a2ds_ctx *ctx, double *res, int kmat, int gmat);

@@ -70,6 +70,16 @@ def jacobian(comp, X, q, alpha=1.0):
     return r, m.reshape(24, 24)
 
 
+def jacobian_dyn(comp, X, q, qdd, alpha=1.0, gamma=0.0):
+    """res (static + M qdd) and alpha K + gamma M"""
+    r = np.zeros(24); m = np.zeros(576)
+    lib().oracle_jacobian_dyn(C.byref(comp), C.c_double(alpha), C.c_double(gamma),
+                              _p(np.ascontiguousarray(X, dtype=np.float64)),
+                              _p(np.ascontiguousarray(q, dtype=np.float64)),
+                              _p(np.ascontiguousarray(qdd, dtype=np.float64)), _p(r), _p(m))
+    return r, m.reshape(24, 24)
+
+
 def mat_type(comp, type_, X, q):
     m = np.zeros(576)
     lib().oracle_mat_type(C.byref(comp), C.c_int(type_),
@@ -88,8 +98,9 @@ def pattern(n_nodes, conn):
 
 
 def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_vars=None,
-             bc_vals=None, alpha=1.0):
-    """op 0 res, 1 jacobian, 2 K, 3 G -> (res[n,6] or None, A[nnz,6,6] or None)."""
+             bc_vals=None, alpha=1.0, gamma=0.0, udd=None):
+    """op 0 res, 1 jacobian (alpha K + gamma M), 2 K, 3 G, 4 M -> (res[n,6] or None,
+    A[nnz,6,6] or None); udd: second time derivatives (inertial term of the residual)."""
     conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
     X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3)
     u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 6)
@@ -102,9 +113,11 @@ def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_var
     bx = np.ascontiguousarray(bc_vals if nb else np.zeros(0), dtype=np.float64)
     res = np.zeros((n, 6)) if op <= 1 else None
     A = np.zeros((len(cols), 6, 6)) if op >= 1 else None
-    miss = lib().oracle_assemble(C.c_int(op), C.c_double(alpha), C.c_int(n), C.c_int(conn.shape[0]),
-                                 _p(conn), _p(ec), arr, _p(X), _p(u), C.c_int(nb), _p(bn), _p(bv),
-                                 _p(bx), _p(np.ascontiguousarray(rowp, dtype=np.int32)),
-                                 _p(np.ascontiguousarray(cols, dtype=np.int32)), _p(res), _p(A))
+    udd = None if udd is None else np.ascontiguousarray(udd, dtype=np.float64).reshape(-1, 6)
+    miss = lib().oracle_assemble_dyn(C.c_int(op), C.c_double(alpha), C.c_double(gamma), C.c_int(n),
+                                     C.c_int(conn.shape[0]), _p(conn), _p(ec), arr, _p(X), _p(u),
+                                     _p(udd), C.c_int(nb), _p(bn), _p(bv), _p(bx),
+                                     _p(np.ascontiguousarray(rowp, dtype=np.int32)),
+                                     _p(np.ascontiguousarray(cols, dtype=np.int32)), _p(res), _p(A))
     assert miss == 0, "element block missing from the pattern"
     return res, A

@@ -540,10 +540,102 @@ void oracle_jacobian(const oracle_comp_t *c, double alpha, const double X[12],
 }
 
 /* TACSShellElement::getMatType, TACSShellElement.h:675-771 */
+/* ---- inertial terms: TACSShellElement::addResidual :410-447, addJacobian :614-648,
+   TACSLinearizedRotation::computeDirectorRates (TACSDirector.h:232-262),
+   addDirectorResidual (:349-367), addDirectorJacobian (:369-486).
+   res (may be NULL) += M qdd;  mat (may be NULL) += gamma * M. --------------------------- */
+static void skew_mat(const double a[3], const double B[9], double D[9]) { /* a^x B, TACSElementAlgebra.h:1331 */
+  for (int j = 0; j < 3; j++) {
+    D[j] = a[1] * B[6 + j] - a[2] * B[3 + j];
+    D[3 + j] = a[2] * B[j] - a[0] * B[6 + j];
+    D[6 + j] = a[0] * B[3 + j] - a[1] * B[j];
+  }
+}
+static void skew_mat_skew(const double a[3], const double B[9], const double c[3], double D[9]) {
+  /* a^x B c^x, TACSElementAlgebra.h:1362 */
+  double t[9];
+  skew_mat(a, B, t);
+  for (int i = 0; i < 3; i++) {
+    D[3 * i] = c[2] * t[3 * i + 1] - c[1] * t[3 * i + 2];
+    D[3 * i + 1] = c[0] * t[3 * i + 2] - c[2] * t[3 * i];
+    D[3 * i + 2] = c[1] * t[3 * i] - c[0] * t[3 * i + 1];
+  }
+}
+
+static void inertia(const oracle_comp_t *c, double gamma, const double X[12],
+                    const double qdd[24], double res[24], double mat[576]) {
+  geo_t g;
+  geometry(c, X, &g);
+  double dddot[12], dd[12], d2Tdotd[144], d2Tdotu[144];
+  static const double zero24[24] = {0};
+  if (!qdd) qdd = zero24;
+  for (int i = 0; i < 4; i++) cross3(&qdd[6 * i + 3], &g.fn[3 * i], &dddot[3 * i]);
+  memset(dd, 0, sizeof(dd));
+  memset(d2Tdotd, 0, sizeof(d2Tdotd));
+  memset(d2Tdotu, 0, sizeof(d2Tdotu));
+  for (int q = 0; q < 4; q++) {
+    const shape_t *sh = &g.sq[q];
+    const double det = g.detXd[q];
+    double u0dd[3], d0dd[3];
+    interp3(sh, qdd, 6, u0dd);
+    interp3(sh, dddot, 3, d0dd);
+    for (int i = 0; i < 4; i++)
+      for (int k = 0; k < 3; k++) {
+        if (res) res[6 * i + k] += sh->N[i] * det * (c->mom[0] * u0dd[k] + c->mom[1] * d0dd[k]);
+        dd[3 * i + k] += sh->N[i] * det * (c->mom[1] * u0dd[k] + c->mom[2] * d0dd[k]);
+      }
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) {
+        const double nn = sh->N[i] * sh->N[j];
+        for (int k = 0; k < 3; k++) {
+          if (mat) mat[24 * (6 * i + k) + 6 * j + k] += gamma * det * c->mom[0] * nn;
+          d2Tdotd[12 * (3 * i + k) + 3 * j + k] += det * c->mom[2] * nn;
+          d2Tdotu[12 * (3 * i + k) + 3 * j + k] += det * c->mom[1] * nn;
+        }
+      }
+  }
+  for (int i = 0; i < 4; i++) {
+    if (res) { /* crossProductAdd(1.0, t, dd, r) */
+      double r[3];
+      cross3(&g.fn[3 * i], &dd[3 * i], r);
+      for (int k = 0; k < 3; k++) res[6 * i + 3 + k] += r[k];
+    }
+    if (!mat) continue;
+    for (int j = 0; j < 4; j++) {
+      double d[9], tmp[9];
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) d[3 * a + b] = gamma * d2Tdotd[12 * (3 * i + a) + 3 * j + b];
+      skew_mat_skew(&g.fn[3 * i], d, &g.fn[3 * j], tmp);
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) mat[24 * (6 * i + 3 + a) + 6 * j + 3 + b] -= tmp[3 * a + b];
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) d[3 * a + b] = gamma * d2Tdotu[12 * (3 * i + a) + 3 * j + b];
+      skew_mat(&g.fn[3 * i], d, tmp);
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+          mat[24 * (6 * i + 3 + a) + 6 * j + b] += tmp[3 * a + b];
+          mat[24 * (6 * j + b) + 6 * i + 3 + a] += tmp[3 * a + b];
+        }
+    }
+  }
+}
+
+void oracle_jacobian_dyn(const oracle_comp_t *c, double alpha, double gamma, const double X[12],
+                         const double q[24], const double qdd[24], double res[24],
+                         double mat[576]) {
+  oracle_jacobian(c, alpha, X, q, res, mat);
+  inertia(c, gamma, X, qdd, res, mat);
+}
+
 void oracle_mat_type(const oracle_comp_t *c, int type, const double X[12],
                      const double q[24], double mat[576]) {
   if (type == 0) {
     res_and_tangent(c, 1.0, c->temperature, X, q, NULL, mat);
+    return;
+  }
+  if (type == 2) { /* TACS_MASS_MATRIX: alpha = beta = 0, gamma = 1, :700-705, :769 */
+    memset(mat, 0, 576 * sizeof(double));
+    inertia(c, 1.0, X, NULL, NULL, mat);
     return;
   }
   /* geometric stiffness: central difference of the nonlinear twin's tangent
@@ -631,6 +723,15 @@ int oracle_assemble(int op, double alpha, int n_nodes, int n_elems, const int *c
                     const double *u, int n_bc, const int *bc_nodes, const int *bc_vars,
                     const double *bc_vals, const int *rowp, const int *cols, double *res,
                     double *A) {
+  return oracle_assemble_dyn(op, alpha, 0.0, n_nodes, n_elems, conn, elem_comp, comps, X, u, NULL,
+                             n_bc, bc_nodes, bc_vars, bc_vals, rowp, cols, res, A);
+}
+
+int oracle_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_elems,
+                        const int *conn, const int *elem_comp, const oracle_comp_t *comps,
+                        const double *X, const double *u, const double *udd, int n_bc,
+                        const int *bc_nodes, const int *bc_vars, const double *bc_vals,
+                        const int *rowp, const int *cols, double *res, double *A) {
   int missing = 0;
   if (res) memset(res, 0, sizeof(double) * 6 * (size_t)n_nodes);
   if (A) memset(A, 0, sizeof(double) * 36 * (size_t)rowp[n_nodes]);
@@ -638,13 +739,15 @@ int oracle_assemble(int op, double alpha, int n_nodes, int n_elems, const int *c
   for (int e = 0; e < n_elems; e++) {
     const int *nd = &conn[4 * e];
     const oracle_comp_t *c = &comps[elem_comp ? elem_comp[e] : 0];
-    double Xe[12], qe[24], re[24], me[576];
+    double Xe[12], qe[24], qdde[24], re[24], me[576];
     for (int i = 0; i < 4; i++) {
       memcpy(&Xe[3 * i], &X[3 * (size_t)nd[i]], 3 * sizeof(double));
       memcpy(&qe[6 * i], &u[6 * (size_t)nd[i]], 6 * sizeof(double));
+      if (udd) memcpy(&qdde[6 * i], &udd[6 * (size_t)nd[i]], 6 * sizeof(double));
+      else memset(&qdde[6 * i], 0, 6 * sizeof(double));
     }
-    if (op == 0) oracle_residual(c, Xe, qe, re);
-    else if (op == 1) oracle_jacobian(c, alpha, Xe, qe, re, me);
+    if (op == 0) { oracle_residual(c, Xe, qe, re); if (udd) inertia(c, 0.0, Xe, qdde, re, NULL); }
+    else if (op == 1) oracle_jacobian_dyn(c, alpha, gamma, Xe, qe, qdde, re, me);
     else oracle_mat_type(c, op - 2, Xe, qe, me);
     if (res && op <= 1)
       for (int i = 0; i < 4; i++)

@@ -26,7 +26,7 @@ typedef struct {
   double axis[3];     /* normalised reference axis (transform == 1) */
   double Cs[22];      /* A[6] B[6] D[6] As[3] drill  (TACSShellConstitutive.h:34) */
   double eth[9];      /* thermal strain per unit temperature */
-  double mom[3];      /* mass moments (unused by the static path) */
+  double mom[3];      /* mass moments (TACSShellConstitutive::evalMassMoments) */
   double temperature; /* TACSShellElement::temperature (TACSShellElement.h:35) */
 } oracle_comp_t;
 
@@ -43,7 +43,13 @@ void oracle_residual(const oracle_comp_t *c, const double X[12], const double q[
 void oracle_jacobian(const oracle_comp_t *c, double alpha, const double X[12],
                      const double q[24], double res[24], double mat[576]);
 
-/* TACSShellElement::getMatType: type 0 = stiffness, 1 = geometric stiffness */
+/* the same with the inertial terms: res += M qdd, mat += gamma * M
+   (TACSShellElement.h:410-447, 614-648; qdd may be NULL = zero) */
+void oracle_jacobian_dyn(const oracle_comp_t *c, double alpha, double gamma, const double X[12],
+                         const double q[24], const double qdd[24], double res[24],
+                         double mat[576]);
+
+/* TACSShellElement::getMatType: type 0 = stiffness, 1 = geometric stiffness, 2 = mass */
 void oracle_mat_type(const oracle_comp_t *c, int type, const double X[12],
                      const double q[24], double mat[576]);
 
@@ -55,7 +61,7 @@ int oracle_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int *co
 /*
  * Assembly over a mesh (TACSAssembler::assembleRes / assembleJacobian /
  * assembleMatType, single rank): op 0 = residual, 1 = Jacobian (res + alpha*K),
- * 2 = matType(K), 3 = matType(G).  res[6*n_nodes] and A[36*nnz] are zeroed first
+ * 2 = matType(K), 3 = matType(G), 4 = matType(M).  res[6*n_nodes] and A[36*nnz] are zeroed first
  * (may be NULL when the op does not produce them); boundary conditions are
  * applied exactly as the reference does (TACSBVec::applyBCs, BCSRMat::zeroRow).
  * Returns 0, or the number of element blocks not found in the pattern.
@@ -65,6 +71,14 @@ int oracle_assemble(int op, double alpha, int n_nodes, int n_elems, const int *c
                     const double *u, int n_bc, const int *bc_nodes, const int *bc_vars,
                     const double *bc_vals, const int *rowp, const int *cols, double *res,
                     double *A);
+
+/* the same with second time derivatives udd (may be NULL) and the gamma term of the
+   Jacobian (op 1): res includes M udd, A = alpha K + gamma M */
+int oracle_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_elems,
+                        const int *conn, const int *elem_comp, const oracle_comp_t *comps,
+                        const double *X, const double *u, const double *udd, int n_bc,
+                        const int *bc_nodes, const int *bc_vars, const double *bc_vals,
+                        const int *rowp, const int *cols, double *res, double *A);
 
 #ifdef __cplusplus
 }

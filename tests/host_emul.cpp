@@ -83,3 +83,27 @@ extern "C" int emul_element(const double *Cs, const double *eth, double temperat
     }
   return 0;
 }
+
+// mass matrix of one element through the kernel's mass_block (k_mass in a2ds.cu)
+extern "C" int emul_mass(const double *mom, int transform, const double *axis, const double *X,
+                         double *M) {
+  CompData c;
+  memset(&c, 0, sizeof(c));
+  memcpy(c.mom, mom, sizeof(c.mom));
+  c.transform = transform;
+  memcpy(c.axis, axis, sizeof(c.axis));
+  static ElemGeom s;
+  memset(&s, 0, sizeof(s));
+  memcpy(s.X, X, sizeof(s.X));
+  for (int m = 0; m < 4; m++) phase_node(c, s, m);
+  for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, false, false, false, (double *)0);
+  for (int p = 0; p < 8; p++)
+    for (int pp = 0; pp < 8; pp++) {
+      double blk[9];
+      mass_block(c, s, p, pp, blk);
+      int r0 = 6 * (p & 3) + (p >= 4 ? 3 : 0), c0 = 6 * (pp & 3) + (pp >= 4 ? 3 : 0);
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) M[24 * (r0 + i) + c0 + j] = blk[3 * i + j];
+    }
+  return 0;
+}

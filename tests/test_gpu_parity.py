@@ -337,10 +337,13 @@ def test_empty_and_tiny_meshes(a2ds):
     r = asm.assembleAll(k, g)
     K = asm.mat_values(k)
     assert np.isfinite(r).all() and np.isfinite(K).all() and np.abs(K).max() > 0
-    with pytest.raises(a2ds.A2dsError):
-        asm.assembleJacobian(1.0, 0.5, 0.0, k)   # inertial terms are not on the device path
+    # beta has no term in this element class: accepted, no effect
+    r2 = asm.assembleJacobian(1.0, 0.5, 0.0, k)
+    assert np.array_equal(r2, asm.assembleJacobian(1.0, 0.0, 0.0, k))
     with pytest.raises(a2ds.A2dsError):
         asm.assembleAll(k, k)
+    with pytest.raises(a2ds.A2dsError):
+        asm.assembleMatType(7, k)
     asm.close()
 
 
@@ -449,4 +452,93 @@ def test_properties_at_baseline_size(a2ds):
     asm.set_state(3.0 * u)
     asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, g)
     assert relmax(asm.mat_mult(g, y), 3.0 * gy) < 1e-11
+    asm.close()
+
+
+def _dynamic_case(a2ds, orc):
+    """curved panel, 7 components with their own mass moments (m1 != 0), both element
+    classes, boundary conditions; returns the assembler and the oracle arguments"""
+    conn, X, bcn = a2ds.meshes.cylinder(21, 7)
+    n = len(X); ne = len(conn)
+    rng = np.random.default_rng(11)
+    ncomp = 7
+    Cs = np.zeros((ncomp, 22)); eth = np.zeros((ncomp, 9)); mom = np.zeros((ncomp, 3))
+    for c in range(ncomp):
+        t = rng.uniform(0.005, 0.02); off = rng.uniform(-0.4, 0.4); rho = rng.uniform(1e3, 8e3)
+        Cs[c], eth[c] = a2ds.iso_shell_tables(t=t, t_offset=off)
+        mom[c] = a2ds.iso_mass_moments(rho, t, off)
+    cls = (rng.uniform(size=ncomp) < 0.4).astype(np.int32)
+    elem_comp = rng.integers(0, ncomp, ne).astype(np.int32)
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-4)
+    udd = a2ds.meshes.seeded_state(np.arange(n) + 77777, 1.0)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n, elem_comp=elem_comp); asm.set_nodes(X)
+    asm.set_components(Cs, eth, elem_class=cls)
+    asm.set_mass_moments(mom)
+    asm.set_bcs(bcn, 63); asm.set_state(u)
+    comps = [orc.make_comp(int(cls[c]), Cs[c], eth[c], mom[c]) for c in range(ncomp)]
+    mat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(mat)
+    bc_vars = np.full(len(bcn), 63, dtype=np.int32); bc_vals = np.zeros((len(bcn), 6))
+    oargs = (conn, elem_comp, comps, X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    return asm, mat, oargs, udd
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_mass_matrix_and_gamma_terms_vs_oracle(a2ds, orc, mode):
+    """TACS_MASS_MATRIX, assembleJacobian(alpha, beta, gamma) and the inertial residual
+    M uddot (TACSShellElement.h:410-447, 614-648)"""
+    asm, mat, oargs, udd = _dynamic_case(a2ds, orc)
+    asm.set_scatter_mode(mode)
+    asm.assembleMatType(a2ds.MASS_MATRIX, mat)
+    _, M_o = orc.assemble(4, *oargs)
+    M = asm.mat_values(mat)
+    assert relmax(M, M_o) < 1e-13
+    # without second derivatives: gamma only adds gamma * M; beta has no effect
+    r = asm.assembleJacobian(0.7, 0.3, 2.5, mat)
+    r_o, J_o = orc.assemble(1, *oargs, alpha=0.7, gamma=2.5)
+    assert relmax(r, r_o) < RES_TOL and relmax(asm.mat_values(mat), J_o) < MAT_TOL
+    # with second derivatives the residual carries M uddot, in assembleRes as well
+    asm.set_state_rates(None, udd)
+    r = asm.assembleJacobian(1.0, 0.0, 4.0, mat)
+    r_o, J_o = orc.assemble(1, *oargs, alpha=1.0, gamma=4.0, udd=udd)
+    assert relmax(r, r_o) < RES_TOL and relmax(asm.mat_values(mat), J_o) < MAT_TOL
+    r0_o, _ = orc.assemble(0, *oargs, udd=udd)
+    assert relmax(asm.assembleRes(), r0_o) < RES_TOL
+    # gamma = 0 with second derivatives: residual only
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, mat)
+    r_o, J_o = orc.assemble(1, *oargs, alpha=1.0, gamma=0.0, udd=udd)
+    assert relmax(r, r_o) < RES_TOL and relmax(asm.mat_values(mat), J_o) < MAT_TOL
+    # and removed again
+    asm.set_state_rates(None, None)
+    r0_o, _ = orc.assemble(0, *oargs)
+    assert relmax(asm.assembleRes(), r0_o) < RES_TOL
+    asm.close()
+
+
+def test_mat_combo_vs_separate_assemblies(a2ds, orc):
+    """TACSAssembler::assembleMatCombo: A = K - sigma G + w M, BCs applied once"""
+    asm, mat, oargs, _ = _dynamic_case(a2ds, orc)
+    types = [a2ds.STIFFNESS_MATRIX, a2ds.GEOMETRIC_STIFFNESS_MATRIX, a2ds.MASS_MATRIX]
+    scales = [1.0, -3.5, 120.0]
+    asm.assembleMatCombo(types, scales, mat)
+    A = asm.mat_values(mat)
+    rowp, cols, bcn = oargs[5], oargs[6], oargs[7]
+    # the oracle applies the BCs per matrix (identity on the diagonal): combine the
+    # unconstrained parts and put the single identity back
+    parts = [orc.assemble(op, *oargs[:7], None, None, None)[1] for op in (2, 3, 4)]
+    A_o = sum(s * p for s, p in zip(scales, parts))
+    for nd in bcn:
+        for j in range(rowp[nd], rowp[nd + 1]):
+            A_o[j] = np.eye(6) if cols[j] == nd else 0.0
+    assert relmax(A, A_o) < MAT_TOL
+    # single-type combos equal assembleMatType times the scale
+    asm.assembleMatCombo([a2ds.MASS_MATRIX], [2.0], mat)
+    M2 = asm.mat_values(mat)
+    asm.assembleMatType(a2ds.MASS_MATRIX, mat)
+    M = asm.mat_values(mat)
+    free = np.ones(len(cols), dtype=bool)
+    for nd in bcn:
+        free[rowp[nd]:rowp[nd + 1]] = False
+    assert relmax(M2[free], 2.0 * M[free]) < 1e-15
     asm.close()

@@ -63,3 +63,21 @@ def test_iso_tables_match_reference(a2ds, ref):
         Cs, eth = a2ds.iso_shell_tables(t_offset=off)
         Cr, er, _ = ref.con_tables(ref.iso_props(t_offset=off))
         assert relmax(Cs, Cr) < 1e-15 and np.array_equal(eth, er)
+
+
+def test_mass_block_against_oracle(emul, orc):
+    """the mass kernel's per-pair block (mass_block, mitc4_math.h) stepped on the host
+    against the oracle's restatement of TACS_MASS_MATRIX"""
+    import ctypes as C
+    X, q = random_elements(30, seed=21)
+    mom = np.array([27.18, -0.8154, 0.0246])   # m1 != 0: offset reference surface
+    axis = np.array([0.3, 1.0, 0.2]); axis /= np.linalg.norm(axis)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for tr in (0, 1):
+        comp = orc.make_comp(0, np.ones(22), np.zeros(9), mom, 0.0, tr, axis)
+        for e in range(X.shape[0]):
+            Xe = np.ascontiguousarray(X[e].ravel())
+            M = np.zeros(576)
+            emul.emul_mass(p(mom), C.c_int(tr), p(axis), p(Xe), p(M))
+            M_or = orc.mat_type(comp, 2, Xe, np.zeros(24))
+            assert relmax(M.reshape(24, 24), M_or) < 1e-13
