@@ -70,6 +70,11 @@ struct KParams {
   double gscale;         // scale of the geometric stiffness (assembleMatCombo; 1 otherwise)
   double res_scale;      // residual entries are multiplied by this before the RED
   double thermal;        // 1: residual of the state;  0: matrix-free product K x (u := x)
+  // matrix-free tangent product of the nonlinear model: y += jvp_scale * K_e(u) x_e instead
+  // of the matrix scatter (null: scatter)
+  const double *jvp_x;
+  double *jvp_y;
+  double jvp_scale;
   int scratch_bytes;
 };
 
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       const int j = sidx >> 4, k = sidx & 15;
       const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
       if (ej >= 0) {
-        if (KMAT) cp_async4(&rb.koff[j][k], &p.Koff[16 * (size_t)ej + k]);
+        if (KMAT && p.Koff) cp_async4(&rb.koff[j][k], &p.Koff[16 * (size_t)ej + k]);
         if (GMAT) cp_async4(&goffb[j][k], &p.Goff[16 * (size_t)ej + k]);
       }
     }
@@ -408,7 +413,23 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
         add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E, p.alpha, lane);
         __syncwarp();
       }
-      if (KMAT) scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
+      if (KMAT) {
+        if (NL && !GMAT && p.jvp_x) {
+          // matrix-free: the staged tangent times the element's slice of x (the second
+          // staging buffer is free in this variant)
+          const int node = ws.nodes[j][(lane / 6) & 3];
+          if (lane < 24) ws.E2[lane] = p.jvp_x[6 * (size_t)node + lane % 6];
+          __syncwarp();
+          if (lane < 24) {
+            double y = 0.0;
+#pragma unroll
+            for (int k = 0; k < 24; k++) y += ws.E[lane * KE_LD + k] * ws.E2[k];
+            atomicAdd(&p.jvp_y[6 * (size_t)node + lane % 6], p.jvp_scale * y);
+          }
+        } else {
+          scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
+        }
+      }
       if (GMAT) {
         if (KMAT) __syncwarp();  // E is reused for G once K has left
         symmetrize_add_geo(gm, wk, &ws.Pq[j][0][0], ws.E2, ws.E, p.gscale, lane);
@@ -1548,23 +1569,29 @@ extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, doub
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("addJacobianVecProduct: mesh or nodes not set");
   if (build_lists(c)) return 1;
-  for (int col = 0; col < c->n_colors; col++)
-    if (c->list_len[1][col] > 0)
-      return fail("addJacobianVecProduct: only linear-strain elements (TACSQuad4Shell) are "
-                  "supported matrix-free; assemble the tangent of nonlinear elements instead");
   c->last_launches = 0;
   CU(cudaEventRecord(c->ev0, c->stream));
   KParams p;
   memset(&p, 0, sizeof(p));
   p.conn = c->conn; p.elem_comp = c->elem_comp; p.comps = c->comps;
-  p.X = c->X; p.u = x_dev; p.res = y_dev; p.alpha = 1.0;
-  p.res_scale = scale * alpha; p.thermal = 0.0;
+  p.X = c->X; p.gscale = 1.0;
   CU(cudaEventRecord(c->evk0, c->stream));
   for (int col = 0; col < c->n_colors; col++) {
+    // linear strain model: K does not depend on the state, K x = residual kernel with u := x
     p.n_list = c->list_len[0][col];
     p.elem_list = c->list_dev[0][col];
-    if (p.n_list == 0) continue;
-    if (launch_one<true, false, false, false>(c, p)) return 1;
+    p.u = x_dev; p.res = y_dev; p.alpha = 1.0;
+    p.res_scale = scale * alpha; p.thermal = 0.0;
+    p.jvp_x = nullptr; p.jvp_y = nullptr;
+    if (p.n_list > 0 && launch_one<true, false, false, false>(c, p)) return 1;
+    // nonlinear strain model: the tangent about the current state is formed per element
+    // (as for assembleJacobian) and multiplied with the element's slice of x in shared
+    // memory instead of being scattered
+    p.n_list = c->list_len[1][col];
+    p.elem_list = c->list_dev[1][col];
+    p.u = c->u; p.res = nullptr; p.alpha = alpha; p.thermal = 1.0;
+    p.jvp_x = x_dev; p.jvp_y = y_dev; p.jvp_scale = scale;
+    if (p.n_list > 0 && launch_one<false, true, false, true>(c, p)) return 1;
   }
   CU(cudaEventRecord(c->evk1, c->stream));
   if (halo_exchange(c, y_dev, true)) return 1;

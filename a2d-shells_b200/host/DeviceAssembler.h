@@ -41,6 +41,14 @@ class DeviceAssembler {
   void setVariables(const double *u, bool owned_only = false) {
     check(a2ds_set_state(ctx_, owned_only ? n_owned_ : n_nodes_, u), "a2ds_set_state");
   }
+  // qdot / qddot of TACSAssembler::setVariables (only qddot enters: inertial term)
+  void setVariableRates(const double *udot, const double *uddot, bool owned_only = false) {
+    check(a2ds_set_state_rates(ctx_, owned_only ? n_owned_ : n_nodes_, udot, uddot),
+          "a2ds_set_state_rates");
+  }
+  void setMassMoments(int n_comp, const double *moments) {
+    check(a2ds_set_mass_moments(ctx_, n_comp, moments), "a2ds_set_mass_moments");
+  }
   void haloForward() { check(a2ds_halo_forward(ctx_), "a2ds_halo_forward"); }
 
   // TACSAssembler::createMat (natural order) / matrices whose pattern comes from a host object
@@ -67,6 +75,12 @@ class DeviceAssembler {
     check(a2ds_assemble_mat_type(ctx_, mat_type, mat), "assembleMatType");
   }
   // residual + K + G in one pass
+  void assembleMatCombo(int n, const int *mat_types, const double *scales, int mat) {
+    check(a2ds_assemble_mat_combo(ctx_, n, mat_types, scales, mat), "assembleMatCombo");
+  }
+  void addJacobianVecProduct(double scale, double alpha, const double *x, double *y) {
+    check(a2ds_add_jacobian_vec_product(ctx_, scale, alpha, x, y), "addJacobianVecProduct");
+  }
   void assembleAll(double *residual, int kmat, int gmat) {
     check(a2ds_assemble_all(ctx_, residual, kmat, gmat), "assembleAll");
   }

@@ -51,8 +51,8 @@ std::map<TACSAssembler *, Shim> g_shims;
 #define CK(call) do { if (call) die(#call); } while (0)
 
 template <class E>
-bool fill_component(TACSElement *e, double *Cs, double *eth, double *T, int *cls, int which,
-                    int *transform, double *axis) {
+bool fill_component(TACSElement *e, double *Cs, double *eth, double *mom, double *T, int *cls,
+                    int which, int *transform, double *axis) {
   E *s = dynamic_cast<E *>(e);
   if (!s) return false;
   double pt[3] = {0.0, 0.0, 0.0}, X[3] = {0.0, 0.0, 0.0};
@@ -60,6 +60,7 @@ bool fill_component(TACSElement *e, double *Cs, double *eth, double *T, int *cls
   // constitutive class the reference ships (TACSIsoShellConstitutive.cpp:192-226)
   s->con->evalTangentStiffness(0, pt, X, Cs);
   s->con->evalThermalStrain(0, pt, X, 1.0, eth);
+  s->con->evalMassMoments(0, pt, X, mom);
   *T = s->temperature;
   *cls = which;
   TACSShellRefAxisTransform *ra = dynamic_cast<TACSShellRefAxisTransform *>(s->transform);
@@ -115,22 +116,24 @@ static void shim_upload_components(TACSAssembler *self, Shim &S, bool first) {
   // per-component tables are refreshed on every call: element temperatures are public
   // data members that drivers change after set-up (mechBuckling.cpp:90-97)
   const int nc = (int)S.comp_elems.size();
-  std::vector<double> Cs(22 * nc), eth(9 * nc), T(nc);
+  std::vector<double> Cs(22 * nc), eth(9 * nc), mom(3 * nc), T(nc);
   std::vector<int> cls(nc);
   int transform = A2DS_TRANSFORM_NATURAL;
   double axis[3] = {1.0, 0.0, 0.0};
   for (int i = 0; i < nc; i++) {
     TACSElement *e = S.comp_elems[i];
-    if (!fill_component<TACSQuad4Shell>(e, &Cs[22 * i], &eth[9 * i], &T[i], &cls[i],
+    if (!fill_component<TACSQuad4Shell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i], &cls[i],
                                         A2DS_QUAD4_SHELL, &transform, axis) &&
-        !fill_component<TACSQuad4NonlinearShell>(e, &Cs[22 * i], &eth[9 * i], &T[i], &cls[i],
-                                                 A2DS_QUAD4_NONLINEAR_SHELL, &transform, axis)) {
+        !fill_component<TACSQuad4NonlinearShell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i],
+                                                 &cls[i], A2DS_QUAD4_NONLINEAR_SHELL, &transform,
+                                                 axis)) {
       fprintf(stderr, "[a2ds shim] element class %s is not supported on the device path "
                       "(TACSQuad4Shell / TACSQuad4NonlinearShell only); there is no CPU fallback\n",
               e->getObjectName());
       abort();
     }
   }
+  CK(a2ds_set_mass_moments(S.ctx, nc, mom.data()));
   CK(a2ds_set_components(S.ctx, nc, Cs.data(), eth.data(), T.data(), cls.data(), transform, axis));
 }
 
@@ -157,6 +160,13 @@ static Shim &shim_get(TACSAssembler *self) {
   TacsScalar *u;
   self->varsVec->getArray(&u);
   CK(a2ds_set_state(S.ctx, S.n_nodes, u));
+  // second time derivatives (inertial term): uploaded only when they are not all zero,
+  // so that static drivers never launch the mass kernel
+  TacsScalar *udd;
+  const int nudd = self->ddvarsVec->getArray(&udd);
+  bool dynamic = false;
+  for (int i = 0; i < nudd && !dynamic; i++) dynamic = udd[i] != 0.0;
+  CK(a2ds_set_state_rates(S.ctx, S.n_nodes, nullptr, dynamic ? udd : nullptr));
   return S;
 }
 
@@ -265,6 +275,7 @@ void TACSAssembler::assembleMatType(ElementMatrixType matType, TACSMat *A,
   int type = -1;
   if (matType == TACS_STIFFNESS_MATRIX) type = A2DS_STIFFNESS_MATRIX;
   if (matType == TACS_GEOMETRIC_STIFFNESS_MATRIX) type = A2DS_GEOMETRIC_STIFFNESS_MATRIX;
+  if (matType == TACS_MASS_MATRIX) type = A2DS_MASS_MATRIX;
   if (type < 0) {
     fprintf(stderr, "[a2ds shim] matrix type %d is not on the device path\n", (int)matType);
     abort();

@@ -177,7 +177,9 @@ int a2ds_assemble_all(a2ds_ctx *ctx, double *res, int kmat, int gmat);
 
 /* TACSAssembler::addJacobianVecProduct (src/TACSAssembler.cpp:4331-4391), matrix free:
  * y <- y + scale * (alpha K) x, BC rows of y zeroed; x, y hold 6 * n_nodes doubles (all
- * local nodes; ghost entries of x must be current).  Linear-strain elements only. */
+ * local nodes; ghost entries of x must be current).  Linear-strain elements: K x is the
+ * residual kernel evaluated at x; nonlinear-strain elements: the element tangent about
+ * the current state is formed on chip and multiplied with x instead of being scattered. */
 int a2ds_add_jacobian_vec_product(a2ds_ctx *ctx, double scale, double alpha, const double *x,
                                   double *y);
 int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *ctx, double scale, double alpha,

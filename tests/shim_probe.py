@@ -26,6 +26,17 @@ u = np.zeros((len(X), 6)); u[ra.new_nodes] = a2ds_meshes.seeded_state(np.arange(
 ra.set_state(u)
 r = ra.assemble_jacobian(pm)
 A = ra.mat_block(pm, 0)["A"]
+# the dynamic terms: mass matrix, and a Jacobian with gamma and second time derivatives
+ra.assemble_mat_type(2, pm)
+M = ra.mat_block(pm, 0)["A"]
+udd = np.zeros((len(X), 6)); udd[ra.new_nodes] = a2ds_meshes.seeded_state(np.arange(len(X)) + 5, 1.0)
+ra.set_state(u, None, udd)
+rd = ra.assemble_jacobian(pm, alpha=1.0, beta=0.0, gamma=1e4)
+Ad = ra.mat_block(pm, 0)["A"]
+w = np.cos(np.arange(A.size)).reshape(A.shape)   # fixed weights: a checksum that sees every entry
 print("SHIM_PROBE " + json.dumps(dict(eig=eig[:6].tolist(), err=err[:6].tolist(),
                                      res_norm=float(np.abs(r).max()), res_sum=float(r.sum()),
-                                     a_max=float(np.abs(A).max()), a_sum=float(A.sum()))))
+                                     a_max=float(np.abs(A).max()), a_sum=float(A.sum()),
+                                     m_max=float(np.abs(M[M != 1.0]).max()), m_chk=float(((M - (M == 1.0)) * w).sum()),
+                                     rd_max=float(np.abs(rd).max()), rd_chk=float((rd * w.ravel()[:rd.size].reshape(rd.shape)).sum()),
+                                     ad_max=float(np.abs(Ad).max()), ad_chk=float((Ad * w).sum()))))

@@ -423,6 +423,37 @@ def test_matrix_free_jacobian_vec_product(a2ds, orc):
     asm.close()
 
 
+def test_matrix_free_product_mixed_element_classes(a2ds, orc):
+    """addJacobianVecProduct with nonlinear-strain elements in the mesh: their tangent about
+    the CURRENT state (with thermal strain) is formed on chip and applied to x."""
+    conn, X, bcn = a2ds.meshes.cylinder(18, 7)
+    n = len(X); ne = len(conn)
+    rng = np.random.default_rng(3)
+    Cs0, eth0 = a2ds.iso_shell_tables(t_offset=0.1)
+    Cs1, eth1 = a2ds.iso_shell_tables(t=0.02)
+    Cs = np.stack([Cs0, Cs1]); eth = np.stack([eth0, eth1])
+    cls = np.array([0, 1], dtype=np.int32)
+    temperature = np.array([5.0, 12.0])
+    elem_comp = rng.integers(0, 2, ne).astype(np.int32)
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-3)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n, elem_comp=elem_comp); asm.set_nodes(X)
+    asm.set_components(Cs, eth, temperature=temperature, elem_class=cls)
+    asm.set_bcs(bcn, 63); asm.set_state(u)
+    x = rng.normal(size=(n, 6)); y0 = rng.normal(size=(n, 6))
+    y = asm.addJacobianVecProduct(-0.3, 1.5, x, y0)
+    rowp, cols = orc.pattern(n, conn)
+    comps = [orc.make_comp(int(cls[c]), Cs[c], eth[c], (0, 0, 0), temperature[c]) for c in range(2)]
+    _, K = orc.assemble(2, conn, elem_comp, comps, X, u, rowp, cols)   # raw tangent at u
+    ref = y0 - 0.3 * 1.5 * bcsr_matvec(K, rowp, cols, x)
+    ref[bcn] = 0.0
+    assert relmax(y, ref) < 1e-12
+    for mode in (a2ds.SCATTER_COLORED,):
+        asm.set_scatter_mode(mode)
+        assert relmax(asm.addJacobianVecProduct(-0.3, 1.5, x, y0), ref) < 1e-12
+    asm.close()
+
+
 def test_properties_at_baseline_size(a2ds):
     """BASELINE configs[1] at full size (1000 x 1000 plate, 1 M elements, 9 M blocks per
     matrix): size-independent properties checked with the device SpMV so that only vectors

@@ -46,3 +46,10 @@ def test_reference_buckling_flow_runs_on_gpu_through_the_shim(ref):
     assert abs(gpu["res_norm"] - base["res_norm"]) <= 1e-12 * base["res_norm"]
     assert abs(gpu["a_max"] - base["a_max"]) <= 1e-10 * base["a_max"]
     assert abs(gpu["a_sum"] - base["a_sum"]) <= 1e-9 * base["a_max"]
+    # TACS_MASS_MATRIX and assembleJacobian(alpha, beta, gamma) with qddot set
+    assert abs(gpu["m_max"] - base["m_max"]) <= 1e-12 * base["m_max"]
+    assert abs(gpu["m_chk"] - base["m_chk"]) <= 1e-10 * base["m_max"]
+    assert abs(gpu["rd_max"] - base["rd_max"]) <= 1e-12 * base["rd_max"]
+    assert abs(gpu["rd_chk"] - base["rd_chk"]) <= 1e-10 * base["rd_max"]
+    assert abs(gpu["ad_max"] - base["ad_max"]) <= 1e-10 * base["ad_max"]
+    assert abs(gpu["ad_chk"] - base["ad_chk"]) <= 1e-9 * base["ad_max"]
