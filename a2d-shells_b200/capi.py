@@ -44,6 +44,20 @@ def lib_path():
     return os.environ.get("A2DS_LIB") or os.path.join(HERE, "lib", "liba2ds_b200.so")
 
 
+def _prefer_bundled_nccl():
+    """The library links libnccl.so.2.  If a newer NCCL ships with the Python environment
+    (the one PyTorch is built against), make that the process-wide copy BEFORE ours resolves
+    the soname: otherwise a later `import torch` finds the older system NCCL already loaded
+    and fails on missing symbols.  Harmless when torch was imported first (already loaded)."""
+    import sysconfig
+    cand = os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "nccl", "lib", "libnccl.so.2")
+    if os.path.exists(cand):
+        try:
+            C.CDLL(cand, mode=C.RTLD_GLOBAL)
+        except OSError:
+            pass
+
+
 def load_library():
     """Load the CUDA library.  Fails loudly if it has not been built — there is no
     fallback implementation."""
@@ -54,6 +68,7 @@ def load_library():
             raise A2dsError(
                 f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+        _prefer_bundled_nccl()
         L = C.CDLL(path)
         L.a2ds_last_error.restype = C.c_char_p
         L.a2ds_version.restype = C.c_char_p

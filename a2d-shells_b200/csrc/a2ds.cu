@@ -483,10 +483,9 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 3) k_mass(const KPar
       }
     }
     __syncwarp();
-    if (lane < 4 * NB && jl < cnt) phase_node(p.comps[ws.raw0.comp[jl]], ws.geo[jl], lane & 3);
+    if (lane < 4 * NB && jl < cnt) mass_node(ws.geo[jl], lane & 3);
     __syncwarp();
-    if (lane < 4 * NB && jl < cnt)
-      phase_qp(p.comps[ws.raw0.comp[jl]], ws.geo[jl], lane & 3, false, false, false, (double *)0);
+    if (lane < 4 * NB && jl < cnt) mass_qp(ws.geo[jl], lane & 3);
     __syncwarp();
 #pragma unroll 1
     for (int j = 0; j < cnt; j++) {

@@ -895,6 +895,40 @@ A2DS_HD void geo_block(const ElemGeom &gm, const ElemWork &s, const double *Pq4,
   for (int i = 0; i < 9; i++) out[i] = blk[i];
 }
 
+// ---- light geometry phases of the mass path: node normal and quadrature weight only ----
+// (the same expressions as phase_node / qp_geometry evaluate for fn and det)
+A2DS_HD void mass_node(ElemGeom &s, int m) {
+  double Xxi[3], Xeta[3];
+  edge_xi(s.X, 3, m / 2, Xxi);
+  edge_eta(s.X, 3, m % 2, Xeta);
+  double fn[3];
+  scross(Xxi, Xeta, fn);
+  double nrm = sqrt(sdot(fn, fn));
+  if (nrm != 0.0) {
+    double inv = 1.0 / nrm;
+    fn[0] = A2DS_MUL(fn[0], inv); fn[1] = A2DS_MUL(fn[1], inv); fn[2] = A2DS_MUL(fn[2], inv);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) s.fn[3 * m + k] = fn[k];
+}
+
+A2DS_HD void mass_qp(ElemGeom &s, int qp) {
+  double na[2], nb[2];
+  qp_shape(qp, na, nb);
+  double a0[3], a1[3], b0[3], b1[3];
+  edge_vectors(s.X, 3, a0, a1, b0, b1);
+  const double N[4] = {na[0] * nb[0], na[1] * nb[0], na[0] * nb[1], na[1] * nb[1]};
+  double A[9];  // Xd = [X,xi | X,eta | n0] (columns), row major
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    A[3 * k] = nb[0] * a0[k] + nb[1] * a1[k];
+    A[3 * k + 1] = na[0] * b0[k] + na[1] * b1[k];
+    A[3 * k + 2] = N[0] * s.fn[k] + N[1] * s.fn[3 + k] + N[2] * s.fn[6 + k] + N[3] * s.fn[9 + k];
+  }
+  s.qp[qp].w = (A[8] * (A[0] * A[4] - A[3] * A[1]) - A[7] * (A[0] * A[5] - A[3] * A[2]) +
+                A[6] * (A[1] * A[5] - A[2] * A[4]));
+}
+
 // ---- mass matrix: one 3x3 block for the generalised node pair (p, pp) -----------
 // Kinetic energy density 1/2 (m0 u'.u' + 2 m1 u'.d' + m2 d'.d') with u and d interpolated
 // bilinearly (TACSShellElement.h:614-648): the block is (sum_qp w N_m N_mm) m_k I with

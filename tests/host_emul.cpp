@@ -95,8 +95,8 @@ extern "C" int emul_mass(const double *mom, int transform, const double *axis, c
   static ElemGeom s;
   memset(&s, 0, sizeof(s));
   memcpy(s.X, X, sizeof(s.X));
-  for (int m = 0; m < 4; m++) phase_node(c, s, m);
-  for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, false, false, false, (double *)0);
+  for (int m = 0; m < 4; m++) mass_node(s, m);
+  for (int qp = 0; qp < 4; qp++) mass_qp(s, qp);
   for (int p = 0; p < 8; p++)
     for (int pp = 0; pp < 8; pp++) {
       double blk[9];

@@ -236,6 +236,30 @@ def test_properties_at_size(a2ds):
     asm.set_state(2.0 * u)
     asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, k)
     assert relmax(asm.mat_values(k), 2.0 * G) < 1e-12
+    # mass matrix: symmetric; a rigid translation carries the total mass m0 * area, and the
+    # gamma term of the Jacobian is exactly gamma * M on top of K
+    mom = a2ds.iso_mass_moments(2718.0, 0.010, 0.2)
+    asm.set_mass_moments(mom[None])
+    asm.assembleMatType(a2ds.MASS_MATRIX, g)
+    M = asm.mat_values(g)
+    a = np.sum(x * bcsr_matvec(M, rowp, cols, y)); b = np.sum(y * bcsr_matvec(M, rowp, cols, x))
+    assert abs(a - b) < 1e-10 * (abs(a) + abs(b))
+    area = 0.0   # surface area of the bumped plate from the same bilinear geometry
+    Xe = X[conn]
+    gp = 0.577350269189626
+    for xi in (-gp, gp):
+        for eta in (-gp, gp):
+            dxi = 0.5 * ((1 - eta) * (Xe[:, 1] - Xe[:, 0]) + (1 + eta) * (Xe[:, 3] - Xe[:, 2])) * 0.5
+            det = 0.5 * ((1 - xi) * (Xe[:, 2] - Xe[:, 0]) + (1 + xi) * (Xe[:, 3] - Xe[:, 1])) * 0.5
+            area += np.linalg.norm(np.cross(dxi, det), axis=1).sum()
+    tz = np.zeros((n, 6)); tz[:, 2] = 1.0
+    total = np.sum(tz * bcsr_matvec(M, rowp, cols, tz))
+    # det[X,xi X,eta n0] uses the interpolated node normal (|n0| = 1 - O((kappa h)^2)), so
+    # the element's area measure differs from |X,xi x X,eta| at the 1e-7 level here
+    assert abs(total - mom[0] * area) < 1e-5 * mom[0] * area
+    asm.set_state(u)
+    asm.assembleJacobian(1.0, 0.0, 7.0, k, download=False)
+    assert relmax(asm.mat_values(k), K + 7.0 * M) < 1e-13
     asm.close()
 
 
