@@ -674,6 +674,11 @@ struct MatrixRec {
 struct a2ds_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // host -> device state uploads run on their own stream so that they overlap the zeroing of
+  // the matrices at the start of the next assembly (both take ~1 ms at 1 M elements)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_state = nullptr, ev_used = nullptr;
+  bool state_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   int n_sm = 0;
   int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
@@ -709,6 +714,15 @@ struct a2ds_ctx {
 
 static int halo_exchange(a2ds_ctx *c, double *vec, bool reverse);
 
+// make the main stream wait for a state upload still in flight on the copy stream
+static int state_wait(a2ds_ctx *c) {
+  if (c->state_pending) {
+    CU(cudaStreamWaitEvent(c->stream, c->ev_state, 0));
+    c->state_pending = false;
+  }
+  return 0;
+}
+
 template <class T>
 static int upload(T **dst, const T *src, size_t n, cudaStream_t st) {
   if (*dst) cudaFree(*dst);
@@ -740,6 +754,9 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
     if (v >= 1 && v <= MAX_WARPS_PER_BLOCK) c->warps_per_block_forced = v;
   }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_used, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreate(&c->evk0));
@@ -763,6 +780,7 @@ static void free_lists(a2ds_ctx *c) {
 extern "C" int a2ds_destroy(a2ds_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
   for (auto &m : c->mats)
     for (void *p : m.owned) cudaFree(p);
@@ -774,6 +792,8 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   if (c->comm) ncclCommDestroy(c->comm);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0);
   cudaEventDestroy(c->evk1); cudaEventDestroy(c->evr0); cudaEventDestroy(c->evr1);
+  cudaEventDestroy(c->ev_state); cudaEventDestroy(c->ev_used);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -781,6 +801,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
 
 extern "C" int a2ds_synchronize(a2ds_ctx *c) {
   CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->copy_stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -799,6 +820,8 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
   else c->h_elem_comp.assign(n_elems, 0);
   if (upload(&c->conn, conn, 4 * (size_t)n_elems, c->stream)) return 1;
   if (upload(&c->elem_comp, c->h_elem_comp.data(), (size_t)n_elems, c->stream)) return 1;
+  CU(cudaStreamSynchronize(c->copy_stream));
+  c->state_pending = false;
   cudaFree(c->X); cudaFree(c->u); cudaFree(c->res); cudaFree(c->udd);
   c->udd = nullptr;
   c->X = c->u = c->res = nullptr;
@@ -909,6 +932,7 @@ extern "C" int a2ds_set_state_dev(a2ds_ctx *c, int n_given, const double *u_dev)
   CU(cudaSetDevice(c->device));
   if (n_given != c->n_nodes && n_given != c->n_owned)
     return fail("a2ds_set_state: n_given must be n_nodes or n_owned");
+  if (state_wait(c)) return 1;
   CU(cudaMemcpyAsync(c->u, u_dev, 6 * (size_t)n_given * sizeof(double), cudaMemcpyDeviceToDevice,
                      c->stream));
   return 0;
@@ -918,8 +942,14 @@ extern "C" int a2ds_set_state(a2ds_ctx *c, int n_given, const double *u) {
   CU(cudaSetDevice(c->device));
   if (n_given != c->n_nodes && n_given != c->n_owned)
     return fail("a2ds_set_state: n_given must be n_nodes or n_owned");
+  // after everything queued so far that reads the old state ...
+  CU(cudaEventRecord(c->ev_used, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_used, 0));
   CU(cudaMemcpyAsync(c->u, u, 6 * (size_t)n_given * sizeof(double), cudaMemcpyHostToDevice,
-                     c->stream));
+                     c->copy_stream));
+  // ... and before the first consumer of the new one (state_wait)
+  CU(cudaEventRecord(c->ev_state, c->copy_stream));
+  c->state_pending = true;
   return 0;
 }
 
@@ -1248,7 +1278,12 @@ extern "C" int a2ds_mat_mult(a2ds_ctx *c, int mat, int block, int ncols, const d
 }
 
 extern "C" int a2ds_res_dev(a2ds_ctx *c, double **r) { *r = c->res; return 0; }
-extern "C" int a2ds_state_dev(a2ds_ctx *c, double **u) { *u = c->u; return 0; }
+extern "C" int a2ds_state_dev(a2ds_ctx *c, double **u) {
+  CU(cudaSetDevice(c->device));
+  if (state_wait(c)) return 1;
+  *u = c->u;
+  return 0;
+}
 
 // ---- halo -------------------------------------------------------------------
 extern "C" int a2ds_comm_unique_id(char id[128]) {
@@ -1316,6 +1351,7 @@ static int halo_exchange(a2ds_ctx *c, double *vec, bool reverse) {
 
 extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
   CU(cudaSetDevice(c->device));
+  if (state_wait(c)) return 1;
   return halo_exchange(c, c->u, false);
 }
 
@@ -1425,6 +1461,8 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
       CU(cudaMemsetAsync(c->mats[mmat].A, 0, c->mats[mmat].total * 36 * sizeof(double), c->stream));
     c->last_launches += (RES ? 1 : 0) + (KM ? 1 : 0) + (GM ? 1 : 0) + (MM && !(KM && mmat == kmat) ? 1 : 0);
   }
+
+  if (state_wait(c)) return 1;  // the upload overlapped the zeroing above
 
   KParams p;
   memset(&p, 0, sizeof(p));
@@ -1568,6 +1606,7 @@ extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, doub
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("addJacobianVecProduct: mesh or nodes not set");
   if (build_lists(c)) return 1;
+  if (state_wait(c)) return 1;
   c->last_launches = 0;
   CU(cudaEventRecord(c->ev0, c->stream));
   KParams p;
