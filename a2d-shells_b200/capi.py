@@ -30,6 +30,7 @@ SYMBOLS = [
     "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
     "a2ds_add_jacobian_vec_product", "a2ds_add_jacobian_vec_product_dev",
     "a2ds_set_mass_moments", "a2ds_set_state_rates", "a2ds_assemble_mat_combo",
+    "a2ds_mat_mult_dist_dev",
 ]
 
 _LIB = None
@@ -287,6 +288,11 @@ class Assembler:
     def mat_mult_dev(self, mat, x_dev, y_dev, block=0):
         self._chk(self.L.a2ds_mat_mult_dev(self.ctx, C.c_int(mat), C.c_int(block),
                                            C.c_void_p(x_dev), C.c_void_p(y_dev)))
+
+    def mat_mult_dist_dev(self, mat, x_dev, y_dev):
+        """distributed y = A x (owned rows), halo exchanges inside; device pointers"""
+        self._chk(self.L.a2ds_mat_mult_dist_dev(self.ctx, C.c_int(mat), C.c_void_p(x_dev),
+                                                C.c_void_p(y_dev)))
 
     # -- assembly (TACSAssembler names) ------------------------------------------------
     def _res_out(self, want):

@@ -566,6 +566,15 @@ __global__ void k_vec_zero_bcs(int n_bc, const int *nodes, const int *vars, doub
   if (n < n_owned && (vars[b] & (1 << k))) y[6 * (size_t)n + k] = 0.0;
 }
 
+// y[bc] = x[bc] on the owned BC rows: what the identity rows of the assembled matrix give
+__global__ void k_vec_copy_bcs(int n_bc, const int *nodes, const int *vars, const double *x,
+                               double *y, int n_owned) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n_bc) return;
+  const int b = t / 6, k = t - 6 * b, n = nodes[b];
+  if (n < n_owned && (vars[b] & (1 << k))) y[6 * (size_t)n + k] = x[6 * (size_t)n + k];
+}
+
 // matrix BC rows: zero the constrained DOF rows of every block in the block row, 1.0 on
 // the diagonal entry of the diagonal block (BCSRMat::zeroRow, BCSRMat.cpp:2005-2030;
 // columns untouched, as the reference)
@@ -1256,6 +1265,30 @@ extern "C" int a2ds_mat_mult_dev(a2ds_ctx *c, int mat, int block, const double *
   k_spmv6<<<(unsigned)((nt + 191) / 192), 192, 0, c->stream>>>(
       nrows, m.d_rowp[block], m.d_cols[block], m.A + 36 * m.base[block], x_dev, y_dev);
   CU(cudaGetLastError());
+  return 0;
+}
+
+// Distributed mat-vec for a matrix assembled per rank over its local nodes (interface rows
+// unassembled: the sum over the ranks of the local matrices is the global matrix; BCs applied
+// per rank).  Owned rows of y on return equal TACSParallelMat::mult
+// (src/bpmat/TACSParallelMat.cpp:248) without any exchange of matrix rows:
+//   ghost entries of x <- owners, y = A_local x over ALL local rows, ghost rows of y -> owners
+//   (add), y[bc] = x[bc].
+extern "C" int a2ds_mat_mult_dist_dev(a2ds_ctx *c, int mat, double *x_dev, double *y_dev) {
+  if (check_mat(c, mat, 0)) return 1;
+  CU(cudaSetDevice(c->device));
+  MatrixRec &m = c->mats[mat];
+  if (m.n_blocks != 1 || m.nrows[0] != c->n_nodes)
+    return fail("a2ds_mat_mult_dist: needs a natural-order matrix over the local nodes "
+                "(a2ds_mat_create_natural)");
+  if (halo_exchange(c, x_dev, false)) return 1;
+  if (a2ds_mat_mult_dev(c, mat, 0, x_dev, y_dev)) return 1;
+  if (halo_exchange(c, y_dev, true)) return 1;
+  if (c->n_bc) {
+    k_vec_copy_bcs<<<(6 * c->n_bc + 255) / 256, 256, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars,
+                                                                     x_dev, y_dev, c->n_owned);
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 

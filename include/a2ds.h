@@ -153,6 +153,13 @@ int a2ds_mat_apply_bcs(a2ds_ctx *ctx, int mat);
  * row/column numbering.  _dev: device pointers; the other takes host pointers. */
 int a2ds_mat_mult_dev(a2ds_ctx *ctx, int mat, int block, const double *x_dev, double *y_dev);
 int a2ds_mat_mult(a2ds_ctx *ctx, int mat, int block, int ncols, const double *x, double *y);
+/* TACSParallelMat::mult (src/bpmat/TACSParallelMat.cpp:248) for the owned rows of a matrix
+ * that every rank assembled over its local nodes (a2ds_mat_create_natural; interface rows
+ * stay unassembled per rank): ghost entries of x are fetched from their owners, y = A x over
+ * all local rows, ghost rows of y are added at their owners (the halo of a2ds_set_halo),
+ * y = x on constrained DOFs.  x_dev, y_dev: 6 * n_nodes doubles on the device; the ghost
+ * part of x is overwritten.  Without a halo this is a2ds_mat_mult_dev plus the BC rows. */
+int a2ds_mat_mult_dist_dev(a2ds_ctx *ctx, int mat, double *x_dev, double *y_dev);
 
 /* ---- assembly: the three reference entry points -------------------------------
  * TACSAssembler::assembleRes (src/TACSAssembler.cpp:4000-4063): res[6 n + k] for the

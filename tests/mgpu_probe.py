@@ -38,7 +38,16 @@ def main():
     res = asm.assembleAll(k, g)
     rowp, cols = asm.mat_pattern(k)
     K = asm.mat_values(k); G = asm.mat_values(g)
-    out = dict(glob=slab["glob"], n_owned=slab["n_owned"], res=res, rowp=rowp, cols=cols, K=K, G=G)
+    # distributed mat-vec y = K x: x known on the owned nodes only, halo inside the call
+    nl, no = slab["n_nodes"], slab["n_owned"]
+    x = torch.zeros((nl, 6), dtype=torch.float64, device="cuda")
+    x[:no] = torch.from_numpy(a2ds.meshes.seeded_state(slab["glob"][:no] + 31337, 1.0)).cuda()
+    x[no:] = float("nan")        # ghosts must come through the halo
+    y = torch.zeros_like(x)
+    asm.mat_mult_dist_dev(k, x.data_ptr(), y.data_ptr())
+    asm.synchronize()
+    out = dict(glob=slab["glob"], n_owned=slab["n_owned"], res=res, rowp=rowp, cols=cols, K=K, G=G,
+               y=y[:no].cpu().numpy())
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(out, gathered, dst=0)
     asm.close()
@@ -62,6 +71,13 @@ def main():
         rp, cl = ref.mat_pattern(kk)
         K_all = ref.mat_values(kk); G_all = ref.mat_values(gg)
         ref.close()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import bcsr_matvec
+        y_all = bcsr_matvec(K_all, rp, cl, a2ds.meshes.seeded_state(np.arange(n) + 31337, 1.0))
+        worst_y = max(np.abs(o["y"] - y_all[o["glob"][:o["n_owned"]]]).max() for o in gathered)
+        worst_y /= np.abs(y_all).max()
+        print("MGPU_MATVEC", worst_y)
+        assert worst_y < 1e-13, worst_y
         worst = [0.0, 0.0, 0.0]
         shared_rows = set()
         for r in range(1, world):

@@ -70,3 +70,90 @@ def test_halo_plan_two_ranks_gloo():
         assert ret[r][0] and ret[r][1], ret[r]
     # every node of the 6 x 8 plate is owned exactly once
     assert sum(ret[r][2] for r in range(world)) == 7 * 9
+
+
+def _exchange(dist, torch, s, vec, reverse):
+    """the halo of a2ds_set_halo with gloo sends: forward owners -> ghosts (overwrite),
+    reverse ghosts -> owners (add)"""
+    reqs = []; bufs = []
+    for p, sl, rl in zip(s["peers"], s["send_lists"], s["recv_lists"]):
+        out, inn = (rl, sl) if reverse else (sl, rl)
+        if len(out):
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(vec[out])), int(p)))
+        if len(inn):
+            b = torch.empty((len(inn), 6), dtype=torch.float64); bufs.append((inn, b))
+            reqs.append(dist.irecv(b, int(p)))
+    for r in reqs:
+        r.wait()
+    for idx, b in bufs:
+        if reverse:
+            vec[idx] += b.numpy()
+        else:
+            vec[idx] = b.numpy()
+
+
+def _matvec_worker(rank, world, port, ret):
+    """the algorithm of a2ds_mat_mult_dist_dev on the CPU: per-rank matrices assembled by the
+    oracle over the local nodes (interface rows unassembled), x forward, local product,
+    y reverse-add, BC rows y = x"""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    a2ds = importlib.import_module("a2d-shells_b200")
+    import oracle_py as orc
+    from helpers import bcsr_matvec
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nx, ny = 5, 3
+    s = a2ds.meshes.plate_slab(rank, world, nx, ny, bump=3e-2)
+    n_owned, n = s["n_owned"], s["n_nodes"]
+    Cs, eth = a2ds.iso_shell_tables()
+    comp = orc.make_comp(0, Cs, eth)
+    rowp, cols = orc.pattern(n, s["conn"])
+    bcn = np.asarray(s["bc_nodes"], dtype=np.int32)
+    bv = np.full(len(bcn), 63, dtype=np.int32)
+    _, K = orc.assemble(2, s["conn"], np.zeros(len(s["conn"]), dtype=np.int32), [comp], s["X"],
+                        np.zeros((n, 6)), rowp, cols, bcn, bv, np.zeros((len(bcn), 6)))
+    x = np.full((n, 6), np.nan)
+    x[:n_owned] = a2ds.meshes.seeded_state(s["glob"][:n_owned] + 99, 1.0)
+    _exchange(dist, torch, s, x, reverse=False)
+    y = bcsr_matvec(K, rowp, cols, x)
+    _exchange(dist, torch, s, y, reverse=True)
+    own_bc = bcn[bcn < n_owned]
+    y[own_bc] = x[own_bc]
+    ret[rank] = (s["glob"][:n_owned].copy(), y[:n_owned].copy())
+    dist.destroy_process_group()
+
+
+def test_distributed_matvec_two_ranks_gloo():
+    import importlib
+    import torch.multiprocessing as mp
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    a2ds = importlib.import_module("a2d-shells_b200")
+    import oracle_py as orc
+    from helpers import bcsr_matvec
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29650 + (os.getpid() % 200)
+    mp.spawn(_matvec_worker, args=(world, port, ret), nprocs=world, join=True)
+    nx, ny = 5, 3
+    conn, X, bcn = a2ds.meshes.plate(nx, ny * world, ly=1.0 * world, bump=3e-2)
+    n = len(X)
+    Xs = np.zeros_like(X)
+    for r in range(world):   # the geometry exactly as the slabs see it
+        s = a2ds.meshes.plate_slab(r, world, nx, ny, bump=3e-2)
+        Xs[s["glob"]] = s["X"]
+    Cs, eth = a2ds.iso_shell_tables()
+    rowp, cols = orc.pattern(n, conn)
+    bv = np.full(len(bcn), 63, dtype=np.int32)
+    _, K = orc.assemble(2, conn, np.zeros(len(conn), dtype=np.int32), [orc.make_comp(0, Cs, eth)],
+                        Xs, np.zeros((n, 6)), rowp, cols, bcn, bv, np.zeros((len(bcn), 6)))
+    y_all = bcsr_matvec(K, rowp, cols, a2ds.meshes.seeded_state(np.arange(n) + 99, 1.0))
+    seen = 0
+    for r in range(world):
+        glob, y = ret[r]
+        assert np.abs(y - y_all[glob]).max() < 1e-13 * np.abs(y_all).max()
+        seen += len(glob)
+    assert seen == n
