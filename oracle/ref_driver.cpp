@@ -487,6 +487,32 @@ int refdrv_buckling(void *h, int kmat, int gmat, int aux, int mode, double sigma
   return 0;
 }
 
+/* TACSFrequencyAnalysis (Lanczos, shift-invert): the reference assembles K and M through
+   TACSAssembler::assembleMatType, forms K - sigma M, applies the BCs, factors and iterates
+   (src/TACSBuckling.cpp:823-870).  Returns the eigenvalues omega^2. */
+int refdrv_frequency(void *h, int kmat, int mmat, double sigma, int max_lanczos, int num_eigs,
+                     double tol, double *eigs, double *errs) {
+  RefCtx *c = (RefCtx *)h;
+  TACSSchurMat *K = (TACSSchurMat *)c->mats[kmat].mat;
+  TACSSchurMat *M = (TACSSchurMat *)c->mats[mmat].mat;
+  TACSSchurPc *pc = new TACSSchurPc(K, 1000000, 10.0, 1);
+  pc->incref();
+  GMRES *solver = new GMRES(K, pc, 10, 15, 0);
+  solver->incref();
+  solver->setTolerances(1e-12, 1e-12);
+  TACSFrequencyAnalysis *f =
+      new TACSFrequencyAnalysis(c->assembler, sigma, M, K, solver, max_lanczos, num_eigs, tol);
+  f->incref();
+  f->solve(NULL, 0);
+  for (int i = 0; i < num_eigs; i++) {
+    TacsScalar err;
+    eigs[i] = f->extractEigenvalue(i, &err);
+    if (errs) errs[i] = err;
+  }
+  f->decref(); solver->decref(); pc->decref();
+  return 0;
+}
+
 /* load-path state the buckling flow assembles G about: zero + setBCs
    (src/TACSBuckling.cpp:262) in the reference numbering */
 int refdrv_bc_state(void *h, double *u) {

@@ -220,6 +220,14 @@ class RefAssembler:
                               C.c_double(tol), _p(u0a), _p(eigs), _p(errs), _p(self.path))
         return eigs, errs
 
+    def frequency(self, kmat, mmat, sigma=0.0, max_lanczos=60, num_eigs=10, tol=1e-12):
+        """TACSFrequencyAnalysis::solve (Lanczos); returns (omega^2[num_eigs], err)"""
+        eig = np.zeros(num_eigs); err = np.zeros(num_eigs)
+        lib().refdrv_frequency(self.h, C.c_int(kmat), C.c_int(mmat), C.c_double(sigma),
+                               C.c_int(max_lanczos), C.c_int(num_eigs), C.c_double(tol),
+                               _p(eig), _p(err))
+        return eig, err
+
     def close(self):
         if self.h:
             lib().refdrv_destroy(self.h)

@@ -33,8 +33,12 @@ udd = np.zeros((len(X), 6)); udd[ra.new_nodes] = a2ds_meshes.seeded_state(np.ara
 ra.set_state(u, None, udd)
 rd = ra.assemble_jacobian(pm, alpha=1.0, beta=0.0, gamma=1e4)
 Ad = ra.mat_block(pm, 0)["A"]
+# TACSFrequencyAnalysis::solve (K and M through assembleMatType, shift-invert Lanczos)
+fk, fm = ra.mat_create(1), ra.mat_create(1)
+feig, ferr = ra.frequency(fk, fm, sigma=1e6, num_eigs=6, max_lanczos=60)
 w = np.cos(np.arange(A.size)).reshape(A.shape)   # fixed weights: a checksum that sees every entry
 print("SHIM_PROBE " + json.dumps(dict(eig=eig[:6].tolist(), err=err[:6].tolist(),
+                                     feig=feig.tolist(), ferr=ferr.tolist(),
                                      res_norm=float(np.abs(r).max()), res_sum=float(r.sum()),
                                      a_max=float(np.abs(A).max()), a_sum=float(A.sum()),
                                      m_max=float(np.abs(M[M != 1.0]).max()), m_chk=float(((M - (M == 1.0)) * w).sum()),

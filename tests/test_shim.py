@@ -46,6 +46,10 @@ def test_reference_buckling_flow_runs_on_gpu_through_the_shim(ref):
     assert abs(gpu["res_norm"] - base["res_norm"]) <= 1e-12 * base["res_norm"]
     assert abs(gpu["a_max"] - base["a_max"]) <= 1e-10 * base["a_max"]
     assert abs(gpu["a_sum"] - base["a_sum"]) <= 1e-9 * base["a_max"]
+    # natural frequencies: the reference's TACSFrequencyAnalysis with K and M from the device
+    f0, f1 = np.array(base["feig"])[:5], np.array(gpu["feig"])[:5]   # those nearest the shift
+    assert np.all(np.array(base["ferr"])[:5] < 1e-6 * np.abs(f0))
+    assert np.all(np.abs(f1 - f0) <= 1e-8 * np.abs(f0)), (f0, f1)
     # TACS_MASS_MATRIX and assembleJacobian(alpha, beta, gamma) with qddot set
     assert abs(gpu["m_max"] - base["m_max"]) <= 1e-12 * base["m_max"]
     assert abs(gpu["m_chk"] - base["m_chk"]) <= 1e-10 * base["m_max"]
