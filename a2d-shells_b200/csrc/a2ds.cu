@@ -85,6 +85,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 }
 
 static const int MAX_WARPS_PER_BLOCK = 4;
+static const int MAX_DEVICES = 64;  // per-device caches of launch configurations
 // Register budget: the residual / tangent kernels run at 12 warps per SM (168
 // registers); the variants that carry the B1(q) fragments across the tangent pass
 // (geometric stiffness, nonlinear model) need the full 255 registers (8 warps per SM).
@@ -748,7 +749,8 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
     return fail("a2ds_create: no CUDA device available (there is no CPU path)");
-  if (device < 0 || device >= n) return fail("a2ds_create: bad device index");
+  if (device < 0 || device >= n || device >= MAX_DEVICES)
+    return fail("a2ds_create: bad device index");
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -1397,7 +1399,9 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   auto kern = k_assemble<RES, KMAT, GMAT, NL>;
   // pick the block size (1..4 warps) that keeps the most warps resident per SM: shared
   // memory is allocated per block, so smaller blocks pack better when it is the limiter
-  static int best_wpb = 0, best_per_sm = 0;  // per instantiation
+  // per instantiation AND per device: function attributes are device state
+  static int best_wpb_dev[MAX_DEVICES] = {0}, best_per_sm_dev[MAX_DEVICES] = {0};
+  int &best_wpb = best_wpb_dev[c->device], &best_per_sm = best_per_sm_dev[c->device];
   if (best_wpb == 0 || c->warps_per_block_forced) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(per_warp * MAX_WARPS_PER_BLOCK)));
@@ -1431,7 +1435,8 @@ static int launch_mass(a2ds_ctx *c, KParams &p) {
   const size_t per_warp = (offsetof(WarpScratch, E2) + 15) & ~size_t(15);
   p.scratch_bytes = (int)per_warp;
   auto kern = k_mass<RES, MAT>;
-  static int per_sm = 0;
+  static int per_sm_dev[MAX_DEVICES] = {0};  // function attributes are device state
+  int &per_sm = per_sm_dev[c->device];
   const int wpb = MAX_WARPS_PER_BLOCK;
   if (per_sm == 0) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));

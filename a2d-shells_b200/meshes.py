@@ -40,6 +40,51 @@ def cylinder(ntheta, nx, radius=0.2, length=0.4, x0=0.0):
     return conn, X, ends
 
 
+def cubed_sphere(n, radius=0.3, shuffle_seed=None):
+    """Closed sphere meshed from the six faces of a cube (n x n quads each): an UNSTRUCTURED
+    quad mesh — the 8 cube corners have valence 3, no global (i, j) numbering exists.
+    Element node order is the tensor order [(0,0),(1,0),(0,1),(1,1)] of each face's own
+    (a, b) parametrisation, oriented so that every element normal points outwards.
+    shuffle_seed: additionally permute node numbers and element order at random.
+    Returns conn, X, and the nodes of one small patch to clamp."""
+    faces = []  # (origin, da, db) on the cube [-1, 1]^3, da x db pointing outwards
+    for axis in range(3):
+        for sign in (-1.0, 1.0):
+            a = np.zeros(3); b = np.zeros(3); o = np.zeros(3)
+            a[(axis + 1) % 3] = 1.0; b[(axis + 2) % 3] = 1.0; o[axis] = sign
+            if sign < 0:
+                a, b = b, a
+            faces.append((o - a - b, 2.0 * a, 2.0 * b))
+    key = {}
+    pts = []
+    conn = []
+    t = np.arange(n + 1) / n
+    for o, da, db in faces:
+        ids = np.zeros((n + 1, n + 1), dtype=np.int64)
+        for j in range(n + 1):
+            for i in range(n + 1):
+                p = o + t[i] * da + t[j] * db
+                k = tuple(np.round(p * n).astype(np.int64))   # exact on the cube lattice
+                if k not in key:
+                    key[k] = len(pts)
+                    pts.append(p)
+                ids[j, i] = key[k]
+        for j in range(n):
+            for i in range(n):
+                conn.append([ids[j, i], ids[j, i + 1], ids[j + 1, i], ids[j + 1, i + 1]])
+    P = np.array(pts)
+    X = radius * P / np.linalg.norm(P, axis=1)[:, None]
+    conn = np.array(conn, dtype=np.int32)
+    if shuffle_seed is not None:
+        rng = np.random.default_rng(shuffle_seed)
+        perm = rng.permutation(len(X))            # new id of old node i
+        Xn = np.zeros_like(X); Xn[perm] = X
+        X = Xn
+        conn = perm[conn].astype(np.int32)[rng.permutation(len(conn))]
+    patch = np.unique(conn[:max(1, n // 2)].ravel()).astype(np.int32)
+    return conn, X, patch
+
+
 def _splitmix64(x):
     x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
     z = x

@@ -148,3 +148,20 @@ def test_structured_slabs_match_generic_partition(a2ds):
         assert np.allclose(s["X"], X[s["glob"]])
         for a, b in zip(s["send_lists"] + s["recv_lists"], p["send_lists"] + p["recv_lists"]):
             assert np.array_equal(a, b)
+
+
+def test_pattern_and_colouring_on_unstructured_mesh(a2ds, orc):
+    """host set-up on a mesh with irregular valence and shuffled numbering: pattern
+    bit-identical to the oracle's, colouring valid (no two elements of a colour share a node)"""
+    for seed in (None, 3):
+        conn, X, _ = a2ds.meshes.cubed_sphere(6, shuffle_seed=seed)
+        n = len(X)
+        assert n == 6 * 36 + 2 and np.bincount(np.bincount(conn.ravel()))[3] == 8
+        rowp, cols = a2ds.host_pattern(n, conn)
+        rp, cl = orc.pattern(n, conn)
+        assert rowp.tobytes() == rp.tobytes() and cols.tobytes() == cl.tobytes()
+        color, nc = a2ds.host_color_elements(n, conn)
+        assert color.min() == 0 and color.max() == nc - 1
+        for c in range(nc):
+            nodes = conn[color == c].ravel()
+            assert len(np.unique(nodes)) == len(nodes)

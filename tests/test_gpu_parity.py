@@ -597,3 +597,41 @@ def test_mat_combo_vs_separate_assemblies(a2ds, orc):
         free[rowp[nd]:rowp[nd + 1]] = False
     assert relmax(M2[free], 2.0 * M[free]) < 1e-15
     asm.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_unstructured_sphere_vs_oracle(a2ds, orc, mode):
+    """closed sphere from six cube faces: valence-3 corners, randomly permuted node and
+    element numbering, reference-axis transform, ragged last batch (n_elems % 4 != 0 after
+    dropping one element) — everything the structured meshes do not exercise"""
+    conn, X, patch = a2ds.meshes.cubed_sphere(7, shuffle_seed=5)
+    conn = conn[:-1]                       # 293 elements: ragged batch, one open hole
+    n = len(X)
+    Cs, eth = a2ds.iso_shell_tables(t_offset=0.15)
+    mom = a2ds.iso_mass_moments(2718.0, 0.010, 0.15)
+    axis = np.array([0.2, 0.3, 1.0])
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-4)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n); asm.set_nodes(X)
+    asm.set_components(Cs[None], eth[None], temperature=[3.0], transform=a2ds.TRANSFORM_REF_AXIS,
+                       ref_axis=axis)
+    asm.set_mass_moments(mom[None])
+    asm.set_bcs(patch, 0b111011); asm.set_state(u)
+    asm.set_scatter_mode(mode)
+    k = asm.create_mat(); g = asm.create_mat()
+    rowp, cols = asm.mat_pattern(k)
+    rp, cl = orc.pattern(n, conn)
+    assert rowp.tobytes() == rp.tobytes() and cols.tobytes() == cl.tobytes()
+    comp = orc.make_comp(0, Cs, eth, mom, 3.0, 1, axis)
+    bv = np.full(len(patch), 0b111011, dtype=np.int32); bx = np.zeros((len(patch), 6))
+    oargs = (conn, np.zeros(len(conn), dtype=np.int32), [comp], X, u, rowp, cols, patch, bv, bx)
+    r_o, k_o = orc.assemble(1, *oargs)
+    _, g_o = orc.assemble(3, *oargs)
+    _, m_o = orc.assemble(4, *oargs)
+    r = asm.assembleAll(k, g)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(k), k_o) < MAT_TOL
+    assert relmax(asm.mat_values(g), g_o) < THERMAL_G_TOL   # T != 0: the reference's FD noise
+    asm.assembleMatType(a2ds.MASS_MATRIX, g)
+    assert relmax(asm.mat_values(g), m_o) < 1e-13
+    asm.close()
