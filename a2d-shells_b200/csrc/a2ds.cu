@@ -619,28 +619,27 @@ __global__ void k_unpack6(int n, const int *nodes, const double *buf, double *v,
 template <bool COPY>
 __global__ void __launch_bounds__(256) k_axpy(size_t n2, double alpha, const double2 *__restrict__ x,
                                               double2 *__restrict__ y) {
-  const size_t stride = gridDim.x * (size_t)blockDim.x;
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n2; i += 4 * stride) {
-    double2 xv[4], yv[4];
+  // one contiguous 16 KB tile per block (4 x 128-bit per thread), no grid-stride loop: the
+  // DRAM pages of a tile are touched by one block at one time
+  const size_t base = blockIdx.x * (size_t)(4 * 256) + threadIdx.x;
+  double2 xv[4], yv[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      xv[k] = __ldcs(&x[i + k * stride]);
-      if (!COPY) yv[k] = __ldcs(&y[i + k * stride]);
+  for (int k = 0; k < 4; k++) {
+    const size_t i = base + 256 * k;
+    if (i < n2) {
+      xv[k] = x[i];
+      if (!COPY) yv[k] = y[i];
     }
+  }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < 4; k++) {
+    const size_t i = base + 256 * k;
+    if (i < n2) {
       double2 r;
       if (COPY) r = xv[k];
       else { r.x = yv[k].x + alpha * xv[k].x; r.y = yv[k].y + alpha * xv[k].y; }
-      __stcs(&y[i + k * stride], r);
+      y[i] = r;
     }
-  }
-  for (; i < n2; i += stride) {
-    double2 xv = x[i], r;
-    if (COPY) r = xv;
-    else { double2 yv = y[i]; r.x = yv.x + alpha * xv.x; r.y = yv.y + alpha * xv.y; }
-    y[i] = r;
   }
 }
 
@@ -679,6 +678,7 @@ struct MatrixRec {
   std::vector<void *> owned;   // device allocations to free
   std::vector<std::vector<int>> h_rowp, h_cols;  // host copy of the patterns
   std::vector<const int *> d_rowp, d_cols;       // device copy, per block
+  unsigned long long pattern_hash = 0;           // fingerprint of (rowp, cols), 0 = not computed
 };
 
 struct a2ds_ctx {
@@ -1212,10 +1212,26 @@ extern "C" int a2ds_mat_values_dev(a2ds_ctx *c, int mat, int block, double **A_d
   return 0;
 }
 
+// 64-bit FNV-1a over the block patterns: computed once per matrix so that copyValues / axpy
+// do not compare megabytes of indices on the host at every call
+static unsigned long long pattern_fingerprint(MatrixRec &m) {
+  if (m.pattern_hash) return m.pattern_hash;
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&](const std::vector<int> &v) {
+    for (int x : v) { h ^= (unsigned)x; h *= 1099511628211ull; }
+    h ^= 0xffu; h *= 1099511628211ull;
+  };
+  for (const auto &v : m.h_rowp) mix(v);
+  for (const auto &v : m.h_cols) mix(v);
+  m.pattern_hash = h ? h : 1;
+  return m.pattern_hash;
+}
+
 static int same_pattern(a2ds_ctx *c, int a, int b) {
   if (check_mat(c, a) || check_mat(c, b)) return 1;
-  const MatrixRec &A = c->mats[a], &B = c->mats[b];
-  if (A.n_blocks != B.n_blocks || A.total != B.total || A.h_rowp != B.h_rowp || A.h_cols != B.h_cols)
+  MatrixRec &A = c->mats[a], &B = c->mats[b];
+  if (A.n_blocks != B.n_blocks || A.total != B.total ||
+      pattern_fingerprint(A) != pattern_fingerprint(B))
     return fail("matrix operation: the two matrices do not share one non-zero pattern");
   return 0;
 }
@@ -1225,7 +1241,7 @@ extern "C" int a2ds_mat_copy(a2ds_ctx *c, int dst, int src) {
   CU(cudaSetDevice(c->device));
   const size_t n2 = (size_t)c->mats[src].total * 18;
   if (n2)
-    k_axpy<true><<<c->n_sm * 16, 256, 0, c->stream>>>(
+    k_axpy<true><<<(unsigned)((n2 + 1023) / 1024), 256, 0, c->stream>>>(
         n2, 1.0, reinterpret_cast<const double2 *>(c->mats[src].A),
         reinterpret_cast<double2 *>(c->mats[dst].A));
   CU(cudaGetLastError());
@@ -1237,7 +1253,7 @@ extern "C" int a2ds_mat_axpy(a2ds_ctx *c, double alpha, int x, int y) {
   CU(cudaSetDevice(c->device));
   const size_t n2 = (size_t)c->mats[x].total * 18;
   if (n2)
-    k_axpy<false><<<c->n_sm * 16, 256, 0, c->stream>>>(
+    k_axpy<false><<<(unsigned)((n2 + 1023) / 1024), 256, 0, c->stream>>>(
         n2, alpha, reinterpret_cast<const double2 *>(c->mats[x].A),
         reinterpret_cast<double2 *>(c->mats[y].A));
   CU(cudaGetLastError());

@@ -25,3 +25,16 @@ for name, fn, nbytes in (("spmv6", lambda: asm.mat_mult_dev(k, x.data_ptr(), y.d
         fn()
     ms = asm.region_end() / 10
     print(f"{name:6s} {ms:7.3f} ms  {nbytes / ms * 1e-6:8.1f} GB/s  ({nnz} blocks)")
+# torch's own copy / axpy of the same size on the same box, for scale
+a = torch.empty(nnz * 36, dtype=torch.float64, device="cuda").normal_(); b = torch.empty_like(a)
+for name, fn, nbytes in (("torch copy_", lambda: b.copy_(a), nnz * 288 * 2),
+                         ("torch add_", lambda: b.add_(a, alpha=0.5), nnz * 288 * 3)):
+    for _ in range(3):
+        fn()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(10):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"{name:12s} {ms:7.3f} ms  {nbytes / ms * 1e-6:8.1f} GB/s")
