@@ -40,10 +40,10 @@ ALG_BYTES_PER_ELEM = 5320.0      # conn 16 + X 24 + u 48 + res
 REF_FLOPS_PER_ELEM = 508437.0    # reference operation count, res + K + G
 DFMA_PEAK_TFLOPS = 34.1          # measured on this pool's B200 (tools/fp64_peak.cu, profiles/)
 # dram__bytes_read.sum + dram__bytes_write.sum of k_assemble<res,K,G> per element, from the
-# ncu --set full capture at 1 M elements (profiles/r01e_ncu_k_assemble_resKG_1M.txt):
-# 6.05 GB read + 6.18 GB written per launch = 2.3 x the algorithmic bytes (the RED
+# ncu --set full capture at 1 M elements (profiles/r01g_ncu_k_assemble_resKG_1M.txt):
+# 6.39 GB read + 6.37 GB written per launch = 2.4 x the algorithmic bytes (the RED
 # read-modify-write re-reads the zeroed matrices once)
-DRAM_TRAFFIC_PER_ELEM = 12227.8
+DRAM_TRAFFIC_PER_ELEM = 12768.8
 
 
 def measured_peaks():
@@ -344,7 +344,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm,
                          "traffic": DRAM_TRAFFIC_PER_ELEM * n_elems if args.workload == "plate" else None,
-                         "traffic_source": "ncu capture at 1M elements, profiles/r01e_*",
+                         "traffic_source": "ncu capture at 1M elements, profiles/r01g_ncu_k_assemble_resKG_1M.txt",
                          "peak_source": which,
                          "kernel": "k_assemble<res,K,nonlinear>" if nonlinear else "k_assemble<res,K,G>",
                          "kernel_ms": k_ms,
