@@ -689,6 +689,7 @@ struct a2ds_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_state = nullptr, ev_used = nullptr;
   bool state_pending = false;
+  bool halo_pending = false;  // forward ghost exchange deferred until the upload is consumed
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   int n_sm = 0;
   int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
@@ -729,6 +730,10 @@ static int state_wait(a2ds_ctx *c) {
   if (c->state_pending) {
     CU(cudaStreamWaitEvent(c->stream, c->ev_state, 0));
     c->state_pending = false;
+  }
+  if (c->halo_pending) {  // a2ds_halo_forward was called while the upload was in flight
+    c->halo_pending = false;
+    if (halo_exchange(c, c->u, false)) return 1;
   }
   return 0;
 }
@@ -833,6 +838,7 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
   if (upload(&c->elem_comp, c->h_elem_comp.data(), (size_t)n_elems, c->stream)) return 1;
   CU(cudaStreamSynchronize(c->copy_stream));
   c->state_pending = false;
+  c->halo_pending = false;
   cudaFree(c->X); cudaFree(c->u); cudaFree(c->res); cudaFree(c->udd);
   c->udd = nullptr;
   c->X = c->u = c->res = nullptr;
@@ -1402,7 +1408,10 @@ static int halo_exchange(a2ds_ctx *c, double *vec, bool reverse) {
 
 extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
   CU(cudaSetDevice(c->device));
-  if (state_wait(c)) return 1;
+  // With a host upload still in flight the exchange is queued behind it at the first use of
+  // the state (every rank does the same, so the sends and receives still pair up): the
+  // zeroing at the start of the next assembly then overlaps the upload on all ranks.
+  if (c->state_pending) { c->halo_pending = true; return 0; }
   return halo_exchange(c, c->u, false);
 }
 
