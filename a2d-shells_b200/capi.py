@@ -30,7 +30,7 @@ SYMBOLS = [
     "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
     "a2ds_add_jacobian_vec_product", "a2ds_add_jacobian_vec_product_dev",
     "a2ds_set_mass_moments", "a2ds_set_state_rates", "a2ds_assemble_mat_combo",
-    "a2ds_mat_mult_dist_dev",
+    "a2ds_mat_mult_dist_dev", "a2ds_mat_set_halo",
 ]
 
 _LIB = None
@@ -288,6 +288,17 @@ class Assembler:
     def mat_mult_dev(self, mat, x_dev, y_dev, block=0):
         self._chk(self.L.a2ds_mat_mult_dev(self.ctx, C.c_int(mat), C.c_int(block),
                                            C.c_void_p(x_dev), C.c_void_p(y_dev)))
+
+    def mat_set_halo(self, mat, peers, send_lists, recv_lists):
+        """matrix halo plan (ParallelMat flavour): per peer the indices of my ghost-row blocks
+        to send and of the blocks arriving contributions are added to"""
+        peers = _i32(peers)
+        sp = _i32(np.concatenate([[0], np.cumsum([len(x) for x in send_lists])]))
+        rp = _i32(np.concatenate([[0], np.cumsum([len(x) for x in recv_lists])]))
+        sb = _i32(np.concatenate(list(send_lists))) if len(peers) and sp[-1] else _i32([])
+        rb = _i32(np.concatenate(list(recv_lists))) if len(peers) and rp[-1] else _i32([])
+        self._chk(self.L.a2ds_mat_set_halo(self.ctx, C.c_int(mat), C.c_int(len(peers)), _p(peers),
+                                           _p(sp), _p(sb), _p(rp), _p(rb)))
 
     def mat_mult_dist_dev(self, mat, x_dev, y_dev):
         """distributed y = A x (owned rows), halo exchanges inside; device pointers"""

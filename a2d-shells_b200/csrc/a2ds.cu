@@ -679,6 +679,11 @@ struct MatrixRec {
   std::vector<std::vector<int>> h_rowp, h_cols;  // host copy of the patterns
   std::vector<const int *> d_rowp, d_cols;       // device copy, per block
   unsigned long long pattern_hash = 0;           // fingerprint of (rowp, cols), 0 = not computed
+  // matrix halo (ParallelMat flavour): blocks of ghost rows sent to / received from peers
+  bool has_halo = false;
+  std::vector<int> halo_peers, halo_send_ptr, halo_recv_ptr;
+  int *halo_send_blk = nullptr, *halo_recv_blk = nullptr;
+  double *halo_send_buf = nullptr, *halo_recv_buf = nullptr;
 };
 
 struct a2ds_ctx {
@@ -1398,11 +1403,107 @@ static int halo_exchange(a2ds_ctx *c, double *vec, bool reverse) {
     if (nr) NC(ncclRecv(c->recv_buf + 6 * (size_t)up_ptr[p], 6 * (size_t)nr, ncclDouble, c->peers[p], c->comm, c->stream));
   }
   NC(ncclGroupEnd());
-  // reverse: contributions are added in peer order (fixed -> deterministic)
-  if (n_up)
-    k_unpack6<<<(6 * n_up + 255) / 256, 256, 0, c->stream>>>(n_up, up_nodes, c->recv_buf, vec, reverse ? 1 : 0);
+  if (!reverse) {
+    if (n_up)
+      k_unpack6<<<(6 * n_up + 255) / 256, 256, 0, c->stream>>>(n_up, up_nodes, c->recv_buf, vec, 0);
+    c->last_launches += (n_pk ? 1 : 0) + (n_up ? 1 : 0);
+  } else {
+    // reverse: a node shared by three or more ranks receives from several peers, so the
+    // contributions are added one peer after the other, in the fixed peer order
+    // (race free and deterministic; a node occurs at most once in one peer's list)
+    for (int p = 0; p < np; p++) {
+      const int nr = up_ptr[p + 1] - up_ptr[p];
+      if (!nr) continue;
+      k_unpack6<<<(6 * nr + 255) / 256, 256, 0, c->stream>>>(
+          nr, up_nodes + up_ptr[p], c->recv_buf + 6 * (size_t)up_ptr[p], vec, 1);
+      c->last_launches++;
+    }
+    c->last_launches += (n_pk ? 1 : 0);
+  }
   CU(cudaGetLastError());
-  c->last_launches += (n_pk ? 1 : 0) + (n_up ? 1 : 0);
+  return 0;
+}
+
+// ---- matrix halo (TACSParallelMat flavour): ghost rows -> owners, added --------------------
+// TACSMatDistribute::beginAssembly/endAssembly (src/bpmat/TACSMatDistribute.cpp:1036-1176):
+// contributions a rank made to block rows it does not own travel to the owner and are added
+// there.  The plan (which of my blocks go to which peer, and where arriving blocks land) is
+// supplied by the host, which knows the global numbering (a2ds_mat_set_halo).
+__global__ void k_pack36(int n, const int *blk, const double2 *A, double2 *buf) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= 18 * (size_t)n) return;
+  const size_t b = t / 18, e = t - 18 * b;
+  buf[t] = A[18 * (size_t)blk[b] + e];
+}
+__global__ void k_unpack36_add(int n, const int *blk, const double2 *buf, double2 *A) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= 18 * (size_t)n) return;
+  const size_t b = t / 18, e = t - 18 * b;
+  double2 *d = &A[18 * (size_t)blk[b] + e];
+  const double2 v = buf[t];
+  d->x += v.x; d->y += v.y;
+}
+
+static int mat_halo_reverse(a2ds_ctx *c, MatrixRec &m) {
+  if (!m.has_halo) return 0;
+  if (!c->comm) return fail("matrix halo: a2ds_comm_init has not been called");
+  const int np = (int)m.halo_peers.size();
+  const int n_send = m.halo_send_ptr[np];
+  if (n_send)
+    k_pack36<<<(unsigned)((18 * (size_t)n_send + 255) / 256), 256, 0, c->stream>>>(
+        n_send, m.halo_send_blk, reinterpret_cast<const double2 *>(m.A),
+        reinterpret_cast<double2 *>(m.halo_send_buf));
+  NC(ncclGroupStart());
+  for (int p = 0; p < np; p++) {
+    const int ns = m.halo_send_ptr[p + 1] - m.halo_send_ptr[p];
+    const int nr = m.halo_recv_ptr[p + 1] - m.halo_recv_ptr[p];
+    if (ns) NC(ncclSend(m.halo_send_buf + 36 * (size_t)m.halo_send_ptr[p], 36 * (size_t)ns, ncclDouble,
+                        m.halo_peers[p], c->comm, c->stream));
+    if (nr) NC(ncclRecv(m.halo_recv_buf + 36 * (size_t)m.halo_recv_ptr[p], 36 * (size_t)nr, ncclDouble,
+                        m.halo_peers[p], c->comm, c->stream));
+  }
+  NC(ncclGroupEnd());
+  for (int p = 0; p < np; p++) {  // one peer after the other: race free, fixed order
+    const int nr = m.halo_recv_ptr[p + 1] - m.halo_recv_ptr[p];
+    if (!nr) continue;
+    k_unpack36_add<<<(unsigned)((18 * (size_t)nr + 255) / 256), 256, 0, c->stream>>>(
+        nr, m.halo_recv_blk + m.halo_recv_ptr[p],
+        reinterpret_cast<const double2 *>(m.halo_recv_buf + 36 * (size_t)m.halo_recv_ptr[p]),
+        reinterpret_cast<double2 *>(m.A));
+    c->last_launches++;
+  }
+  c->last_launches += n_send ? 1 : 0;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int a2ds_mat_set_halo(a2ds_ctx *c, int mat, int n_peers, const int *peer_rank,
+                                 const int *send_ptr, const int *send_blocks,
+                                 const int *recv_ptr, const int *recv_blocks) {
+  if (check_mat(c, mat)) return 1;
+  CU(cudaSetDevice(c->device));
+  MatrixRec &m = c->mats[mat];
+  if (n_peers < 0) return fail("a2ds_mat_set_halo: bad peer count");
+  const long long ns = n_peers ? send_ptr[n_peers] : 0, nr = n_peers ? recv_ptr[n_peers] : 0;
+  for (long long i = 0; i < ns; i++)
+    if (send_blocks[i] < 0 || send_blocks[i] >= m.total) return fail("a2ds_mat_set_halo: bad send block");
+  for (long long i = 0; i < nr; i++)
+    if (recv_blocks[i] < 0 || recv_blocks[i] >= m.total) return fail("a2ds_mat_set_halo: bad receive block");
+  m.halo_peers.assign(peer_rank, peer_rank + n_peers);
+  m.halo_send_ptr.assign(send_ptr, send_ptr + n_peers + 1);
+  m.halo_recv_ptr.assign(recv_ptr, recv_ptr + n_peers + 1);
+  if (n_peers == 0) { m.halo_send_ptr.assign(1, 0); m.halo_recv_ptr.assign(1, 0); }
+  int *sb = nullptr, *rb = nullptr;
+  if (upload(&sb, send_blocks, (size_t)ns, c->stream)) return 1;
+  if (upload(&rb, recv_blocks, (size_t)nr, c->stream)) return 1;
+  double *sbuf = nullptr, *rbuf = nullptr;
+  CU(cudaMalloc((void **)&sbuf, std::max<size_t>(36 * (size_t)ns, 2) * sizeof(double)));
+  CU(cudaMalloc((void **)&rbuf, std::max<size_t>(36 * (size_t)nr, 2) * sizeof(double)));
+  m.halo_send_blk = sb; m.halo_recv_blk = rb; m.halo_send_buf = sbuf; m.halo_recv_buf = rbuf;
+  if (sb) m.owned.push_back(sb);
+  if (rb) m.owned.push_back(rb);
+  m.owned.push_back(sbuf); m.owned.push_back(rbuf);
+  m.has_halo = n_peers > 0;
   return 0;
 }
 
@@ -1592,6 +1693,11 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
                                                                 c->bc_vals, c->u, c->res, c->n_owned);
     c->last_launches++;
   }
+  // ghost block rows -> owners (only for matrices with a halo plan), then the BCs
+  if (KM && mat_halo_reverse(c, c->mats[kmat])) return 1;
+  if (GM && !(KM && gmat == kmat) && mat_halo_reverse(c, c->mats[gmat])) return 1;
+  if (MM && !(KM && mmat == kmat) && !(GM && mmat == gmat) && mat_halo_reverse(c, c->mats[mmat]))
+    return 1;
   if (KM && apply_mat_bcs(c, kmat)) return 1;
   if (GM && !(KM && gmat == kmat) && apply_mat_bcs(c, gmat)) return 1;
   if (MM && !(KM && mmat == kmat) && !(GM && mmat == gmat) && apply_mat_bcs(c, mmat)) return 1;

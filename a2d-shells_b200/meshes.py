@@ -192,12 +192,20 @@ def cylinder_slab(rank, n_ranks, ntheta, nx, radius=0.2, length=0.4):
                 recv_lists=recv_lists)
 
 
-def partition_rows(conn, n_nodes, elem_rank):
+def partition_rows(conn, n_nodes, elem_rank, matrix_halo=False):
     """Element-wise partition -> per-rank local meshes with TACSCreator's node ownership
     rule: a node belongs to the rank of the first element (in global order) touching it
     (src/TACSCreator.cpp:1156-1205).  Returns a list of dicts per rank:
       conn_local, owned (global ids), ghosts (global ids), elems (global element ids),
-      peers / send_lists / recv_lists (local indices) for the halo exchange."""
+      peers / send_lists / recv_lists (local indices) for the halo exchange.
+    matrix_halo=True prepares the TACSParallelMat flavour as well: the ghosts of a rank then
+    also include every node coupled to one of its owned nodes through ANOTHER rank's
+    elements (the reference's external column map), and each dict gains
+      rowp / cols                     local non-zero pattern: full global rows for the owned
+                                      nodes, the local elements' couplings for ghost rows
+      mat_send_lists / mat_recv_lists per peer (same order as peers): block indices of my
+                                      ghost rows to send / of the blocks arriving ones add to,
+                                      both sorted by (global row, global column)."""
     conn = np.asarray(conn)
     elem_rank = np.asarray(elem_rank)
     n_ranks = int(elem_rank.max()) + 1
@@ -218,13 +226,20 @@ def partition_rows(conn, n_nodes, elem_rank):
         extra = np.nonzero(owner == r)[0]
         owned = np.union1d(owned, extra)
         ghosts = used[owner[used] != r]
+        if matrix_halo:
+            # column nodes of the owned rows that only other ranks' elements bring in
+            grp, gcl = _global_pattern(n_nodes, conn)
+            coupled = np.unique(np.concatenate([gcl[grp[g]:grp[g + 1]] for g in owned])) \
+                if len(owned) else np.zeros(0, dtype=np.int64)
+            ghosts = np.union1d(ghosts, np.setdiff1d(coupled, owned))
         glob = np.concatenate([owned, ghosts])
         lookup = {}
         local_of = np.full(n_nodes, -1, dtype=np.int64)
         local_of[glob] = np.arange(len(glob))
         parts.append(dict(rank=r, elems=elems, owned=owned, ghosts=ghosts, glob=glob,
                           conn_local=local_of[conn[elems]].astype(np.int32),
-                          local_of=local_of, ghost_owner=owner[ghosts]))
+                          local_of=local_of, ghost_owner=owner[ghosts],
+                          ghost_owner_all=owner[ghosts]))
     # halo lists: for each (r, p): ghosts of r owned by p, sorted by global id on both sides
     for r in range(n_ranks):
         P = parts[r]
@@ -239,4 +254,68 @@ def partition_rows(conn, n_nodes, elem_rank):
         P["peers"] = np.asarray(peers, dtype=np.int32)
         P["send_lists"] = send_lists
         P["recv_lists"] = recv_lists
+    if matrix_halo:
+        grp, gcl = _global_pattern(n_nodes, conn)
+        for P in parts:
+            # local pattern: couplings of the local elements, plus the full global row of
+            # every owned node (all its columns are local by construction)
+            nl = len(P["glob"])
+            rows = [set() for _ in range(nl)]
+            for e in P["conn_local"]:
+                for a in e:
+                    rows[a].update(int(b) for b in e)
+            for l, g in enumerate(P["owned"]):
+                rows[l].update(int(x) for x in P["local_of"][gcl[grp[g]:grp[g + 1]]])
+            rowp = np.zeros(nl + 1, dtype=np.int32)
+            rowp[1:] = np.cumsum([len(x) for x in rows])
+            P["rowp"] = rowp
+            P["cols"] = np.array([c for x in rows for c in sorted(x)], dtype=np.int32)
+            # blocks of ghost rows that carry local element contributions, by owner
+            P["_ghost_blocks"] = {}
+            for l in range(len(P["owned"]), nl):
+                elem_cols = set()
+                for e in P["conn_local"]:
+                    if l in e:
+                        elem_cols.update(int(b) for b in e)
+                if not elem_cols:
+                    continue
+                own = int(P["ghost_owner_all"][l - len(P["owned"])])
+                lst = P["_ghost_blocks"].setdefault(own, [])
+                for k in range(rowp[l], rowp[l + 1]):
+                    if int(P["cols"][k]) in elem_cols:
+                        lst.append((int(P["glob"][l]), int(P["glob"][P["cols"][k]]), k))
+        for P in parts:
+            P["mat_send_lists"] = []; P["mat_recv_lists"] = []
+            for p in P["peers"]:
+                mine = sorted(P["_ghost_blocks"].get(int(p), []))
+                P["mat_send_lists"].append(np.array([k for _, _, k in mine], dtype=np.int32))
+                Q = parts[int(p)]
+                theirs = sorted(Q["_ghost_blocks"].get(P["rank"], []))
+                dest = []
+                for grow, gcol, _ in theirs:
+                    lr, lc = int(P["local_of"][grow]), int(P["local_of"][gcol])
+                    seg = P["cols"][P["rowp"][lr]:P["rowp"][lr + 1]]
+                    k = int(np.searchsorted(seg, lc))
+                    assert k < len(seg) and seg[k] == lc, "owner pattern misses an arriving block"
+                    dest.append(P["rowp"][lr] + k)
+                P["mat_recv_lists"].append(np.array(dest, dtype=np.int32))
     return parts
+
+
+_pattern_cache = {}
+
+
+def _global_pattern(n_nodes, conn):
+    """node-to-node couplings of the whole mesh (rowp, cols), cached per call site"""
+    key = (n_nodes, conn.shape[0], int(conn[:, 0].sum()), int(conn[-1, -1]))
+    if key not in _pattern_cache:
+        rows = [set() for _ in range(n_nodes)]
+        for e in np.asarray(conn):
+            for a in e:
+                rows[a].update(int(b) for b in e)
+        rowp = np.zeros(n_nodes + 1, dtype=np.int64)
+        rowp[1:] = np.cumsum([len(x) for x in rows])
+        cols = np.array([c for x in rows for c in sorted(x)], dtype=np.int64)
+        _pattern_cache.clear()
+        _pattern_cache[key] = (rowp, cols)
+    return _pattern_cache[key]

@@ -209,6 +209,22 @@ int a2ds_set_halo(a2ds_ctx *ctx, int n_peers, const int *peer_rank, const int *s
                   const int *send_nodes, const int *recv_ptr, const int *recv_nodes);
 /* forward: owner -> ghost copies of the state (beginForward/endForward) */
 int a2ds_halo_forward(a2ds_ctx *ctx);
+
+/* Matrix halo for the TACSParallelMat flavour (TACSMatDistribute::beginAssembly/endAssembly,
+ * src/bpmat/TACSMatDistribute.cpp:1036-1176): after the element loop the blocks a rank
+ * contributed to block rows it does not own are sent to the owners and added there, so
+ * that every rank's OWNED rows are fully assembled.  The plan comes from the host, which
+ * knows the global numbering: per peer, send_blocks = indices (into the concatenated block
+ * array of this matrix) of my ghost-row blocks, recv_blocks = indices of the blocks the
+ * peer's contributions are added to, both in one order agreed by the two sides (e.g.
+ * sorted by (global row, global column)).  The owner's pattern must contain every
+ * arriving block, i.e. its local node set includes the column nodes of those contributions
+ * (the reference's external column map does the same).  Once set, every assemble call on
+ * this matrix performs the exchange before the boundary conditions.  Matrices without a
+ * plan keep the TACSSchurMat convention (interface rows unassembled per rank). */
+int a2ds_mat_set_halo(a2ds_ctx *ctx, int mat, int n_peers, const int *peer_rank,
+                      const int *send_ptr, const int *send_blocks, const int *recv_ptr,
+                      const int *recv_blocks);
 /* reverse: ghost residual contributions added to their owners, done inside
  * a2ds_assemble_* when a halo is set (beginReverse/endReverse, TACS_ADD_VALUES) */
 

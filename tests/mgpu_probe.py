@@ -98,7 +98,90 @@ def main():
         print("MGPU_RESULT", world, *worst)
         assert worst[0] < 1e-12 and worst[1] < 1e-10 and worst[2] < 1e-10, worst
         print("MGPU_OK")
+    parallel_mat_flavour(rank, world, local)
     dist.destroy_process_group()
+
+
+def parallel_mat_flavour(rank, world, local):
+    """TACSParallelMat flavour: generic element partition (column strips, so every rank has
+    two neighbours at world > 2), matrix halo -> the OWNED rows of every rank must equal the
+    rows of the matrix assembled on one GPU, for K (Jacobian), G and M"""
+    nx, ny = 4 * world, 9
+    conn, X, bcn = a2ds.meshes.plate(nx, ny, bump=3e-2)
+    n = len(X)
+    elem_rank = (np.arange(nx * ny) % nx) // 4
+    P = a2ds.meshes.partition_rows(conn, n, elem_rank, matrix_halo=True)[rank]
+    Cs, eth = a2ds.iso_shell_tables(t_offset=0.1)
+    mom = a2ds.iso_mass_moments(2718.0, 0.01, 0.1)
+    glob = P["glob"]; no = len(P["owned"]); nl = len(glob)
+    asm = a2ds.Assembler(local)
+    asm.set_mesh(P["conn_local"], nl, no); asm.set_nodes(X[glob])
+    asm.set_components(Cs[None], eth[None]); asm.set_mass_moments(mom[None])
+    bc_local = P["local_of"][bcn]; bc_local = bc_local[bc_local >= 0].astype(np.int32)
+    asm.set_bcs(bc_local, 63)
+    uid = [asm.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    asm.comm_init(world, rank, uid[0])
+    asm.set_halo(P["peers"], P["send_lists"], P["recv_lists"])
+    ident = np.arange(nl, dtype=np.int32)
+    mats = []
+    for _ in range(3):
+        m = asm.create_mat_from_pattern([dict(nrows=nl, rowp=P["rowp"], cols=P["cols"], row_map=ident,
+                                              col_map=ident, ident=1)])
+        asm.mat_set_halo(m, P["peers"], P["mat_send_lists"], P["mat_recv_lists"])
+        mats.append(m)
+    asm.set_state(a2ds.meshes.seeded_state(glob[:no], 1e-5)); asm.halo_forward()
+    res = asm.assembleJacobian(1.0, 0.0, 0.0, mats[0])
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, mats[1])
+    asm.assembleMatType(a2ds.MASS_MATRIX, mats[2])
+    vals = [asm.mat_values(m) for m in mats]
+    # ParallelMat::mult with the assembled owned rows: only the forward exchange of x
+    x = torch.full((nl, 6), float("nan"), dtype=torch.float64, device="cuda")
+    x[:no] = torch.from_numpy(a2ds.meshes.seeded_state(glob[:no] + 4242, 1.0)).cuda()
+    asm.set_state_dev(nl, x.data_ptr()); asm.halo_forward()       # reuse the state halo for x
+    y = torch.zeros_like(x)
+    asm.mat_mult_dev(mats[0], asm.state_dev(), y.data_ptr())
+    asm.synchronize()
+    out = dict(glob=glob, no=no, rowp=P["rowp"], cols=P["cols"], res=res, vals=vals,
+               y=y[:no].cpu().numpy())
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(out, gathered, dst=0)
+    asm.close()
+    if rank != 0:
+        return
+    ref = a2ds.Assembler(local)
+    ref.set_mesh(conn, n); ref.set_nodes(X); ref.set_components(Cs[None], eth[None])
+    ref.set_mass_moments(mom[None]); ref.set_bcs(bcn, 63)
+    ref.set_state(a2ds.meshes.seeded_state(np.arange(n), 1e-5))
+    k = ref.create_mat(); g = ref.create_mat(); mm = ref.create_mat()
+    r_all = ref.assembleJacobian(1.0, 0.0, 0.0, k)
+    ref.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, g)
+    ref.assembleMatType(a2ds.MASS_MATRIX, mm)
+    rp, cl = ref.mat_pattern(k)
+    full = [ref.mat_values(m) for m in (k, g, mm)]
+    ref.close()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import bcsr_matvec
+    y_all = bcsr_matvec(full[0], rp, cl, a2ds.meshes.seeded_state(np.arange(n) + 4242, 1.0))
+    worst = [0.0, 0.0, 0.0, 0.0, 0.0]
+    rows = 0
+    for o in gathered:
+        gl, no = o["glob"], o["no"]
+        worst[3] = max(worst[3], np.abs(o["res"] - r_all[gl[:no]]).max() / np.abs(r_all).max())
+        worst[4] = max(worst[4], np.abs(o["y"] - y_all[gl[:no]]).max() / np.abs(y_all).max())
+        for lr in range(no):
+            gr = int(gl[lr]); rows += 1
+            assert o["rowp"][lr + 1] - o["rowp"][lr] == rp[gr + 1] - rp[gr]
+            for kb in range(o["rowp"][lr], o["rowp"][lr + 1]):
+                gc = int(gl[o["cols"][kb]])
+                j = rp[gr] + int(np.searchsorted(cl[rp[gr]:rp[gr + 1]], gc))
+                assert cl[j] == gc
+                for t in range(3):
+                    worst[t] = max(worst[t], np.abs(o["vals"][t][kb] - full[t][j]).max() /
+                                   np.abs(full[t]).max())
+    print("MGPU_PARALLELMAT", world, rows, *worst)
+    assert rows == n and max(worst[:3]) < 1e-10 and worst[3] < 1e-12 and worst[4] < 1e-12, worst
+    print("MGPU_PARALLELMAT_OK")
 
 
 if __name__ == "__main__":

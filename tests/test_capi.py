@@ -165,3 +165,46 @@ def test_pattern_and_colouring_on_unstructured_mesh(a2ds, orc):
         for c in range(nc):
             nodes = conn[color == c].ravel()
             assert len(np.unique(nodes)) == len(nodes)
+
+
+def test_matrix_halo_plan_assembles_owned_rows(a2ds, orc):
+    """ParallelMat flavour on a 2 x 2 partition (the centre node is shared by four ranks):
+    per-rank matrices from the oracle on the local meshes and patterns of
+    partition_rows(matrix_halo=True), the block exchange of a2ds_mat_set_halo emulated in
+    numpy -> every rank's owned rows equal the rows of the globally assembled matrix."""
+    nx = 6
+    conn, X, _ = a2ds.meshes.plate(nx, nx, bump=4e-2)
+    n = len(X)
+    ei = np.arange(nx * nx) % nx; ej = np.arange(nx * nx) // nx
+    elem_rank = (ei >= nx // 2).astype(int) + 2 * (ej >= nx // 2).astype(int)
+    parts = a2ds.meshes.partition_rows(conn, n, elem_rank, matrix_halo=True)
+    Cs, eth = a2ds.iso_shell_tables()
+    comp = orc.make_comp(0, Cs, eth)
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-5)
+    rowp_g, cols_g = orc.pattern(n, conn)
+    _, K_g = orc.assemble(2, conn, np.zeros(len(conn), dtype=np.int32), [comp], X, u, rowp_g, cols_g)
+    K_loc = []
+    for P in parts:
+        _, K = orc.assemble(2, P["conn_local"], np.zeros(len(P["conn_local"]), dtype=np.int32),
+                            [comp], X[P["glob"]], u[P["glob"]], P["rowp"], P["cols"])
+        K_loc.append(K)
+    # the exchange: sender packs its listed blocks, receiver adds them at its listed blocks
+    recv = [K.copy() for K in K_loc]
+    for P in parts:
+        for ip, p in enumerate(P["peers"]):
+            Q = parts[int(p)]
+            iq = list(Q["peers"]).index(P["rank"])
+            src = K_loc[P["rank"]][P["mat_send_lists"][ip]]
+            dst = Q["mat_recv_lists"][iq]
+            assert len(src) == len(dst)
+            np.add.at(recv[int(p)], dst, src)
+    seen = 0
+    for P, K in zip(parts, recv):
+        for l, g in enumerate(P["owned"]):
+            row_l = {int(P["glob"][c]): K[k] for k, c in
+                     zip(range(P["rowp"][l], P["rowp"][l + 1]), P["cols"][P["rowp"][l]:P["rowp"][l + 1]])}
+            for k in range(rowp_g[g], rowp_g[g + 1]):
+                assert np.abs(row_l[int(cols_g[k])] - K_g[k]).max() <= 1e-13 * np.abs(K_g).max()
+            assert len(row_l) == rowp_g[g + 1] - rowp_g[g]
+            seen += 1
+    assert seen == n

@@ -21,10 +21,13 @@ def _n_gpus():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_gpu() or _n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_two_rank_assembly_matches_single_gpu(world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533",
            os.path.join(ROOT, "tests", "mgpu_probe.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "MGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MGPU_PARALLELMAT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
