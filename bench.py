@@ -39,6 +39,11 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_PER_ELEM = 5320.0      # conn 16 + X 24 + u 48 + res 48 + K 2592 + G 2592
 REF_FLOPS_PER_ELEM = 508437.0    # reference operation count, res + K + G
 DFMA_PEAK_TFLOPS = 34.1          # measured on this pool's B200 (tools/fp64_peak.cu, profiles/)
+# FP64 operations the fused kernel EXECUTES per element (lean formulation), from the same
+# ncu capture: 13 419 DFMA + 10 232 DMUL + 3 483 DADD thread instructions (40.6 kflop) and
+# 126 DMMA.8x8x4 (64.5 kflop).  FP64 + DMMA together keep the one FP64 pipe 50.6 % busy.
+EXEC_FLOPS_PER_ELEM = 105065.0
+FP64_PIPE_BUSY = 0.506
 # dram__bytes_read.sum + dram__bytes_write.sum of k_assemble<res,K,G> per element, from the
 # ncu --set full capture at 1 M elements (profiles/r01g_ncu_k_assemble_resKG_1M.txt):
 # 6.39 GB read + 6.37 GB written per launch = 2.4 x the algorithmic bytes (the RED
@@ -353,7 +358,15 @@ def main():
                      "dfma_peak_tflops_measured": DFMA_PEAK_TFLOPS,
                      "reference_flops_per_element": 171290.0 if nonlinear else REF_FLOPS_PER_ELEM,
                      "reference_count_tflops": (171290.0 if nonlinear else REF_FLOPS_PER_ELEM) *
-                     n_elems / (k_ms * 1e-3) / 1e12},
+                     n_elems / (k_ms * 1e-3) / 1e12,
+                     "executed_flops_per_element": None if nonlinear or args.workload != "plate"
+                     else EXEC_FLOPS_PER_ELEM,
+                     "executed_tflops": None if nonlinear or args.workload != "plate"
+                     else EXEC_FLOPS_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12,
+                     "frac_of_dfma_peak": None if nonlinear or args.workload != "plate"
+                     else EXEC_FLOPS_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12 / DFMA_PEAK_TFLOPS,
+                     "pipe_busy_ncu": None if nonlinear or args.workload != "plate"
+                     else FP64_PIPE_BUSY},
             "e2e": {"value": total_elems / (e2e_ms * 1e-3), "unit": "elements/s",
                     "h2d_bytes_per_step": int(u_host.numel() * 8 * world),
                     "d2h_bytes_per_step": int(r_host.numel() * 8 * world),

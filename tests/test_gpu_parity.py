@@ -635,3 +635,54 @@ def test_unstructured_sphere_vs_oracle(a2ds, orc, mode):
     asm.assembleMatType(a2ds.MASS_MATRIX, g)
     assert relmax(asm.mat_values(g), m_o) < 1e-13
     asm.close()
+
+
+def test_error_behaviour_is_loud(a2ds):
+    """misuse is reported through the return code / a2ds_last_error (raised as A2dsError by
+    the ctypes face) instead of being printed and ignored as the reference does"""
+    asm = a2ds.Assembler(0)
+    with pytest.raises(a2ds.A2dsError):           # nothing set yet
+        asm.assembleRes()
+    with pytest.raises(a2ds.A2dsError):
+        asm.create_mat()
+    conn, X, bcn = a2ds.meshes.plate(4, 3)
+    n = len(X)
+    bad = conn.copy(); bad[0, 0] = n                # node outside the local range
+    with pytest.raises(a2ds.A2dsError):
+        asm.set_mesh(bad, n)
+    asm.set_mesh(conn, n); asm.set_nodes(X)
+    with pytest.raises(a2ds.A2dsError):           # components missing
+        asm.assembleRes()
+    Cs, eth = a2ds.iso_shell_tables()
+    with pytest.raises(a2ds.A2dsError):           # unknown element class
+        asm.set_components(Cs[None], eth[None], elem_class=[5])
+    asm.set_components(Cs[None], eth[None])
+    with pytest.raises(a2ds.A2dsError):           # state of the wrong length
+        asm.set_state(np.zeros((n - 1, 6)))
+    k = asm.create_mat()
+    with pytest.raises(a2ds.A2dsError):           # unknown matrix id
+        asm.assembleMatType(a2ds.STIFFNESS_MATRIX, k + 7)
+    # a pattern that misses an element block is refused when the matrix is created
+    rowp, cols = asm.mat_pattern(k)
+    keep = np.ones(len(cols), dtype=bool); keep[rowp[5]] = False
+    rowp2 = rowp.copy(); rowp2[6:] -= 1
+    ident = np.arange(n, dtype=np.int32)
+    with pytest.raises(a2ds.A2dsError):
+        asm.create_mat_from_pattern([dict(nrows=n, rowp=rowp2, cols=cols[keep], row_map=ident,
+                                          col_map=ident)])
+    # matrix algebra across different patterns is refused
+    other = a2ds.Assembler(0)
+    c2, X2, _ = a2ds.meshes.plate(3, 3)
+    other.set_mesh(c2, len(X2)); other.set_nodes(X2); other.set_components(Cs[None], eth[None])
+    small = asm.create_mat_from_pattern([dict(nrows=n, rowp=rowp, cols=cols, row_map=ident,
+                                              col_map=ident)])
+    asm.mat_copy(small, k)                          # same pattern: fine
+    with pytest.raises(a2ds.A2dsError):
+        asm.mat_set_halo(k, [0], [np.array([len(cols)], dtype=np.int32)], [np.zeros(0, dtype=np.int32)])
+    with pytest.raises(a2ds.A2dsError):           # unknown scatter mode
+        asm.set_scatter_mode(9)
+    # the context is still usable after all of that
+    asm.set_state(a2ds.meshes.seeded_state(np.arange(n), 1e-5))
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, k)
+    assert np.isfinite(r).all() and np.abs(asm.mat_values(k)).max() > 0
+    other.close(); asm.close()
