@@ -15,6 +15,7 @@ TRANSFORM_NATURAL = 0
 TRANSFORM_REF_AXIS = 1
 SCATTER_ATOMIC = 0
 SCATTER_COLORED = 1
+SCATTER_ATOMIC_COLOR_ORDER = 2
 
 # every symbol include/a2ds.h declares (tests check the library exports them all)
 SYMBOLS = [

@@ -76,6 +76,7 @@ struct KParams {
   double *jvp_y;
   double jvp_scale;
   int scratch_bytes;
+  int *work_counter;     // dynamic batch scheduling: next batch index (zeroed per launch)
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -242,7 +243,6 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     k_assemble(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
   WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
   ElemWork &wk = ws.work;
   const bool PF = GMAT || NL;  // full scratch + asynchronous prefetch of the next batch
@@ -252,7 +252,6 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
   const bool need_state = GMAT || NL;
 
   const int n_groups = (p.n_list + NB - 1) / NB;
-  const int stride = gridDim.x * warps_per_block;
 
   // element id and node id this lane is responsible for in a batch: lane = 4 j + m
   auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
@@ -294,17 +293,30 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     if ((lane & 3) == 0 && lane < 4 * NB && e_l >= 0) cp_async4(&rb.comp[lane >> 2], &p.elem_comp[e_l]);
   };
 
-  int grp = blockIdx.x * warps_per_block + warp;
+  // dynamic scheduling: warps draw the next batch from one counter, so that the batches in
+  // flight at any time stay close together in the element order (L2 locality of the
+  // read-modify-write scatter) however the warps drift
+  auto next_group = [&]() {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(p.work_counter, 1);
+    return __shfl_sync(FULL, g, 0);
+  };
+  int grp = next_group();
+  int grp_nxt = PF ? next_group() : 0;
   int buf = 0;
   int e_cur, nd_cur;
   batch_ids(grp, e_cur, nd_cur);
   if (PF && grp < n_groups) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
-  for (; grp < n_groups; grp += stride, buf ^= 1) {
+  for (; grp < n_groups; buf ^= 1) {
+    // the draw for the trip after this one (after next with prefetch) is issued now and read
+    // at the end of the trip: its latency never shows
+    int drawn = 0;
+    if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
     const int base = grp * NB;
     const int cnt = min(NB, p.n_list - base);
     // ids of the NEXT batch: requested now, consumed after the geometry phases
     int e_nxt = -1, nd_nxt = 0;
-    if (PF) batch_ids(grp + stride, e_nxt, nd_nxt);
+    if (PF) batch_ids(grp_nxt, e_nxt, nd_nxt);
 
     // ---- the batch gathered during the previous trip (or right now without prefetch) -----
     if (!PF) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
                  need_state ? &ws.Pq[j][lane & 3][0] : (double *)0);
     }
     // start the gather of the next batch into the other raw buffer
-    if (PF && grp + stride < n_groups)
+    if (PF && grp_nxt < n_groups)
       issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ? 0 : 1], e_nxt, nd_nxt);
     if (PF) { e_cur = e_nxt; nd_cur = nd_nxt; }
     __syncwarp();
@@ -439,7 +451,9 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       }
       __syncwarp();
     }
-    if (!PF) batch_ids(grp + stride, e_cur, nd_cur);
+    drawn = __shfl_sync(FULL, drawn, 0);
+    if (PF) { grp = grp_nxt; grp_nxt = drawn; }
+    else { grp = drawn; batch_ids(grp, e_cur, nd_cur); }
   }
 }
 
@@ -704,6 +718,7 @@ struct a2ds_ctx {
   std::vector<double> h_mom;          // mass moments per component (a2ds_set_mass_moments)
   std::vector<CompData> h_comps;
   double *X = nullptr, *u = nullptr, *res = nullptr;
+  int *work_counter = nullptr;   // one int, zeroed before every k_assemble launch
   double *udd = nullptr;  // second time derivative of the state (null until set)
   CompData *comps = nullptr;
   int *bc_nodes = nullptr, *bc_vars = nullptr;
@@ -986,7 +1001,8 @@ extern "C" int a2ds_set_bcs(a2ds_ctx *c, int n_bc, const int *nodes, const int *
 }
 
 extern "C" int a2ds_set_scatter_mode(a2ds_ctx *c, int mode) {
-  if (mode != A2DS_SCATTER_ATOMIC && mode != A2DS_SCATTER_COLORED)
+  if (mode != A2DS_SCATTER_ATOMIC && mode != A2DS_SCATTER_COLORED &&
+      mode != A2DS_SCATTER_ATOMIC_COLOR_ORDER)
     return fail("a2ds_set_scatter_mode: unknown mode");
   if (mode != c->scatter_mode) free_lists(c);
   c->scatter_mode = mode;
@@ -1030,21 +1046,33 @@ static int build_lists(a2ds_ctx *c) {
       return fail("assemble: element component index out of range");
   std::vector<int> color;
   int ncol = 1;
-  if (c->scatter_mode == A2DS_SCATTER_COLORED)
+  if (c->scatter_mode != A2DS_SCATTER_ATOMIC)
     color_elements(c->n_nodes, c->n_elems, c->h_conn.data(), color, ncol);
+  // colour order in ONE launch: the lists of the colours are concatenated, so that elements
+  // in flight together rarely share a node (fewer RED collisions in L2), without the launch
+  // boundaries (and the reproducibility) of the coloured mode
+  const bool one_launch = c->scatter_mode == A2DS_SCATTER_ATOMIC_COLOR_ORDER;
+  const int ncol_color = ncol;
+  if (one_launch) ncol = 1;
   c->n_colors = ncol;
   for (int k = 0; k < 2; k++) {
     std::vector<std::vector<int>> lists(ncol);
-    for (int e = 0; e < c->n_elems; e++)
-      if (c->h_class[c->h_elem_comp[e]] == k)
-        lists[c->scatter_mode == A2DS_SCATTER_COLORED ? color[e] : 0].push_back(e);
+    if (one_launch) {
+      for (int col = 0; col < ncol_color; col++)
+        for (int e = 0; e < c->n_elems; e++)
+          if (color[e] == col && c->h_class[c->h_elem_comp[e]] == k) lists[0].push_back(e);
+    } else {
+      for (int e = 0; e < c->n_elems; e++)
+        if (c->h_class[c->h_elem_comp[e]] == k)
+          lists[c->scatter_mode == A2DS_SCATTER_COLORED ? color[e] : 0].push_back(e);
+    }
     c->list_dev[k].assign(ncol, nullptr);
     c->list_len[k].assign(ncol, 0);
     for (int col = 0; col < ncol; col++) {
       c->list_len[k][col] = (int)lists[col].size();
       if (lists[col].empty()) continue;
       // the identity list needs no indirection
-      if ((int)lists[col].size() == c->n_elems) continue;
+      if ((int)lists[col].size() == c->n_elems && !one_launch) continue;
       if (upload(&c->list_dev[k][col], lists[col].data(), lists[col].size(), c->stream)) return 1;
     }
   }
@@ -1547,6 +1575,9 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   }
   const int wpb = best_wpb, per_sm = best_per_sm;
   const size_t smem = per_warp * (size_t)wpb;
+  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, sizeof(int)));
+  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  p.work_counter = c->work_counter;
   const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
   kern<<<grid, wpb * 32, smem, c->stream>>>(p);

@@ -203,6 +203,9 @@ def main():
                          "per GPU, nonlinear Newton tangent res+K (configs[2], strong scaling)")
     ap.add_argument("--ref-nx", type=int, default=250, help="plate side of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored", "color-order"],
+                    help="atomic: one launch, RED order as it comes; colored: one launch per "
+                         "element colour, bit-reproducible")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -251,6 +254,9 @@ def main():
         asm.comm_init(world, rank, uid[0])
         asm.set_halo(slab["peers"], slab["send_lists"], slab["recv_lists"])
     kmat = asm.create_mat(); gmat = asm.create_mat()
+    if args.scatter != "atomic":
+        asm.set_scatter_mode(a2ds.SCATTER_COLORED if args.scatter == "colored"
+                             else a2ds.SCATTER_ATOMIC_COLOR_ORDER)
 
     # pinned host buffers: the state comes from the host each e2e step, the residual goes back
     u_host = torch.empty((n_owned, 6), dtype=torch.float64, pin_memory=True)
@@ -345,7 +351,7 @@ def main():
                 "workload": wl,
                 "elements_per_gpu": n_elems, "partition": f"{world} row slabs, first-touch ownership",
                 "l2": "outputs (2 x 2.6 GB BCSR) and inputs exceed the 126 MB L2 every step",
-                "scatter": "atomic"},
+                "scatter": args.scatter},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm,
                          "traffic": DRAM_TRAFFIC_PER_ELEM * n_elems if args.workload == "plate" else None,

@@ -53,6 +53,9 @@ typedef struct a2ds_ctx a2ds_ctx;
    fixed colour order (bit-reproducible run to run) */
 #define A2DS_SCATTER_ATOMIC 0
 #define A2DS_SCATTER_COLORED 1
+/* atomics, one launch, elements visited colour by colour: elements in flight together rarely
+   share a node (fewer collisions of the atomic adds); not bit-reproducible */
+#define A2DS_SCATTER_ATOMIC_COLOR_ORDER 2
 
 const char *a2ds_last_error(void);
 const char *a2ds_version(void);

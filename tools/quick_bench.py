@@ -11,6 +11,8 @@ Cs, eth = a2ds.iso_shell_tables()
 asm = a2ds.Assembler(0)
 asm.set_mesh(conn, n); asm.set_nodes(X); asm.set_components(Cs[None], eth[None]); asm.set_state(u)
 asm.set_bcs(bcn, 63)
+if len(sys.argv) > 2 and sys.argv[2] == "colored":
+    asm.set_scatter_mode(a2ds.SCATTER_COLORED)   # one launch per element colour, bit-reproducible
 asm.set_mass_moments(a2ds.iso_mass_moments()[None])
 import torch
 xd = torch.randn(n, 6, dtype=torch.float64, device="cuda"); yd = torch.zeros_like(xd)
