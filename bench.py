@@ -41,14 +41,14 @@ REF_FLOPS_PER_ELEM = 508437.0    # reference operation count, res + K + G (SURVE
 DFMA_PEAK_TFLOPS = 34.1          # measured on this pool's B200 (tools/fp64_peak.cu, profiles/)
 # FP64 operations the fused kernel EXECUTES per element (lean formulation), from the same
 # ncu capture: 13 419 DFMA + 10 232 DMUL + 3 483 DADD thread instructions (40.6 kflop) and
-# 126 DMMA.8x8x4 (64.5 kflop).  FP64 + DMMA together keep the one FP64 pipe 50.6 % busy.
+# 126 DMMA.8x8x4 (64.5 kflop).  FP64 + DMMA together keep the one FP64 pipe 50.7 % busy.
 EXEC_FLOPS_PER_ELEM = 105065.0
-FP64_PIPE_BUSY = 0.506
+FP64_PIPE_BUSY = 0.507
 # dram__bytes_read.sum + dram__bytes_write.sum of k_assemble<res,K,G> per element, from the
-# ncu --set full capture at 1 M elements (profiles/r01g_ncu_k_assemble_resKG_1M.txt):
-# 6.39 GB read + 6.37 GB written per launch = 2.4 x the algorithmic bytes (the RED
+# ncu --set full capture at 1 M elements (profiles/r01i_ncu_k_assemble_resKG_1M.txt):
+# 5.46 GB read + 5.18 GB written per launch = 2.0 x the algorithmic bytes (the RED
 # read-modify-write re-reads the zeroed matrices once)
-DRAM_TRAFFIC_PER_ELEM = 12768.8
+DRAM_TRAFFIC_PER_ELEM = 10637.8
 
 
 def measured_peaks():
@@ -355,7 +355,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm,
                          "traffic": DRAM_TRAFFIC_PER_ELEM * n_elems if args.workload == "plate" else None,
-                         "traffic_source": "ncu capture at 1M elements, profiles/r01g_ncu_k_assemble_resKG_1M.txt",
+                         "traffic_source": "ncu capture at 1M elements, profiles/r01i_ncu_k_assemble_resKG_1M.txt",
                          "peak_source": which,
                          "kernel": "k_assemble<res,K,nonlinear>" if nonlinear else "k_assemble<res,K,G>",
                          "kernel_ms": k_ms,
