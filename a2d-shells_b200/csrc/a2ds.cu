@@ -1,15 +1,19 @@
 // a2ds.cu — CUDA kernels (sm_100a) and the C ABI of liba2ds_b200.so.
 //
-// Hot kernel: k_assemble<RES, KMAT, GMAT, NL>.  One warp owns one MITC4 element:
-//   1. gather the 4 nodes' coordinates and state (coalesced by node, 24/48 B rows)
-//   2. node phase, column phase, stress phase: mitc4_math.h, FP64 FMA pipe
-//   3. the 24x24 contractions  K = B^T (w C B),  G = B1^T W + W^T B1  as FP64
-//      tensor-core MMAs (mma.sync m8n8k4 f64 -> DMMA.8x8x4), operands staged in
-//      shared memory [dof][36] (conflict-free fragment loads), accumulators in
-//      registers, only the upper block triangle is computed
-//   4. stage the element matrices in shared memory, add the geometric-stiffness
-//      3x3 blocks, then scatter with coalesced RED.E.ADD.F64 through a
-//      precomputed element -> BCSR block offset table (16 offsets per element)
+// Hot kernel: k_assemble<RES, KMAT, GMAT, NL>.  A warp draws batches of 4 MITC4 elements from
+// a work counter and, per batch:
+//   1. gathers the nodes' coordinates, state and block offsets (cp.async; double-buffered for
+//      the geometric-stiffness / nonlinear variants)
+//   2. node phase and Gauss-point phase with one lane per (element, node) / (element, point)
+//   3. then element by element with all 32 lanes: strain-matrix columns in registers
+//      (mitc4_math.h, FP64 FMA pipe) which ARE the fragments of the 24x24 contractions
+//      K = B^T (w C B),  Z = B1^T W  on the FP64 tensor path (mma.sync m8n8k4 f64 ->
+//      DMMA.8x8x4), accumulators in registers, upper tiles only for the symmetric K
+//   4. stages the element matrices in shared memory, adds the geometric-stiffness 3x3
+//      blocks (G = Z + Z^T + blocks), then scatters with full-warp RED.E.ADD.F64 through a
+//      precomputed element -> BCSR block offset table (16 offsets per element per matrix)
+// k_mass: mass matrix / inertial residual.  k_spmv6, k_axpy, k_mat_bcs: the matrix algebra of
+// the buckling flow.  k_pack6/k_unpack6, k_pack36/k_unpack36_add: vector and matrix halos.
 // Roofline notes live in DESIGN.md.
 #include <cuda_runtime.h>
 #include <nccl.h>

@@ -6,10 +6,10 @@
 // ElemWork records that live in shared memory.  Node and Gauss-point phases are run for a
 // small batch of elements at once (one lane per node / per Gauss point), the column,
 // contraction and scatter phases then take the elements of the batch one at a time with
-// all 32 lanes.  The functions below are the phase bodies.  They are written against plain pointers so that the very same
-// code can be stepped lane by lane on the host (tests/host_emul.cpp) — the CUDA
-// kernel in assemble.cu only adds the warp synchronisation between phases, the
-// DMMA contraction and the scatter.
+// all 32 lanes.  The functions below are the phase bodies.  They are written against plain
+// pointers so that the very same code can be stepped lane by lane on the host
+// (tests/host_emul.cpp) — the CUDA kernel in a2ds.cu only adds the warp synchronisation
+// between phases, the DMMA contraction and the scatter.
 //
 // What is computed (reference: TACSShellElement<Quad2x2, QuadBasis<2>,
 // LinearizedRotation, Linear|NonlinearModel>, src/elements/shell/
