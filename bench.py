@@ -121,15 +121,17 @@ class c_stdout_to_stderr:
         os.close(self.saved)
 
 
-def cpu_reference_rate(nx, reps, threads=None):
+def cpu_reference_rate(nx, reps, threads=None, warmup=0, aggregate=False):
     with c_stdout_to_stderr():
-        return _cpu_reference_rate(nx, reps, threads)
+        return _cpu_reference_rate(nx, reps, threads, warmup, aggregate)
 
 
-def _cpu_reference_rate(nx, reps, threads=None):
+def _cpu_reference_rate(nx, reps, threads=None, warmup=0, aggregate=False):
     """elements/s of the UNMODIFIED reference (oracle/_ref) for res + K + G on an nx x nx
     plate: assembleJacobian (res + K) + assembleMatType(G), threaded as the reference
-    allows (<= 16 pthreads, src/utils/TACSObject.h:150)."""
+    allows (<= 16 pthreads, src/utils/TACSObject.h:150).  `warmup` untimed passes first;
+    the rate is the median pass (cpu_baseline leg) or, with `aggregate`, all `reps` passes
+    over their summed time (the --impl reference arm: K timed steps)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refdrv
     a2ds = importlib.import_module("a2d-shells_b200")
@@ -147,29 +149,37 @@ def _cpu_reference_rate(nx, reps, threads=None):
     ra.set_state(u)
     km = ra.mat_create(1); gm = ra.mat_create(1)   # TACSSchurMat, as the shipped examples
     ra.set_threads(threads)
+    for _ in range(warmup):
+        ra.time(1, km); ra.time(3, gm)
     times = []
     for _ in range(reps):
         t = ra.time(1, km) + ra.time(3, gm)
         times.append(t)
     ra.close()
-    t = float(np.median(times))
+    t = float(np.sum(times) / len(times)) if aggregate else float(np.median(times))
+    how = f"{reps} timed passes after {warmup} warm-up" if aggregate else f"median of {reps}"
     return dict(value=len(conn) / t, unit="elements/s", cores=threads, kind="reference",
-                sample=f"plate {nx}x{nx} ({len(conn)} elements), median of {reps}: "
+                sample=f"plate {nx}x{nx} ({len(conn)} elements), {how}: "
                        f"assembleJacobian(res+K)+assembleMatType(G) into TACSSchurMat, "
                        f"{threads} pthreads on {cores} host cores",
                 seconds_per_pass=t, n_elems=len(conn))
 
 
+PLATE_WORKLOAD = ("flat plate {nx}x{ny} MITC4 quads (BASELINE configs[1] per GPU), fused "
+                  "residual+Kmat+Gmat, linear elastic iso shell")
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path, same metric"""
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified
+    sources compiled into oracle/_ref), same metric and workload as our arm.  One step = one
+    pass (res + K, then G) over a bounded sample of the workload (--ref-nx squared elements of
+    the same plate), all the host threads the reference can use (<= 16).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    nx = args.ref_nx
     t0 = time.time()
-    for _ in range(args.warmup):
-        pass  # warm-up is folded into the first repetitions below (each rep rebuilds nothing)
-    r = cpu_reference_rate(nx, max(args.steps, 1))
+    r = cpu_reference_rate(args.ref_nx, max(args.steps, 1), warmup=max(args.warmup, 0),
+                           aggregate=True)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built"}))
         return 0
@@ -179,7 +189,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_pass"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"flat plate 1000x1000 MITC4, res+K+G; CPU sample {r['sample']}"},
+        "config": {"workload": PLATE_WORKLOAD.format(nx=args.nx, ny=args.nx * args.gpus),
+                   "elements_per_step": r["n_elems"],
+                   "sample": r["sample"]},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "elements/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -228,8 +240,7 @@ def main():
     nonlinear = args.workload == "cylinder-nl"
     if args.workload == "plate":
         slab = a2ds.meshes.plate_slab(rank, world, nx, ny, bump=0.0)
-        wl = (f"flat plate {nx}x{ny * world} MITC4 quads (BASELINE configs[1] per GPU), fused "
-              f"residual+Kmat+Gmat, linear elastic iso shell")
+        wl = PLATE_WORKLOAD.format(nx=nx, ny=ny * world)
     elif args.workload == "cylinder":
         nx, ny = 4000, 500
         slab = a2ds.meshes.cylinder_slab(rank, world, nx, ny)
