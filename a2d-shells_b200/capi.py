@@ -32,6 +32,9 @@ SYMBOLS = [
     "a2ds_add_jacobian_vec_product", "a2ds_add_jacobian_vec_product_dev",
     "a2ds_set_mass_moments", "a2ds_set_state_rates", "a2ds_assemble_mat_combo",
     "a2ds_mat_mult_dist_dev", "a2ds_mat_set_halo",
+    "a2ds_mesh_read_bdf", "a2ds_mesh_read_bin", "a2ds_mesh_write_bin", "a2ds_mesh_from_arrays",
+    "a2ds_mesh_free", "a2ds_mesh_sizes", "a2ds_mesh_connectivity", "a2ds_mesh_bcs",
+    "a2ds_mesh_file_numbers", "a2ds_mesh_component", "a2ds_mesh_quad4",
 ]
 
 _LIB = None
@@ -74,6 +77,7 @@ def load_library():
         L = C.CDLL(path)
         L.a2ds_last_error.restype = C.c_char_p
         L.a2ds_version.restype = C.c_char_p
+        L.a2ds_mesh_free.restype = None
         _LIB = L
     return _LIB
 
@@ -114,6 +118,116 @@ def host_color_elements(n_nodes, conn):
                                   C.byref(nc)):
         raise A2dsError(L.a2ds_last_error().decode())
     return color, nc.value
+
+
+class Mesh:
+    """A mesh container of the library (include/a2ds.h, a2ds_mesh_*): what
+    TACSMeshLoader::scanBDFFile + getConnectivity + getBCs give (src/io/TACSMeshLoader.cpp).
+    Host only — no device needed.  Arrays are copied out on construction:
+      elem_ptr, elem_conn, elem_comp, X (n, 3), bc_nodes, bc_ptr, bc_vars, bc_vals,
+      node_nums / elem_nums (the file's own numbers, 0-based), elem_descript, comp_descript."""
+
+    def __init__(self, handle):
+        L = self.L = load_library()
+        self.h = handle
+        n = [C.c_int() for _ in range(6)]
+        self._chk(L.a2ds_mesh_sizes(self.h, *[C.byref(x) for x in n]))
+        (self.n_nodes, self.n_elems, self.conn_size, self.n_bcs, self.bc_size,
+         self.n_comp) = [x.value for x in n]
+        IP, DP = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+        def ints(ptr, k):
+            return np.ctypeslib.as_array(ptr, shape=(k,)).copy() if k else np.zeros(0, np.int32)
+
+        def reals(ptr, k):
+            return np.ctypeslib.as_array(ptr, shape=(k,)).copy() if k else np.zeros(0)
+
+        a, b, c, x = IP(), IP(), IP(), DP()
+        self._chk(L.a2ds_mesh_connectivity(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(x)))
+        self.elem_ptr = ints(a, self.n_elems + 1)
+        self.elem_conn = ints(b, self.conn_size)
+        self.elem_comp = ints(c, self.n_elems)
+        self.X = reals(x, 3 * self.n_nodes).reshape(-1, 3)
+        a, b, c, x = IP(), IP(), IP(), DP()
+        self._chk(L.a2ds_mesh_bcs(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(x)))
+        self.bc_nodes = ints(a, self.n_bcs)
+        self.bc_ptr = ints(b, self.n_bcs + 1)
+        self.bc_vars = ints(c, self.bc_size)
+        self.bc_vals = reals(x, self.bc_size)
+        a, b = IP(), IP()
+        self._chk(L.a2ds_mesh_file_numbers(self.h, C.byref(a), C.byref(b)))
+        self.node_nums = ints(a, self.n_nodes)
+        self.elem_nums = ints(b, self.n_elems)
+        self.elem_descript, self.comp_descript = [], []
+        for k in range(self.n_comp):
+            e, d = C.c_char_p(), C.c_char_p()
+            self._chk(L.a2ds_mesh_component(self.h, C.c_int(k), C.byref(e), C.byref(d)))
+            self.elem_descript.append(e.value.decode())
+            self.comp_descript.append(d.value.decode())
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise A2dsError(self.L.a2ds_last_error().decode())
+
+    @classmethod
+    def _open(cls, fn, *args):
+        L = load_library()
+        h = C.c_void_p()
+        if getattr(L, fn)(*args, C.byref(h)):
+            raise A2dsError(L.a2ds_last_error().decode())
+        return cls(h)
+
+    @classmethod
+    def read_bdf(cls, path, n_threads=0):
+        """TACSMeshLoader::scanBDFFile"""
+        return cls._open("a2ds_mesh_read_bdf", C.c_char_p(os.fsencode(path)), C.c_int(n_threads))
+
+    @classmethod
+    def read_bin(cls, path):
+        return cls._open("a2ds_mesh_read_bin", C.c_char_p(os.fsencode(path)))
+
+    @classmethod
+    def from_arrays(cls, conn, X, elem_comp=None, bc_nodes=(), bc_vars=(), bc_vals=None):
+        """conn: (n_elems, nodes per element); bc_vars: per BC entry a list of 0-based DOFs;
+        bc_vals: per entry one value or a list matching bc_vars"""
+        conn = _i32(conn)
+        conn = conn.reshape(conn.shape[0], -1) if conn.size else conn.reshape(0, 4)
+        X = _f64(X).reshape(-1, 3)
+        ptr = _i32(np.arange(conn.shape[0] + 1) * conn.shape[1])
+        ec = None if elem_comp is None else _i32(elem_comp)
+        nb = len(bc_nodes)
+        bptr = _i32(np.concatenate([[0], np.cumsum([len(v) for v in bc_vars])])) if nb else _i32([0])
+        bvars = _i32(np.concatenate([np.asarray(v, dtype=np.int32) for v in bc_vars])) if nb else _i32([])
+        if bc_vals is None:
+            bvals = np.zeros(len(bvars))
+        else:
+            bvals = np.concatenate([np.broadcast_to(np.asarray(v, dtype=float), (len(w),))
+                                    for v, w in zip(bc_vals, bc_vars)]) if nb else np.zeros(0)
+        return cls._open("a2ds_mesh_from_arrays", C.c_int(X.shape[0]), C.c_int(conn.shape[0]),
+                         _p(ptr), _p(conn), _p(ec), _p(X), C.c_int(nb), _p(_i32(bc_nodes)),
+                         _p(bptr), _p(bvars), _p(_f64(bvals)))
+
+    def write_bin(self, path):
+        self._chk(self.L.a2ds_mesh_write_bin(self.h, C.c_char_p(os.fsencode(path))))
+
+    def quad4(self):
+        """(conn (n_elems, 4), bc_masks, bc_vals (n_bcs, 6)) for Assembler.set_mesh / set_bcs"""
+        conn = np.zeros((self.n_elems, 4), dtype=np.int32)
+        masks = np.zeros(self.n_bcs, dtype=np.int32)
+        vals = np.zeros((self.n_bcs, 6))
+        self._chk(self.L.a2ds_mesh_quad4(self.h, _p(conn), _p(masks), _p(vals)))
+        return conn, masks, vals
+
+    def close(self):
+        if self.h:
+            self.L.a2ds_mesh_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Assembler:

@@ -51,6 +51,9 @@ static int fail(const std::string &m) {
     if (r_ != ncclSuccess) return fail(std::string(#call) + ": " + ncclGetErrorString(r_)); \
   } while (0)
 
+// used by the other translation units of the library (mesh_io.cpp)
+int a2ds_set_error_(const char *msg) { return fail(msg); }
+
 extern "C" const char *a2ds_last_error(void) { return g_err.c_str(); }
 extern "C" const char *a2ds_version(void) { return "a2ds-b200 0.1 (sm_100a)"; }
 

@@ -319,3 +319,67 @@ def _global_pattern(n_nodes, conn):
         _pattern_cache.clear()
         _pattern_cache[key] = (rowp, cols)
     return _pattern_cache[key]
+
+
+# ---- NASTRAN bulk-data writer (the input format of the reference's examples) -------------
+def _real8(x):
+    """a real in 8 columns, NASTRAN compact form ("1.2345-3": exponent sign without a letter),
+    with as many digits as fit"""
+    if x == 0.0:
+        return "      0."
+    for digits in range(5, -1, -1):
+        m, e = f"{x:.{digits}E}".split("E")
+        if digits == 0:
+            m += "."            # NASTRAN reals carry a decimal point
+        s = f"{m}{int(e):+d}"
+        if len(s) <= 8:
+            return s.rjust(8)
+    raise ValueError(f"{x!r} does not fit an 8-column field")
+
+
+def write_bdf(path, conn, X, bc_nodes=(), bc_dofs=(), bc_vals=None, elem_comp=None, fmt="large",
+              node_ids=None, elem_ids=None, comp_names=None, keyword="CQUAD4", order="file"):
+    """Write a deck the reference's loader (and a2ds_mesh_read_bdf) reads.
+
+    conn: (n_elems, 4) in the tensor order used everywhere in this package; the card lists the
+    corners counter-clockwise, i.e. [n0, n1, n3, n2].  bc_dofs: per BC entry a string of DOF
+    digits ("123456") or a list of 0-based DOFs; bc_vals: one value per entry.  fmt: "large"
+    (GRID*, SPC*, 16-column fields, full double precision as the shipped decks), "small"
+    (8-column fields) or "free" (comma separated GRID, small elements).  node_ids / elem_ids:
+    the numbers written in the file (1-based, any order, gaps allowed)."""
+    conn = np.asarray(conn).reshape(-1, 4)
+    X = np.asarray(X, dtype=float).reshape(-1, 3)
+    nid = np.arange(1, len(X) + 1) if node_ids is None else np.asarray(node_ids)
+    eid = np.arange(1, len(conn) + 1) if elem_ids is None else np.asarray(elem_ids)
+    comp = np.zeros(len(conn), dtype=int) if elem_comp is None else np.asarray(elem_comp)
+    out = ["$ written by a2d-shells_b200.meshes.write_bdf", "SOL 103", "CEND", "BEGIN BULK"]
+    for name in (comp_names or []):
+        out.append("$       Shell element data for family".ljust(41) + str(name)[:32])
+    for k in range(len(X)):
+        x, y, z = X[k]
+        if fmt == "large":
+            out.append(f"GRID*   {nid[k]:>16d}{'':16s}{x:16.9E}{y:16.9E}*       ")
+            out.append(f"*       {z:16.9E}")
+        elif fmt == "small":
+            out.append(f"GRID    {nid[k]:>8d}{'':8s}{_real8(x)}{_real8(y)}{_real8(z)}")
+        else:
+            out.append(f"GRID    {nid[k]},,{x:.10E},{y:.10E},{z:.10E}")
+    for e in range(len(conn)):
+        n = nid[conn[e][[0, 1, 3, 2]]]
+        if fmt == "large":
+            out.append(f"{keyword + '*':<8s}{eid[e]:>16d}{comp[e] + 1:>16d}{n[0]:>16d}{n[1]:>16d}")
+            out.append(f"*       {n[2]:>16d}{n[3]:>16d}")
+        else:
+            out.append(f"{keyword:<8s}{eid[e]:>8d}{comp[e] + 1:>8d}{n[0]:>8d}{n[1]:>8d}{n[2]:>8d}{n[3]:>8d}")
+    vals = np.zeros(len(bc_nodes)) if bc_vals is None else np.broadcast_to(bc_vals, (len(bc_nodes),))
+    for b in range(len(bc_nodes)):
+        d = bc_dofs[b] if isinstance(bc_dofs[b], str) else "".join(str(int(v) + 1) for v in bc_dofs[b])
+        node = nid[bc_nodes[b]]
+        if fmt == "large":
+            v = "0." if vals[b] == 0 else f"{vals[b]:.9E}"
+            out.append(f"SPC*    {1:>16d}{node:>16d}{d:>16s}{v:>16s}")
+        else:
+            out.append(f"SPC     {1:>8d}{node:>8d}{d:>8s}{_real8(vals[b])}")
+    out.append("ENDDATA")
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")

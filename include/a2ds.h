@@ -241,6 +241,54 @@ int a2ds_host_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int 
 int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *color,
                              int *n_colors);
 
+/* ---- mesh input (host only) -------------------------------------------------------
+ * The data format in front of the path: NASTRAN bulk-data decks as the reference's examples
+ * ship them, and a flat binary container for meshes too large to parse at every start.
+ *
+ * a2ds_mesh_read_bdf stands in for TACSMeshLoader::scanBDFFile
+ * (src/io/TACSMeshLoader.cpp:570-1096): GRID / GRID* / SPC / SPC* and the element keywords of
+ * src/io/TACSMeshLoader.h:20-35 in small, large and comma-separated fields; nodes and elements
+ * come out sorted by their file numbers (0-based), element nodes in the tensor-product order of
+ * the element basis, components 0-based — array for array what getConnectivity / getBCs
+ * (:1221-1278) hand out.  n_threads <= 0: one parser per host core (at most 16); the result
+ * does not depend on it.  Failures return non-zero (missing file, empty line inside the bulk
+ * data — where the reference stops too —, an element card without its numbers or with too few
+ * nodes, references to undefined grid points); unknown cards are reported on stderr and
+ * skipped, as the reference does. */
+typedef struct a2ds_mesh a2ds_mesh;
+int a2ds_mesh_read_bdf(const char *path, int n_threads, a2ds_mesh **mesh);
+/* binary container written by a2ds_mesh_write_bin: no parsing, arrays read as they are */
+int a2ds_mesh_read_bin(const char *path, a2ds_mesh **mesh);
+int a2ds_mesh_write_bin(const a2ds_mesh *mesh, const char *path);
+/* a container from arrays in memory (generated meshes); BC arrays may be NULL with n_bcs == 0 */
+int a2ds_mesh_from_arrays(int n_nodes, int n_elems, const int *elem_ptr, const int *elem_conn,
+                          const int *elem_comp, const double *X, int n_bcs, const int *bc_nodes,
+                          const int *bc_ptr, const int *bc_vars, const double *bc_vals,
+                          a2ds_mesh **mesh);
+void a2ds_mesh_free(a2ds_mesh *mesh);
+/* getNumNodes / getNumElements / getNumComponents (:1102, :1189, :537); conn_size and bc_size
+ * are the lengths of elem_conn and bc_vars / bc_vals.  Any pointer may be NULL. */
+int a2ds_mesh_sizes(const a2ds_mesh *mesh, int *n_nodes, int *n_elems, int *conn_size,
+                    int *n_bcs, int *bc_size, int *n_comp);
+/* TACSMeshLoader::getConnectivity (:1221-1247): borrowed pointers, valid until a2ds_mesh_free;
+ * elem_ptr[n_elems + 1], elem_conn[conn_size], elem_comp[n_elems], X[3 n_nodes] */
+int a2ds_mesh_connectivity(const a2ds_mesh *mesh, const int **elem_ptr, const int **elem_conn,
+                           const int **elem_comp, const double **X);
+/* TACSMeshLoader::getBCs (:1252-1278): one entry per SPC card; bc_vars are 0-based DOFs
+ * (digits 1..8 of the card), bc_vals the card's value repeated per DOF */
+int a2ds_mesh_bcs(const a2ds_mesh *mesh, const int **bc_nodes, const int **bc_ptr,
+                  const int **bc_vars, const double **bc_vals);
+/* the file's own node / element numbers (0-based, ascending): entry k belongs to node /
+ * element k of the arrays above (what getAssemblerNodeNums searches, :1200-1215) */
+int a2ds_mesh_file_numbers(const a2ds_mesh *mesh, const int **node_nums, const int **elem_nums);
+/* getElementDescript / getComponentDescript (:552-566): keyword of the first element of the
+ * component, and its name from an ICEM "$       Shell" comment ("" if there is none) */
+int a2ds_mesh_component(const a2ds_mesh *mesh, int comp, const char **elem_descript,
+                        const char **comp_descript);
+/* the arrays a2ds_set_mesh / a2ds_set_bcs take, for a deck of 4-node shells: conn4[4 n_elems],
+ * per SPC card a DOF bit mask and six prescribed values.  Fails if an element is not 4-noded. */
+int a2ds_mesh_quad4(const a2ds_mesh *mesh, int *conn4, int *bc_masks, double *bc_vals6);
+
 /* ---- instrumentation ------------------------------------------------------------
  * device time of the last assemble call in milliseconds (CUDA events on the context
  * stream) and the number of kernels it launched */

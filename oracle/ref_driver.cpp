@@ -29,6 +29,7 @@
 #include "TACSCreator.h"
 #include "TACSIsoShellConstitutive.h"
 #include "TACSMaterialProperties.h"
+#include "TACSMeshLoader.h"
 #include "TACSParallelMat.h"
 #include "TACSSchurMat.h"
 #include "TACSShellElementDefs.h"
@@ -526,5 +527,53 @@ int refdrv_bc_state(void *h, double *u) {
   v->decref();
   return n;
 }
+
+/* The reference's BDF reader (TACSMeshLoader::scanBDFFile, src/io/TACSMeshLoader.cpp:570):
+   scan, then hand out what getConnectivity / getBCs return.  Two-call protocol: with
+   elem_ptr == NULL only the sizes are filled.  Returns scanBDFFile's own return value;
+   the loader stays alive in *h until refdrv_bdf_free.  secs: wall time of the scan. */
+int refdrv_bdf_scan(const char *path, void **h, int *sizes, double *secs) {
+  TACSMeshLoader *ml = new TACSMeshLoader(MPI_COMM_WORLD);
+  ml->incref();
+  double t0 = MPI_Wtime();
+  int fail = ml->scanBDFFile(path);
+  *secs = MPI_Wtime() - t0;
+  int nn = 0, ne = 0, nb = 0;
+  const int *eptr = NULL, *bptr = NULL;
+  ml->getConnectivity(&nn, &ne, &eptr, NULL, NULL, NULL);
+  ml->getBCs(&nb, NULL, NULL, &bptr, NULL);
+  sizes[0] = nn; sizes[1] = ne; sizes[2] = (eptr ? eptr[ne] : 0);
+  sizes[3] = nb; sizes[4] = (bptr ? bptr[nb] : 0); sizes[5] = ml->getNumComponents();
+  *h = ml;
+  return fail;
+}
+
+void refdrv_bdf_arrays(void *h, int *elem_ptr, int *elem_conn, int *elem_comp, double *X,
+                       int *bc_nodes, int *bc_ptr, int *bc_vars, double *bc_vals,
+                       char *elem_descript /* 9 per component */,
+                       char *comp_descript /* 33 per component */) {
+  TACSMeshLoader *ml = (TACSMeshLoader *)h;
+  int nn, ne, nb;
+  const int *eptr, *econn, *ecomp, *bn, *bv, *bp;
+  const TacsScalar *Xp, *bvals;
+  ml->getConnectivity(&nn, &ne, &eptr, &econn, &ecomp, &Xp);
+  ml->getBCs(&nb, &bn, &bv, &bp, &bvals);
+  memcpy(elem_ptr, eptr, (ne + 1) * sizeof(int));
+  memcpy(elem_conn, econn, eptr[ne] * sizeof(int));
+  memcpy(elem_comp, ecomp, ne * sizeof(int));
+  memcpy(X, Xp, 3 * nn * sizeof(double));
+  memcpy(bc_nodes, bn, nb * sizeof(int));
+  memcpy(bc_ptr, bp, (nb + 1) * sizeof(int));
+  memcpy(bc_vars, bv, bp[nb] * sizeof(int));
+  memcpy(bc_vals, bvals, bp[nb] * sizeof(double));
+  for (int k = 0; k < ml->getNumComponents(); k++) {
+    memset(&elem_descript[9 * k], 0, 9);
+    memset(&comp_descript[33 * k], 0, 33);
+    strncpy(&elem_descript[9 * k], ml->getElementDescript(k), 8);
+    strncpy(&comp_descript[33 * k], ml->getComponentDescript(k), 32);
+  }
+}
+
+void refdrv_bdf_free(void *h) { ((TACSMeshLoader *)h)->decref(); }
 
 }  // extern "C"

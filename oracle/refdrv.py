@@ -232,3 +232,29 @@ class RefAssembler:
         if self.h:
             lib().refdrv_destroy(self.h)
             self.h = None
+
+
+def bdf_scan(path):
+    """TACSMeshLoader::scanBDFFile + getConnectivity + getBCs of the unmodified reference.
+    Returns (fail, dict of arrays, seconds spent in scanBDFFile)."""
+    L = lib()
+    h = C.c_void_p()
+    sizes = np.zeros(6, dtype=np.int32)
+    secs = C.c_double()
+    fail = L.refdrv_bdf_scan(C.c_char_p(os.fsencode(path)), C.byref(h), _p(sizes), C.byref(secs))
+    nn, ne, nc, nb, nv, ncomp = [int(x) for x in sizes]
+    out = dict(elem_ptr=np.zeros(ne + 1, np.int32), elem_conn=np.zeros(nc, np.int32),
+               elem_comp=np.zeros(ne, np.int32), X=np.zeros((nn, 3)),
+               bc_nodes=np.zeros(nb, np.int32), bc_ptr=np.zeros(nb + 1, np.int32),
+               bc_vars=np.zeros(nv, np.int32), bc_vals=np.zeros(nv))
+    ed = C.create_string_buffer(9 * max(ncomp, 1))
+    cd = C.create_string_buffer(33 * max(ncomp, 1))
+    if fail == 0:
+        L.refdrv_bdf_arrays(h, *[_p(out[k]) for k in ("elem_ptr", "elem_conn", "elem_comp", "X",
+                                                       "bc_nodes", "bc_ptr", "bc_vars", "bc_vals")],
+                            ed, cd)
+    out["elem_descript"] = [ed.raw[9 * k:9 * k + 9].split(b"\0")[0].decode() for k in range(ncomp)]
+    out["comp_descript"] = [cd.raw[33 * k:33 * k + 33].split(b"\0")[0].decode() for k in range(ncomp)]
+    out["n_comp"] = ncomp
+    L.refdrv_bdf_free(h)
+    return fail, out, secs.value

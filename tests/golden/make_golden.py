@@ -10,6 +10,11 @@ of the reference itself on seeded inputs:
   plate.npz, cylinder.npz : small assembled meshes (reference numbering): pattern,
                  res, K, G of assembleJacobian / assembleMatType, with BCs
   buckling.npz : lowest 6 buckling eigenvalues of a 40x20 cylinder
+  bdf.npz      : what the reference's TACSMeshLoader reads from the decks in this
+                 directory (mixed.bdf: hand-written, every card family and field format;
+                 cyl_large.bdf / cyl_small.bdf / cyl_free.bdf: written here by
+                 meshes.write_bdf with shuffled file numbers) and from the two decks the
+                 reference ships (examples/cylinder-buckling, kept as array digests only)
 """
 import importlib
 import os
@@ -76,6 +81,40 @@ def mesh(name):
     ra.close()
 
 
+def bdf():
+    out = {}
+    rng = np.random.default_rng(7)
+    conn, X, bcn = a2ds.meshes.cylinder(16, 5)
+    nid = rng.permutation(len(X)) * 3 + 5
+    eid = rng.permutation(len(conn)) * 2 + 11
+    comp = rng.integers(0, 3, len(conn))
+    for fmt in ("large", "small", "free"):
+        a2ds.meshes.write_bdf(os.path.join(HERE, f"cyl_{fmt}.bdf"), conn, X, bcn,
+                              ["123456" if i % 2 else "13" for i in range(len(bcn))],
+                              [(-1e-5 if i % 3 else 0.0) for i in range(len(bcn))], comp, fmt, nid,
+                              eid, comp_names=["SKIN", "RIB.001", "SPAR"])
+    decks = {f"cyl_{f}": os.path.join(HERE, f"cyl_{f}.bdf") for f in ("large", "small", "free")}
+    decks["mixed"] = os.path.join(HERE, "mixed.bdf")
+    for name, path in decks.items():
+        fail, ref, _ = refdrv.bdf_scan(path)
+        assert fail == 0, path
+        for k, v in ref.items():
+            out[f"{name}_{k}"] = np.array(v)
+    # the shipped decks cannot travel with the repository: keep what the reference reads from
+    # them as sizes and checksums
+    ex = "/root/reference/examples/cylinder-buckling"
+    for name in ("mech-cylinder", "therm-cylinder"):
+        fail, ref, _ = refdrv.bdf_scan(os.path.join(ex, name + ".bdf"))
+        assert fail == 0
+        out[name + "_sizes"] = np.array([len(ref["X"]), len(ref["elem_comp"]), len(ref["bc_nodes"])])
+        out[name + "_digest"] = np.array([
+            float(ref["X"].sum()), float(np.abs(ref["X"]).sum()),
+            float((ref["elem_conn"].astype(np.int64) * (1 + np.arange(len(ref["elem_conn"])) % 7)).sum()),
+            float((ref["bc_nodes"].astype(np.int64) * (1 + ref["bc_vars"])).sum()),
+            float(ref["bc_vals"].sum())])
+    np.savez_compressed(os.path.join(HERE, "bdf.npz"), **out)
+
+
 def buckling():
     """cylinder 40x20 under end shortening; the reference solves for the load path itself
     (u0 = NULL) and runs Lanczos with the shipped example's settings (100 vectors, 50
@@ -94,6 +133,9 @@ def buckling():
 
 
 if __name__ == "__main__":
-    elements(); mesh("plate"); mesh("cylinder"); buckling()
+    which = sys.argv[1:] or ["elements", "plate", "cylinder", "buckling", "bdf"]
+    for w in which:   # e.g. `python make_golden.py bdf` regenerates only bdf.npz
+        {"elements": elements, "plate": lambda: mesh("plate"), "cylinder": lambda: mesh("cylinder"),
+         "buckling": buckling, "bdf": bdf}[w]()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
