@@ -35,6 +35,8 @@ SYMBOLS = [
     "a2ds_mesh_read_bdf", "a2ds_mesh_read_bin", "a2ds_mesh_write_bin", "a2ds_mesh_from_arrays",
     "a2ds_mesh_free", "a2ds_mesh_sizes", "a2ds_mesh_connectivity", "a2ds_mesh_bcs",
     "a2ds_mesh_file_numbers", "a2ds_mesh_component", "a2ds_mesh_quad4",
+    "a2ds_partition_build", "a2ds_partition_free", "a2ds_partition_sizes", "a2ds_partition_mesh",
+    "a2ds_partition_halo", "a2ds_partition_apply",
 ]
 
 _LIB = None
@@ -78,6 +80,7 @@ def load_library():
         L.a2ds_last_error.restype = C.c_char_p
         L.a2ds_version.restype = C.c_char_p
         L.a2ds_mesh_free.restype = None
+        L.a2ds_partition_free.restype = None
         _LIB = L
     return _LIB
 
@@ -221,6 +224,59 @@ class Mesh:
     def close(self):
         if self.h:
             self.L.a2ds_mesh_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Partition:
+    """One rank's sub-mesh and halo plan from the global mesh (a2ds_partition_*; node ownership
+    as TACSCreator, src/TACSCreator.cpp:1156-1205).  Host only.  Attributes: n_nodes, n_owned,
+    elems, conn_local (n, 4), glob, ghost_owner, peers, send_lists, recv_lists."""
+
+    def __init__(self, conn, n_nodes, elem_rank, n_ranks, rank):
+        L = self.L = load_library()
+        conn = _i32(conn).reshape(-1, 4)
+        er = _i32(elem_rank)
+        assert len(er) == len(conn)
+        self.h = C.c_void_p()
+        if L.a2ds_partition_build(C.c_int(n_nodes), C.c_int(len(conn)), _p(conn), _p(er),
+                                  C.c_int(n_ranks), C.c_int(rank), C.byref(self.h)):
+            raise A2dsError(L.a2ds_last_error().decode())
+        n = [C.c_int() for _ in range(6)]
+        L.a2ds_partition_sizes(self.h, *[C.byref(x) for x in n])
+        self.n_nodes, self.n_owned, ne, npeer, ns, nr = [x.value for x in n]
+        IP = C.POINTER(C.c_int)
+
+        def ints(ptr, k):
+            return np.ctypeslib.as_array(ptr, shape=(k,)).copy() if k else np.zeros(0, np.int32)
+
+        a, b, c, d = IP(), IP(), IP(), IP()
+        L.a2ds_partition_mesh(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        self.elems = ints(a, ne)
+        self.conn_local = ints(b, 4 * ne).reshape(-1, 4)
+        self.glob = ints(c, self.n_nodes)
+        self.ghost_owner = ints(d, self.n_nodes - self.n_owned)
+        a, b, c, d, e = IP(), IP(), IP(), IP(), IP()
+        L.a2ds_partition_halo(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e))
+        self.peers = ints(a, npeer)
+        sp, sn, rp, rn = ints(b, npeer + 1), ints(c, ns), ints(d, npeer + 1), ints(e, nr)
+        self.send_lists = [sn[sp[k]:sp[k + 1]] for k in range(npeer)]
+        self.recv_lists = [rn[rp[k]:rp[k + 1]] for k in range(npeer)]
+
+    def apply(self, asm, elem_comp=None):
+        """a2ds_set_mesh + a2ds_set_halo on an Assembler"""
+        ec = None if elem_comp is None else _i32(elem_comp)
+        asm._chk(self.L.a2ds_partition_apply(asm.ctx, self.h, _p(ec)))
+        asm.n_nodes, asm.n_owned, asm.n_elems = self.n_nodes, self.n_owned, len(self.elems)
+
+    def close(self):
+        if self.h:
+            self.L.a2ds_partition_free(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

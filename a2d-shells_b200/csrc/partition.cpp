@@ -1,0 +1,171 @@
+// partition.cpp — element-wise partition of a global mesh into one rank's sub-mesh and its
+// ghost-exchange plan, behind the C ABI of include/a2ds.h (a2ds_partition_*).  Host only.
+//
+// What the reference spreads over TACSCreator::createTACS (node ownership and numbering,
+// src/TACSCreator.cpp:1156-1205: a node belongs to the rank of the first element, in global
+// element order, that refers to it; every rank numbers its owned nodes first) and the
+// TACSBVecDistribute / TACSBVecIndices pair built in TACSAssembler::initialize (the ghost
+// nodes of a rank, sorted by global number, and for each owner the nodes it has to send,
+// src/bpmat/TACSBVecDistribute.cpp:280-420).  Here each rank derives its own part straight
+// from the global connectivity and the element -> rank array, with no communication: every
+// rank sees the same two arrays, so the send list rank a builds for rank b and the receive
+// list rank b builds for rank a hold the same global nodes in the same (ascending) order.
+//
+// Cost: three passes over the 4 n_elems connectivity entries plus sorts of the interface
+// sets; 16 M elements take well under a second per rank.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/a2ds.h"
+
+int a2ds_set_error_(const char *msg);  // a2ds.cu
+
+struct a2ds_partition {
+  int n_owned = 0;
+  std::vector<int> elems;       // global ids of this rank's elements, ascending
+  std::vector<int> conn_local;  // 4 per local element, local node indices
+  std::vector<int> glob;        // local node -> global node: owned (ascending), then ghosts (ascending)
+  std::vector<int> ghost_owner; // owner rank of each ghost
+  std::vector<int> peers, send_ptr, send_nodes, recv_ptr, recv_nodes;
+};
+
+extern "C" int a2ds_partition_build(int n_nodes, int n_elems, const int *conn,
+                                    const int *elem_rank, int n_ranks, int rank,
+                                    a2ds_partition **out) {
+  *out = nullptr;
+  if (n_nodes < 0 || n_elems < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+    return a2ds_set_error_("a2ds_partition_build: bad sizes");
+  for (int e = 0; e < n_elems; e++)
+    if (elem_rank[e] < 0 || elem_rank[e] >= n_ranks)
+      return a2ds_set_error_("a2ds_partition_build: elem_rank outside [0, n_ranks)");
+  for (size_t i = 0; i < 4 * (size_t)n_elems; i++)
+    if (conn[i] < 0 || conn[i] >= n_nodes)
+      return a2ds_set_error_("a2ds_partition_build: connectivity refers to a node outside [0, n_nodes)");
+
+  // pass 1: owner = rank of the first element that touches the node
+  std::vector<int> owner((size_t)n_nodes, -1);
+  for (int e = 0; e < n_elems; e++)
+    for (int k = 0; k < 4; k++) {
+      int &o = owner[conn[4 * (size_t)e + k]];
+      if (o < 0) o = elem_rank[e];
+    }
+
+  a2ds_partition *p = new a2ds_partition();
+  // pass 2: my elements; nodes they use; nodes of mine that other ranks use
+  // mark: bit 0 = used by one of my elements; per peer sets are collected as (peer, node) pairs
+  std::vector<unsigned char> used((size_t)n_nodes, 0);
+  std::vector<uint64_t> wanted;  // (peer << 32 | global node) for my nodes used by `peer`
+  for (int e = 0; e < n_elems; e++) {
+    const int r = elem_rank[e];
+    if (r == rank) {
+      p->elems.push_back(e);
+      for (int k = 0; k < 4; k++) used[conn[4 * (size_t)e + k]] = 1;
+    } else {
+      for (int k = 0; k < 4; k++) {
+        const int g = conn[4 * (size_t)e + k];
+        if (owner[g] == rank) wanted.push_back(((uint64_t)r << 32) | (uint32_t)g);
+      }
+    }
+  }
+  std::sort(wanted.begin(), wanted.end());
+  wanted.erase(std::unique(wanted.begin(), wanted.end()), wanted.end());
+
+  // local numbering: owned nodes (ascending global number), then ghosts (ascending)
+  std::vector<int> local_of((size_t)n_nodes, -1);
+  for (int g = 0; g < n_nodes; g++)
+    if (owner[g] == rank) {
+      local_of[g] = (int)p->glob.size();
+      p->glob.push_back(g);
+    }
+  p->n_owned = (int)p->glob.size();
+  for (int g = 0; g < n_nodes; g++)
+    if (used[g] && owner[g] != rank) {
+      local_of[g] = (int)p->glob.size();
+      p->glob.push_back(g);
+      p->ghost_owner.push_back(owner[g]);
+    }
+  p->conn_local.resize(4 * p->elems.size());
+  for (size_t i = 0; i < p->elems.size(); i++)
+    for (int k = 0; k < 4; k++)
+      p->conn_local[4 * i + k] = local_of[conn[4 * (size_t)p->elems[i] + k]];
+
+  // peers: ranks that own one of my ghosts or use one of my nodes
+  std::vector<char> is_peer((size_t)n_ranks, 0);
+  for (int o : p->ghost_owner) is_peer[o] = 1;
+  for (uint64_t w : wanted) is_peer[(size_t)(w >> 32)] = 1;
+  for (int r = 0; r < n_ranks; r++)
+    if (is_peer[r]) p->peers.push_back(r);
+  p->send_ptr.assign(1, 0);
+  p->recv_ptr.assign(1, 0);
+  size_t wi = 0;
+  for (int r : p->peers) {
+    // nodes of mine that rank r reads as ghosts (ascending global number)
+    while (wi < wanted.size() && (int)(wanted[wi] >> 32) < r) wi++;
+    for (; wi < wanted.size() && (int)(wanted[wi] >> 32) == r; wi++)
+      p->send_nodes.push_back(local_of[(uint32_t)wanted[wi]]);
+    p->send_ptr.push_back((int)p->send_nodes.size());
+    // my ghosts owned by rank r (the ghost block is already ascending)
+    for (size_t k = 0; k < p->ghost_owner.size(); k++)
+      if (p->ghost_owner[k] == r) p->recv_nodes.push_back(p->n_owned + (int)k);
+    p->recv_ptr.push_back((int)p->recv_nodes.size());
+  }
+  *out = p;
+  return 0;
+}
+
+extern "C" void a2ds_partition_free(a2ds_partition *p) { delete p; }
+
+extern "C" int a2ds_partition_sizes(const a2ds_partition *p, int *n_local_nodes, int *n_owned,
+                                    int *n_local_elems, int *n_peers, int *n_send, int *n_recv) {
+  if (!p) return a2ds_set_error_("a2ds_partition_sizes: null partition");
+  if (n_local_nodes) *n_local_nodes = (int)p->glob.size();
+  if (n_owned) *n_owned = p->n_owned;
+  if (n_local_elems) *n_local_elems = (int)p->elems.size();
+  if (n_peers) *n_peers = (int)p->peers.size();
+  if (n_send) *n_send = (int)p->send_nodes.size();
+  if (n_recv) *n_recv = (int)p->recv_nodes.size();
+  return 0;
+}
+
+extern "C" int a2ds_partition_mesh(const a2ds_partition *p, const int **elems,
+                                   const int **conn_local, const int **glob,
+                                   const int **ghost_owner) {
+  if (!p) return a2ds_set_error_("a2ds_partition_mesh: null partition");
+  if (elems) *elems = p->elems.data();
+  if (conn_local) *conn_local = p->conn_local.data();
+  if (glob) *glob = p->glob.data();
+  if (ghost_owner) *ghost_owner = p->ghost_owner.data();
+  return 0;
+}
+
+extern "C" int a2ds_partition_halo(const a2ds_partition *p, const int **peers,
+                                   const int **send_ptr, const int **send_nodes,
+                                   const int **recv_ptr, const int **recv_nodes) {
+  if (!p) return a2ds_set_error_("a2ds_partition_halo: null partition");
+  if (peers) *peers = p->peers.data();
+  if (send_ptr) *send_ptr = p->send_ptr.data();
+  if (send_nodes) *send_nodes = p->send_nodes.data();
+  if (recv_ptr) *recv_ptr = p->recv_ptr.data();
+  if (recv_nodes) *recv_nodes = p->recv_nodes.data();
+  return 0;
+}
+
+// mesh and halo of this rank into a device context: a2ds_set_mesh (with the components of the
+// local elements picked from the global elem_comp array, may be NULL) + a2ds_set_halo
+extern "C" int a2ds_partition_apply(a2ds_ctx *ctx, const a2ds_partition *p, const int *elem_comp) {
+  if (!p) return a2ds_set_error_("a2ds_partition_apply: null partition");
+  std::vector<int> comp;
+  if (elem_comp) {
+    comp.resize(p->elems.size());
+    for (size_t i = 0; i < p->elems.size(); i++) comp[i] = elem_comp[p->elems[i]];
+  }
+  if (a2ds_set_mesh(ctx, (int)p->glob.size(), p->n_owned, (int)p->elems.size(),
+                    p->conn_local.data(), elem_comp ? comp.data() : nullptr))
+    return 1;
+  return a2ds_set_halo(ctx, (int)p->peers.size(), p->peers.data(), p->send_ptr.data(),
+                       p->send_nodes.data(), p->recv_ptr.data(), p->recv_nodes.data());
+}

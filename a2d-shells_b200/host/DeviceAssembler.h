@@ -50,6 +50,28 @@ class DeviceAssembler {
     check(a2ds_set_mass_moments(ctx_, n_comp, moments), "a2ds_set_mass_moments");
   }
   void haloForward() { check(a2ds_halo_forward(ctx_), "a2ds_halo_forward"); }
+  // multi-GPU, one process per GPU: this rank's part of an element-wise partitioned global
+  // mesh (node ownership and numbering as TACSCreator::createTACS) and its ghost-exchange
+  // plan, then a2ds_set_mesh + a2ds_set_halo.  Returns local -> global node numbers.
+  std::vector<int> setPartitionedMesh(int n_nodes, int n_elems, const int *conn,
+                                      const int *elem_rank, const int *elem_comp, int n_ranks,
+                                      int rank) {
+    a2ds_partition *part = nullptr;
+    check(a2ds_partition_build(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, &part),
+          "a2ds_partition_build");
+    const int rc = a2ds_partition_apply(ctx_, part, elem_comp);
+    const int *glob = nullptr;
+    a2ds_partition_sizes(part, &n_nodes_, &n_owned_, nullptr, nullptr, nullptr, nullptr);
+    a2ds_partition_mesh(part, nullptr, nullptr, &glob, nullptr);
+    std::vector<int> out(glob, glob + n_nodes_);
+    a2ds_partition_free(part);
+    check(rc, "a2ds_partition_apply");
+    return out;
+  }
+  // NCCL communicator: id from a2ds_comm_unique_id on rank 0, broadcast by the launcher
+  void initComm(int n_ranks, int rank, const char id[128]) {
+    check(a2ds_comm_init(ctx_, n_ranks, rank, id), "a2ds_comm_init");
+  }
 
   // TACSAssembler::createMat (natural order) / matrices whose pattern comes from a host object
   int createMat() {

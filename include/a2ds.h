@@ -241,6 +241,32 @@ int a2ds_host_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int 
 int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *color,
                              int *n_colors);
 
+/* ---- partition (host only) ---------------------------------------------------------
+ * One rank's part of an element-wise partitioned global mesh and its ghost-exchange plan,
+ * derived without communication from the global connectivity (4 global nodes per element)
+ * and the element -> rank array every rank holds.  Node ownership and numbering follow
+ * TACSCreator::createTACS (src/TACSCreator.cpp:1156-1205): a node belongs to the rank of the
+ * first element, in global element order, that refers to it; local numbering is the owned
+ * nodes (ascending global number) followed by the ghosts (ascending).  The halo lists are
+ * what TACSBVecDistribute is built from in TACSAssembler::initialize
+ * (src/bpmat/TACSBVecDistribute.cpp:280-420): per peer, my nodes it reads as ghosts and my
+ * ghosts it owns, both in ascending global order — so the two sides of a pair agree. */
+typedef struct a2ds_partition a2ds_partition;
+int a2ds_partition_build(int n_nodes, int n_elems, const int *conn, const int *elem_rank,
+                         int n_ranks, int rank, a2ds_partition **part);
+void a2ds_partition_free(a2ds_partition *part);
+int a2ds_partition_sizes(const a2ds_partition *part, int *n_local_nodes, int *n_owned,
+                         int *n_local_elems, int *n_peers, int *n_send, int *n_recv);
+/* borrowed pointers: elems[n_local_elems] global element ids; conn_local[4 n_local_elems];
+ * glob[n_local_nodes] local -> global node; ghost_owner[n_local_nodes - n_owned] */
+int a2ds_partition_mesh(const a2ds_partition *part, const int **elems, const int **conn_local,
+                        const int **glob, const int **ghost_owner);
+/* the arguments of a2ds_set_halo */
+int a2ds_partition_halo(const a2ds_partition *part, const int **peers, const int **send_ptr,
+                        const int **send_nodes, const int **recv_ptr, const int **recv_nodes);
+/* a2ds_set_mesh + a2ds_set_halo for this rank; elem_comp: component per GLOBAL element or NULL */
+int a2ds_partition_apply(a2ds_ctx *ctx, const a2ds_partition *part, const int *elem_comp);
+
 /* ---- mesh input (host only) -------------------------------------------------------
  * The data format in front of the path: NASTRAN bulk-data decks as the reference's examples
  * ship them, and a flat binary container for meshes too large to parse at every start.

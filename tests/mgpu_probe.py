@@ -99,7 +99,49 @@ def main():
         assert worst[0] < 1e-12 and worst[1] < 1e-10 and worst[2] < 1e-10, worst
         print("MGPU_OK")
     parallel_mat_flavour(rank, world, local)
+    native_partition(rank, world, local)
     dist.destroy_process_group()
+
+
+def native_partition(rank, world, local):
+    """a2ds_partition_build / a2ds_partition_apply (host C++): every rank derives its sub-mesh
+    and halo plan from the global mesh on its own; unstructured mesh, scattered element ->
+    rank map (every rank talks to every other); the residual of the owned nodes (ghost
+    contributions reverse-added over NCCL) must equal the one-GPU residual"""
+    conn, X = a2ds.meshes.cubed_sphere(6, shuffle_seed=11)[:2]
+    n = len(X)
+    elem_rank = ((np.arange(len(conn)) * 7919) % 97) % world
+    elem_comp = (np.arange(len(conn)) % 3).astype(np.int32)
+    Cs, eth = a2ds.iso_shell_tables()
+    Cs3 = np.stack([Cs * (1.0 + 0.5 * k) for k in range(3)]); eth3 = np.stack([eth] * 3)
+    P = a2ds.Partition(conn, n, elem_rank, world, rank)
+    asm = a2ds.Assembler(local)
+    uid = [asm.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    asm.comm_init(world, rank, uid[0])
+    P.apply(asm, elem_comp)
+    asm.set_nodes(X[P.glob]); asm.set_components(Cs3, eth3)
+    asm.set_state(a2ds.meshes.seeded_state(P.glob[:P.n_owned], 1e-5)); asm.halo_forward()
+    res = asm.assembleRes()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(dict(glob=P.glob, no=P.n_owned, res=res), gathered, dst=0)
+    asm.close()
+    if rank != 0:
+        return
+    ref = a2ds.Assembler(local)
+    ref.set_mesh(conn, n, elem_comp=elem_comp); ref.set_nodes(X); ref.set_components(Cs3, eth3)
+    ref.set_state(a2ds.meshes.seeded_state(np.arange(n), 1e-5))
+    r_all = ref.assembleRes()
+    ref.close()
+    seen = np.zeros(n, dtype=int)
+    worst = 0.0
+    for o in gathered:
+        own = o["glob"][:o["no"]]
+        seen[own] += 1
+        worst = max(worst, np.abs(o["res"] - r_all[own]).max() / np.abs(r_all).max())
+    print("MGPU_NATIVE_PARTITION", world, worst)
+    assert np.all(seen[np.unique(conn)] == 1) and worst < 1e-12, worst
+    print("MGPU_NATIVE_PARTITION_OK")
 
 
 def parallel_mat_flavour(rank, world, local):

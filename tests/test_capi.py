@@ -208,3 +208,51 @@ def test_matrix_halo_plan_assembles_owned_rows(a2ds, orc):
             assert len(row_l) == rowp_g[g + 1] - rowp_g[g]
             seen += 1
     assert seen == n
+
+
+def test_native_partition_matches_reference_ownership_rule(a2ds):
+    """a2ds_partition_build (host C++): one rank's sub-mesh and halo plan from the global mesh;
+    against meshes.partition_rows (first-touch ownership of TACSCreator.cpp:1156-1205, checked
+    above) on structured and unstructured meshes, slab and random element -> rank maps"""
+    rng = np.random.default_rng(5)
+    meshes = dict(plate=a2ds.meshes.plate(9, 7)[:2], cyl=a2ds.meshes.cylinder(10, 6)[:2],
+                  sphere=a2ds.meshes.cubed_sphere(4, shuffle_seed=3)[:2])
+    for name, (conn, X) in meshes.items():
+        for N in (1, 2, 3, 5):
+            for mode in ("slab", "random"):
+                er = (np.arange(len(conn)) * N // len(conn)) if mode == "slab" \
+                    else rng.integers(0, N, len(conn))
+                if er.max() + 1 < N:
+                    continue
+                parts = a2ds.meshes.partition_rows(conn, len(X), er)
+                for r in range(N):
+                    P, Q = a2ds.Partition(conn, len(X), er, N, r), parts[r]
+                    assert np.array_equal(P.glob, Q["glob"]) and P.n_owned == len(Q["owned"])
+                    assert np.array_equal(P.elems, Q["elems"])
+                    assert np.array_equal(P.conn_local, Q["conn_local"])
+                    assert np.array_equal(P.ghost_owner, Q["ghost_owner"])
+                    assert np.array_equal(P.peers, Q["peers"])
+                    assert len(P.send_lists) == len(Q["send_lists"])
+                    for a, b in zip(P.send_lists + P.recv_lists, Q["send_lists"] + Q["recv_lists"]):
+                        assert np.array_equal(a, b)
+    # the two sides of every pair name the same global nodes in the same order
+    conn, X = meshes["sphere"]
+    er = rng.integers(0, 4, len(conn))
+    P = [a2ds.Partition(conn, len(X), er, 4, r) for r in range(4)]
+    owners = np.full(len(X), -1)
+    for a in P:
+        assert np.all(owners[a.glob[:a.n_owned]] == -1)       # every node has one owner
+        owners[a.glob[:a.n_owned]] = 1
+        for k, q in enumerate(a.peers):
+            b = P[int(q)]
+            kb = list(b.peers).index(P.index(a))
+            assert np.array_equal(a.glob[a.send_lists[k]], b.glob[b.recv_lists[kb]])
+    assert np.all(owners[np.unique(conn)] == 1)
+    # a rank without elements, and bad input
+    er0 = np.zeros(len(conn), dtype=np.int32)
+    E = a2ds.Partition(conn, len(X), er0, 2, 1)
+    assert E.n_nodes == 0 and len(E.elems) == 0 and len(E.peers) == 0
+    with pytest.raises(a2ds.A2dsError, match="elem_rank"):
+        a2ds.Partition(conn, len(X), er0 + 7, 2, 0)
+    with pytest.raises(a2ds.A2dsError, match="outside"):
+        a2ds.Partition(conn + len(X), len(X), er0, 1, 0)

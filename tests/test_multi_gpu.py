@@ -31,3 +31,4 @@ def test_two_rank_assembly_matches_single_gpu(world):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "MGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MGPU_PARALLELMAT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MGPU_NATIVE_PARTITION_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
