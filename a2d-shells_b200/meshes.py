@@ -85,6 +85,55 @@ def cubed_sphere(n, radius=0.3, shuffle_seed=None):
     return conn, X, patch
 
 
+def wingbox(n_bays=6, nx=3, ny=4, nz=2, span=3.0, chord=1.0, height=0.25):
+    """Synthetic wing box (BASELINE configs[3] stand-in: the uCRM mesh itself is not part of
+    the reference checkout): upper and lower skin, front and rear spar, and a rib at every bay
+    boundary, all sharing their nodes where they meet — skin/spar/rib junction nodes have 5 or
+    6 elements around them, so matrix rows hold up to 15 blocks instead of the 9 of a
+    structured surface.  Tapered, swept, skins slightly cambered.  n_bays bays of nx elements
+    along the span, ny across the chord, nz through the height.
+    Returns conn[ne,4] (tensor node order), X[nn,3], elem_comp[ne] (one component per skin /
+    spar panel per bay and per rib: 4 n_bays + n_bays + 1), root nodes (clamped end)."""
+    NX = n_bays * nx
+    ids = {}
+    X = []
+
+    def node(i, j, k):
+        key = (i, j, k)
+        if key not in ids:
+            ids[key] = len(X)
+            s, c, h = i / NX, j / ny, k / nz
+            taper = 1.0 - 0.5 * s
+            camber = 0.04 * chord * np.sin(np.pi * c) * (1.0 if k == nz else -1.0 if k == 0 else 0.0)
+            X.append((span * s,
+                      0.35 * span * s + chord * taper * (c - 0.5),
+                      0.03 * span * s * s + height * taper * (h - 0.5) + camber * taper))
+        return ids[key]
+
+    conn, comp = [], []
+
+    def quad(a, b, c, d, cid):        # tensor order: (0,0) (1,0) (0,1) (1,1)
+        conn.append((a, b, c, d)); comp.append(cid)
+
+    for bay in range(n_bays):
+        for i in range(bay * nx, (bay + 1) * nx):
+            for j in range(ny):       # skins: k = nz (upper), k = 0 (lower)
+                quad(node(i, j, nz), node(i + 1, j, nz), node(i, j + 1, nz), node(i + 1, j + 1, nz), 4 * bay)
+                quad(node(i, j, 0), node(i, j + 1, 0), node(i + 1, j, 0), node(i + 1, j + 1, 0), 4 * bay + 1)
+            for k in range(nz):       # spars: j = 0 (front), j = ny (rear)
+                quad(node(i, 0, k), node(i + 1, 0, k), node(i, 0, k + 1), node(i + 1, 0, k + 1), 4 * bay + 2)
+                quad(node(i, ny, k), node(i, ny, k + 1), node(i + 1, ny, k), node(i + 1, ny, k + 1), 4 * bay + 3)
+    for rib in range(n_bays + 1):
+        i = rib * nx
+        for j in range(ny):
+            for k in range(nz):
+                quad(node(i, j, k), node(i, j + 1, k), node(i, j, k + 1), node(i, j + 1, k + 1),
+                     4 * n_bays + rib)
+    root = sorted(v for (i, j, k), v in ids.items() if i == 0)
+    return (np.array(conn, dtype=np.int32), np.array(X), np.array(comp, dtype=np.int32),
+            np.array(root, dtype=np.int32))
+
+
 def _splitmix64(x):
     x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
     z = x
