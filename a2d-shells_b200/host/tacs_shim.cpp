@@ -252,10 +252,13 @@ void TACSAssembler::assembleRes(TACSBVec *residual, const TacsScalar lambda) {
 void TACSAssembler::assembleJacobian(TacsScalar alpha, TacsScalar beta, TacsScalar gamma,
                                      TACSBVec *residual, TACSMat *A, MatrixOrientation matOr,
                                      const TacsScalar lambda) {
-  if (matOr != TACS_MAT_NORMAL) {
-    fprintf(stderr, "[a2ds shim] transposed assembly is not supported\n");
-    abort();
-  }
+  // matOr: TACS_MAT_TRANSPOSE only transposes the element matrix on its way into A
+  // (addMatValues -> addWeightValues(..., matOr), src/TACSAssembler.h:453-507); the boundary
+  // conditions are applied the same way (A->applyBCs, src/TACSAssembler.cpp:4173).  The
+  // element matrices of this class are symmetric (alpha K + gamma M, G: Hessians of an
+  // energy; the reference's own differ from their transposes by 2e-16), so both
+  // orientations assemble the same matrix and take the same device path.
+  (void)matOr;
   Shim &S = shim_get(this);
   const int id = shim_matrix(this, S, A);
   TacsScalar *r = nullptr;
@@ -266,10 +269,13 @@ void TACSAssembler::assembleJacobian(TacsScalar alpha, TacsScalar beta, TacsScal
 
 void TACSAssembler::assembleMatType(ElementMatrixType matType, TACSMat *A,
                                     MatrixOrientation matOr, const TacsScalar lambda) {
-  if (matOr != TACS_MAT_NORMAL) {
-    fprintf(stderr, "[a2ds shim] transposed assembly is not supported\n");
-    abort();
-  }
+  // matOr: TACS_MAT_TRANSPOSE only transposes the element matrix on its way into A
+  // (addMatValues -> addWeightValues(..., matOr), src/TACSAssembler.h:453-507); the boundary
+  // conditions are applied the same way (A->applyBCs, src/TACSAssembler.cpp:4173).  The
+  // element matrices of this class are symmetric (alpha K + gamma M, G: Hessians of an
+  // energy; the reference's own differ from their transposes by 2e-16), so both
+  // orientations assemble the same matrix and take the same device path.
+  (void)matOr;
   Shim &S = shim_get(this);
   const int id = shim_matrix(this, S, A);
   int type = -1;

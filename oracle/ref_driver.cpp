@@ -403,6 +403,17 @@ int refdrv_assemble_jacobian(void *h, double alpha, double beta, double gamma, i
   return n;
 }
 
+/* the same with TACS_MAT_TRANSPOSE (element matrices transposed on their way into A) */
+int refdrv_assemble_jacobian_transpose(void *h, double alpha, double beta, double gamma, int mat,
+                                       double *res) {
+  RefCtx *c = (RefCtx *)h;
+  c->assembler->assembleJacobian(alpha, beta, gamma, c->res, c->mats[mat].mat, TACS_MAT_TRANSPOSE);
+  TacsScalar *a;
+  int n = c->res->getArray(&a);
+  if (res) memcpy(res, a, n * sizeof(double));
+  return n;
+}
+
 /* type: 0 K, 1 G, 2 M */
 int refdrv_assemble_mat_type(void *h, int type, int mat) {
   RefCtx *c = (RefCtx *)h;

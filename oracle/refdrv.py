@@ -198,10 +198,10 @@ class RefAssembler:
         lib().refdrv_assemble_res(self.h, _p(r))
         return r
 
-    def assemble_jacobian(self, mat, alpha=1.0, beta=0.0, gamma=0.0):
+    def assemble_jacobian(self, mat, alpha=1.0, beta=0.0, gamma=0.0, transpose=False):
         r = np.zeros((self.n_nodes, 6))
-        lib().refdrv_assemble_jacobian(self.h, C.c_double(alpha), C.c_double(beta),
-                                       C.c_double(gamma), C.c_int(mat), _p(r))
+        fn = lib().refdrv_assemble_jacobian_transpose if transpose else lib().refdrv_assemble_jacobian
+        fn(self.h, C.c_double(alpha), C.c_double(beta), C.c_double(gamma), C.c_int(mat), _p(r))
         return r
 
     def assemble_mat_type(self, type_, mat):

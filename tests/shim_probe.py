@@ -33,6 +33,9 @@ udd = np.zeros((len(X), 6)); udd[ra.new_nodes] = a2ds_meshes.seeded_state(np.ara
 ra.set_state(u, None, udd)
 rd = ra.assemble_jacobian(pm, alpha=1.0, beta=0.0, gamma=1e4)
 Ad = ra.mat_block(pm, 0)["A"]
+# TACS_MAT_TRANSPOSE: the same Jacobian assembled with the element matrices transposed
+rt = ra.assemble_jacobian(pm, alpha=1.0, beta=0.0, gamma=1e4, transpose=True)
+At = ra.mat_block(pm, 0)["A"]
 # TACSFrequencyAnalysis::solve (K and M through assembleMatType, shift-invert Lanczos)
 fk, fm = ra.mat_create(1), ra.mat_create(1)
 feig, ferr = ra.frequency(fk, fm, sigma=1e6, num_eigs=6, max_lanczos=60)
@@ -43,4 +46,6 @@ print("SHIM_PROBE " + json.dumps(dict(eig=eig[:6].tolist(), err=err[:6].tolist()
                                      a_max=float(np.abs(A).max()), a_sum=float(A.sum()),
                                      m_max=float(np.abs(M[M != 1.0]).max()), m_chk=float(((M - (M == 1.0)) * w).sum()),
                                      rd_max=float(np.abs(rd).max()), rd_chk=float((rd * w.ravel()[:rd.size].reshape(rd.shape)).sum()),
-                                     ad_max=float(np.abs(Ad).max()), ad_chk=float((Ad * w).sum()))))
+                                     ad_max=float(np.abs(Ad).max()), ad_chk=float((Ad * w).sum()),
+                                     at_max=float(np.abs(At).max()), at_chk=float((At * w).sum()),
+                                     at_vs_ad=float(np.abs(At - Ad).max() / np.abs(Ad).max()))))

@@ -57,3 +57,8 @@ def test_reference_buckling_flow_runs_on_gpu_through_the_shim(ref):
     assert abs(gpu["rd_chk"] - base["rd_chk"]) <= 1e-10 * base["rd_max"]
     assert abs(gpu["ad_max"] - base["ad_max"]) <= 1e-10 * base["ad_max"]
     assert abs(gpu["ad_chk"] - base["ad_chk"]) <= 1e-9 * base["ad_max"]
+    # TACS_MAT_TRANSPOSE: symmetric element matrices, so the reference's transposed assembly is
+    # its normal one to rounding, and the shim takes the same device path for both
+    assert base["at_vs_ad"] < 1e-13 and gpu["at_vs_ad"] < 1e-13
+    assert abs(gpu["at_max"] - base["at_max"]) <= 1e-10 * base["at_max"]
+    assert abs(gpu["at_chk"] - base["at_chk"]) <= 1e-9 * base["at_max"]
