@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/a2ds.h"
@@ -722,6 +723,9 @@ struct a2ds_ctx {
   bool mesh_set = false;
   int *conn = nullptr, *elem_comp = nullptr;
   std::vector<int> h_conn, h_elem_comp, h_class;
+  // natural-order pattern of the current mesh, built by the first a2ds_mat_create_natural
+  std::vector<int> nat_rowp, nat_cols;
+  bool nat_ready = false;
   std::vector<double> h_mom;          // mass moments per component (a2ds_set_mass_moments)
   std::vector<CompData> h_comps;
   double *X = nullptr, *u = nullptr, *res = nullptr;
@@ -859,6 +863,7 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
                   "(dependent nodes are not supported)");
   c->n_nodes = n_nodes; c->n_owned = n_owned; c->n_elems = n_elems;
   c->h_conn.assign(conn, conn + 4 * (size_t)n_elems);
+  c->nat_ready = false;
   if (elem_comp) c->h_elem_comp.assign(elem_comp, elem_comp + n_elems);
   else c->h_elem_comp.assign(n_elems, 0);
   if (upload(&c->conn, conn, 4 * (size_t)n_elems, c->stream)) return 1;
@@ -1159,7 +1164,9 @@ static int check_mat(a2ds_ctx *c, int mat, int block = 0) {
   return 0;
 }
 
-// node -> nodes of its elements (4 per incidence), then sort + unique per row
+// node -> nodes of its elements (4 per incidence), then sort + unique per row.  The rows are
+// independent once the incidences are bucketed: the sort / unique pass runs on all host cores
+// (two sweeps: count the distinct columns of every row, then write them at their offsets).
 static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &rowp,
                            std::vector<int> &cols) {
   std::vector<int> ptr(nn + 1, 0);
@@ -1177,16 +1184,31 @@ static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &ro
       const int r = conn[4 * e + i];
       for (int j = 0; j < 4; j++) tmp[fill[r]++] = conn[4 * e + j];
     }
+  fill.clear(); fill.shrink_to_fit();
   rowp.assign(nn + 1, 0);
-  cols.clear();
-  cols.reserve((size_t)9 * nn + 16);
-  for (int r = 0; r < nn; r++) {
-    std::sort(tmp.begin() + ptr[r], tmp.begin() + ptr[r + 1]);
-    int last = -1;
-    for (int k = ptr[r]; k < ptr[r + 1]; k++)
-      if (k == ptr[r] || tmp[k] != last) { cols.push_back(tmp[k]); last = tmp[k]; }
-    rowp[r + 1] = (int)cols.size();
-  }
+  const int nt = (int)std::max(1u, std::min(16u, nn < (1 << 16) ? 1u : std::thread::hardware_concurrency()));
+  auto sweep = [&](bool write) {
+    auto work = [&](int t) {
+      const int r0 = (int)((long long)nn * t / nt), r1 = (int)((long long)nn * (t + 1) / nt);
+      for (int r = r0; r < r1; r++) {
+        int *b = tmp.data() + ptr[r], *e = tmp.data() + ptr[r + 1];
+        if (!write) {
+          std::sort(b, e);
+          rowp[r + 1] = (int)(std::unique(b, e) - b);   // distinct columns now lead the bucket
+        } else {
+          std::copy(b, b + (rowp[r + 1] - rowp[r]), cols.begin() + rowp[r]);
+        }
+      }
+    };
+    if (nt == 1) { work(0); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++) pool.emplace_back(work, t);
+    for (auto &th : pool) th.join();
+  };
+  sweep(false);
+  for (int r = 0; r < nn; r++) rowp[r + 1] += rowp[r];
+  cols.assign((size_t)rowp[nn], 0);
+  sweep(true);
   return 0;
 }
 
@@ -1212,10 +1234,12 @@ extern "C" int a2ds_host_color_elements(int n_nodes, int n_elems, const int *con
 
 extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   if (!c->mesh_set) return fail("a2ds_mat_create_natural: call a2ds_set_mesh first");
-  std::vector<int> rowp, cols;
-  if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), rowp, cols)) return 1;
+  if (!c->nat_ready) {
+    if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), c->nat_rowp, c->nat_cols)) return 1;
+    c->nat_ready = true;
+  }
   const int nrows = c->n_nodes;
-  const int *rp = rowp.data(), *cp = cols.data();
+  const int *rp = c->nat_rowp.data(), *cp = c->nat_cols.data();
   const int ident = 1;
   return a2ds_mat_create(c, 1, &nrows, &rp, &cp, nullptr, nullptr, &ident, mat);
 }

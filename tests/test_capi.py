@@ -53,6 +53,15 @@ def test_host_pattern_matches_oracle_pattern(a2ds, orc):
     assert rp.tolist() == [0] * 5 and len(cl) == 0
 
 
+def test_host_pattern_threaded_path(a2ds, orc):
+    """above 65 536 nodes the sort / unique sweep of the pattern runs on several host threads"""
+    for conn, X in (a2ds.meshes.plate(300, 280)[:2], a2ds.meshes.cubed_sphere(120, shuffle_seed=5)[:2]):
+        assert len(X) > (1 << 16)
+        rp, cl = a2ds.host_pattern(len(X), conn)
+        rpo, clo = orc.pattern(len(X), conn)
+        assert rp.tobytes() == rpo.tobytes() and cl.tobytes() == clo.tobytes()
+
+
 def test_host_pattern_matches_golden(a2ds):
     for name in ("plate", "cylinder"):
         g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
