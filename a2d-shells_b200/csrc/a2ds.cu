@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -40,6 +41,18 @@ static int fail(const std::string &m) {
   g_err = m;
   return 1;
 }
+// A2DS_VERBOSE=1: wall time of the host-side set-up stages on stderr
+struct StageTimer {
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  const bool on = getenv("A2DS_VERBOSE") != nullptr;
+  void lap(const char *what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[a2ds] %-28s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
+
 #define CU(call)                                                                       \
   do {                                                                                 \
     cudaError_t e_ = (call);                                                           \
@@ -1099,6 +1112,7 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   CU(cudaSetDevice(c->device));
   if (n_blocks < 1 || n_blocks > 4) return fail("a2ds_mat_create: 1..4 BCSR blocks");
   if (!c->mesh_set) return fail("a2ds_mat_create: call a2ds_set_mesh first");
+  StageTimer tm;
   MatrixRec m;
   m.n_blocks = n_blocks;
   std::vector<BlockDev> hb(n_blocks);
@@ -1125,6 +1139,7 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
     total += nnz;
   }
   if (total >= (1ll << 31)) return fail("a2ds_mat_create: more than 2^31 blocks on one GPU");
+  tm.lap("mat_create: pattern upload");
   m.total = total;
   CU(cudaMalloc((void **)&m.A, std::max<long long>(total, 1) * 36 * sizeof(double)));
   m.owned.push_back(m.A);
@@ -1147,13 +1162,15 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   int missing = 0;
   CU(cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  tm.lap("mat_create: alloc+zero+offsets");
   cudaFree(d_missing);
   if (missing) {
     for (void *p : m.owned) cudaFree(p);
     return fail("a2ds_mat_create: " + std::to_string(missing) +
                 " element blocks have no entry in the supplied non-zero pattern");
   }
-  c->mats.push_back(m);
+  c->mats.push_back(std::move(m));
+  tm.lap("mat_create: record");
   *mat = (int)c->mats.size() - 1;
   return 0;
 }
@@ -1235,8 +1252,10 @@ extern "C" int a2ds_host_color_elements(int n_nodes, int n_elems, const int *con
 extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   if (!c->mesh_set) return fail("a2ds_mat_create_natural: call a2ds_set_mesh first");
   if (!c->nat_ready) {
+    StageTimer tm;
     if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), c->nat_rowp, c->nat_cols)) return 1;
     c->nat_ready = true;
+    tm.lap("natural pattern (host)");
   }
   const int nrows = c->n_nodes;
   const int *rp = c->nat_rowp.data(), *cp = c->nat_cols.data();
