@@ -1018,10 +1018,19 @@ extern "C" int a2ds_set_state(a2ds_ctx *c, int n_given, const double *u) {
 extern "C" int a2ds_set_bcs(a2ds_ctx *c, int n_bc, const int *nodes, const int *vars,
                             const double *vals) {
   CU(cudaSetDevice(c->device));
+  if (!c->mesh_set) return fail("a2ds_set_bcs: call a2ds_set_mesh first");
+  if (n_bc < 0 || (n_bc > 0 && (!nodes || !vars))) return fail("a2ds_set_bcs: bad arguments");
+  for (int b = 0; b < n_bc; b++) {
+    if (nodes[b] < 0 || nodes[b] >= c->n_nodes)
+      return fail("a2ds_set_bcs: boundary-condition node " + std::to_string(nodes[b]) +
+                  " is outside [0, n_nodes)");
+    // bits above the six shell DOFs are ignored (TACSBcMap carries them for larger blocks)
+  }
+  const std::vector<double> zeros(vals ? 0 : 6 * (size_t)n_bc, 0.0);  // NULL: homogeneous
   c->n_bc = n_bc;
   if (upload(&c->bc_nodes, nodes, (size_t)n_bc, c->stream)) return 1;
   if (upload(&c->bc_vars, vars, (size_t)n_bc, c->stream)) return 1;
-  if (upload(&c->bc_vals, vals, 6 * (size_t)n_bc, c->stream)) return 1;
+  if (upload(&c->bc_vals, vals ? vals : zeros.data(), 6 * (size_t)n_bc, c->stream)) return 1;
   return 0;
 }
 
@@ -1404,6 +1413,11 @@ extern "C" int a2ds_mat_mult(a2ds_ctx *c, int mat, int block, int ncols, const d
   if (check_mat(c, mat, block)) return 1;
   CU(cudaSetDevice(c->device));
   const int nrows = c->mats[mat].nrows[block];
+  const std::vector<int> &hc = c->mats[mat].h_cols[block];
+  const int max_col = hc.empty() ? -1 : *std::max_element(hc.begin(), hc.end());
+  if (ncols <= max_col || !x || !y)
+    return fail("a2ds_mat_mult: x has " + std::to_string(ncols) + " block columns, the matrix "
+                "block refers to column " + std::to_string(max_col));
   double *dx = nullptr, *dy = nullptr;
   CU(cudaMalloc((void **)&dx, std::max<size_t>(6 * (size_t)ncols, 1) * sizeof(double)));
   CU(cudaMalloc((void **)&dy, std::max<size_t>(6 * (size_t)nrows, 1) * sizeof(double)));
@@ -1446,6 +1460,22 @@ extern "C" int a2ds_comm_init(a2ds_ctx *c, int n_ranks, int rank, const char id[
 extern "C" int a2ds_set_halo(a2ds_ctx *c, int n_peers, const int *peer_rank, const int *send_ptr,
                              const int *send_nodes, const int *recv_ptr, const int *recv_nodes) {
   CU(cudaSetDevice(c->device));
+  if (!c->mesh_set) return fail("a2ds_set_halo: call a2ds_set_mesh first");
+  if (n_peers < 0 || !send_ptr || !recv_ptr || send_ptr[0] != 0 || recv_ptr[0] != 0)
+    return fail("a2ds_set_halo: bad arguments");
+  for (int p = 0; p < n_peers; p++) {
+    if (peer_rank[p] < 0 || (c->comm && (peer_rank[p] >= c->n_ranks || peer_rank[p] == c->rank)))
+      return fail("a2ds_set_halo: peer rank " + std::to_string(peer_rank[p]) + " is not another rank");
+    if (send_ptr[p + 1] < send_ptr[p] || recv_ptr[p + 1] < recv_ptr[p])
+      return fail("a2ds_set_halo: send_ptr / recv_ptr must not decrease");
+  }
+  // owners send owned nodes, ghosts are received: anything else would overwrite owned values
+  for (int i = 0; i < send_ptr[n_peers]; i++)
+    if (send_nodes[i] < 0 || send_nodes[i] >= c->n_owned)
+      return fail("a2ds_set_halo: send list holds a node that is not an owned node");
+  for (int i = 0; i < recv_ptr[n_peers]; i++)
+    if (recv_nodes[i] < c->n_owned || recv_nodes[i] >= c->n_nodes)
+      return fail("a2ds_set_halo: receive list holds a node that is not a ghost node");
   c->peers.assign(peer_rank, peer_rank + n_peers);
   c->send_ptr.assign(send_ptr, send_ptr + n_peers + 1);
   c->recv_ptr.assign(recv_ptr, recv_ptr + n_peers + 1);

@@ -681,6 +681,12 @@ def test_error_behaviour_is_loud(a2ds):
         asm.mat_set_halo(k, [0], [np.array([len(cols)], dtype=np.int32)], [np.zeros(0, dtype=np.int32)])
     with pytest.raises(a2ds.A2dsError):           # unknown scatter mode
         asm.set_scatter_mode(9)
+    with pytest.raises(a2ds.A2dsError, match="outside"):      # BC on a node that does not exist
+        asm.set_bcs([n], 63)
+    with pytest.raises(a2ds.A2dsError, match="not a ghost"):  # halo that would overwrite an owned node
+        asm.set_halo([1], [np.array([0], dtype=np.int32)], [np.array([1], dtype=np.int32)])
+    with pytest.raises(a2ds.A2dsError, match="block columns"):   # x too short for the matrix
+        asm.mat_mult(k, np.zeros((n - 1, 6)))
     # the context is still usable after all of that
     asm.set_state(a2ds.meshes.seeded_state(np.arange(n), 1e-5))
     r = asm.assembleJacobian(1.0, 0.0, 0.0, k)
