@@ -103,7 +103,8 @@ int a2ds_set_state_dev(a2ds_ctx *ctx, int n_given, const double *u_dev);
 int a2ds_set_state_rates(a2ds_ctx *ctx, int n_given, const double *udot, const double *uddot);
 
 /* TACSBcMap (src/bpmat/KSM.h:43-75): bc_nodes[b] local node, bc_vars[b] bit mask of
- * constrained DOFs, bc_vals[6 b + k] prescribed values */
+ * constrained DOFs (bits above the six shell DOFs are ignored), bc_vals[6 b + k] prescribed
+ * values (NULL: all zero).  Nodes outside [0, n_nodes) are refused. */
 int a2ds_set_bcs(a2ds_ctx *ctx, int n_bc, const int *bc_nodes, const int *bc_vars,
                  const double *bc_vals);
 
