@@ -36,7 +36,7 @@ SYMBOLS = [
     "a2ds_mesh_free", "a2ds_mesh_sizes", "a2ds_mesh_connectivity", "a2ds_mesh_bcs",
     "a2ds_mesh_file_numbers", "a2ds_mesh_component", "a2ds_mesh_quad4",
     "a2ds_partition_build", "a2ds_partition_free", "a2ds_partition_sizes", "a2ds_partition_mesh",
-    "a2ds_partition_halo", "a2ds_partition_apply",
+    "a2ds_partition_halo", "a2ds_partition_apply", "a2ds_partition_rcb",
 ]
 
 _LIB = None
@@ -231,6 +231,18 @@ class Mesh:
             self.close()
         except Exception:
             pass
+
+
+def partition_rcb(conn, X, n_ranks):
+    """element -> rank by recursive coordinate bisection (a2ds_partition_rcb); host only"""
+    L = load_library()
+    conn = _i32(conn).reshape(-1, 4)
+    X = _f64(X).reshape(-1, 3)
+    out = np.zeros(conn.shape[0], dtype=np.int32)
+    if L.a2ds_partition_rcb(C.c_int(X.shape[0]), C.c_int(conn.shape[0]), _p(conn), _p(X),
+                            C.c_int(n_ranks), _p(out)):
+        raise A2dsError(L.a2ds_last_error().decode())
+    return out
 
 
 class Partition:

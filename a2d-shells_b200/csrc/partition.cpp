@@ -117,6 +117,60 @@ extern "C" int a2ds_partition_build(int n_nodes, int n_elems, const int *conn,
   return 0;
 }
 
+// Element -> rank by recursive coordinate bisection of the element centroids: the set is split
+// at the median along its longest axis into two parts sized in proportion to the ranks each
+// side gets, recursively.  Deterministic, balanced to within one element per split, compact
+// parts (short interfaces) on shell structures.  Stands in for the METIS call of
+// TACSCreator::partitionMesh (src/TACSCreator.cpp:923, METIS calls :1118-1125) — the reference's partitioner is an
+// external library; any element -> rank array works with a2ds_partition_build.
+namespace {
+void rcb(std::vector<int> &ids, int lo, int hi, int r0, int r1, const double *cen, int *elem_rank) {
+  if (r1 - r0 == 1 || hi - lo <= 0) {
+    for (int i = lo; i < hi; i++) elem_rank[ids[i]] = r0;
+    return;
+  }
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = lo; i < hi; i++)
+    for (int k = 0; k < 3; k++) {
+      mn[k] = std::min(mn[k], cen[3 * (size_t)ids[i] + k]);
+      mx[k] = std::max(mx[k], cen[3 * (size_t)ids[i] + k]);
+    }
+  int ax = 0;
+  for (int k = 1; k < 3; k++)
+    if (mx[k] - mn[k] > mx[ax] - mn[ax]) ax = k;
+  const int rm = r0 + (r1 - r0) / 2;
+  const int mid = lo + (int)((long long)(hi - lo) * (rm - r0) / (r1 - r0));
+  // ties broken by element number: the split does not depend on the input order of `ids`
+  std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int a, int b) {
+    const double ca = cen[3 * (size_t)a + ax], cb = cen[3 * (size_t)b + ax];
+    return ca < cb || (ca == cb && a < b);
+  });
+  rcb(ids, lo, mid, r0, rm, cen, elem_rank);
+  rcb(ids, mid, hi, rm, r1, cen, elem_rank);
+}
+}  // namespace
+
+extern "C" int a2ds_partition_rcb(int n_nodes, int n_elems, const int *conn, const double *X,
+                                  int n_ranks, int *elem_rank) {
+  if (n_nodes < 0 || n_elems < 0 || n_ranks < 1) return a2ds_set_error_("a2ds_partition_rcb: bad sizes");
+  std::vector<double> cen(3 * (size_t)n_elems);
+  for (int e = 0; e < n_elems; e++)
+    for (int k = 0; k < 3; k++) {
+      double c = 0.0;
+      for (int i = 0; i < 4; i++) {
+        const int n = conn[4 * (size_t)e + i];
+        if (n < 0 || n >= n_nodes)
+          return a2ds_set_error_("a2ds_partition_rcb: connectivity refers to a node outside [0, n_nodes)");
+        c += X[3 * (size_t)n + k];
+      }
+      cen[3 * (size_t)e + k] = 0.25 * c;
+    }
+  std::vector<int> ids(n_elems);
+  for (int e = 0; e < n_elems; e++) ids[e] = e;
+  rcb(ids, 0, n_elems, 0, n_ranks, cen.data(), elem_rank);
+  return 0;
+}
+
 extern "C" void a2ds_partition_free(a2ds_partition *p) { delete p; }
 
 extern "C" int a2ds_partition_sizes(const a2ds_partition *p, int *n_local_nodes, int *n_owned,

@@ -253,6 +253,12 @@ int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *col
  * (src/bpmat/TACSBVecDistribute.cpp:280-420): per peer, my nodes it reads as ghosts and my
  * ghosts it owns, both in ascending global order — so the two sides of a pair agree. */
 typedef struct a2ds_partition a2ds_partition;
+/* element -> rank by recursive coordinate bisection of the element centroids (X: 3 per global
+ * node): balanced, deterministic, compact parts.  In place of the METIS call of
+ * TACSCreator::partitionMesh (src/TACSCreator.cpp:923, METIS calls :1118-1125); any other element -> rank array
+ * (slabs, METIS output) works with a2ds_partition_build just as well. */
+int a2ds_partition_rcb(int n_nodes, int n_elems, const int *conn, const double *X, int n_ranks,
+                       int *elem_rank);
 int a2ds_partition_build(int n_nodes, int n_elems, const int *conn, const int *elem_rank,
                          int n_ranks, int rank, a2ds_partition **part);
 void a2ds_partition_free(a2ds_partition *part);

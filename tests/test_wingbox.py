@@ -61,6 +61,35 @@ def test_wingbox_topology_pattern_colouring_partition(a2ds, orc):
             assert np.array_equal(p.glob[p.send_lists[k]], o.glob[o.recv_lists[ko]])
 
 
+def test_rcb_partition_is_balanced_compact_and_deterministic(a2ds):
+    """a2ds_partition_rcb (in place of the reference's METIS call): element counts differ by at
+    most one per bisection, interfaces an order of magnitude shorter than a random partition,
+    the result does not depend on anything but the mesh"""
+    conn, X, comp, root = a2ds.meshes.wingbox(24, 4, 12, 3)
+    n = len(X)
+    for N in (1, 2, 3, 5, 8):
+        er = a2ds.partition_rcb(conn, X, N)
+        assert np.array_equal(er, a2ds.partition_rcb(conn, X, N))
+        cnt = np.bincount(er, minlength=N)
+        assert cnt.sum() == len(conn) and cnt.max() - cnt.min() <= int(np.ceil(np.log2(max(N, 2))))
+        if N == 1:
+            continue
+        P = [a2ds.Partition(conn, n, er, N, r) for r in range(N)]
+        rnd = np.random.default_rng(0).integers(0, N, len(conn))
+        R = [a2ds.Partition(conn, n, rnd, N, r) for r in range(N)]
+        ghosts = sum(p.n_nodes - p.n_owned for p in P)
+        assert 10 * ghosts < sum(p.n_nodes - p.n_owned for p in R)
+        assert sum(p.n_owned for p in P) == n
+    # elements of a part are neighbours in space: every part's bounding box along the span is
+    # a fraction of the wing for a span-dominated box
+    er = a2ds.partition_rcb(conn, X, 8)
+    cen = X[conn].mean(axis=1)
+    widths = [np.ptp(cen[er == r, 0]) for r in range(8)]
+    assert max(widths) < 0.3 * np.ptp(cen[:, 0])
+    with pytest.raises(a2ds.A2dsError, match="outside"):
+        a2ds.partition_rcb(conn + n, X, 2)
+
+
 def test_wingbox_oracle_against_reference_live(a2ds, orc, ref):
     """pins the oracle on this topology and constitutive family: residual, K and G of the
     UNMODIFIED reference (general 22-entry tangent per component, reference-axis transform)"""
