@@ -228,6 +228,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries the ONE JSON line and nothing else: libraries that write to the C-level
+    # stdout (NCCL prints its version there when NCCL_DEBUG is set) go to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -446,7 +451,8 @@ def main():
                     line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "error": str(e)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     asm.close()
     if world > 1:
         dist.destroy_process_group()
