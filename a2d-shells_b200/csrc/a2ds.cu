@@ -227,7 +227,28 @@ __device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWor
 
 // A warp prepares NB elements at a time: the node phase and the Gauss-point phase then run
 // on NB*4 distinct work items (one lane each) instead of 8 redundant copies per element.
-static const int NB = 4;
+// Build-time knobs for occupancy experiments (defaults = the measured configuration):
+//   A2DS_NB          elements per batch (1, 2, 4 or 8).  Shared memory per warp scales with it:
+//                    27.7 KB at 4, 19.4 KB at 2 for the geometric-stiffness / nonlinear variants
+//   A2DS_PREFETCH_G  0: no double-buffered gather for those variants (-0.7 KB per warp at NB 2)
+//   A2DS_MB_G        blocks per SM the launch bounds ask for (3 -> 168 registers, 12 warps/SM)
+// e.g. -DA2DS_NB=2 -DA2DS_PREFETCH_G=0 -DA2DS_MB_G=3: 18.7 KB per warp, 12 instead of 8 warps
+// per SM for the fused kernel (192 B of spills per thread) — see profiles/README.md.
+#ifndef A2DS_NB
+#define A2DS_NB 4
+#endif
+#ifndef A2DS_PREFETCH_G
+#define A2DS_PREFETCH_G 1
+#endif
+#if A2DS_PREFETCH_G
+#define A2DS_RAW1(ws) (ws).raw1
+#define A2DS_GOFF1 1
+#else   // never selected at run time (PF is false), only has to name something that exists
+#define A2DS_RAW1(ws) (ws).raw0
+#define A2DS_GOFF1 0
+#endif
+static const int NB = A2DS_NB;
+static_assert(NB == 1 || NB == 2 || NB == 4 || NB == 8, "one lane per (element, node): NB * 4 <= 32");
 struct RawBatch {          // gathered inputs of one batch, filled by cp.async
   double xq[NB][36];       // per element: X[12] then q[24]
   int koff[NB][16];
@@ -243,8 +264,12 @@ struct WarpScratch {
   double E2[24 * KE_LD];  // second staging buffer (geometric stiffness)
   ElemWork work;
   double Pq[NB][4][6];    // per Gauss point T T^T
+#if A2DS_PREFETCH_G
   RawBatch raw1;          // double buffer: batch i+1 lands (cp.async) while batch i is processed
   int goff[2][NB][16];    // block offsets of the geometric stiffness matrix (per raw buffer)
+#else
+  int goff[1][NB][16];    // block offsets of the geometric stiffness matrix
+#endif
 };
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
@@ -266,7 +291,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
   ElemWork &wk = ws.work;
-  const bool PF = GMAT || NL;  // full scratch + asynchronous prefetch of the next batch
+  // full scratch + asynchronous prefetch of the next batch
+  const bool PF = (GMAT || NL) && A2DS_PREFETCH_G != 0;
   const unsigned FULL = 0xffffffffu;
   Want w;
   w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL; w.thermal = p.thermal;
@@ -343,8 +369,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     if (!PF) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
     cp_async_wait_all();
     __syncwarp();
-    const RawBatch &rb = (PF && buf) ? ws.raw1 : ws.raw0;
-    const int (*goffb)[16] = ws.goff[(PF && buf) ? 1 : 0];
+    const RawBatch &rb = (PF && buf) ? A2DS_RAW1(ws) : ws.raw0;
+    const int (*goffb)[16] = ws.goff[(PF && buf) ? A2DS_GOFF1 : 0];
     if (lane < 4 * NB) ws.nodes[lane >> 2][lane & 3] = nd_cur;
 #pragma unroll
     for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
@@ -372,7 +398,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     }
     // start the gather of the next batch into the other raw buffer
     if (PF && grp_nxt < n_groups)
-      issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ? 0 : 1], e_nxt, nd_nxt);
+      issue_gather(buf ? ws.raw0 : A2DS_RAW1(ws), ws.goff[buf ? 0 : A2DS_GOFF1], e_nxt, nd_nxt);
     if (PF) { e_cur = e_nxt; nd_cur = nd_nxt; }
     __syncwarp();
 

@@ -18,7 +18,7 @@ if [ "$1" = build ]; then
       "$ROOT"/a2d-shells_b200/csrc/a2ds.cu "$ROOT"/a2d-shells_b200/csrc/mesh_io.cpp \
       "$ROOT"/a2d-shells_b200/csrc/partition.cpp -lnccl 2>&1 |
       grep -E "Compiling entry|Used|spill" | grep -A2 k_assemble | grep -E "Compiling|Used|spill" |
-      paste - - - | sed -E "s/.*function '([^']+)'.*([0-9]+) bytes spill stores.*Used ([0-9]+) registers.*/  \3 regs, \2 B spill  \1/"
+      paste - - - | sed -E "s/.*function '([^']+)'.* ([0-9]+) bytes stack frame, ([0-9]+) bytes spill stores, ([0-9]+) bytes spill loads.*Used ([0-9]+) registers.*/  \5 regs, spill st \3 ld \4 B  \1/"
   done
 elif [ "$1" = run ]; then
   nx="${2:-700}"; mkdir -p "$ROOT/gpurun_out"; out="$ROOT/gpurun_out/variants.txt"; : > "$out"
