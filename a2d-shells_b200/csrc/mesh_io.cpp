@@ -687,6 +687,21 @@ extern "C" int a2ds_mesh_read_bin(const char *path, a2ds_mesh **out) {
       fclose(fp);
       return failm(std::string("a2ds_mesh_read_bin: corrupt header in ") + path);
     }
+  // the header fixes the file size: check it before allocating anything from it
+  {
+    auto padded = [](int64_t n, int64_t size) { return (n * size + 7) / 8 * 8; };
+    const int64_t want = 8 + 6 * 8 + padded(c[1] + 1, 4) + padded(c[2], 4) + padded(c[1], 4) +
+                         padded(3 * c[0], 8) + padded(c[3], 4) + padded(c[3] + 1, 4) +
+                         padded(c[4], 4) + padded(c[4], 8) + padded(c[0], 4) + padded(c[1], 4) +
+                         padded(9 * c[5], 1) + padded(33 * c[5], 1);
+    fseek(fp, 0, SEEK_END);
+    const int64_t have = (int64_t)ftell(fp);
+    fseek(fp, 8 + 6 * 8, SEEK_SET);
+    if (have != want) {
+      fclose(fp);
+      return failm(std::string("a2ds_mesh_read_bin: truncated or inconsistent file ") + path);
+    }
+  }
   a2ds_mesh *m = new a2ds_mesh();
   m->n_comp = (int)c[5];
   bool ok = get(fp, m->elem_ptr, c[1] + 1) && get(fp, m->elem_conn, c[2]) &&

@@ -187,6 +187,11 @@ def test_reader_failures_are_loud(a2ds, tmp_path):
     open(p, "wb").write(raw[:len(raw) // 2])
     with pytest.raises(a2ds.A2dsError, match="truncated or inconsistent"):
         a2ds.Mesh.read_bin(p)
+    # a header that claims gigabytes is refused before anything is allocated from it
+    import struct
+    open(p, "wb").write(b"A2DSMSH1" + struct.pack("<6q", 2**31 - 1, 2**31 - 1, 2**31 - 1, 0, 0, 1) + b"\0" * 64)
+    with pytest.raises(a2ds.A2dsError, match="truncated or inconsistent"):
+        a2ds.Mesh.read_bin(p)
 
 
 def test_nastran_real_forms(a2ds, tmp_path):
