@@ -50,6 +50,16 @@ namespace {
 
 int failm(const std::string &m) { return a2ds_set_error_(m.c_str()); }
 
+// no exception leaves the C ABI: out-of-memory and the like become an error return
+template <class F>
+int guarded(const char *what, F &&body) {
+  try {
+    return body();
+  } catch (const std::exception &e) {
+    return failm(std::string(what) + ": " + e.what());
+  }
+}
+
 // element keywords in matching order (longer keywords before their prefixes) with the
 // admissible node counts — src/io/TACSMeshLoader.h:20-35
 struct ElemKind { const char *key; int len, nmin, nmax; };
@@ -403,7 +413,7 @@ struct a2ds_mesh {
   long n_unknown = 0;
 };
 
-extern "C" int a2ds_mesh_read_bdf(const char *path, int n_threads, a2ds_mesh **out) {
+static int read_bdf_impl(const char *path, int n_threads, a2ds_mesh **out) {
   *out = nullptr;
   FILE *fp = fopen(path, "rb");
   if (!fp) return failm(std::string("a2ds_mesh_read_bdf: unable to open file ") + path);
@@ -671,7 +681,7 @@ extern "C" int a2ds_mesh_write_bin(const a2ds_mesh *m, const char *path) {
   return ok ? 0 : failm(std::string("a2ds_mesh_write_bin: short write to ") + path);
 }
 
-extern "C" int a2ds_mesh_read_bin(const char *path, a2ds_mesh **out) {
+static int read_bin_impl(const char *path, a2ds_mesh **out) {
   *out = nullptr;
   FILE *fp = fopen(path, "rb");
   if (!fp) return failm(std::string("a2ds_mesh_read_bin: unable to open file ") + path);
@@ -727,10 +737,10 @@ extern "C" int a2ds_mesh_read_bin(const char *path, a2ds_mesh **out) {
 }
 
 // a mesh container from arrays already in memory (generated meshes -> binary file)
-extern "C" int a2ds_mesh_from_arrays(int n_nodes, int n_elems, const int *elem_ptr,
-                                     const int *elem_conn, const int *elem_comp, const double *X,
-                                     int n_bcs, const int *bc_nodes, const int *bc_ptr,
-                                     const int *bc_vars, const double *bc_vals, a2ds_mesh **out) {
+static int from_arrays_impl(int n_nodes, int n_elems, const int *elem_ptr, const int *elem_conn,
+                            const int *elem_comp, const double *X, int n_bcs, const int *bc_nodes,
+                            const int *bc_ptr, const int *bc_vars, const double *bc_vals,
+                            a2ds_mesh **out) {
   *out = nullptr;
   if (n_nodes < 0 || n_elems < 0 || n_bcs < 0) return failm("a2ds_mesh_from_arrays: bad sizes");
   a2ds_mesh *m = new a2ds_mesh();
@@ -760,4 +770,20 @@ extern "C" int a2ds_mesh_from_arrays(int n_nodes, int n_elems, const int *elem_p
     }
   *out = m;
   return 0;
+}
+
+extern "C" int a2ds_mesh_read_bdf(const char *path, int n_threads, a2ds_mesh **out) {
+  return guarded("a2ds_mesh_read_bdf", [&] { return read_bdf_impl(path, n_threads, out); });
+}
+extern "C" int a2ds_mesh_read_bin(const char *path, a2ds_mesh **out) {
+  return guarded("a2ds_mesh_read_bin", [&] { return read_bin_impl(path, out); });
+}
+extern "C" int a2ds_mesh_from_arrays(int n_nodes, int n_elems, const int *elem_ptr,
+                                     const int *elem_conn, const int *elem_comp, const double *X,
+                                     int n_bcs, const int *bc_nodes, const int *bc_ptr,
+                                     const int *bc_vars, const double *bc_vals, a2ds_mesh **out) {
+  return guarded("a2ds_mesh_from_arrays", [&] {
+    return from_arrays_impl(n_nodes, n_elems, elem_ptr, elem_conn, elem_comp, X, n_bcs, bc_nodes,
+                            bc_ptr, bc_vars, bc_vals, out);
+  });
 }

@@ -33,9 +33,8 @@ struct a2ds_partition {
   std::vector<int> peers, send_ptr, send_nodes, recv_ptr, recv_nodes;
 };
 
-extern "C" int a2ds_partition_build(int n_nodes, int n_elems, const int *conn,
-                                    const int *elem_rank, int n_ranks, int rank,
-                                    a2ds_partition **out) {
+static int build_impl(int n_nodes, int n_elems, const int *conn, const int *elem_rank, int n_ranks,
+                      int rank, a2ds_partition **out) {
   *out = nullptr;
   if (n_nodes < 0 || n_elems < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
     return a2ds_set_error_("a2ds_partition_build: bad sizes");
@@ -150,8 +149,8 @@ void rcb(std::vector<int> &ids, int lo, int hi, int r0, int r1, const double *ce
 }
 }  // namespace
 
-extern "C" int a2ds_partition_rcb(int n_nodes, int n_elems, const int *conn, const double *X,
-                                  int n_ranks, int *elem_rank) {
+static int rcb_impl(int n_nodes, int n_elems, const int *conn, const double *X, int n_ranks,
+                    int *elem_rank) {
   if (n_nodes < 0 || n_elems < 0 || n_ranks < 1) return a2ds_set_error_("a2ds_partition_rcb: bad sizes");
   std::vector<double> cen(3 * (size_t)n_elems);
   for (int e = 0; e < n_elems; e++)
@@ -222,4 +221,23 @@ extern "C" int a2ds_partition_apply(a2ds_ctx *ctx, const a2ds_partition *p, cons
     return 1;
   return a2ds_set_halo(ctx, (int)p->peers.size(), p->peers.data(), p->send_ptr.data(),
                        p->send_nodes.data(), p->recv_ptr.data(), p->recv_nodes.data());
+}
+
+// no exception leaves the C ABI: out-of-memory and the like become an error return
+extern "C" int a2ds_partition_build(int n_nodes, int n_elems, const int *conn,
+                                    const int *elem_rank, int n_ranks, int rank,
+                                    a2ds_partition **out) {
+  try {
+    return build_impl(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, out);
+  } catch (const std::exception &e) {
+    return a2ds_set_error_((std::string("a2ds_partition_build: ") + e.what()).c_str());
+  }
+}
+extern "C" int a2ds_partition_rcb(int n_nodes, int n_elems, const int *conn, const double *X,
+                                  int n_ranks, int *elem_rank) {
+  try {
+    return rcb_impl(n_nodes, n_elems, conn, X, n_ranks, elem_rank);
+  } catch (const std::exception &e) {
+    return a2ds_set_error_((std::string("a2ds_partition_rcb: ") + e.what()).c_str());
+  }
 }
