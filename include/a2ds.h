@@ -93,7 +93,11 @@ int a2ds_set_mass_moments(a2ds_ctx *ctx, int n_comp, const double *moments);
 
 /* TACSAssembler::setVariables (src/TACSAssembler.cpp:3825-3857): u[6 n + k] for all
  * local nodes when n_given == n_nodes, or for the owned nodes only when
- * n_given == n_owned (ghost values then come from a2ds_halo_forward). */
+ * n_given == n_owned (ghost values then come from a2ds_halo_forward).  The upload runs on a
+ * copy stream and overlaps the zeroing of the next assembly's outputs; the next consumer waits
+ * for it.  With a page-locked `u` the call returns before the copy has read it: leave the
+ * buffer unchanged until a call that synchronises (an assemble call with a host result,
+ * a2ds_synchronize).  Pageable memory is read before the call returns. */
 int a2ds_set_state(a2ds_ctx *ctx, int n_given, const double *u);
 int a2ds_set_state_dev(a2ds_ctx *ctx, int n_given, const double *u_dev);
 /* the qdot / qddot arguments of TACSAssembler::setVariables.  Only uddot enters this element
