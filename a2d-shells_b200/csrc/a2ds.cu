@@ -228,7 +228,7 @@ __device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWor
 // A warp prepares NB elements at a time: the node phase and the Gauss-point phase then run
 // on NB*4 distinct work items (one lane each) instead of 8 redundant copies per element.
 // Build-time knobs for occupancy experiments (defaults = the measured configuration):
-//   A2DS_NB          elements per batch (1, 2, 4 or 8).  Shared memory per warp scales with it:
+//   A2DS_NB          elements per batch (2, 4 or 8).  Shared memory per warp scales with it:
 //                    27.7 KB at 4, 19.4 KB at 2 for the geometric-stiffness / nonlinear variants
 //   A2DS_PREFETCH_G  0: no double-buffered gather for those variants (-0.7 KB per warp at NB 2)
 //   A2DS_MB_G        blocks per SM the launch bounds ask for (3 -> 168 registers, 12 warps/SM)
@@ -248,7 +248,8 @@ __device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWor
 #define A2DS_GOFF1 0
 #endif
 static const int NB = A2DS_NB;
-static_assert(NB == 1 || NB == 2 || NB == 4 || NB == 8, "one lane per (element, node): NB * 4 <= 32");
+static_assert(NB == 2 || NB == 4 || NB == 8,
+              "one lane per (element, node): NB * 4 <= 32; the offset gather moves 32 entries per pass");
 struct RawBatch {          // gathered inputs of one batch, filled by cp.async
   double xq[NB][36];       // per element: X[12] then q[24]
   int koff[NB][16];
