@@ -37,6 +37,7 @@ SYMBOLS = [
     "a2ds_mesh_file_numbers", "a2ds_mesh_component", "a2ds_mesh_quad4",
     "a2ds_partition_build", "a2ds_partition_free", "a2ds_partition_sizes", "a2ds_partition_mesh",
     "a2ds_partition_halo", "a2ds_partition_apply", "a2ds_partition_rcb",
+    "a2ds_partition_build_matrix", "a2ds_partition_matrix", "a2ds_partition_create_mat",
 ]
 
 _LIB = None
@@ -250,14 +251,18 @@ class Partition:
     as TACSCreator, src/TACSCreator.cpp:1156-1205).  Host only.  Attributes: n_nodes, n_owned,
     elems, conn_local (n, 4), glob, ghost_owner, peers, send_lists, recv_lists."""
 
-    def __init__(self, conn, n_nodes, elem_rank, n_ranks, rank):
+    def __init__(self, conn, n_nodes, elem_rank, n_ranks, rank, matrix_halo=False):
+        """matrix_halo: TACSParallelMat flavour — extended ghost set, local pattern (rowp, cols)
+        and per-peer block lists (mat_send_lists, mat_recv_lists); create_mat(asm) then gives a
+        matrix whose owned rows are fully assembled by every assemble call"""
         L = self.L = load_library()
         conn = _i32(conn).reshape(-1, 4)
         er = _i32(elem_rank)
         assert len(er) == len(conn)
         self.h = C.c_void_p()
-        if L.a2ds_partition_build(C.c_int(n_nodes), C.c_int(len(conn)), _p(conn), _p(er),
-                                  C.c_int(n_ranks), C.c_int(rank), C.byref(self.h)):
+        build = L.a2ds_partition_build_matrix if matrix_halo else L.a2ds_partition_build
+        if build(C.c_int(n_nodes), C.c_int(len(conn)), _p(conn), _p(er), C.c_int(n_ranks),
+                 C.c_int(rank), C.byref(self.h)):
             raise A2dsError(L.a2ds_last_error().decode())
         n = [C.c_int() for _ in range(6)]
         L.a2ds_partition_sizes(self.h, *[C.byref(x) for x in n])
@@ -279,6 +284,23 @@ class Partition:
         sp, sn, rp, rn = ints(b, npeer + 1), ints(c, ns), ints(d, npeer + 1), ints(e, nr)
         self.send_lists = [sn[sp[k]:sp[k + 1]] for k in range(npeer)]
         self.recv_lists = [rn[rp[k]:rp[k + 1]] for k in range(npeer)]
+        if matrix_halo:
+            a, b, c, d, e, f = IP(), IP(), IP(), IP(), IP(), IP()
+            if L.a2ds_partition_matrix(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d),
+                                       C.byref(e), C.byref(f)):
+                raise A2dsError(L.a2ds_last_error().decode())
+            self.rowp = ints(a, self.n_nodes + 1)
+            self.cols = ints(b, int(self.rowp[-1]) if self.n_nodes else 0)
+            sp, rp = ints(c, npeer + 1), ints(e, npeer + 1)
+            sb, rb = ints(d, int(sp[-1])), ints(f, int(rp[-1]))
+            self.mat_send_lists = [sb[sp[k]:sp[k + 1]] for k in range(npeer)]
+            self.mat_recv_lists = [rb[rp[k]:rp[k + 1]] for k in range(npeer)]
+
+    def create_mat(self, asm):
+        """a matrix with the partition's pattern and matrix halo on an Assembler"""
+        m = C.c_int()
+        asm._chk(self.L.a2ds_partition_create_mat(asm.ctx, self.h, C.byref(m)))
+        return m.value
 
     def apply(self, asm, elem_comp=None):
         """a2ds_set_mesh + a2ds_set_halo on an Assembler"""

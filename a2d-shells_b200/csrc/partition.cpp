@@ -31,10 +31,14 @@ struct a2ds_partition {
   std::vector<int> glob;        // local node -> global node: owned (ascending), then ghosts (ascending)
   std::vector<int> ghost_owner; // owner rank of each ghost
   std::vector<int> peers, send_ptr, send_nodes, recv_ptr, recv_nodes;
+  // matrix-halo mode (TACSParallelMat flavour) only:
+  bool matrix = false;
+  std::vector<int> rowp, cols;   // local pattern: full rows for owned nodes, local couplings for ghosts
+  std::vector<int> mat_send_ptr, mat_send_blocks, mat_recv_ptr, mat_recv_blocks;  // per peer
 };
 
 static int build_impl(int n_nodes, int n_elems, const int *conn, const int *elem_rank, int n_ranks,
-                      int rank, a2ds_partition **out) {
+                      int rank, bool matrix, a2ds_partition **out) {
   *out = nullptr;
   if (n_nodes < 0 || n_elems < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
     return a2ds_set_error_("a2ds_partition_build: bad sizes");
@@ -58,16 +62,32 @@ static int build_impl(int n_nodes, int n_elems, const int *conn, const int *elem
   // mark: bit 0 = used by one of my elements; per peer sets are collected as (peer, node) pairs
   std::vector<unsigned char> used((size_t)n_nodes, 0);
   std::vector<uint64_t> wanted;  // (peer << 32 | global node) for my nodes used by `peer`
+  p->matrix = matrix;
   for (int e = 0; e < n_elems; e++) {
     const int r = elem_rank[e];
+    const int *en = &conn[4 * (size_t)e];
     if (r == rank) {
       p->elems.push_back(e);
-      for (int k = 0; k < 4; k++) used[conn[4 * (size_t)e + k]] = 1;
+      for (int k = 0; k < 4; k++) used[en[k]] = 1;
     } else {
-      for (int k = 0; k < 4; k++) {
-        const int g = conn[4 * (size_t)e + k];
-        if (owner[g] == rank) wanted.push_back(((uint64_t)r << 32) | (uint32_t)g);
-      }
+      for (int k = 0; k < 4; k++)
+        if (owner[en[k]] == rank) wanted.push_back(((uint64_t)r << 32) | (uint32_t)en[k]);
+    }
+    if (matrix) {
+      // The owner of a node holds the node's whole matrix row: every node that shares an
+      // element (of any rank) with one of MY nodes is a column of mine, hence local here
+      // (the reference's external column map); and my nodes are ghosts wherever a node of
+      // another owner shares an element with them.
+      bool mine = false;
+      for (int k = 0; k < 4; k++) mine = mine || owner[en[k]] == rank;
+      if (mine)
+        for (int k = 0; k < 4; k++) {
+          used[en[k]] = 1;
+          const int o = owner[en[k]];
+          if (o != rank)
+            for (int j = 0; j < 4; j++)
+              if (owner[en[j]] == rank) wanted.push_back(((uint64_t)o << 32) | (uint32_t)en[j]);
+        }
     }
   }
   std::sort(wanted.begin(), wanted.end());
@@ -111,6 +131,81 @@ static int build_impl(int n_nodes, int n_elems, const int *conn, const int *elem
     for (size_t k = 0; k < p->ghost_owner.size(); k++)
       if (p->ghost_owner[k] == r) p->recv_nodes.push_back(p->n_owned + (int)k);
     p->recv_ptr.push_back((int)p->recv_nodes.size());
+  }
+  if (matrix) {
+    // ---- local pattern: rows of my elements' nodes (all of them), and the full row of every
+    //      owned node (contributions of any rank's elements) — count, fill, sort + unique
+    const int nl = (int)p->glob.size();
+    std::vector<int> ptr(nl + 1, 0);
+    auto for_rows = [&](auto &&visit) {
+      for (int e = 0; e < n_elems; e++) {
+        const int *en = &conn[4 * (size_t)e];
+        const bool my_elem = elem_rank[e] == rank;
+        for (int k = 0; k < 4; k++)
+          if (my_elem || owner[en[k]] == rank) visit(local_of[en[k]], en);
+      }
+    };
+    for_rows([&](int row, const int *) { ptr[row + 1] += 4; });
+    for (int i = 0; i < nl; i++) ptr[i + 1] += ptr[i];
+    std::vector<int> tmp(ptr[nl]), fill(ptr.begin(), ptr.end() - 1);
+    for_rows([&](int row, const int *en) {
+      for (int j = 0; j < 4; j++) tmp[fill[row]++] = local_of[en[j]];
+    });
+    p->rowp.assign(nl + 1, 0);
+    for (int r = 0; r < nl; r++) {
+      std::sort(tmp.begin() + ptr[r], tmp.begin() + ptr[r + 1]);
+      const int nu = (int)(std::unique(tmp.begin() + ptr[r], tmp.begin() + ptr[r + 1]) - (tmp.begin() + ptr[r]));
+      p->rowp[r + 1] = p->rowp[r] + nu;
+    }
+    p->cols.resize(p->rowp[nl]);
+    for (int r = 0; r < nl; r++)
+      std::copy(tmp.begin() + ptr[r], tmp.begin() + ptr[r] + (p->rowp[r + 1] - p->rowp[r]),
+                p->cols.begin() + p->rowp[r]);
+    auto block_of = [&](int grow, int gcol) {
+      const int lr = local_of[grow], lc = local_of[gcol];
+      const int *b = p->cols.data() + p->rowp[lr], *e = p->cols.data() + p->rowp[lr + 1];
+      const int *it = std::lower_bound(b, e, lc);
+      return (it != e && *it == lc) ? (int)(it - p->cols.data()) : -1;
+    };
+    // ---- blocks that travel: (peer, global row, global column), unique, in that order on
+    //      both sides.  I send the blocks my elements add to rows another rank owns; I receive
+    //      the blocks other ranks' elements add to rows I own.
+    struct Key { int peer, row, col; };
+    auto less = [](const Key &a, const Key &b) {
+      return a.peer != b.peer ? a.peer < b.peer : (a.row != b.row ? a.row < b.row : a.col < b.col);
+    };
+    auto same = [](const Key &a, const Key &b) { return a.peer == b.peer && a.row == b.row && a.col == b.col; };
+    std::vector<Key> snd, rcv;
+    for (int e = 0; e < n_elems; e++) {
+      const int *en = &conn[4 * (size_t)e];
+      const int r = elem_rank[e];
+      for (int k = 0; k < 4; k++) {
+        const int o = owner[en[k]];
+        if (r == rank && o != rank)
+          for (int j = 0; j < 4; j++) snd.push_back({o, en[k], en[j]});
+        if (r != rank && o == rank)
+          for (int j = 0; j < 4; j++) rcv.push_back({r, en[k], en[j]});
+      }
+    }
+    for (auto *v : {&snd, &rcv}) {
+      std::sort(v->begin(), v->end(), less);
+      v->erase(std::unique(v->begin(), v->end(), same), v->end());
+    }
+    p->mat_send_ptr.assign(1, 0);
+    p->mat_recv_ptr.assign(1, 0);
+    size_t si = 0, ri = 0;
+    for (int r : p->peers) {
+      for (; si < snd.size() && snd[si].peer <= r; si++)
+        if (snd[si].peer == r) p->mat_send_blocks.push_back(block_of(snd[si].row, snd[si].col));
+      p->mat_send_ptr.push_back((int)p->mat_send_blocks.size());
+      for (; ri < rcv.size() && rcv[ri].peer <= r; ri++)
+        if (rcv[ri].peer == r) p->mat_recv_blocks.push_back(block_of(rcv[ri].row, rcv[ri].col));
+      p->mat_recv_ptr.push_back((int)p->mat_recv_blocks.size());
+    }
+    for (int b : p->mat_send_blocks)
+      if (b < 0) { delete p; return a2ds_set_error_("a2ds_partition_build: internal: a block to send is not in the pattern"); }
+    for (int b : p->mat_recv_blocks)
+      if (b < 0) { delete p; return a2ds_set_error_("a2ds_partition_build: internal: an arriving block is not in the pattern"); }
   }
   *out = p;
   return 0;
@@ -228,10 +323,49 @@ extern "C" int a2ds_partition_build(int n_nodes, int n_elems, const int *conn,
                                     const int *elem_rank, int n_ranks, int rank,
                                     a2ds_partition **out) {
   try {
-    return build_impl(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, out);
+    return build_impl(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, false, out);
   } catch (const std::exception &e) {
     return a2ds_set_error_((std::string("a2ds_partition_build: ") + e.what()).c_str());
   }
+}
+extern "C" int a2ds_partition_build_matrix(int n_nodes, int n_elems, const int *conn,
+                                           const int *elem_rank, int n_ranks, int rank,
+                                           a2ds_partition **out) {
+  try {
+    return build_impl(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, true, out);
+  } catch (const std::exception &e) {
+    return a2ds_set_error_((std::string("a2ds_partition_build_matrix: ") + e.what()).c_str());
+  }
+}
+
+extern "C" int a2ds_partition_matrix(const a2ds_partition *p, const int **rowp, const int **cols,
+                                     const int **send_ptr, const int **send_blocks,
+                                     const int **recv_ptr, const int **recv_blocks) {
+  if (!p || !p->matrix)
+    return a2ds_set_error_("a2ds_partition_matrix: the partition was not built with a2ds_partition_build_matrix");
+  if (rowp) *rowp = p->rowp.data();
+  if (cols) *cols = p->cols.data();
+  if (send_ptr) *send_ptr = p->mat_send_ptr.data();
+  if (send_blocks) *send_blocks = p->mat_send_blocks.data();
+  if (recv_ptr) *recv_ptr = p->mat_recv_ptr.data();
+  if (recv_blocks) *recv_blocks = p->mat_recv_blocks.data();
+  return 0;
+}
+
+// a matrix over the local nodes with this pattern whose ghost-row blocks travel to their
+// owners inside every assemble call: a2ds_mat_create + a2ds_mat_set_halo
+extern "C" int a2ds_partition_create_mat(a2ds_ctx *ctx, const a2ds_partition *p, int *mat) {
+  if (!p || !p->matrix)
+    return a2ds_set_error_("a2ds_partition_create_mat: the partition was not built with a2ds_partition_build_matrix");
+  const int nl = (int)p->glob.size();
+  std::vector<int> ident(nl);
+  for (int i = 0; i < nl; i++) ident[i] = i;
+  const int *rp = p->rowp.data(), *cl = p->cols.data(), *id = ident.data();
+  const int one = 1;
+  if (a2ds_mat_create(ctx, 1, &nl, &rp, &cl, &id, &id, &one, mat)) return 1;
+  return a2ds_mat_set_halo(ctx, *mat, (int)p->peers.size(), p->peers.data(), p->mat_send_ptr.data(),
+                           p->mat_send_blocks.data(), p->mat_recv_ptr.data(),
+                           p->mat_recv_blocks.data());
 }
 extern "C" int a2ds_partition_rcb(int n_nodes, int n_elems, const int *conn, const double *X,
                                   int n_ranks, int *elem_rank) {

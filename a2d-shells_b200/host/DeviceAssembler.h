@@ -16,10 +16,13 @@ namespace a2ds {
 
 class DeviceAssembler {
  public:
-  explicit DeviceAssembler(int device = 0) : ctx_(nullptr), n_nodes_(0), n_owned_(0) {
+  explicit DeviceAssembler(int device = 0) : ctx_(nullptr), n_nodes_(0), n_owned_(0), part_(nullptr) {
     check(a2ds_create(device, &ctx_), "a2ds_create");
   }
-  ~DeviceAssembler() { if (ctx_) a2ds_destroy(ctx_); }
+  ~DeviceAssembler() {
+    if (part_) a2ds_partition_free(part_);
+    if (ctx_) a2ds_destroy(ctx_);
+  }
   DeviceAssembler(const DeviceAssembler &) = delete;
   DeviceAssembler &operator=(const DeviceAssembler &) = delete;
 
@@ -53,20 +56,32 @@ class DeviceAssembler {
   // multi-GPU, one process per GPU: this rank's part of an element-wise partitioned global
   // mesh (node ownership and numbering as TACSCreator::createTACS) and its ghost-exchange
   // plan, then a2ds_set_mesh + a2ds_set_halo.  Returns local -> global node numbers.
+  // matrix_halo: TACSParallelMat flavour — createPartitionedMat() then gives matrices whose
+  // owned rows are fully assembled (ghost-row blocks travel inside every assemble call)
   std::vector<int> setPartitionedMesh(int n_nodes, int n_elems, const int *conn,
                                       const int *elem_rank, const int *elem_comp, int n_ranks,
-                                      int rank) {
+                                      int rank, bool matrix_halo = false) {
     a2ds_partition *part = nullptr;
-    check(a2ds_partition_build(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, &part),
+    check(matrix_halo
+              ? a2ds_partition_build_matrix(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, &part)
+              : a2ds_partition_build(n_nodes, n_elems, conn, elem_rank, n_ranks, rank, &part),
           "a2ds_partition_build");
     const int rc = a2ds_partition_apply(ctx_, part, elem_comp);
     const int *glob = nullptr;
     a2ds_partition_sizes(part, &n_nodes_, &n_owned_, nullptr, nullptr, nullptr, nullptr);
     a2ds_partition_mesh(part, nullptr, nullptr, &glob, nullptr);
     std::vector<int> out(glob, glob + n_nodes_);
-    a2ds_partition_free(part);
+    if (part_) a2ds_partition_free(part_);
+    part_ = matrix_halo ? part : nullptr;
+    if (!matrix_halo) a2ds_partition_free(part);
     check(rc, "a2ds_partition_apply");
     return out;
+  }
+  int createPartitionedMat() {
+    if (!part_) throw std::runtime_error("createPartitionedMat: setPartitionedMesh(..., matrix_halo = true) first");
+    int m = -1;
+    check(a2ds_partition_create_mat(ctx_, part_, &m), "a2ds_partition_create_mat");
+    return m;
   }
   // NCCL communicator: id from a2ds_comm_unique_id on rank 0, broadcast by the launcher
   void initComm(int n_ranks, int rank, const char id[128]) {
@@ -130,6 +145,7 @@ class DeviceAssembler {
   }
   a2ds_ctx *ctx_;
   int n_nodes_, n_owned_;
+  a2ds_partition *part_;  // kept only in matrix-halo mode (createPartitionedMat needs it)
 };
 
 }  // namespace a2ds

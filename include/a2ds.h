@@ -277,6 +277,21 @@ int a2ds_partition_halo(const a2ds_partition *part, const int **peers, const int
                         const int **send_nodes, const int **recv_ptr, const int **recv_nodes);
 /* a2ds_set_mesh + a2ds_set_halo for this rank; elem_comp: component per GLOBAL element or NULL */
 int a2ds_partition_apply(a2ds_ctx *ctx, const a2ds_partition *part, const int *elem_comp);
+/* The same partition prepared for the TACSParallelMat flavour (every rank's OWNED matrix rows
+ * fully assembled, a2ds_mat_set_halo): the local node set additionally holds every node that
+ * shares an element of ANY rank with an owned node (the reference's external column map,
+ * TACSMatDistribute, src/bpmat/TACSMatDistribute.cpp:150-330), the vector halo covers them,
+ * and a2ds_partition_matrix hands out the local pattern (full rows for the owned nodes, the
+ * local elements' couplings for ghost rows; columns ascending) and, per peer in the order of
+ * a2ds_partition_halo, the block indices to send / to add arriving blocks to, both sorted by
+ * (global row, global column) so that the two sides of a pair agree. */
+int a2ds_partition_build_matrix(int n_nodes, int n_elems, const int *conn, const int *elem_rank,
+                                int n_ranks, int rank, a2ds_partition **part);
+int a2ds_partition_matrix(const a2ds_partition *part, const int **rowp, const int **cols,
+                          const int **send_ptr, const int **send_blocks, const int **recv_ptr,
+                          const int **recv_blocks);
+/* a2ds_mat_create with that pattern + a2ds_mat_set_halo */
+int a2ds_partition_create_mat(a2ds_ctx *ctx, const a2ds_partition *part, int *mat);
 
 /* ---- mesh input (host only) -------------------------------------------------------
  * The data format in front of the path: NASTRAN bulk-data decks as the reference's examples

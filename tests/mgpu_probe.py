@@ -165,9 +165,15 @@ def parallel_mat_flavour(rank, world, local):
     dist.broadcast_object_list(uid, src=0)
     asm.comm_init(world, rank, uid[0])
     asm.set_halo(P["peers"], P["send_lists"], P["recv_lists"])
+    # the native planner (a2ds_partition_build_matrix) must give the very same plan; the first
+    # matrix is created from it, the others from the Python plan
+    PN = a2ds.Partition(conn, n, elem_rank, world, rank, matrix_halo=True)
+    assert np.array_equal(PN.glob, glob) and np.array_equal(PN.rowp, P["rowp"]) and np.array_equal(PN.cols, P["cols"])
+    for a, b in zip(PN.mat_send_lists + PN.mat_recv_lists, P["mat_send_lists"] + P["mat_recv_lists"]):
+        assert np.array_equal(a, b)
     ident = np.arange(nl, dtype=np.int32)
-    mats = []
-    for _ in range(3):
+    mats = [PN.create_mat(asm)]
+    for _ in range(2):
         m = asm.create_mat_from_pattern([dict(nrows=nl, rowp=P["rowp"], cols=P["cols"], row_map=ident,
                                               col_map=ident, ident=1)])
         asm.mat_set_halo(m, P["peers"], P["mat_send_lists"], P["mat_recv_lists"])

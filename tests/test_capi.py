@@ -265,3 +265,36 @@ def test_native_partition_matches_reference_ownership_rule(a2ds):
         a2ds.Partition(conn, len(X), er0 + 7, 2, 0)
     with pytest.raises(a2ds.A2dsError, match="outside"):
         a2ds.Partition(conn + len(X), len(X), er0, 1, 0)
+
+
+def test_native_matrix_halo_plan_matches_python_planner(a2ds):
+    """a2ds_partition_build_matrix (TACSParallelMat flavour): extended ghost set, local pattern
+    and per-peer block lists identical to meshes.partition_rows(matrix_halo=True), whose plan
+    the 2- and 4-GPU tests assemble with"""
+    rng = np.random.default_rng(1)
+    meshes = dict(plate=a2ds.meshes.plate(8, 9)[:2], cyl=a2ds.meshes.cylinder(8, 5)[:2],
+                  sphere=a2ds.meshes.cubed_sphere(3, shuffle_seed=2)[:2],
+                  wing=a2ds.meshes.wingbox(3, 2, 3, 2)[:2])
+    for name, (conn, X) in meshes.items():
+        n = len(X)
+        for N in (2, 3, 4):
+            for mode in ("slab", "strip", "random"):
+                er = {"slab": np.arange(len(conn)) * N // len(conn), "strip": np.arange(len(conn)) % N,
+                      "random": rng.integers(0, N, len(conn))}[mode]
+                if er.max() + 1 < N:
+                    continue
+                parts = a2ds.meshes.partition_rows(conn, n, er, matrix_halo=True)
+                for r in range(N):
+                    P, Q = a2ds.Partition(conn, n, er, N, r, matrix_halo=True), parts[r]
+                    assert np.array_equal(P.glob, Q["glob"]) and P.n_owned == len(Q["owned"])
+                    assert np.array_equal(P.conn_local, Q["conn_local"])
+                    assert np.array_equal(P.peers, Q["peers"])
+                    assert np.array_equal(P.rowp, Q["rowp"]) and np.array_equal(P.cols, Q["cols"])
+                    pairs = zip(P.send_lists + P.recv_lists + P.mat_send_lists + P.mat_recv_lists,
+                                Q["send_lists"] + Q["recv_lists"] + Q["mat_send_lists"] + Q["mat_recv_lists"])
+                    for a, b in pairs:
+                        assert np.array_equal(a, b), (name, N, mode, r)
+    # the vector-only partition does not carry a matrix plan
+    conn, X = meshes["plate"]
+    P = a2ds.Partition(conn, len(X), np.zeros(len(conn), dtype=np.int32), 1, 0)
+    assert not hasattr(P, "rowp")
