@@ -8,6 +8,8 @@ LIB = os.path.join(HERE, "lib", "liba2ds_b200.so")
 SRCS = [os.path.join(HERE, "csrc", "a2ds.cu"), os.path.join(HERE, "csrc", "mesh_io.cpp"),
         os.path.join(HERE, "csrc", "partition.cpp")]
 DEPS = SRCS + [os.path.join(HERE, "csrc", "mitc4_math.h"),
+               os.path.join(HERE, "csrc", "assemble_kernels.cuh"),
+               os.path.join(HERE, "csrc", "aux_kernels.cuh"),
                os.path.join(HERE, "..", "include", "a2ds.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -1,0 +1,526 @@
+// assemble_kernels.cuh — the element kernels of liba2ds_b200.so (sm_100a), included by a2ds.cu.
+//
+// k_assemble<RES, KMAT, GMAT, NL>: a warp draws batches of NB MITC4 elements from a work
+// counter; per batch the node and Gauss-point phases run with one lane per (element, node) /
+// (element, point), then element by element all 32 lanes form their columns of the strain
+// matrices in registers (mitc4_math.h) — which ARE the fragments of the 24x24 contractions on
+// the FP64 tensor path (mma.sync m8n8k4 f64) — stage the element matrices in shared memory and
+// scatter them with full-warp RED.E.ADD.F64 through the element -> block offset tables.
+// k_mass<RES, MAT>: mass matrix / inertial residual with the same batching and scatter.
+// Roofline notes live in DESIGN.md, measurements in profiles/.
+#ifndef A2DS_ASSEMBLE_KERNELS_CUH
+#define A2DS_ASSEMBLE_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "mitc4_math.h"
+
+using namespace a2ds;
+struct KParams {
+  const int *elem_list;  // elements to process (NULL: 0..n_list-1)
+  int n_list;
+  const int *conn;       // 4 local nodes per element
+  const int *elem_comp;
+  const CompData *comps;
+  const double *X;       // 3 per node
+  const double *u;       // 6 per node
+  double *res;           // 6 per node
+  double *Kval;          // concatenated block values of the tangent matrix
+  const int *Koff;       // 16 block offsets per element (-1: not stored here)
+  double *Gval;
+  const int *Goff;
+  double alpha;          // scale of the tangent (and of the mass matrix in k_mass)
+  double gscale;         // scale of the geometric stiffness (assembleMatCombo; 1 otherwise)
+  double res_scale;      // residual entries are multiplied by this before the RED
+  double thermal;        // 1: residual of the state;  0: matrix-free product K x (u := x)
+  // matrix-free tangent product of the nonlinear model: y += jvp_scale * K_e(u) x_e instead
+  // of the matrix scatter (null: scatter)
+  const double *jvp_x;
+  double *jvp_y;
+  double jvp_scale;
+  int scratch_bytes;
+  int *work_counter;     // dynamic batch scheduling: next batch index (zeroed per launch)
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+static const int MAX_WARPS_PER_BLOCK = 4;
+static const int MAX_DEVICES = 64;  // per-device caches of launch configurations
+// Register budget: the residual / tangent kernels run at 12 warps per SM (168
+// registers); the variants that carry the B1(q) fragments across the tangent pass
+// (geometric stiffness, nonlinear model) need the full 255 registers (8 warps per SM).
+#ifndef A2DS_MB_G
+#define A2DS_MB_G 2
+#endif
+#ifndef A2DS_MB_K
+#define A2DS_MB_K 3
+#endif
+#define A2DS_MIN_BLOCKS(GMAT, NL) (((GMAT) || (NL)) ? A2DS_MB_G : A2DS_MB_K)
+
+// scatter one staged 24x24 element matrix.  Per 8 of the 16 node-pair blocks: 8 full-warp
+// REDs carry entries 0..31 of one block each (consecutive lanes -> consecutive doubles) and
+// ONE more full-warp RED carries the four remaining entries 32..35 of all 8 blocks (lane =
+// 4 * block + entry): 18 REDs per matrix, no divergent tail.  Every slot has a block
+// (a2ds_mat_create refuses patterns with missing blocks), so there is no validity branch;
+// loads are batched so the REDs do not wait on shared memory one by one.
+template <bool SCALED = false>
+__device__ __forceinline__ void scatter_matrix(const double *E, double *vals, int off16,
+                                               int lane, double scale = 1.0) {
+  const unsigned FULL = 0xffffffffu;
+  const int r0 = lane / 6, c0 = lane - 6 * r0;   // entry `lane` of a 6x6 block
+  const int src0 = r0 * KE_LD + c0;
+  const int tb = lane >> 2;                      // tail RED: block tb of the current 8
+  const int src1 = 6 * (tb >> 2) * KE_LD + 6 * (tb & 3) + 5 * KE_LD + 2 + (lane & 3);
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    double v0[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int b = 8 * half + k;
+      v0[k] = E[6 * (b >> 2) * KE_LD + 6 * (b & 3) + src0];
+      if (SCALED) v0[k] *= scale;
+    }
+    double v1 = E[12 * half * KE_LD + src1];   // blocks 8..15 start two block rows down
+    if (SCALED) v1 *= scale;
+    const int offt = __shfl_sync(FULL, off16, 8 * half + tb);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int off = __shfl_sync(FULL, off16, 8 * half + k);
+      atomicAdd(vals + 36 * (size_t)off + lane, v0[k]);
+    }
+    atomicAdd(vals + 36 * (size_t)offt + 32 + (lane & 3), v1);
+  }
+}
+
+// DMMA accumulators of the 6 upper tiles -> staged symmetric 24x24.  In the fragment
+// layout of mitc4_math.h the accumulator of tile (ti, tj) holds, on lane (c, qp'),
+// K[3 c + ti][6 qp' + tj] and K[3 c + ti][6 qp' + 3 + tj]  (c = lane >> 2, qp' = lane & 3).
+__device__ __forceinline__ void stage_tiles(double *E, const double (&acc)[6][2], double scale,
+                                            int lane) {
+  const int rowb = 3 * (lane >> 2), colb = 6 * (lane & 3);
+  int idx = 0;
+#pragma unroll
+  for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+    for (int tj = ti; tj < 3; tj++, idx++) {
+      const int row = rowb + ti, col0 = colb + tj, col1 = colb + 3 + tj;
+      const double a0 = scale * acc[idx][0], a1 = scale * acc[idx][1];
+      E[row * KE_LD + col0] = a0;
+      E[row * KE_LD + col1] = a1;
+      if (ti != tj) {
+        E[col0 * KE_LD + row] = a0;
+        E[col1 * KE_LD + row] = a1;
+      }
+    }
+}
+
+// all 9 tiles of an unsymmetric 24x24 (Z = B1^T W) into the staging area
+__device__ __forceinline__ void stage_tiles_full(double *E, const double (&acc)[9][2], int lane) {
+  const int rowb = 3 * (lane >> 2), colb = 6 * (lane & 3);
+#pragma unroll
+  for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+    for (int tj = 0; tj < 3; tj++) {
+      E[(rowb + ti) * KE_LD + colb + tj] = acc[3 * ti + tj][0];
+      E[(rowb + ti) * KE_LD + colb + 3 + tj] = acc[3 * ti + tj][1];
+    }
+}
+
+// G = Z + Z^T + geometric blocks, written block by block (64 generalised node pairs, 2 per
+// lane) from the staged Z into a second buffer
+__device__ __forceinline__ void symmetrize_add_geo(const ElemGeom &gm, const ElemWork &wk,
+                                                   const double *Pq4, const double *Z, double *G,
+                                                   double scale, int lane) {
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+    double blk[9];
+    geo_block(gm, wk, Pq4, pr, pc, blk);
+    const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        G[(r0 + i) * KE_LD + c0 + j] =
+            scale * (blk[3 * i + j] + Z[(r0 + i) * KE_LD + c0 + j] + Z[(c0 + j) * KE_LD + r0 + i]);
+  }
+}
+
+// 64 geometric-stiffness 3x3 blocks (generalised node pairs), 2 per lane, added in place
+__device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWork &wk,
+                                               const double *Pq4, double *E, double scale,
+                                               int lane) {
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+    double blk[9];
+    geo_block(gm, wk, Pq4, pr, pc, blk);
+    const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) E[(r0 + i) * KE_LD + c0 + j] += scale * blk[3 * i + j];
+  }
+}
+
+// A warp prepares NB elements at a time: the node phase and the Gauss-point phase then run
+// on NB*4 distinct work items (one lane each) instead of 8 redundant copies per element.
+// Build-time knobs for occupancy experiments (defaults = the measured configuration):
+//   A2DS_NB          elements per batch (2, 4 or 8).  Shared memory per warp scales with it:
+//                    27.7 KB at 4, 19.4 KB at 2 for the geometric-stiffness / nonlinear variants
+//   A2DS_PREFETCH_G  0: no double-buffered gather for those variants (-0.7 KB per warp at NB 2)
+//   A2DS_MB_G        blocks per SM the launch bounds ask for (3 -> 168 registers, 12 warps/SM)
+// e.g. -DA2DS_NB=2 -DA2DS_PREFETCH_G=0 -DA2DS_MB_G=3: 18.7 KB per warp, 12 instead of 8 warps
+// per SM for the fused kernel (192 B of spills per thread) — see profiles/README.md.
+#ifndef A2DS_NB
+#define A2DS_NB 4
+#endif
+#ifndef A2DS_PREFETCH_G
+#define A2DS_PREFETCH_G 1
+#endif
+#if A2DS_PREFETCH_G
+#define A2DS_RAW1(ws) (ws).raw1
+#define A2DS_GOFF1 1
+#else   // never selected at run time (PF is false), only has to name something that exists
+#define A2DS_RAW1(ws) (ws).raw0
+#define A2DS_GOFF1 0
+#endif
+static const int NB = A2DS_NB;
+static_assert(NB == 2 || NB == 4 || NB == 8,
+              "one lane per (element, node): NB * 4 <= 32; the offset gather moves 32 entries per pass");
+struct RawBatch {          // gathered inputs of one batch, filled by cp.async
+  double xq[NB][36];       // per element: X[12] then q[24]
+  int koff[NB][16];
+  int comp[NB];
+};
+struct WarpScratch {
+  RawBatch raw0;
+  int nodes[NB][4];
+  ElemGeom geo[NB];
+  double E[24 * KE_LD];   // staging of a 24x24 element matrix for the scatter (tangent)
+  // ---- only the geometric-stiffness / nonlinear variants use what follows; the linear
+  //      residual / tangent kernels allocate up to here (12 instead of 8 warps per SM) ----
+  double E2[24 * KE_LD];  // second staging buffer (geometric stiffness)
+  ElemWork work;
+  double Pq[NB][4][6];    // per Gauss point T T^T
+#if A2DS_PREFETCH_G
+  RawBatch raw1;          // double buffer: batch i+1 lands (cp.async) while batch i is processed
+  int goff[2][NB][16];    // block offsets of the geometric stiffness matrix (per raw buffer)
+#else
+  int goff[1][NB][16];    // block offsets of the geometric stiffness matrix
+#endif
+};
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool RES, bool KMAT, bool GMAT, bool NL>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT, NL))
+    k_assemble(const KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  ElemWork &wk = ws.work;
+  // full scratch + asynchronous prefetch of the next batch
+  const bool PF = (GMAT || NL) && A2DS_PREFETCH_G != 0;
+  const unsigned FULL = 0xffffffffu;
+  Want w;
+  w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL; w.thermal = p.thermal;
+  const bool need_state = GMAT || NL;
+
+  const int n_groups = (p.n_list + NB - 1) / NB;
+
+  // element id and node id this lane is responsible for in a batch: lane = 4 j + m
+  auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
+    const int j = (lane >> 2) & (NB - 1);
+    const int idx = grp_ * NB + j;
+    e_out = -1; nd_out = 0;
+    if (grp_ < n_groups && idx < p.n_list) {
+      e_out = p.elem_list ? __ldg(&p.elem_list[idx]) : idx;
+      nd_out = __ldg(&p.conn[4 * e_out + (lane & 3)]);
+    }
+  };
+  // asynchronous gather of a batch into raw buffer `rb` (addresses from the ids above)
+  auto issue_gather = [&](RawBatch &rb, int (*goffb)[16], int e_l, int nd_l) {
+#pragma unroll
+    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx / 36, k = sidx - 36 * j;
+      const bool isx = k < 12;
+      const int node = isx ? k / 3 : (k - 12) / 6;
+      const int comp_k = isx ? k - 3 * node : (k - 12) - 6 * node;
+      const int src_lane = (4 * j + node) & 31;
+      const int nd = __shfl_sync(FULL, nd_l, src_lane);
+      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+      if (sidx < NB * 36 && ej >= 0) {
+        const double *src = isx ? &p.X[3 * (size_t)nd + comp_k] : &p.u[6 * (size_t)nd + comp_k];
+        cp_async8(&rb.xq[j][k], src);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NB * 16 / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx >> 4, k = sidx & 15;
+      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+      if (ej >= 0) {
+        if (KMAT && p.Koff) cp_async4(&rb.koff[j][k], &p.Koff[16 * (size_t)ej + k]);
+        if (GMAT) cp_async4(&goffb[j][k], &p.Goff[16 * (size_t)ej + k]);
+      }
+    }
+    if ((lane & 3) == 0 && lane < 4 * NB && e_l >= 0) cp_async4(&rb.comp[lane >> 2], &p.elem_comp[e_l]);
+  };
+
+  // dynamic scheduling: warps draw the next batch from one counter, so that the batches in
+  // flight at any time stay close together in the element order (L2 locality of the
+  // read-modify-write scatter) however the warps drift
+  auto next_group = [&]() {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(p.work_counter, 1);
+    return __shfl_sync(FULL, g, 0);
+  };
+  int grp = next_group();
+  int grp_nxt = PF ? next_group() : 0;
+  int buf = 0;
+  int e_cur, nd_cur;
+  batch_ids(grp, e_cur, nd_cur);
+  if (PF && grp < n_groups) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
+  for (; grp < n_groups; buf ^= 1) {
+    // the draw for the trip after this one (after next with prefetch) is issued now and read
+    // at the end of the trip: its latency never shows
+    int drawn = 0;
+    if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
+    const int base = grp * NB;
+    const int cnt = min(NB, p.n_list - base);
+    // ids of the NEXT batch: requested now, consumed after the geometry phases
+    int e_nxt = -1, nd_nxt = 0;
+    if (PF) batch_ids(grp_nxt, e_nxt, nd_nxt);
+
+    // ---- the batch gathered during the previous trip (or right now without prefetch) -----
+    if (!PF) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
+    cp_async_wait_all();
+    __syncwarp();
+    const RawBatch &rb = (PF && buf) ? A2DS_RAW1(ws) : ws.raw0;
+    const int (*goffb)[16] = ws.goff[(PF && buf) ? A2DS_GOFF1 : 0];
+    if (lane < 4 * NB) ws.nodes[lane >> 2][lane & 3] = nd_cur;
+#pragma unroll
+    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx / 36, k = sidx - 36 * j;
+      if (sidx < NB * 36) {
+        const double v = rb.xq[j][k];
+        if (k < 12) ws.geo[j].X[k] = v; else ws.geo[j].q[k - 12] = v;
+      }
+    }
+    __syncwarp();
+
+    // ---- node phase: lane = (element of the batch, node) --------------------------------
+    {
+      const int j = (lane >> 2) & (NB - 1);
+      if (lane < 4 * NB && j < cnt) phase_node(p.comps[rb.comp[j]], ws.geo[j], lane & 3);
+    }
+    __syncwarp();
+    // ---- Gauss point phase: lane = (element of the batch, Gauss point) ------------------
+    {
+      const int j = (lane >> 2) & (NB - 1);
+      if (lane < 4 * NB && j < cnt)
+        phase_qp(p.comps[rb.comp[j]], ws.geo[j], lane & 3, RES || GMAT || NL, need_state, NL,
+                 need_state ? &ws.Pq[j][lane & 3][0] : (double *)0);
+    }
+    // start the gather of the next batch into the other raw buffer
+    if (PF && grp_nxt < n_groups)
+      issue_gather(buf ? ws.raw0 : A2DS_RAW1(ws), ws.goff[buf ? 0 : A2DS_GOFF1], e_nxt, nd_nxt);
+    if (PF) { e_cur = e_nxt; nd_cur = nd_nxt; }
+    __syncwarp();
+
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+      const ElemGeom &gm = ws.geo[j];
+      const CompData &c = p.comps[rb.comp[j]];
+
+      // ---- column phase + contractions on the FP64 tensor path ----------------------
+      // The lane's columns of B, w C B and B1(q) ARE the DMMA fragments (mitc4_math.h), so
+      // operands go from the FMA pipe to the tensor path without leaving registers.
+      //      K = B^T (w C B),   G = B1^T W + W^T B1      (upper tiles only)
+      // Order: B0/W -> strains, residual -> K pass -> B1 -> G pass, so that B0 and B1 are
+      // never live together (the nonlinear model needs B1 first: B = B0 + B1).
+      double Bc[9][3], Wc[9][3], Bq[9][3];
+      double kacc[6][2], zacc[9][2];
+      if (NL) lane_b1(gm, wk, lane, Bq);
+      lane_b0w(c, gm, lane, w, Bq, Bc, Wc);
+      if (RES || GMAT || NL) {
+        double r3[3];
+        lane_stress(c, gm, wk, lane, w, Wc, r3);
+        if (RES) {
+          // residual: sum over the 4 Gauss points (lane bits 0..1)
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 1);
+            r3[k] += __shfl_xor_sync(FULL, r3[k], 2);
+          }
+          if ((lane & 3) == 0) {
+            double *r = &p.res[6 * (size_t)ws.nodes[j][lane_m(lane)] + 3 * lane_h(lane)];
+            atomicAdd(r, p.res_scale * r3[0]);
+            atomicAdd(r + 1, p.res_scale * r3[1]);
+            atomicAdd(r + 2, p.res_scale * r3[2]);
+          }
+        }
+      }
+      if (KMAT) {
+#pragma unroll
+        for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 9; ks++) {
+          int idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], Bc[ks][ti], Wc[ks][tj]);
+        }
+      }
+      if (GMAT) {
+        // Z = B1^T W over all 9 tiles (not symmetric); G = Z + Z^T is formed when the tiles
+        // are staged: 9 instead of 12 DMMAs per k-step
+        lane_b1(gm, wk, lane, Bq);
+#pragma unroll
+        for (int t = 0; t < 9; t++) zacc[t][0] = zacc[t][1] = 0.0;
+        // the drilling strain is linear in the state: row 8 of B1 is zero, 8 k-steps suffice
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++)
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = 0; tj < 3; tj++) dmma884(zacc[3 * ti + tj], Bq[ks][ti], Wc[ks][tj]);
+      }
+      // ---- stage, add the geometric blocks, scatter -------------------------------------
+      if (KMAT) stage_tiles(ws.E, kacc, p.alpha, lane);
+      if (GMAT) stage_tiles_full(ws.E2, zacc, lane);
+      if (GMAT || NL) {
+        __syncwarp();  // the per Gauss point stresses (lane_stress) are published
+        if (lane < 9) sum_tying_stress(wk, lane);
+      }
+      __syncwarp();
+      if (NL && KMAT) {
+        add_geo_blocks(gm, wk, &ws.Pq[j][0][0], ws.E, p.alpha, lane);
+        __syncwarp();
+      }
+      if (KMAT) {
+        if (NL && !GMAT && p.jvp_x) {
+          // matrix-free: the staged tangent times the element's slice of x (the second
+          // staging buffer is free in this variant)
+          const int node = ws.nodes[j][(lane / 6) & 3];
+          if (lane < 24) ws.E2[lane] = p.jvp_x[6 * (size_t)node + lane % 6];
+          __syncwarp();
+          if (lane < 24) {
+            double y = 0.0;
+#pragma unroll
+            for (int k = 0; k < 24; k++) y += ws.E[lane * KE_LD + k] * ws.E2[k];
+            atomicAdd(&p.jvp_y[6 * (size_t)node + lane % 6], p.jvp_scale * y);
+          }
+        } else {
+          scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
+        }
+      }
+      if (GMAT) {
+        if (KMAT) __syncwarp();  // E is reused for G once K has left
+        symmetrize_add_geo(gm, wk, &ws.Pq[j][0][0], ws.E2, ws.E, p.gscale, lane);
+        __syncwarp();
+        scatter_matrix(ws.E, p.Gval, goffb[j][lane & 15], lane);
+      }
+      __syncwarp();
+    }
+    drawn = __shfl_sync(FULL, drawn, 0);
+    if (PF) { grp = grp_nxt; grp_nxt = drawn; }
+    else { grp = drawn; batch_ids(grp, e_cur, nd_cur); }
+  }
+}
+
+// ---- mass path (gamma terms of assembleJacobian, TACS_MASS_MATRIX, inertial residual) ----
+// M_e = sum_qp w (m0 N^T N on u, m1 on u-d, m2 on d-d) folded onto the rotations
+// (TACSShellElement.h:410-447, 614-648); RES adds M_e * p.u (p.u = second time derivative
+// of the state) to the residual, MAT adds p.alpha * M_e to the matrix p.Kval.
+// Memory-bound (2.6 kB of matrix per element, a few hundred flops): same batched geometry
+// phases and scatter as k_assemble, no tensor-core part.
+template <bool RES, bool MAT>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 3) k_mass(const KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  const unsigned FULL = 0xffffffffu;
+  const int n_groups = (p.n_list + NB - 1) / NB;
+  for (int grp = blockIdx.x * warps_per_block + warp; grp < n_groups;
+       grp += gridDim.x * warps_per_block) {
+    const int base = grp * NB, cnt = min(NB, p.n_list - base);
+    // lane = 4 j + m: node m of element j
+    const int jl = (lane >> 2) & (NB - 1);
+    int e_l = -1, nd_l = 0;
+    if (jl < cnt) {
+      e_l = p.elem_list ? __ldg(&p.elem_list[base + jl]) : base + jl;
+      nd_l = __ldg(&p.conn[4 * e_l + (lane & 3)]);
+    }
+    if (lane < 4 * NB && e_l >= 0) {
+      const int m = lane & 3;
+#pragma unroll
+      for (int k = 0; k < 3; k++) ws.geo[jl].X[3 * m + k] = p.X[3 * (size_t)nd_l + k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) ws.geo[jl].q[6 * m + k] = RES ? p.u[6 * (size_t)nd_l + k] : 0.0;
+      if (m == 0) ws.raw0.comp[jl] = __ldg(&p.elem_comp[e_l]);
+    }
+    if (MAT) {
+#pragma unroll
+      for (int r = 0; r < NB * 16 / 32; r++) {
+        const int sidx = lane + 32 * r, j = sidx >> 4, k = sidx & 15;
+        const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+        if (ej >= 0) ws.raw0.koff[j][k] = __ldg(&p.Koff[16 * (size_t)ej + k]);
+      }
+    }
+    __syncwarp();
+    if (lane < 4 * NB && jl < cnt) mass_node(ws.geo[jl], lane & 3);
+    __syncwarp();
+    if (lane < 4 * NB && jl < cnt) mass_qp(ws.geo[jl], lane & 3);
+    __syncwarp();
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+      const ElemGeom &gm = ws.geo[j];
+      const CompData &c = p.comps[ws.raw0.comp[j]];
+#pragma unroll
+      for (int pass = 0; pass < 2; pass++) {
+        const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+        double blk[9];
+        mass_block(c, gm, pr, pc, blk);
+        const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) ws.E[(r0 + i) * KE_LD + c0 + k] = blk[3 * i + k];
+      }
+      __syncwarp();
+      if (RES) {
+        const int node = __shfl_sync(FULL, nd_l, 4 * j + (lane / 6 & 3));
+        if (lane < 24) {
+          double r = 0.0;
+#pragma unroll
+          for (int k = 0; k < 24; k++) r += ws.E[lane * KE_LD + k] * gm.q[k];
+          atomicAdd(&p.res[6 * (size_t)node + lane % 6], p.res_scale * r);
+        }
+      }
+      if (MAT) scatter_matrix<true>(ws.E, p.Kval, ws.raw0.koff[j][lane & 15], lane, p.alpha);
+      __syncwarp();
+    }
+  }
+}
+
+#endif

@@ -1,0 +1,174 @@
+// aux_kernels.cuh — the small kernels around the element kernels, included by a2ds.cu: element
+// -> block offset tables, boundary conditions, vector and matrix halo pack / unpack, and the
+// HBM-bound matrix algebra of the buckling flow (copy / axpy, 6x6 BCSR mat-vec).
+#ifndef A2DS_AUX_KERNELS_CUH
+#define A2DS_AUX_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+// One BCSR block of a matrix as the kernels see it
+struct BlockDev {
+  const int *rowp, *cols, *row_map, *col_map;
+  long long base;  // first 6x6 block of this BCSR block in the concatenated array
+  int nrows, ident;
+};
+
+// element -> block offset table; replaces TACSSchurMat::addValues' findIndex +
+// BCSRMat::addRowValues' bsearch (TACSSchurMat.cpp:453-531, BCSRMat.cpp:1778-1827)
+__global__ void k_build_offsets(int n_elems, const int *conn, int n_blocks, const BlockDev *blk,
+                                int *off, int *missing) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= 16 * (size_t)n_elems) return;
+  const int e = (int)(t >> 4), slot = (int)(t & 15);
+  const int rn = conn[4 * e + (slot >> 2)], cn = conn[4 * e + (slot & 3)];
+  int found = -1;
+  for (int b = 0; b < n_blocks && found < 0; b++) {
+    const int rr = blk[b].row_map ? blk[b].row_map[rn] : (rn < blk[b].nrows ? rn : -1);
+    const int cc = blk[b].col_map ? blk[b].col_map[cn] : cn;
+    if (rr < 0 || cc < 0) continue;
+    int lo = blk[b].rowp[rr], hi = blk[b].rowp[rr + 1] - 1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1, v = blk[b].cols[mid];
+      if (v == cc) { found = (int)(blk[b].base + mid); break; }
+      if (v < cc) lo = mid + 1; else hi = mid - 1;
+    }
+  }
+  off[t] = found;
+  if (found < 0) atomicAdd(missing, 1);
+}
+
+// residual BC rows: r = u - ubar on owned nodes (TACSBVec::applyBCs, TACSBVec.cpp:546-585)
+__global__ void k_res_bcs(int n_bc, const int *nodes, const int *vars, const double *vals,
+                          const double *u, double *res, int n_owned) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n_bc) return;
+  const int b = t / 6, k = t - 6 * b, n = nodes[b];
+  if (n < n_owned && (vars[b] & (1 << k))) res[6 * (size_t)n + k] = u[6 * (size_t)n + k] - vals[t];
+}
+
+// vector BC rows set to zero (TACSBVec::applyBCs without a state vector, TACSBVec.cpp:570-584)
+__global__ void k_vec_zero_bcs(int n_bc, const int *nodes, const int *vars, double *y, int n_owned) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n_bc) return;
+  const int b = t / 6, k = t - 6 * b, n = nodes[b];
+  if (n < n_owned && (vars[b] & (1 << k))) y[6 * (size_t)n + k] = 0.0;
+}
+
+// y[bc] = x[bc] on the owned BC rows: what the identity rows of the assembled matrix give
+__global__ void k_vec_copy_bcs(int n_bc, const int *nodes, const int *vars, const double *x,
+                               double *y, int n_owned) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n_bc) return;
+  const int b = t / 6, k = t - 6 * b, n = nodes[b];
+  if (n < n_owned && (vars[b] & (1 << k))) y[6 * (size_t)n + k] = x[6 * (size_t)n + k];
+}
+
+// matrix BC rows: zero the constrained DOF rows of every block in the block row, 1.0 on
+// the diagonal entry of the diagonal block (BCSRMat::zeroRow, BCSRMat.cpp:2005-2030;
+// columns untouched, as the reference)
+__global__ void k_mat_bcs(int n_bc, const int *nodes, const int *vars, int n_blocks,
+                          const BlockDev *blk, double *A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_bc * n_blocks) return;
+  const int b = t / n_blocks, ib = t - b * n_blocks;
+  const BlockDev B = blk[ib];
+  const int n = nodes[b], mask = vars[b];
+  const int row = B.row_map ? B.row_map[n] : (n < B.nrows ? n : -1);
+  if (row < 0) return;
+  const int diag_col = B.col_map ? B.col_map[n] : n;
+  for (int j = B.rowp[row]; j < B.rowp[row + 1]; j++) {
+    double *a = &A[36 * (size_t)(B.base + j)];
+    for (int ii = 0; ii < 6; ii++)
+      if (mask & (1 << ii))
+        for (int jj = 0; jj < 6; jj++) a[6 * ii + jj] = 0.0;
+    if (B.ident && B.cols[j] == diag_col)
+      for (int ii = 0; ii < 6; ii++)
+        if (mask & (1 << ii)) a[7 * ii] = 1.0;
+  }
+}
+
+// halo pack / unpack (VecDistGetVars6 and the TACS_ADD_VALUES scatter of
+// TACSBVecDistribute.cpp:543-747)
+__global__ void k_pack6(int n, const int *nodes, const double *v, double *buf) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 6 * n) buf[t] = v[6 * (size_t)nodes[t / 6] + t % 6];
+}
+__global__ void k_unpack6(int n, const int *nodes, const double *buf, double *v, int add) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n) return;
+  double *d = &v[6 * (size_t)nodes[t / 6] + t % 6];
+  if (add) *d += buf[t]; else *d = buf[t];
+}
+
+// y <- beta y + alpha x over all stored values (BCSRMat::axpy / copyValues, BCSRMat.cpp:2375,
+// 2430).  Pure HBM streaming: 128-bit accesses, four independent loads in flight per thread.
+// n2 = number of double2 (block values come in multiples of 36 doubles, 16-byte aligned).
+template <bool COPY>
+__global__ void __launch_bounds__(256) k_axpy(size_t n2, double alpha, const double2 *__restrict__ x,
+                                              double2 *__restrict__ y) {
+  // one contiguous 16 KB tile per block (4 x 128-bit per thread), no grid-stride loop: the
+  // DRAM pages of a tile are touched by one block at one time
+  const size_t base = blockIdx.x * (size_t)(4 * 256) + threadIdx.x;
+  double2 xv[4], yv[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const size_t i = base + 256 * k;
+    if (i < n2) {
+      xv[k] = x[i];
+      if (!COPY) yv[k] = y[i];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const size_t i = base + 256 * k;
+    if (i < n2) {
+      double2 r;
+      if (COPY) r = xv[k];
+      else { r.x = yv[k].x + alpha * xv[k].x; r.y = yv[k].y + alpha * xv[k].y; }
+      y[i] = r;
+    }
+  }
+}
+
+// 6x6 BCSR mat-vec (BCSRMatVecMult6, BCSRMatMult6.cpp:82): one thread per scalar row, the six
+// threads of a block row read the 288 contiguous bytes of each block between them.
+// HBM bound: 288 B of values + 4 B of column index per block; x is reused through L1/L2.
+__global__ void k_spmv6(int nrows, const int *__restrict__ rowp, const int *__restrict__ cols,
+                        const double *__restrict__ A, const double *__restrict__ x,
+                        double *__restrict__ y) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int row = (int)(t / 6), r = (int)(t - 6 * (size_t)row);
+  if (row >= nrows) return;
+  double acc = 0.0;
+  const int end = rowp[row + 1];
+  for (int k = rowp[row]; k < end; k++) {
+    const double2 *a = reinterpret_cast<const double2 *>(A + 36 * (size_t)k + 6 * r);
+    const double2 *xv = reinterpret_cast<const double2 *>(x + 6 * (size_t)__ldg(&cols[k]));
+    const double2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+    const double2 x0 = __ldg(xv), x1 = __ldg(xv + 1), x2 = __ldg(xv + 2);
+    acc += a0.x * x0.x + a0.y * x0.y + a1.x * x1.x + a1.y * x1.y + a2.x * x2.x + a2.y * x2.y;
+  }
+  y[t] = acc;
+}
+
+// ---- matrix halo (TACSParallelMat flavour): ghost rows -> owners, added --------------------
+// TACSMatDistribute::beginAssembly/endAssembly (src/bpmat/TACSMatDistribute.cpp:1036-1176):
+// contributions a rank made to block rows it does not own travel to the owner and are added
+// there.  The plan (which of my blocks go to which peer, and where arriving blocks land) is
+// supplied by the host, which knows the global numbering (a2ds_mat_set_halo).
+__global__ void k_pack36(int n, const int *blk, const double2 *A, double2 *buf) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= 18 * (size_t)n) return;
+  const size_t b = t / 18, e = t - 18 * b;
+  buf[t] = A[18 * (size_t)blk[b] + e];
+}
+__global__ void k_unpack36_add(int n, const int *blk, const double2 *buf, double2 *A) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= 18 * (size_t)n) return;
+  const size_t b = t / 18, e = t - 18 * b;
+  double2 *d = &A[18 * (size_t)blk[b] + e];
+  const double2 v = buf[t];
+  d->x += v.x; d->y += v.y;
+}
+
+#endif

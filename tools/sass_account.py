@@ -7,19 +7,21 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(root, "a2d-shells_b200", "lib", "liba2ds_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+# the library is linked from several sources: take the cubin that holds the kernels
+cubin = max((f for f in os.listdir(tmp) if f.endswith(".cubin")),
+            key=lambda f: os.path.getsize(os.path.join(tmp, f)))
 sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)],
                       capture_output=True, text=True).stdout.splitlines()
 # function line ranges of the two sources
 ranges = {}
-for fn in ("a2d-shells_b200/csrc/mitc4_math.h", "a2d-shells_b200/csrc/a2ds.cu"):
+for fn in ("a2d-shells_b200/csrc/mitc4_math.h", "a2d-shells_b200/csrc/assemble_kernels.cuh"):
     src = open(os.path.join(root, fn)).read().splitlines()
     marks = []
     for i, l in enumerate(src, 1):
         m = re.match(r"^(?:A2DS_HD|__device__ __forceinline__|__global__|template.*__global__|static|inline)?.*?\b([A-Za-z_0-9]+)\(.*[,{(]\s*$", l)
         if m and not l.startswith(" ") and not l.startswith("//") and not l.startswith("#"):
             marks.append((i, m.group(1)))
-    if fn.endswith("a2ds.cu"):  # the kernel body: one bucket per "// ----" phase comment
+    if fn.endswith("assemble_kernels.cuh"):  # the kernel body: one bucket per "// ----" phase comment
         k0 = next(i for i, l in enumerate(src, 1) if re.match(r"\s+k_assemble\(const KParams", l))
         k1 = next(i for i, l in enumerate(src, 1) if i > k0 and l.startswith("}"))
         marks = [mk for mk in marks if not (k0 <= mk[0] <= k1)]
