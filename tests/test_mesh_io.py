@@ -306,3 +306,45 @@ def test_deck_to_assembly_on_the_device(a2ds, orc):
     r_o, k_o = orc.assemble(1, conn, m.elem_comp, comps, m.X, u, rowp, cols, m.bc_nodes, masks, vals)
     _, g_o = orc.assemble(3, conn, m.elem_comp, comps, m.X, u, rowp, cols, m.bc_nodes, masks, vals)
     assert relmax(res, r_o) < 1e-12 and relmax(K, k_o) < 1e-10 and relmax(G, g_o) < 1e-10
+
+
+def test_shipped_cylinder_deck_assembly_oracle_vs_reference(a2ds, orc, ref):
+    """BASELINE configs[0] as shipped (examples/cylinder-buckling/mech-cylinder.bdf, 3200 MITC4
+    elements): deck read by OUR reader, then residual, Kmat and Gmat of the oracle against the
+    unmodified reference assembling the same arrays with the example's section and BCs —
+    pins the oracle at the size and numbering of the shipped example (build container only)"""
+    from helpers import relmax
+    deck = "/root/reference/examples/cylinder-buckling/mech-cylinder.bdf"
+    if not os.path.exists(deck):
+        pytest.skip("reference examples not present")
+    m = a2ds.Mesh.read_bdf(deck)
+    conn, masks, vals = m.quad4()
+    n = m.n_nodes
+    bc_vars = [[k for k in range(6) if mk >> k & 1] for mk in masks]
+    bc_vals = [[vals[b, k] for k in v] for b, v in enumerate(bc_vars)]
+    props = ref.iso_props()                       # the section of mechBuckling.cpp:41-58
+    ra = ref.RefAssembler(conn, m.X, m.elem_comp, props[None], m.bc_nodes, bc_vars, bc_vals)
+    try:
+        conn_r, X_r = ra.conn(), ra.nodes()
+        nodes_b, vars_b, vals_b = ra.bcs()
+        u = np.zeros((n, 6)); u[ra.new_nodes] = a2ds.meshes.seeded_state(m.node_nums, 1e-5)
+        ra.set_state(u)
+        mat = ra.mat_create(0)
+        r_ref = ra.assemble_jacobian(mat)
+        blk = ra.mat_block(mat, 0)
+        rowp, cols, K_ref = blk["rowp"], blk["cols"], blk["A"]
+        ra.assemble_mat_type(1, mat)
+        G_ref = ra.mat_block(mat, 0)["A"]
+    finally:
+        ra.close()
+    assert len(conn_r) == 3200 and X_r.shape == (3300, 3) and masks.sum() > 0
+    Cs, eth, mom = ref.con_tables(props)
+    comp = orc.make_comp(0, Cs, eth, mom)
+    ec = np.zeros(len(conn_r), dtype=np.int32)
+    r, K = orc.assemble(1, conn_r, ec, [comp], X_r, u, rowp, cols, nodes_b, vars_b, vals_b)
+    _, G = orc.assemble(3, conn_r, ec, [comp], X_r, u, rowp, cols, nodes_b, vars_b, vals_b)
+    assert relmax(r, r_ref) < 1e-12 and relmax(K, K_ref) < 1e-13 and relmax(G, G_ref) < 1e-9
+    # the prescribed end shortening of the deck arrives in the residual rows: r = u - ubar
+    b = int(np.argmin(vals_b.min(axis=1)))
+    nd, k = int(nodes_b[b]), int(np.argmin(vals_b[b]))
+    assert vals_b[b, k] == -1e-5 and r_ref[nd, k] == u[nd, k] + 1e-5
