@@ -107,3 +107,37 @@ extern "C" int emul_mass(const double *mom, int transform, const double *axis, c
     }
   return 0;
 }
+
+// strain matrices B0[qp][strain][dof] (and B1(q) for the state) of one element, assembled from
+// the per-lane fragments: lets the tests look at the structure the contraction exploits
+extern "C" int emul_strain_matrices(const double *Cs, int transform, const double *axis,
+                                    const double *X, const double *q, double *B0, double *B1) {
+  CompData c;
+  memset(&c, 0, sizeof(c));
+  memcpy(c.Cs, Cs, sizeof(c.Cs));
+  c.transform = transform;
+  memcpy(c.axis, axis, sizeof(c.axis));
+  static ElemGeom s;
+  static ElemWork wk;
+  memset(&s, 0, sizeof(s));
+  memset(&wk, 0, sizeof(wk));
+  memcpy(s.X, X, sizeof(s.X));
+  memcpy(s.q, q, sizeof(s.q));
+  Want w;
+  w.res = true; w.kmat = true; w.gmat = true; w.nonlinear = false; w.thermal = 1.0;
+  for (int m = 0; m < 4; m++) phase_node(c, s, m);
+  static double Pq[4][6];
+  for (int qp = 0; qp < 4; qp++) phase_qp(c, s, qp, true, true, false, Pq[qp]);
+  for (int lane = 0; lane < 32; lane++) {
+    double Bc[9][3], Wc[9][3], Bq[9][3];
+    lane_b1(s, wk, lane, Bq);
+    lane_b0w(c, s, lane, w, Bq, Bc, Wc);
+    const int qp = lane_qp(lane), col = 6 * lane_m(lane) + 3 * lane_h(lane);
+    for (int r = 0; r < 9; r++)
+      for (int k = 0; k < 3; k++) {
+        B0[(qp * 9 + r) * 24 + col + k] = Bc[r][k];
+        B1[(qp * 9 + r) * 24 + col + k] = Bq[r][k];
+      }
+  }
+  return 0;
+}

@@ -81,3 +81,24 @@ def test_mass_block_against_oracle(emul, orc):
             emul.emul_mass(p(mom), C.c_int(tr), p(axis), p(Xe), p(M))
             M_or = orc.mat_type(comp, 2, Xe, np.zeros(24))
             assert relmax(M.reshape(24, 24), M_or) < 1e-13
+
+
+def test_tying_rows_have_rank_nine_across_the_gauss_points(emul, a2ds):
+    """Structure behind a cheaper contraction (profiles/README.md, experiment 1): the membrane /
+    transverse-shear rows of B0 and of B1(q) at the four Gauss points are interpolations of the
+    same 9 tying-point rows, so the 20 x 24 stack has rank 9 — K and Z could contract over 9
+    tying points (3 k-steps of the m8n8k4 MMA) instead of 5 strains x 4 points (5 k-steps)"""
+    import ctypes as C
+    X, q = random_elements(6, seed=3)
+    Cs, _ = a2ds.iso_shell_tables()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for tr, axis in ((0, np.array([1.0, 0.0, 0.0])), (1, np.array([0.6, 0.8, 0.0]))):
+        for e in range(X.shape[0]):
+            B0 = np.zeros((4, 9, 24)); B1 = np.zeros((4, 9, 24))
+            emul.emul_strain_matrices(p(np.ascontiguousarray(Cs)), C.c_int(tr), p(axis),
+                                      p(np.ascontiguousarray(X[e]).ravel()),
+                                      p(np.ascontiguousarray(q[e]).ravel()), p(B0), p(B1))
+            assert np.abs(B1[:, 8]).max() == 0.0          # the drilling strain is linear in the state
+            for B in (B0, B1):
+                sv = np.linalg.svd(B[:, [0, 1, 2, 6, 7], :].reshape(20, 24), compute_uv=False)
+                assert sv[8] > 1e-6 * sv[0] and sv[9] < 1e-13 * sv[0]
