@@ -58,6 +58,15 @@ struct StageTimer {
 // used by the other translation units of the library (mesh_io.cpp)
 int a2ds_set_error_(const char *msg) { return fail(msg); }
 
+// no C++ exception leaves the C ABI (std::bad_alloc of a host-side table and the like):
+// every multi-line entry point runs between these two
+#define A2DS_TRY try {
+#define A2DS_CATCH(fn)                                              \
+  }                                                                 \
+  catch (const std::exception &e_) {                                \
+    return fail(std::string(#fn ": ") + e_.what());                 \
+  }
+
 extern "C" const char *a2ds_last_error(void) { return g_err.c_str(); }
 extern "C" const char *a2ds_version(void) { return "a2ds-b200 0.1 (sm_100a)"; }
 
@@ -159,6 +168,7 @@ static int upload(T **dst, const T *src, size_t n, cudaStream_t st) {
 }
 
 extern "C" int a2ds_create(int device, a2ds_ctx **out) {
+  A2DS_TRY
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
@@ -190,6 +200,7 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   CU(cudaEventCreate(&c->evr1));
   *out = c;
   return 0;
+  A2DS_CATCH(a2ds_create)
 }
 
 static void free_lists(a2ds_ctx *c) {
@@ -203,6 +214,7 @@ static void free_lists(a2ds_ctx *c) {
 }
 
 extern "C" int a2ds_destroy(a2ds_ctx *c) {
+  A2DS_TRY
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->copy_stream);
@@ -222,17 +234,21 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
+  A2DS_CATCH(a2ds_destroy)
 }
 
 extern "C" int a2ds_synchronize(a2ds_ctx *c) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->copy_stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+  A2DS_CATCH(a2ds_synchronize)
 }
 
 extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems, const int *conn,
                              const int *elem_comp) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (n_owned > n_nodes || n_nodes < 0 || n_elems < 0) return fail("a2ds_set_mesh: bad sizes");
   for (size_t i = 0; i < 4 * (size_t)n_elems; i++)
@@ -260,20 +276,24 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
   free_lists(c);
   c->mesh_set = true;
   return 0;
+  A2DS_CATCH(a2ds_set_mesh)
 }
 
 extern "C" int a2ds_set_nodes(a2ds_ctx *c, const double *X) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (!c->X) return fail("a2ds_set_nodes: call a2ds_set_mesh first");
   CU(cudaMemcpyAsync(c->X, X, 3 * (size_t)c->n_nodes * sizeof(double), cudaMemcpyHostToDevice,
                      c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+  A2DS_CATCH(a2ds_set_nodes)
 }
 
 extern "C" int a2ds_set_components(a2ds_ctx *c, int n_comp, const double *Cs, const double *eth,
                                    const double *temperature, const int *elem_class,
                                    int transform, const double *ref_axis) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (n_comp <= 0) return fail("a2ds_set_components: need at least one component");
   if (transform != A2DS_TRANSFORM_NATURAL && transform != A2DS_TRANSFORM_REF_AXIS)
@@ -311,12 +331,14 @@ extern "C" int a2ds_set_components(a2ds_ctx *c, int n_comp, const double *Cs, co
   if (upload(&c->comps, h.data(), (size_t)n_comp, c->stream)) return 1;
   free_lists(c);
   return 0;
+  A2DS_CATCH(a2ds_set_components)
 }
 
 // mass moments per component, as TACSShellConstitutive::evalMassMoments returns them
 // (TACSIsoShellConstitutive.cpp:120-129); may be called before or after
 // a2ds_set_components
 extern "C" int a2ds_set_mass_moments(a2ds_ctx *c, int n_comp, const double *moments) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (n_comp <= 0 || !moments) return fail("a2ds_set_mass_moments: bad arguments");
   c->h_mom.assign(moments, moments + 3 * (size_t)n_comp);
@@ -328,6 +350,7 @@ extern "C" int a2ds_set_mass_moments(a2ds_ctx *c, int n_comp, const double *mome
     if (upload(&c->comps, c->h_comps.data(), (size_t)n_comp, c->stream)) return 1;
   }
   return 0;
+  A2DS_CATCH(a2ds_set_mass_moments)
 }
 
 // time derivatives of the state (TACSAssembler::setVariables(q, qdot, qddot),
@@ -336,6 +359,7 @@ extern "C" int a2ds_set_mass_moments(a2ds_ctx *c, int n_comp, const double *mome
 // removes the inertial term again.
 extern "C" int a2ds_set_state_rates(a2ds_ctx *c, int n_given, const double *udot,
                                     const double *uddot) {
+  A2DS_TRY
   (void)udot;
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("a2ds_set_state_rates: mesh not set");
@@ -353,9 +377,11 @@ extern "C" int a2ds_set_state_rates(a2ds_ctx *c, int n_given, const double *udot
                      c->stream));
   if (c->has_halo && n_given == c->n_owned && halo_exchange(c, c->udd, false)) return 1;
   return 0;
+  A2DS_CATCH(a2ds_set_state_rates)
 }
 
 extern "C" int a2ds_set_state_dev(a2ds_ctx *c, int n_given, const double *u_dev) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (n_given != c->n_nodes && n_given != c->n_owned)
     return fail("a2ds_set_state: n_given must be n_nodes or n_owned");
@@ -363,9 +389,11 @@ extern "C" int a2ds_set_state_dev(a2ds_ctx *c, int n_given, const double *u_dev)
   CU(cudaMemcpyAsync(c->u, u_dev, 6 * (size_t)n_given * sizeof(double), cudaMemcpyDeviceToDevice,
                      c->stream));
   return 0;
+  A2DS_CATCH(a2ds_set_state_dev)
 }
 
 extern "C" int a2ds_set_state(a2ds_ctx *c, int n_given, const double *u) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (n_given != c->n_nodes && n_given != c->n_owned)
     return fail("a2ds_set_state: n_given must be n_nodes or n_owned");
@@ -378,10 +406,12 @@ extern "C" int a2ds_set_state(a2ds_ctx *c, int n_given, const double *u) {
   CU(cudaEventRecord(c->ev_state, c->copy_stream));
   c->state_pending = true;
   return 0;
+  A2DS_CATCH(a2ds_set_state)
 }
 
 extern "C" int a2ds_set_bcs(a2ds_ctx *c, int n_bc, const int *nodes, const int *vars,
                             const double *vals) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("a2ds_set_bcs: call a2ds_set_mesh first");
   if (n_bc < 0 || (n_bc > 0 && (!nodes || !vars))) return fail("a2ds_set_bcs: bad arguments");
@@ -397,15 +427,18 @@ extern "C" int a2ds_set_bcs(a2ds_ctx *c, int n_bc, const int *nodes, const int *
   if (upload(&c->bc_vars, vars, (size_t)n_bc, c->stream)) return 1;
   if (upload(&c->bc_vals, vals ? vals : zeros.data(), 6 * (size_t)n_bc, c->stream)) return 1;
   return 0;
+  A2DS_CATCH(a2ds_set_bcs)
 }
 
 extern "C" int a2ds_set_scatter_mode(a2ds_ctx *c, int mode) {
+  A2DS_TRY
   if (mode != A2DS_SCATTER_ATOMIC && mode != A2DS_SCATTER_COLORED &&
       mode != A2DS_SCATTER_ATOMIC_COLOR_ORDER)
     return fail("a2ds_set_scatter_mode: unknown mode");
   if (mode != c->scatter_mode) free_lists(c);
   c->scatter_mode = mode;
   return 0;
+  A2DS_CATCH(a2ds_set_scatter_mode)
 }
 
 // Greedy element colouring: two elements that share a node get different colours, so
@@ -483,6 +516,7 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
                                const int *const *rowp, const int *const *cols,
                                const int *const *row_map, const int *const *col_map,
                                const int *bc_ident, int *mat) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (n_blocks < 1 || n_blocks > 4) return fail("a2ds_mat_create: 1..4 BCSR blocks");
   if (!c->mesh_set) return fail("a2ds_mat_create: call a2ds_set_mesh first");
@@ -547,6 +581,7 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   tm.lap("mat_create: record");
   *mat = (int)c->mats.size() - 1;
   return 0;
+  A2DS_CATCH(a2ds_mat_create)
 }
 
 static int check_mat(a2ds_ctx *c, int mat, int block = 0) {
@@ -605,25 +640,30 @@ static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &ro
 
 extern "C" int a2ds_host_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int *cols,
                                  long long *nnz) {
+  A2DS_TRY
   std::vector<int> rp, cl;
   if (natural_pattern(n_nodes, n_elems, conn, rp, cl)) return 1;
   if (rowp) memcpy(rowp, rp.data(), rp.size() * sizeof(int));
   if (cols) memcpy(cols, cl.data(), cl.size() * sizeof(int));
   if (nnz) *nnz = (long long)cl.size();
   return 0;
+  A2DS_CATCH(a2ds_host_pattern)
 }
 
 extern "C" int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *color,
                                         int *n_colors) {
+  A2DS_TRY
   std::vector<int> col;
   int nc = 0;
   color_elements(n_nodes, n_elems, conn, col, nc);
   memcpy(color, col.data(), col.size() * sizeof(int));
   *n_colors = nc;
   return 0;
+  A2DS_CATCH(a2ds_host_color_elements)
 }
 
 extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
+  A2DS_TRY
   if (!c->mesh_set) return fail("a2ds_mat_create_natural: call a2ds_set_mesh first");
   if (!c->nat_ready) {
     StageTimer tm;
@@ -635,31 +675,39 @@ extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   const int *rp = c->nat_rowp.data(), *cp = c->nat_cols.data();
   const int ident = 1;
   return a2ds_mat_create(c, 1, &nrows, &rp, &cp, nullptr, nullptr, &ident, mat);
+  A2DS_CATCH(a2ds_mat_create_natural)
 }
 
 extern "C" int a2ds_mat_pattern(a2ds_ctx *c, int mat, int block, int *nrows, int *rowp, int *cols) {
+  A2DS_TRY
   if (check_mat(c, mat, block)) return 1;
   MatrixRec &m = c->mats[mat];
   if (nrows) *nrows = m.nrows[block];
   if (rowp) memcpy(rowp, m.h_rowp[block].data(), m.h_rowp[block].size() * sizeof(int));
   if (cols) memcpy(cols, m.h_cols[block].data(), m.h_cols[block].size() * sizeof(int));
   return 0;
+  A2DS_CATCH(a2ds_mat_pattern)
 }
 
 extern "C" int a2ds_mat_nnz(a2ds_ctx *c, int mat, int block, long long *nnz) {
+  A2DS_TRY
   if (check_mat(c, mat, block)) return 1;
   *nnz = c->mats[mat].nnz[block];
   return 0;
+  A2DS_CATCH(a2ds_mat_nnz)
 }
 
 extern "C" int a2ds_mat_zero(a2ds_ctx *c, int mat) {
+  A2DS_TRY
   if (check_mat(c, mat)) return 1;
   CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->mats[mat].A, 0, c->mats[mat].total * 36 * sizeof(double), c->stream));
   return 0;
+  A2DS_CATCH(a2ds_mat_zero)
 }
 
 extern "C" int a2ds_mat_download(a2ds_ctx *c, int mat, int block, double *A) {
+  A2DS_TRY
   if (check_mat(c, mat, block)) return 1;
   CU(cudaSetDevice(c->device));
   MatrixRec &m = c->mats[mat];
@@ -667,12 +715,15 @@ extern "C" int a2ds_mat_download(a2ds_ctx *c, int mat, int block, double *A) {
                      cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+  A2DS_CATCH(a2ds_mat_download)
 }
 
 extern "C" int a2ds_mat_values_dev(a2ds_ctx *c, int mat, int block, double **A_dev) {
+  A2DS_TRY
   if (check_mat(c, mat, block)) return 1;
   *A_dev = c->mats[mat].A + 36 * c->mats[mat].base[block];
   return 0;
+  A2DS_CATCH(a2ds_mat_values_dev)
 }
 
 // 64-bit FNV-1a over the block patterns: computed once per matrix so that copyValues / axpy
@@ -700,6 +751,7 @@ static int same_pattern(a2ds_ctx *c, int a, int b) {
 }
 
 extern "C" int a2ds_mat_copy(a2ds_ctx *c, int dst, int src) {
+  A2DS_TRY
   if (same_pattern(c, dst, src)) return 1;
   CU(cudaSetDevice(c->device));
   const size_t n2 = (size_t)c->mats[src].total * 18;
@@ -709,9 +761,11 @@ extern "C" int a2ds_mat_copy(a2ds_ctx *c, int dst, int src) {
         reinterpret_cast<double2 *>(c->mats[dst].A));
   CU(cudaGetLastError());
   return 0;
+  A2DS_CATCH(a2ds_mat_copy)
 }
 
 extern "C" int a2ds_mat_axpy(a2ds_ctx *c, double alpha, int x, int y) {
+  A2DS_TRY
   if (same_pattern(c, x, y)) return 1;
   CU(cudaSetDevice(c->device));
   const size_t n2 = (size_t)c->mats[x].total * 18;
@@ -721,9 +775,11 @@ extern "C" int a2ds_mat_axpy(a2ds_ctx *c, double alpha, int x, int y) {
         reinterpret_cast<double2 *>(c->mats[y].A));
   CU(cudaGetLastError());
   return 0;
+  A2DS_CATCH(a2ds_mat_axpy)
 }
 
 extern "C" int a2ds_mat_apply_bcs(a2ds_ctx *c, int mat) {
+  A2DS_TRY
   if (check_mat(c, mat)) return 1;
   CU(cudaSetDevice(c->device));
   if (!c->n_bc) return 0;
@@ -733,10 +789,12 @@ extern "C" int a2ds_mat_apply_bcs(a2ds_ctx *c, int mat) {
                                                      m.blk_dev, m.A);
   CU(cudaGetLastError());
   return 0;
+  A2DS_CATCH(a2ds_mat_apply_bcs)
 }
 
 extern "C" int a2ds_mat_mult_dev(a2ds_ctx *c, int mat, int block, const double *x_dev,
                                  double *y_dev) {
+  A2DS_TRY
   if (check_mat(c, mat, block)) return 1;
   CU(cudaSetDevice(c->device));
   MatrixRec &m = c->mats[mat];
@@ -747,6 +805,7 @@ extern "C" int a2ds_mat_mult_dev(a2ds_ctx *c, int mat, int block, const double *
       nrows, m.d_rowp[block], m.d_cols[block], m.A + 36 * m.base[block], x_dev, y_dev);
   CU(cudaGetLastError());
   return 0;
+  A2DS_CATCH(a2ds_mat_mult_dev)
 }
 
 // Distributed mat-vec for a matrix assembled per rank over its local nodes (interface rows
@@ -756,6 +815,7 @@ extern "C" int a2ds_mat_mult_dev(a2ds_ctx *c, int mat, int block, const double *
 //   ghost entries of x <- owners, y = A_local x over ALL local rows, ghost rows of y -> owners
 //   (add), y[bc] = x[bc].
 extern "C" int a2ds_mat_mult_dist_dev(a2ds_ctx *c, int mat, double *x_dev, double *y_dev) {
+  A2DS_TRY
   if (check_mat(c, mat, 0)) return 1;
   CU(cudaSetDevice(c->device));
   MatrixRec &m = c->mats[mat];
@@ -771,10 +831,12 @@ extern "C" int a2ds_mat_mult_dist_dev(a2ds_ctx *c, int mat, double *x_dev, doubl
     CU(cudaGetLastError());
   }
   return 0;
+  A2DS_CATCH(a2ds_mat_mult_dist_dev)
 }
 
 extern "C" int a2ds_mat_mult(a2ds_ctx *c, int mat, int block, int ncols, const double *x,
                              double *y) {
+  A2DS_TRY
   if (check_mat(c, mat, block)) return 1;
   CU(cudaSetDevice(c->device));
   const int nrows = c->mats[mat].nrows[block];
@@ -794,36 +856,44 @@ extern "C" int a2ds_mat_mult(a2ds_ctx *c, int mat, int block, int ncols, const d
   }
   cudaFree(dx); cudaFree(dy);
   return rc;
+  A2DS_CATCH(a2ds_mat_mult)
 }
 
 extern "C" int a2ds_res_dev(a2ds_ctx *c, double **r) { *r = c->res; return 0; }
 extern "C" int a2ds_state_dev(a2ds_ctx *c, double **u) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (state_wait(c)) return 1;
   *u = c->u;
   return 0;
+  A2DS_CATCH(a2ds_state_dev)
 }
 
 // ---- halo -------------------------------------------------------------------
 extern "C" int a2ds_comm_unique_id(char id[128]) {
+  A2DS_TRY
   ncclUniqueId uid;
   NC(ncclGetUniqueId(&uid));
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   memcpy(id, &uid, 128);
   return 0;
+  A2DS_CATCH(a2ds_comm_unique_id)
 }
 
 extern "C" int a2ds_comm_init(a2ds_ctx *c, int n_ranks, int rank, const char id[128]) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   ncclUniqueId uid;
   memcpy(&uid, id, 128);
   NC(ncclCommInitRank(&c->comm, n_ranks, uid, rank));
   c->n_ranks = n_ranks; c->rank = rank;
   return 0;
+  A2DS_CATCH(a2ds_comm_init)
 }
 
 extern "C" int a2ds_set_halo(a2ds_ctx *c, int n_peers, const int *peer_rank, const int *send_ptr,
                              const int *send_nodes, const int *recv_ptr, const int *recv_nodes) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("a2ds_set_halo: call a2ds_set_mesh first");
   if (n_peers < 0 || !send_ptr || !recv_ptr || send_ptr[0] != 0 || recv_ptr[0] != 0)
@@ -855,6 +925,7 @@ extern "C" int a2ds_set_halo(a2ds_ctx *c, int n_peers, const int *peer_rank, con
   CU(cudaMalloc((void **)&c->recv_buf, std::max<size_t>(nb, 1) * 6 * sizeof(double)));
   c->has_halo = n_peers > 0;
   return 0;
+  A2DS_CATCH(a2ds_set_halo)
 }
 
 // forward: owners send the values of send_nodes, ghosts receive into recv_nodes
@@ -933,6 +1004,7 @@ static int mat_halo_reverse(a2ds_ctx *c, MatrixRec &m) {
 extern "C" int a2ds_mat_set_halo(a2ds_ctx *c, int mat, int n_peers, const int *peer_rank,
                                  const int *send_ptr, const int *send_blocks,
                                  const int *recv_ptr, const int *recv_blocks) {
+  A2DS_TRY
   if (check_mat(c, mat)) return 1;
   CU(cudaSetDevice(c->device));
   MatrixRec &m = c->mats[mat];
@@ -958,15 +1030,18 @@ extern "C" int a2ds_mat_set_halo(a2ds_ctx *c, int mat, int n_peers, const int *p
   m.owned.push_back(sbuf); m.owned.push_back(rbuf);
   m.has_halo = n_peers > 0;
   return 0;
+  A2DS_CATCH(a2ds_mat_set_halo)
 }
 
 extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   // With a host upload still in flight the exchange is queued behind it at the first use of
   // the state (every rank does the same, so the sends and receives still pair up): the
   // zeroing at the start of the next assembly then overlaps the upload on all ranks.
   if (c->state_pending) { c->halo_pending = true; return 0; }
   return halo_exchange(c, c->u, false);
+  A2DS_CATCH(a2ds_halo_forward)
 }
 
 // ---- assembly ------------------------------------------------------------------
@@ -1174,7 +1249,9 @@ static int run_assembly(a2ds_ctx *c, int what, double alpha, int kmat, int gmat,
 }
 
 extern "C" int a2ds_assemble_res(a2ds_ctx *c, double *res) {
+  A2DS_TRY
   return run_assembly(c, 1, 1.0, -1, -1, res);
+  A2DS_CATCH(a2ds_assemble_res)
 }
 
 // beta multiplies dR/d(udot): this element class has no velocity dependent term (the
@@ -1182,14 +1259,17 @@ extern "C" int a2ds_assemble_res(a2ds_ctx *c, double *res) {
 // TACSDirector.h:369-486), so any beta is accepted and has no effect.
 extern "C" int a2ds_assemble_jacobian(a2ds_ctx *c, double alpha, double beta, double gamma,
                                       double *res, int mat) {
+  A2DS_TRY
   (void)beta;
   AsmReq rq;
   rq.what = 3 | (gamma != 0.0 ? 8 : 0);
   rq.alpha = alpha; rq.mscale = gamma; rq.kmat = mat; rq.mmat = mat; rq.res_host = res;
   return run_assembly(c, rq);
+  A2DS_CATCH(a2ds_assemble_jacobian)
 }
 
 extern "C" int a2ds_assemble_mat_type(a2ds_ctx *c, int mat_type, int mat) {
+  A2DS_TRY
   if (mat_type == A2DS_STIFFNESS_MATRIX) return run_assembly(c, 2, 1.0, mat, -1, nullptr);
   if (mat_type == A2DS_GEOMETRIC_STIFFNESS_MATRIX) return run_assembly(c, 4, 1.0, -1, mat, nullptr);
   if (mat_type == A2DS_MASS_MATRIX) {
@@ -1198,12 +1278,14 @@ extern "C" int a2ds_assemble_mat_type(a2ds_ctx *c, int mat_type, int mat) {
     return run_assembly(c, rq);
   }
   return fail("a2ds_assemble_mat_type: unknown matrix type");
+  A2DS_CATCH(a2ds_assemble_mat_type)
 }
 
 // TACSAssembler::assembleMatCombo (src/TACSAssembler.cpp:4264-4318): A = sum_i scale[i] *
 // matType[i], boundary conditions applied once at the end.
 extern "C" int a2ds_assemble_mat_combo(a2ds_ctx *c, int n, const int *mat_types,
                                        const double *scales, int mat) {
+  A2DS_TRY
   if (n <= 0) return fail("a2ds_assemble_mat_combo: need at least one matrix type");
   if (check_mat(c, mat)) return 1;
   for (int i = 0; i < n; i++) {
@@ -1216,10 +1298,13 @@ extern "C" int a2ds_assemble_mat_combo(a2ds_ctx *c, int n, const int *mat_types,
     if (run_assembly(c, rq)) return 1;
   }
   return 0;
+  A2DS_CATCH(a2ds_assemble_mat_combo)
 }
 
 extern "C" int a2ds_assemble_all(a2ds_ctx *c, double *res, int kmat, int gmat) {
+  A2DS_TRY
   return run_assembly(c, 7, 1.0, kmat, gmat, res);
+  A2DS_CATCH(a2ds_assemble_all)
 }
 
 // TACSAssembler::addJacobianVecProduct (src/TACSAssembler.cpp:4331-4391), matrix free:
@@ -1228,6 +1313,7 @@ extern "C" int a2ds_assemble_all(a2ds_ctx *c, double *res, int kmat, int gmat) {
 // without thermal strain: r(x) = sum w B^T C B x — the residual kernel with u := x.
 extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, double alpha,
                                                  const double *x_dev, double *y_dev) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("addJacobianVecProduct: mesh or nodes not set");
   if (build_lists(c)) return 1;
@@ -1266,10 +1352,12 @@ extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, doub
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, c->stream));
   return 0;
+  A2DS_CATCH(a2ds_add_jacobian_vec_product_dev)
 }
 
 extern "C" int a2ds_add_jacobian_vec_product(a2ds_ctx *c, double scale, double alpha,
                                              const double *x, double *y) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   const size_t nb = 6 * (size_t)c->n_nodes * sizeof(double);
   double *dx = nullptr, *dy = nullptr;
@@ -1284,34 +1372,43 @@ extern "C" int a2ds_add_jacobian_vec_product(a2ds_ctx *c, double scale, double a
   }
   cudaFree(dx); cudaFree(dy);
   return rc;
+  A2DS_CATCH(a2ds_add_jacobian_vec_product)
 }
 
 extern "C" int a2ds_last_timing(a2ds_ctx *c, float *ms, int *launches) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->ev1));
   CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   if (ms) *ms = c->last_ms;
   if (launches) *launches = c->last_launches;
   return 0;
+  A2DS_CATCH(a2ds_last_timing)
 }
 
 extern "C" int a2ds_last_kernel_ms(a2ds_ctx *c, float *ms) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->evk1));
   CU(cudaEventElapsedTime(ms, c->evk0, c->evk1));
   return 0;
+  A2DS_CATCH(a2ds_last_kernel_ms)
 }
 
 extern "C" int a2ds_region_begin(a2ds_ctx *c) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   CU(cudaEventRecord(c->evr0, c->stream));
   return 0;
+  A2DS_CATCH(a2ds_region_begin)
 }
 
 extern "C" int a2ds_region_end(a2ds_ctx *c, float *ms) {
+  A2DS_TRY
   CU(cudaSetDevice(c->device));
   CU(cudaEventRecord(c->evr1, c->stream));
   CU(cudaEventSynchronize(c->evr1));
   CU(cudaEventElapsedTime(ms, c->evr0, c->evr1));
   return 0;
+  A2DS_CATCH(a2ds_region_end)
 }
