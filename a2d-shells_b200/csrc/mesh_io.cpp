@@ -449,7 +449,13 @@ static int read_bdf_impl(const char *path, int n_threads, a2ds_mesh **out) {
   } else {
     std::vector<std::thread> pool;
     for (int k = 0; k < parts; k++)
-      pool.emplace_back([&, k] { parse_chunk(buf, cuts[k], cuts[k + 1], chunk[k]); });
+      pool.emplace_back([&, k] {
+        try {
+          parse_chunk(buf, cuts[k], cuts[k + 1], chunk[k]);
+        } catch (const std::exception &e) {  // out of memory in a worker: report, do not terminate
+          chunk[k].error = std::string("parser thread: ") + e.what();
+        }
+      });
     for (auto &t : pool) t.join();
   }
 
