@@ -127,8 +127,9 @@ struct a2ds_ctx {
   // element lists: [class][colour]; colour list 0 of the atomic mode holds everything
   bool lists_ready = false;
   int n_colors = 0;
-  std::vector<int *> list_dev[2];
-  std::vector<int> list_len[2];
+  // class = strain model (0 linear, 1 nonlinear) + 2 * (section with membrane-bending coupling)
+  std::vector<int *> list_dev[4];
+  std::vector<int> list_len[4];
   // halo
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -204,7 +205,7 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
 }
 
 static void free_lists(a2ds_ctx *c) {
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < 4; k++) {
     for (int *p : c->list_dev[k])
       if (p) cudaFree(p);
     c->list_dev[k].clear();
@@ -310,10 +311,10 @@ extern "C" int a2ds_set_components(a2ds_ctx *c, int n_comp, const double *Cs, co
     if (h[i].model != A2DS_QUAD4_SHELL && h[i].model != A2DS_QUAD4_NONLINEAR_SHELL)
       return fail("a2ds_set_components: unsupported element class (only TACSQuad4Shell and "
                   "TACSQuad4NonlinearShell are implemented)");
-    c->h_class[i] = h[i].model;
     h[i].coupled = 0;
     for (int k = 6; k < 12; k++)
       if (h[i].Cs[k] != 0.0) h[i].coupled = 1;
+    c->h_class[i] = h[i].model + 2 * h[i].coupled;
     h[i].pad_ = 0;
     h[i].transform = transform;
     h[i].axis[0] = h[i].axis[1] = h[i].axis[2] = 0.0;
@@ -487,7 +488,7 @@ static int build_lists(a2ds_ctx *c) {
   const int ncol_color = ncol;
   if (one_launch) ncol = 1;
   c->n_colors = ncol;
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < 4; k++) {
     std::vector<std::vector<int>> lists(ncol);
     if (one_launch) {
       for (int col = 0; col < ncol_color; col++)
@@ -1086,6 +1087,54 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   return 0;
 }
 
+// the tying-level kernel (components without membrane-bending coupling)
+template <bool RES, bool KMAT, bool GMAT, bool NL>
+static int launch_one_t(a2ds_ctx *c, KParams &p) {
+  const size_t raw = (GMAT || NL) ? sizeof(WarpScratchT) : offsetof(WarpScratchT, raw1);
+  const size_t per_warp = (raw + 15) & ~size_t(15);
+  p.scratch_bytes = (int)per_warp;
+  auto kern = k_assemble_t<RES, KMAT, GMAT, NL>;
+  static int best_wpb_dev[MAX_DEVICES] = {0}, best_per_sm_dev[MAX_DEVICES] = {0};
+  int &best_wpb = best_wpb_dev[c->device], &best_per_sm = best_per_sm_dev[c->device];
+  if (best_wpb == 0 || c->warps_per_block_forced) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(per_warp * MAX_WARPS_PER_BLOCK)));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    int best = 0;
+    for (int wv = MAX_WARPS_PER_BLOCK; wv >= 1; wv--) {
+      if (c->warps_per_block_forced && wv != c->warps_per_block_forced) continue;
+      int per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wv * 32, per_warp * wv));
+      if (per_sm * wv > best) { best = per_sm * wv; best_wpb = wv; best_per_sm = per_sm; }
+    }
+    if (best == 0) return fail("k_assemble_t does not fit on an SM");
+    if (getenv("A2DS_VERBOSE"))
+      fprintf(stderr, "[a2ds] k_assemble_t<%d,%d,%d,%d>: %zu B scratch/warp, %d warps/block x %d blocks/SM\n",
+              (int)RES, (int)KMAT, (int)GMAT, (int)NL, per_warp, best_wpb, best_per_sm);
+  }
+  const int wpb = best_wpb, per_sm = best_per_sm;
+  const size_t smem = per_warp * (size_t)wpb;
+  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, sizeof(int)));
+  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  p.work_counter = c->work_counter;
+  const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
+  const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
+  kern<<<grid, wpb * 32, smem, c->stream>>>(p);
+  CU(cudaGetLastError());
+  c->last_launches++;
+  return 0;
+}
+
+// element kernel of a class: tying-level formulation unless the section couples membrane and
+// bending (or A2DS_FORMULATION=0 asks for the first formulation everywhere: A/B measurements)
+template <bool RES, bool KMAT, bool GMAT, bool NL>
+static int launch_elem(a2ds_ctx *c, KParams &p, bool coupled) {
+  static const bool force_first = getenv("A2DS_FORMULATION") && atoi(getenv("A2DS_FORMULATION")) == 0;
+  if (coupled || force_first) return launch_one<RES, KMAT, GMAT, NL>(c, p);
+  return launch_one_t<RES, KMAT, GMAT, NL>(c, p);
+}
+
 // launch the mass kernel over one element list
 template <bool RES, bool MAT>
 static int launch_mass(a2ds_ctx *c, KParams &p) {
@@ -1169,19 +1218,20 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
 
   CU(cudaEventRecord(c->evk0, c->stream));
   for (int col = 0; col < c->n_colors; col++) {
-    for (int cls = 0; cls < 2; cls++) {
+    for (int cls = 0; cls < 4; cls++) {
+      const bool cpl = cls >= 2;
       p.n_list = c->list_len[cls][col];
       p.elem_list = c->list_dev[cls][col];
       if (p.n_list == 0) continue;
       int rc = 0;
-      if (cls == 0) {
+      if ((cls & 1) == 0) {
         switch (what) {
           case 0: break;
-          case 1: rc = launch_one<true, false, false, false>(c, p); break;
-          case 2: rc = launch_one<false, true, false, false>(c, p); break;
-          case 3: rc = launch_one<true, true, false, false>(c, p); break;
-          case 4: rc = launch_one<false, false, true, false>(c, p); break;
-          case 7: rc = launch_one<true, true, true, false>(c, p); break;
+          case 1: rc = launch_elem<true, false, false, false>(c, p, cpl); break;
+          case 2: rc = launch_elem<false, true, false, false>(c, p, cpl); break;
+          case 3: rc = launch_elem<true, true, false, false>(c, p, cpl); break;
+          case 4: rc = launch_elem<false, false, true, false>(c, p, cpl); break;
+          case 7: rc = launch_elem<true, true, true, false>(c, p, cpl); break;
           default: return fail("assemble: unsupported output combination");
         }
       } else {
@@ -1191,13 +1241,13 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
         // for the linear model and is evaluated with the linear-model kernel.
         switch (what) {
           case 0: break;
-          case 1: rc = launch_one<true, false, false, true>(c, p); break;
-          case 2: rc = launch_one<false, true, false, true>(c, p); break;
-          case 3: rc = launch_one<true, true, false, true>(c, p); break;
-          case 4: rc = launch_one<false, false, true, false>(c, p); break;
+          case 1: rc = launch_elem<true, false, false, true>(c, p, cpl); break;
+          case 2: rc = launch_elem<false, true, false, true>(c, p, cpl); break;
+          case 3: rc = launch_elem<true, true, false, true>(c, p, cpl); break;
+          case 4: rc = launch_elem<false, false, true, false>(c, p, cpl); break;
           case 7:
-            rc = launch_one<true, true, false, true>(c, p);
-            if (!rc) rc = launch_one<false, false, true, false>(c, p);
+            rc = launch_elem<true, true, false, true>(c, p, cpl);
+            if (!rc) rc = launch_elem<false, false, true, false>(c, p, cpl);
             break;
           default: return fail("assemble: unsupported output combination");
         }
@@ -1325,23 +1375,24 @@ extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, doub
   p.conn = c->conn; p.elem_comp = c->elem_comp; p.comps = c->comps;
   p.X = c->X; p.gscale = 1.0;
   CU(cudaEventRecord(c->evk0, c->stream));
-  for (int col = 0; col < c->n_colors; col++) {
-    // linear strain model: K does not depend on the state, K x = residual kernel with u := x
-    p.n_list = c->list_len[0][col];
-    p.elem_list = c->list_dev[0][col];
-    p.u = x_dev; p.res = y_dev; p.alpha = 1.0;
-    p.res_scale = scale * alpha; p.thermal = 0.0;
-    p.jvp_x = nullptr; p.jvp_y = nullptr;
-    if (p.n_list > 0 && launch_one<true, false, false, false>(c, p)) return 1;
-    // nonlinear strain model: the tangent about the current state is formed per element
-    // (as for assembleJacobian) and multiplied with the element's slice of x in shared
-    // memory instead of being scattered
-    p.n_list = c->list_len[1][col];
-    p.elem_list = c->list_dev[1][col];
-    p.u = c->u; p.res = nullptr; p.alpha = alpha; p.thermal = 1.0;
-    p.jvp_x = x_dev; p.jvp_y = y_dev; p.jvp_scale = scale;
-    if (p.n_list > 0 && launch_one<false, true, false, true>(c, p)) return 1;
-  }
+  for (int col = 0; col < c->n_colors; col++)
+    for (int cpl = 0; cpl < 2; cpl++) {
+      // linear strain model: K does not depend on the state, K x = residual kernel with u := x
+      p.n_list = c->list_len[2 * cpl][col];
+      p.elem_list = c->list_dev[2 * cpl][col];
+      p.u = x_dev; p.res = y_dev; p.alpha = 1.0;
+      p.res_scale = scale * alpha; p.thermal = 0.0;
+      p.jvp_x = nullptr; p.jvp_y = nullptr;
+      if (p.n_list > 0 && launch_elem<true, false, false, false>(c, p, cpl != 0)) return 1;
+      // nonlinear strain model: the tangent about the current state is formed per element
+      // (as for assembleJacobian) and multiplied with the element's slice of x in shared
+      // memory instead of being scattered
+      p.n_list = c->list_len[2 * cpl + 1][col];
+      p.elem_list = c->list_dev[2 * cpl + 1][col];
+      p.u = c->u; p.res = nullptr; p.alpha = alpha; p.thermal = 1.0;
+      p.jvp_x = x_dev; p.jvp_y = y_dev; p.jvp_scale = scale;
+      if (p.n_list > 0 && launch_elem<false, true, false, true>(c, p, cpl != 0)) return 1;
+    }
   CU(cudaEventRecord(c->evk1, c->stream));
   if (halo_exchange(c, y_dev, true)) return 1;
   if (c->n_bc) {

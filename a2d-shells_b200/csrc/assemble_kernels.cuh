@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "mitc4_math.h"
+#include "mitc4_tying.h"
 
 using namespace a2ds;
 struct KParams {
@@ -436,6 +437,314 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
       if (GMAT) {
         if (KMAT) __syncwarp();  // E is reused for G once K has left
         symmetrize_add_geo(gm, wk, &ws.Pq[j][0][0], ws.E2, ws.E, p.gscale, lane);
+        __syncwarp();
+        scatter_matrix(ws.E, p.Gval, goffb[j][lane & 15], lane);
+      }
+      __syncwarp();
+    }
+    drawn = __shfl_sync(FULL, drawn, 0);
+    if (PF) { grp = grp_nxt; grp_nxt = drawn; }
+    else { grp = drawn; batch_ids(grp, e_cur, nd_cur); }
+  }
+}
+
+
+// =====================================================================================
+// k_assemble_t<RES, KMAT, GMAT, NL>: the same assembly with the element contraction at the
+// tying-point level (mitc4_tying.h): 7 instead of 9 DMMA k-steps for the tangent, 6 instead
+// of 8 for the geometric stiffness, which accumulates Z + Z^T directly in the 6 upper tiles
+// (two MMAs per off-diagonal tile; the diagonal tiles are symmetrised when the geometric
+// blocks are added), so there is no second staging tile.  Components without
+// membrane-bending coupling only (run_assembly sends coupled ones to k_assemble).
+// =====================================================================================
+struct BatchTmp {   // inputs of the batched phases; overlaid on the staging tile E, which is
+  double X[12], q[24], dr[12], etn[4];   // only live inside the per-element loop
+};                  // 52 doubles = 4 (mod 16)
+struct NodeView {   // what phase_node / qp_geometry address as one record
+  double *X, *q, *fn, *dr, *wn, *cdr, *etn;
+};
+struct ElemRecT {   // ElemRec without the batch-phase-only arrays
+  double fn[12], wn[12], cdr[36];
+  NodeTab t0[4], t1[4];
+  QpRec qp[4];
+  double pad_[12];  // 532 doubles = 4 (mod 16): the 16 (element, point) lanes hit 16 banks
+};
+struct WarpScratchT {
+  RawBatch raw0;
+  int nodes[NB][4];
+  ElemRecT rec[NB];
+  union {
+    double E[24 * KE_LD];   // staging of a 24x24 element matrix for the scatter
+    BatchTmp tmp[NB];
+  };
+  TyWork work;
+  // ---- double-buffered gather (geometric stiffness / nonlinear variants) ----
+  RawBatch raw1;
+  int goff[2][NB][16];
+};
+static_assert(sizeof(BatchTmp) * NB <= sizeof(double) * 24 * KE_LD, "batch inputs overlay E");
+
+// record view used by the per-lane functions of mitc4_tying.h (they address ElemRec members)
+struct RecView {
+  const double *fn, *wn, *cdr;
+  const NodeTab *t0, *t1;
+  const QpRec *qp;
+};
+
+__device__ __forceinline__ void stage_tiles_g(double *E, const double (&acc)[6][2], int lane) {
+  const int rowb = 3 * (lane >> 2), colb = 6 * (lane & 3);
+  int idx = 0;
+#pragma unroll
+  for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+    for (int tj = ti; tj < 3; tj++, idx++) {
+      const int row = rowb + ti, col0 = colb + tj, col1 = colb + 3 + tj;
+      E[row * KE_LD + col0] = acc[idx][0];
+      E[row * KE_LD + col1] = acc[idx][1];
+      if (ti != tj) {   // off-diagonal tiles already hold Z + Z^T: mirror
+        E[col0 * KE_LD + row] = acc[idx][0];
+        E[col1 * KE_LD + row] = acc[idx][1];
+      }
+    }
+}
+
+template <bool RES, bool KMAT, bool GMAT, bool NL>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(const KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpScratchT &ws = *reinterpret_cast<WarpScratchT *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  TyWork &wk = ws.work;
+  const bool PF = (GMAT || NL);   // asynchronous prefetch of the next batch
+  const unsigned FULL = 0xffffffffu;
+  Want w;
+  w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL; w.thermal = p.thermal;
+  const bool need_state = GMAT || NL;
+  const int n_groups = (p.n_list + NB - 1) / NB;
+
+  // lane constants: the two entries of H_tt this lane builds per element; zero row of H
+  TyPlan pl0, pl1;
+  ty_plan(lane, pl0);
+  ty_plan(lane + 32 < 45 ? lane + 32 : 44, pl1);
+  if (lane < TY_LD) { wk.H[TY_LD * 9 + lane] = 0.0; wk.H[TY_LD * lane + 9] = 0.0; wk.sigt[lane] = 0.0; }
+
+  auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
+    const int j = (lane >> 2) & (NB - 1);
+    const int idx = grp_ * NB + j;
+    e_out = -1; nd_out = 0;
+    if (grp_ < n_groups && idx < p.n_list) {
+      e_out = p.elem_list ? __ldg(&p.elem_list[idx]) : idx;
+      nd_out = __ldg(&p.conn[4 * e_out + (lane & 3)]);
+    }
+  };
+  auto issue_gather = [&](RawBatch &rb, int (*goffb)[16], int e_l, int nd_l) {
+#pragma unroll
+    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx / 36, k = sidx - 36 * j;
+      const bool isx = k < 12;
+      const int node = isx ? k / 3 : (k - 12) / 6;
+      const int comp_k = isx ? k - 3 * node : (k - 12) - 6 * node;
+      const int src_lane = (4 * j + node) & 31;
+      const int nd = __shfl_sync(FULL, nd_l, src_lane);
+      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+      if (sidx < NB * 36 && ej >= 0) {
+        const double *src = isx ? &p.X[3 * (size_t)nd + comp_k] : &p.u[6 * (size_t)nd + comp_k];
+        cp_async8(&rb.xq[j][k], src);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NB * 16 / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx >> 4, k = sidx & 15;
+      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
+      if (ej >= 0) {
+        if (KMAT && p.Koff) cp_async4(&rb.koff[j][k], &p.Koff[16 * (size_t)ej + k]);
+        if (GMAT) cp_async4(&goffb[j][k], &p.Goff[16 * (size_t)ej + k]);
+      }
+    }
+    if ((lane & 3) == 0 && lane < 4 * NB && e_l >= 0) cp_async4(&rb.comp[lane >> 2], &p.elem_comp[e_l]);
+  };
+  auto next_group = [&]() {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(p.work_counter, 1);
+    return __shfl_sync(FULL, g, 0);
+  };
+  int grp = next_group();
+  int grp_nxt = PF ? next_group() : 0;
+  int buf = 0;
+  int e_cur, nd_cur;
+  batch_ids(grp, e_cur, nd_cur);
+  if (PF && grp < n_groups) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
+  for (; grp < n_groups; buf ^= 1) {
+    int drawn = 0;
+    if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
+    const int base = grp * NB;
+    const int cnt = min(NB, p.n_list - base);
+    int e_nxt = -1, nd_nxt = 0;
+    if (PF) batch_ids(grp_nxt, e_nxt, nd_nxt);
+
+    if (!PF) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
+    cp_async_wait_all();
+    __syncwarp();
+    const RawBatch &rb = (PF && buf) ? ws.raw1 : ws.raw0;
+    const int (*goffb)[16] = ws.goff[(PF && buf) ? 1 : 0];
+    if (lane < 4 * NB) ws.nodes[lane >> 2][lane & 3] = nd_cur;
+#pragma unroll
+    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
+      const int sidx = lane + 32 * r;
+      const int j = sidx / 36, k = sidx - 36 * j;
+      if (sidx < NB * 36) {
+        const double v = rb.xq[j][k];
+        if (k < 12) ws.tmp[j].X[k] = v; else ws.tmp[j].q[k - 12] = v;
+      }
+    }
+    __syncwarp();
+
+    // ---- batched phases: lane = (element of the batch, node | Gauss point) ----------------
+    const int jb = (lane >> 2) & (NB - 1);
+    const bool act = lane < 4 * NB && jb < cnt;
+    NodeView nv;
+    nv.X = ws.tmp[jb].X; nv.q = ws.tmp[jb].q; nv.dr = ws.tmp[jb].dr; nv.etn = ws.tmp[jb].etn;
+    nv.fn = ws.rec[jb].fn; nv.wn = ws.rec[jb].wn; nv.cdr = ws.rec[jb].cdr;
+    if (act) phase_node(p.comps[rb.comp[jb]], nv, lane & 3);
+    __syncwarp();
+    if (act) {
+      ElemRecT &rc = ws.rec[jb];
+      const int m = lane & 3;
+      node_tab(rc.t0[m], nv.X, 3, nv.fn, &nv.fn[3 * m], m);
+      if (need_state) node_tab(rc.t1[m], nv.q, 6, nv.dr, &nv.fn[3 * m], m);
+      phase_qp_t(p.comps[rb.comp[jb]], nv, rc.qp[lane & 3], lane & 3, w);
+    }
+    if (PF && grp_nxt < n_groups)
+      issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ? 0 : 1], e_nxt, nd_nxt);
+    if (PF) { e_cur = e_nxt; nd_cur = nd_nxt; }
+    __syncwarp();
+
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+      const ElemRecT &rc = ws.rec[j];
+      RecView gm;
+      gm.fn = rc.fn; gm.wn = rc.wn; gm.cdr = rc.cdr; gm.t0 = rc.t0; gm.t1 = rc.t1; gm.qp = rc.qp;
+      // ---- element prologue: H_tt (45 entries over 32 lanes) and the tying stresses --------
+      if (KMAT || GMAT) {
+        ty_H_entry(gm, pl0, wk.H);
+        if (lane + 32 < 45) ty_H_entry(gm, pl1, wk.H);
+      }
+      if ((RES || need_state) && lane < 9) ty_sum_stress(gm, wk, lane);
+      __syncwarp();
+
+      // ---- column phase: the lane's rows of Bt, W = H Bt (and Bt1) ARE the DMMA fragments ----
+      LaneFrag f;
+      double B1[6][3];
+      lane_fragments(gm, wk, lane, w, f, B1);
+      if (RES) {
+        double r3[3];
+        lane_residual(gm, wk, lane, f, r3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          r3[k] += __shfl_xor_sync(FULL, r3[k], 1);
+          r3[k] += __shfl_xor_sync(FULL, r3[k], 2);
+        }
+        if ((lane & 3) == 0) {
+          double *r = &p.res[6 * (size_t)ws.nodes[j][lane_m(lane)] + 3 * lane_h(lane)];
+          atomicAdd(r, p.res_scale * r3[0]);
+          atomicAdd(r + 1, p.res_scale * r3[1]);
+          atomicAdd(r + 2, p.res_scale * r3[2]);
+        }
+      }
+      if (KMAT) {
+        double kacc[6][2];
+#pragma unroll
+        for (int t = 0; t < 6; t++) kacc[t][0] = kacc[t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < TY_ROWS; ks++) {
+          int idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], f.B[ks][ti], f.W[ks][tj]);
+        }
+        stage_tiles(ws.E, kacc, p.alpha, lane);
+      }
+      double gacc[6][2];
+      if (GMAT) {
+        // G = Bt1^T W + W^T Bt1 in the 6 upper tiles: off-diagonal tiles take both products,
+        // diagonal tiles take Z_tt = Bt1_t^T W_t and are symmetrised below
+#pragma unroll
+        for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 6; ks++) {
+          int idx = 0;
+#pragma unroll
+          for (int ti = 0; ti < 3; ti++)
+#pragma unroll
+            for (int tj = ti; tj < 3; tj++, idx++) {
+              dmma884(gacc[idx], B1[ks][ti], f.W[ks][tj]);
+              if (ti != tj) dmma884(gacc[idx], f.W[ks][ti], B1[ks][tj]);
+            }
+        }
+      }
+      __syncwarp();   // E staged; coefficient pairs of the geometric phase published
+      if (KMAT) {
+        if (NL) {
+#pragma unroll
+          for (int pass = 0; pass < 2; pass++) {
+            const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+            double blk[9];
+            geo_block_t(gm, wk, pr, pc, blk);
+            const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+              for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] += p.alpha * blk[3 * i + jj];
+          }
+          __syncwarp();
+        }
+        if (NL && !GMAT && p.jvp_x) {
+          const int node = ws.nodes[j][(lane / 6) & 3];
+          double xv = 0.0;
+          if (lane < 24) xv = p.jvp_x[6 * (size_t)node + lane % 6];
+          double y = 0.0;
+#pragma unroll
+          for (int k = 0; k < 24; k++) {
+            const double xk = __shfl_sync(FULL, xv, k);
+            if (lane < 24) y += ws.E[lane * KE_LD + k] * xk;
+          }
+          if (lane < 24) atomicAdd(&p.jvp_y[6 * (size_t)node + lane % 6], p.jvp_scale * y);
+        } else {
+          scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
+        }
+      }
+      if (GMAT) {
+        if (KMAT) __syncwarp();   // E is reused for G once K has left
+        stage_tiles_g(ws.E, gacc, lane);
+        __syncwarp();
+        double v[2][9];
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+          const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+          double blk[9];
+          geo_block_t(gm, wk, pr, pc, blk);
+          const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++) {
+              double z = ws.E[(r0 + i) * KE_LD + c0 + jj];
+              if (i == jj) z += ws.E[(c0 + jj) * KE_LD + r0 + i];   // diagonal tiles: Z + Z^T
+              v[pass][3 * i + jj] = p.gscale * (blk[3 * i + jj] + z);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+          const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+          const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] = v[pass][3 * i + jj];
+        }
         __syncwarp();
         scatter_matrix(ws.E, p.Gval, goffb[j][lane & 15], lane);
       }

@@ -258,7 +258,8 @@ A2DS_HD double sdet2(double a, double b, double c, double d) {  // a*b - c*d
   return A2DS_ADD(A2DS_MUL(a, b), -A2DS_MUL(c, d));
 }
 
-A2DS_HD void phase_node(const CompData &c, ElemGeom &s, int m) {
+template <class Rec>
+A2DS_HD void phase_node(const CompData &c, Rec &s, int m) {
   double Xxi[3], Xeta[3];
   edge_xi(s.X, 3, m / 2, Xxi);    // X,xi at the node (eta = +-1)
   edge_eta(s.X, 3, m % 2, Xeta);  // X,eta at the node (xi = +-1)
@@ -361,7 +362,8 @@ struct QpGeom {
 
 // ---- phase 2a: Gauss point geometry (lane >> 3) ------------------------------
 // TACSShellElement.h:520-534 and TacsShellComputeDispGrad (TACSShellUtilities.h:361-421)
-A2DS_HD void qp_geometry(const CompData &c, const ElemGeom &s, int qp, bool want_e, bool want_P,
+template <class Rec>
+A2DS_HD void qp_geometry(const CompData &c, const Rec &s, int qp, bool want_e, bool want_P,
                          bool nonlinear, QpGeom &g) {
   const double xi = (qp & 1) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;
   const double eta = (qp & 2) ? A2DS_GAUSS_PT : -A2DS_GAUSS_PT;

@@ -45,9 +45,9 @@ def emul():
     import ctypes as C
     so = os.path.join(ROOT, "tests", "_host_emul.so")
     src = os.path.join(ROOT, "tests", "host_emul.cpp")
-    hdr = os.path.join(ROOT, "a2d-shells_b200", "csrc", "mitc4_math.h")
-    if (not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src),
-                                                             os.path.getmtime(hdr))):
+    hdrs = [os.path.join(ROOT, "a2d-shells_b200", "csrc", h) for h in ("mitc4_math.h", "mitc4_tying.h")]
+    if (not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] +
+                                                             [os.path.getmtime(h) for h in hdrs])):
         # -mfma + contraction on: mimics nvcc's FMA fusion outside the strict sections
         subprocess.check_call(["g++", "-O2", "-std=c++14", "-mfma", "-ffp-contract=fast", "-fPIC",
                                "-shared", "-o", so, src])

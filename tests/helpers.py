@@ -31,7 +31,9 @@ def random_elements(n, seed, h_range=(-3, 0), state_range=(-6, -3), flat=False):
     return X, q
 
 
-def emul_element(L, Cs, eth, T, model, transform, axis, X, q, want_g):
+def emul_element(L, Cs, eth, T, model, transform, axis, X, q, want_g, tying=False):
+    """one element through the host emulation of the kernel math; tying=True: the tying-level
+    formulation of k_assemble_t (uncoupled sections only)"""
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     res = np.zeros(24); K = np.zeros(576); G = np.zeros(576)
     ax = np.asarray(axis, float)
@@ -39,8 +41,10 @@ def emul_element(L, Cs, eth, T, model, transform, axis, X, q, want_g):
     Cs = np.ascontiguousarray(Cs, dtype=np.float64); eth = np.ascontiguousarray(eth, dtype=np.float64)
     X = np.ascontiguousarray(X, dtype=np.float64).ravel()
     q = np.ascontiguousarray(q, dtype=np.float64).ravel()
-    L.emul_element(p(Cs), p(eth), C.c_double(T), C.c_int(model), C.c_int(transform), p(ax), p(X),
-                   p(q), C.c_int(want_g), p(res), p(K), p(G))
+    fn = L.emul_element_t if tying else L.emul_element
+    rc = fn(p(Cs), p(eth), C.c_double(T), C.c_int(model), C.c_int(transform), p(ax), p(X),
+            p(q), C.c_int(want_g), p(res), p(K), p(G))
+    assert rc == 0
     return res, K.reshape(24, 24), G.reshape(24, 24)
 
 

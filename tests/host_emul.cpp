@@ -141,3 +141,85 @@ extern "C" int emul_strain_matrices(const double *Cs, int transform, const doubl
   }
   return 0;
 }
+
+// ---- tying-level formulation (mitc4_tying.h, kernel k_assemble_t) ----------------------
+#include "../a2d-shells_b200/csrc/mitc4_tying.h"
+
+extern "C" int emul_element_t(const double *Cs, const double *eth, double temperature, int model,
+                              int transform, const double *axis, const double *X, const double *q,
+                              int want_gmat, double *res, double *K, double *G) {
+  CompData c;
+  memcpy(c.Cs, Cs, sizeof(c.Cs));
+  memcpy(c.eth, eth, sizeof(c.eth));
+  c.temperature = temperature;
+  c.model = model;
+  c.transform = transform;
+  c.coupled = 0;
+  for (int k = 6; k < 12; k++)
+    if (c.Cs[k] != 0.0) return 1;  // this formulation is for uncoupled sections
+  memcpy(c.axis, axis, sizeof(c.axis));
+  static ElemRec s;
+  static TyWork wk;
+  memset(&s, 0, sizeof(s));
+  memset(&wk, 0, sizeof(wk));
+  memcpy(s.X, X, sizeof(s.X));
+  memcpy(s.q, q, sizeof(s.q));
+  Want w;
+  w.res = true; w.kmat = true; w.gmat = want_gmat != 0; w.nonlinear = model == 1; w.thermal = 1.0;
+  const bool need_state = w.gmat || w.nonlinear;
+  for (int m = 0; m < 4; m++) phase_node(c, s, m);
+  for (int m = 0; m < 4; m++) phase_node_tab(s, m, need_state);
+  for (int qp = 0; qp < 4; qp++) phase_qp_t(c, s, s.qp[qp], qp, w);
+  for (int e = 0; e < 45; e++) {
+    TyPlan pl;
+    ty_plan(e, pl);
+    ty_H_entry(s, pl, wk.H);
+  }
+  for (int t = 0; t < 9; t++) ty_sum_stress(s, wk, t);
+  static LaneFrag f[32];
+  static double B1[32][6][3];
+  memset(B1, 0, sizeof(B1));
+  memset(res, 0, 24 * sizeof(double));
+  for (int lane = 0; lane < 32; lane++) {
+    lane_fragments(s, wk, lane, w, f[lane], B1[lane]);
+    double r3[3];
+    lane_residual(s, wk, lane, f[lane], r3);
+    const int col = 6 * lane_m(lane) + 3 * lane_h(lane);
+    for (int k = 0; k < 3; k++) res[col + k] += r3[k];
+  }
+  // dense operands [dof][k = 4 s + kk]
+  static double BA[24][28], W[24][28], BB[24][28];
+  memset(BB, 0, sizeof(BB));
+  for (int lane = 0; lane < 32; lane++) {
+    const int kk = lane_qp(lane), col = 6 * lane_m(lane) + 3 * lane_h(lane);
+    for (int r = 0; r < 7; r++)
+      for (int k = 0; k < 3; k++) {
+        BA[col + k][4 * r + kk] = f[lane].B[r][k];
+        W[col + k][4 * r + kk] = f[lane].W[r][k];
+        if (r < 6) BB[col + k][4 * r + kk] = B1[lane][r][k];
+      }
+  }
+  double geo[576];
+  memset(geo, 0, sizeof(geo));
+  if (need_state)
+    for (int p = 0; p < 8; p++)
+      for (int pp = 0; pp < 8; pp++) {
+        double blk[9];
+        geo_block_t(s, wk, p, pp, blk);
+        int r0 = 6 * (p & 3) + (p >= 4 ? 3 : 0), c0 = 6 * (pp & 3) + (pp >= 4 ? 3 : 0);
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) geo[24 * (r0 + i) + c0 + j] += blk[3 * i + j];
+      }
+  for (int r = 0; r < 24; r++)
+    for (int cc = 0; cc < 24; cc++) {
+      double k = 0.0, gm = 0.0;
+      for (int t = 0; t < 28; t++) {
+        k += BA[r][t] * W[cc][t];
+        gm += BB[r][t] * W[cc][t] + W[r][t] * BB[cc][t];
+      }
+      if (w.nonlinear) k += geo[24 * r + cc];
+      K[24 * r + cc] = k;
+      if (G) G[24 * r + cc] = gm + geo[24 * r + cc];
+    }
+  return 0;
+}
