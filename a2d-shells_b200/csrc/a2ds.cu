@@ -116,7 +116,10 @@ struct a2ds_ctx {
   std::vector<double> h_mom;          // mass moments per component (a2ds_set_mass_moments)
   std::vector<CompData> h_comps;
   double *X = nullptr, *u = nullptr, *res = nullptr;
-  int *work_counter = nullptr;   // one int, zeroed before every k_assemble launch
+  int *work_counter = nullptr;   // [0] batch counter, [1..] zero_done rounds; zeroed before every k_assemble launch
+  // matrices the next k_assemble_t launch has to zero itself (in-kernel zeroing)
+  double *pz_K = nullptr, *pz_G = nullptr;
+  long long pz_nK = 0, pz_nG = 0;
   double *udd = nullptr;  // second time derivative of the state (null until set)
   CompData *comps = nullptr;
   int *bc_nodes = nullptr, *bc_vars = nullptr;
@@ -1046,6 +1049,7 @@ extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
 }
 
 // ---- assembly ------------------------------------------------------------------
+static const int MAX_ZERO_ROUNDS = 4096;   // rounds of the in-kernel zeroing (k_assemble_t)
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_one(a2ds_ctx *c, KParams &p) {
   const size_t raw = (GMAT || NL) ? sizeof(WarpScratch) : offsetof(WarpScratch, E2);
@@ -1076,12 +1080,43 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   }
   const int wpb = best_wpb, per_sm = best_per_sm;
   const size_t smem = per_warp * (size_t)wpb;
-  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, sizeof(int)));
-  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, (1 + MAX_ZERO_ROUNDS) * sizeof(int)));
   p.work_counter = c->work_counter;
-  const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
+  const int n_groups = (p.n_list + NB - 1) / NB;
+  const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
-  kern<<<grid, wpb * 32, smem, c->stream>>>(p);
+  p.zero_rounds = 0;
+  if (c->pz_K || c->pz_G) {
+    // in-kernel zeroing (see k_assemble_t): about one round per trip of a warp
+    static const int ahead = getenv("A2DS_ZERO_AHEAD") ? atoi(getenv("A2DS_ZERO_AHEAD")) : 3;
+    const int n_gw = grid * wpb;
+    const int rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / n_gw));
+    p.zero_rounds = rounds;
+    p.zero_ahead = std::max(1, ahead);
+    p.zeroK = (double2 *)c->pz_K; p.zero_nK = c->pz_nK;
+    p.zeroG = (double2 *)c->pz_G; p.zero_nG = c->pz_nG;
+    const long long per_round = (long long)rounds * n_gw;
+    // whole blocks per chunk (18 double2 each)
+    p.zero_cK = 18 * (int)std::max<long long>(1, (c->pz_nK / 18 + per_round - 1) / per_round);
+    p.zero_cG = 18 * (int)std::max<long long>(1, (c->pz_nG / 18 + per_round - 1) / per_round);
+    // both matrices use the same round boundaries in blocks only when they have the same
+    // chunk; the kernel takes the larger round index of the two, so use the smaller chunk
+    {
+      const double bpr = (double)n_gw * (double)(std::min(p.zeroK ? p.zero_cK : p.zero_cG,
+                                                          p.zeroG ? p.zero_cG : p.zero_cK) / 18);
+      p.zero_inv_round = (float)(1.0 / bpr) * (1.0f + 1e-6f);
+    }
+    p.zero_done = c->work_counter + 1;
+    c->pz_K = c->pz_G = nullptr;
+  }
+  CU(cudaMemsetAsync(c->work_counter, 0, (1 + p.zero_rounds) * sizeof(int), c->stream));
+  if (p.zero_rounds > 0) {
+    // the zeroing protocol waits on every warp of the grid: all blocks must be co-resident
+    void *args[] = {(void *)&p};
+    CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(wpb * 32), args, smem, c->stream));
+  } else {
+    kern<<<grid, wpb * 32, smem, c->stream>>>(p);
+  }
   CU(cudaGetLastError());
   c->last_launches++;
   return 0;
@@ -1090,7 +1125,7 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
 // the tying-level kernel (components without membrane-bending coupling)
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_one_t(a2ds_ctx *c, KParams &p) {
-  const size_t raw = (GMAT || NL) ? sizeof(WarpScratchT) : offsetof(WarpScratchT, raw1);
+  const size_t raw = sizeof(WarpScratchT);
   const size_t per_warp = (raw + 15) & ~size_t(15);
   p.scratch_bytes = (int)per_warp;
   auto kern = k_assemble_t<RES, KMAT, GMAT, NL>;
@@ -1098,14 +1133,14 @@ static int launch_one_t(a2ds_ctx *c, KParams &p) {
   int &best_wpb = best_wpb_dev[c->device], &best_per_sm = best_per_sm_dev[c->device];
   if (best_wpb == 0 || c->warps_per_block_forced) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(per_warp * MAX_WARPS_PER_BLOCK)));
+                            (int)(per_warp * MAX_WARPS_PER_BLOCK + BLOCK_SHARED_T)));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     int best = 0;
     for (int wv = MAX_WARPS_PER_BLOCK; wv >= 1; wv--) {
       if (c->warps_per_block_forced && wv != c->warps_per_block_forced) continue;
       int per_sm = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wv * 32, per_warp * wv));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wv * 32, per_warp * wv + BLOCK_SHARED_T));
       if (per_sm * wv > best) { best = per_sm * wv; best_wpb = wv; best_per_sm = per_sm; }
     }
     if (best == 0) return fail("k_assemble_t does not fit on an SM");
@@ -1114,13 +1149,44 @@ static int launch_one_t(a2ds_ctx *c, KParams &p) {
               (int)RES, (int)KMAT, (int)GMAT, (int)NL, per_warp, best_wpb, best_per_sm);
   }
   const int wpb = best_wpb, per_sm = best_per_sm;
-  const size_t smem = per_warp * (size_t)wpb;
-  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, sizeof(int)));
-  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  const size_t smem = per_warp * (size_t)wpb + BLOCK_SHARED_T;
+  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, (1 + MAX_ZERO_ROUNDS) * sizeof(int)));
   p.work_counter = c->work_counter;
-  const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
+  const int n_groups = (p.n_list + NB - 1) / NB;
+  const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
-  kern<<<grid, wpb * 32, smem, c->stream>>>(p);
+  p.zero_rounds = 0;
+  if (c->pz_K || c->pz_G) {
+    // in-kernel zeroing (see k_assemble_t): about one round per trip of a warp
+    static const int ahead = getenv("A2DS_ZERO_AHEAD") ? atoi(getenv("A2DS_ZERO_AHEAD")) : 3;
+    const int n_gw = grid * wpb;
+    const int rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / n_gw));
+    p.zero_rounds = rounds;
+    p.zero_ahead = std::max(1, ahead);
+    p.zeroK = (double2 *)c->pz_K; p.zero_nK = c->pz_nK;
+    p.zeroG = (double2 *)c->pz_G; p.zero_nG = c->pz_nG;
+    const long long per_round = (long long)rounds * n_gw;
+    // whole blocks per chunk (18 double2 each)
+    p.zero_cK = 18 * (int)std::max<long long>(1, (c->pz_nK / 18 + per_round - 1) / per_round);
+    p.zero_cG = 18 * (int)std::max<long long>(1, (c->pz_nG / 18 + per_round - 1) / per_round);
+    // both matrices use the same round boundaries in blocks only when they have the same
+    // chunk; the kernel takes the larger round index of the two, so use the smaller chunk
+    {
+      const double bpr = (double)n_gw * (double)(std::min(p.zeroK ? p.zero_cK : p.zero_cG,
+                                                          p.zeroG ? p.zero_cG : p.zero_cK) / 18);
+      p.zero_inv_round = (float)(1.0 / bpr) * (1.0f + 1e-6f);
+    }
+    p.zero_done = c->work_counter + 1;
+    c->pz_K = c->pz_G = nullptr;
+  }
+  CU(cudaMemsetAsync(c->work_counter, 0, (1 + p.zero_rounds) * sizeof(int), c->stream));
+  if (p.zero_rounds > 0) {
+    // the zeroing protocol waits on every warp of the grid: all blocks must be co-resident
+    void *args[] = {(void *)&p};
+    CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(wpb * 32), args, smem, c->stream));
+  } else {
+    kern<<<grid, wpb * 32, smem, c->stream>>>(p);
+  }
   CU(cudaGetLastError());
   c->last_launches++;
   return 0;
@@ -1195,15 +1261,35 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   if (MM && check_mat(c, mmat)) return 1;
   if (KM && GM && kmat == gmat && what == 7)
     return fail("assemble: tangent and geometric matrices must differ");
+  c->pz_K = c->pz_G = nullptr;
   if (rq.zero) {
     c->last_launches = 0;
     CU(cudaEventRecord(c->ev0, c->stream));
     if (RES) CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)c->n_nodes * sizeof(double), c->stream));
-    if (KM) CU(cudaMemsetAsync(c->mats[kmat].A, 0, c->mats[kmat].total * 36 * sizeof(double), c->stream));
-    if (GM) CU(cudaMemsetAsync(c->mats[gmat].A, 0, c->mats[gmat].total * 36 * sizeof(double), c->stream));
+    // the tangent / geometric matrices are zeroed by the first element kernel itself when
+    // that is k_assemble_t in a single launch per class (atomic scatter); otherwise here
+    static const bool ikz_env = !(getenv("A2DS_INKERNEL_ZERO") && atoi(getenv("A2DS_INKERNEL_ZERO")) == 0);
+    static const bool first_form = getenv("A2DS_FORMULATION") && atoi(getenv("A2DS_FORMULATION")) == 0;
+    int first_cls = -1;
+    for (int cls = 0; cls < 4 && first_cls < 0; cls++)
+      if (c->list_len[cls][0] > 0) first_cls = cls;
+#ifndef A2DS_IKZ
+    const bool ikz_built = false;   // experimental, see assemble_kernels.cuh
+#else
+    const bool ikz_built = true;
+#endif
+    const bool ikz = ikz_built && ikz_env && !first_form && c->n_colors == 1 && (KM || GM) && first_cls >= 0 &&
+                     first_cls < 2 && (what == 2 || what == 3 || what == 4 || what == 7);
+    if (ikz) {
+      if (KM) { c->pz_K = c->mats[kmat].A; c->pz_nK = c->mats[kmat].total * 18; }
+      if (GM) { c->pz_G = c->mats[gmat].A; c->pz_nG = c->mats[gmat].total * 18; }
+    } else {
+      if (KM) CU(cudaMemsetAsync(c->mats[kmat].A, 0, c->mats[kmat].total * 36 * sizeof(double), c->stream));
+      if (GM) CU(cudaMemsetAsync(c->mats[gmat].A, 0, c->mats[gmat].total * 36 * sizeof(double), c->stream));
+    }
     if (MM && !(KM && mmat == kmat))
       CU(cudaMemsetAsync(c->mats[mmat].A, 0, c->mats[mmat].total * 36 * sizeof(double), c->stream));
-    c->last_launches += (RES ? 1 : 0) + (KM ? 1 : 0) + (GM ? 1 : 0) + (MM && !(KM && mmat == kmat) ? 1 : 0);
+    c->last_launches += (RES ? 1 : 0) + (ikz ? 0 : (KM ? 1 : 0) + (GM ? 1 : 0)) + (MM && !(KM && mmat == kmat) ? 1 : 0);
   }
 
   if (state_wait(c)) return 1;  // the upload overlapped the zeroing above
@@ -1366,6 +1452,8 @@ extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, doub
   A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("addJacobianVecProduct: mesh or nodes not set");
+  if (((uintptr_t)x_dev & 15) || ((uintptr_t)y_dev & 7))
+    return fail("addJacobianVecProduct: x must be 16-byte aligned (rows are fetched with 16-byte cp.async)");
   if (build_lists(c)) return 1;
   if (state_wait(c)) return 1;
   c->last_launches = 0;

@@ -41,6 +41,15 @@ struct KParams {
   double jvp_scale;
   int scratch_bytes;
   int *work_counter;     // dynamic batch scheduling: next batch index (zeroed per launch)
+  // in-kernel zeroing of the output matrices (k_assemble_t, cooperative launch): the value
+  // arrays are cut into zero_rounds rounds of one chunk per warp; see zero_round() there
+  double2 *zeroK, *zeroG;        // arrays to zero (null: none), lengths in double2 units
+  long long zero_nK, zero_nG;
+  int zero_cK, zero_cG;          // chunk of one warp in one round (double2 units, whole blocks)
+  float zero_inv_round;          // 1 / (blocks per round), rounded up
+  int zero_rounds;               // 0: the matrices were zeroed by the caller
+  int zero_ahead;                // rounds zeroed before the first batch
+  int *zero_done;                // per round: number of warps that have zeroed and fenced
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -193,7 +202,7 @@ __device__ __forceinline__ void add_geo_blocks(const ElemGeom &gm, const ElemWor
 static const int NB = A2DS_NB;
 static_assert(NB == 2 || NB == 4 || NB == 8,
               "one lane per (element, node): NB * 4 <= 32; the offset gather moves 32 entries per pass");
-struct RawBatch {          // gathered inputs of one batch, filled by cp.async
+struct alignas(16) RawBatch {   // gathered inputs of one batch, filled by cp.async
   double xq[NB][36];       // per element: X[12] then q[24]
   int koff[NB][16];
   int comp[NB];
@@ -223,6 +232,10 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -457,9 +470,12 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
 // blocks are added), so there is no second staging tile.  Components without
 // membrane-bending coupling only (run_assembly sends coupled ones to k_assemble).
 // =====================================================================================
-struct BatchTmp {   // inputs of the batched phases; overlaid on the staging tile E, which is
-  double X[12], q[24], dr[12], etn[4];   // only live inside the per-element loop
-};                  // 52 doubles = 4 (mod 16)
+#ifndef A2DS_MB_T
+#define A2DS_MB_T 2
+#endif
+struct BatchTmp {   // node-phase outputs only the Gauss-point phase reads; overlaid on the staging
+  double dr[12], etn[4], pad_[4];   // tile E, which is only live inside the per-element loop
+};                  // 20 doubles = 4 (mod 16)
 struct NodeView {   // what phase_node / qp_geometry address as one record
   double *X, *q, *fn, *dr, *wn, *cdr, *etn;
 };
@@ -478,11 +494,16 @@ struct WarpScratchT {
     BatchTmp tmp[NB];
   };
   TyWork work;
-  // ---- double-buffered gather (geometric stiffness / nonlinear variants) ----
-  RawBatch raw1;
-  int goff[2][NB][16];
+  RawBatch raw1;            // double buffer: batch i+1 lands (cp.async) while batch i is processed
+  alignas(16) int goff[2][NB][16];
 };
 static_assert(sizeof(BatchTmp) * NB <= sizeof(double) * 24 * KE_LD, "batch inputs overlay E");
+// block-shared part of the dynamic shared memory, in front of the per-warp scratch: the plans of
+// the 45 entries of H_tt (Gauss-point weights and slots; constant)
+struct BlockSharedT {
+  TyPlan plan[45];
+};
+static const int BLOCK_SHARED_T = (int)((sizeof(BlockSharedT) + 15) & ~size_t(15));
 
 // record view used by the per-lane functions of mitc4_tying.h (they address ElemRec members)
 struct RecView {
@@ -508,24 +529,159 @@ __device__ __forceinline__ void stage_tiles_g(double *E, const double (&acc)[6][
     }
 }
 
+// ---- zeroing of the output matrices inside k_assemble_t ------------------------------------
+// Instead of a memset in front of the kernel (5.2 GB written, evicted, and read back by the
+// first RED of every block), every warp zeroes ONE chunk per trip, a few rounds ahead of where
+// the element batches drawn at that time scatter: round r = chunk r of every warp = one
+// contiguous slice of the value arrays.  A warp publishes a round (fence + counter) after its
+// batched phases, when its own earlier REDs have long drained, and before it scatters a batch
+// it checks that the round its highest block offset falls into has been zeroed by ALL warps
+// (zero_done[r] == number of warps; rounds complete in order per warp).  A warp that has to
+// wait zeroes ahead instead of spinning idle, so the scheme cannot deadlock and degenerates to
+// "zero everything first" for element orders without locality.  All warps are co-resident
+// (cooperative launch).  Kept out of line: the hot loops must not pay registers for it.
+// one chunk (round r, warp gw) of one value array: c2 double2 from (r * n_gw + gw) * c2
+__device__ __forceinline__ void ikz_zero_chunk(double2 *zb, long long n2, int c2, int r, int gw,
+                                               int n_gw, int lane) {
+  if (!zb) return;
+  const long long s0 = ((long long)r * n_gw + gw) * c2;
+  const long long left = n2 - s0;
+  const int len = left < c2 ? (left > 0 ? (int)left : 0) : c2;
+  double2 *q = zb + s0;
+#pragma unroll 4
+  for (int i = lane; i < len; i += 32) q[i] = make_double2(0.0, 0.0);
+}
+__device__ __forceinline__ void ikz_publish(int *done, int from, int to, int lane) {
+  __threadfence();
+  __syncwarp();
+  if (lane == 0)
+    for (int r = from; r < to; r++) atomicAdd(&done[r], 1);
+}
+// cold paths, out of line: rounds [from, to) of this warp zeroed and published ...
+__device__ __noinline__ void ikz_rounds(double2 *zK, long long nK, int cK, double2 *zG, long long nG,
+                                        int cG, int *done, int from, int to, int gw, int n_gw,
+                                        int lane) {
+  for (int r = from; r < to; r++) {
+    ikz_zero_chunk(zK, nK, cK, r, gw, n_gw, lane);
+    ikz_zero_chunk(zG, nG, cG, r, gw, n_gw, lane);
+  }
+  ikz_publish(done, from, to, lane);
+}
+// ... and the wait for round rneed: zeroes further rounds of this warp instead of idling.
+// Returns the warp's new round count.
+__device__ __noinline__ int ikz_wait(double2 *zK, long long nK, int cK, double2 *zG, long long nG,
+                                     int cG, int *done, int rneed, int zr, int n_zr, int gw,
+                                     int n_gw, int lane) {
+  for (;;) {
+    int v = 0;
+    if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + rneed) : "memory");
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if (v >= n_gw) return zr;
+    if (zr < n_zr) {
+      ikz_zero_chunk(zK, nK, cK, zr, gw, n_gw, lane);
+      ikz_zero_chunk(zG, nG, cG, zr, gw, n_gw, lane);
+      ikz_publish(done, zr, zr + 1, lane);
+      zr++;
+    } else {
+      __nanosleep(256);
+    }
+  }
+}
+
+#ifndef A2DS_GEO_MMA
+#define A2DS_GEO_MMA 0   // measured: the MMA saves FP64 work but its pair -> lane map stages with more bank conflicts (profiles/README.md)
+#endif
+#ifndef A2DS_G_ORDER
+#define A2DS_G_ORDER 1
+#endif
+// The 64 geometric-stiffness blocks of an element, two per lane.  The bending scalars
+//   mq_qp(p, pp) = [a_p; b_p]^T [[0, Sigma], [Sigma, 0]] [a_pp; b_pp]       (8 x 8 per Gauss point)
+// are one m8n8k4 MMA per Gauss point: A = the coefficient 4-vectors of the 8 generalised nodes,
+// B = Sigma4 times them.  Lane (row = lane >> 2, j = lane & 3) ends up with the pairs
+// (p, pp) = (row, 2 j) and (row, 2 j + 1).
+// generalised node pair e (0, 1) of a lane in the geometric phase
+__device__ __forceinline__ void geo_pair(int lane, int e, int &pr, int &pc) {
+#if A2DS_GEO_MMA
+  pr = lane >> 2; pc = 2 * (lane & 3) + e;         // accumulator layout of the MMA
+#else
+  const int pair = lane + 32 * e; pr = pair >> 3; pc = pair & 7;
+#endif
+}
+template <class Rec>
+__device__ __forceinline__ void geo_blocks_mma(const Rec &gm, const TyWork &wk, int lane,
+                                               double blk[2][9]) {
+  const int row = lane >> 2, k = lane & 3;
+#if !A2DS_GEO_MMA
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    int pr, pc;
+    geo_pair(lane, e, pr, pc);
+    geo_block_t(gm, wk, pr, pc, blk[e]);
+  }
+  return;
+#endif
+  // ca / cb are adjacent [4][8][2] arrays: lane offsets once, the Gauss point is an immediate
+  const double *cab = &wk.ca[0][0][0];
+  const int offA = 64 * (k >> 1) + 2 * row + (k & 1);   // (k < 2 ? ca : cb)[.][row][k & 1]
+  const int offC = 64 * (1 - (k >> 1)) + 2 * row;       // (k < 2 ? cb : ca)[.][row][0..1]
+  const int sa = 2 * (k & 1), sb = 2 - (k & 1);         // (s3, s5) or (s5, s4) of (w s3, w s4, w s5)
+  double mq[4][2];
+#pragma unroll
+  for (int qp = 0; qp < 4; qp++) {
+    const double a = cab[offA + 16 * qp];
+    const double *sg = gm.qp[qp].sg;
+    const double b = sg[sa] * cab[offC + 16 * qp] + sg[sb] * cab[offC + 16 * qp + 1];
+    mq[qp][0] = mq[qp][1] = 0.0;
+    dmma884(mq[qp], a, b);
+  }
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const double m4[4] = {mq[0][e], mq[1][e], mq[2][e], mq[3][e]};
+    geo_block_from_mq(gm, wk, row, 2 * k + e, m4, blk[e]);
+  }
+}
+
 template <bool RES, bool KMAT, bool GMAT, bool NL>
-__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(const KParams p) {
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assemble_t(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpScratchT &ws = *reinterpret_cast<WarpScratchT *>(smem_raw + (size_t)warp * p.scratch_bytes);
+  BlockSharedT &bs = *reinterpret_cast<BlockSharedT *>(smem_raw);
+  WarpScratchT &ws = *reinterpret_cast<WarpScratchT *>(smem_raw + BLOCK_SHARED_T +
+                                                        (size_t)warp * p.scratch_bytes);
   TyWork &wk = ws.work;
-  const bool PF = (GMAT || NL);   // asynchronous prefetch of the next batch
   const unsigned FULL = 0xffffffffu;
   Want w;
   w.res = RES; w.kmat = KMAT; w.gmat = GMAT; w.nonlinear = NL; w.thermal = p.thermal;
   const bool need_state = GMAT || NL;
   const int n_groups = (p.n_list + NB - 1) / NB;
+  if (threadIdx.x < 45) ty_plan(threadIdx.x, bs.plan[threadIdx.x]);
+  __syncthreads();
+  // lane constants of the column phase: opaque, so that they stay in registers across the
+  // element loop instead of being recomputed per element
+  LaneConst lc;
+  lane_const(lane, lc);
+#ifndef A2DS_NO_OPAQUE
+  asm volatile("" : "+d"(lc.Nxi), "+d"(lc.Neta), "+d"(lc.N), "+d"(lc.Nq[0]), "+d"(lc.Nq[1]),
+                    "+d"(lc.Nq[2]), "+d"(lc.Nq[3]));
+#endif
 
-  // lane constants: the two entries of H_tt this lane builds per element; zero row of H
-  TyPlan pl0, pl1;
-  ty_plan(lane, pl0);
-  ty_plan(lane + 32 < 45 ? lane + 32 : 44, pl1);
+  // zero row / column of H
   if (lane < TY_LD) { wk.H[TY_LD * 9 + lane] = 0.0; wk.H[TY_LD * lane + 9] = 0.0; wk.sigt[lane] = 0.0; }
+
+  // in-kernel zeroing of the output matrices (see ikz_zero_round above)
+#ifdef A2DS_IKZ
+  const int n_zr = p.zero_rounds;
+#else
+  const int n_zr = 0;   // compiled out: the caller zeroes the matrices (see profiles/README.md)
+#endif
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp, n_gw = gridDim.x * (blockDim.x >> 5);
+  int zr = 0, zknown = -1;   // rounds zeroed AND published by this warp; highest round known complete
+  bool zpend = false;        // round zr is stored but not yet published
+  if (n_zr > 0) {
+    zr = min(n_zr, p.zero_ahead);
+    ikz_rounds(p.zeroK, p.zero_nK, p.zero_cK, p.zeroG, p.zero_nG, p.zero_cG, p.zero_done, 0, zr, gw,
+               n_gw, lane);
+  }
 
   auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
     const int j = (lane >> 2) & (NB - 1);
@@ -536,33 +692,23 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
       nd_out = __ldg(&p.conn[4 * e_out + (lane & 3)]);
     }
   };
+  // asynchronous gather of a batch: lane = (element j, node m) fetches its node's coordinates
+  // and state (the rows of X / u are 24 / 48 bytes) and a quarter of the element's offsets
   auto issue_gather = [&](RawBatch &rb, int (*goffb)[16], int e_l, int nd_l) {
-#pragma unroll
-    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
-      const int sidx = lane + 32 * r;
-      const int j = sidx / 36, k = sidx - 36 * j;
-      const bool isx = k < 12;
-      const int node = isx ? k / 3 : (k - 12) / 6;
-      const int comp_k = isx ? k - 3 * node : (k - 12) - 6 * node;
-      const int src_lane = (4 * j + node) & 31;
-      const int nd = __shfl_sync(FULL, nd_l, src_lane);
-      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
-      if (sidx < NB * 36 && ej >= 0) {
-        const double *src = isx ? &p.X[3 * (size_t)nd + comp_k] : &p.u[6 * (size_t)nd + comp_k];
-        cp_async8(&rb.xq[j][k], src);
-      }
+    if (lane < 4 * NB && e_l >= 0) {
+      const int j = lane >> 2, m = lane & 3;
+      const double *xs = &p.X[3 * (size_t)nd_l];
+      cp_async8(&rb.xq[j][3 * m], xs);
+      cp_async8(&rb.xq[j][3 * m + 1], xs + 1);
+      cp_async8(&rb.xq[j][3 * m + 2], xs + 2);
+      const double *us = &p.u[6 * (size_t)nd_l];
+      cp_async16(&rb.xq[j][12 + 6 * m], us);
+      cp_async16(&rb.xq[j][12 + 6 * m + 2], us + 2);
+      cp_async16(&rb.xq[j][12 + 6 * m + 4], us + 4);
+      if (KMAT && p.Koff) cp_async16(&rb.koff[j][4 * m], &p.Koff[16 * (size_t)e_l + 4 * m]);
+      if (GMAT) cp_async16(&goffb[j][4 * m], &p.Goff[16 * (size_t)e_l + 4 * m]);
+      if (m == 0) cp_async4(&rb.comp[j], &p.elem_comp[e_l]);
     }
-#pragma unroll
-    for (int r = 0; r < NB * 16 / 32; r++) {
-      const int sidx = lane + 32 * r;
-      const int j = sidx >> 4, k = sidx & 15;
-      const int ej = __shfl_sync(FULL, e_l, (4 * j) & 31);
-      if (ej >= 0) {
-        if (KMAT && p.Koff) cp_async4(&rb.koff[j][k], &p.Koff[16 * (size_t)ej + k]);
-        if (GMAT) cp_async4(&goffb[j][k], &p.Goff[16 * (size_t)ej + k]);
-      }
-    }
-    if ((lane & 3) == 0 && lane < 4 * NB && e_l >= 0) cp_async4(&rb.comp[lane >> 2], &p.elem_comp[e_l]);
   };
   auto next_group = [&]() {
     int g = 0;
@@ -570,41 +716,34 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
     return __shfl_sync(FULL, g, 0);
   };
   int grp = next_group();
-  int grp_nxt = PF ? next_group() : 0;
+  int grp_nxt = next_group();
   int buf = 0;
   int e_cur, nd_cur;
   batch_ids(grp, e_cur, nd_cur);
-  if (PF && grp < n_groups) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
+  if (grp < n_groups) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
   for (; grp < n_groups; buf ^= 1) {
     int drawn = 0;
     if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
     const int base = grp * NB;
     const int cnt = min(NB, p.n_list - base);
     int e_nxt = -1, nd_nxt = 0;
-    if (PF) batch_ids(grp_nxt, e_nxt, nd_nxt);
-
-    if (!PF) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
+    batch_ids(grp_nxt, e_nxt, nd_nxt);
+    if (zr < n_zr) {   // stores only: published after the batched phases
+      ikz_zero_chunk(p.zeroK, p.zero_nK, p.zero_cK, zr, gw, n_gw, lane);
+      ikz_zero_chunk(p.zeroG, p.zero_nG, p.zero_cG, zr, gw, n_gw, lane);
+      zpend = true;
+    }
     cp_async_wait_all();
     __syncwarp();
-    const RawBatch &rb = (PF && buf) ? ws.raw1 : ws.raw0;
-    const int (*goffb)[16] = ws.goff[(PF && buf) ? 1 : 0];
+    const RawBatch &rb = buf ? ws.raw1 : ws.raw0;
+    const int (*goffb)[16] = ws.goff[buf];
     if (lane < 4 * NB) ws.nodes[lane >> 2][lane & 3] = nd_cur;
-#pragma unroll
-    for (int r = 0; r < (NB * 36 + 31) / 32; r++) {
-      const int sidx = lane + 32 * r;
-      const int j = sidx / 36, k = sidx - 36 * j;
-      if (sidx < NB * 36) {
-        const double v = rb.xq[j][k];
-        if (k < 12) ws.tmp[j].X[k] = v; else ws.tmp[j].q[k - 12] = v;
-      }
-    }
-    __syncwarp();
-
     // ---- batched phases: lane = (element of the batch, node | Gauss point) ----------------
     const int jb = (lane >> 2) & (NB - 1);
     const bool act = lane < 4 * NB && jb < cnt;
     NodeView nv;
-    nv.X = ws.tmp[jb].X; nv.q = ws.tmp[jb].q; nv.dr = ws.tmp[jb].dr; nv.etn = ws.tmp[jb].etn;
+    nv.X = const_cast<double *>(&rb.xq[jb][0]); nv.q = const_cast<double *>(&rb.xq[jb][12]);
+    nv.dr = ws.tmp[jb].dr; nv.etn = ws.tmp[jb].etn;
     nv.fn = ws.rec[jb].fn; nv.wn = ws.rec[jb].wn; nv.cdr = ws.rec[jb].cdr;
     if (act) phase_node(p.comps[rb.comp[jb]], nv, lane & 3);
     __syncwarp();
@@ -615,10 +754,32 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
       if (need_state) node_tab(rc.t1[m], nv.q, 6, nv.dr, &nv.fn[3 * m], m);
       phase_qp_t(p.comps[rb.comp[jb]], nv, rc.qp[lane & 3], lane & 3, w);
     }
-    if (PF && grp_nxt < n_groups)
-      issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ? 0 : 1], e_nxt, nd_nxt);
-    if (PF) { e_cur = e_nxt; nd_cur = nd_nxt; }
+    if (grp_nxt < n_groups)
+      issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ^ 1], e_nxt, nd_nxt);
+    e_cur = e_nxt; nd_cur = nd_nxt;
     __syncwarp();
+    if (n_zr > 0) {
+      if (zpend) { ikz_publish(p.zero_done, zr, zr + 1, lane); zr++; zpend = false; }
+      // the round that must be complete before this batch scatters, from its highest block
+      // offset (rounded up: one round early costs nothing, one round late is a race)
+      int mx = 0;
+#pragma unroll
+      for (int r = 0; r < NB * 16 / 32; r++) {
+        const int sidx = lane + 32 * r, j = sidx >> 4, k = sidx & 15;
+        if (j < cnt) {
+          if (KMAT && p.zeroK) mx = max(mx, rb.koff[j][k]);
+          if (GMAT && p.zeroG) mx = max(mx, goffb[j][k]);
+        }
+      }
+      int rneed = min(n_zr - 1, (int)((float)mx * p.zero_inv_round) + 1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rneed = max(rneed, __shfl_xor_sync(FULL, rneed, o));
+      if (rneed > zknown) {
+        zr = ikz_wait(p.zeroK, p.zero_nK, p.zero_cK, p.zeroG, p.zero_nG, p.zero_cG, p.zero_done, rneed,
+                      zr, n_zr, gw, n_gw, lane);
+        zknown = rneed;
+      }
+    }
 
 #pragma unroll 1
     for (int j = 0; j < cnt; j++) {
@@ -627,8 +788,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
       gm.fn = rc.fn; gm.wn = rc.wn; gm.cdr = rc.cdr; gm.t0 = rc.t0; gm.t1 = rc.t1; gm.qp = rc.qp;
       // ---- element prologue: H_tt (45 entries over 32 lanes) and the tying stresses --------
       if (KMAT || GMAT) {
-        ty_H_entry(gm, pl0, wk.H);
-        if (lane + 32 < 45) ty_H_entry(gm, pl1, wk.H);
+        ty_H_entry(gm, bs.plan[lane], wk.H);
+        if (lane + 32 < 45) ty_H_entry(gm, bs.plan[lane + 32], wk.H);
       }
       if ((RES || need_state) && lane < 9) ty_sum_stress(gm, wk, lane);
       __syncwarp();
@@ -636,7 +797,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
       // ---- column phase: the lane's rows of Bt, W = H Bt (and Bt1) ARE the DMMA fragments ----
       LaneFrag f;
       double B1[6][3];
-      lane_fragments(gm, wk, lane, w, f, B1);
+      lane_fragments(gm, wk, lane, lc, w, f, B1);
       if (RES) {
         double r3[3];
         lane_residual(gm, wk, lane, f, r3);
@@ -674,29 +835,39 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
         for (int t = 0; t < 6; t++) gacc[t][0] = gacc[t][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 6; ks++) {
+          // all six B1^T W products first, then the three W^T B1 of the off-diagonal tiles:
+          // no MMA waits on the accumulator of the one issued just before it
           int idx = 0;
 #pragma unroll
           for (int ti = 0; ti < 3; ti++)
 #pragma unroll
             for (int tj = ti; tj < 3; tj++, idx++) {
               dmma884(gacc[idx], B1[ks][ti], f.W[ks][tj]);
+#if !A2DS_G_ORDER
               if (ti != tj) dmma884(gacc[idx], f.W[ks][ti], B1[ks][tj]);
+#endif
             }
+#if A2DS_G_ORDER
+          dmma884(gacc[1], f.W[ks][0], B1[ks][1]);
+          dmma884(gacc[2], f.W[ks][0], B1[ks][2]);
+          dmma884(gacc[4], f.W[ks][1], B1[ks][2]);
+#endif
         }
       }
       __syncwarp();   // E staged; coefficient pairs of the geometric phase published
       if (KMAT) {
         if (NL) {
+          double blk[2][9];
+          geo_blocks_mma(gm, wk, lane, blk);
 #pragma unroll
-          for (int pass = 0; pass < 2; pass++) {
-            const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
-            double blk[9];
-            geo_block_t(gm, wk, pr, pc, blk);
+          for (int e = 0; e < 2; e++) {
+            int pr, pc;
+            geo_pair(lane, e, pr, pc);
             const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
-              for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] += p.alpha * blk[3 * i + jj];
+              for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] += p.alpha * blk[e][3 * i + jj];
           }
           __syncwarp();
         }
@@ -720,11 +891,11 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
         stage_tiles_g(ws.E, gacc, lane);
         __syncwarp();
         double v[2][9];
+        geo_blocks_mma(gm, wk, lane, v);
 #pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-          const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
-          double blk[9];
-          geo_block_t(gm, wk, pr, pc, blk);
+        for (int e = 0; e < 2; e++) {
+          int pr, pc;
+          geo_pair(lane, e, pr, pc);
           const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
 #pragma unroll
           for (int i = 0; i < 3; i++)
@@ -732,18 +903,19 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
             for (int jj = 0; jj < 3; jj++) {
               double z = ws.E[(r0 + i) * KE_LD + c0 + jj];
               if (i == jj) z += ws.E[(c0 + jj) * KE_LD + r0 + i];   // diagonal tiles: Z + Z^T
-              v[pass][3 * i + jj] = p.gscale * (blk[3 * i + jj] + z);
+              v[e][3 * i + jj] = p.gscale * (v[e][3 * i + jj] + z);
             }
         }
         __syncwarp();
 #pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-          const int pair = lane + 32 * pass, pr = pair >> 3, pc = pair & 7;
+        for (int e = 0; e < 2; e++) {
+          int pr, pc;
+          geo_pair(lane, e, pr, pc);
           const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] = v[pass][3 * i + jj];
+            for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] = v[e][3 * i + jj];
         }
         __syncwarp();
         scatter_matrix(ws.E, p.Gval, goffb[j][lane & 15], lane);
@@ -751,9 +923,12 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 2) k_assemble_t(cons
       __syncwarp();
     }
     drawn = __shfl_sync(FULL, drawn, 0);
-    if (PF) { grp = grp_nxt; grp_nxt = drawn; }
-    else { grp = drawn; batch_ids(grp, e_cur, nd_cur); }
+    grp = grp_nxt; grp_nxt = drawn;
   }
+  // rounds this warp has not reached yet (short lists, warps without a batch)
+  if (n_zr > 0 && zr < n_zr)
+    ikz_rounds(p.zeroK, p.zero_nK, p.zero_cK, p.zeroG, p.zero_nG, p.zero_cG, p.zero_done, zr, n_zr, gw,
+               n_gw, lane);
 }
 
 // ---- mass path (gamma terms of assembleJacobian, TACS_MASS_MATRIX, inertial residual) ----

@@ -239,17 +239,36 @@ A2DS_HD void ty_sum_stress(const Rec &s, TyWork &wk, int t) {
 // ---- column phase: lane = (kk = lane & 3, m, h) -------------------------------------
 // The lane's three columns (DOFs 6 m + 3 h + 0..2) of the generalised rows k = 4 s + kk.
 
+// Lane constants of the column phase (lane = (kk, m, h)): kept in registers across the
+// element loop (made opaque to the compiler in the kernel so that they are not recomputed
+// per element)
+struct LaneConst {
+  double Nxi, Neta, N;  // N_m,xi  N_m,eta  N_m at Gauss point kk
+  double Nq[4];         // N_n(kk), n = 0..3; 0 for the node diagonally opposite to m
+};
+A2DS_HD void lane_const(int lane, LaneConst &lc) {
+  const int kk = lane_qp(lane), m = lane_m(lane);
+  double na[2], nb[2];
+  qp_shape(kk, na, nb);
+  const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
+  const double nam = (m % 2) ? na[1] : na[0], nbm = (m / 2) ? nb[1] : nb[0];
+  lc.Nxi = dN * nbm; lc.Neta = nam * dM; lc.N = nam * nbm;
+  for (int n = 0; n < 4; n++) lc.Nq[n] = ((m ^ n) == 3) ? 0.0 : na[n % 2] * nb[n / 2];
+}
+
 // non-zero tying rows of the lane's columns (g11, g13, g22, g23, g12) and its own slots s = 3,4,5
-A2DS_HD void lane_tying(const NodeTab &t, int m, int h, int kk, double Gnz[5][3],
-                        double R[3][3]) {
+// zero10: ten zeros (the rotation columns have no g11 / g22 / g12 rows)
+A2DS_HD void lane_tying(const NodeTab &t, const double *zero10, int m, int h, int kk,
+                        double Gnz[5][3], double R[3][3]) {
   const int x = m / 2, y = m % 2;
+  const double *gm = h ? zero10 : t.gm;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    Gnz[0][k] = h ? 0.0 : t.gm[k];
+    Gnz[0][k] = gm[k];
     Gnz[1][k] = t.gs[h][k];
-    Gnz[2][k] = h ? 0.0 : t.gm[3 + k];
+    Gnz[2][k] = gm[3 + k];
     Gnz[3][k] = t.gs[h][3 + k];
-    Gnz[4][k] = h ? 0.0 : t.gm[6 + k];
+    Gnz[4][k] = gm[6 + k];
   }
   // slot kk of s = 3, 4 is a tying point on the eta edge kk (kk < 2) / the xi edge kk - 2
   const bool on = kk < 2 ? (x == kk) : (y == kk - 2);
@@ -276,11 +295,8 @@ A2DS_HD void lane_w_tying(const double *H, int m, int kk, const double Gnz[5][3]
   }
 }
 
-A2DS_HD void node_coef_t(const QpRec &g, const double na[2], const double nb[2], int m,
-                         NodeCoef &n) {
-  const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
-  const double nam = (m % 2) ? na[1] : na[0], nbm = (m / 2) ? nb[1] : nb[0];
-  const double Nxi = dN * nbm, Neta = nam * dM, N = nam * nbm;
+A2DS_HD void node_coef_t(const QpRec &g, const LaneConst &lc, NodeCoef &n) {
+  const double Nxi = lc.Nxi, Neta = lc.Neta, N = lc.N;
 #pragma unroll
   for (int j = 0; j < 2; j++) {
     n.a[j] = Nxi * g.S[j] + Neta * g.S[2 + j];
@@ -292,8 +308,8 @@ A2DS_HD void node_coef_t(const QpRec &g, const double na[2], const double nb[2],
 
 // bending rows (e3, e4, e5 at Gauss point kk) of B0 and the drilling row
 template <class Rec>
-A2DS_HD void lane_bend0(const Rec &s, int m, int h, int qp, const double na[2],
-                        const double nb[2], const NodeCoef &nc, double R[3][3], double Rd[3]) {
+A2DS_HD void lane_bend0(const Rec &s, int m, int h, int qp, const LaneConst &lc,
+                        const NodeCoef &nc, double R[3][3], double Rd[3]) {
   const QpRec &g = s.qp[qp];
   const double *fn = &s.fn[3 * m];
   const double cz0 = h ? nc.cc[0] : nc.az[0], cz1 = h ? nc.cc[1] : nc.az[1];
@@ -309,19 +325,16 @@ A2DS_HD void lane_bend0(const Rec &s, int m, int h, int qp, const double na[2],
   }
   // drilling strain row: et(qp) = sum_n N_n etn_n,
   // etn_n = 1/2 (u0x[1][0] - u0x[0][1]) - theta_n . (t0n x t1n)   (TACSDirector.h:560-564)
-  const double nas = (m % 2) ? na[1] : na[0], nbs = (m / 2) ? nb[1] : nb[0];
   double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int n = 0; n < 4; n++) {
-    const int slot = m ^ n;  // 3: diagonally opposite node, no contribution
-    const double Nq = (slot == 3) ? 0.0 : na[n % 2] * nb[n / 2];
+    const int slot = m ^ n;  // 3: diagonally opposite node, no contribution (Nq = 0)
     const double *cd = &s.cdr[9 * n + 3 * (slot & ~(slot >> 1))];
 #pragma unroll
-    for (int k = 0; k < 3; k++) acc[k] += Nq * cd[k];
+    for (int k = 0; k < 3; k++) acc[k] += lc.Nq[n] * cd[k];
   }
-  const double Nq = nas * nbs;
 #pragma unroll
-  for (int k = 0; k < 3; k++) Rd[k] = h ? -Nq * s.wn[3 * m + k] : acc[k];
+  for (int k = 0; k < 3; k++) Rd[k] = h ? -lc.N * s.wn[3 * m + k] : acc[k];
 }
 
 // bending rows of B1(q); publishes the coefficient pairs of the geometric phase
@@ -359,20 +372,19 @@ struct LaneFrag {
 };
 
 template <class Rec>
-A2DS_HD void lane_fragments(const Rec &s, TyWork &wk, int lane, const Want &w, LaneFrag &f,
-                            double B1[6][3]) {
+A2DS_HD void lane_fragments(const Rec &s, TyWork &wk, int lane, const LaneConst &lc, const Want &w,
+                            LaneFrag &f, double B1[6][3]) {
   const int kk = lane_qp(lane), m = lane_m(lane), h = lane_h(lane);
-  double na[2], nb[2];
-  qp_shape(kk, na, nb);
+  const double *zero10 = &wk.H[TY_LD * 9];
   NodeCoef nc;
-  node_coef_t(s.qp[kk], na, nb, m, nc);
+  node_coef_t(s.qp[kk], lc, nc);
   double Gnz[5][3];
-  lane_bend0(s, m, h, kk, na, nb, nc, &f.B[0], f.B[6]);
-  lane_tying(s.t0[m], m, h, kk, Gnz, &f.B[3]);
+  lane_bend0(s, m, h, kk, lc, nc, &f.B[0], f.B[6]);
+  lane_tying(s.t0[m], zero10, m, h, kk, Gnz, &f.B[3]);
   if (w.gmat || w.nonlinear) {
     double G1[5][3];
     lane_bend1(s, wk, m, h, kk, nc, &B1[0]);
-    lane_tying(s.t1[m], m, h, kk, G1, &B1[3]);
+    lane_tying(s.t1[m], zero10, m, h, kk, G1, &B1[3]);
     if (w.nonlinear) {
 #pragma unroll
       for (int r = 0; r < 6; r++)
@@ -414,10 +426,12 @@ A2DS_HD void lane_residual(const Rec &s, const TyWork &wk, int lane, const LaneF
 }
 
 // ---- geometric stiffness: one 3x3 block for the generalised node pair (p, pp) -----------
-// as geo_block (mitc4_math.h) on the records of this formulation
-template <class Rec>
-A2DS_HD void geo_block_t(const Rec &gm, const TyWork &s, int p, int pp, double out[9]) {
-  const double *sig = s.sigt;
+// p, pp in 0..7: 0..3 displacement of node p, 4..7 director of node p - 4 (as geo_block in
+// mitc4_math.h, on the records of this formulation).  Three pieces:
+//   geo_tying_scalar: the scalar on the identity from the tying-point stresses
+//   geo_bending_mq:   per Gauss point, the scalar multiplying T T^T (bending stresses)
+//   geo_fold:         rows / columns of director nodes folded onto the rotations
+A2DS_HD double geo_tying_scalar(const double *sig, int p, int pp) {
   const int m = p & 3, mm = pp & 3;
   const bool pd = p >= 4, ppd = pp >= 4;
   const double dN = (m % 2) ? 0.5 : -0.5, dM = (m / 2) ? 0.5 : -0.5;
@@ -433,20 +447,19 @@ A2DS_HD void geo_block_t(const Rec &gm, const TyWork &s, int p, int pp, double o
     if (md % 2 == mu % 2) sc += sig[5 + 2 * (md % 2)] * 0.5 * 0.5 * dMu;  // g23
     if (md / 2 == mu / 2) sc += sig[1 + 2 * (md / 2)] * 0.5 * 0.5 * dNu;  // g13
   }
-  double blk[9] = {sc, 0.0, 0.0, 0.0, sc, 0.0, 0.0, 0.0, sc};
-#pragma unroll
-  for (int qp = 0; qp < 4; qp++) {
-    const double *ap = s.ca[qp][p], *bp = s.cb[qp][p], *app = s.ca[qp][pp], *bpp = s.cb[qp][pp];
-    const double s3 = gm.qp[qp].sg[0], s4 = gm.qp[qp].sg[1], s5 = gm.qp[qp].sg[2];
-    const double mq = ap[0] * (s3 * bpp[0] + s5 * bpp[1]) + ap[1] * (s5 * bpp[0] + s4 * bpp[1]) +
-                      bp[0] * (s3 * app[0] + s5 * app[1]) + bp[1] * (s5 * app[0] + s4 * app[1]);
-    const double *P = gm.qp[qp].Pq;
-    blk[0] += mq * P[0]; blk[1] += mq * P[1]; blk[2] += mq * P[2];
-    blk[3] += mq * P[1]; blk[4] += mq * P[3]; blk[5] += mq * P[4];
-    blk[6] += mq * P[2]; blk[7] += mq * P[4]; blk[8] += mq * P[5];
-  }
-  if (pd) {  // rows: skew(fn_m) * blk
-    const double *f = &gm.fn[3 * m];
+  return sc;
+}
+// mq = alpha_p^T Sigma beta_pp + beta_p^T Sigma alpha_pp, Sigma = [[s3, s5], [s5, s4]]
+A2DS_HD double geo_bending_mq(const double *ap, const double *bp, const double *app,
+                              const double *bpp, const double *sg) {
+  const double s3 = sg[0], s4 = sg[1], s5 = sg[2];
+  return ap[0] * (s3 * bpp[0] + s5 * bpp[1]) + ap[1] * (s5 * bpp[0] + s4 * bpp[1]) +
+         bp[0] * (s3 * app[0] + s5 * app[1]) + bp[1] * (s5 * app[0] + s4 * app[1]);
+}
+A2DS_HD void geo_fold(const double *fn12, int p, int pp, double blk[9]) {
+  const int m = p & 3, mm = pp & 3;
+  if (p >= 4) {  // rows: skew(fn_m) * blk
+    const double *f = &fn12[3 * m];
     double t[9];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -457,8 +470,8 @@ A2DS_HD void geo_block_t(const Rec &gm, const TyWork &s, int p, int pp, double o
 #pragma unroll
     for (int i = 0; i < 9; i++) blk[i] = t[i];
   }
-  if (ppd) {  // columns: blk * skew(fn_mm)^T
-    const double *f = &gm.fn[3 * mm];
+  if (pp >= 4) {  // columns: blk * skew(fn_mm)^T
+    const double *f = &fn12[3 * mm];
     double t[9];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -470,8 +483,31 @@ A2DS_HD void geo_block_t(const Rec &gm, const TyWork &s, int p, int pp, double o
 #pragma unroll
     for (int i = 0; i < 9; i++) blk[i] = t[i];
   }
+}
+// block from the four bending scalars mq[qp] (however they were formed)
+template <class Rec>
+A2DS_HD void geo_block_from_mq(const Rec &gm, const TyWork &s, int p, int pp, const double mq[4],
+                               double out[9]) {
+  const double sc = geo_tying_scalar(s.sigt, p, pp);
+  double blk[9] = {sc, 0.0, 0.0, 0.0, sc, 0.0, 0.0, 0.0, sc};
+#pragma unroll
+  for (int qp = 0; qp < 4; qp++) {
+    const double *P = gm.qp[qp].Pq;
+    blk[0] += mq[qp] * P[0]; blk[1] += mq[qp] * P[1]; blk[2] += mq[qp] * P[2];
+    blk[3] += mq[qp] * P[1]; blk[4] += mq[qp] * P[3]; blk[5] += mq[qp] * P[4];
+    blk[6] += mq[qp] * P[2]; blk[7] += mq[qp] * P[4]; blk[8] += mq[qp] * P[5];
+  }
+  geo_fold(gm.fn, p, pp, blk);
 #pragma unroll
   for (int i = 0; i < 9; i++) out[i] = blk[i];
+}
+template <class Rec>
+A2DS_HD void geo_block_t(const Rec &gm, const TyWork &s, int p, int pp, double out[9]) {
+  double mq[4];
+#pragma unroll
+  for (int qp = 0; qp < 4; qp++)
+    mq[qp] = geo_bending_mq(s.ca[qp][p], s.cb[qp][p], s.ca[qp][pp], s.cb[qp][pp], gm.qp[qp].sg);
+  geo_block_from_mq(gm, s, p, pp, mq, out);
 }
 
 }  // namespace a2ds

@@ -181,7 +181,9 @@ extern "C" int emul_element_t(const double *Cs, const double *eth, double temper
   memset(B1, 0, sizeof(B1));
   memset(res, 0, 24 * sizeof(double));
   for (int lane = 0; lane < 32; lane++) {
-    lane_fragments(s, wk, lane, w, f[lane], B1[lane]);
+    LaneConst lc;
+    lane_const(lane, lc);
+    lane_fragments(s, wk, lane, lc, w, f[lane], B1[lane]);
     double r3[3];
     lane_residual(s, wk, lane, f[lane], r3);
     const int col = 6 * lane_m(lane) + 3 * lane_h(lane);
