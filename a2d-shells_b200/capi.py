@@ -23,7 +23,7 @@ SYMBOLS = [
     "a2ds_set_mesh", "a2ds_set_nodes", "a2ds_set_components", "a2ds_set_state",
     "a2ds_set_state_dev", "a2ds_set_bcs", "a2ds_set_scatter_mode", "a2ds_mat_create",
     "a2ds_mat_create_natural", "a2ds_mat_pattern", "a2ds_mat_nnz", "a2ds_mat_zero",
-    "a2ds_mat_download", "a2ds_mat_values_dev", "a2ds_assemble_res", "a2ds_assemble_jacobian",
+    "a2ds_mat_download", "a2ds_mat_values_dev", "a2ds_mat_download_rows", "a2ds_assemble_res", "a2ds_assemble_jacobian",
     "a2ds_assemble_mat_type", "a2ds_assemble_all", "a2ds_res_dev", "a2ds_state_dev",
     "a2ds_comm_unique_id", "a2ds_comm_init", "a2ds_set_halo", "a2ds_halo_forward",
     "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
@@ -464,6 +464,16 @@ class Assembler:
         A = np.empty((n, 6, 6)) if out is None else out
         self._chk(self.L.a2ds_mat_download(self.ctx, C.c_int(mat), C.c_int(block), _p(A)))
         return A
+
+    def mat_rows(self, mat, rows, rowp, block=0):
+        """values of the listed block rows: list of arrays [nnz_row, 6, 6] (rowp: the block's
+        row pointer, e.g. from mat_pattern)"""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cnt = (rowp[rows + 1] - rowp[rows]).astype(np.int64)
+        A = np.empty((int(cnt.sum()), 6, 6))
+        self._chk(self.L.a2ds_mat_download_rows(self.ctx, C.c_int(mat), C.c_int(block),
+                                                C.c_int(len(rows)), _p(rows), _p(A)))
+        return np.split(A, np.cumsum(cnt)[:-1])
 
     def mat_values_dev(self, mat, block=0):
         p = C.c_void_p()

@@ -77,6 +77,7 @@ extern "C" const char *a2ds_version(void) { return "a2ds-b200 0.1 (sm_100a)"; }
 // host side
 // ---------------------------------------------------------------------------
 struct MatrixRec {
+  bool dead = false;   // its mesh was replaced: device memory freed, id kept invalid
   int n_blocks = 0;
   std::vector<long long> nnz, base;
   std::vector<int> nrows;
@@ -116,6 +117,10 @@ struct a2ds_ctx {
   std::vector<double> h_mom;          // mass moments per component (a2ds_set_mass_moments)
   std::vector<CompData> h_comps;
   double *X = nullptr, *u = nullptr, *res = nullptr;
+  // persistent device scratch of the host-pointer variants (mat-vec, matrix-free product):
+  // two vectors, grown on demand, so that a Krylov loop does not allocate per call
+  double *scratch_x = nullptr, *scratch_y = nullptr;
+  size_t scratch_nx = 0, scratch_ny = 0;
   int *work_counter = nullptr;   // [0] batch counter, [1..] zero_done rounds; zeroed before every k_assemble launch
   // matrices the next k_assemble_t launch has to zero itself (in-kernel zeroing)
   double *pz_K = nullptr, *pz_G = nullptr;
@@ -228,6 +233,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   free_lists(c);
   cudaFree(c->conn); cudaFree(c->elem_comp); cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
   cudaFree(c->udd);
+  cudaFree(c->scratch_x); cudaFree(c->scratch_y);
   cudaFree(c->comps); cudaFree(c->bc_nodes); cudaFree(c->bc_vars); cudaFree(c->bc_vals);
   cudaFree(c->send_nodes); cudaFree(c->recv_nodes); cudaFree(c->send_buf); cudaFree(c->recv_buf);
   if (c->comm) ncclCommDestroy(c->comm);
@@ -259,6 +265,20 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
     if (conn[i] < 0 || conn[i] >= n_nodes)
       return fail("a2ds_set_mesh: connectivity refers to a node outside [0, n_nodes) "
                   "(dependent nodes are not supported)");
+  if (c->mesh_set) {
+    // a second mesh on the same context: nothing sized for the old one may survive — the
+    // matrices (offset tables of 16 * old n_elems), the halo lists and the BC arrays
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto &m : c->mats) {
+      for (void *p : m.owned) cudaFree(p);
+      m.owned.clear();
+      m.A = nullptr; m.off = nullptr; m.blk_dev = nullptr; m.has_halo = false;
+      m.dead = true;
+    }
+    c->has_halo = false;
+    c->peers.clear(); c->send_ptr.clear(); c->recv_ptr.clear();
+    c->n_bc = 0;
+  }
   c->n_nodes = n_nodes; c->n_owned = n_owned; c->n_elems = n_elems;
   c->h_conn.assign(conn, conn + 4 * (size_t)n_elems);
   c->nat_ready = false;
@@ -458,17 +478,22 @@ static void color_elements(int nn, int ne, const int *conn, std::vector<int> &co
     for (int i = 0; i < 4; i++) adj[fill[conn[4 * e + i]]++] = e;
   color.assign(ne, -1);
   n_colors = 0;
+  // mark[col] == e: colour col is taken by a neighbour of element e (any number of colours:
+  // high-valence fan / junction nodes can need more than a machine word of them)
+  std::vector<int> mark;
   for (int e = 0; e < ne; e++) {
-    unsigned long long used = 0ull;
     for (int i = 0; i < 4; i++) {
       const int n = conn[4 * e + i];
       for (int k = ptr[n]; k < ptr[n + 1]; k++) {
         const int o = adj[k];
-        if (color[o] >= 0 && color[o] < 64) used |= 1ull << color[o];
+        if (color[o] >= 0) {
+          if (color[o] >= (int)mark.size()) mark.resize(color[o] + 1, -1);
+          mark[color[o]] = e;
+        }
       }
     }
     int col = 0;
-    while (used & (1ull << col)) col++;
+    while (col < (int)mark.size() && mark[col] == e) col++;
     color[e] = col;
     n_colors = std::max(n_colors, col + 1);
   }
@@ -529,6 +554,21 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   m.n_blocks = n_blocks;
   std::vector<BlockDev> hb(n_blocks);
   long long total = 0;
+  // the patterns come from the caller: every index the kernels will follow is checked here
+  for (int b = 0; b < n_blocks; b++) {
+    if (nrows[b] < 0) return fail("a2ds_mat_create: negative row count");
+    if (nrows[b] > 0) {
+      if (!rowp[b] || rowp[b][0] != 0) return fail("a2ds_mat_create: rowp must start at 0");
+      for (int r = 0; r < nrows[b]; r++)
+        if (rowp[b][r + 1] < rowp[b][r]) return fail("a2ds_mat_create: rowp is not monotone");
+      if (rowp[b][nrows[b]] > 0 && !cols[b]) return fail("a2ds_mat_create: cols missing");
+      for (int k = 0; k < rowp[b][nrows[b]]; k++)
+        if (cols[b][k] < 0) return fail("a2ds_mat_create: negative column index");
+    }
+    if (row_map && row_map[b])
+      for (int n = 0; n < c->n_nodes; n++)
+        if (row_map[b][n] >= nrows[b]) return fail("a2ds_mat_create: row_map entry beyond the block's rows");
+  }
   for (int b = 0; b < n_blocks; b++) {
     const long long nnz = nrows[b] > 0 ? rowp[b][nrows[b]] : 0;
     m.nnz.push_back(nnz); m.base.push_back(total); m.nrows.push_back(nrows[b]);
@@ -588,8 +628,24 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   A2DS_CATCH(a2ds_mat_create)
 }
 
+static int scratch_vectors(a2ds_ctx *c, size_t nx, size_t ny, double **dx, double **dy) {
+  if (nx > c->scratch_nx) {
+    cudaFree(c->scratch_x); c->scratch_x = nullptr; c->scratch_nx = 0;
+    CU(cudaMalloc((void **)&c->scratch_x, std::max<size_t>(nx, 1) * sizeof(double)));
+    c->scratch_nx = nx;
+  }
+  if (ny > c->scratch_ny) {
+    cudaFree(c->scratch_y); c->scratch_y = nullptr; c->scratch_ny = 0;
+    CU(cudaMalloc((void **)&c->scratch_y, std::max<size_t>(ny, 1) * sizeof(double)));
+    c->scratch_ny = ny;
+  }
+  *dx = c->scratch_x; *dy = c->scratch_y;
+  return 0;
+}
+
 static int check_mat(a2ds_ctx *c, int mat, int block = 0) {
   if (mat < 0 || mat >= (int)c->mats.size()) return fail("bad matrix id");
+  if (c->mats[mat].dead) return fail("matrix id belongs to a mesh that has been replaced (a2ds_set_mesh)");
   if (block < 0 || block >= c->mats[mat].n_blocks) return fail("bad BCSR block index");
   return 0;
 }
@@ -722,6 +778,32 @@ extern "C" int a2ds_mat_download(a2ds_ctx *c, int mat, int block, double *A) {
   A2DS_CATCH(a2ds_mat_download)
 }
 
+// selected block rows of one BCSR block to the host: the blocks of rows[0], rows[1], ... one
+// after the other in A (36 doubles each, sum over the rows of rowp[r + 1] - rowp[r] blocks);
+// what BCSRMat::getArrays + a row loop gives on the host side — for spot checks of matrices
+// that are too large to copy back whole
+extern "C" int a2ds_mat_download_rows(a2ds_ctx *c, int mat, int block, int n_rows, const int *rows,
+                                      double *A) {
+  A2DS_TRY
+  if (check_mat(c, mat, block)) return 1;
+  CU(cudaSetDevice(c->device));
+  MatrixRec &m = c->mats[mat];
+  const std::vector<int> &rowp = m.h_rowp[block];
+  size_t out = 0;
+  for (int i = 0; i < n_rows; i++) {
+    const int r = rows[i];
+    if (r < 0 || r >= m.nrows[block]) return fail("a2ds_mat_download_rows: row out of range");
+    const size_t nb = (size_t)(rowp[r + 1] - rowp[r]);
+    if (nb)
+      CU(cudaMemcpyAsync(A + 36 * out, m.A + 36 * ((size_t)m.base[block] + rowp[r]),
+                         nb * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    out += nb;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+  A2DS_CATCH(a2ds_mat_download_rows)
+}
+
 extern "C" int a2ds_mat_values_dev(a2ds_ctx *c, int mat, int block, double **A_dev) {
   A2DS_TRY
   if (check_mat(c, mat, block)) return 1;
@@ -826,6 +908,11 @@ extern "C" int a2ds_mat_mult_dist_dev(a2ds_ctx *c, int mat, double *x_dev, doubl
   if (m.n_blocks != 1 || m.nrows[0] != c->n_nodes)
     return fail("a2ds_mat_mult_dist: needs a natural-order matrix over the local nodes "
                 "(a2ds_mat_create_natural)");
+  if (m.has_halo)
+    return fail("a2ds_mat_mult_dist: this matrix has a matrix halo (TACSParallelMat flavour): its "
+                "owned rows are already complete and its ghost rows still hold the local shares, so "
+                "the reverse vector exchange would count the interface couplings twice; use a "
+                "matrix without a2ds_mat_set_halo (interface rows unassembled) for this product");
   if (halo_exchange(c, x_dev, false)) return 1;
   if (a2ds_mat_mult_dev(c, mat, 0, x_dev, y_dev)) return 1;
   if (halo_exchange(c, y_dev, true)) return 1;
@@ -850,15 +937,13 @@ extern "C" int a2ds_mat_mult(a2ds_ctx *c, int mat, int block, int ncols, const d
     return fail("a2ds_mat_mult: x has " + std::to_string(ncols) + " block columns, the matrix "
                 "block refers to column " + std::to_string(max_col));
   double *dx = nullptr, *dy = nullptr;
-  CU(cudaMalloc((void **)&dx, std::max<size_t>(6 * (size_t)ncols, 1) * sizeof(double)));
-  CU(cudaMalloc((void **)&dy, std::max<size_t>(6 * (size_t)nrows, 1) * sizeof(double)));
+  if (scratch_vectors(c, 6 * (size_t)ncols, 6 * (size_t)nrows, &dx, &dy)) return 1;
   CU(cudaMemcpyAsync(dx, x, 6 * (size_t)ncols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   int rc = a2ds_mat_mult_dev(c, mat, block, dx, dy);
   if (!rc) {
     CU(cudaMemcpyAsync(y, dy, 6 * (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
-  cudaFree(dx); cudaFree(dy);
   return rc;
   A2DS_CATCH(a2ds_mat_mult)
 }
@@ -1500,8 +1585,7 @@ extern "C" int a2ds_add_jacobian_vec_product(a2ds_ctx *c, double scale, double a
   CU(cudaSetDevice(c->device));
   const size_t nb = 6 * (size_t)c->n_nodes * sizeof(double);
   double *dx = nullptr, *dy = nullptr;
-  CU(cudaMalloc((void **)&dx, std::max<size_t>(nb, 8)));
-  CU(cudaMalloc((void **)&dy, std::max<size_t>(nb, 8)));
+  if (scratch_vectors(c, 6 * (size_t)c->n_nodes, 6 * (size_t)c->n_nodes, &dx, &dy)) return 1;
   CU(cudaMemcpyAsync(dx, x, nb, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(dy, y, nb, cudaMemcpyHostToDevice, c->stream));
   int rc = a2ds_add_jacobian_vec_product_dev(c, scale, alpha, dx, dy);
@@ -1509,7 +1593,6 @@ extern "C" int a2ds_add_jacobian_vec_product(a2ds_ctx *c, double scale, double a
     CU(cudaMemcpyAsync(y, dy, nb, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
-  cudaFree(dx); cudaFree(dy);
   return rc;
   A2DS_CATCH(a2ds_add_jacobian_vec_product)
 }

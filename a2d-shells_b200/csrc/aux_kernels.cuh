@@ -25,7 +25,7 @@ __global__ void k_build_offsets(int n_elems, const int *conn, int n_blocks, cons
   for (int b = 0; b < n_blocks && found < 0; b++) {
     const int rr = blk[b].row_map ? blk[b].row_map[rn] : (rn < blk[b].nrows ? rn : -1);
     const int cc = blk[b].col_map ? blk[b].col_map[cn] : cn;
-    if (rr < 0 || cc < 0) continue;
+    if (rr < 0 || rr >= blk[b].nrows || cc < 0) continue;
     int lo = blk[b].rowp[rr], hi = blk[b].rowp[rr + 1] - 1;
     while (lo <= hi) {
       const int mid = (lo + hi) >> 1, v = blk[b].cols[mid];
@@ -73,8 +73,8 @@ __global__ void k_mat_bcs(int n_bc, const int *nodes, const int *vars, int n_blo
   const int b = t / n_blocks, ib = t - b * n_blocks;
   const BlockDev B = blk[ib];
   const int n = nodes[b], mask = vars[b];
-  const int row = B.row_map ? B.row_map[n] : (n < B.nrows ? n : -1);
-  if (row < 0) return;
+  const int row = B.row_map ? B.row_map[n] : n;
+  if (row < 0 || row >= B.nrows) return;
   const int diag_col = B.col_map ? B.col_map[n] : n;
   for (int j = B.rowp[row]; j < B.rowp[row + 1]; j++) {
     double *a = &A[36 * (size_t)(B.base + j)];

@@ -41,6 +41,8 @@ struct Shim {
   std::map<TACSMat *, int> mats;
   std::vector<TACSElement *> comp_elems;  // one record per distinct element object
   int n_nodes = 0;
+  std::vector<double> comp_key;   // component tables as last uploaded
+  std::vector<double> x_key;      // node coordinates as last uploaded (setNodes after set-up)
 };
 std::map<TACSAssembler *, Shim> g_shims;
 
@@ -105,13 +107,19 @@ static void shim_upload_components(TACSAssembler *self, Shim &S, bool first) {
     }
     S.n_nodes = self->numNodes;
     CK(a2ds_set_mesh(S.ctx, S.n_nodes, self->numOwnedNodes, ne, conn.data(), elem_comp.data()));
-    TacsScalar *x;
-    self->xptVec->getArray(&x);
-    CK(a2ds_set_nodes(S.ctx, x));
     const int *nodes, *vars;
     TacsScalar *vals;
     int nbc = self->bcMap->getBCs(&nodes, &vars, &vals);
     CK(a2ds_set_bcs(S.ctx, nbc, nodes, vars, vals));
+  }
+  {
+    // node coordinates: re-uploaded whenever the driver changed them (TACSAssembler::setNodes)
+    TacsScalar *x;
+    const int nx = self->xptVec->getArray(&x);
+    if ((int)S.x_key.size() != nx || memcmp(S.x_key.data(), x, nx * sizeof(double)) != 0) {
+      S.x_key.assign(x, x + nx);
+      CK(a2ds_set_nodes(S.ctx, x));
+    }
   }
   // per-component tables are refreshed on every call: element temperatures are public
   // data members that drivers change after set-up (mechBuckling.cpp:90-97)
@@ -133,6 +141,18 @@ static void shim_upload_components(TACSAssembler *self, Shim &S, bool first) {
       abort();
     }
   }
+  // upload only when a table changed (temperature, section data): a2ds_set_components drops
+  // the cached element lists / colouring, which every assemble call would otherwise rebuild
+  std::vector<double> key;
+  key.insert(key.end(), Cs.begin(), Cs.end());
+  key.insert(key.end(), eth.begin(), eth.end());
+  key.insert(key.end(), mom.begin(), mom.end());
+  key.insert(key.end(), T.begin(), T.end());
+  for (int i = 0; i < nc; i++) key.push_back((double)cls[i]);
+  key.push_back((double)transform);
+  key.insert(key.end(), axis, axis + 3);
+  if (key == S.comp_key) return;
+  S.comp_key = key;
   CK(a2ds_set_mass_moments(S.ctx, nc, mom.data()));
   CK(a2ds_set_components(S.ctx, nc, Cs.data(), eth.data(), T.data(), cls.data(), transform, axis));
 }
@@ -197,7 +217,9 @@ static int shim_matrix(TACSAssembler *self, Shim &S, TACSMat *A) {
     std::vector<int> ident(n), none(n, -1);
     for (int i = 0; i < n; i++) ident[i] = i;
     maps[0][0] = ident; maps[0][1] = ident;
-    maps[1][0] = ident; maps[1][1] = none;
+    // Bext: on one rank the external block has no rows -> no node maps to a row of it (an
+    // identity map here would send the BC kernel past the 0-row rowp)
+    maps[1][0] = none; maps[1][1] = none;
     nb = 2;
   } else {
     fprintf(stderr, "[a2ds shim] unsupported matrix class %s\n", A->getObjectName());

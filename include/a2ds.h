@@ -147,6 +147,10 @@ int a2ds_mat_zero(a2ds_ctx *ctx, int mat);
  * reference solver" path: BCSRMat::getArrays) / borrow the device pointer */
 int a2ds_mat_download(a2ds_ctx *ctx, int mat, int block, double *A);
 int a2ds_mat_values_dev(a2ds_ctx *ctx, int mat, int block, double **A_dev);
+/* the blocks of the listed block rows only, row after row (36 doubles per block): spot checks
+ * of matrices too large to copy back (a row loop over BCSRMat::getArrays, BCSRMat.cpp:2312) */
+int a2ds_mat_download_rows(a2ds_ctx *ctx, int mat, int block, int n_rows, const int *rows,
+                           double *A);
 
 /* ---- matrix algebra on the device-resident values (the buckling flow's K/G handling) ----
  * TACSMat::copyValues (src/bpmat/BCSRMat.cpp:2375): dst <- src, same pattern required */

@@ -1,5 +1,5 @@
 """summarise an .ncu-rep (raw page + SASS sampling) into a small text file for profiles/"""
-import csv, collections, subprocess, sys
+import csv, collections, os, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -56,3 +56,62 @@ if len(sys.argv) > 2:
 top = sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:12]
 print("\nhottest SASS instructions:")
 for r in top: print(f"  {int(r[ix['# Samples']]):6d}  {r[ix['Source']][:80]}")
+
+
+def write_counters(rep, n_elems, out_path):
+    """profiles/kernel_counters.json: what bench.py quotes about the fused kernel, tied to the
+    kernel sources it was captured from (sha1) — executed FP64 work, pipe cycles, DRAM bytes"""
+    import hashlib, json, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha1()
+    for f in ("assemble_kernels.cuh", "mitc4_math.h", "mitc4_tying.h"):
+        h.update(open(os.path.join(root, "a2d-shells_b200", "csrc", f), "rb").read())
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    d = {hh: (v, u) for hh, u, v in zip(rows[0], rows[1], rows[2])}
+    def val(k, scale={"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "s": 1.0}):
+        v, u = d[k]
+        return float(v) * scale.get(u, 1.0)
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    hdr = rows[1]; ix = {hh: i for i, hh in enumerate(hdr)}
+    thr = collections.Counter(); wrp = collections.Counter()
+    for r in rows[2:]:
+        if len(r) < len(hdr) or not r[ix["# Samples"]].isdigit():
+            continue
+        m = re.match(r"\s*(?:@!?U?P\w+\s+)?([A-Z0-9_.]+)", r[ix["Source"]])
+        if not m:
+            continue
+        op = m.group(1).split(".")[0]
+        if op in ("DFMA", "DMUL", "DADD", "DMMA"):
+            wrp[op] += int(r[ix["Instructions Executed"]])
+            thr[op] += int(r[ix["Predicated-On Thread Instructions Executed"]])
+    flops = 2 * thr["DFMA"] + thr["DMUL"] + thr["DADD"] + 512 * wrp["DMMA"]
+    pipe_cycles = 2 * (wrp["DFMA"] + wrp["DMUL"] + wrp["DADD"]) + 16 * wrp["DMMA"]   # per SM sub-partition
+    n_smsp = 148 * 4
+    clock = 1.965e9
+    out = {
+        "source_hash": h.hexdigest(), "kernel": d["Kernel Name"][0], "n_elems": n_elems,
+        "report": "profiles/" + os.path.basename(rep).replace(".ncu-rep", ".txt") +
+                  " (ncu --set full --clock-control none)",
+        "kernel_time_under_ncu_s": val("gpu__time_duration.sum"),
+        "fp64_flops_per_elem": flops / n_elems,
+        "fp64_thread_instr_per_elem": {k: thr[k] / n_elems for k in ("DFMA", "DMUL", "DADD")},
+        "dmma_per_elem": wrp["DMMA"] / n_elems,
+        "warp_instr_per_elem": float(d["smsp__inst_executed.sum"][0]) / n_elems,
+        "fp64_pipe_cycles_per_elem": pipe_cycles / n_elems,
+        "fp64_pipe_ceiling_elems_per_s": n_smsp * clock / (pipe_cycles / n_elems),
+        "fp64_pipe_busy": float(d["sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active"][0]) / 100.0,
+        "dram_bytes_per_elem": (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / n_elems,
+        "warps_active_pct": float(d["sm__warps_active.avg.pct_of_peak_sustained_active"][0]),
+    }
+    json.dump(out, open(out_path, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if "--counters" in sys.argv:
+    i = sys.argv.index("--counters")
+    write_counters(rep, int(sys.argv[i + 1]),
+                   sys.argv[i + 2] if len(sys.argv) > i + 2 else
+                   os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "kernel_counters.json"))

@@ -29,4 +29,26 @@ for mode in (a2ds.SCATTER_ATOMIC, a2ds.SCATTER_COLORED):
     z = asm.mat_mult(m, u)
     print("mode", mode, float(np.abs(r).max()), float(np.abs(y).max()), float(np.abs(z).max()))
     asm.close()
+# uncoupled components as well (the tying-level kernel k_assemble_t; the wing box above has
+# coupled sections and runs the first formulation), and a TACSParallelMat-style matrix: two
+# BCSR blocks with row maps, the second one EMPTY (Bext on one rank), boundary conditions on
+asm = a2ds.Assembler(0)
+conn2, X2, ends2 = a2ds.meshes.cylinder(12, 5)
+n2 = len(X2)
+Cs2, eth2 = a2ds.iso_shell_tables()
+asm.set_mesh(conn2, n2); asm.set_nodes(X2)
+asm.set_components(np.stack([Cs2, Cs2]), np.stack([eth2, eth2]), elem_class=[0, 1])
+asm.set_bcs(ends2, 0b100111)
+asm.set_state(a2ds.meshes.seeded_state(np.arange(n2), 1e-4))
+rowp, cols = asm.mat_pattern(asm.create_mat())
+ident = np.arange(n2, dtype=np.int32); none = np.full(n2, -1, dtype=np.int32)
+blocks = [dict(nrows=n2, rowp=rowp, cols=cols, row_map=ident, col_map=ident, ident=1),
+          dict(nrows=0, rowp=np.zeros(1, np.int32), cols=np.zeros(0, np.int32), row_map=none,
+               col_map=none, ident=0)]
+pk = asm.create_mat_from_pattern(blocks); pg = asm.create_mat_from_pattern(blocks)
+r2 = asm.assembleAll(pk, pg)
+asm.assembleJacobian(1.0, 0.0, 0.0, pk); asm.assembleMatType(1, pg)
+y2 = asm.addJacobianVecProduct(1.0, 1.0, np.ones((n2, 6)), np.zeros((n2, 6)))
+print("two-block", float(np.abs(r2).max()), float(np.abs(asm.mat_values(pk)).max()), float(np.abs(y2).max()))
+asm.close()
 print("SANITIZE_DRIVER_DONE")
