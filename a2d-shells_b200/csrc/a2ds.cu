@@ -124,6 +124,7 @@ struct a2ds_ctx {
   int *work_counter = nullptr;   // [0] batch counter, [1..] zero_done rounds; zeroed before every k_assemble launch
   // matrices the next k_assemble_t launch has to zero itself (in-kernel zeroing)
   double *pz_K = nullptr, *pz_G = nullptr;
+  struct ZeroPlan *zplan_dev = nullptr;
   long long pz_nK = 0, pz_nG = 0;
   double *udd = nullptr;  // second time derivative of the state (null until set)
   CompData *comps = nullptr;
@@ -233,7 +234,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   free_lists(c);
   cudaFree(c->conn); cudaFree(c->elem_comp); cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
   cudaFree(c->udd);
-  cudaFree(c->scratch_x); cudaFree(c->scratch_y);
+  cudaFree(c->scratch_x); cudaFree(c->scratch_y); cudaFree(c->zplan_dev);
   cudaFree(c->comps); cudaFree(c->bc_nodes); cudaFree(c->bc_vars); cudaFree(c->bc_vals);
   cudaFree(c->send_nodes); cudaFree(c->recv_nodes); cudaFree(c->send_buf); cudaFree(c->recv_buf);
   if (c->comm) ncclCommDestroy(c->comm);
@@ -1170,38 +1171,9 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   const int n_groups = (p.n_list + NB - 1) / NB;
   const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
-  p.zero_rounds = 0;
-  if (c->pz_K || c->pz_G) {
-    // in-kernel zeroing (see k_assemble_t): about one round per trip of a warp
-    static const int ahead = getenv("A2DS_ZERO_AHEAD") ? atoi(getenv("A2DS_ZERO_AHEAD")) : 3;
-    const int n_gw = grid * wpb;
-    const int rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / n_gw));
-    p.zero_rounds = rounds;
-    p.zero_ahead = std::max(1, ahead);
-    p.zeroK = (double2 *)c->pz_K; p.zero_nK = c->pz_nK;
-    p.zeroG = (double2 *)c->pz_G; p.zero_nG = c->pz_nG;
-    const long long per_round = (long long)rounds * n_gw;
-    // whole blocks per chunk (18 double2 each)
-    p.zero_cK = 18 * (int)std::max<long long>(1, (c->pz_nK / 18 + per_round - 1) / per_round);
-    p.zero_cG = 18 * (int)std::max<long long>(1, (c->pz_nG / 18 + per_round - 1) / per_round);
-    // both matrices use the same round boundaries in blocks only when they have the same
-    // chunk; the kernel takes the larger round index of the two, so use the smaller chunk
-    {
-      const double bpr = (double)n_gw * (double)(std::min(p.zeroK ? p.zero_cK : p.zero_cG,
-                                                          p.zeroG ? p.zero_cG : p.zero_cK) / 18);
-      p.zero_inv_round = (float)(1.0 / bpr) * (1.0f + 1e-6f);
-    }
-    p.zero_done = c->work_counter + 1;
-    c->pz_K = c->pz_G = nullptr;
-  }
-  CU(cudaMemsetAsync(c->work_counter, 0, (1 + p.zero_rounds) * sizeof(int), c->stream));
-  if (p.zero_rounds > 0) {
-    // the zeroing protocol waits on every warp of the grid: all blocks must be co-resident
-    void *args[] = {(void *)&p};
-    CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(wpb * 32), args, smem, c->stream));
-  } else {
-    kern<<<grid, wpb * 32, smem, c->stream>>>(p);
-  }
+  p.zplan = nullptr;
+  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  kern<<<grid, wpb * 32, smem, c->stream>>>(p);
   CU(cudaGetLastError());
   c->last_launches++;
   return 0;
@@ -1240,32 +1212,33 @@ static int launch_one_t(a2ds_ctx *c, KParams &p) {
   const int n_groups = (p.n_list + NB - 1) / NB;
   const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
-  p.zero_rounds = 0;
+  p.zplan = nullptr;
+  int rounds = 0;
   if (c->pz_K || c->pz_G) {
-    // in-kernel zeroing (see k_assemble_t): about one round per trip of a warp
+    // in-kernel zeroing (see ikz_service): about one round per trip of a warp
     static const int ahead = getenv("A2DS_ZERO_AHEAD") ? atoi(getenv("A2DS_ZERO_AHEAD")) : 3;
     const int n_gw = grid * wpb;
-    const int rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / n_gw));
-    p.zero_rounds = rounds;
-    p.zero_ahead = std::max(1, ahead);
-    p.zeroK = (double2 *)c->pz_K; p.zero_nK = c->pz_nK;
-    p.zeroG = (double2 *)c->pz_G; p.zero_nG = c->pz_nG;
+    rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / n_gw));
+    ZeroPlan zp;
+    zp.zK = (double2 *)c->pz_K; zp.nK = c->pz_nK;
+    zp.zG = (double2 *)c->pz_G; zp.nG = c->pz_nG;
     const long long per_round = (long long)rounds * n_gw;
     // whole blocks per chunk (18 double2 each)
-    p.zero_cK = 18 * (int)std::max<long long>(1, (c->pz_nK / 18 + per_round - 1) / per_round);
-    p.zero_cG = 18 * (int)std::max<long long>(1, (c->pz_nG / 18 + per_round - 1) / per_round);
-    // both matrices use the same round boundaries in blocks only when they have the same
-    // chunk; the kernel takes the larger round index of the two, so use the smaller chunk
-    {
-      const double bpr = (double)n_gw * (double)(std::min(p.zeroK ? p.zero_cK : p.zero_cG,
-                                                          p.zeroG ? p.zero_cG : p.zero_cK) / 18);
-      p.zero_inv_round = (float)(1.0 / bpr) * (1.0f + 1e-6f);
-    }
-    p.zero_done = c->work_counter + 1;
+    zp.cK = 18 * (int)std::max<long long>(1, (c->pz_nK / 18 + per_round - 1) / per_round);
+    zp.cG = 18 * (int)std::max<long long>(1, (c->pz_nG / 18 + per_round - 1) / per_round);
+    // the kernel takes ONE round index from the highest offset of both matrices: use the
+    // smaller chunk (round boundaries in blocks)
+    const double bpr = (double)n_gw * (double)(std::min(zp.zK ? zp.cK : zp.cG, zp.zG ? zp.cG : zp.cK) / 18);
+    zp.inv_round = (float)(1.0 / bpr) * (1.0f + 1e-6f);
+    zp.rounds = rounds; zp.ahead = std::max(1, ahead);
+    zp.done = c->work_counter + 1;
+    if (!c->zplan_dev) CU(cudaMalloc((void **)&c->zplan_dev, sizeof(ZeroPlan)));
+    CU(cudaMemcpyAsync(c->zplan_dev, &zp, sizeof(ZeroPlan), cudaMemcpyHostToDevice, c->stream));
+    p.zplan = c->zplan_dev;
     c->pz_K = c->pz_G = nullptr;
   }
-  CU(cudaMemsetAsync(c->work_counter, 0, (1 + p.zero_rounds) * sizeof(int), c->stream));
-  if (p.zero_rounds > 0) {
+  CU(cudaMemsetAsync(c->work_counter, 0, (1 + rounds) * sizeof(int), c->stream));
+  if (p.zplan) {
     // the zeroing protocol waits on every warp of the grid: all blocks must be co-resident
     void *args[] = {(void *)&p};
     CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(wpb * 32), args, smem, c->stream));

@@ -41,15 +41,9 @@ struct KParams {
   double jvp_scale;
   int scratch_bytes;
   int *work_counter;     // dynamic batch scheduling: next batch index (zeroed per launch)
-  // in-kernel zeroing of the output matrices (k_assemble_t, cooperative launch): the value
-  // arrays are cut into zero_rounds rounds of one chunk per warp; see zero_round() there
-  double2 *zeroK, *zeroG;        // arrays to zero (null: none), lengths in double2 units
-  long long zero_nK, zero_nG;
-  int zero_cK, zero_cG;          // chunk of one warp in one round (double2 units, whole blocks)
-  float zero_inv_round;          // 1 / (blocks per round), rounded up
-  int zero_rounds;               // 0: the matrices were zeroed by the caller
-  int zero_ahead;                // rounds zeroed before the first batch
-  int *zero_done;                // per round: number of warps that have zeroed and fenced
+  // in-kernel zeroing of the output matrices (k_assemble_t, cooperative launch): plan in device
+  // memory, null when the caller zeroed the matrices (see ikz_service)
+  const struct ZeroPlan *zplan;
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -470,8 +464,26 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
 // blocks are added), so there is no second staging tile.  Components without
 // membrane-bending coupling only (run_assembly sends coupled ones to k_assemble).
 // =====================================================================================
+// in-kernel zeroing of the output matrices: plan and per-warp state (see ikz_service)
+struct ZeroPlan {
+  double2 *zK, *zG;        // arrays to zero (null: none)
+  long long nK, nG;        // lengths in double2 units
+  int cK, cG;              // chunk of one warp in one round (double2 units, whole blocks)
+  float inv_round;         // 1 / (blocks per round)
+  int rounds, ahead;       // number of rounds; rounds zeroed before the first batch
+  int *done;               // per round: number of warps that have zeroed and fenced
+};
+struct IkzState {          // per warp, in shared memory
+  int stored;              // rounds whose stores have been issued
+  int published;           // rounds fenced and counted in done[]
+  int known;               // highest round known to be complete on all warps
+  int pad_;
+};
 #ifndef A2DS_MB_T
 #define A2DS_MB_T 2
+#endif
+#ifndef A2DS_CTA_SYNC
+#define A2DS_CTA_SYNC 1
 #endif
 struct BatchTmp {   // node-phase outputs only the Gauss-point phase reads; overlaid on the staging
   double dr[12], etn[4], pad_[4];   // tile E, which is only live inside the per-element loop
@@ -494,6 +506,7 @@ struct WarpScratchT {
     BatchTmp tmp[NB];
   };
   TyWork work;
+  IkzState ikz;
   RawBatch raw1;            // double buffer: batch i+1 lands (cp.async) while batch i is processed
   alignas(16) int goff[2][NB][16];
 };
@@ -502,6 +515,8 @@ static_assert(sizeof(BatchTmp) * NB <= sizeof(double) * 24 * KE_LD, "batch input
 // the 45 entries of H_tt (Gauss-point weights and slots; constant)
 struct BlockSharedT {
   TyPlan plan[45];
+  int draw[2];   // block-synchronous scheduling: first batch of the block in trips t, t + 1
+  int pad_[2];
 };
 static const int BLOCK_SHARED_T = (int)((sizeof(BlockSharedT) + 15) & ~size_t(15));
 
@@ -533,14 +548,15 @@ __device__ __forceinline__ void stage_tiles_g(double *E, const double (&acc)[6][
 // Instead of a memset in front of the kernel (5.2 GB written, evicted, and read back by the
 // first RED of every block), every warp zeroes ONE chunk per trip, a few rounds ahead of where
 // the element batches drawn at that time scatter: round r = chunk r of every warp = one
-// contiguous slice of the value arrays.  A warp publishes a round (fence + counter) after its
-// batched phases, when its own earlier REDs have long drained, and before it scatters a batch
-// it checks that the round its highest block offset falls into has been zeroed by ALL warps
-// (zero_done[r] == number of warps; rounds complete in order per warp).  A warp that has to
+// contiguous slice of the value arrays.  Once per trip, after the batched phases (when the
+// warp's earlier REDs have long drained, so the fence is cheap), a warp calls ikz_service:
+// it publishes the round it stored a trip ago (fence + counter), stores the next one, and
+// checks that the round the batch's highest block offset falls into has been zeroed by ALL
+// warps (done[r] == number of warps; rounds complete in order per warp).  A warp that has to
 // wait zeroes ahead instead of spinning idle, so the scheme cannot deadlock and degenerates to
 // "zero everything first" for element orders without locality.  All warps are co-resident
-// (cooperative launch).  Kept out of line: the hot loops must not pay registers for it.
-// one chunk (round r, warp gw) of one value array: c2 double2 from (r * n_gw + gw) * c2
+// (cooperative launch).  Out of line, state in shared memory, plan in device memory: the hot
+// loops carry no register for it.
 __device__ __forceinline__ void ikz_zero_chunk(double2 *zb, long long n2, int c2, int r, int gw,
                                                int n_gw, int lane) {
   if (!zb) return;
@@ -551,41 +567,67 @@ __device__ __forceinline__ void ikz_zero_chunk(double2 *zb, long long n2, int c2
 #pragma unroll 4
   for (int i = lane; i < len; i += 32) q[i] = make_double2(0.0, 0.0);
 }
-__device__ __forceinline__ void ikz_publish(int *done, int from, int to, int lane) {
-  __threadfence();
-  __syncwarp();
-  if (lane == 0)
-    for (int r = from; r < to; r++) atomicAdd(&done[r], 1);
-}
-// cold paths, out of line: rounds [from, to) of this warp zeroed and published ...
-__device__ __noinline__ void ikz_rounds(double2 *zK, long long nK, int cK, double2 *zG, long long nG,
-                                        int cG, int *done, int from, int to, int gw, int n_gw,
-                                        int lane) {
-  for (int r = from; r < to; r++) {
-    ikz_zero_chunk(zK, nK, cK, r, gw, n_gw, lane);
-    ikz_zero_chunk(zG, nG, cG, r, gw, n_gw, lane);
+__device__ __forceinline__ void ikz_publish(const ZeroPlan &z, IkzState &st, int lane) {
+  if (st.published < st.stored) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0)
+      for (int r = st.published; r < st.stored; r++) atomicAdd(&z.done[r], 1);
+    __syncwarp();
+    if (lane == 0) st.published = st.stored;
+    __syncwarp();
   }
-  ikz_publish(done, from, to, lane);
 }
-// ... and the wait for round rneed: zeroes further rounds of this warp instead of idling.
-// Returns the warp's new round count.
-__device__ __noinline__ int ikz_wait(double2 *zK, long long nK, int cK, double2 *zG, long long nG,
-                                     int cG, int *done, int rneed, int zr, int n_zr, int gw,
-                                     int n_gw, int lane) {
+__device__ __forceinline__ void ikz_store_next(const ZeroPlan &z, IkzState &st, int gw, int n_gw, int lane) {
+  const int r = st.stored;
+  if (r < z.rounds) {
+    ikz_zero_chunk(z.zK, z.nK, z.cK, r, gw, n_gw, lane);
+    ikz_zero_chunk(z.zG, z.nG, z.cG, r, gw, n_gw, lane);
+    __syncwarp();
+    if (lane == 0) st.stored = r + 1;
+    __syncwarp();
+  }
+}
+// mode 0: kernel start (first `ahead` rounds);  1: once per trip, mx = highest block offset the
+// batch scatters to;  2: kernel end (all remaining rounds)
+__device__ __noinline__ void ikz_service(const ZeroPlan *zp, IkzState *stp, int mode, int mx, int gw,
+                                         int n_gw, int lane) {
+  const ZeroPlan z = *zp;
+  IkzState &st = *stp;
+  if (mode == 0) {
+    if (lane == 0) { st.stored = 0; st.published = 0; st.known = -1; }
+    __syncwarp();
+    for (int r = 0; r < z.ahead && r < z.rounds; r++) ikz_store_next(z, st, gw, n_gw, lane);
+    ikz_publish(z, st, lane);
+    return;
+  }
+  if (mode == 2) {
+    while (st.stored < z.rounds) ikz_store_next(z, st, gw, n_gw, lane);
+    ikz_publish(z, st, lane);
+    return;
+  }
+  ikz_publish(z, st, lane);              // the round stored one trip ago
+  ikz_store_next(z, st, gw, n_gw, lane); // stores only
+  // round that must be complete before this batch scatters (rounded up: one round early costs
+  // nothing, one round late is a race)
+  int rneed = (int)((float)mx * z.inv_round) + 1;
+  if (rneed > z.rounds - 1) rneed = z.rounds - 1;
+  if (rneed <= st.known) return;
   for (;;) {
     int v = 0;
-    if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + rneed) : "memory");
+    if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(z.done + rneed) : "memory");
     v = __shfl_sync(0xffffffffu, v, 0);
-    if (v >= n_gw) return zr;
-    if (zr < n_zr) {
-      ikz_zero_chunk(zK, nK, cK, zr, gw, n_gw, lane);
-      ikz_zero_chunk(zG, nG, cG, zr, gw, n_gw, lane);
-      ikz_publish(done, zr, zr + 1, lane);
-      zr++;
+    if (v >= n_gw) break;
+    if (st.stored < z.rounds || st.published < st.stored) {   // zero ahead instead of idling
+      ikz_publish(z, st, lane);
+      ikz_store_next(z, st, gw, n_gw, lane);
+      ikz_publish(z, st, lane);
     } else {
       __nanosleep(256);
     }
   }
+  if (lane == 0) st.known = rneed;
+  __syncwarp();
 }
 
 #ifndef A2DS_GEO_MMA
@@ -668,20 +710,14 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
   // zero row / column of H
   if (lane < TY_LD) { wk.H[TY_LD * 9 + lane] = 0.0; wk.H[TY_LD * lane + 9] = 0.0; wk.sigt[lane] = 0.0; }
 
-  // in-kernel zeroing of the output matrices (see ikz_zero_round above)
+  // in-kernel zeroing of the output matrices (see ikz_service above)
 #ifdef A2DS_IKZ
-  const int n_zr = p.zero_rounds;
+  const bool ikz = p.zplan != nullptr;
 #else
-  const int n_zr = 0;   // compiled out: the caller zeroes the matrices (see profiles/README.md)
+  const bool ikz = false;   // compiled out: the caller zeroes the matrices
 #endif
   const int gw = blockIdx.x * (blockDim.x >> 5) + warp, n_gw = gridDim.x * (blockDim.x >> 5);
-  int zr = 0, zknown = -1;   // rounds zeroed AND published by this warp; highest round known complete
-  bool zpend = false;        // round zr is stored but not yet published
-  if (n_zr > 0) {
-    zr = min(n_zr, p.zero_ahead);
-    ikz_rounds(p.zeroK, p.zero_nK, p.zero_cK, p.zeroG, p.zero_nG, p.zero_cG, p.zero_done, 0, zr, gw,
-               n_gw, lane);
-  }
+  if (ikz) ikz_service(p.zplan, &ws.ikz, 0, 0, gw, n_gw, lane);
 
   auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
     const int j = (lane >> 2) & (NB - 1);
@@ -715,24 +751,46 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
     if (lane == 0) g = atomicAdd(p.work_counter, 1);
     return __shfl_sync(FULL, g, 0);
   };
-  int grp = next_group();
-  int grp_nxt = next_group();
+  // Block-synchronous trips for the big variants: the warps of a block draw their batches
+  // together (one atomic per block and trip) and start every trip at a block barrier, so that
+  // they walk the same code at the same time — the batched phases are ~45 KB of straight-line
+  // SASS per trip and the instruction cache serves four warps with one fetch.  Measured:
+  // -4 % for the fused / geometric-stiffness kernels, +3 % for the residual / linear tangent
+  // ones (short trips against the barrier wait), which keep drawing per warp.
+  constexpr bool CS = A2DS_CTA_SYNC && GMAT;
+  const int wpb = blockDim.x >> 5;
+  int base_cur = 0, trip = 0;
+  int grp, grp_nxt;
+  if constexpr (CS) {
+    if (threadIdx.x == 0) {
+      bs.draw[0] = atomicAdd(p.work_counter, wpb);
+      bs.draw[1] = atomicAdd(p.work_counter, wpb);
+    }
+    __syncthreads();
+    base_cur = bs.draw[0];
+    grp = base_cur + warp; grp_nxt = bs.draw[1] + warp;
+  } else {
+    grp = next_group();
+    grp_nxt = next_group();
+  }
   int buf = 0;
   int e_cur, nd_cur;
   batch_ids(grp, e_cur, nd_cur);
   if (grp < n_groups) issue_gather(ws.raw0, ws.goff[0], e_cur, nd_cur);
-  for (; grp < n_groups; buf ^= 1) {
-    int drawn = 0;
-    if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
+  for (; CS ? (base_cur < n_groups) : (grp < n_groups); buf ^= 1, trip++) {
+    int drawn = 0, base_nxt = 0;
+    if constexpr (CS) {
+      __syncthreads();
+      base_nxt = bs.draw[(trip + 1) & 1];   // drawn one trip ago (or in the prologue)
+      grp_nxt = base_nxt + warp;
+      if (threadIdx.x == 0) bs.draw[trip & 1] = atomicAdd(p.work_counter, wpb);   // for trip + 2
+    } else {
+      if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
+    }
     const int base = grp * NB;
-    const int cnt = min(NB, p.n_list - base);
+    const int cnt = grp < n_groups ? min(NB, p.n_list - base) : 0;
     int e_nxt = -1, nd_nxt = 0;
     batch_ids(grp_nxt, e_nxt, nd_nxt);
-    if (zr < n_zr) {   // stores only: published after the batched phases
-      ikz_zero_chunk(p.zeroK, p.zero_nK, p.zero_cK, zr, gw, n_gw, lane);
-      ikz_zero_chunk(p.zeroG, p.zero_nG, p.zero_cG, zr, gw, n_gw, lane);
-      zpend = true;
-    }
     cp_async_wait_all();
     __syncwarp();
     const RawBatch &rb = buf ? ws.raw1 : ws.raw0;
@@ -758,27 +816,19 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ^ 1], e_nxt, nd_nxt);
     e_cur = e_nxt; nd_cur = nd_nxt;
     __syncwarp();
-    if (n_zr > 0) {
-      if (zpend) { ikz_publish(p.zero_done, zr, zr + 1, lane); zr++; zpend = false; }
-      // the round that must be complete before this batch scatters, from its highest block
-      // offset (rounded up: one round early costs nothing, one round late is a race)
+    if (ikz) {
       int mx = 0;
 #pragma unroll
       for (int r = 0; r < NB * 16 / 32; r++) {
         const int sidx = lane + 32 * r, j = sidx >> 4, k = sidx & 15;
         if (j < cnt) {
-          if (KMAT && p.zeroK) mx = max(mx, rb.koff[j][k]);
-          if (GMAT && p.zeroG) mx = max(mx, goffb[j][k]);
+          if (KMAT) mx = max(mx, rb.koff[j][k]);
+          if (GMAT) mx = max(mx, goffb[j][k]);
         }
       }
-      int rneed = min(n_zr - 1, (int)((float)mx * p.zero_inv_round) + 1);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rneed = max(rneed, __shfl_xor_sync(FULL, rneed, o));
-      if (rneed > zknown) {
-        zr = ikz_wait(p.zeroK, p.zero_nK, p.zero_cK, p.zeroG, p.zero_nG, p.zero_cG, p.zero_done, rneed,
-                      zr, n_zr, gw, n_gw, lane);
-        zknown = rneed;
-      }
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+      ikz_service(p.zplan, &ws.ikz, 1, mx, gw, n_gw, lane);
     }
 
 #pragma unroll 1
@@ -891,11 +941,16 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
         stage_tiles_g(ws.E, gacc, lane);
         __syncwarp();
         double v[2][9];
+#if A2DS_GEO_MMA
         geo_blocks_mma(gm, wk, lane, v);
+#endif
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           int pr, pc;
           geo_pair(lane, e, pr, pc);
+#if !A2DS_GEO_MMA
+          geo_block_t(gm, wk, pr, pc, v[e]);
+#endif
           const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
 #pragma unroll
           for (int i = 0; i < 3; i++)
@@ -922,13 +977,15 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       }
       __syncwarp();
     }
-    drawn = __shfl_sync(FULL, drawn, 0);
-    grp = grp_nxt; grp_nxt = drawn;
+    if constexpr (CS) {
+      base_cur = base_nxt; grp = grp_nxt;
+    } else {
+      drawn = __shfl_sync(FULL, drawn, 0);
+      grp = grp_nxt; grp_nxt = drawn;
+    }
   }
   // rounds this warp has not reached yet (short lists, warps without a batch)
-  if (n_zr > 0 && zr < n_zr)
-    ikz_rounds(p.zeroK, p.zero_nK, p.zero_cK, p.zeroG, p.zero_nG, p.zero_cG, p.zero_done, zr, n_zr, gw,
-               n_gw, lane);
+  if (ikz) ikz_service(p.zplan, &ws.ikz, 2, 0, gw, n_gw, lane);
 }
 
 // ---- mass path (gamma terms of assembleJacobian, TACS_MASS_MATRIX, inertial residual) ----
