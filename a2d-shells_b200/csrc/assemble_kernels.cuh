@@ -464,6 +464,16 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
 // blocks are added), so there is no second staging tile.  Components without
 // membrane-bending coupling only (run_assembly sends coupled ones to k_assemble).
 // =====================================================================================
+// Staging tile of k_assemble_t: the 24 x 24 element matrix as 4 x 4 node-pair blocks of 36
+// doubles in their BCSR order, block (bi, bj) at ET_R * bi + ET_C * bj.  ET_C = 36 = 4 (mod 16)
+// and ET_R = 145 = 1 (mod 16) make every access pattern of the kernel conflict free on the 16
+// 8-byte banks a half-warp touches: the MMA accumulator stores (lane = (c, q): block row c >> 1,
+// block column q), the scatter (32 consecutive entries of a block; 4 tail entries of 4 blocks)
+// and the geometric pass (16 node pairs (a, b) of one u/d class per half-warp).
+static const int ET_R = 145, ET_C = 36, ET_SIZE = 3 * ET_R + 3 * ET_C + 36;
+__device__ __forceinline__ int et_at(int bi, int rr, int bj, int cc) {
+  return ET_R * bi + ET_C * bj + 6 * rr + cc;
+}
 // in-kernel zeroing of the output matrices: plan and per-warp state (see ikz_service)
 struct ZeroPlan {
   double2 *zK, *zG;        // arrays to zero (null: none)
@@ -485,6 +495,9 @@ struct IkzState {          // per warp, in shared memory
 #ifndef A2DS_CTA_SYNC
 #define A2DS_CTA_SYNC 1
 #endif
+#ifndef A2DS_ELEM_SYNC
+#define A2DS_ELEM_SYNC 0
+#endif
 struct BatchTmp {   // node-phase outputs only the Gauss-point phase reads; overlaid on the staging
   double dr[12], etn[4], pad_[4];   // tile E, which is only live inside the per-element loop
 };                  // 20 doubles = 4 (mod 16)
@@ -495,14 +508,14 @@ struct ElemRecT {   // ElemRec without the batch-phase-only arrays
   double fn[12], wn[12], cdr[36];
   NodeTab t0[4], t1[4];
   QpRec qp[4];
-  double pad_[12];  // 532 doubles = 4 (mod 16): the 16 (element, point) lanes hit 16 banks
+  double pad_[12];  // 548 doubles = 4 (mod 16): the 16 (element, point) lanes hit 16 banks
 };
 struct WarpScratchT {
   RawBatch raw0;
   int nodes[NB][4];
   ElemRecT rec[NB];
   union {
-    double E[24 * KE_LD];   // staging of a 24x24 element matrix for the scatter
+    double E[ET_SIZE];      // staging tile (block-major, see et_at)
     BatchTmp tmp[NB];
   };
   TyWork work;
@@ -510,7 +523,7 @@ struct WarpScratchT {
   RawBatch raw1;            // double buffer: batch i+1 lands (cp.async) while batch i is processed
   alignas(16) int goff[2][NB][16];
 };
-static_assert(sizeof(BatchTmp) * NB <= sizeof(double) * 24 * KE_LD, "batch inputs overlay E");
+static_assert(sizeof(BatchTmp) * NB <= sizeof(double) * ET_SIZE, "batch inputs overlay E");
 // block-shared part of the dynamic shared memory, in front of the per-warp scratch: the plans of
 // the 45 entries of H_tt (Gauss-point weights and slots; constant)
 struct BlockSharedT {
@@ -527,22 +540,52 @@ struct RecView {
   const QpRec *qp;
 };
 
-__device__ __forceinline__ void stage_tiles_g(double *E, const double (&acc)[6][2], int lane) {
-  const int rowb = 3 * (lane >> 2), colb = 6 * (lane & 3);
+// MMA accumulators of the 6 upper tiles -> staging tile (lower tiles mirrored).  Lane (c, q)
+// holds K[3 c + ti][6 q + tj] and K[3 c + ti][6 q + 3 + tj]: block (c >> 1, q).
+template <bool SCALE>
+__device__ __forceinline__ void stage_tiles_t(double *E, const double (&acc)[6][2], double scale,
+                                              int lane) {
+  const int c = lane >> 2, q = lane & 3;
+  const int up = ET_R * (c >> 1) + ET_C * q + 18 * (c & 1);        // + 6 ti + tj (+3)
+  const int lo = ET_R * q + ET_C * (c >> 1) + 3 * (c & 1);         // + 6 tj (+18) + ti
   int idx = 0;
 #pragma unroll
   for (int ti = 0; ti < 3; ti++)
 #pragma unroll
     for (int tj = ti; tj < 3; tj++, idx++) {
-      const int row = rowb + ti, col0 = colb + tj, col1 = colb + 3 + tj;
-      E[row * KE_LD + col0] = acc[idx][0];
-      E[row * KE_LD + col1] = acc[idx][1];
-      if (ti != tj) {   // off-diagonal tiles already hold Z + Z^T: mirror
-        E[col0 * KE_LD + row] = acc[idx][0];
-        E[col1 * KE_LD + row] = acc[idx][1];
+      const double a0 = SCALE ? scale * acc[idx][0] : acc[idx][0];
+      const double a1 = SCALE ? scale * acc[idx][1] : acc[idx][1];
+      E[up + 6 * ti + tj] = a0;
+      E[up + 6 * ti + 3 + tj] = a1;
+      if (ti != tj) {
+        E[lo + 6 * tj + ti] = a0;
+        E[lo + 6 * (3 + tj) + ti] = a1;
       }
     }
 }
+// scatter of the staged blocks: as scatter_matrix, on the block-major tile
+__device__ __forceinline__ void scatter_matrix_t(const double *E, double *vals, int off16, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const int tb = lane >> 2;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    double v0[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int b = 8 * half + k;
+      v0[k] = E[ET_R * (b >> 2) + ET_C * (b & 3) + lane];
+    }
+    const double v1 = E[ET_R * (2 * half + (tb >> 2)) + ET_C * (tb & 3) + 32 + (lane & 3)];
+    const int offt = __shfl_sync(FULL, off16, 8 * half + tb);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int off = __shfl_sync(FULL, off16, 8 * half + k);
+      atomicAdd(vals + 36 * (size_t)off + lane, v0[k]);
+    }
+    atomicAdd(vals + 36 * (size_t)offt + 32 + (lane & 3), v1);
+  }
+}
+
 
 // ---- zeroing of the output matrices inside k_assemble_t ------------------------------------
 // Instead of a memset in front of the kernel (5.2 GB written, evicted, and read back by the
@@ -641,12 +684,15 @@ __device__ __noinline__ void ikz_service(const ZeroPlan *zp, IkzState *stp, int 
 // are one m8n8k4 MMA per Gauss point: A = the coefficient 4-vectors of the 8 generalised nodes,
 // B = Sigma4 times them.  Lane (row = lane >> 2, j = lane & 3) ends up with the pairs
 // (p, pp) = (row, 2 j) and (row, 2 j + 1).
-// generalised node pair e (0, 1) of a lane in the geometric phase
+// generalised node pair e (0, 1) of a lane in the geometric phase.  Scalar path: a half-warp
+// takes the 16 node pairs (a, b) of ONE class (u-u, u-d, d-u, d-d), which are 16 different
+// banks of the staging tile (and a uniform fold branch per half-warp)
 __device__ __forceinline__ void geo_pair(int lane, int e, int &pr, int &pc) {
 #if A2DS_GEO_MMA
   pr = lane >> 2; pc = 2 * (lane & 3) + e;         // accumulator layout of the MMA
 #else
-  const int pair = lane + 32 * e; pr = pair >> 3; pc = pair & 7;
+  const int g = 2 * e + (lane >> 4);
+  pr = (lane & 3) + 4 * (g >> 1); pc = ((lane >> 2) & 3) + 4 * (g & 1);
 #endif
 }
 template <class Rec>
@@ -832,7 +878,13 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
     }
 
 #pragma unroll 1
-    for (int j = 0; j < cnt; j++) {
+    for (int j = 0; j < (A2DS_ELEM_SYNC && CS ? NB : cnt); j++) {
+#if A2DS_ELEM_SYNC
+      if constexpr (CS) {
+        __syncthreads();
+        if (j >= cnt) continue;
+      }
+#endif
       const ElemRecT &rc = ws.rec[j];
       RecView gm;
       gm.fn = rc.fn; gm.wn = rc.wn; gm.cdr = rc.cdr; gm.t0 = rc.t0; gm.t1 = rc.t1; gm.qp = rc.qp;
@@ -875,7 +927,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
 #pragma unroll
             for (int tj = ti; tj < 3; tj++, idx++) dmma884(kacc[idx], f.B[ks][ti], f.W[ks][tj]);
         }
-        stage_tiles(ws.E, kacc, p.alpha, lane);
+        stage_tiles_t<true>(ws.E, kacc, p.alpha, lane);
       }
       double gacc[6][2];
       if (GMAT) {
@@ -913,11 +965,11 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
           for (int e = 0; e < 2; e++) {
             int pr, pc;
             geo_pair(lane, e, pr, pc);
-            const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+            const int at = et_at(pr & 3, 3 * (pr >> 2), pc & 3, 3 * (pc >> 2));
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
-              for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] += p.alpha * blk[e][3 * i + jj];
+              for (int jj = 0; jj < 3; jj++) ws.E[at + 6 * i + jj] += p.alpha * blk[e][3 * i + jj];
           }
           __syncwarp();
         }
@@ -929,16 +981,16 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
 #pragma unroll
           for (int k = 0; k < 24; k++) {
             const double xk = __shfl_sync(FULL, xv, k);
-            if (lane < 24) y += ws.E[lane * KE_LD + k] * xk;
+            if (lane < 24) y += ws.E[et_at(lane / 6, lane % 6, k / 6, k % 6)] * xk;
           }
           if (lane < 24) atomicAdd(&p.jvp_y[6 * (size_t)node + lane % 6], p.jvp_scale * y);
         } else {
-          scatter_matrix(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
+          scatter_matrix_t(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
         }
       }
       if (GMAT) {
         if (KMAT) __syncwarp();   // E is reused for G once K has left
-        stage_tiles_g(ws.E, gacc, lane);
+        stage_tiles_t<false>(ws.E, gacc, 1.0, lane);
         __syncwarp();
         double v[2][9];
 #if A2DS_GEO_MMA
@@ -951,13 +1003,14 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
 #if !A2DS_GEO_MMA
           geo_block_t(gm, wk, pr, pc, v[e]);
 #endif
-          const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+          const int at = et_at(pr & 3, 3 * (pr >> 2), pc & 3, 3 * (pc >> 2));
+          const int tr = et_at(pc & 3, 3 * (pc >> 2), pr & 3, 3 * (pr >> 2));   // transposed block
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int jj = 0; jj < 3; jj++) {
-              double z = ws.E[(r0 + i) * KE_LD + c0 + jj];
-              if (i == jj) z += ws.E[(c0 + jj) * KE_LD + r0 + i];   // diagonal tiles: Z + Z^T
+              double z = ws.E[at + 6 * i + jj];
+              if (i == jj) z += ws.E[tr + 6 * jj + i];   // diagonal tiles: Z + Z^T
               v[e][3 * i + jj] = p.gscale * (v[e][3 * i + jj] + z);
             }
         }
@@ -966,14 +1019,14 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
         for (int e = 0; e < 2; e++) {
           int pr, pc;
           geo_pair(lane, e, pr, pc);
-          const int r0 = 6 * (pr & 3) + (pr >= 4 ? 3 : 0), c0 = 6 * (pc & 3) + (pc >= 4 ? 3 : 0);
+          const int at = et_at(pr & 3, 3 * (pr >> 2), pc & 3, 3 * (pc >> 2));
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int jj = 0; jj < 3; jj++) ws.E[(r0 + i) * KE_LD + c0 + jj] = v[e][3 * i + jj];
+            for (int jj = 0; jj < 3; jj++) ws.E[at + 6 * i + jj] = v[e][3 * i + jj];
         }
         __syncwarp();
-        scatter_matrix(ws.E, p.Gval, goffb[j][lane & 15], lane);
+        scatter_matrix_t(ws.E, p.Gval, goffb[j][lane & 15], lane);
       }
       __syncwarp();
     }

@@ -47,6 +47,7 @@ static const int TY_ROWS = 7; // k-steps of the tangent contraction (6 for B1: n
 struct NodeTab {
   double gm[10];    // h = 0 only: g11 row (3), g22 row (3), g12 row (3), pad
   double gs[2][6];  // [h]: g13 row (3), g23 row (3)
+  double pad_[2];   // 24 doubles: the (node, h) pairs a half-warp reads fall into distinct banks
 };
 
 // Per Gauss point record (written by phase_qp_t, one lane per Gauss point)
