@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       __syncthreads();
       base_nxt = bs.draw[(trip + 1) & 1];   // drawn one trip ago (or in the prologue)
       grp_nxt = base_nxt + warp;
-      if (threadIdx.x == 0) bs.draw[trip & 1] = atomicAdd(p.work_counter, wpb);   // for trip + 2
+      if (threadIdx.x == 0) drawn = atomicAdd(p.work_counter, wpb);   // for trip + 2, stored at the end
     } else {
       if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
     }
@@ -877,6 +877,21 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       ikz_service(p.zplan, &ws.ikz, 1, mx, gw, n_gw, lane);
     }
 
+    // element prologue: H_tt (45 entries over 32 lanes: Gauss-point sums of Q) and the tying
+    // stresses.  A pure latency chain (plan -> Q -> 4 FMA -> store); it is issued for element
+    // j + 1 right before the last scatter of element j, whose REDs cover it.
+    auto prologue = [&](int jn) {
+      const ElemRecT &rn = ws.rec[jn];
+      RecView gn;
+      gn.fn = rn.fn; gn.wn = rn.wn; gn.cdr = rn.cdr; gn.t0 = rn.t0; gn.t1 = rn.t1; gn.qp = rn.qp;
+      if (KMAT || GMAT) {
+        ty_H_entry(gn, bs.plan[lane], wk.H);
+        if (lane + 32 < 45) ty_H_entry(gn, bs.plan[lane + 32], wk.H);
+      }
+      if ((RES || need_state) && lane < 9) ty_sum_stress(gn, wk, lane);
+    };
+    if (cnt > 0) prologue(0);
+    __syncwarp();
 #pragma unroll 1
     for (int j = 0; j < (A2DS_ELEM_SYNC && CS ? NB : cnt); j++) {
 #if A2DS_ELEM_SYNC
@@ -888,13 +903,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       const ElemRecT &rc = ws.rec[j];
       RecView gm;
       gm.fn = rc.fn; gm.wn = rc.wn; gm.cdr = rc.cdr; gm.t0 = rc.t0; gm.t1 = rc.t1; gm.qp = rc.qp;
-      // ---- element prologue: H_tt (45 entries over 32 lanes) and the tying stresses --------
-      if (KMAT || GMAT) {
-        ty_H_entry(gm, bs.plan[lane], wk.H);
-        if (lane + 32 < 45) ty_H_entry(gm, bs.plan[lane + 32], wk.H);
-      }
-      if ((RES || need_state) && lane < 9) ty_sum_stress(gm, wk, lane);
-      __syncwarp();
+      // (H_tt and the tying stresses of this element were formed by `prologue` during the
+      // previous element's scatter — or in front of the loop for the first one)
 
       // ---- column phase: the lane's rows of Bt, W = H Bt (and Bt1) ARE the DMMA fragments ----
       LaneFrag f;
@@ -973,6 +983,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
           }
           __syncwarp();
         }
+        if (!GMAT && j + 1 < cnt) prologue(j + 1);   // covered by the scatter below
         if (NL && !GMAT && p.jvp_x) {
           const int node = ws.nodes[j][(lane / 6) & 3];
           double xv = 0.0;
@@ -1026,11 +1037,15 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
             for (int jj = 0; jj < 3; jj++) ws.E[at + 6 * i + jj] = v[e][3 * i + jj];
         }
         __syncwarp();
+        if (j + 1 < cnt) prologue(j + 1);   // H and the tying stresses are free from here on
         scatter_matrix_t(ws.E, p.Gval, goffb[j][lane & 15], lane);
       }
+      if (!GMAT && !KMAT && j + 1 < cnt) prologue(j + 1);
       __syncwarp();
     }
     if constexpr (CS) {
+      // slot trip & 1 held this trip's base, read by everybody before this trip's barrier
+      if (threadIdx.x == 0) bs.draw[trip & 1] = drawn;
       base_cur = base_nxt; grp = grp_nxt;
     } else {
       drawn = __shfl_sync(FULL, drawn, 0);
