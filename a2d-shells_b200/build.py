@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "lib", "liba2ds_b200.so")
 SRCS = [os.path.join(HERE, "csrc", "a2ds.cu"), os.path.join(HERE, "csrc", "mesh_io.cpp"),
         os.path.join(HERE, "csrc", "partition.cpp")]
-DEPS = SRCS + [os.path.join(HERE, "csrc", "mitc4_math.h"),
+DEPS = SRCS + [os.path.join(HERE, "csrc", "mitc4_math.h"), os.path.join(HERE, "csrc", "mitc4_tying.h"),
                os.path.join(HERE, "csrc", "assemble_kernels.cuh"),
                os.path.join(HERE, "csrc", "aux_kernels.cuh"),
                os.path.join(HERE, "..", "include", "a2ds.h")]

@@ -674,59 +674,82 @@ __device__ __noinline__ void ikz_service(const ZeroPlan *zp, IkzState *stp, int 
 }
 
 #ifndef A2DS_GEO_MMA
-#define A2DS_GEO_MMA 0   // measured: the MMA saves FP64 work but its pair -> lane map stages with more bank conflicts (profiles/README.md)
-#endif
+#define A2DS_GEO_MMA 2   // 0: scalar bending scalars; 1: MMA, pairs in accumulator layout (staging
+#endif                   // conflicts: measured slower); 2: MMA + redistribution through shared memory
 #ifndef A2DS_G_ORDER
 #define A2DS_G_ORDER 1
 #endif
-// The 64 geometric-stiffness blocks of an element, two per lane.  The bending scalars
-//   mq_qp(p, pp) = [a_p; b_p]^T [[0, Sigma], [Sigma, 0]] [a_pp; b_pp]       (8 x 8 per Gauss point)
-// are one m8n8k4 MMA per Gauss point: A = the coefficient 4-vectors of the 8 generalised nodes,
-// B = Sigma4 times them.  Lane (row = lane >> 2, j = lane & 3) ends up with the pairs
-// (p, pp) = (row, 2 j) and (row, 2 j + 1).
 // generalised node pair e (0, 1) of a lane in the geometric phase.  Scalar path: a half-warp
 // takes the 16 node pairs (a, b) of ONE class (u-u, u-d, d-u, d-d), which are 16 different
 // banks of the staging tile (and a uniform fold branch per half-warp)
 __device__ __forceinline__ void geo_pair(int lane, int e, int &pr, int &pc) {
-#if A2DS_GEO_MMA
+#if A2DS_GEO_MMA == 1
   pr = lane >> 2; pc = 2 * (lane & 3) + e;         // accumulator layout of the MMA
 #else
   const int g = 2 * e + (lane >> 4);
   pr = (lane & 3) + 4 * (g >> 1); pc = ((lane >> 2) & 3) + 4 * (g & 1);
 #endif
 }
+// The bending scalars of the geometric stiffness,
+//   mq_qp(p, pp) = [a_p; b_p]^T [[0, Sigma], [Sigma, 0]] [a_pp; b_pp]       (8 x 8 per Gauss point),
+// as one m8n8k4 MMA per Gauss point: A = the coefficient 4-vectors of the 8 generalised nodes,
+// B = Sigma4 times them.  Lane (row = lane >> 2, k = lane & 3) receives mq(row, 2 k), mq(row, 2 k + 1).
 template <class Rec>
-__device__ __forceinline__ void geo_blocks_mma(const Rec &gm, const TyWork &wk, int lane,
-                                               double blk[2][9]) {
+__device__ __forceinline__ void geo_mq_mma(const Rec &gm, const TyWork &wk, int lane, double (&acc)[4][2]) {
   const int row = lane >> 2, k = lane & 3;
-#if !A2DS_GEO_MMA
-#pragma unroll
-  for (int e = 0; e < 2; e++) {
-    int pr, pc;
-    geo_pair(lane, e, pr, pc);
-    geo_block_t(gm, wk, pr, pc, blk[e]);
-  }
-  return;
-#endif
   // ca / cb are adjacent [4][8][2] arrays: lane offsets once, the Gauss point is an immediate
   const double *cab = &wk.ca[0][0][0];
   const int offA = 64 * (k >> 1) + 2 * row + (k & 1);   // (k < 2 ? ca : cb)[.][row][k & 1]
   const int offC = 64 * (1 - (k >> 1)) + 2 * row;       // (k < 2 ? cb : ca)[.][row][0..1]
   const int sa = 2 * (k & 1), sb = 2 - (k & 1);         // (s3, s5) or (s5, s4) of (w s3, w s4, w s5)
-  double mq[4][2];
 #pragma unroll
   for (int qp = 0; qp < 4; qp++) {
     const double a = cab[offA + 16 * qp];
     const double *sg = gm.qp[qp].sg;
     const double b = sg[sa] * cab[offC + 16 * qp] + sg[sb] * cab[offC + 16 * qp + 1];
-    mq[qp][0] = mq[qp][1] = 0.0;
-    dmma884(mq[qp], a, b);
+    acc[qp][0] = acc[qp][1] = 0.0;
+    dmma884(acc[qp], a, b);
   }
+}
+// The 64 geometric-stiffness blocks of an element, two per lane (pairs: geo_pair).
+template <class Rec>
+__device__ __forceinline__ void geo_mq(const Rec &gm, TyWork &wk, int lane, double (&mq)[2][4]) {
+#if A2DS_GEO_MMA == 1
+  double acc[4][2];
+  geo_mq_mma(gm, wk, lane, acc);
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int qp = 0; qp < 4; qp++) mq[e][qp] = acc[qp][e];
+#elif A2DS_GEO_MMA == 2
+  // MMA, then through shared memory into the class-wise pair map of the staging pass; the
+  // scratch overlays H, ca, cb (consumed: H by the column phase, ca / cb by the MMA fragments)
+  double acc[4][2];
+  geo_mq_mma(gm, wk, lane, acc);
+  double *mqs = &wk.H[0];                  // [qp][p][pp], 256 doubles
+  __syncwarp();                            // every lane has read its fragments
+  const int row = lane >> 2, k = lane & 3;
+#pragma unroll
+  for (int qp = 0; qp < 4; qp++)
+    *reinterpret_cast<double2 *>(&mqs[64 * qp + 8 * row + 2 * k]) = make_double2(acc[qp][0], acc[qp][1]);
+  __syncwarp();
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    const double m4[4] = {mq[0][e], mq[1][e], mq[2][e], mq[3][e]};
-    geo_block_from_mq(gm, wk, row, 2 * k + e, m4, blk[e]);
+    int pr, pc;
+    geo_pair(lane, e, pr, pc);
+#pragma unroll
+    for (int qp = 0; qp < 4; qp++) mq[e][qp] = mqs[64 * qp + 8 * pr + pc];
   }
+#else
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    int pr, pc;
+    geo_pair(lane, e, pr, pc);
+#pragma unroll
+    for (int qp = 0; qp < 4; qp++)
+      mq[e][qp] = geo_bending_mq(wk.ca[qp][pr], wk.cb[qp][pr], wk.ca[qp][pc], wk.cb[qp][pc], gm.qp[qp].sg);
+  }
+#endif
 }
 
 template <bool RES, bool KMAT, bool GMAT, bool NL>
@@ -887,6 +910,10 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       if (KMAT || GMAT) {
         ty_H_entry(gn, bs.plan[lane], wk.H);
         if (lane + 32 < 45) ty_H_entry(gn, bs.plan[lane + 32], wk.H);
+#if A2DS_GEO_MMA == 2
+        // the geometric phase used H as scratch: restore its zero row / column
+        if (need_state && lane < TY_LD) { wk.H[TY_LD * 9 + lane] = 0.0; wk.H[TY_LD * lane + 9] = 0.0; }
+#endif
       }
       if ((RES || need_state) && lane < 9) ty_sum_stress(gn, wk, lane);
     };
@@ -969,12 +996,13 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       __syncwarp();   // E staged; coefficient pairs of the geometric phase published
       if (KMAT) {
         if (NL) {
-          double blk[2][9];
-          geo_blocks_mma(gm, wk, lane, blk);
+          double blk[2][9], mq[2][4];
+          geo_mq(gm, wk, lane, mq);
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             int pr, pc;
             geo_pair(lane, e, pr, pc);
+            geo_block_from_mq(gm, wk, pr, pc, mq[e], blk[e]);
             const int at = et_at(pr & 3, 3 * (pr >> 2), pc & 3, 3 * (pc >> 2));
 #pragma unroll
             for (int i = 0; i < 3; i++)
@@ -1003,17 +1031,13 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
         if (KMAT) __syncwarp();   // E is reused for G once K has left
         stage_tiles_t<false>(ws.E, gacc, 1.0, lane);
         __syncwarp();
-        double v[2][9];
-#if A2DS_GEO_MMA
-        geo_blocks_mma(gm, wk, lane, v);
-#endif
+        double v[2][9], mq[2][4];
+        geo_mq(gm, wk, lane, mq);
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           int pr, pc;
           geo_pair(lane, e, pr, pc);
-#if !A2DS_GEO_MMA
-          geo_block_t(gm, wk, pr, pc, v[e]);
-#endif
+          geo_block_from_mq(gm, wk, pr, pc, mq[e], v[e]);
           const int at = et_at(pr & 3, 3 * (pr >> 2), pc & 3, 3 * (pc >> 2));
           const int tr = et_at(pc & 3, 3 * (pc >> 2), pr & 3, 3 * (pr >> 2));   // transposed block
 #pragma unroll

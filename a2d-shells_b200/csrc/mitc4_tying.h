@@ -74,10 +74,12 @@ struct ElemRec {
 };
 
 // per element working set of the column phase (one per warp)
-struct TyWork {
-  double H[TY_LD * TY_LD];          // H_tt (9 x 9) + zero row / column
+struct alignas(16) TyWork {
   double sigt[TY_LD];               // tying-point stresses summed over the Gauss points
+  double H[TY_LD * TY_LD];          // H_tt (9 x 9) + zero row / column
   double ca[4][8][2], cb[4][8][2];  // geometric phase: coefficient pairs per Gauss point, gen. node
+  double pad_[28];                  // H .. pad_ = 256 doubles: scratch of the geometric phase (mq of
+                                    // the 64 node pairs x 4 Gauss points), once H, ca, cb are consumed
 };
 
 // g5 component (g11=0, g12=1, g13=2, g22=3, g23=4) of tying index t, 3 bits each
