@@ -26,6 +26,7 @@ SYMBOLS = [
     "a2ds_mat_download", "a2ds_mat_values_dev", "a2ds_mat_download_rows", "a2ds_assemble_res", "a2ds_assemble_jacobian",
     "a2ds_assemble_mat_type", "a2ds_assemble_all", "a2ds_res_dev", "a2ds_state_dev",
     "a2ds_comm_unique_id", "a2ds_comm_init", "a2ds_set_halo", "a2ds_halo_forward",
+    "a2ds_halo_from_distribute",
     "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
     "a2ds_last_kernel_ms", "a2ds_region_begin", "a2ds_region_end",
     "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
@@ -232,6 +233,29 @@ class Mesh:
             self.close()
         except Exception:
             pass
+
+
+def halo_from_distribute(lo, n_owned, ext_proc, ext_ptr, ext_count, req_proc, req_ptr, req_count,
+                         req_vars):
+    """TACSBVecDistribute's slab lists (global node numbers) -> (peers, send_lists, recv_lists)
+    in the device path's local numbering, as a2ds_set_halo takes them (host only)"""
+    L = load_library()
+    ext_proc, ext_ptr, ext_count = _i32(ext_proc), _i32(ext_ptr), _i32(ext_count)
+    req_proc, req_ptr, req_count, req_vars = _i32(req_proc), _i32(req_ptr), _i32(req_count), _i32(req_vars)
+    nmax = len(ext_proc) + len(req_proc)
+    peers = np.zeros(max(nmax, 1), dtype=np.int32)
+    sp = np.zeros(nmax + 1, dtype=np.int32); rp = np.zeros(nmax + 1, dtype=np.int32)
+    sn = np.zeros(max(int(req_count.sum()), 1), dtype=np.int32)
+    rn = np.zeros(max(int(ext_count.sum()), 1), dtype=np.int32)
+    n = C.c_int()
+    if L.a2ds_halo_from_distribute(C.c_int(lo), C.c_int(n_owned), C.c_int(len(ext_proc)), _p(ext_proc),
+                                   _p(ext_ptr), _p(ext_count), C.c_int(len(req_proc)), _p(req_proc),
+                                   _p(req_ptr), _p(req_count), _p(req_vars), C.byref(n), _p(peers),
+                                   _p(sp), _p(sn), _p(rp), _p(rn)):
+        raise A2dsError(L.a2ds_last_error().decode())
+    k = n.value
+    return (peers[:k].copy(), [sn[sp[i]:sp[i + 1]].copy() for i in range(k)],
+            [rn[rp[i]:rp[i + 1]].copy() for i in range(k)])
 
 
 def partition_rcb(conn, X, n_ranks):

@@ -1135,7 +1135,7 @@ extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
 }
 
 // ---- assembly ------------------------------------------------------------------
-static const int MAX_ZERO_ROUNDS = 4096;   // rounds of the in-kernel zeroing (k_assemble_t)
+static const int MAX_ZERO_ROUNDS = 4096;   // rounds of the in-kernel zeroing (see ZeroPlan)
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_one(a2ds_ctx *c, KParams &p) {
   const size_t raw = (GMAT || NL) ? sizeof(WarpScratch) : offsetof(WarpScratch, E2);
@@ -1215,17 +1215,17 @@ static int launch_one_t(a2ds_ctx *c, KParams &p) {
   p.zplan = nullptr;
   int rounds = 0;
   if (c->pz_K || c->pz_G) {
-    // in-kernel zeroing (see ikz_service): about one round per trip of a warp
+    // in-kernel zeroing by rounds (see ZeroPlan): about one round per trip of a warp
     static const int ahead = getenv("A2DS_ZERO_AHEAD") ? atoi(getenv("A2DS_ZERO_AHEAD")) : 3;
     const int n_gw = grid * wpb;
     rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / n_gw));
     ZeroPlan zp;
-    zp.zK = (double2 *)c->pz_K; zp.nK = c->pz_nK;
-    zp.zG = (double2 *)c->pz_G; zp.nG = c->pz_nG;
+    zp.zK = (double2 *)c->pz_K; zp.nK = 18ll * c->pz_nK;
+    zp.zG = (double2 *)c->pz_G; zp.nG = 18ll * c->pz_nG;
     const long long per_round = (long long)rounds * n_gw;
     // whole blocks per chunk (18 double2 each)
-    zp.cK = 18 * (int)std::max<long long>(1, (c->pz_nK / 18 + per_round - 1) / per_round);
-    zp.cG = 18 * (int)std::max<long long>(1, (c->pz_nG / 18 + per_round - 1) / per_round);
+    zp.cK = 18 * (int)std::max<long long>(1, (c->pz_nK + per_round - 1) / per_round);
+    zp.cG = 18 * (int)std::max<long long>(1, (c->pz_nG + per_round - 1) / per_round);
     // the kernel takes ONE round index from the highest offset of both matrices: use the
     // smaller chunk (round boundaries in blocks)
     const double bpr = (double)n_gw * (double)(std::min(zp.zK ? zp.cK : zp.cG, zp.zG ? zp.cG : zp.cK) / 18);
@@ -1331,16 +1331,12 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     int first_cls = -1;
     for (int cls = 0; cls < 4 && first_cls < 0; cls++)
       if (c->list_len[cls][0] > 0) first_cls = cls;
-#ifndef A2DS_IKZ
-    const bool ikz_built = false;   // experimental, see assemble_kernels.cuh
-#else
-    const bool ikz_built = true;
-#endif
+    const bool ikz_built = A2DS_ZWAIT != 0;   // zero blocks compiled into k_assemble_t
     const bool ikz = ikz_built && ikz_env && !first_form && c->n_colors == 1 && (KM || GM) && first_cls >= 0 &&
                      first_cls < 2 && (what == 2 || what == 3 || what == 4 || what == 7);
     if (ikz) {
-      if (KM) { c->pz_K = c->mats[kmat].A; c->pz_nK = c->mats[kmat].total * 18; }
-      if (GM) { c->pz_G = c->mats[gmat].A; c->pz_nG = c->mats[gmat].total * 18; }
+      if (KM) { c->pz_K = c->mats[kmat].A; c->pz_nK = c->mats[kmat].total; }
+      if (GM) { c->pz_G = c->mats[gmat].A; c->pz_nG = c->mats[gmat].total; }
     } else {
       if (KM) CU(cudaMemsetAsync(c->mats[kmat].A, 0, c->mats[kmat].total * 36 * sizeof(double), c->stream));
       if (GM) CU(cudaMemsetAsync(c->mats[gmat].A, 0, c->mats[gmat].total * 36 * sizeof(double), c->stream));

@@ -41,8 +41,8 @@ struct KParams {
   double jvp_scale;
   int scratch_bytes;
   int *work_counter;     // dynamic batch scheduling: next batch index (zeroed per launch)
-  // in-kernel zeroing of the output matrices (k_assemble_t, cooperative launch): plan in device
-  // memory, null when the caller zeroed the matrices (see ikz_service)
+  // zeroing of the output matrices inside k_assemble_t (cooperative launch; null: the caller
+  // zeroed them): see ZeroPlan
   const struct ZeroPlan *zplan;
 };
 
@@ -474,20 +474,30 @@ static const int ET_R = 145, ET_C = 36, ET_SIZE = 3 * ET_R + 3 * ET_C + 36;
 __device__ __forceinline__ int et_at(int bi, int rr, int bj, int cc) {
   return ET_R * bi + ET_C * bj + 6 * rr + cc;
 }
-// in-kernel zeroing of the output matrices: plan and per-warp state (see ikz_service)
+// ---- zeroing of the output matrices inside k_assemble_t -------------------------------------
+// A memset in front of the kernel writes 5.2 GB of zeros that are evicted to DRAM and read back
+// by the first RED of every block (0.8 ms of a 5.8 ms step, 3 x the algorithmic traffic).
+// Instead every warp zeroes ONE small chunk per trip, a few rounds ahead of where the element
+// batches drawn at that time scatter: round r = chunk r of every warp = one contiguous slice of
+// the value arrays (zeroing needs the store bandwidth of ALL SMs: a few dedicated zero blocks
+// reach only ~30 GB/s each, measured).  The stores are issued at the top of a trip and
+// published after the batched phases (bar.warp.sync + red.release.gpu on done[r]: by then the
+// warp's earlier REDs and these stores have long drained, so the release costs nothing).
+// Before a batch scatters, the warp checks that the round its highest block offset falls into
+// has been zeroed by ALL warps (done[r] == number of warps, acquire; rounds complete in order
+// per warp, the last check is cached).  A warp that has to wait zeroes ahead instead of idling,
+// so the scheme cannot deadlock for any element order (without locality it degenerates to
+// zeroing everything first).  All warps are co-resident (cooperative launch).
+// The zeros are still in L2 when the REDs arrive: nothing is read from DRAM and every block is
+// written to DRAM once.  No __threadfence(), no call: either one, merely present in the
+// kernel, costs every variant 15-17 % (measured; profiles/README.md).
 struct ZeroPlan {
   double2 *zK, *zG;        // arrays to zero (null: none)
   long long nK, nG;        // lengths in double2 units
   int cK, cG;              // chunk of one warp in one round (double2 units, whole blocks)
   float inv_round;         // 1 / (blocks per round)
   int rounds, ahead;       // number of rounds; rounds zeroed before the first batch
-  int *done;               // per round: number of warps that have zeroed and fenced
-};
-struct IkzState {          // per warp, in shared memory
-  int stored;              // rounds whose stores have been issued
-  int published;           // rounds fenced and counted in done[]
-  int known;               // highest round known to be complete on all warps
-  int pad_;
+  int *done;               // per round: number of warps that have zeroed it
 };
 #ifndef A2DS_MB_T
 #define A2DS_MB_T 2
@@ -498,6 +508,9 @@ struct IkzState {          // per warp, in shared memory
 #ifndef A2DS_ELEM_SYNC
 #define A2DS_ELEM_SYNC 0
 #endif
+#ifndef A2DS_ZWAIT
+#define A2DS_ZWAIT 0   // 1: zeroing of the output matrices inside k_assemble_t (see ZeroPlan).  Built
+#endif                 // and measured, not faster than the memsets it replaces (profiles/README.md): off
 struct BatchTmp {   // node-phase outputs only the Gauss-point phase reads; overlaid on the staging
   double dr[12], etn[4], pad_[4];   // tile E, which is only live inside the per-element loop
 };                  // 20 doubles = 4 (mod 16)
@@ -519,7 +532,6 @@ struct WarpScratchT {
     BatchTmp tmp[NB];
   };
   TyWork work;
-  IkzState ikz;
   RawBatch raw1;            // double buffer: batch i+1 lands (cp.async) while batch i is processed
   alignas(16) int goff[2][NB][16];
 };
@@ -527,6 +539,7 @@ static_assert(sizeof(BatchTmp) * NB <= sizeof(double) * ET_SIZE, "batch inputs o
 // block-shared part of the dynamic shared memory, in front of the per-warp scratch: the plans of
 // the 45 entries of H_tt (Gauss-point weights and slots; constant)
 struct BlockSharedT {
+  alignas(16) double zero_src[128];   // source of the bulk copies that zero the matrices (ZeroPlan)
   TyPlan plan[45];
   int draw[2];   // block-synchronous scheduling: first batch of the block in trips t, t + 1
   int pad_[2];
@@ -587,90 +600,37 @@ __device__ __forceinline__ void scatter_matrix_t(const double *E, double *vals, 
 }
 
 
-// ---- zeroing of the output matrices inside k_assemble_t ------------------------------------
-// Instead of a memset in front of the kernel (5.2 GB written, evicted, and read back by the
-// first RED of every block), every warp zeroes ONE chunk per trip, a few rounds ahead of where
-// the element batches drawn at that time scatter: round r = chunk r of every warp = one
-// contiguous slice of the value arrays.  Once per trip, after the batched phases (when the
-// warp's earlier REDs have long drained, so the fence is cheap), a warp calls ikz_service:
-// it publishes the round it stored a trip ago (fence + counter), stores the next one, and
-// checks that the round the batch's highest block offset falls into has been zeroed by ALL
-// warps (done[r] == number of warps; rounds complete in order per warp).  A warp that has to
-// wait zeroes ahead instead of spinning idle, so the scheme cannot deadlock and degenerates to
-// "zero everything first" for element orders without locality.  All warps are co-resident
-// (cooperative launch).  Out of line, state in shared memory, plan in device memory: the hot
-// loops carry no register for it.
-__device__ __forceinline__ void ikz_zero_chunk(double2 *zb, long long n2, int c2, int r, int gw,
-                                               int n_gw, int lane) {
+// one chunk (round r, warp gw) of one value array (see ZeroPlan), written by the TMA unit from a
+// small zeroed shared-memory buffer (bulk copies issued by lane 0): plain stores of 21 KB per
+// trip hold the warp ~3 us at the LSU (measured: in-kernel zeroing then costs what the memset
+// did), bulk copies cost it a dozen instructions
+static const int ZERO_SRC_BYTES = 1024;
+__device__ __forceinline__ void zero_chunk(double2 *zb, long long n2, int c2, int r, int gw, int n_gw,
+                                           unsigned src) {
   if (!zb) return;
   const long long s0 = ((long long)r * n_gw + gw) * c2;
   const long long left = n2 - s0;
-  const int len = left < c2 ? (left > 0 ? (int)left : 0) : c2;
-  double2 *q = zb + s0;
-#pragma unroll 4
-  for (int i = lane; i < len; i += 32) q[i] = make_double2(0.0, 0.0);
-}
-__device__ __forceinline__ void ikz_publish(const ZeroPlan &z, IkzState &st, int lane) {
-  if (st.published < st.stored) {
-    __threadfence();
-    __syncwarp();
-    if (lane == 0)
-      for (int r = st.published; r < st.stored; r++) atomicAdd(&z.done[r], 1);
-    __syncwarp();
-    if (lane == 0) st.published = st.stored;
-    __syncwarp();
+  int bytes = 16 * (left < c2 ? (left > 0 ? (int)left : 0) : c2);
+  unsigned char *dst = reinterpret_cast<unsigned char *>(zb + s0);
+  while (bytes > 0) {
+    const int n = bytes > ZERO_SRC_BYTES ? ZERO_SRC_BYTES : bytes;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(n) : "memory");
+    dst += n; bytes -= n;
   }
 }
-__device__ __forceinline__ void ikz_store_next(const ZeroPlan &z, IkzState &st, int gw, int n_gw, int lane) {
-  const int r = st.stored;
-  if (r < z.rounds) {
-    ikz_zero_chunk(z.zK, z.nK, z.cK, r, gw, n_gw, lane);
-    ikz_zero_chunk(z.zG, z.nG, z.cG, r, gw, n_gw, lane);
-    __syncwarp();
-    if (lane == 0) st.stored = r + 1;
-    __syncwarp();
+__device__ __forceinline__ void zero_round(const ZeroPlan &z, int r, int gw, int n_gw, unsigned src, int lane) {
+  if (lane == 0) {
+    zero_chunk(z.zK, z.nK, z.cK, r, gw, n_gw, src);
+    zero_chunk(z.zG, z.nG, z.cG, r, gw, n_gw, src);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 }
-// mode 0: kernel start (first `ahead` rounds);  1: once per trip, mx = highest block offset the
-// batch scatters to;  2: kernel end (all remaining rounds)
-__device__ __noinline__ void ikz_service(const ZeroPlan *zp, IkzState *stp, int mode, int mx, int gw,
-                                         int n_gw, int lane) {
-  const ZeroPlan z = *zp;
-  IkzState &st = *stp;
-  if (mode == 0) {
-    if (lane == 0) { st.stored = 0; st.published = 0; st.known = -1; }
-    __syncwarp();
-    for (int r = 0; r < z.ahead && r < z.rounds; r++) ikz_store_next(z, st, gw, n_gw, lane);
-    ikz_publish(z, st, lane);
-    return;
+// round r of this warp is zeroed: wait for the bulk copies, then count it (release)
+__device__ __forceinline__ void zero_publish(int *done, int r, int lane) {
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(done + r) : "memory");
   }
-  if (mode == 2) {
-    while (st.stored < z.rounds) ikz_store_next(z, st, gw, n_gw, lane);
-    ikz_publish(z, st, lane);
-    return;
-  }
-  ikz_publish(z, st, lane);              // the round stored one trip ago
-  ikz_store_next(z, st, gw, n_gw, lane); // stores only
-  // round that must be complete before this batch scatters (rounded up: one round early costs
-  // nothing, one round late is a race)
-  int rneed = (int)((float)mx * z.inv_round) + 1;
-  if (rneed > z.rounds - 1) rneed = z.rounds - 1;
-  if (rneed <= st.known) return;
-  for (;;) {
-    int v = 0;
-    if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(z.done + rneed) : "memory");
-    v = __shfl_sync(0xffffffffu, v, 0);
-    if (v >= n_gw) break;
-    if (st.stored < z.rounds || st.published < st.stored) {   // zero ahead instead of idling
-      ikz_publish(z, st, lane);
-      ikz_store_next(z, st, gw, n_gw, lane);
-      ikz_publish(z, st, lane);
-    } else {
-      __nanosleep(256);
-    }
-  }
-  if (lane == 0) st.known = rneed;
-  __syncwarp();
 }
 
 #ifndef A2DS_GEO_MMA
@@ -766,6 +726,11 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
   const bool need_state = GMAT || NL;
   const int n_groups = (p.n_list + NB - 1) / NB;
   if (threadIdx.x < 45) ty_plan(threadIdx.x, bs.plan[threadIdx.x]);
+#if A2DS_ZWAIT
+  bs.zero_src[threadIdx.x & 127] = 0.0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // read by the async proxy (bulk copies)
+  const unsigned zsrc = (unsigned)__cvta_generic_to_shared(bs.zero_src);
+#endif
   __syncthreads();
   // lane constants of the column phase: opaque, so that they stay in registers across the
   // element loop instead of being recomputed per element
@@ -779,14 +744,21 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
   // zero row / column of H
   if (lane < TY_LD) { wk.H[TY_LD * 9 + lane] = 0.0; wk.H[TY_LD * lane + 9] = 0.0; wk.sigt[lane] = 0.0; }
 
-  // in-kernel zeroing of the output matrices (see ikz_service above)
-#ifdef A2DS_IKZ
-  const bool ikz = p.zplan != nullptr;
-#else
-  const bool ikz = false;   // compiled out: the caller zeroes the matrices
-#endif
+#if A2DS_ZWAIT
+  // zeroing of the output matrices by rounds (see ZeroPlan)
+  const bool zon = p.zplan != nullptr;
   const int gw = blockIdx.x * (blockDim.x >> 5) + warp, n_gw = gridDim.x * (blockDim.x >> 5);
-  if (ikz) ikz_service(p.zplan, &ws.ikz, 0, 0, gw, n_gw, lane);
+  int zr = 0;        // rounds this warp has zeroed (the last one possibly not yet published)
+  int zknown = -1;   // highest round known complete on all warps
+  bool zpend = false;
+  if (zon) {
+    const ZeroPlan z = *p.zplan;
+    for (; zr < z.rounds && zr < z.ahead; zr++) {
+      zero_round(z, zr, gw, n_gw, zsrc, lane);
+      zero_publish(z.done, zr, lane);
+    }
+  }
+#endif
 
   auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
     const int j = (lane >> 2) & (NB - 1);
@@ -858,6 +830,12 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
     }
     const int base = grp * NB;
     const int cnt = grp < n_groups ? min(NB, p.n_list - base) : 0;
+#if A2DS_ZWAIT
+    if (zon && zr < p.zplan->rounds) {   // issued here, published after the batched phases
+      zero_round(*p.zplan, zr, gw, n_gw, zsrc, lane);
+      zpend = true;
+    }
+#endif
     int e_nxt = -1, nd_nxt = 0;
     batch_ids(grp_nxt, e_nxt, nd_nxt);
     cp_async_wait_all();
@@ -885,20 +863,38 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ^ 1], e_nxt, nd_nxt);
     e_cur = e_nxt; nd_cur = nd_nxt;
     __syncwarp();
-    if (ikz) {
-      int mx = 0;
+#if A2DS_ZWAIT
+    if (zon) {
+      const int n_zr = p.zplan->rounds;
+      int *zdone = p.zplan->done;
+      if (zpend) { zero_publish(zdone, zr, lane); zr++; zpend = false; }
+      // the round the highest block offset of this batch falls into must be complete (rounded
+      // up: one round early costs nothing, one round late is a race)
+      int mxw = 0;
 #pragma unroll
       for (int r = 0; r < NB * 16 / 32; r++) {
         const int sidx = lane + 32 * r, j = sidx >> 4, k = sidx & 15;
         if (j < cnt) {
-          if (KMAT) mx = max(mx, rb.koff[j][k]);
-          if (GMAT) mx = max(mx, goffb[j][k]);
+          if (KMAT) mxw = max(mxw, rb.koff[j][k]);
+          if (GMAT) mxw = max(mxw, goffb[j][k]);
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-      ikz_service(p.zplan, &ws.ikz, 1, mx, gw, n_gw, lane);
+      for (int o = 16; o > 0; o >>= 1) mxw = max(mxw, __shfl_xor_sync(FULL, mxw, o));
+      const int rneed = min(n_zr - 1, (int)((float)mxw * p.zplan->inv_round) + 1);
+      while (rneed > zknown) {
+        int v = 0;
+        if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(zdone + rneed) : "memory");
+        v = __shfl_sync(FULL, v, 0);
+        if (v >= n_gw) { zknown = rneed; break; }
+        if (zr < n_zr) {   // zero ahead instead of idling
+          zero_round(*p.zplan, zr, gw, n_gw, zsrc, lane);
+          zero_publish(zdone, zr, lane);
+          zr++;
+        }
+      }
     }
+#endif
 
     // element prologue: H_tt (45 entries over 32 lanes: Gauss-point sums of Q) and the tying
     // stresses.  A pure latency chain (plan -> Q -> 4 FMA -> store); it is issued for element
@@ -1076,8 +1072,17 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       grp = grp_nxt; grp_nxt = drawn;
     }
   }
+#if A2DS_ZWAIT
   // rounds this warp has not reached yet (short lists, warps without a batch)
-  if (ikz) ikz_service(p.zplan, &ws.ikz, 2, 0, gw, n_gw, lane);
+  if (zon) {
+    const ZeroPlan z = *p.zplan;
+    if (zpend) { zero_publish(z.done, zr, lane); zr++; }
+    for (; zr < z.rounds; zr++) {
+      zero_round(z, zr, gw, n_gw, zsrc, lane);
+      zero_publish(z.done, zr, lane);
+    }
+  }
+#endif
 }
 
 // ---- mass path (gamma terms of assembleJacobian, TACS_MASS_MATRIX, inertial residual) ----

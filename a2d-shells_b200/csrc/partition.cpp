@@ -375,3 +375,59 @@ extern "C" int a2ds_partition_rcb(int n_nodes, int n_elems, const int *conn, con
     return a2ds_set_error_((std::string("a2ds_partition_rcb: ") + e.what()).c_str());
   }
 }
+
+// ---- halo plan from the reference's own exchange plan --------------------------------------
+// TACSBVecDistribute (src/bpmat/TACSBVecDistribute.h:156-172) describes the ghost exchange of a
+// rank with two slab lists of GLOBAL node numbers: ext_vars (sorted; slab i = the nodes this
+// rank reads from their owner ext_proc[i]) and req_vars (slab i = the owned nodes rank
+// req_proc[i] reads from this rank).  In the local numbering of the device path (owned nodes
+// first, g - lo; then the ghosts in the order of ext_vars, exactly the order of TACSBVec's
+// external array, src/bpmat/TACSBVec.cpp:982-1039) this becomes the peer / send / receive
+// lists of a2ds_set_halo.  Pure host arithmetic: what the drop-in binding calls once per
+// assembler on a multi-rank run (host/tacs_shim.cpp).
+static int halo_from_distribute_impl(int lo, int n_owned, int n_ext_proc, const int *ext_proc,
+                                     const int *ext_ptr, const int *ext_count, int n_req_proc,
+                                     const int *req_proc, const int *req_ptr, const int *req_count,
+                                     const int *req_vars, int *n_peers, int *peer_rank,
+                                     int *send_ptr, int *send_nodes, int *recv_ptr, int *recv_nodes) {
+  if (n_ext_proc < 0 || n_req_proc < 0 || n_owned < 0)
+    return a2ds_set_error_("a2ds_halo_from_distribute: bad sizes");
+  std::vector<int> peers;
+  for (int i = 0; i < n_ext_proc; i++) peers.push_back(ext_proc[i]);
+  for (int i = 0; i < n_req_proc; i++) peers.push_back(req_proc[i]);
+  std::sort(peers.begin(), peers.end());
+  peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+  int ns = 0, nr = 0;
+  for (size_t k = 0; k < peers.size(); k++) {
+    peer_rank[k] = peers[k];
+    send_ptr[k] = ns; recv_ptr[k] = nr;
+    for (int i = 0; i < n_req_proc; i++)
+      if (req_proc[i] == peers[k])
+        for (int j = 0; j < req_count[i]; j++) {
+          const int g = req_vars[req_ptr[i] + j];
+          if (g < lo || g >= lo + n_owned)
+            return a2ds_set_error_("a2ds_halo_from_distribute: a requested node is not owned by this rank");
+          send_nodes[ns++] = g - lo;
+        }
+    for (int i = 0; i < n_ext_proc; i++)
+      if (ext_proc[i] == peers[k])
+        for (int j = 0; j < ext_count[i]; j++) recv_nodes[nr++] = n_owned + ext_ptr[i] + j;
+  }
+  send_ptr[peers.size()] = ns; recv_ptr[peers.size()] = nr;
+  *n_peers = (int)peers.size();
+  return 0;
+}
+extern "C" int a2ds_halo_from_distribute(int lo, int n_owned, int n_ext_proc, const int *ext_proc,
+                                         const int *ext_ptr, const int *ext_count, int n_req_proc,
+                                         const int *req_proc, const int *req_ptr,
+                                         const int *req_count, const int *req_vars, int *n_peers,
+                                         int *peer_rank, int *send_ptr, int *send_nodes,
+                                         int *recv_ptr, int *recv_nodes) {
+  try {
+    return halo_from_distribute_impl(lo, n_owned, n_ext_proc, ext_proc, ext_ptr, ext_count, n_req_proc,
+                                     req_proc, req_ptr, req_count, req_vars, n_peers, peer_rank,
+                                     send_ptr, send_nodes, recv_ptr, recv_nodes);
+  } catch (const std::exception &e) {
+    return a2ds_set_error_((std::string("a2ds_halo_from_distribute: ") + e.what()).c_str());
+  }
+}

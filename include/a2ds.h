@@ -219,6 +219,17 @@ int a2ds_comm_unique_id(char id[128]);
 int a2ds_comm_init(a2ds_ctx *ctx, int n_ranks, int rank, const char id[128]);
 int a2ds_set_halo(a2ds_ctx *ctx, int n_peers, const int *peer_rank, const int *send_ptr,
                   const int *send_nodes, const int *recv_ptr, const int *recv_nodes);
+/* The same lists from the reference's own plan: TACSBVecDistribute's slab lists of GLOBAL node
+ * numbers (src/bpmat/TACSBVecDistribute.h:156-172: ext_proc/ext_ptr/ext_count over the sorted
+ * ext_vars this rank reads, req_proc/req_ptr/req_count/req_vars the owned nodes other ranks
+ * read) in the device path's local numbering (owned g - lo first, then the ghosts in ext_vars
+ * order).  Outputs sized by the caller: peer_rank[n_ext_proc + n_req_proc], send_ptr / recv_ptr
+ * one longer, send_nodes[sum req_count], recv_nodes[sum ext_count].  Host only. */
+int a2ds_halo_from_distribute(int lo, int n_owned, int n_ext_proc, const int *ext_proc,
+                              const int *ext_ptr, const int *ext_count, int n_req_proc,
+                              const int *req_proc, const int *req_ptr, const int *req_count,
+                              const int *req_vars, int *n_peers, int *peer_rank, int *send_ptr,
+                              int *send_nodes, int *recv_ptr, int *recv_nodes);
 /* forward: owner -> ghost copies of the state (beginForward/endForward) */
 int a2ds_halo_forward(a2ds_ctx *ctx);
 

@@ -216,3 +216,66 @@ def test_native_partition_three_ranks_gloo():
         seen[glob] += 1
         assert np.abs(r - r_all[glob]).max() <= 1e-12 * np.abs(r_all).max()
     assert (seen == 1).all()
+
+
+def test_halo_plan_from_the_references_distribute_plan(a2ds):
+    """a2ds_halo_from_distribute: TACSBVecDistribute's slab lists of GLOBAL node numbers
+    (src/bpmat/TACSBVecDistribute.h:156-172), emulated here from an element partition the way
+    the reference builds them (ext_vars = sorted ghost globals grouped by owner, req_vars = what
+    each other rank's ext list asks of this rank; owners hold contiguous global ranges), must
+    give the same peers / send / receive lists as the native planner — for a 4-rank scattered
+    partition of an unstructured mesh and for row slabs."""
+    for conn, X, er, nr in _distribute_cases(a2ds):
+        parts = a2ds.meshes.partition_rows(conn, len(X), er)
+        for q in parts:
+            q["n_owned"] = len(q["owned"])
+        # reference numbering: rank r owns the contiguous global range [lo_r, lo_r + n_owned_r)
+        lo = np.concatenate([[0], np.cumsum([p["n_owned"] for p in parts])])
+        new_of = np.full(len(X), -1, dtype=np.int64)
+        for r, p in enumerate(parts):
+            new_of[p["glob"][:p["n_owned"]]] = lo[r] + np.arange(p["n_owned"])
+        owner = np.searchsorted(lo, np.arange(lo[-1]), side="right") - 1
+        ext = []      # per rank: sorted global (new numbering) ghost ids
+        for r, p in enumerate(parts):
+            ext.append(np.sort(new_of[p["glob"][p["n_owned"]:]]))
+        for r, p in enumerate(parts):
+            ev = ext[r]
+            eo = owner[ev]
+            ext_proc = np.unique(eo)
+            ext_ptr = np.array([np.searchsorted(eo, q) for q in ext_proc])
+            ext_count = np.array([np.sum(eo == q) for q in ext_proc])
+            req_proc, req_vars = [], []
+            for q in range(nr):
+                if q == r:
+                    continue
+                mine = ext[q][owner[ext[q]] == r]
+                if len(mine):
+                    req_proc.append(q); req_vars.append(mine)
+            req_count = np.array([len(v) for v in req_vars], dtype=np.int64)
+            req_ptr = np.concatenate([[0], np.cumsum(req_count)])[:-1] if len(req_vars) else np.zeros(0)
+            peers, sends, recvs = a2ds.halo_from_distribute(
+                int(lo[r]), p["n_owned"], ext_proc, ext_ptr, ext_count, req_proc, req_ptr, req_count,
+                np.concatenate(req_vars) if req_vars else np.zeros(0))
+            # the same exchange in the reference's numbering: map our local ids back to globals
+            # of the ORIGINAL mesh and compare as sets per peer with the native plan
+            glob_new = np.concatenate([lo[r] + np.arange(p["n_owned"]), ev])   # local -> new global
+            old_of_new = np.zeros(lo[-1], dtype=np.int64); old_of_new[new_of[new_of >= 0]] = np.nonzero(new_of >= 0)[0]
+            native = {int(q): (set(p["glob"][s].tolist()), set(p["glob"][v].tolist()))
+                      for q, s, v in zip(p["peers"], p["send_lists"], p["recv_lists"])}
+            got = {int(q): (set(old_of_new[glob_new[s]].tolist()), set(old_of_new[glob_new[v]].tolist()))
+                   for q, s, v in zip(peers, sends, recvs)}
+            got = {q: sv for q, sv in got.items() if sv[0] or sv[1]}
+            native = {q: sv for q, sv in native.items() if sv[0] or sv[1]}
+            assert got == native
+            for v in recvs:
+                assert np.all(v >= p["n_owned"])
+            for s in sends:
+                assert np.all((s >= 0) & (s < p["n_owned"]))
+
+
+def _distribute_cases(a2ds):
+    conn, X, _ = a2ds.meshes.plate(9, 8)
+    yield conn, X, (np.arange(len(conn)) // 9 // 2).astype(np.int32), 4
+    conn, X, _ = a2ds.meshes.cubed_sphere(4, shuffle_seed=3)
+    rng = np.random.default_rng(5)
+    yield conn, X, rng.integers(0, 4, len(conn)).astype(np.int32), 4

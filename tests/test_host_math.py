@@ -14,18 +14,47 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 @pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("tr", [0, 1])
 @pytest.mark.parametrize("ci", [0, 1])
-def test_kernel_math_against_golden(emul, kind, tr, ci):
+@pytest.mark.parametrize("tying", [False, True])
+def test_kernel_math_against_golden(emul, kind, tr, ci, tying):
+    """both formulations of the element kernels stepped on the host: the first one (strain rows
+    per Gauss point, k_assemble) and the tying-level one (mitc4_tying.h, k_assemble_t)"""
     g = np.load(os.path.join(GOLD, "elements.npz"))
     key = f"k{kind}_t{tr}_c{ci}"
     T = float(g[key + "_T"])
+    if tying and np.any(g[key + "_Cs"][6:12] != 0.0):
+        pytest.skip("coupled section: the tying-level kernel is not used for it")
     for e in range(g["X"].shape[0]):
         r, K, G = emul_element(emul, g[key + "_Cs"], g[key + "_eth"], T, kind, tr, g["axis"],
-                               g["X"][e], g["q"][e], 1 if kind == 0 else 0)
+                               g["X"][e], g["q"][e], 1 if kind == 0 else 0, tying=tying)
         assert relmax(r, g[key + "_res"][e]) < 1e-12      # north_star residual tolerance
         assert relmax(K, g[key + "_K"][e]) < 1e-10        # north_star matrix tolerance
         if kind == 0:
             assert relmax(G, g[key + "_G"][e]) < (1e-10 if T == 0.0 else 1e-6)
             assert np.abs(G - G.T).max() <= 1e-13 * np.abs(G).max()
+
+
+def test_tying_level_formulation_against_oracle_many(emul, orc, a2ds):
+    """mitc4_tying.h (K = Bt^T H Bt over the tying points): 300 random distorted elements, both
+    classes, both transforms, with and without temperature — residual, tangent and geometric
+    stiffness against the oracle and against the first formulation"""
+    X, q = random_elements(300, seed=17)
+    axis = np.array([0.3, 1.0, 0.2])
+    Cs, eth = a2ds.iso_shell_tables()
+    for kind in (0, 1):
+        for tr in (0, 1):
+            for T in (0.0, 10.0):
+                comp = orc.make_comp(kind, Cs, eth, (0, 0, 0), T, tr, axis)
+                worst = [0.0, 0.0, 0.0]
+                for e in range(X.shape[0]):
+                    wg = 1 if kind == 0 else 0
+                    r, K, G = emul_element(emul, Cs, eth, T, kind, tr, axis, X[e], q[e], wg, tying=True)
+                    ro, ko = orc.jacobian(comp, X[e].ravel(), q[e].ravel())
+                    worst[0] = max(worst[0], relmax(r, ro)); worst[1] = max(worst[1], relmax(K, ko))
+                    if wg:
+                        _, _, G0 = emul_element(emul, Cs, eth, T, kind, tr, axis, X[e], q[e], 1)
+                        worst[2] = max(worst[2], relmax(G, G0))
+                        assert np.abs(G - G.T).max() <= 1e-13 * np.abs(G).max()
+                assert worst[0] < 1e-12 and worst[1] < 1e-11 and worst[2] < 1e-13, worst
 
 
 def test_kernel_math_against_oracle_many(emul, orc, a2ds):
