@@ -6,6 +6,8 @@
 // BCs, halo pack / unpack, copy / axpy, 6x6 BCSR mat-vec); the per-lane element math in
 // mitc4_math.h; mesh input and the partition planner (host only) in mesh_io.cpp, partition.cpp.
 #include <cuda_runtime.h>
+#include <memory>
+#include <cub/cub.cuh>
 #include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -86,9 +88,11 @@ struct MatrixRec {
   int *off = nullptr;          // 16 per element
   BlockDev *blk_dev = nullptr;
   std::vector<void *> owned;   // device allocations to free
-  std::vector<std::vector<int>> h_rowp, h_cols;  // host copy of the patterns
+  // host copy of the patterns (shared between the natural-order matrices of one mesh)
+  std::vector<std::shared_ptr<const std::vector<int>>> h_rowp, h_cols;
   std::vector<const int *> d_rowp, d_cols;       // device copy, per block
   unsigned long long pattern_hash = 0;           // fingerprint of (rowp, cols), 0 = not computed
+  unsigned long long *shared_hash = nullptr;     // natural-order matrices of one mesh share it
   // matrix halo (ParallelMat flavour): blocks of ghost rows sent to / received from peers
   bool has_halo = false;
   std::vector<int> halo_peers, halo_send_ptr, halo_recv_ptr;
@@ -112,7 +116,9 @@ struct a2ds_ctx {
   int *conn = nullptr, *elem_comp = nullptr;
   std::vector<int> h_conn, h_elem_comp, h_class;
   // natural-order pattern of the current mesh, built by the first a2ds_mat_create_natural
-  std::vector<int> nat_rowp, nat_cols;
+  std::shared_ptr<std::vector<int>> nat_rowp, nat_cols;   // host copy
+  int *nat_d_rowp = nullptr, *nat_d_cols = nullptr;       // device copy, shared by those matrices
+  unsigned long long nat_hash = 0;
   bool nat_ready = false;
   std::vector<double> h_mom;          // mass moments per component (a2ds_set_mass_moments)
   std::vector<CompData> h_comps;
@@ -235,6 +241,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   cudaFree(c->conn); cudaFree(c->elem_comp); cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
   cudaFree(c->udd);
   cudaFree(c->scratch_x); cudaFree(c->scratch_y); cudaFree(c->zplan_dev);
+  cudaFree(c->nat_d_rowp); cudaFree(c->nat_d_cols);
   cudaFree(c->comps); cudaFree(c->bc_nodes); cudaFree(c->bc_vars); cudaFree(c->bc_vals);
   cudaFree(c->send_nodes); cudaFree(c->recv_nodes); cudaFree(c->send_buf); cudaFree(c->recv_buf);
   if (c->comm) ncclCommDestroy(c->comm);
@@ -283,6 +290,8 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
   c->n_nodes = n_nodes; c->n_owned = n_owned; c->n_elems = n_elems;
   c->h_conn.assign(conn, conn + 4 * (size_t)n_elems);
   c->nat_ready = false;
+  cudaFree(c->nat_d_rowp); cudaFree(c->nat_d_cols);
+  c->nat_d_rowp = c->nat_d_cols = nullptr; c->nat_hash = 0;
   if (elem_comp) c->h_elem_comp.assign(elem_comp, elem_comp + n_elems);
   else c->h_elem_comp.assign(n_elems, 0);
   if (upload(&c->conn, conn, 4 * (size_t)n_elems, c->stream)) return 1;
@@ -573,9 +582,9 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   for (int b = 0; b < n_blocks; b++) {
     const long long nnz = nrows[b] > 0 ? rowp[b][nrows[b]] : 0;
     m.nnz.push_back(nnz); m.base.push_back(total); m.nrows.push_back(nrows[b]);
-    m.h_rowp.emplace_back(nrows[b] > 0 ? std::vector<int>(rowp[b], rowp[b] + nrows[b] + 1)
-                                       : std::vector<int>(1, 0));
-    m.h_cols.emplace_back(cols[b], cols[b] + nnz);
+    m.h_rowp.push_back(std::make_shared<const std::vector<int>>(
+        nrows[b] > 0 ? std::vector<int>(rowp[b], rowp[b] + nrows[b] + 1) : std::vector<int>(1, 0)));
+    m.h_cols.push_back(std::make_shared<const std::vector<int>>(cols[b], cols[b] + nnz));
     int *d_rowp = nullptr, *d_cols = nullptr, *d_rm = nullptr, *d_cm = nullptr;
     std::vector<int> zero_rowp(1, 0);
     if (upload(&d_rowp, nrows[b] > 0 ? rowp[b] : zero_rowp.data(), (size_t)nrows[b] + 1, c->stream)) return 1;
@@ -723,19 +732,113 @@ extern "C" int a2ds_host_color_elements(int n_nodes, int n_elems, const int *con
   A2DS_CATCH(a2ds_host_color_elements)
 }
 
+// natural-order pattern built on the device (aux_kernels.cuh, k_pat_*); the host copy is one
+// download.  Returns 1 on error, 2 when a node has too many elements around it (host path).
+static int natural_pattern_device(a2ds_ctx *c) {
+  const int nn = c->n_nodes;
+  const size_t n4 = 4 * (size_t)c->n_elems;
+  int *deg = nullptr, *ptr = nullptr, *adj = nullptr, *cnt = nullptr, *ovf = nullptr;
+  void *tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(deg); cudaFree(ptr); cudaFree(adj); cudaFree(cnt); cudaFree(ovf); cudaFree(tmp); };
+  CU(cudaMalloc((void **)&deg, ((size_t)nn + 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&ptr, ((size_t)nn + 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&cnt, ((size_t)nn + 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&adj, std::max<size_t>(n4, 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&ovf, sizeof(int)));
+  CU(cudaMemsetAsync(deg, 0, ((size_t)nn + 1) * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(cnt, 0, ((size_t)nn + 1) * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(ovf, 0, sizeof(int), c->stream));
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, ptr, nn + 1, c->stream);
+  CU(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+  const unsigned g4 = (unsigned)((n4 + 255) / 256), gn = (unsigned)((nn + 127) / 128);
+  if (n4) k_pat_count<<<g4, 256, 0, c->stream>>>(n4, c->conn, deg);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, ptr, nn + 1, c->stream);
+  CU(cudaMemsetAsync(deg, 0, ((size_t)nn + 1) * sizeof(int), c->stream));   // reused as the fill cursor
+  if (n4) k_pat_fill<<<g4, 256, 0, c->stream>>>(n4, c->conn, ptr, deg, adj);
+  if (nn) k_pat_rows<false><<<gn, 128, 0, c->stream>>>(nn, c->conn, ptr, adj, cnt, nullptr, nullptr, ovf);
+  int overflow = 0;
+  CU(cudaMemcpyAsync(&overflow, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int *d_rowp = nullptr, *d_cols = nullptr;
+  CU(cudaMalloc((void **)&d_rowp, ((size_t)nn + 1) * sizeof(int)));
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, d_rowp, nn + 1, c->stream);
+  int nnz = 0;
+  CU(cudaMemcpyAsync(&nnz, d_rowp + nn, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (overflow) { cleanup(); cudaFree(d_rowp); return 2; }
+  CU(cudaMalloc((void **)&d_cols, std::max<size_t>((size_t)nnz, 1) * sizeof(int)));
+  if (nn) k_pat_rows<true><<<gn, 128, 0, c->stream>>>(nn, c->conn, ptr, adj, nullptr, d_rowp, d_cols, ovf);
+  CU(cudaGetLastError());
+  auto hr = std::make_shared<std::vector<int>>((size_t)nn + 1);
+  auto hc = std::make_shared<std::vector<int>>((size_t)nnz);
+  CU(cudaMemcpyAsync(hr->data(), d_rowp, ((size_t)nn + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (nnz) CU(cudaMemcpyAsync(hc->data(), d_cols, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cleanup();
+  c->nat_rowp = hr; c->nat_cols = hc; c->nat_d_rowp = d_rowp; c->nat_d_cols = d_cols;
+  return 0;
+}
+
 extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   A2DS_TRY
   if (!c->mesh_set) return fail("a2ds_mat_create_natural: call a2ds_set_mesh first");
+  CU(cudaSetDevice(c->device));
+  StageTimer tm;
   if (!c->nat_ready) {
-    StageTimer tm;
-    if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), c->nat_rowp, c->nat_cols)) return 1;
+    static const bool host_only = getenv("A2DS_HOST_PATTERN") && atoi(getenv("A2DS_HOST_PATTERN")) != 0;
+    int rc = host_only ? 2 : natural_pattern_device(c);
+    if (rc == 1) return 1;
+    if (rc == 2) {   // very high valence somewhere (or asked for): host sort / unique sweep
+      auto hr = std::make_shared<std::vector<int>>(), hc = std::make_shared<std::vector<int>>();
+      if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), *hr, *hc)) return 1;
+      c->nat_rowp = hr; c->nat_cols = hc;
+      if (upload(&c->nat_d_rowp, hr->data(), hr->size(), c->stream)) return 1;
+      if (upload(&c->nat_d_cols, hc->data(), hc->size(), c->stream)) return 1;
+    }
     c->nat_ready = true;
-    tm.lap("natural pattern (host)");
+    tm.lap(rc == 2 ? "natural pattern (host)" : "natural pattern (device)");
   }
-  const int nrows = c->n_nodes;
-  const int *rp = c->nat_rowp.data(), *cp = c->nat_cols.data();
-  const int ident = 1;
-  return a2ds_mat_create(c, 1, &nrows, &rp, &cp, nullptr, nullptr, &ident, mat);
+  // the matrices of one mesh share the pattern arrays, on the host and on the device
+  MatrixRec m;
+  m.n_blocks = 1;
+  const long long nnz = (long long)c->nat_cols->size();
+  m.nnz.push_back(nnz); m.base.push_back(0); m.nrows.push_back(c->n_nodes);
+  m.h_rowp.push_back(c->nat_rowp); m.h_cols.push_back(c->nat_cols);
+  m.d_rowp.push_back(c->nat_d_rowp); m.d_cols.push_back(c->nat_d_cols);
+  m.total = nnz;
+  BlockDev hb;
+  hb.rowp = c->nat_d_rowp; hb.cols = c->nat_d_cols; hb.row_map = nullptr; hb.col_map = nullptr;
+  hb.base = 0; hb.nrows = c->n_nodes; hb.ident = 1;
+  CU(cudaMalloc((void **)&m.A, std::max<long long>(nnz, 1) * 36 * sizeof(double)));
+  m.owned.push_back(m.A);
+  CU(cudaMemsetAsync(m.A, 0, nnz * 36 * sizeof(double), c->stream));
+  CU(cudaMalloc((void **)&m.blk_dev, sizeof(BlockDev)));
+  m.owned.push_back(m.blk_dev);
+  CU(cudaMemcpyAsync(m.blk_dev, &hb, sizeof(BlockDev), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMalloc((void **)&m.off, std::max<size_t>(16 * (size_t)c->n_elems, 1) * sizeof(int)));
+  m.owned.push_back(m.off);
+  int *d_missing = nullptr;
+  CU(cudaMalloc((void **)&d_missing, sizeof(int)));
+  CU(cudaMemsetAsync(d_missing, 0, sizeof(int), c->stream));
+  if (c->n_elems > 0) {
+    const size_t nt = 16 * (size_t)c->n_elems;
+    k_build_offsets<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(c->n_elems, c->conn, 1, m.blk_dev,
+                                                                        m.off, d_missing);
+    CU(cudaGetLastError());
+  }
+  int missing = 0;
+  CU(cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_missing);
+  tm.lap("mat_create_natural: alloc+zero+offsets");
+  if (missing) {
+    for (void *p : m.owned) cudaFree(p);
+    return fail("a2ds_mat_create_natural: the pattern misses " + std::to_string(missing) + " element blocks");
+  }
+  m.shared_hash = &c->nat_hash;
+  c->mats.push_back(std::move(m));
+  *mat = (int)c->mats.size() - 1;
+  return 0;
   A2DS_CATCH(a2ds_mat_create_natural)
 }
 
@@ -744,8 +847,8 @@ extern "C" int a2ds_mat_pattern(a2ds_ctx *c, int mat, int block, int *nrows, int
   if (check_mat(c, mat, block)) return 1;
   MatrixRec &m = c->mats[mat];
   if (nrows) *nrows = m.nrows[block];
-  if (rowp) memcpy(rowp, m.h_rowp[block].data(), m.h_rowp[block].size() * sizeof(int));
-  if (cols) memcpy(cols, m.h_cols[block].data(), m.h_cols[block].size() * sizeof(int));
+  if (rowp) memcpy(rowp, m.h_rowp[block]->data(), m.h_rowp[block]->size() * sizeof(int));
+  if (cols) memcpy(cols, m.h_cols[block]->data(), m.h_cols[block]->size() * sizeof(int));
   return 0;
   A2DS_CATCH(a2ds_mat_pattern)
 }
@@ -789,7 +892,7 @@ extern "C" int a2ds_mat_download_rows(a2ds_ctx *c, int mat, int block, int n_row
   if (check_mat(c, mat, block)) return 1;
   CU(cudaSetDevice(c->device));
   MatrixRec &m = c->mats[mat];
-  const std::vector<int> &rowp = m.h_rowp[block];
+  const std::vector<int> &rowp = *m.h_rowp[block];
   size_t out = 0;
   for (int i = 0; i < n_rows; i++) {
     const int r = rows[i];
@@ -817,14 +920,16 @@ extern "C" int a2ds_mat_values_dev(a2ds_ctx *c, int mat, int block, double **A_d
 // do not compare megabytes of indices on the host at every call
 static unsigned long long pattern_fingerprint(MatrixRec &m) {
   if (m.pattern_hash) return m.pattern_hash;
+  if (m.shared_hash && *m.shared_hash) return m.pattern_hash = *m.shared_hash;
   unsigned long long h = 1469598103934665603ull;
   auto mix = [&](const std::vector<int> &v) {
     for (int x : v) { h ^= (unsigned)x; h *= 1099511628211ull; }
     h ^= 0xffu; h *= 1099511628211ull;
   };
-  for (const auto &v : m.h_rowp) mix(v);
-  for (const auto &v : m.h_cols) mix(v);
+  for (const auto &v : m.h_rowp) mix(*v);
+  for (const auto &v : m.h_cols) mix(*v);
   m.pattern_hash = h ? h : 1;
+  if (m.shared_hash) *m.shared_hash = m.pattern_hash;
   return m.pattern_hash;
 }
 
@@ -932,7 +1037,7 @@ extern "C" int a2ds_mat_mult(a2ds_ctx *c, int mat, int block, int ncols, const d
   if (check_mat(c, mat, block)) return 1;
   CU(cudaSetDevice(c->device));
   const int nrows = c->mats[mat].nrows[block];
-  const std::vector<int> &hc = c->mats[mat].h_cols[block];
+  const std::vector<int> &hc = *c->mats[mat].h_cols[block];
   const int max_col = hc.empty() ? -1 : *std::max_element(hc.begin(), hc.end());
   if (ncols <= max_col || !x || !y)
     return fail("a2ds_mat_mult: x has " + std::to_string(ncols) + " block columns, the matrix "

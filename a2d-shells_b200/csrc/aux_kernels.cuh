@@ -37,6 +37,59 @@ __global__ void k_build_offsets(int n_elems, const int *conn, int n_blocks, cons
   if (found < 0) atomicAdd(missing, 1);
 }
 
+// ---- non-zero pattern of the natural-order matrix on the device -------------------------------
+// TACSAssembler::computeLocalNodeToNodeCSR + TacsSortAndUniquifyCSR (src/TACSAssembler.cpp:1839,
+// src/utils/TacsUtilities.cpp:280): node -> nodes of its elements, sorted and unique per row.
+// Three light kernels around two prefix sums: element incidences per node, then per node the
+// (at most 4 per element) candidate columns are sorted and made unique in a per-thread array
+// — once to count, once to write.  PAT_MAX_ELEMS bounds the elements around one node; meshes
+// beyond it (very high-valence fans) take the host path.
+static const int PAT_MAX_ELEMS = 24;
+__global__ void k_pat_count(size_t n4, const int *conn, int *deg) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t < n4) atomicAdd(&deg[conn[t]], 1);
+}
+__global__ void k_pat_fill(size_t n4, const int *conn, const int *ptr, int *cursor, int *adj) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n4) return;
+  const int n = conn[t];
+  adj[ptr[n] + atomicAdd(&cursor[n], 1)] = (int)(t >> 2);
+}
+// WRITE = false: cnt[n] = number of distinct columns of row n (overflow: more than PAT_MAX_ELEMS
+// elements around a node); WRITE = true: cols[rowp[n] ..] = the sorted distinct columns
+template <bool WRITE>
+__global__ void k_pat_rows(int nn, const int *conn, const int *ptr, const int *adj, int *cnt,
+                           const int *rowp, int *cols, int *overflow) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  const int a = ptr[n], b = ptr[n + 1];
+  if (b - a > PAT_MAX_ELEMS) {
+    if (!WRITE) { cnt[n] = 0; atomicAdd(overflow, 1); }
+    return;
+  }
+  int c[4 * PAT_MAX_ELEMS];
+  int m = 0;
+  for (int k = a; k < b; k++) {
+    const int e = adj[k];
+    for (int j = 0; j < 4; j++) {
+      const int v = conn[4 * (size_t)e + j];
+      // insertion into the sorted, distinct prefix c[0 .. m)
+      int pos = m;
+      while (pos > 0 && c[pos - 1] > v) pos--;
+      if (pos > 0 && c[pos - 1] == v) continue;
+      for (int i = m; i > pos; i--) c[i] = c[i - 1];
+      c[pos] = v;
+      m++;
+    }
+  }
+  if (!WRITE) {
+    cnt[n] = m;
+  } else {
+    int *out = cols + rowp[n];
+    for (int i = 0; i < m; i++) out[i] = c[i];
+  }
+}
+
 // residual BC rows: r = u - ubar on owned nodes (TACSBVec::applyBCs, TACSBVec.cpp:546-585)
 __global__ void k_res_bcs(int n_bc, const int *nodes, const int *vars, const double *vals,
                           const double *u, double *res, int n_owned) {
