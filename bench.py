@@ -462,9 +462,16 @@ def run_case(args, workload, steps, warmup, dist, world, rank, local_rank, want_
             for q in allp:
                 for k, v in (q.get("max_rel") or {}).items():
                     worst[k] = max(worst.get(k, 0.0), v)
+            noise, used = {}, {}
+            for q in allp:
+                for k, v in (q.get("reference_fma_spread") or {}).items():
+                    noise[k] = max(noise.get(k, 0.0), v)
+                for k, v in (q.get("tol_used") or {}).items():
+                    used[k] = max(used.get(k, 0.0), v)
             parity = dict(rows=int(sum(q.get("rows", 0) for q in allp)),
                           interface_rows=int(sum(q.get("interface_rows", 0) for q in allp)),
-                          max_rel=worst, tol=allp[0].get("tol"), ok=bool(all(q.get("ok") for q in allp)),
+                          max_rel=worst, tol=allp[0].get("tol"), reference_fma_spread=noise,
+                          tol_used=used, ok=bool(all(q.get("ok") for q in allp)),
                           against=allp[0].get("against"), ranks=world,
                           errors=[q["error"] for q in allp if "error" in q] or None)
     res = dict(workload=workload, wl=wl, nonlinear=nonlinear, strong=strong, nx=nx, ny=ny,

@@ -44,6 +44,21 @@ def lib():
     return _LIB
 
 
+_LIB_FMA = None
+
+
+def lib_fma():
+    """the same C restatement compiled with FMA contraction (noise-floor measurements only)"""
+    global _LIB_FMA
+    if _LIB_FMA is None:
+        path = os.path.join(_HERE, "liboracle_shell_fma.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", _HERE, "liboracle_shell_fma.so"])
+        _LIB_FMA = C.CDLL(path)
+    return _LIB_FMA
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -98,7 +113,7 @@ def pattern(n_nodes, conn):
 
 
 def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_vars=None,
-             bc_vals=None, alpha=1.0, gamma=0.0, udd=None):
+             bc_vals=None, alpha=1.0, gamma=0.0, udd=None, fma=False):
     """op 0 res, 1 jacobian (alpha K + gamma M), 2 K, 3 G, 4 M -> (res[n,6] or None,
     A[nnz,6,6] or None); udd: second time derivatives (inertial term of the residual)."""
     conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
@@ -114,7 +129,7 @@ def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_var
     res = np.zeros((n, 6)) if op <= 1 else None
     A = np.zeros((len(cols), 6, 6)) if op >= 1 else None
     udd = None if udd is None else np.ascontiguousarray(udd, dtype=np.float64).reshape(-1, 6)
-    miss = lib().oracle_assemble_dyn(C.c_int(op), C.c_double(alpha), C.c_double(gamma), C.c_int(n),
+    miss = (lib_fma() if fma else lib()).oracle_assemble_dyn(C.c_int(op), C.c_double(alpha), C.c_double(gamma), C.c_int(n),
                                      C.c_int(conn.shape[0]), _p(conn), _p(ec), arr, _p(X), _p(u),
                                      _p(udd), C.c_int(nb), _p(bn), _p(bv), _p(bx),
                                      _p(np.ascontiguousarray(rowp, dtype=np.int32)),
