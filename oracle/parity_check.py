@@ -184,9 +184,10 @@ def check(asm, kmat, gmat, conn, X, u, elem_comp, comps, bc_nodes, n_owned, bc_m
     if not want_g:
         rel.pop("G"); nrel.pop("G")
     tol = dict(res=1e-12, K=1e-10, G=1e-10)
-    # gate: the north-star tolerance, or 2 x the reference's own build-to-build spread on this
-    # mesh where that is larger (residual of very fine meshes far from the origin)
-    used = {k: max(tol[k], 2.0 * nrel[k]) for k in rel}
+    # gate: the north-star tolerance, or 4 x the reference's own build-to-build spread on this
+    # mesh where that is larger (residual of very fine meshes far from the origin; the spread is
+    # taken on ~100 rows, the comparison on all sampled rows of all ranks)
+    used = {k: max(tol[k], 4.0 * nrel[k]) for k in rel}
     return dict(rows=n_rows, interface_rows=int(len(iface)), max_rel=rel,
                 tol={k: tol[k] for k in rel}, reference_fma_spread=nrel, tol_used=used,
                 ok=bool(all(rel[k] <= used[k] for k in rel)),
