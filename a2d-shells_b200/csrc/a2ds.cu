@@ -100,6 +100,17 @@ struct MatrixRec {
   double *halo_send_buf = nullptr, *halo_recv_buf = nullptr;
 };
 
+// element ranges and residual row chunks of the streamed assembly (host, cached per mesh)
+struct StreamPlan {
+  bool ready = false;
+  int C = 0;
+  std::vector<int> e0;        // C + 1 element boundaries
+  std::vector<int> max_node;  // highest node an element range refers to
+  std::vector<int> order;     // launch order of the ranges
+  std::vector<int> row_lo;    // R + 1 boundaries of the owned node rows (R = ROWS_PER_CHUNK * C)
+  std::vector<int> row_pos;   // launch position after which a row chunk is final (C: after the reverse halo)
+};
+
 struct a2ds_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -109,6 +120,18 @@ struct a2ds_ctx {
   cudaEvent_t ev_state = nullptr, ev_used = nullptr;
   bool state_pending = false;
   bool halo_pending = false;  // forward ghost exchange deferred until the upload is consumed
+  // streamed assembly (large meshes with host I/O in the step): the state goes up in row chunks,
+  // the element kernel runs per element range as soon as its rows have arrived, and the
+  // residual rows go back (on d2h_stream) as soon as the last range that adds to them is done
+  static const int MAX_CHUNKS = 16, ROWS_PER_CHUNK = 4;   // residual row chunks are finer than the ranges
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_up[MAX_CHUNKS] = {}, ev_row[MAX_CHUNKS * ROWS_PER_CHUNK] = {};
+  int stream_chunks = 8;         // A2DS_STREAM_CHUNKS (1: off)
+  int stream_min_elems = 200000; // A2DS_STREAM_MIN_ELEMS: smaller meshes are not worth the launch tails
+  int up_chunks = 0, up_rows = 0;   // chunks / node rows of the upload in flight
+  int up_hi[MAX_CHUNKS] = {};       // node rows [0, up_hi[k]) are on the device once ev_up[k] has fired
+  struct StreamPlan splan[2];       // [ghost-touching ranges last]
+  std::vector<int> h_send_nodes;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   int n_sm = 0;
   int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
@@ -206,6 +229,12 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < a2ds_ctx::MAX_CHUNKS; k++) CU(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming));
+  for (cudaEvent_t &e : c->ev_row) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (const char *env = getenv("A2DS_STREAM_CHUNKS"))
+    c->stream_chunks = std::max(1, std::min((int)a2ds_ctx::MAX_CHUNKS, atoi(env)));
+  if (const char *env = getenv("A2DS_STREAM_MIN_ELEMS")) c->stream_min_elems = std::max(1, atoi(env));
   CU(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_used, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev0));
@@ -227,6 +256,7 @@ static void free_lists(a2ds_ctx *c) {
     c->list_len[k].clear();
   }
   c->lists_ready = false;
+  c->splan[0].ready = c->splan[1].ready = false;
 }
 
 extern "C" int a2ds_destroy(a2ds_ctx *c) {
@@ -234,6 +264,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->copy_stream);
+  cudaStreamSynchronize(c->d2h_stream);
   cudaStreamSynchronize(c->stream);
   for (auto &m : c->mats)
     for (void *p : m.owned) cudaFree(p);
@@ -248,6 +279,9 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0);
   cudaEventDestroy(c->evk1); cudaEventDestroy(c->evr0); cudaEventDestroy(c->evr1);
   cudaEventDestroy(c->ev_state); cudaEventDestroy(c->ev_used);
+  for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_row) cudaEventDestroy(e);
+  cudaStreamDestroy(c->d2h_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -259,6 +293,7 @@ extern "C" int a2ds_synchronize(a2ds_ctx *c) {
   A2DS_TRY
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->copy_stream));
+  CU(cudaStreamSynchronize(c->d2h_stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
   A2DS_CATCH(a2ds_synchronize)
@@ -434,8 +469,16 @@ extern "C" int a2ds_set_state(a2ds_ctx *c, int n_given, const double *u) {
   // after everything queued so far that reads the old state ...
   CU(cudaEventRecord(c->ev_used, c->stream));
   CU(cudaStreamWaitEvent(c->copy_stream, c->ev_used, 0));
-  CU(cudaMemcpyAsync(c->u, u, 6 * (size_t)n_given * sizeof(double), cudaMemcpyHostToDevice,
-                     c->copy_stream));
+  // in row chunks when the mesh is large enough for the streamed assembly to use them
+  const int C = (c->n_elems >= c->stream_min_elems && n_given >= 64 * c->stream_chunks) ? c->stream_chunks : 1;
+  for (int k = 0; k < C; k++) {
+    const size_t lo = (size_t)n_given * k / C, hi = (size_t)n_given * (k + 1) / C;
+    CU(cudaMemcpyAsync(c->u + 6 * lo, u + 6 * lo, 6 * (hi - lo) * sizeof(double), cudaMemcpyHostToDevice,
+                       c->copy_stream));
+    CU(cudaEventRecord(c->ev_up[k], c->copy_stream));
+    c->up_hi[k] = (int)hi;
+  }
+  c->up_chunks = C; c->up_rows = n_given;
   // ... and before the first consumer of the new one (state_wait)
   CU(cudaEventRecord(c->ev_state, c->copy_stream));
   c->state_pending = true;
@@ -1110,6 +1153,8 @@ extern "C" int a2ds_set_halo(a2ds_ctx *c, int n_peers, const int *peer_rank, con
   c->send_ptr.assign(send_ptr, send_ptr + n_peers + 1);
   c->recv_ptr.assign(recv_ptr, recv_ptr + n_peers + 1);
   const size_t ns = send_ptr[n_peers], nr = recv_ptr[n_peers];
+  c->h_send_nodes.assign(send_nodes, send_nodes + ns);
+  c->splan[0].ready = c->splan[1].ready = false;
   if (upload(&c->send_nodes, send_nodes, ns, c->stream)) return 1;
   if (upload(&c->recv_nodes, recv_nodes, nr, c->stream)) return 1;
   cudaFree(c->send_buf); cudaFree(c->recv_buf);
@@ -1388,6 +1433,95 @@ static int launch_mass(a2ds_ctx *c, KParams &p) {
   return 0;
 }
 
+// element kernels of one class list (p.elem_list / p.n_list set) for the outputs in `what`
+static int launch_class(a2ds_ctx *c, KParams &p, int cls, int what) {
+  const bool cpl = cls >= 2;
+  int rc = 0;
+  if ((cls & 1) == 0) {
+    switch (what) {
+      case 0: break;
+      case 1: rc = launch_elem<true, false, false, false>(c, p, cpl); break;
+      case 2: rc = launch_elem<false, true, false, false>(c, p, cpl); break;
+      case 3: rc = launch_elem<true, true, false, false>(c, p, cpl); break;
+      case 4: rc = launch_elem<false, false, true, false>(c, p, cpl); break;
+      case 7: rc = launch_elem<true, true, true, false>(c, p, cpl); break;
+      default: return fail("assemble: unsupported output combination");
+    }
+  } else {
+    // nonlinear strain model: residual and tangent about the current state.
+    // Its geometric stiffness (a finite difference about the ZERO state in the
+    // reference, TACSShellElement.h:705-751) is the same linear-in-state term as
+    // for the linear model and is evaluated with the linear-model kernel.
+    switch (what) {
+      case 0: break;
+      case 1: rc = launch_elem<true, false, false, true>(c, p, cpl); break;
+      case 2: rc = launch_elem<false, true, false, true>(c, p, cpl); break;
+      case 3: rc = launch_elem<true, true, false, true>(c, p, cpl); break;
+      case 4: rc = launch_elem<false, false, true, false>(c, p, cpl); break;
+      case 7:
+        rc = launch_elem<true, true, false, true>(c, p, cpl);
+        if (!rc) rc = launch_elem<false, false, true, false>(c, p, cpl);
+        break;
+      default: return fail("assemble: unsupported output combination");
+    }
+  }
+  return rc;
+}
+
+// Streamed assembly plan: C element ranges in natural order (ranges that refer to ghost nodes
+// last when a forward halo exchange is pending: it needs the whole upload), C chunks of the
+// owned residual rows and, for each, the launch position after which nothing adds to it any
+// more (C: only after the reverse halo exchange).
+static void build_stream_plan(a2ds_ctx *c, bool ghost_last, StreamPlan &pl) {
+  const int C = c->stream_chunks, ne = c->n_elems, no = c->n_owned;
+  pl.C = C;
+  pl.e0.assign(C + 1, 0);
+  // equal ranges, the last one halved: what follows the last range (its residual rows going
+  // home) is exposed, what follows the others is not
+  for (int k = 1; k < C; k++) {
+    const double f = C > 2 ? (k < C - 1 ? (double)k / (C - 1) : 1.0 - 0.5 / (C - 1)) : (double)k / C;
+    pl.e0[k] = (int)(f * ne) & ~63;   // whole batches, 16-byte aligned tables
+  }
+  pl.e0[C] = ne;
+  pl.max_node.assign(C, -1);
+  const int *conn = c->h_conn.data();
+  for (int k = 0; k < C; k++) {
+    int mx = -1;
+    for (size_t i = 4 * (size_t)pl.e0[k]; i < 4 * (size_t)pl.e0[k + 1]; i++) mx = std::max(mx, conn[i]);
+    pl.max_node[k] = mx;
+  }
+  pl.order.clear();
+  for (int k = 0; k < C; k++)
+    if (!(ghost_last && pl.max_node[k] >= no)) pl.order.push_back(k);
+  for (int k = 0; k < C; k++)
+    if (ghost_last && pl.max_node[k] >= no) pl.order.push_back(k);
+  std::vector<int> pos(C);
+  for (int i = 0; i < C; i++) pos[pl.order[i]] = i;
+  std::vector<signed char> node_pos((size_t)std::max(no, 1), -1);
+  for (int k = 0; k < C; k++)
+    for (size_t i = 4 * (size_t)pl.e0[k]; i < 4 * (size_t)pl.e0[k + 1]; i++) {
+      const int n = conn[i];
+      if (n < no && node_pos[n] < pos[k]) node_pos[n] = (signed char)pos[k];
+    }
+  if (c->has_halo)   // owned rows that receive ghost contributions from peers
+    for (int n : c->h_send_nodes) node_pos[n] = (signed char)C;
+  const int R = C * a2ds_ctx::ROWS_PER_CHUNK;
+  pl.row_lo.assign(R + 1, 0);
+  for (int j = 0; j <= R; j++) pl.row_lo[j] = (int)((long long)no * j / R);
+  pl.row_pos.assign(R, 0);
+  for (int j = 0; j < R; j++) {
+    int mx = 0;
+    for (int n = pl.row_lo[j]; n < pl.row_lo[j + 1]; n++) mx = std::max(mx, (int)node_pos[n]);
+    pl.row_pos[j] = mx;
+  }
+  pl.ready = true;
+}
+
+struct AsmReq;
+// the element launches, the residual halo, its boundary conditions and its way back of a
+// streamed assembly (see a2ds_ctx::d2h_stream); the outputs are zeroed already
+static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int what);
+
 // One assembly request.  what: bit 0 residual, bit 1 tangent, bit 2 geometric stiffness,
 // bit 3 mass matrix (into mmat, which may be the tangent matrix: gamma term of the Jacobian).
 struct AsmReq {
@@ -1407,6 +1541,75 @@ static int apply_mat_bcs(a2ds_ctx *c, int mat) {
                                                      m.blk_dev, m.A);
   c->last_launches++;
   return 0;
+}
+
+
+static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int what) {
+  const bool RES = what & 1;
+  const bool ghost_last = c->halo_pending;
+  StreamPlan &pl = c->splan[ghost_last ? 1 : 0];
+  if (!pl.ready || pl.C != c->stream_chunks) build_stream_plan(c, ghost_last, pl);
+  const int C = pl.C;
+  const bool pending = c->state_pending;
+  int waited = -1;           // upload chunks [0, waited] are ordered before the main stream's next work
+  bool halo_done = !c->halo_pending;
+  // finish the row chunks that are final after launch position `at` and send them home
+  const int R = (int)pl.row_pos.size();
+  auto finish_rows = [&](int at) -> int {
+    if (!RES) return 0;
+    for (int j = 0; j < R; j++) {
+      if (pl.row_pos[j] != at) continue;
+      const int lo = pl.row_lo[j];
+      while (j + 1 < R && pl.row_pos[j + 1] == at) j++;   // neighbours that are final together
+      const int hi = pl.row_lo[j + 1];
+      if (hi <= lo) continue;
+      if (c->n_bc) {
+        k_res_bcs<<<(6 * c->n_bc + 255) / 256, 256, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars,
+                                                                    c->bc_vals, c->u, c->res, lo, hi);
+        c->last_launches++;
+      }
+      if (rq.res_host) {
+        CU(cudaEventRecord(c->ev_row[j], c->stream));
+        CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_row[j], 0));
+        CU(cudaMemcpyAsync(rq.res_host + 6 * (size_t)lo, c->res + 6 * (size_t)lo,
+                           6 * (size_t)(hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
+      }
+    }
+    return 0;
+  };
+  const KParams base = p;
+  for (int at = 0; at < C; at++) {
+    const int k = pl.order[at];
+    const int e0 = pl.e0[k], e1 = pl.e0[k + 1];
+    const bool ghost = pl.max_node[k] >= c->n_owned;
+    if (pending) {
+      // rows this range reads: up to its highest node, or everything that is coming
+      const int need = (ghost && !halo_done) ? c->up_rows : std::min(pl.max_node[k] + 1, c->up_rows);
+      int w = 0;
+      while (w < c->up_chunks - 1 && c->up_hi[w] < need) w++;
+      if (w > waited) { CU(cudaStreamWaitEvent(c->stream, c->ev_up[w], 0)); waited = w; }
+    }
+    if (ghost && !halo_done) {   // the deferred forward exchange: packs owned rows of the whole upload
+      if (halo_exchange(c, c->u, false)) return 1;
+      halo_done = true;
+    }
+    if (e1 > e0) {
+      p = base;
+      p.elem_list = nullptr; p.n_list = e1 - e0;
+      p.conn = base.conn + 4 * (size_t)e0; p.elem_comp = base.elem_comp + e0;
+      if (base.Koff) p.Koff = base.Koff + 16 * (size_t)e0;
+      if (base.Goff) p.Goff = base.Goff + 16 * (size_t)e0;
+      if (launch_class(c, p, cls, what)) return 1;
+    }
+    if (finish_rows(at)) return 1;
+  }
+  if (pending && waited < c->up_chunks - 1) CU(cudaStreamWaitEvent(c->stream, c->ev_state, 0));
+  c->state_pending = false;
+  if (!halo_done && halo_exchange(c, c->u, false)) return 1;
+  c->halo_pending = false;
+  CU(cudaEventRecord(c->evk1, c->stream));
+  if (RES && halo_exchange(c, c->res, true)) return 1;
+  return finish_rows(C);
 }
 
 static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
@@ -1451,7 +1654,14 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     c->last_launches += (RES ? 1 : 0) + (ikz ? 0 : (KM ? 1 : 0) + (GM ? 1 : 0)) + (MM && !(KM && mmat == kmat) ? 1 : 0);
   }
 
-  if (state_wait(c)) return 1;  // the upload overlapped the zeroing above
+  // streamed: one class, natural element order, atomic scatter, host I/O in the step
+  int only_cls = -1, n_nonempty = 0;
+  for (int cls = 0; cls < 4; cls++)
+    if (c->list_len[cls][0] > 0) { n_nonempty++; only_cls = cls; }
+  const bool streamed = c->stream_chunks > 1 && rq.zero && rq.finish && c->n_colors == 1 && n_nonempty == 1 &&
+                        c->list_dev[only_cls][0] == nullptr && c->n_elems >= c->stream_min_elems &&
+                        !MM && !MRES && what != 0 && !c->pz_K && !c->pz_G &&
+                        ((c->state_pending && c->up_chunks > 1) || (rq.res_host && RES));
 
   KParams p;
   memset(&p, 0, sizeof(p));
@@ -1462,62 +1672,40 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   if (GM) { p.Gval = c->mats[gmat].A; p.Goff = c->mats[gmat].off; }
 
   CU(cudaEventRecord(c->evk0, c->stream));
-  for (int col = 0; col < c->n_colors; col++) {
-    for (int cls = 0; cls < 4; cls++) {
-      const bool cpl = cls >= 2;
-      p.n_list = c->list_len[cls][col];
-      p.elem_list = c->list_dev[cls][col];
-      if (p.n_list == 0) continue;
-      int rc = 0;
-      if ((cls & 1) == 0) {
-        switch (what) {
-          case 0: break;
-          case 1: rc = launch_elem<true, false, false, false>(c, p, cpl); break;
-          case 2: rc = launch_elem<false, true, false, false>(c, p, cpl); break;
-          case 3: rc = launch_elem<true, true, false, false>(c, p, cpl); break;
-          case 4: rc = launch_elem<false, false, true, false>(c, p, cpl); break;
-          case 7: rc = launch_elem<true, true, true, false>(c, p, cpl); break;
-          default: return fail("assemble: unsupported output combination");
+  if (streamed) {
+    if (run_streamed(c, rq, p, only_cls, what)) return 1;
+  } else {
+    if (state_wait(c)) return 1;  // the upload overlapped the zeroing above
+    for (int col = 0; col < c->n_colors; col++) {
+      for (int cls = 0; cls < 4; cls++) {
+        p.n_list = c->list_len[cls][col];
+        p.elem_list = c->list_dev[cls][col];
+        if (p.n_list == 0) continue;
+        if (launch_class(c, p, cls, what)) return 1;
+        if (MM || MRES) {
+          // mass path: same element lists (and colours), both element classes alike
+          KParams pm = p;
+          pm.u = c->udd; pm.alpha = rq.mscale;
+          int rc = 0;
+          if (MM) { pm.Kval = c->mats[mmat].A; pm.Koff = c->mats[mmat].off; }
+          if (MM && MRES) rc = launch_mass<true, true>(c, pm);
+          else if (MM) rc = launch_mass<false, true>(c, pm);
+          else rc = launch_mass<true, false>(c, pm);
+          if (rc) return rc;
         }
-      } else {
-        // nonlinear strain model: residual and tangent about the current state.
-        // Its geometric stiffness (a finite difference about the ZERO state in the
-        // reference, TACSShellElement.h:705-751) is the same linear-in-state term as
-        // for the linear model and is evaluated with the linear-model kernel.
-        switch (what) {
-          case 0: break;
-          case 1: rc = launch_elem<true, false, false, true>(c, p, cpl); break;
-          case 2: rc = launch_elem<false, true, false, true>(c, p, cpl); break;
-          case 3: rc = launch_elem<true, true, false, true>(c, p, cpl); break;
-          case 4: rc = launch_elem<false, false, true, false>(c, p, cpl); break;
-          case 7:
-            rc = launch_elem<true, true, false, true>(c, p, cpl);
-            if (!rc) rc = launch_elem<false, false, true, false>(c, p, cpl);
-            break;
-          default: return fail("assemble: unsupported output combination");
-        }
-      }
-      if (rc) return rc;
-      if (MM || MRES) {
-        // mass path: same element lists (and colours), both element classes alike
-        KParams pm = p;
-        pm.u = c->udd; pm.alpha = rq.mscale;
-        if (MM) { pm.Kval = c->mats[mmat].A; pm.Koff = c->mats[mmat].off; }
-        if (MM && MRES) rc = launch_mass<true, true>(c, pm);
-        else if (MM) rc = launch_mass<false, true>(c, pm);
-        else rc = launch_mass<true, false>(c, pm);
-        if (rc) return rc;
       }
     }
   }
-  CU(cudaEventRecord(c->evk1, c->stream));
+  if (!streamed) CU(cudaEventRecord(c->evk1, c->stream));
   if (!rq.finish) return 0;
   // ghost residual contributions -> owners (TACSBVec::beginSetValues/endSetValues, ADD)
-  if (RES && halo_exchange(c, c->res, true)) return 1;
-  if (RES && c->n_bc) {
-    k_res_bcs<<<(6 * c->n_bc + 255) / 256, 256, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars,
-                                                                c->bc_vals, c->u, c->res, c->n_owned);
-    c->last_launches++;
+  if (!streamed) {
+    if (RES && halo_exchange(c, c->res, true)) return 1;
+    if (RES && c->n_bc) {
+      k_res_bcs<<<(6 * c->n_bc + 255) / 256, 256, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars,
+                                                                  c->bc_vals, c->u, c->res, 0, c->n_owned);
+      c->last_launches++;
+    }
   }
   // ghost block rows -> owners (only for matrices with a halo plan), then the BCs
   if (KM && mat_halo_reverse(c, c->mats[kmat])) return 1;
@@ -1530,8 +1718,12 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, c->stream));
   if (rq.res_host) {
-    CU(cudaMemcpyAsync(rq.res_host, c->res, 6 * (size_t)c->n_owned * sizeof(double),
-                       cudaMemcpyDeviceToHost, c->stream));
+    if (streamed && RES) {   // the rows went back chunk by chunk
+      CU(cudaStreamSynchronize(c->d2h_stream));
+    } else {
+      CU(cudaMemcpyAsync(rq.res_host, c->res, 6 * (size_t)c->n_owned * sizeof(double),
+                         cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
   }
   return 0;

@@ -91,12 +91,13 @@ __global__ void k_pat_rows(int nn, const int *conn, const int *ptr, const int *a
 }
 
 // residual BC rows: r = u - ubar on owned nodes (TACSBVec::applyBCs, TACSBVec.cpp:546-585)
+// (rows [row_lo, row_hi) only: the streamed assembly finishes the residual chunk by chunk)
 __global__ void k_res_bcs(int n_bc, const int *nodes, const int *vars, const double *vals,
-                          const double *u, double *res, int n_owned) {
+                          const double *u, double *res, int row_lo, int row_hi) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 6 * n_bc) return;
   const int b = t / 6, k = t - 6 * b, n = nodes[b];
-  if (n < n_owned && (vars[b] & (1 << k))) res[6 * (size_t)n + k] = u[6 * (size_t)n + k] - vals[t];
+  if (n >= row_lo && n < row_hi && (vars[b] & (1 << k))) res[6 * (size_t)n + k] = u[6 * (size_t)n + k] - vals[t];
 }
 
 // vector BC rows set to zero (TACSBVec::applyBCs without a state vector, TACSBVec.cpp:570-584)

@@ -148,6 +148,55 @@ def test_assembly_vs_oracle(a2ds, orc, name, mode):
 
 
 @pytest.mark.parametrize("name", ["plate", "cylinder"])
+@pytest.mark.parametrize("chunks", [3, 8])
+def test_streamed_assembly_vs_oracle(a2ds, orc, name, chunks, monkeypatch):
+    """host state up / residual down in row chunks with the element kernel launched per element
+    range in between (run_streamed, csrc/a2ds.cu): same results as the oracle, for every entry
+    point that takes host buffers, with prescribed boundary values inside every row chunk"""
+    monkeypatch.setenv("A2DS_STREAM_CHUNKS", str(chunks))
+    monkeypatch.setenv("A2DS_STREAM_MIN_ELEMS", "1")
+    if name == "plate":
+        conn, X, bcn = a2ds.meshes.plate(40, 31, bump=2e-2)
+    else:
+        conn, X, bcn = a2ds.meshes.cylinder(48, 29)
+    n = len(X)
+    u = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)
+    Cs, eth = a2ds.iso_shell_tables()
+    bc_vars = np.full(len(bcn), 63, dtype=np.int32); bc_vars[::2] = 0b000111
+    bc_vals = np.zeros((len(bcn), 6)); bc_vals[:, 0] = -1e-5
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n)
+    asm.set_nodes(X)
+    asm.set_components(Cs[None], eth[None])
+    asm.set_bcs(bcn, bc_vars, bc_vals)
+    kmat = asm.create_mat(); gmat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(kmat)
+    comp = orc.make_comp(0, Cs, eth)
+    ec = np.zeros(len(conn), dtype=np.int32)
+    r_o, k_o = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    _, g_o = orc.assemble(3, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    for rep in range(2):
+        asm.set_state(u)               # upload in flight when the assembly starts
+        r = asm.assembleAll(kmat, gmat)
+        assert asm.last_timing()[1] >= chunks, "the streamed path did not run"
+        assert relmax(r, r_o) < RES_TOL
+        assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL
+        assert relmax(asm.mat_values(gmat), g_o) < MAT_TOL
+    asm.set_state(0 * u)
+    asm.set_state(u)
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, gmat)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(gmat), k_o) < MAT_TOL
+    # state resident, residual streamed back
+    r = asm.assembleRes()
+    assert relmax(r, r_o) < RES_TOL
+    asm.set_state(u)
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, kmat)
+    assert relmax(asm.mat_values(kmat), g_o) < MAT_TOL
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["plate", "cylinder"])
 def test_assembly_vs_reference_schur_and_parallel(a2ds, ref, name):
     """drop-in style: connectivity, nodes, BCs and BOTH matrix patterns are taken from the
     reference assembler; values must match block for block."""

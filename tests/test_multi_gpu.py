@@ -32,3 +32,10 @@ def test_two_rank_assembly_matches_single_gpu(world):
     assert "MGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MGPU_PARALLELMAT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MGPU_NATIVE_PARTITION_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    if world == 2:
+        # the same with the streamed assembly forced on these small slabs: state chunks, element
+        # ranges with the ghost-touching ones last, forward halo in between, residual chunks back
+        env = dict(os.environ, A2DS_STREAM_CHUNKS="3", A2DS_STREAM_MIN_ELEMS="1")
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        assert "MGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+        assert "MGPU_NATIVE_PARTITION_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
