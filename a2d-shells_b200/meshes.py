@@ -40,6 +40,38 @@ def cylinder(ntheta, nx, radius=0.2, length=0.4, x0=0.0):
     return conn, X, ends
 
 
+def plate9(nx, ny, lx=1.0, ly=1.0, bump=1e-3):
+    """The same plate meshed with nx x ny 9-node elements (TACSQuad9Shell): a (2 nx + 1) x
+    (2 ny + 1) node grid, element node order = tensor order of TACSShellQuadBasis<3>
+    (TACSShellElementQuadBasis.h:147-150: xi fastest, 3 x 3).  Returns conn[ne,9], X, BC nodes."""
+    mx, my = 2 * nx + 1, 2 * ny + 1
+    ii, jj = np.meshgrid(np.arange(mx), np.arange(my), indexing="xy")   # node id = j*mx + i
+    x = ii.ravel() * (lx / (mx - 1)); y = jj.ravel() * (ly / (my - 1))
+    z = bump * np.sin(2 * np.pi * x / lx) * np.sin(2 * np.pi * y / ly)
+    X = np.stack([x, y, z], axis=1)
+    ei, ej = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    n0 = (2 * ej * mx + 2 * ei).ravel()
+    conn = np.stack([n0 + b * mx + a for b in range(3) for a in range(3)], axis=1).astype(np.int32)
+    bc_nodes = (np.arange(my) * mx).astype(np.int32)
+    return conn, X, bc_nodes
+
+
+def cylinder9(ntheta, nx, radius=0.2, length=0.4):
+    """Closed cylinder of ntheta x nx 9-node elements (2 ntheta nodes around, 2 nx + 1 along);
+    nodes ON the cylinder (the mid-side nodes too).  Returns conn[ne,9], X, end-ring nodes."""
+    mt, mx = 2 * ntheta, 2 * nx + 1
+    tt, xx = np.meshgrid(np.arange(mt), np.arange(mx), indexing="xy")   # node id = ix*mt + it
+    th = tt.ravel() * (2 * np.pi / mt)
+    x = xx.ravel() * (length / (mx - 1))
+    X = np.stack([x, -radius * np.sin(th), -radius * np.cos(th)], axis=1)
+    et, ex = np.meshgrid(np.arange(ntheta), np.arange(nx), indexing="xy")
+    et = et.ravel(); ex = ex.ravel()
+    conn = np.stack([(2 * ex + b) * mt + (2 * et + a) % mt for b in range(3) for a in range(3)],
+                    axis=1).astype(np.int32)
+    ends = np.concatenate([np.arange(mt), (mx - 1) * mt + np.arange(mt)]).astype(np.int32)
+    return conn, X, ends
+
+
 def cubed_sphere(n, radius=0.3, shuffle_seed=None):
     """Closed sphere meshed from the six faces of a cube (n x n quads each): an UNSTRUCTURED
     quad mesh — the 8 cube corners have valence 3, no global (i, j) numbering exists.

@@ -63,63 +63,75 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def strain(comp, X, q):
-    e = np.zeros(36); det = np.zeros(4)
-    lib().oracle_strain(C.byref(comp), _p(np.ascontiguousarray(X, dtype=np.float64)),
+def _fn(name, order):
+    """entry point for the element order: 2 = 4-node (oracle_*), 3 = 9-node (oracle9_*)"""
+    assert order in (2, 3)
+    return getattr(lib(), ("oracle_" if order == 2 else "oracle9_") + name)
+
+
+def strain(comp, X, q, order=2):
+    nn = order * order
+    e = np.zeros(9 * nn); det = np.zeros(nn)
+    _fn("strain", order)(C.byref(comp), _p(np.ascontiguousarray(X, dtype=np.float64)),
                         _p(np.ascontiguousarray(q, dtype=np.float64)), _p(e), _p(det))
-    return e.reshape(4, 9), det
+    return e.reshape(nn, 9), det
 
 
-def residual(comp, X, q):
-    r = np.zeros(24)
-    lib().oracle_residual(C.byref(comp), _p(np.ascontiguousarray(X, dtype=np.float64)),
+def residual(comp, X, q, order=2):
+    r = np.zeros(6 * order * order)
+    _fn("residual", order)(C.byref(comp), _p(np.ascontiguousarray(X, dtype=np.float64)),
                           _p(np.ascontiguousarray(q, dtype=np.float64)), _p(r))
     return r
 
 
-def jacobian(comp, X, q, alpha=1.0):
-    r = np.zeros(24); m = np.zeros(576)
-    lib().oracle_jacobian(C.byref(comp), C.c_double(alpha),
-                          _p(np.ascontiguousarray(X, dtype=np.float64)),
-                          _p(np.ascontiguousarray(q, dtype=np.float64)), _p(r), _p(m))
-    return r, m.reshape(24, 24)
+def jacobian(comp, X, q, alpha=1.0, order=2):
+    nv = 6 * order * order
+    r = np.zeros(nv); m = np.zeros(nv * nv)
+    _fn("jacobian", order)(C.byref(comp), C.c_double(alpha),
+                           _p(np.ascontiguousarray(X, dtype=np.float64)),
+                           _p(np.ascontiguousarray(q, dtype=np.float64)), _p(r), _p(m))
+    return r, m.reshape(nv, nv)
 
 
-def jacobian_dyn(comp, X, q, qdd, alpha=1.0, gamma=0.0):
+def jacobian_dyn(comp, X, q, qdd, alpha=1.0, gamma=0.0, order=2):
     """res (static + M qdd) and alpha K + gamma M"""
-    r = np.zeros(24); m = np.zeros(576)
-    lib().oracle_jacobian_dyn(C.byref(comp), C.c_double(alpha), C.c_double(gamma),
+    nv = 6 * order * order
+    r = np.zeros(nv); m = np.zeros(nv * nv)
+    _fn("jacobian_dyn", order)(C.byref(comp), C.c_double(alpha), C.c_double(gamma),
                               _p(np.ascontiguousarray(X, dtype=np.float64)),
                               _p(np.ascontiguousarray(q, dtype=np.float64)),
                               _p(np.ascontiguousarray(qdd, dtype=np.float64)), _p(r), _p(m))
-    return r, m.reshape(24, 24)
+    return r, m.reshape(nv, nv)
 
 
-def mat_type(comp, type_, X, q):
-    m = np.zeros(576)
-    lib().oracle_mat_type(C.byref(comp), C.c_int(type_),
-                          _p(np.ascontiguousarray(X, dtype=np.float64)),
-                          _p(np.ascontiguousarray(q, dtype=np.float64)), _p(m))
-    return m.reshape(24, 24)
+def mat_type(comp, type_, X, q, order=2):
+    nv = 6 * order * order
+    m = np.zeros(nv * nv)
+    _fn("mat_type", order)(C.byref(comp), C.c_int(type_),
+                           _p(np.ascontiguousarray(X, dtype=np.float64)),
+                           _p(np.ascontiguousarray(q, dtype=np.float64)), _p(m))
+    return m.reshape(nv, nv)
 
 
-def pattern(n_nodes, conn):
-    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
+def pattern(n_nodes, conn, order=2):
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, order * order)
     rowp = np.zeros(n_nodes + 1, dtype=np.int32)
-    nnz = lib().oracle_pattern(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), None)
+    f = _fn("pattern", order)
+    nnz = f(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), None)
     cols = np.zeros(nnz, dtype=np.int32)
-    lib().oracle_pattern(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), _p(cols))
+    f(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(rowp), _p(cols))
     return rowp, cols
 
 
 def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_vars=None,
-             bc_vals=None, alpha=1.0, gamma=0.0, udd=None, fma=False):
+             bc_vals=None, alpha=1.0, gamma=0.0, udd=None, fma=False, order=2):
     """op 0 res, 1 jacobian (alpha K + gamma M), 2 K, 3 G, 4 M -> (res[n,6] or None,
     A[nnz,6,6] or None); udd: second time derivatives (inertial term of the residual)."""
-    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, order * order)
     X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3)
     u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 6)
     n = X.shape[0]
+    f = getattr(lib_fma() if fma else lib(), "oracle_assemble_dyn" if order == 2 else "oracle9_assemble_dyn")
     arr = (Comp * len(comps))(*comps)
     ec = np.ascontiguousarray(elem_comp, dtype=np.int32)
     nb = 0 if bc_nodes is None else len(bc_nodes)
@@ -129,7 +141,7 @@ def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_var
     res = np.zeros((n, 6)) if op <= 1 else None
     A = np.zeros((len(cols), 6, 6)) if op >= 1 else None
     udd = None if udd is None else np.ascontiguousarray(udd, dtype=np.float64).reshape(-1, 6)
-    miss = (lib_fma() if fma else lib()).oracle_assemble_dyn(C.c_int(op), C.c_double(alpha), C.c_double(gamma), C.c_int(n),
+    miss = f(C.c_int(op), C.c_double(alpha), C.c_double(gamma), C.c_int(n),
                                      C.c_int(conn.shape[0]), _p(conn), _p(ec), arr, _p(X), _p(u),
                                      _p(udd), C.c_int(nb), _p(bn), _p(bv), _p(bx),
                                      _p(np.ascontiguousarray(rowp, dtype=np.int32)),

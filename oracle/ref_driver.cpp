@@ -84,8 +84,20 @@ static TACSShellConstitutive *make_con(const double *p) {
 /* temperature lives on the element object (TACSShellElement.h:35,76) */
 static TACSElement *make_element(const double *p, TACSShellTransform *tr) {
   TACSShellConstitutive *con = make_con(p);
+  /* p[0]: 0 TACSQuad4Shell, 1 TACSQuad4NonlinearShell, 2 TACSQuad9Shell,
+     3 TACSQuad9NonlinearShell (TACSShellElementDefs.h:12-37) */
   if ((int)p[0] == 1) {
     TACSQuad4NonlinearShell *e = new TACSQuad4NonlinearShell(tr, con);
+    e->setTemperature(p[2]);
+    return e;
+  }
+  if ((int)p[0] == 2) {
+    TACSQuad9Shell *e = new TACSQuad9Shell(tr, con);
+    e->setTemperature(p[2]);
+    return e;
+  }
+  if ((int)p[0] == 3) {
+    TACSQuad9NonlinearShell *e = new TACSQuad9NonlinearShell(tr, con);
     e->setTemperature(p[2]);
     return e;
   }
@@ -138,8 +150,9 @@ int refdrv_element(const double *p, int transform_kind, const double *axis, int 
   tr->incref();
   TACSElement *e = make_element(p, tr);
   e->incref();
-  if (res) memset(res, 0, 24 * sizeof(double));
-  if (mat) memset(mat, 0, 576 * sizeof(double));
+  const int nv = e->getNumVariables();   /* 24 (4 nodes) or 54 (9 nodes) */
+  if (res) memset(res, 0, nv * sizeof(double));
+  if (mat) memset(mat, 0, nv * nv * sizeof(double));
   switch (op) {
     case 0: e->addResidual(0, 0.0, X, vars, dvars, ddvars, res); break;
     case 1: e->addJacobian(0, 0.0, alpha, beta, gamma, X, vars, dvars, ddvars, res, mat); break;
@@ -191,10 +204,23 @@ double refdrv_element_batch(const double *p, int transform_kind, const double *a
    ("original") numbering, through TACSCreator exactly as
    TACSMeshLoader::createTACS does (src/io/TACSMeshLoader.cpp:1130-1184):
    NATURAL_ORDER / DIRECT_SCHUR defaults (TACSMeshLoader.h:75-78). */
+void *refdrv_create_n(int nodes_per_elem, int n_nodes, int n_elems, const int *conn,
+                      const int *elem_comp, const double *X, int n_bc, const int *bc_nodes,
+                      const int *bc_ptr, const int *bc_vars, const double *bc_vals, int n_comp,
+                      const double *comp_props, int transform_kind, const double *axis);
 void *refdrv_create(int n_nodes, int n_elems, const int *conn, const int *elem_comp,
                     const double *X, int n_bc, const int *bc_nodes, const int *bc_ptr,
                     const int *bc_vars, const double *bc_vals, int n_comp,
                     const double *comp_props, int transform_kind, const double *axis) {
+  return refdrv_create_n(4, n_nodes, n_elems, conn, elem_comp, X, n_bc, bc_nodes, bc_ptr, bc_vars,
+                         bc_vals, n_comp, comp_props, transform_kind, axis);
+}
+/* the same for elements of nodes_per_elem nodes (9: TACSQuad9Shell, node order of
+   TACSShellQuadBasis<3>::getNodePoint, xi fastest) */
+void *refdrv_create_n(int nodes_per_elem, int n_nodes, int n_elems, const int *conn,
+                      const int *elem_comp, const double *X, int n_bc, const int *bc_nodes,
+                      const int *bc_ptr, const int *bc_vars, const double *bc_vals, int n_comp,
+                      const double *comp_props, int transform_kind, const double *axis) {
   if (!TacsIsInitialized()) {
     MPI_Init(NULL, NULL);
     TacsInitialize();
@@ -208,7 +234,7 @@ void *refdrv_create(int n_nodes, int n_elems, const int *conn, const int *elem_c
   c->creator->setReorderingType(TACSAssembler::NATURAL_ORDER, TACSAssembler::DIRECT_SCHUR);
 
   std::vector<int> ptr(n_elems + 1);
-  for (int i = 0; i <= n_elems; i++) ptr[i] = 4 * i;
+  for (int i = 0; i <= n_elems; i++) ptr[i] = nodes_per_elem * i;
   c->creator->setGlobalConnectivity(n_nodes, n_elems, ptr.data(), conn, elem_comp);
   c->creator->setBoundaryConditions(n_bc, bc_nodes, bc_ptr, bc_vars, bc_vals);
   c->creator->setNodes(X);
@@ -255,7 +281,7 @@ int refdrv_get_conn(void *h, int *conn) {
   RefCtx *c = (RefCtx *)h;
   const int *ptr, *cn;
   c->assembler->getElementConnectivity(&ptr, &cn);
-  memcpy(conn, cn, 4 * (size_t)c->n_elems * sizeof(int));
+  memcpy(conn, cn, (size_t)ptr[c->n_elems] * sizeof(int));
   return 0;
 }
 
@@ -309,6 +335,10 @@ int refdrv_set_temperature(void *h, double T) {
     if (l) l->setTemperature(T);
     TACSQuad4NonlinearShell *nl = dynamic_cast<TACSQuad4NonlinearShell *>(e);
     if (nl) nl->setTemperature(T);
+    TACSQuad9Shell *l9 = dynamic_cast<TACSQuad9Shell *>(e);
+    if (l9) l9->setTemperature(T);
+    TACSQuad9NonlinearShell *nl9 = dynamic_cast<TACSQuad9NonlinearShell *>(e);
+    if (nl9) nl9->setTemperature(T);
   }
   return 0;
 }

@@ -75,18 +75,20 @@ def con_tables(props):
 
 def element(props, op, X, vars_, dvars=None, ddvars=None, alpha=1.0, beta=0.0, gamma=0.0,
             transform=0, axis=(1.0, 0.0, 0.0)):
-    """op: 0 addResidual, 1 addJacobian, 2 K, 3 G, 4 M -> (res[24], mat[24,24])."""
-    z = np.zeros(24)
+    """op: 0 addResidual, 1 addJacobian, 2 K, 3 G, 4 M -> (res[nv], mat[nv,nv]); nv = 24 for
+    the 4-node kinds (props[0] = 0, 1), 54 for the 9-node kinds (2: TACSQuad9Shell, 3: nonlinear)."""
+    nv = 54 if int(props[0]) >= 2 else 24
+    z = np.zeros(nv)
     dv = z if dvars is None else np.ascontiguousarray(dvars, dtype=np.float64)
     ddv = z if ddvars is None else np.ascontiguousarray(ddvars, dtype=np.float64)
-    res = np.zeros(24); mat = np.zeros(576)
+    res = np.zeros(nv); mat = np.zeros(nv * nv)
     ax = np.asarray(axis, dtype=np.float64)
     lib().refdrv_element(_p(np.ascontiguousarray(props)), C.c_int(transform), _p(ax), C.c_int(op),
                          C.c_double(alpha), C.c_double(beta), C.c_double(gamma),
                          _p(np.ascontiguousarray(X, dtype=np.float64)),
                          _p(np.ascontiguousarray(vars_, dtype=np.float64)), _p(dv), _p(ddv),
                          _p(res), _p(mat))
-    return res, mat.reshape(24, 24)
+    return res, mat.reshape(nv, nv)
 
 
 def element_batch(props, op, X, vars_, alpha=1.0, beta=0.0, gamma=0.0, transform=0,
@@ -107,9 +109,11 @@ class RefAssembler:
     """Reference TACSAssembler built through TACSCreator for a quad mesh."""
 
     def __init__(self, conn, X, elem_comp, comp_props, bc_nodes=None, bc_vars=None, bc_vals=None,
-                 transform=0, axis=(1.0, 0.0, 0.0)):
+                 transform=0, axis=(1.0, 0.0, 0.0), nodes_per_elem=4):
         L = lib()
-        conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
+        L.refdrv_create_n.restype = C.c_void_p
+        self.nodes_per_elem = nodes_per_elem   # 9: TACSQuad9Shell components (props[0] = 2, 3)
+        conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, nodes_per_elem)
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3)
         self.n_elems = conn.shape[0]
         self.n_nodes = X.shape[0]
@@ -129,8 +133,8 @@ class RefAssembler:
             np.concatenate([np.asarray(v, dtype=np.float64) for v in bc_vals]) if len(bc_vals) else
             np.zeros(0), dtype=np.float64)
         ax = np.asarray(axis, dtype=np.float64)
-        self.h = C.c_void_p(L.refdrv_create(
-            C.c_int(self.n_nodes), C.c_int(self.n_elems), _p(conn), _p(elem_comp), _p(X),
+        self.h = C.c_void_p(L.refdrv_create_n(
+            C.c_int(nodes_per_elem), C.c_int(self.n_nodes), C.c_int(self.n_elems), _p(conn), _p(elem_comp), _p(X),
             C.c_int(len(bc_nodes)), _p(bc_nodes), _p(ptr), _p(flat_vars), _p(flat_vals),
             C.c_int(comp_props.shape[0]), _p(comp_props), C.c_int(transform), _p(ax)))
         self.new_nodes = np.zeros(self.n_nodes, dtype=np.int32)
@@ -138,7 +142,7 @@ class RefAssembler:
         self._keep = (conn, X, elem_comp, comp_props)
 
     def conn(self):
-        c = np.zeros((self.n_elems, 4), dtype=np.int32)
+        c = np.zeros((self.n_elems, self.nodes_per_elem), dtype=np.int32)
         lib().refdrv_get_conn(self.h, _p(c))
         return c
 

@@ -20,14 +20,42 @@
  * Mass/inertial terms (beta, gamma) are outside the static hot path and are not
  * restated.
  */
+/* Element order: 2 = MITC4 (TACSQuad4Shell / TACSQuad4NonlinearShell, the default build), 3 = MITC9
+ * (TACSQuad9Shell / TACSQuad9NonlinearShell, TACSShellElementDefs.h:16-37) — the reference's
+ * element template is the same for both (TACSShellElement<quadrature, TACSShellQuadBasis<order>,
+ * ...>), so this file is compiled once per order (shell_oracle_q9.c sets ORACLE_ORDER 3 and
+ * includes it); the order-3 entry points are called oracle9_*. */
+#ifndef ORACLE_ORDER
+#define ORACLE_ORDER 2
+#endif
+#if ORACLE_ORDER == 3
+#define oracle_strain oracle9_strain
+#define oracle_residual oracle9_residual
+#define oracle_jacobian oracle9_jacobian
+#define oracle_jacobian_dyn oracle9_jacobian_dyn
+#define oracle_mat_type oracle9_mat_type
+#define oracle_pattern oracle9_pattern
+#define oracle_assemble oracle9_assemble
+#define oracle_assemble_dyn oracle9_assemble_dyn
+#endif
 #include "shell_oracle.h"
 
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
-/* 2-point Gauss abscissa, 15-digit literal: basis/TACSGaussQuadrature.h:26 */
+#define ORD ORACLE_ORDER
+#define NN (ORD * ORD)                                  /* nodes, TACSShellQuadBasis::NUM_NODES :121 */
+#define NV (6 * NN)                                     /* element variables */
+#define NQ (ORD * ORD)                                  /* quadrature points */
+#define NTY (4 * ORD * (ORD - 1) + (ORD - 1) * (ORD - 1)) /* tying points, :125-142 */
+
+/* Gauss abscissae and weights, 15-digit literals: basis/TACSGaussQuadrature.h:23-30 */
 static const double GAUSS_PT = 0.577350269189626;
+#if ORD == 3
+static const double GAUSS_PTS[3] = {-0.774596669241483, 0.0, 0.774596669241483};
+static const double GAUSS_WTS[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
+#endif
 
 /* ---- small algebra, TACSElementAlgebra.h ------------------------------- */
 static void cross3(const double x[3], const double y[3], double o[3]) { /* :39 */
@@ -88,46 +116,101 @@ static void symm_transform_t(const double T[9], const double S[6], double A[6]) 
   A[5] = T[2] * W[2] + T[5] * W[5] + T[8] * W[8];
 }
 
-/* ---- basis, TACSShellElementQuadBasis.h (order 2) ----------------------- */
-typedef struct { double N[4], Nxi[4], Neta[4]; } shape_t;
+/* ---- basis, TACSShellElementQuadBasis.h ---------------------------------- */
+typedef struct { double N[NN], Nxi[NN], Neta[NN]; } shape_t;
 
 static void shape_eval(const double pt[2], shape_t *s) { /* :62-114, :171-232 */
+#if ORD == 2
   double na[2] = {0.5 * (1.0 - pt[0]), 0.5 * (1.0 + pt[0])};
   double nb[2] = {0.5 * (1.0 - pt[1]), 0.5 * (1.0 + pt[1])};
   const double dna[2] = {-0.5, 0.5}, dnb[2] = {-0.5, 0.5};
-  for (int j = 0; j < 2; j++)
-    for (int i = 0; i < 2; i++) {
-      s->N[2 * j + i] = na[i] * nb[j];
-      s->Nxi[2 * j + i] = dna[i] * nb[j];
-      s->Neta[2 * j + i] = na[i] * dnb[j];
+#else /* TacsLagrangeLobattoShapeFuncDerivative<3> :96-104 */
+  const double u = pt[0], v = pt[1];
+  double na[3] = {-0.5 * u * (1.0 - u), (1.0 - u) * (1.0 + u), 0.5 * (1.0 + u) * u};
+  double nb[3] = {-0.5 * v * (1.0 - v), (1.0 - v) * (1.0 + v), 0.5 * (1.0 + v) * v};
+  const double dna[3] = {-0.5 + u, -2.0 * u, 0.5 + u}, dnb[3] = {-0.5 + v, -2.0 * v, 0.5 + v};
+#endif
+  for (int j = 0; j < ORD; j++)
+    for (int i = 0; i < ORD; i++) {
+      s->N[ORD * j + i] = na[i] * nb[j];
+      s->Nxi[ORD * j + i] = dna[i] * nb[j];
+      s->Neta[ORD * j + i] = na[i] * dnb[j];
     }
 }
 /* interpFields<stride,3> :171 */
 static void interp3(const shape_t *s, const double *v, int stride, double f[3]) {
   f[0] = f[1] = f[2] = 0.0;
-  for (int n = 0; n < 4; n++)
+  for (int n = 0; n < NN; n++)
     for (int k = 0; k < 3; k++) f[k] += s->N[n] * v[stride * n + k];
 }
 /* interpFieldsGrad<stride,3> :210 — grad[2k] = d/dxi, grad[2k+1] = d/deta */
 static void interp3_grad(const shape_t *s, const double *v, int stride, double g[6]) {
   for (int k = 0; k < 6; k++) g[k] = 0.0;
-  for (int n = 0; n < 4; n++)
+  for (int n = 0; n < NN; n++)
     for (int k = 0; k < 3; k++) {
       g[2 * k] += s->Nxi[n] * v[stride * n + k];
       g[2 * k + 1] += s->Neta[n] * v[stride * n + k];
     }
 }
 static void node_point(int n, double pt[2]) { /* getNodePoint :147 */
-  pt[0] = -1.0 + 2.0 * (n % 2);
-  pt[1] = -1.0 + 2.0 * (n / 2);
+  pt[0] = -1.0 + (2.0 / (ORD - 1)) * (n % ORD);
+  pt[1] = -1.0 + (2.0 / (ORD - 1)) * (n / ORD);
 }
 /* tying points, getTyingPoint :530-564 with knots {-1,1} / {0}; field per index
    getTyingField :487: 0,1 g11; 2,3 g22; 4 g12; 5,6 g23; 7,8 g13 */
+#if ORD == 2
 static const double TY_PT[9][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}, {0, 0},
                                    {-1, 0}, {1, 0}, {0, -1}, {0, 1}};
 static const int TY_FIELD[9] = {0, 0, 1, 1, 2, 3, 3, 4, 4};
+#else
+/* order 3: "order" knots = 3-point Gauss, "reduced" knots = 2-point Gauss (getTyingKnots :510-512);
+   point of index t within its field, getTyingPoint :530-564; field blocks of 6, 6, 4, 6, 6 */
+#define G3 0.774596669241483
+#define G2 0.577350269189626
+static const double TY_PT[28][2] = {
+    {-G2, -G3}, {G2, -G3}, {-G2, 0.0}, {G2, 0.0}, {-G2, G3}, {G2, G3},     /* g11: reduced x order */
+    {-G3, -G2}, {0.0, -G2}, {G3, -G2}, {-G3, G2}, {0.0, G2}, {G3, G2},     /* g22: order x reduced */
+    {-G2, -G2}, {G2, -G2}, {-G2, G2}, {G2, G2},                            /* g12: reduced x reduced */
+    {-G3, -G2}, {0.0, -G2}, {G3, -G2}, {-G3, G2}, {0.0, G2}, {G3, G2},     /* g23: as g22 */
+    {-G2, -G3}, {G2, -G3}, {-G2, 0.0}, {G2, 0.0}, {-G2, G3}, {G2, G3}};    /* g13: as g11 */
+static const int TY_FIELD[28] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2,
+                                 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4};
+/* TacsLagrangeShapeFunction<order> :17-30, same operation order */
+static void lagrange(int order, double u, const double *knots, double *N) {
+  for (int i = 0; i < order; i++) {
+    N[i] = 1.0;
+    for (int j = 0; j < order; j++)
+      if (i != j) {
+        double d = 1.0 / (knots[i] - knots[j]);
+        N[i] *= (u - knots[j]) * d;
+      }
+  }
+}
+#endif
 /* interpTyingStrain :651-672 (evalTyingInterp :569-616): gty = [g11 g12 g13 g22 g23 0] */
-static void interp_tying(const double pt[2], const double ety[9], double gty[6]) {
+static void interp_tying(const double pt[2], const double ety[NTY], double gty[6]) {
+#if ORD == 3
+  static const double ko[3] = {-G3, 0.0, G3}, kr[2] = {-G2, G2};
+  static const int index[5] = {0, 3, 1, 4, 2};
+  double na[3], nb[3], nar[2], nbr[2], N[28], *w = N;
+  lagrange(3, pt[0], ko, na);
+  lagrange(3, pt[1], ko, nb);
+  lagrange(2, pt[0], kr, nar);
+  lagrange(2, pt[1], kr, nbr);
+  for (int j = 0; j < 3; j++) for (int i = 0; i < 2; i++) *w++ = nar[i] * nb[j];   /* g11 */
+  for (int j = 0; j < 2; j++) for (int i = 0; i < 3; i++) *w++ = na[i] * nbr[j];   /* g22 */
+  for (int j = 0; j < 2; j++) for (int i = 0; i < 2; i++) *w++ = nar[i] * nbr[j];  /* g12 */
+  for (int j = 0; j < 2; j++) for (int i = 0; i < 3; i++) *w++ = na[i] * nbr[j];   /* g23 */
+  for (int j = 0; j < 3; j++) for (int i = 0; i < 2; i++) *w++ = nar[i] * nb[j];   /* g13 */
+  static const int npts[5] = {6, 6, 4, 6, 6};
+  const double *N0 = N;
+  for (int field = 0; field < 5; field++) {
+    gty[index[field]] = 0.0;
+    for (int k = 0; k < npts[field]; k++, N0++, ety++) gty[index[field]] += N0[0] * ety[0];
+  }
+  gty[5] = 0.0;
+  return;
+#else
   double na[2] = {0.5 * (1.0 - pt[0]), 0.5 * (1.0 + pt[0])};
   double nb[2] = {0.5 * (1.0 - pt[1]), 0.5 * (1.0 + pt[1])};
   gty[0] = 0.0; gty[0] += (1.0 * nb[0]) * ety[0]; gty[0] += (1.0 * nb[1]) * ety[1];
@@ -136,6 +219,7 @@ static void interp_tying(const double pt[2], const double ety[9], double gty[6])
   gty[4] = 0.0; gty[4] += (na[0] * 1.0) * ety[5]; gty[4] += (na[1] * 1.0) * ety[6];
   gty[2] = 0.0; gty[2] += (1.0 * nb[0]) * ety[7]; gty[2] += (1.0 * nb[1]) * ety[8];
   gty[5] = 0.0;
+#endif
 }
 
 /* ---- transforms, TACSShellElementTransform.h ---------------------------- */
@@ -169,12 +253,12 @@ static void compute_transform(const oracle_comp_t *c, const double Xxi[6], const
 
 /* ---- element geometry (state independent) ------------------------------- */
 typedef struct {
-  double fn[12], Xdn[36], Tn[36], XdinvTn[36];
-  shape_t sn[4];                     /* shape functions at the nodes */
-  shape_t st[9];                     /* ... at the tying points */
-  double Xxi_t[9][6], n0_t[9][3];
-  shape_t sq[4];                     /* ... at the Gauss points */
-  double pt[4][2], T[4][9], XdinvT[4][9], XdinvzT[4][9], detXd[4];
+  double fn[3 * NN], Xdn[9 * NN], Tn[9 * NN], XdinvTn[9 * NN];
+  shape_t sn[NN];                    /* shape functions at the nodes */
+  shape_t st[NTY];                   /* ... at the tying points */
+  double Xxi_t[NTY][6], n0_t[NTY][3];
+  shape_t sq[NQ];                    /* ... at the Gauss points */
+  double pt[NQ][2], T[NQ][9], XdinvT[NQ][9], XdinvzT[NQ][9], detXd[NQ];
 } geo_t;
 
 /* frame [a|b|c] with the vectors in columns, TacsShellAssembleFrame (TACSShellUtilities.h:8-35) */
@@ -189,9 +273,9 @@ static void frame_x0(const double nxi[6], double Xdz[9]) {
   Xdz[6] = nxi[4]; Xdz[7] = nxi[5]; Xdz[8] = 0.0;
 }
 
-static void geometry(const oracle_comp_t *c, const double X[12], geo_t *g) {
+static void geometry(const oracle_comp_t *c, const double *X, geo_t *g) {
   /* TacsShellComputeNodeNormals, TACSShellUtilities.h:301-342 */
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < NN; i++) {
     double pt[2];
     node_point(i, pt);
     shape_eval(pt, &g->sn[i]);
@@ -212,17 +296,25 @@ static void geometry(const oracle_comp_t *c, const double X[12], geo_t *g) {
     matmul(Xdinv, &g->Tn[9 * i], &g->XdinvTn[9 * i]);
   }
   /* tying-point frames, TACSShellElementModel.h:36-47,62-64 */
-  for (int t = 0; t < 9; t++) {
+  for (int t = 0; t < NTY; t++) {
     shape_eval(TY_PT[t], &g->st[t]);
     interp3_grad(&g->st[t], X, 3, g->Xxi_t[t]);
     interp3(&g->st[t], g->fn, 3, g->n0_t[t]);
   }
   /* Gauss points, TACSShellElement.h:514-534 and TacsShellComputeDispGrad
      (TACSShellUtilities.h:369-393); quadrature order xi fastest
-     (TACSShellElementQuadrature.h:22-27), weight 1 */
-  for (int q = 0; q < 4; q++) {
+     (TACSShellElementQuadrature.h:22-27, :69-77), weight 1 for order 2 */
+  for (int q = 0; q < NQ; q++) {
+#if ORD == 2
+    const double wq = 1.0;
     g->pt[q][0] = (q % 2 == 0) ? -GAUSS_PT : GAUSS_PT;
     g->pt[q][1] = (q / 2 == 0) ? -GAUSS_PT : GAUSS_PT;
+#else
+    const double wq = GAUSS_WTS[q % 3] * GAUSS_WTS[q / 3];
+    g->pt[q][0] = GAUSS_PTS[q % 3];
+    g->pt[q][1] = GAUSS_PTS[q / 3];
+    (void)GAUSS_PT;
+#endif
     shape_eval(g->pt[q], &g->sq[q]);
     double Xxi[6], n0[3], nxi[6];
     interp3_grad(&g->sq[q], X, 3, Xxi);
@@ -232,7 +324,7 @@ static void geometry(const oracle_comp_t *c, const double X[12], geo_t *g) {
     double Xd[9], Xdz[9], Xdinv[9], neg[9];
     frame_xn(Xxi, n0, Xd);
     frame_x0(nxi, Xdz);
-    g->detXd[q] = inv3(Xd, Xdinv) * 1.0;
+    g->detXd[q] = inv3(Xd, Xdinv) * wq;
     matmul(Xdinv, Xdz, neg);
     for (int k = 0; k < 9; k++) neg[k] *= -1.0;
     matmul(Xdinv, g->T[q], g->XdinvT[q]);
@@ -242,20 +334,20 @@ static void geometry(const oracle_comp_t *c, const double X[12], geo_t *g) {
 
 /* ---- quantities that are LINEAR in the element state ---------------------- */
 typedef struct {
-  double d[12];                       /* director d = q x fn, TACSDirector.h:244-267 */
-  double Uxi_t[9][6], d0_t[9][3];     /* at the tying points */
-  double u0x[4][9], u1x[4][9];        /* at the Gauss points */
-  double u0xn[4][9], Ctn_lin[4][9];   /* at the nodes: u0x and T^T(-q^x)T */
+  double d[3 * NN];                   /* director d = q x fn, TACSDirector.h:244-267 */
+  double Uxi_t[NTY][6], d0_t[NTY][3]; /* at the tying points */
+  double u0x[NQ][9], u1x[NQ][9];      /* at the Gauss points */
+  double u0xn[NN][9], Ctn_lin[NN][9]; /* at the nodes: u0x and T^T(-q^x)T */
 } lin_t;
 
-static void linear_maps(const geo_t *g, const double v[24], lin_t *l) {
-  for (int n = 0; n < 4; n++) cross3(&v[6 * n + 3], &g->fn[3 * n], &l->d[3 * n]);
-  for (int t = 0; t < 9; t++) {
+static void linear_maps(const geo_t *g, const double v[NV], lin_t *l) {
+  for (int n = 0; n < NN; n++) cross3(&v[6 * n + 3], &g->fn[3 * n], &l->d[3 * n]);
+  for (int t = 0; t < NTY; t++) {
     interp3_grad(&g->st[t], v, 6, l->Uxi_t[t]);
     interp3(&g->st[t], l->d, 3, l->d0_t[t]);
   }
   /* TacsShellComputeDispGrad, TACSShellUtilities.h:395-418 */
-  for (int q = 0; q < 4; q++) {
+  for (int q = 0; q < NQ; q++) {
     double d0[3], d0xi[6], u0xi[6], u0d[9], u1d[9], tmp[9];
     interp3(&g->sq[q], l->d, 3, d0);
     interp3_grad(&g->sq[q], l->d, 3, d0xi);
@@ -269,7 +361,7 @@ static void linear_maps(const geo_t *g, const double v[24], lin_t *l) {
     trans_matmul(g->T[q], tmp, l->u0x[q]);
   }
   /* TacsShellComputeDrillStrain(Deriv), TACSShellUtilities.h:665-691, 740-759 */
-  for (int n = 0; n < 4; n++) {
+  for (int n = 0; n < NN; n++) {
     double u0xi[6], u0d[9], tmp[9], Cd[9];
     interp3_grad(&g->sn[n], v, 6, u0xi);
     frame_x0(u0xi, u0d);
@@ -289,8 +381,8 @@ static void linear_maps(const geo_t *g, const double v[24], lin_t *l) {
    TACSShellLinearModel::computeTyingStrain(Deriv) (TACSShellElementModel.h:33-77),
    interpTyingStrain, mat3x3SymmTransformTranspose, evalStrain (:440-455),
    drill strain evalDrillStrainDeriv (TACSDirector.h:590-599). */
-static void tying_linear(const geo_t *g, const lin_t *l, double ety[9]) {
-  for (int t = 0; t < 9; t++) {
+static void tying_linear(const geo_t *g, const lin_t *l, double ety[NTY]) {
+  for (int t = 0; t < NTY; t++) {
     const double *Uxi = l->Uxi_t[t], *Xxi = g->Xxi_t[t], *d0 = l->d0_t[t], *n0 = g->n0_t[t];
     switch (TY_FIELD[t]) {
       case 0: ety[t] = (Uxi[0] * Xxi[0] + Uxi[2] * Xxi[2] + Uxi[4] * Xxi[4]); break;
@@ -311,8 +403,8 @@ static void tying_linear(const geo_t *g, const lin_t *l, double ety[9]) {
 }
 /* Bilinear (polar) part of the nonlinear tying strains,
    TACSShellNonlinearModel::computeTyingStrainDeriv (TACSShellElementModel.h:1033-1109) */
-static void tying_bilinear(const lin_t *a, const lin_t *b, double ety[9]) {
-  for (int t = 0; t < 9; t++) {
+static void tying_bilinear(const lin_t *a, const lin_t *b, double ety[NTY]) {
+  for (int t = 0; t < NTY; t++) {
     const double *Ua = a->Uxi_t[t], *Ub = b->Uxi_t[t], *da = a->d0_t[t], *db = b->d0_t[t];
     switch (TY_FIELD[t]) {
       case 0: ety[t] = Ua[0] * Ub[0] + Ua[2] * Ub[2] + Ua[4] * Ub[4]; break;
@@ -332,7 +424,7 @@ static void tying_bilinear(const lin_t *a, const lin_t *b, double ety[9]) {
   }
 }
 /* tying strains -> e[0,1,2,6,7] at Gauss point q */
-static void membrane_shear(const geo_t *g, int q, const double ety[9], double e[9]) {
+static void membrane_shear(const geo_t *g, int q, const double ety[NTY], double e[9]) {
   double gty[6], e0ty[6];
   interp_tying(g->pt[q], ety, gty);
   symm_transform_t(g->XdinvT[q], gty, e0ty);
@@ -342,7 +434,7 @@ static void membrane_shear(const geo_t *g, int q, const double ety[9], double e[
   e[6] = 2.0 * e0ty[4];
   e[7] = 2.0 * e0ty[2];
 }
-static void strain_linear(const geo_t *g, const lin_t *l, const double ety[9], int q,
+static void strain_linear(const geo_t *g, const lin_t *l, const double ety[NTY], int q,
                           double e[9]) {
   membrane_shear(g, q, ety, e);
   const double *u1x = l->u1x[q];
@@ -350,7 +442,7 @@ static void strain_linear(const geo_t *g, const lin_t *l, const double ety[9], i
   e[4] = u1x[4];
   e[5] = u1x[1] + u1x[3];
   double et = 0.0;
-  for (int n = 0; n < 4; n++) {
+  for (int n = 0; n < NN; n++) {
     double etn = 0.5 * (l->Ctn_lin[n][3] + l->u0xn[n][3] - l->Ctn_lin[n][1] - l->u0xn[n][1]);
     et += g->sq[q].N[n] * etn;
   }
@@ -358,7 +450,7 @@ static void strain_linear(const geo_t *g, const lin_t *l, const double ety[9], i
 }
 /* bilinear part: TACSShellNonlinearModel::evalStrainDeriv (TACSShellElementModel.h:1172-1211) */
 static void strain_bilinear(const geo_t *g, const lin_t *a, const lin_t *b,
-                            const double ety_ab[9], int q, double e[9]) {
+                            const double ety_ab[NTY], int q, double e[9]) {
   membrane_shear(g, q, ety_ab, e);
   const double *u0a = a->u0x[q], *u1a = a->u1x[q], *u0b = b->u0x[q], *u1b = b->u1x[q];
   e[3] = (u0b[0] * u1a[0] + u0b[3] * u1a[3] + u0b[6] * u1a[6] + u0a[0] * u1b[0] +
@@ -373,11 +465,11 @@ static void strain_bilinear(const geo_t *g, const lin_t *a, const lin_t *b,
 
 /* ---- forward strain evaluation exactly as the reference orders it ----------
    TACSShellElement::addResidual, TACSShellElement.h:314-373 */
-static void forward_strain(const oracle_comp_t *c, const geo_t *g, const double q[24],
-                           double e_out[36]) {
+static void forward_strain(const oracle_comp_t *c, const geo_t *g, const double *q,
+                           double e_out[9 * NQ]) {
   /* drill strain at the nodes, TacsShellComputeDrillStrain (TACSShellUtilities.h:651-693) */
-  double etn[4];
-  for (int i = 0; i < 4; i++) {
+  double etn[NN];
+  for (int i = 0; i < NN; i++) {
     double u0xi[6], u0d[9], C[9], tmp[9], Ct[9], u0x[9];
     interp3_grad(&g->sn[i], q, 6, u0xi);
     frame_x0(u0xi, u0d);
@@ -395,14 +487,14 @@ static void forward_strain(const oracle_comp_t *c, const geo_t *g, const double 
   lin_t l;
   linear_maps(g, q, &l);
   /* tying strain, computeTyingStrain (TACSShellElementModel.h:33 / :644) */
-  double ety[9];
+  double ety[NTY];
   tying_linear(g, &l, ety);
   if (c->model == 1) {
-    double eb[9];
+    double eb[NTY];
     tying_bilinear(&l, &l, eb);
-    for (int t = 0; t < 9; t++) ety[t] += 0.5 * eb[t];
+    for (int t = 0; t < NTY; t++) ety[t] += 0.5 * eb[t];
   }
-  for (int qp = 0; qp < 4; qp++) {
+  for (int qp = 0; qp < NQ; qp++) {
     double *e = &e_out[9 * qp];
     membrane_shear(g, qp, ety, e);
     const double *u0x = l.u0x[qp], *u1x = l.u1x[qp];
@@ -417,7 +509,7 @@ static void forward_strain(const oracle_comp_t *c, const geo_t *g, const double 
               u1x[3] * u0x[4] + u1x[6] * u0x[7]);
     }
     double et = 0.0;
-    for (int n = 0; n < 4; n++) et += g->sq[qp].N[n] * etn[n];
+    for (int n = 0; n < NN; n++) et += g->sq[qp].N[n] * etn[n];
     e[8] = et;
   }
 }
@@ -436,38 +528,38 @@ static void stress(const double Cs[22], const double e[9], double s[9]) {
   s[8] = Cs[21] * e[8];
 }
 
-void oracle_strain(const oracle_comp_t *c, const double X[12], const double q[24],
-                   double e[36], double detXd[4]) {
+void oracle_strain(const oracle_comp_t *c, const double *X, const double *q,
+                   double *e, double *detXd) {
   geo_t g;
   geometry(c, X, &g);
   forward_strain(c, &g, q, e);
-  for (int i = 0; i < 4; i++) detXd[i] = g.detXd[i];
+  for (int i = 0; i < NQ; i++) detXd[i] = g.detXd[i];
 }
 
 /* residual and (optionally) tangent by exact differentiation of the energy */
 static void res_and_tangent(const oracle_comp_t *c, double alpha, double temperature,
-                            const double X[12], const double q[24], double res[24],
-                            double mat[576]) {
+                            const double *X, const double *q, double *res,
+                            double *mat) {
   geo_t g;
   geometry(c, X, &g);
-  double e[36];
+  double e[9 * NQ];
   forward_strain(c, &g, q, e);
 
   /* stresses of the mechanical strain, TACSShellElement.h:549-574 */
-  double s[4][9];
-  for (int qp = 0; qp < 4; qp++) {
+  double s[NQ][9];
+  for (int qp = 0; qp < NQ; qp++) {
     double em[9];
     for (int i = 0; i < 9; i++) em[i] = e[9 * qp + i] - c->eth[i] * temperature;
     stress(c->Cs, em, s[qp]);
   }
 
-  /* linear maps of the 24 unit directions and of the state */
-  static const int NDOF = 24;
-  lin_t *lu = (lin_t *)malloc(sizeof(lin_t) * 25);
-  lin_t *lq = &lu[24];
-  double ety_lin[24][9];
+  /* linear maps of the unit directions and of the state */
+  static const int NDOF = NV;
+  lin_t *lu = (lin_t *)malloc(sizeof(lin_t) * (NV + 1));
+  lin_t *lq = &lu[NV];
+  double ety_lin[NV][NTY];
   for (int a = 0; a < NDOF; a++) {
-    double v[24];
+    double v[NV];
     memset(v, 0, sizeof(v));
     v[a] = 1.0;
     linear_maps(&g, v, &lu[a]);
@@ -476,11 +568,11 @@ static void res_and_tangent(const oracle_comp_t *c, double alpha, double tempera
   linear_maps(&g, q, lq);
 
   /* B[qp][a][i] = de_i/dq_a at the state */
-  double B[4][24][9];
+  double (*B)[NV][9] = (double (*)[NV][9])malloc(sizeof(double) * NQ * NV * 9);
   for (int a = 0; a < NDOF; a++) {
-    double etb[9];
+    double etb[NTY];
     if (c->model == 1) tying_bilinear(lq, &lu[a], etb);
-    for (int qp = 0; qp < 4; qp++) {
+    for (int qp = 0; qp < NQ; qp++) {
       strain_linear(&g, &lu[a], ety_lin[a], qp, B[qp][a]);
       if (c->model == 1) {
         double eb[9];
@@ -493,7 +585,7 @@ static void res_and_tangent(const oracle_comp_t *c, double alpha, double tempera
   if (res) {
     for (int a = 0; a < NDOF; a++) {
       double r = 0.0;
-      for (int qp = 0; qp < 4; qp++) {
+      for (int qp = 0; qp < NQ; qp++) {
         double t = 0.0;
         for (int i = 0; i < 9; i++) t += B[qp][a][i] * s[qp][i];
         r += g.detXd[qp] * t;
@@ -503,15 +595,15 @@ static void res_and_tangent(const oracle_comp_t *c, double alpha, double tempera
   }
 
   if (mat) {
-    double CB[4][24][9];
-    for (int qp = 0; qp < 4; qp++)
+    double (*CB)[NV][9] = (double (*)[NV][9])malloc(sizeof(double) * NQ * NV * 9);
+    for (int qp = 0; qp < NQ; qp++)
       for (int a = 0; a < NDOF; a++) stress(c->Cs, B[qp][a], CB[qp][a]);
     for (int a = 0; a < NDOF; a++) {
       for (int b = a; b < NDOF; b++) {
-        double etb[9];
+        double etb[NTY];
         if (c->model == 1) tying_bilinear(&lu[a], &lu[b], etb);
         double k = 0.0;
-        for (int qp = 0; qp < 4; qp++) {
+        for (int qp = 0; qp < NQ; qp++) {
           double t = 0.0;
           for (int i = 0; i < 9; i++) t += B[qp][a][i] * CB[qp][b][i];
           if (c->model == 1) {
@@ -521,21 +613,23 @@ static void res_and_tangent(const oracle_comp_t *c, double alpha, double tempera
           }
           k += g.detXd[qp] * t;
         }
-        mat[24 * a + b] = alpha * k;
-        mat[24 * b + a] = alpha * k;
+        mat[NV * a + b] = alpha * k;
+        mat[NV * b + a] = alpha * k;
       }
     }
+    free(CB);
   }
+  free(B);
   free(lu);
 }
 
-void oracle_residual(const oracle_comp_t *c, const double X[12], const double q[24],
-                     double res[24]) {
+void oracle_residual(const oracle_comp_t *c, const double *X, const double *q,
+                     double *res) {
   res_and_tangent(c, 1.0, c->temperature, X, q, res, NULL);
 }
 
-void oracle_jacobian(const oracle_comp_t *c, double alpha, const double X[12],
-                     const double q[24], double res[24], double mat[576]) {
+void oracle_jacobian(const oracle_comp_t *c, double alpha, const double *X,
+                     const double *q, double *res, double *mat) {
   res_and_tangent(c, alpha, c->temperature, X, q, res, mat);
 }
 
@@ -562,79 +656,79 @@ static void skew_mat_skew(const double a[3], const double B[9], const double c[3
   }
 }
 
-static void inertia(const oracle_comp_t *c, double gamma, const double X[12],
-                    const double qdd[24], double res[24], double mat[576]) {
+static void inertia(const oracle_comp_t *c, double gamma, const double *X,
+                    const double *qdd, double *res, double *mat) {
   geo_t g;
   geometry(c, X, &g);
-  double dddot[12], dd[12], d2Tdotd[144], d2Tdotu[144];
-  static const double zero24[24] = {0};
+  double dddot[3 * NN], dd[3 * NN], d2Tdotd[9 * NN * NN], d2Tdotu[9 * NN * NN];
+  static const double zero24[NV] = {0};
   if (!qdd) qdd = zero24;
-  for (int i = 0; i < 4; i++) cross3(&qdd[6 * i + 3], &g.fn[3 * i], &dddot[3 * i]);
+  for (int i = 0; i < NN; i++) cross3(&qdd[6 * i + 3], &g.fn[3 * i], &dddot[3 * i]);
   memset(dd, 0, sizeof(dd));
   memset(d2Tdotd, 0, sizeof(d2Tdotd));
   memset(d2Tdotu, 0, sizeof(d2Tdotu));
-  for (int q = 0; q < 4; q++) {
+  for (int q = 0; q < NQ; q++) {
     const shape_t *sh = &g.sq[q];
     const double det = g.detXd[q];
     double u0dd[3], d0dd[3];
     interp3(sh, qdd, 6, u0dd);
     interp3(sh, dddot, 3, d0dd);
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < NN; i++)
       for (int k = 0; k < 3; k++) {
         if (res) res[6 * i + k] += sh->N[i] * det * (c->mom[0] * u0dd[k] + c->mom[1] * d0dd[k]);
         dd[3 * i + k] += sh->N[i] * det * (c->mom[1] * u0dd[k] + c->mom[2] * d0dd[k]);
       }
-    for (int i = 0; i < 4; i++)
-      for (int j = 0; j < 4; j++) {
+    for (int i = 0; i < NN; i++)
+      for (int j = 0; j < NN; j++) {
         const double nn = sh->N[i] * sh->N[j];
         for (int k = 0; k < 3; k++) {
-          if (mat) mat[24 * (6 * i + k) + 6 * j + k] += gamma * det * c->mom[0] * nn;
-          d2Tdotd[12 * (3 * i + k) + 3 * j + k] += det * c->mom[2] * nn;
-          d2Tdotu[12 * (3 * i + k) + 3 * j + k] += det * c->mom[1] * nn;
+          if (mat) mat[NV * (6 * i + k) + 6 * j + k] += gamma * det * c->mom[0] * nn;
+          d2Tdotd[3 * NN * (3 * i + k) + 3 * j + k] += det * c->mom[2] * nn;
+          d2Tdotu[3 * NN * (3 * i + k) + 3 * j + k] += det * c->mom[1] * nn;
         }
       }
   }
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < NN; i++) {
     if (res) { /* crossProductAdd(1.0, t, dd, r) */
       double r[3];
       cross3(&g.fn[3 * i], &dd[3 * i], r);
       for (int k = 0; k < 3; k++) res[6 * i + 3 + k] += r[k];
     }
     if (!mat) continue;
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < NN; j++) {
       double d[9], tmp[9];
       for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) d[3 * a + b] = gamma * d2Tdotd[12 * (3 * i + a) + 3 * j + b];
+        for (int b = 0; b < 3; b++) d[3 * a + b] = gamma * d2Tdotd[3 * NN * (3 * i + a) + 3 * j + b];
       skew_mat_skew(&g.fn[3 * i], d, &g.fn[3 * j], tmp);
       for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) mat[24 * (6 * i + 3 + a) + 6 * j + 3 + b] -= tmp[3 * a + b];
+        for (int b = 0; b < 3; b++) mat[NV * (6 * i + 3 + a) + 6 * j + 3 + b] -= tmp[3 * a + b];
       for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) d[3 * a + b] = gamma * d2Tdotu[12 * (3 * i + a) + 3 * j + b];
+        for (int b = 0; b < 3; b++) d[3 * a + b] = gamma * d2Tdotu[3 * NN * (3 * i + a) + 3 * j + b];
       skew_mat(&g.fn[3 * i], d, tmp);
       for (int a = 0; a < 3; a++)
         for (int b = 0; b < 3; b++) {
-          mat[24 * (6 * i + 3 + a) + 6 * j + b] += tmp[3 * a + b];
-          mat[24 * (6 * j + b) + 6 * i + 3 + a] += tmp[3 * a + b];
+          mat[NV * (6 * i + 3 + a) + 6 * j + b] += tmp[3 * a + b];
+          mat[NV * (6 * j + b) + 6 * i + 3 + a] += tmp[3 * a + b];
         }
     }
   }
 }
 
-void oracle_jacobian_dyn(const oracle_comp_t *c, double alpha, double gamma, const double X[12],
-                         const double q[24], const double qdd[24], double res[24],
-                         double mat[576]) {
+void oracle_jacobian_dyn(const oracle_comp_t *c, double alpha, double gamma, const double *X,
+                         const double *q, const double *qdd, double *res,
+                         double *mat) {
   oracle_jacobian(c, alpha, X, q, res, mat);
   inertia(c, gamma, X, qdd, res, mat);
 }
 
-void oracle_mat_type(const oracle_comp_t *c, int type, const double X[12],
-                     const double q[24], double mat[576]) {
+void oracle_mat_type(const oracle_comp_t *c, int type, const double *X,
+                     const double *q, double *mat) {
   if (type == 0) {
     res_and_tangent(c, 1.0, c->temperature, X, q, NULL, mat);
     return;
   }
   if (type == 2) { /* TACS_MASS_MATRIX: alpha = beta = 0, gamma = 1, :700-705, :769 */
-    memset(mat, 0, 576 * sizeof(double));
+    memset(mat, 0, NV * NV * sizeof(double));
     inertia(c, 1.0, X, NULL, NULL, mat);
     return;
   }
@@ -644,12 +738,12 @@ void oracle_mat_type(const oracle_comp_t *c, int type, const double X[12],
   nl.model = 1;
   const double dh = 1e-4;
   double norm = 0.0;
-  for (int i = 0; i < 24; i++) norm += q[i] * q[i];
+  for (int i = 0; i < NV; i++) norm += q[i] * q[i];
   norm += c->temperature * c->temperature;
   if (norm == 0.0) norm = 1.0; else norm = sqrt(norm);
   double alpha = 0.5 * norm / dh;
-  double path[24], mp[576], mm[576];
-  for (int i = 0; i < 24; i++) path[i] = dh * q[i] / norm;
+  double path[NV], *mp = (double *)malloc(2 * sizeof(double) * NV * NV), *mm = mp + NV * NV;
+  for (int i = 0; i < NV; i++) path[i] = dh * q[i] / norm;
   double Tp = c->temperature + dh * c->temperature / norm;
   /* For a linear-model element the perturbation is applied to the hidden nonlinear
      twin about the element's own temperature (:735,:747).  A nonlinear-model element
@@ -660,9 +754,10 @@ void oracle_mat_type(const oracle_comp_t *c, int type, const double X[12],
   double Tbase = (c->model == 1) ? Tp : c->temperature;
   double Tm = Tbase - dh * Tbase / norm;
   res_and_tangent(&nl, alpha, Tp, X, path, NULL, mp);
-  for (int i = 0; i < 24; i++) path[i] = -dh * q[i] / norm;
+  for (int i = 0; i < NV; i++) path[i] = -dh * q[i] / norm;
   res_and_tangent(&nl, -alpha, Tm, X, path, NULL, mm);
-  for (int i = 0; i < 576; i++) mat[i] = mp[i] + mm[i];
+  for (int i = 0; i < NV * NV; i++) mat[i] = mp[i] + mm[i];
+  free(mp);
 }
 
 /* ---- single-rank assembly -------------------------------------------------- */
@@ -677,15 +772,15 @@ static int cmp_int(const void *a, const void *b) {
 int oracle_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int *cols) {
   int *cnt = (int *)calloc((size_t)n_nodes + 1, sizeof(int));
   for (int e = 0; e < n_elems; e++)
-    for (int i = 0; i < 4; i++) cnt[conn[4 * e + i] + 1] += 4;
+    for (int i = 0; i < NN; i++) cnt[conn[NN * e + i] + 1] += NN;
   for (int i = 0; i < n_nodes; i++) cnt[i + 1] += cnt[i];
   int *tmp = (int *)malloc(sizeof(int) * (size_t)cnt[n_nodes]);
   int *fill = (int *)malloc(sizeof(int) * (size_t)n_nodes);
   for (int i = 0; i < n_nodes; i++) fill[i] = cnt[i];
   for (int e = 0; e < n_elems; e++)
-    for (int i = 0; i < 4; i++) {
-      int r = conn[4 * e + i];
-      for (int j = 0; j < 4; j++) tmp[fill[r]++] = conn[4 * e + j];
+    for (int i = 0; i < NN; i++) {
+      int r = conn[NN * e + i];
+      for (int j = 0; j < NN; j++) tmp[fill[r]++] = conn[NN * e + j];
     }
   int nnz = 0;
   rowp[0] = 0;
@@ -737,10 +832,10 @@ int oracle_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_e
   if (A) memset(A, 0, sizeof(double) * 36 * (size_t)rowp[n_nodes]);
   /* element loop, src/TACSAssembler.cpp:4038-4054 / :4131-4153 / :4228-4242 */
   for (int e = 0; e < n_elems; e++) {
-    const int *nd = &conn[4 * e];
+    const int *nd = &conn[NN * e];
     const oracle_comp_t *c = &comps[elem_comp ? elem_comp[e] : 0];
-    double Xe[12], qe[24], qdde[24], re[24], me[576];
-    for (int i = 0; i < 4; i++) {
+    double Xe[3 * NN], qe[NV], qdde[NV], re[NV], me[NV * NV];
+    for (int i = 0; i < NN; i++) {
       memcpy(&Xe[3 * i], &X[3 * (size_t)nd[i]], 3 * sizeof(double));
       memcpy(&qe[6 * i], &u[6 * (size_t)nd[i]], 6 * sizeof(double));
       if (udd) memcpy(&qdde[6 * i], &udd[6 * (size_t)nd[i]], 6 * sizeof(double));
@@ -750,17 +845,17 @@ int oracle_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_e
     else if (op == 1) oracle_jacobian_dyn(c, alpha, gamma, Xe, qe, qdde, re, me);
     else oracle_mat_type(c, op - 2, Xe, qe, me);
     if (res && op <= 1)
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < NN; i++)
         for (int k = 0; k < 6; k++) res[6 * (size_t)nd[i] + k] += re[6 * i + k];
     if (A && op >= 1) {
       /* TACSAssembler::addMatValues -> BCSRMat::addRowValues, block (i,j) row-major */
-      for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) {
+      for (int i = 0; i < NN; i++)
+        for (int j = 0; j < NN; j++) {
           int k = find_col(rowp, cols, nd[i], nd[j]);
           if (k < 0) { missing++; continue; }
           double *a = &A[36 * (size_t)k];
           for (int r = 0; r < 6; r++)
-            for (int cc = 0; cc < 6; cc++) a[6 * r + cc] += me[24 * (6 * i + r) + 6 * j + cc];
+            for (int cc = 0; cc < 6; cc++) a[6 * r + cc] += me[NV * (6 * i + r) + 6 * j + cc];
         }
     }
   }

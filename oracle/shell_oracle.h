@@ -30,28 +30,31 @@ typedef struct {
   double temperature; /* TACSShellElement::temperature (TACSShellElement.h:35) */
 } oracle_comp_t;
 
+/* Array sizes below are for the 4-node element (order 2): X 12, q 24, res 24, mat 576, e 36,
+   detXd 4.  The same entry points compiled for the 9-node element (shell_oracle_q9.c) are
+   called oracle9_*: X 27, q 54, res 54, mat 2916 (54 x 54), e 81, detXd 9, conn 9 per element. */
 /* strains e[4][9] and detXd*weight at the 4 Gauss points for state q[24] */
-void oracle_strain(const oracle_comp_t *c, const double X[12], const double q[24],
-                   double e[36], double detXd[4]);
+void oracle_strain(const oracle_comp_t *c, const double *X, const double *q,
+                   double *e, double *detXd);
 
 /* TACSShellElement::addResidual (static terms): res[24] (overwritten) */
-void oracle_residual(const oracle_comp_t *c, const double X[12], const double q[24],
-                     double res[24]);
+void oracle_residual(const oracle_comp_t *c, const double *X, const double *q,
+                     double *res);
 
 /* TACSShellElement::addJacobian with beta = gamma = 0: res[24], mat[576] = alpha*dR/dq
    (both overwritten; either may be NULL) */
-void oracle_jacobian(const oracle_comp_t *c, double alpha, const double X[12],
-                     const double q[24], double res[24], double mat[576]);
+void oracle_jacobian(const oracle_comp_t *c, double alpha, const double *X,
+                     const double *q, double *res, double *mat);
 
 /* the same with the inertial terms: res += M qdd, mat += gamma * M
    (TACSShellElement.h:410-447, 614-648; qdd may be NULL = zero) */
-void oracle_jacobian_dyn(const oracle_comp_t *c, double alpha, double gamma, const double X[12],
-                         const double q[24], const double qdd[24], double res[24],
-                         double mat[576]);
+void oracle_jacobian_dyn(const oracle_comp_t *c, double alpha, double gamma, const double *X,
+                         const double *q, const double *qdd, double *res,
+                         double *mat);
 
 /* TACSShellElement::getMatType: type 0 = stiffness, 1 = geometric stiffness, 2 = mass */
-void oracle_mat_type(const oracle_comp_t *c, int type, const double X[12],
-                     const double q[24], double mat[576]);
+void oracle_mat_type(const oracle_comp_t *c, int type, const double *X,
+                     const double *q, double *mat);
 
 /* Non-zero pattern of the node-to-node matrix, columns sorted per row
    (TACSAssembler::computeLocalNodeToNodeCSR).  Two-pass: call with cols == NULL
@@ -79,6 +82,26 @@ int oracle_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_e
                         const double *X, const double *u, const double *udd, int n_bc,
                         const int *bc_nodes, const int *bc_vars, const double *bc_vals,
                         const int *rowp, const int *cols, double *res, double *A);
+
+/* order 3 (TACSQuad9Shell / TACSQuad9NonlinearShell): same semantics, sizes as stated above */
+void oracle9_strain(const oracle_comp_t *c, const double *X, const double *q, double *e, double *detXd);
+void oracle9_residual(const oracle_comp_t *c, const double *X, const double *q, double *res);
+void oracle9_jacobian(const oracle_comp_t *c, double alpha, const double *X, const double *q,
+                      double *res, double *mat);
+void oracle9_jacobian_dyn(const oracle_comp_t *c, double alpha, double gamma, const double *X,
+                          const double *q, const double *qdd, double *res, double *mat);
+void oracle9_mat_type(const oracle_comp_t *c, int type, const double *X, const double *q, double *mat);
+int oracle9_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int *cols);
+int oracle9_assemble(int op, double alpha, int n_nodes, int n_elems, const int *conn,
+                     const int *elem_comp, const oracle_comp_t *comps, const double *X,
+                     const double *u, int n_bc, const int *bc_nodes, const int *bc_vars,
+                     const double *bc_vals, const int *rowp, const int *cols, double *res,
+                     double *A);
+int oracle9_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_elems,
+                         const int *conn, const int *elem_comp, const oracle_comp_t *comps,
+                         const double *X, const double *u, const double *udd, int n_bc,
+                         const int *bc_nodes, const int *bc_vars, const double *bc_vals,
+                         const int *rowp, const int *cols, double *res, double *A);
 
 #ifdef __cplusplus
 }

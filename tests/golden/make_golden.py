@@ -9,6 +9,7 @@ of the reference itself on seeded inputs:
                  linear class, getMatType(G)
   plate.npz, cylinder.npz : small assembled meshes (reference numbering): pattern,
                  res, K, G of assembleJacobian / assembleMatType, with BCs
+  quad9.npz    : the 9-node element (TACSQuad9Shell): random elements and a small assembled plate
   buckling.npz : lowest 6 buckling eigenvalues of a 40x20 cylinder
   bdf.npz      : what the reference's TACSMeshLoader reads from the decks in this
                  directory (mixed.bdf: hand-written, every card family and field format;
@@ -26,7 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import refdrv  # noqa: E402
-from helpers import random_elements  # noqa: E402
+from helpers import random_elements, random_elements9  # noqa: E402
 
 a2ds = importlib.import_module("a2d-shells_b200")
 AXIS = np.array([0.3, 1.0, 0.2])
@@ -50,6 +51,51 @@ def elements():
                                                    transform=tr, axis=AXIS)
                     out[key + "_G"] = g
     np.savez_compressed(os.path.join(HERE, "elements.npz"), **out)
+
+
+def quad9():
+    """quad9.npz: the 9-node element (TACSQuad9Shell / TACSQuad9NonlinearShell, props kind 2 / 3):
+    4 random elements x {linear, nonlinear} x {natural, ref-axis} x {T=0, T=10 & offset}
+    addJacobian res/K (+ getMatType(G) for the linear class), and a small assembled plate of
+    9-node elements with boundary conditions (reference numbering)"""
+    X, q = random_elements9(4, seed=909)
+    out = dict(X=X, q=q, axis=AXIS)
+    for kind in (0, 1):
+        for tr in (0, 1):
+            for ci, (T, off) in enumerate(((0.0, 0.0), (10.0, 0.3))):
+                p = refdrv.iso_props(kind=2 + kind, temperature=T, t_offset=off)
+                Cs, eth, _ = refdrv.con_tables(p)
+                key = f"k{kind}_t{tr}_c{ci}"
+                rs, ks, gs = [], [], []
+                for e in range(X.shape[0]):
+                    r, k = refdrv.element(p, 1, X[e].ravel(), q[e].ravel(), transform=tr, axis=AXIS)
+                    rs.append(r); ks.append(k)
+                    if kind == 0:
+                        gs.append(refdrv.element(p, 3, X[e].ravel(), q[e].ravel(), transform=tr,
+                                                 axis=AXIS)[1])
+                out[key + "_res"] = np.array(rs); out[key + "_K"] = np.array(ks)
+                out[key + "_Cs"] = Cs; out[key + "_eth"] = eth; out[key + "_T"] = T
+                if kind == 0:
+                    out[key + "_G"] = np.array(gs)
+    conn, Xm, bcn = a2ds.meshes.plate9(3, 2, bump=2e-2)
+    n = len(Xm)
+    p = refdrv.iso_props(kind=2)
+    Cs, eth, _ = refdrv.con_tables(p)
+    bc_vars = [list(range(6)) if i % 2 else [0, 1, 2] for i in range(len(bcn))]
+    bc_vals = [[-1e-5] + [0.0] * (len(v) - 1) for v in bc_vars]
+    ra = refdrv.RefAssembler(conn, Xm, np.zeros(len(conn), dtype=np.int32), p[None], bcn, bc_vars,
+                             bc_vals, nodes_per_elem=9)
+    conn_r, X_r = ra.conn(), ra.nodes()
+    nodes_b, vars_b, vals_b = ra.bcs()
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-5)
+    ra.set_state(u)
+    m = ra.mat_create(0)
+    res = ra.assemble_jacobian(m)
+    blk = ra.mat_block(m, 0)
+    out.update(m_conn=conn_r, m_X=X_r, m_u=u, m_bc_nodes=nodes_b, m_bc_vars=vars_b, m_bc_vals=vals_b,
+               m_rowp=blk["rowp"], m_cols=blk["cols"], m_res=res, m_K=blk["A"], m_Cs=Cs, m_eth=eth)
+    ra.close()
+    np.savez_compressed(os.path.join(HERE, "quad9.npz"), **out)
 
 
 def mesh(name):
@@ -133,9 +179,9 @@ def buckling():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["elements", "plate", "cylinder", "buckling", "bdf"]
+    which = sys.argv[1:] or ["elements", "plate", "cylinder", "buckling", "bdf", "quad9"]
     for w in which:   # e.g. `python make_golden.py bdf` regenerates only bdf.npz
         {"elements": elements, "plate": lambda: mesh("plate"), "cylinder": lambda: mesh("cylinder"),
-         "buckling": buckling, "bdf": bdf}[w]()
+         "buckling": buckling, "bdf": bdf, "quad9": quad9}[w]()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -31,6 +31,27 @@ def random_elements(n, seed, h_range=(-3, 0), state_range=(-6, -3), flat=False):
     return X, q
 
 
+def random_elements9(n, seed, h_range=(-3, 0), state_range=(-6, -3)):
+    """n random curved, distorted, arbitrarily oriented 9-node quads (3 x 3 nodes, xi fastest)
+    with random states.  Returns X[n,9,3], q[n,9,6]."""
+    rng = np.random.default_rng(seed)
+    g = np.array([0.0, 0.5, 1.0])
+    base = np.array([[a, b, 0.0] for b in g for a in g])
+    X = np.zeros((n, 9, 3)); q = np.zeros((n, 9, 6))
+    for e in range(n):
+        h = 10.0 ** rng.uniform(*h_range)
+        curv = rng.uniform(-0.3, 0.3, 3)
+        bend = np.zeros((9, 3))
+        bend[:, 2] = curv[0] * base[:, 0] ** 2 + curv[1] * base[:, 1] ** 2 + curv[2] * base[:, 0] * base[:, 1]
+        Xe = h * (base + bend + 0.06 * rng.uniform(-1, 1, (9, 3)))
+        R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        X[e] = Xe @ R.T + rng.uniform(-1, 1, 3)
+        sc = 10.0 ** rng.uniform(*state_range)
+        q[e, :, :3] = sc * h * rng.uniform(-1, 1, (9, 3))
+        q[e, :, 3:] = sc * rng.uniform(-1, 1, (9, 3))
+    return X, q
+
+
 def emul_element(L, Cs, eth, T, model, transform, axis, X, q, want_g, tying=False):
     """one element through the host emulation of the kernel math; tying=True: the tying-level
     formulation of k_assemble_t (uncoupled sections only)"""

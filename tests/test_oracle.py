@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import random_elements, relmax
+from helpers import random_elements, random_elements9, relmax
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -161,3 +161,57 @@ def test_oracle_dynamic_assembly_against_reference_live(orc, ref):
     assert relmax(r, r_ref) < 1e-13 and relmax(J, J_ref) < 1e-13
     r0, _ = orc.assemble(0, *args, udd=udd)
     assert relmax(r0, r0_ref) < 1e-13
+
+
+# ---- 9-node element (TACSQuad9Shell, oracle9_*: shell_oracle.c compiled with ORACLE_ORDER 3) ----
+@pytest.mark.parametrize("kind,tr,ci", list(_cases()))
+def test_quad9_elements_against_golden(orc, kind, tr, ci):
+    g = np.load(os.path.join(GOLD, "quad9.npz"))
+    key = f"k{kind}_t{tr}_c{ci}"
+    T = float(g[key + "_T"])
+    comp = orc.make_comp(kind, g[key + "_Cs"], g[key + "_eth"], (0, 0, 0), T, tr, g["axis"])
+    for e in range(g["X"].shape[0]):
+        X = g["X"][e].ravel(); q = g["q"][e].ravel()
+        r, k = orc.jacobian(comp, X, q, order=3)
+        assert relmax(r, g[key + "_res"][e]) < 1e-13
+        assert relmax(k, g[key + "_K"][e]) < 1e-13
+        assert relmax(orc.residual(comp, X, q, order=3), g[key + "_res"][e]) < 1e-13
+        if kind == 0:
+            tol = 1e-10 if T == 0.0 else 1e-6   # the reference's finite-difference noise, as above
+            assert relmax(orc.mat_type(comp, 1, X, q, order=3), g[key + "_G"][e]) < tol
+
+
+def test_quad9_assembly_against_golden(orc):
+    g = np.load(os.path.join(GOLD, "quad9.npz"))
+    conn, X, u = g["m_conn"], g["m_X"], g["m_u"]
+    n = len(X)
+    rowp, cols = orc.pattern(n, conn, order=3)
+    assert rowp.tobytes() == g["m_rowp"].tobytes() and cols.tobytes() == g["m_cols"].tobytes()
+    comp = orc.make_comp(0, g["m_Cs"], g["m_eth"])
+    ec = np.zeros(len(conn), dtype=np.int32)
+    r, K = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, g["m_bc_nodes"], g["m_bc_vars"],
+                        g["m_bc_vals"], order=3)
+    assert relmax(r, g["m_res"]) < 1e-13 and relmax(K, g["m_K"]) < 1e-13
+
+
+def test_quad9_oracle_against_reference_live(orc, ref):
+    """random 9-node elements beyond the fixture: residual, tangent, geometric stiffness and
+    mass matrix of TACSQuad9Shell / TACSQuad9NonlinearShell"""
+    X, q = random_elements9(10, seed=31)
+    axis = np.array([0.3, 1.0, 0.2])
+    for kind in (0, 1):
+        for tr in (0, 1):
+            p = ref.iso_props(kind=2 + kind, temperature=0.0, t_offset=0.2)
+            Cs, eth, mom = ref.con_tables(p)
+            assert mom[0] > 0
+            comp = orc.make_comp(kind, Cs, eth, mom, 0.0, tr, axis)
+            for e in range(X.shape[0]):
+                Xe, qe = X[e].ravel(), q[e].ravel()
+                r_ref, k_ref = ref.element(p, 1, Xe, qe, transform=tr, axis=axis)
+                r, k = orc.jacobian(comp, Xe, qe, order=3)
+                assert relmax(r, r_ref) < 1e-13 and relmax(k, k_ref) < 1e-13
+                g_ref = ref.element(p, 3, Xe, qe, transform=tr, axis=axis)[1]
+                assert relmax(orc.mat_type(comp, 1, Xe, qe, order=3), g_ref) < 1e-10
+                m_ref = ref.element(p, 4, Xe, qe, transform=tr, axis=axis)[1]
+                assert np.abs(m_ref).max() > 0
+                assert relmax(orc.mat_type(comp, 2, Xe, qe, order=3), m_ref) < 1e-13
