@@ -1,0 +1,405 @@
+// mitc9_math.h — element math of the 9-node MITC shell (TACSQuad9Shell =
+// TACSShellElement<TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3>, TACSLinearizedRotation,
+// TACSShellLinearModel>, src/elements/shell/TACSShellElementDefs.h:16-18), written as the work
+// items of k_assemble9 (assemble9_kernels.cuh): one thread block per element, every function
+// below is the job of ONE thread for one node / tying point / Gauss point / table entry /
+// element column.  Host-callable as well: tests/host_emul.cpp steps the same functions on the
+// CPU against the oracle (oracle/shell_oracle_q9.c).
+//
+// Strain order as the reference (TACSShellElementModel.h:33-77, TACSShellConstitutive.h:125):
+//   0,1,2 membrane (e11, e22, 2e12)   3,4,5 bending   6,7 transverse shear (2e23, 2e13)   8 drill
+// Rows 0,1,2,6,7 come from the 28 tying strains (6 g11, 6 g22, 4 g12, 6 g23, 6 g13;
+// TACSShellElementQuadBasis.h:125-142, 487-616).  The 9 Gauss points are the tensor product of
+// the 3-point rule, which is also the "order" knot set of the tying interpolation (:510-512): at
+// a Gauss point the full-order Lagrange factors are 0 / 1, and each interpolated tying
+// component is a combination of 2 (g11, g22, g23, g13) or 4 (g12) tying points only.
+//
+// The tangent is K = sum_qp w det B^T C B with B = d(strain)/d(state) written out in closed
+// form (linear strain model: B does not depend on the state); the residual is
+// sum_qp w det B^T C (e - T e_th) with the strains e of the state evaluated forward exactly as
+// the reference orders it for the drilling strain (see drill_strain_state in mitc4_math.h).
+#ifndef A2DS_MITC9_MATH_H
+#define A2DS_MITC9_MATH_H
+
+#include "mitc4_math.h"
+
+namespace a2ds {
+
+static const int Q9_NN = 9, Q9_NV = 54, Q9_NTY = 28, Q9_LD = 56, Q9_KROWS = 12;
+
+// element record in shared memory (one per thread block)
+struct Elem9 {
+  double X[27], q[54];
+  double fn[27];                    // node normals (TacsShellComputeNodeNormals)
+  double dr[27];                    // directors d_n = theta_n x fn_n (TACSDirector.h:244-267)
+  double a1[27], a2[27], t2n[27];   // drill derivative coefficients per node, node normal axis
+  double etn[9];                    // drill strain of the state at the nodes
+  double tXxi[28][3], tXeta[28][3], tn0[28][3];   // tying-point frames
+  double ety[28];                   // tying strains of the state
+  double qT[9][9], qA[9][9], qZ[9][9];            // Gauss point: T, Xd^-1 T, -Xd^-1 Xdz Xd^-1 T
+  double qw[9];                     // quadrature weight * det(Xd)
+  double sq[9][9];                  // w det C (e - T e_th) at the Gauss points
+  double Gt[Q9_NTY][Q9_LD];         // d(tying strain t) / d(dof)
+  double Dn[Q9_NN][Q9_LD];          // d(drill strain at node n) / d(dof)
+  double B[Q9_KROWS][Q9_LD];        // B of the current Gauss point (rows 9..11, columns 54, 55 zero)
+  double CB[Q9_KROWS][Q9_LD];       // w det C B
+};
+
+// quadratic Lagrange functions on {-1, 0, 1} (TacsLagrangeLobattoShapeFuncDerivative<3>, :96-104)
+A2DS_HD void q9_lag(double u, double N[3], double dN[3]) {
+  N[0] = -0.5 * u * (1.0 - u); N[1] = (1.0 - u) * (1.0 + u); N[2] = 0.5 * (1.0 + u) * u;
+  dN[0] = -0.5 + u; dN[1] = -2.0 * u; dN[2] = 0.5 + u;
+}
+// 15-digit literals of basis/TACSGaussQuadrature.h:26-30
+#define Q9_G3 0.774596669241483
+#define Q9_G2 0.577350269189626
+A2DS_HD double q9_gauss3(int i) { return i == 0 ? -Q9_G3 : (i == 1 ? 0.0 : Q9_G3); }
+A2DS_HD double q9_wt3(int i) { return i == 1 ? 8.0 / 9.0 : 5.0 / 9.0; }
+// linear Lagrange functions on the reduced knots {-g2, g2}
+A2DS_HD void q9_red(double u, double r[2]) {
+  r[0] = (Q9_G2 - u) * (0.5 / Q9_G2);
+  r[1] = (u + Q9_G2) * (0.5 / Q9_G2);
+}
+// tying point t -> field (0 g11, 1 g22, 2 g12, 3 g23, 4 g13) and parametric point
+// (getTyingField :487, getTyingPoint :530-564)
+A2DS_HD int q9_ty_point(int t, double pt[2]) {
+  int field, k;
+  if (t < 6) { field = 0; k = t; }
+  else if (t < 12) { field = 1; k = t - 6; }
+  else if (t < 16) { field = 2; k = t - 12; }
+  else if (t < 22) { field = 3; k = t - 16; }
+  else { field = 4; k = t - 22; }
+  if (field == 0 || field == 4) {          // reduced in xi, full order in eta
+    pt[0] = (k % 2) ? Q9_G2 : -Q9_G2; pt[1] = q9_gauss3(k / 2);
+  } else if (field == 1 || field == 3) {   // full order in xi, reduced in eta
+    pt[0] = q9_gauss3(k % 3); pt[1] = (k / 3) ? Q9_G2 : -Q9_G2;
+  } else {
+    pt[0] = (k % 2) ? Q9_G2 : -Q9_G2; pt[1] = (k / 2) ? Q9_G2 : -Q9_G2;
+  }
+  return field;
+}
+// shape functions and their parametric derivatives at a point, node index 3 j + i
+A2DS_HD void q9_shape(const double pt[2], double N[9], double Nx[9], double Ne[9]) {
+  double na[3], nb[3], da[3], db[3];
+  q9_lag(pt[0], na, da);
+  q9_lag(pt[1], nb, db);
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) {
+      N[3 * j + i] = na[i] * nb[j];
+      Nx[3 * j + i] = da[i] * nb[j];
+      Ne[3 * j + i] = na[i] * db[j];
+    }
+}
+A2DS_HD void q9_interp3(const double w[9], const double *v, int ld, double f[3]) {
+  f[0] = f[1] = f[2] = 0.0;
+  for (int n = 0; n < 9; n++)
+    for (int k = 0; k < 3; k++) f[k] += w[n] * v[ld * n + k];
+}
+
+// frame of a point: T = [t1 | t2 | n] (row major, columns are the axes), from X,xi and the
+// (not necessarily unit) normal; TACSShellElementTransform.h:25-92 (natural, including the
+// t1[0]-only projection of :42-44) and :116-213 (reference axis).  strict: reference's rounding.
+A2DS_HD void q9_transform(const CompData &c, const double Xxi[3], const double n0[3], double t1[3],
+                          double t2[3], double n[3]) {
+  double inv = 1.0 / sqrt(sdot(n0, n0));
+  n[0] = A2DS_MUL(n0[0], inv); n[1] = A2DS_MUL(n0[1], inv); n[2] = A2DS_MUL(n0[2], inv);
+  if (c.transform == 0) {
+    t1[0] = Xxi[0]; t1[1] = Xxi[1]; t1[2] = Xxi[2];
+    const double d = sdot(n, t1);
+    t1[0] = A2DS_ADD(t1[0], -A2DS_MUL(d, n[0]));
+    t1[0] = A2DS_ADD(t1[0], -A2DS_MUL(d, n[0]));
+    t1[0] = A2DS_ADD(t1[0], -A2DS_MUL(d, n[0]));
+  } else {
+    const double an = sdot(c.axis, n);
+    t1[0] = A2DS_ADD(c.axis[0], -A2DS_MUL(an, n[0]));
+    t1[1] = A2DS_ADD(c.axis[1], -A2DS_MUL(an, n[1]));
+    t1[2] = A2DS_ADD(c.axis[2], -A2DS_MUL(an, n[2]));
+  }
+  inv = 1.0 / sqrt(sdot(t1, t1));
+  t1[0] = A2DS_MUL(t1[0], inv); t1[1] = A2DS_MUL(t1[1], inv); t1[2] = A2DS_MUL(t1[2], inv);
+  scross(n, t1, t2);
+}
+// inverse of Xd = [a | b | c] (columns), inv3x3 (TACSElementAlgebra.h:1980); returns det
+A2DS_HD double q9_frame_inverse(const double a[3], const double b[3], const double c[3], double Xi[9]) {
+  const double A[9] = {a[0], b[0], c[0], a[1], b[1], c[1], a[2], b[2], c[2]};
+  const double det = A2DS_ADD(A2DS_ADD(A2DS_MUL(A[8], sdet2(A[0], A[4], A[3], A[1])),
+                                       -A2DS_MUL(A[7], sdet2(A[0], A[5], A[3], A[2]))),
+                              A2DS_MUL(A[6], sdet2(A[1], A[5], A[2], A[4])));
+  const double di = 1.0 / det;
+  Xi[0] = A2DS_MUL(sdet2(A[4], A[8], A[5], A[7]), di);
+  Xi[1] = A2DS_MUL(-sdet2(A[1], A[8], A[2], A[7]), di);
+  Xi[2] = A2DS_MUL(sdet2(A[1], A[5], A[2], A[4]), di);
+  Xi[3] = A2DS_MUL(-sdet2(A[3], A[8], A[5], A[6]), di);
+  Xi[4] = A2DS_MUL(sdet2(A[0], A[8], A[2], A[6]), di);
+  Xi[5] = A2DS_MUL(-sdet2(A[0], A[5], A[2], A[3]), di);
+  Xi[6] = A2DS_MUL(sdet2(A[3], A[7], A[4], A[6]), di);
+  Xi[7] = A2DS_MUL(-sdet2(A[0], A[7], A[1], A[6]), di);
+  Xi[8] = A2DS_MUL(sdet2(A[0], A[4], A[1], A[3]), di);
+  return det;
+}
+A2DS_HD void q9_matmul_strict(const double A[9], const double B[9], double C[9]) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      C[3 * i + j] = A2DS_ADD(A2DS_ADD(A2DS_MUL(A[3 * i], B[j]), A2DS_MUL(A[3 * i + 1], B[3 + j])),
+                              A2DS_MUL(A[3 * i + 2], B[6 + j]));
+}
+// interpFieldsGrad in the reference's operation order (TACSShellElementQuadBasis.h:210-232)
+A2DS_HD void q9_grad_strict(const double pt[2], const double *v, int ld, double gxi[3], double geta[3]) {
+  double na[3], nb[3], da[3], db[3];
+  q9_lag(pt[0], na, da);
+  q9_lag(pt[1], nb, db);
+  for (int k = 0; k < 3; k++) gxi[k] = geta[k] = 0.0;
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) {
+      const double wx = A2DS_MUL(da[i], nb[j]), we = A2DS_MUL(na[i], db[j]);
+      for (int k = 0; k < 3; k++) {
+        gxi[k] = A2DS_ADD(gxi[k], A2DS_MUL(wx, v[ld * (3 * j + i) + k]));
+        geta[k] = A2DS_ADD(geta[k], A2DS_MUL(we, v[ld * (3 * j + i) + k]));
+      }
+    }
+}
+
+// ---- node n: normal, frame, drill strain of the state and its derivative coefficients -------
+// TacsShellComputeNodeNormals (TACSShellUtilities.h:301-342), TacsShellComputeDrillStrain
+// (:651-693); d(et_n)/d(u_m) = 1/2 (a0 t2 - a1 t1) with a_j = N_m,xi(n) S[0][j] + N_m,eta(n) S[1][j]
+// = N_m,xi(n) a1 + N_m,eta(n) a2;  d(et_n)/d(theta_n) = -normal axis of the node frame.
+A2DS_HD void q9_node(const CompData &c, Elem9 &E, int n) {
+  const double pt[2] = {-1.0 + (n % 3), -1.0 + (n / 3)};
+  double Xxi[3], Xeta[3], fn[3];
+  q9_grad_strict(pt, E.X, 3, Xxi, Xeta);
+  scross(Xxi, Xeta, fn);
+  const double nrm = sqrt(sdot(fn, fn));
+  if (nrm != 0.0) {
+    const double inv = 1.0 / nrm;
+    fn[0] = A2DS_MUL(fn[0], inv); fn[1] = A2DS_MUL(fn[1], inv); fn[2] = A2DS_MUL(fn[2], inv);
+  }
+  double t1[3], t2[3], nn[3];
+  q9_transform(c, Xxi, fn, t1, t2, nn);
+  double Xi[9], S[9];
+  q9_frame_inverse(Xxi, Xeta, fn, Xi);
+  const double T[9] = {t1[0], t2[0], nn[0], t1[1], t2[1], nn[1], t1[2], t2[2], nn[2]};
+  q9_matmul_strict(Xi, T, S);
+  double uxi[3], ueta[3];
+  q9_grad_strict(pt, E.q, 6, uxi, ueta);
+  const double th[3] = {E.q[6 * n + 3], E.q[6 * n + 4], E.q[6 * n + 5]};
+  E.etn[n] = drill_strain_state(T, S, uxi, ueta, th);
+  double w[3];
+  cross(t1, t2, w);
+  for (int k = 0; k < 3; k++) {
+    E.fn[3 * n + k] = fn[k];
+    E.a1[3 * n + k] = 0.5 * (S[0] * t2[k] - S[1] * t1[k]);
+    E.a2[3 * n + k] = 0.5 * (S[3] * t2[k] - S[4] * t1[k]);
+    E.t2n[3 * n + k] = w[k];
+  }
+  scross(th, fn, &E.dr[3 * n]);
+}
+
+// ---- tying point t: frame vectors and the tying strain of the state ---------------------------
+// TACSShellLinearModel::computeTyingStrain (TACSShellElementModel.h:33-77)
+A2DS_HD void q9_tying(Elem9 &E, int t) {
+  double pt[2], N[9], Nx[9], Ne[9];
+  const int field = q9_ty_point(t, pt);
+  q9_shape(pt, N, Nx, Ne);
+  double Xxi[3], Xeta[3], n0[3], Uxi[3], Ueta[3], d0[3];
+  q9_interp3(Nx, E.X, 3, Xxi);
+  q9_interp3(Ne, E.X, 3, Xeta);
+  q9_interp3(N, E.fn, 3, n0);
+  q9_interp3(Nx, E.q, 6, Uxi);
+  q9_interp3(Ne, E.q, 6, Ueta);
+  q9_interp3(N, E.dr, 3, d0);
+  for (int k = 0; k < 3; k++) { E.tXxi[t][k] = Xxi[k]; E.tXeta[t][k] = Xeta[k]; E.tn0[t][k] = n0[k]; }
+  double e;
+  if (field == 0) e = dot(Uxi, Xxi);
+  else if (field == 1) e = dot(Ueta, Xeta);
+  else if (field == 2) e = 0.5 * (dot(Uxi, Xeta) + dot(Ueta, Xxi));
+  else if (field == 3) e = 0.5 * (dot(Xeta, d0) + dot(n0, Ueta));
+  else e = 0.5 * (dot(Xxi, d0) + dot(n0, Uxi));
+  E.ety[t] = e;
+}
+
+// ---- Gauss point q: frame, Xd^-1 T, the through-thickness term, weight * det -------------------
+// TACSShellElement.h:514-534, TacsShellComputeDispGrad (TACSShellUtilities.h:369-393)
+A2DS_HD void q9_qp(const CompData &c, Elem9 &E, int q) {
+  const double pt[2] = {q9_gauss3(q % 3), q9_gauss3(q / 3)};
+  double N[9], Nx[9], Ne[9];
+  q9_shape(pt, N, Nx, Ne);
+  double Xxi[3], Xeta[3], n0[3], nxi[3], neta[3];
+  q9_interp3(Nx, E.X, 3, Xxi);
+  q9_interp3(Ne, E.X, 3, Xeta);
+  q9_interp3(N, E.fn, 3, n0);
+  q9_interp3(Nx, E.fn, 3, nxi);
+  q9_interp3(Ne, E.fn, 3, neta);
+  double t1[3], t2[3], nn[3];
+  q9_transform(c, Xxi, n0, t1, t2, nn);
+  double Xi[9];
+  const double det = q9_frame_inverse(Xxi, Xeta, n0, Xi);
+  const double T[9] = {t1[0], t2[0], nn[0], t1[1], t2[1], nn[1], t1[2], t2[2], nn[2]};
+  // A = Xd^-1 T;  Z = -(Xd^-1 Xdz) A with Xdz = [n,xi | n,eta | 0]
+  double A[9], P[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      A[3 * i + j] = Xi[3 * i] * T[j] + Xi[3 * i + 1] * T[3 + j] + Xi[3 * i + 2] * T[6 + j];
+  for (int i = 0; i < 3; i++) {
+    P[3 * i] = Xi[3 * i] * nxi[0] + Xi[3 * i + 1] * nxi[1] + Xi[3 * i + 2] * nxi[2];
+    P[3 * i + 1] = Xi[3 * i] * neta[0] + Xi[3 * i + 1] * neta[1] + Xi[3 * i + 2] * neta[2];
+    P[3 * i + 2] = 0.0;
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      E.qT[q][3 * i + j] = T[3 * i + j];
+      E.qA[q][3 * i + j] = A[3 * i + j];
+      E.qZ[q][3 * i + j] = -(P[3 * i] * A[j] + P[3 * i + 1] * A[3 + j] + P[3 * i + 2] * A[6 + j]);
+    }
+  E.qw[q] = det * (q9_wt3(q % 3) * q9_wt3(q / 3));
+}
+
+// the 5 interpolated tying components (g11, g22, g12, g23, g13) at Gauss point q of a set of 28
+// tying values with stride ld (interpTyingStrain :651-672 at a point of the "order" knot set)
+A2DS_HD void q9_interp_tying(int q, const double *ty, int ld, double g[5]) {
+  const int a = q % 3, b = q / 3;
+  double ra[2], rb[2];
+  q9_red(q9_gauss3(a), ra);
+  q9_red(q9_gauss3(b), rb);
+  g[0] = ra[0] * ty[ld * (2 * b)] + ra[1] * ty[ld * (2 * b + 1)];
+  g[1] = rb[0] * ty[ld * (6 + a)] + rb[1] * ty[ld * (6 + 3 + a)];
+  g[2] = rb[0] * (ra[0] * ty[ld * 12] + ra[1] * ty[ld * 13]) +
+         rb[1] * (ra[0] * ty[ld * 14] + ra[1] * ty[ld * 15]);
+  g[3] = rb[0] * ty[ld * (16 + a)] + rb[1] * ty[ld * (16 + 3 + a)];
+  g[4] = ra[0] * ty[ld * (22 + 2 * b)] + ra[1] * ty[ld * (22 + 2 * b + 1)];
+}
+// e0ty = A^T gty A (mat3x3SymmTransformTranspose) -> strains 0, 1, 2, 6, 7
+A2DS_HD void q9_membrane_shear(const double A[9], const double g[5], double e[9]) {
+  // gty = [[g11 g12 g13] [g12 g22 g23] [g13 g23 0]]
+  const double G[9] = {g[0], g[2], g[4], g[2], g[1], g[3], g[4], g[3], 0.0};
+  double W[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) W[3 * i + j] = G[3 * i] * A[j] + G[3 * i + 1] * A[3 + j] + G[3 * i + 2] * A[6 + j];
+  const double e00 = A[0] * W[0] + A[3] * W[3] + A[6] * W[6];
+  const double e01 = A[0] * W[1] + A[3] * W[4] + A[6] * W[7];
+  const double e02 = A[0] * W[2] + A[3] * W[5] + A[6] * W[8];
+  const double e11 = A[1] * W[1] + A[4] * W[4] + A[7] * W[7];
+  const double e12 = A[1] * W[2] + A[4] * W[5] + A[7] * W[8];
+  e[0] = e00; e[1] = e11; e[2] = 2.0 * e01; e[6] = 2.0 * e12; e[7] = 2.0 * e02;
+}
+// TACSShellConstitutive::computeStress (TACSShellConstitutive.h:125-147)
+A2DS_HD void q9_stress(const double Cs[22], const double e[9], double s[9]) {
+  const double *A = &Cs[0], *B = &Cs[6], *D = &Cs[12], *As = &Cs[18];
+  s[0] = A[0] * e[0] + A[1] * e[1] + A[2] * e[2] + B[0] * e[3] + B[1] * e[4] + B[2] * e[5];
+  s[1] = A[1] * e[0] + A[3] * e[1] + A[4] * e[2] + B[1] * e[3] + B[3] * e[4] + B[4] * e[5];
+  s[2] = A[2] * e[0] + A[4] * e[1] + A[5] * e[2] + B[2] * e[3] + B[4] * e[4] + B[5] * e[5];
+  s[3] = B[0] * e[0] + B[1] * e[1] + B[2] * e[2] + D[0] * e[3] + D[1] * e[4] + D[2] * e[5];
+  s[4] = B[1] * e[0] + B[3] * e[1] + B[4] * e[2] + D[1] * e[3] + D[3] * e[4] + D[4] * e[5];
+  s[5] = B[2] * e[0] + B[4] * e[1] + B[5] * e[2] + D[2] * e[3] + D[4] * e[4] + D[5] * e[5];
+  s[6] = As[0] * e[6] + As[1] * e[7];
+  s[7] = As[1] * e[6] + As[2] * e[7];
+  s[8] = Cs[21] * e[8];
+}
+
+// ---- Gauss point q: strains of the state and the weighted stresses ----------------------------
+// TACSShellElement::addResidual, TACSShellElement.h:314-373 (thermal: :549-574)
+A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, int q, double thermal) {
+  const double pt[2] = {q9_gauss3(q % 3), q9_gauss3(q / 3)};
+  double N[9], Nx[9], Ne[9];
+  q9_shape(pt, N, Nx, Ne);
+  double e[9], g[5];
+  q9_interp_tying(q, E.ety, 1, g);
+  q9_membrane_shear(E.qA[q], g, e);
+  double u0xi[3], u0eta[3], d0[3], d0xi[3], d0eta[3];
+  q9_interp3(Nx, E.q, 6, u0xi);
+  q9_interp3(Ne, E.q, 6, u0eta);
+  q9_interp3(N, E.dr, 3, d0);
+  q9_interp3(Nx, E.dr, 3, d0xi);
+  q9_interp3(Ne, E.dr, 3, d0eta);
+  const double *T = E.qT[q], *A = E.qA[q], *Z = E.qZ[q];
+  double u1x[2][2];   // rows / columns 0, 1 of T^T (u1d A + u0d Z)
+  for (int j = 0; j < 2; j++) {
+    double v[3];
+    for (int k = 0; k < 3; k++)
+      v[k] = d0xi[k] * A[j] + d0eta[k] * A[3 + j] + u0xi[k] * Z[j] + u0eta[k] * Z[3 + j] + d0[k] * Z[6 + j];
+    for (int i = 0; i < 2; i++) u1x[i][j] = T[i] * v[0] + T[3 + i] * v[1] + T[6 + i] * v[2];
+  }
+  e[3] = u1x[0][0]; e[4] = u1x[1][1]; e[5] = u1x[0][1] + u1x[1][0];
+  double et = 0.0;
+  for (int n = 0; n < 9; n++) et += N[n] * E.etn[n];
+  e[8] = et;
+  for (int k = 0; k < 9; k++) e[k] -= thermal * c.temperature * c.eth[k];
+  double s[9];
+  q9_stress(c.Cs, e, s);
+  for (int k = 0; k < 9; k++) E.sq[q][k] = E.qw[q] * s[k];
+}
+
+// ---- table entries ----------------------------------------------------------------------------
+// Gt[t][dof] = d(tying strain t)/d(dof), dof = 6 m + k (k < 3 displacement, k >= 3 rotation)
+A2DS_HD double q9_gt(const Elem9 &E, int t, int dof) {
+  double pt[2], na[3], nb[3], da[3], db[3];
+  const int field = q9_ty_point(t, pt);
+  q9_lag(pt[0], na, da);
+  q9_lag(pt[1], nb, db);
+  const int m = dof / 6, k = dof % 6, i = m % 3, j = m / 3;
+  const double N = na[i] * nb[j], Nx = da[i] * nb[j], Ne = na[i] * db[j];
+  if (k < 3) {
+    if (field == 0) return Nx * E.tXxi[t][k];
+    if (field == 1) return Ne * E.tXeta[t][k];
+    if (field == 2) return 0.5 * (Nx * E.tXeta[t][k] + Ne * E.tXxi[t][k]);
+    if (field == 3) return 0.5 * Ne * E.tn0[t][k];
+    return 0.5 * Nx * E.tn0[t][k];
+  }
+  if (field < 3) return 0.0;
+  // X,a . (theta x fn) = theta . (fn x X,a)
+  const double *v = field == 3 ? E.tXeta[t] : E.tXxi[t], *f = &E.fn[3 * m];
+  const int c = k - 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+  return 0.5 * N * (f[c1] * v[c2] - f[c2] * v[c1]);
+}
+// Dn[n][dof] = d(drill strain at node n)/d(dof)
+A2DS_HD double q9_dn(const Elem9 &E, int n, int dof) {
+  const int m = dof / 6, k = dof % 6;
+  if (k >= 3) return m == n ? -E.t2n[3 * n + k - 3] : 0.0;
+  const double pt[2] = {-1.0 + (n % 3), -1.0 + (n / 3)};
+  double na[3], nb[3], da[3], db[3];
+  q9_lag(pt[0], na, da);
+  q9_lag(pt[1], nb, db);
+  const int i = m % 3, j = m / 3;
+  return da[i] * nb[j] * E.a1[3 * n + k] + na[i] * db[j] * E.a2[3 * n + k];
+}
+
+// ---- column `dof` of B at Gauss point q (9 strain rows) ----------------------------------------
+A2DS_HD void q9_bcol(const Elem9 &E, int q, int dof, double Bk[9]) {
+  const double pt[2] = {q9_gauss3(q % 3), q9_gauss3(q / 3)};
+  double na[3], nb[3], da[3], db[3];
+  q9_lag(pt[0], na, da);
+  q9_lag(pt[1], nb, db);
+  const int m = dof / 6, k = dof % 6, i = m % 3, j = m / 3;
+  const double N = na[i] * nb[j], Nx = da[i] * nb[j], Ne = na[i] * db[j];
+  double g[5];
+  q9_interp_tying(q, &E.Gt[0][dof], Q9_LD, g);
+  q9_membrane_shear(E.qA[q], g, Bk);
+  const double *T = E.qT[q], *A = E.qA[q], *Z = E.qZ[q];
+  // u1x_ij = t_i . (u1d a_j + u0d z_j): displacement dofs enter through u0d = [u,xi | u,eta | d],
+  // rotation dofs through the director d_m = theta_m x fn_m in u0d and u1d = [d,xi | d,eta | 0]
+  double w0, w1, v0, v1;   // coefficient of column j = 0, 1 and the vector component dotted with t_i
+  if (k < 3) {
+    w0 = Nx * Z[0] + Ne * Z[3];
+    w1 = Nx * Z[1] + Ne * Z[4];
+    v0 = T[3 * k]; v1 = T[3 * k + 1];         // t_0[k], t_1[k]
+  } else {
+    w0 = Nx * A[0] + Ne * A[3] + N * Z[6];
+    w1 = Nx * A[1] + Ne * A[4] + N * Z[7];
+    const double *f = &E.fn[3 * m];
+    const int c = k - 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+    // t_i . (theta x fn) = theta . (fn x t_i)
+    v0 = f[c1] * T[3 * c2] - f[c2] * T[3 * c1];
+    v1 = f[c1] * T[3 * c2 + 1] - f[c2] * T[3 * c1 + 1];
+  }
+  Bk[3] = w0 * v0;
+  Bk[4] = w1 * v1;
+  Bk[5] = w1 * v0 + w0 * v1;
+  double N9[9];
+  for (int jj = 0; jj < 3; jj++)
+    for (int ii = 0; ii < 3; ii++) N9[3 * jj + ii] = na[ii] * nb[jj];
+  double d = 0.0;
+  for (int n = 0; n < 9; n++) d += N9[n] * E.Dn[n][dof];
+  Bk[8] = d;
+}
+
+}  // namespace a2ds
+#endif

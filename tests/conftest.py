@@ -45,7 +45,7 @@ def emul():
     import ctypes as C
     so = os.path.join(ROOT, "tests", "_host_emul.so")
     src = os.path.join(ROOT, "tests", "host_emul.cpp")
-    hdrs = [os.path.join(ROOT, "a2d-shells_b200", "csrc", h) for h in ("mitc4_math.h", "mitc4_tying.h")]
+    hdrs = [os.path.join(ROOT, "a2d-shells_b200", "csrc", h) for h in ("mitc4_math.h", "mitc4_tying.h", "mitc9_math.h")]
     if (not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] +
                                                              [os.path.getmtime(h) for h in hdrs])):
         # -mfma + contraction on: mimics nvcc's FMA fusion outside the strict sections

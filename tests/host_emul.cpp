@@ -225,3 +225,52 @@ extern "C" int emul_element_t(const double *Cs, const double *eth, double temper
     }
   return 0;
 }
+
+// ---- 9-node element (mitc9_math.h): the work items of k_assemble9 stepped in the kernel's
+// phase order; the DMMA contraction replaced by plain loops over the same B / CB tables ----
+#include "../a2d-shells_b200/csrc/mitc9_math.h"
+
+extern "C" int emul_element9(const double *Cs, const double *eth, double temperature, int transform,
+                             const double *axis, const double *X, const double *q, double *res,
+                             double *K) {
+  CompData c;
+  memset(&c, 0, sizeof(c));
+  memcpy(c.Cs, Cs, sizeof(c.Cs));
+  memcpy(c.eth, eth, sizeof(c.eth));
+  c.temperature = temperature;
+  c.transform = transform;
+  memcpy(c.axis, axis, sizeof(c.axis));
+  static Elem9 E;
+  memset(&E, 0, sizeof(E));
+  memcpy(E.X, X, sizeof(E.X));
+  memcpy(E.q, q, sizeof(E.q));
+  for (int n = 0; n < 9; n++) q9_node(c, E, n);
+  for (int t = 0; t < 28; t++) q9_tying(E, t);
+  for (int qp = 0; qp < 9; qp++) q9_qp(c, E, qp);
+  for (int t = 0; t < 28; t++)
+    for (int d = 0; d < 54; d++) E.Gt[t][d] = q9_gt(E, t, d);
+  for (int n = 0; n < 9; n++)
+    for (int d = 0; d < 54; d++) E.Dn[n][d] = q9_dn(E, n, d);
+  for (int qp = 0; qp < 9; qp++) q9_qp_state(c, E, qp, 1.0);
+  memset(res, 0, 54 * sizeof(double));
+  memset(K, 0, 54 * 54 * sizeof(double));
+  for (int qp = 0; qp < 9; qp++) {
+    for (int d = 0; d < 54; d++) {
+      double Bk[9], Sk[9];
+      q9_bcol(E, qp, d, Bk);
+      q9_stress(c.Cs, Bk, Sk);
+      for (int k = 0; k < 9; k++) { E.B[k][d] = Bk[k]; E.CB[k][d] = E.qw[qp] * Sk[k]; }
+    }
+    for (int a = 0; a < 54; a++) {
+      double r = 0.0;
+      for (int k = 0; k < 9; k++) r += E.B[k][a] * E.sq[qp][k];
+      res[a] += r;
+      for (int b = 0; b < 54; b++) {
+        double s = 0.0;
+        for (int k = 0; k < 9; k++) s += E.B[k][a] * E.CB[k][b];
+        K[54 * a + b] += s;
+      }
+    }
+  }
+  return 0;
+}

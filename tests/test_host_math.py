@@ -131,3 +131,44 @@ def test_tying_rows_have_rank_nine_across_the_gauss_points(emul, a2ds):
             for B in (B0, B1):
                 sv = np.linalg.svd(B[:, [0, 1, 2, 6, 7], :].reshape(20, 24), compute_uv=False)
                 assert sv[8] > 1e-6 * sv[0] and sv[9] < 1e-13 * sv[0]
+
+
+@pytest.mark.parametrize("tr", [0, 1])
+@pytest.mark.parametrize("ci", [0, 1])
+def test_quad9_kernel_math_against_golden(emul, tr, ci):
+    """the work items of k_assemble9 (a2d-shells_b200/csrc/mitc9_math.h: node / tying point /
+    Gauss point frames, the tying and drill derivative tables, the columns of B) stepped on the
+    host against the reference's TACSQuad9Shell (tests/golden/quad9.npz)"""
+    import ctypes as C
+    g = np.load(os.path.join(GOLD, "quad9.npz"))
+    key = f"k0_t{tr}_c{ci}"
+    T = float(g[key + "_T"])
+    p = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
+    ax = g["axis"] / np.linalg.norm(g["axis"])
+    for e in range(g["X"].shape[0]):
+        res = np.zeros(54); K = np.zeros(54 * 54)
+        emul.emul_element9(p(g[key + "_Cs"]), p(g[key + "_eth"]), C.c_double(T), C.c_int(tr), p(ax),
+                           p(g["X"][e]), p(g["q"][e]), p(res), p(K))
+        assert relmax(res, g[key + "_res"][e]) < 1e-12
+        assert relmax(K.reshape(54, 54), g[key + "_K"][e]) < 1e-10
+
+
+def test_quad9_kernel_math_against_oracle_many(emul, orc, a2ds):
+    from helpers import random_elements9
+    import ctypes as C
+    X, q = random_elements9(60, seed=77)
+    Cs, eth = a2ds.iso_shell_tables(t_offset=0.2)
+    p = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
+    axis = np.array([0.3, 1.0, 0.2]); ax = axis / np.linalg.norm(axis)
+    worst = [0.0, 0.0]
+    for tr in (0, 1):
+        for T in (0.0, 25.0):
+            comp = orc.make_comp(0, Cs, eth, (0, 0, 0), T, tr, axis)
+            for e in range(len(X)):
+                res = np.zeros(54); K = np.zeros(54 * 54)
+                emul.emul_element9(p(Cs), p(eth), C.c_double(T), C.c_int(tr), p(ax), p(X[e]), p(q[e]),
+                                   p(res), p(K))
+                r_o, k_o = orc.jacobian(comp, X[e].ravel(), q[e].ravel(), order=3)
+                worst[0] = max(worst[0], relmax(res, r_o))
+                worst[1] = max(worst[1], relmax(K.reshape(54, 54), k_o))
+    assert worst[0] < 1e-12 and worst[1] < 1e-10, worst
