@@ -20,7 +20,7 @@ SCATTER_ATOMIC_COLOR_ORDER = 2
 # every symbol include/a2ds.h declares (tests check the library exports them all)
 SYMBOLS = [
     "a2ds_last_error", "a2ds_version", "a2ds_create", "a2ds_destroy", "a2ds_synchronize",
-    "a2ds_set_mesh", "a2ds_set_nodes", "a2ds_set_components", "a2ds_set_state",
+    "a2ds_set_mesh", "a2ds_set_mesh_order", "a2ds_set_nodes", "a2ds_set_components", "a2ds_set_state",
     "a2ds_set_state_dev", "a2ds_set_bcs", "a2ds_set_scatter_mode", "a2ds_mat_create",
     "a2ds_mat_create_natural", "a2ds_mat_pattern", "a2ds_mat_nnz", "a2ds_mat_zero",
     "a2ds_mat_download", "a2ds_mat_values_dev", "a2ds_mat_download_rows", "a2ds_assemble_res", "a2ds_assemble_jacobian",
@@ -371,14 +371,20 @@ class Assembler:
             pass
 
     # -- mesh -------------------------------------------------------------------
-    def set_mesh(self, conn, n_nodes, n_owned=None, elem_comp=None):
-        conn = _i32(conn).reshape(-1, 4)
+    def set_mesh(self, conn, n_nodes, n_owned=None, elem_comp=None, order=2):
+        """order 2: conn[ne, 4] (MITC4); order 3: conn[ne, 9] (TACSQuad9Shell, residual + tangent)"""
+        conn = _i32(conn).reshape(-1, order * order)
         self.n_elems = conn.shape[0]
         self.n_nodes = int(n_nodes)
         self.n_owned = self.n_nodes if n_owned is None else int(n_owned)
         ec = None if elem_comp is None else _i32(elem_comp)
-        self._chk(self.L.a2ds_set_mesh(self.ctx, C.c_int(self.n_nodes), C.c_int(self.n_owned),
-                                       C.c_int(self.n_elems), _p(conn), _p(ec)))
+        if order == 2:
+            self._chk(self.L.a2ds_set_mesh(self.ctx, C.c_int(self.n_nodes), C.c_int(self.n_owned),
+                                           C.c_int(self.n_elems), _p(conn), _p(ec)))
+        else:
+            self._chk(self.L.a2ds_set_mesh_order(self.ctx, C.c_int(order), C.c_int(self.n_nodes),
+                                                 C.c_int(self.n_owned), C.c_int(self.n_elems),
+                                                 _p(conn), _p(ec)))
 
     def set_nodes(self, X):
         X = _f64(X).reshape(-1, 3)

@@ -73,6 +73,7 @@ extern "C" const char *a2ds_last_error(void) { return g_err.c_str(); }
 extern "C" const char *a2ds_version(void) { return "a2ds-b200 0.1 (sm_100a)"; }
 
 #include "assemble_kernels.cuh"
+#include "assemble9_kernels.cuh"
 #include "aux_kernels.cuh"
 
 // ---------------------------------------------------------------------------
@@ -135,6 +136,7 @@ struct a2ds_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   int n_sm = 0;
   int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
+  int npe = 4;   // nodes per element: 4 (MITC4, every entry point) or 9 (MITC9, see a2ds_set_mesh_order)
   bool mesh_set = false;
   int *conn = nullptr, *elem_comp = nullptr;
   std::vector<int> h_conn, h_elem_comp, h_class;
@@ -301,10 +303,17 @@ extern "C" int a2ds_synchronize(a2ds_ctx *c) {
 
 extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems, const int *conn,
                              const int *elem_comp) {
+  return a2ds_set_mesh_order(c, 2, n_nodes, n_owned, n_elems, conn, elem_comp);
+}
+
+extern "C" int a2ds_set_mesh_order(a2ds_ctx *c, int order, int n_nodes, int n_owned, int n_elems,
+                                   const int *conn, const int *elem_comp) {
   A2DS_TRY
   CU(cudaSetDevice(c->device));
+  if (order != 2 && order != 3) return fail("a2ds_set_mesh_order: order must be 2 (4 nodes) or 3 (9 nodes)");
   if (n_owned > n_nodes || n_nodes < 0 || n_elems < 0) return fail("a2ds_set_mesh: bad sizes");
-  for (size_t i = 0; i < 4 * (size_t)n_elems; i++)
+  const int npe = order * order;
+  for (size_t i = 0; i < npe * (size_t)n_elems; i++)
     if (conn[i] < 0 || conn[i] >= n_nodes)
       return fail("a2ds_set_mesh: connectivity refers to a node outside [0, n_nodes) "
                   "(dependent nodes are not supported)");
@@ -322,14 +331,14 @@ extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems,
     c->peers.clear(); c->send_ptr.clear(); c->recv_ptr.clear();
     c->n_bc = 0;
   }
-  c->n_nodes = n_nodes; c->n_owned = n_owned; c->n_elems = n_elems;
-  c->h_conn.assign(conn, conn + 4 * (size_t)n_elems);
+  c->n_nodes = n_nodes; c->n_owned = n_owned; c->n_elems = n_elems; c->npe = npe;
+  c->h_conn.assign(conn, conn + npe * (size_t)n_elems);
   c->nat_ready = false;
   cudaFree(c->nat_d_rowp); cudaFree(c->nat_d_cols);
   c->nat_d_rowp = c->nat_d_cols = nullptr; c->nat_hash = 0;
   if (elem_comp) c->h_elem_comp.assign(elem_comp, elem_comp + n_elems);
   else c->h_elem_comp.assign(n_elems, 0);
-  if (upload(&c->conn, conn, 4 * (size_t)n_elems, c->stream)) return 1;
+  if (upload(&c->conn, conn, npe * (size_t)n_elems, c->stream)) return 1;
   if (upload(&c->elem_comp, c->h_elem_comp.data(), (size_t)n_elems, c->stream)) return 1;
   CU(cudaStreamSynchronize(c->copy_stream));
   c->state_pending = false;
@@ -653,15 +662,15 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   m.owned.push_back(m.blk_dev);
   CU(cudaMemcpyAsync(m.blk_dev, hb.data(), n_blocks * sizeof(BlockDev), cudaMemcpyHostToDevice,
                      c->stream));
-  CU(cudaMalloc((void **)&m.off, std::max<size_t>(16 * (size_t)c->n_elems, 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&m.off, std::max<size_t>(c->npe * c->npe * (size_t)c->n_elems, 1) * sizeof(int)));
   m.owned.push_back(m.off);
   int *d_missing = nullptr;
   CU(cudaMalloc((void **)&d_missing, sizeof(int)));
   CU(cudaMemsetAsync(d_missing, 0, sizeof(int), c->stream));
   if (c->n_elems > 0) {
-    const size_t nt = 16 * (size_t)c->n_elems;
+    const size_t nt = c->npe * c->npe * (size_t)c->n_elems;
     k_build_offsets<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(
-        c->n_elems, c->conn, n_blocks, m.blk_dev, m.off, d_missing);
+        c->n_elems, c->npe, c->conn, n_blocks, m.blk_dev, m.off, d_missing);
     CU(cudaGetLastError());
   }
   int missing = 0;
@@ -707,11 +716,11 @@ static int check_mat(a2ds_ctx *c, int mat, int block = 0) {
 // independent once the incidences are bucketed: the sort / unique pass runs on all host cores
 // (two sweeps: count the distinct columns of every row, then write them at their offsets).
 static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &rowp,
-                           std::vector<int> &cols) {
+                           std::vector<int> &cols, int npe = 4) {
   std::vector<int> ptr(nn + 1, 0);
-  for (size_t i = 0; i < 4 * (size_t)ne; i++) {
+  for (size_t i = 0; i < npe * (size_t)ne; i++) {
     if (conn[i] < 0 || conn[i] >= nn) return fail("pattern: node index out of range");
-    ptr[conn[i] + 1] += 4;
+    ptr[conn[i] + 1] += npe;
   }
   for (int i = 0; i < nn; i++) {
     if ((long long)ptr[i] + ptr[i + 1] > 0x7fffffffll) return fail("pattern too large");
@@ -719,9 +728,9 @@ static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &ro
   }
   std::vector<int> tmp(ptr[nn]), fill(ptr.begin(), ptr.end() - 1);
   for (int e = 0; e < ne; e++)
-    for (int i = 0; i < 4; i++) {
-      const int r = conn[4 * e + i];
-      for (int j = 0; j < 4; j++) tmp[fill[r]++] = conn[4 * e + j];
+    for (int i = 0; i < npe; i++) {
+      const int r = conn[npe * (size_t)e + i];
+      for (int j = 0; j < npe; j++) tmp[fill[r]++] = conn[npe * (size_t)e + j];
     }
   fill.clear(); fill.shrink_to_fit();
   rowp.assign(nn + 1, 0);
@@ -829,11 +838,11 @@ extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   StageTimer tm;
   if (!c->nat_ready) {
     static const bool host_only = getenv("A2DS_HOST_PATTERN") && atoi(getenv("A2DS_HOST_PATTERN")) != 0;
-    int rc = host_only ? 2 : natural_pattern_device(c);
+    int rc = (host_only || c->npe != 4) ? 2 : natural_pattern_device(c);   // 9-node meshes: host sweep
     if (rc == 1) return 1;
     if (rc == 2) {   // very high valence somewhere (or asked for): host sort / unique sweep
       auto hr = std::make_shared<std::vector<int>>(), hc = std::make_shared<std::vector<int>>();
-      if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), *hr, *hc)) return 1;
+      if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), *hr, *hc, c->npe)) return 1;
       c->nat_rowp = hr; c->nat_cols = hc;
       if (upload(&c->nat_d_rowp, hr->data(), hr->size(), c->stream)) return 1;
       if (upload(&c->nat_d_cols, hc->data(), hc->size(), c->stream)) return 1;
@@ -858,15 +867,15 @@ extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   CU(cudaMalloc((void **)&m.blk_dev, sizeof(BlockDev)));
   m.owned.push_back(m.blk_dev);
   CU(cudaMemcpyAsync(m.blk_dev, &hb, sizeof(BlockDev), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMalloc((void **)&m.off, std::max<size_t>(16 * (size_t)c->n_elems, 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&m.off, std::max<size_t>(c->npe * c->npe * (size_t)c->n_elems, 1) * sizeof(int)));
   m.owned.push_back(m.off);
   int *d_missing = nullptr;
   CU(cudaMalloc((void **)&d_missing, sizeof(int)));
   CU(cudaMemsetAsync(d_missing, 0, sizeof(int), c->stream));
   if (c->n_elems > 0) {
-    const size_t nt = 16 * (size_t)c->n_elems;
-    k_build_offsets<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(c->n_elems, c->conn, 1, m.blk_dev,
-                                                                        m.off, d_missing);
+    const size_t nt = c->npe * c->npe * (size_t)c->n_elems;
+    k_build_offsets<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(c->n_elems, c->npe, c->conn, 1,
+                                                                        m.blk_dev, m.off, d_missing);
     CU(cudaGetLastError());
   }
   int missing = 0;
@@ -1433,8 +1442,46 @@ static int launch_mass(a2ds_ctx *c, KParams &p) {
   return 0;
 }
 
+// 9-node elements: one thread block per element (assemble9_kernels.cuh)
+template <bool RES, bool KMAT>
+static int launch_nine(a2ds_ctx *c, KParams &p) {
+  auto kern = k_assemble9<RES, KMAT>;
+  static int per_sm_dev[MAX_DEVICES] = {0};   // function attributes are device state
+  int &per_sm = per_sm_dev[c->device];
+  const size_t smem = (sizeof(Elem9Block) + 15) & ~size_t(15);
+  if (per_sm == 0) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q9_THREADS, smem));
+    if (per_sm == 0) return fail("k_assemble9 does not fit on an SM");
+    if (getenv("A2DS_VERBOSE"))
+      fprintf(stderr, "[a2ds] k_assemble9<%d,%d>: %zu B shared per block, %d blocks/SM\n", (int)RES,
+              (int)KMAT, smem, per_sm);
+  }
+  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, (1 + MAX_ZERO_ROUNDS) * sizeof(int)));
+  p.work_counter = c->work_counter;
+  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  const int grid = std::max(1, std::min(p.n_list, c->n_sm * per_sm));
+  kern<<<grid, Q9_THREADS, smem, c->stream>>>(p);
+  CU(cudaGetLastError());
+  c->last_launches++;
+  return 0;
+}
+
 // element kernels of one class list (p.elem_list / p.n_list set) for the outputs in `what`
 static int launch_class(a2ds_ctx *c, KParams &p, int cls, int what) {
+  if (c->npe == 9) {
+    // TACSQuad9Shell: residual and tangent of the linear strain model (any 22-entry section)
+    if (cls & 1) return fail("assemble: the nonlinear strain model is not available for 9-node elements");
+    switch (what) {
+      case 0: return 0;
+      case 1: return launch_nine<true, false>(c, p);
+      case 2: return launch_nine<false, true>(c, p);
+      case 3: return launch_nine<true, true>(c, p);
+      default: return fail("assemble: 9-node elements provide the residual and the tangent matrix only");
+    }
+  }
   const bool cpl = cls >= 2;
   int rc = 0;
   if ((cls & 1) == 0) {
@@ -1622,6 +1669,8 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   const int kmat = rq.kmat, gmat = rq.gmat, mmat = rq.mmat;
   // inertial residual M * uddot (TACSShellElement.h:410-447) once second derivatives are set
   const bool MRES = RES && c->udd != nullptr;
+  if (c->npe != 4 && (MM || MRES || GM || c->scatter_mode != A2DS_SCATTER_ATOMIC))
+    return fail("assemble: 9-node elements provide the residual and the tangent matrix (atomic scatter) only");
   if (KM && check_mat(c, kmat)) return 1;
   if (GM && check_mat(c, gmat)) return 1;
   if (MM && check_mat(c, mmat)) return 1;
@@ -1658,7 +1707,7 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   int only_cls = -1, n_nonempty = 0;
   for (int cls = 0; cls < 4; cls++)
     if (c->list_len[cls][0] > 0) { n_nonempty++; only_cls = cls; }
-  const bool streamed = c->stream_chunks > 1 && rq.zero && rq.finish && c->n_colors == 1 && n_nonempty == 1 &&
+  const bool streamed = c->npe == 4 && c->stream_chunks > 1 && rq.zero && rq.finish && c->n_colors == 1 && n_nonempty == 1 &&
                         c->list_dev[only_cls][0] == nullptr && c->n_elems >= c->stream_min_elems &&
                         !MM && !MRES && what != 0 && !c->pz_K && !c->pz_G &&
                         ((c->state_pending && c->up_chunks > 1) || (rq.res_host && RES));
@@ -1803,6 +1852,7 @@ extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, doub
   A2DS_TRY
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("addJacobianVecProduct: mesh or nodes not set");
+  if (c->npe != 4) return fail("addJacobianVecProduct: 4-node elements only");
   if (((uintptr_t)x_dev & 15) || ((uintptr_t)y_dev & 7))
     return fail("addJacobianVecProduct: x must be 16-byte aligned (rows are fetched with 16-byte cp.async)");
   if (build_lists(c)) return 1;

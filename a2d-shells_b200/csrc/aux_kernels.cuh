@@ -15,12 +15,15 @@ struct BlockDev {
 
 // element -> block offset table; replaces TACSSchurMat::addValues' findIndex +
 // BCSRMat::addRowValues' bsearch (TACSSchurMat.cpp:453-531, BCSRMat.cpp:1778-1827)
-__global__ void k_build_offsets(int n_elems, const int *conn, int n_blocks, const BlockDev *blk,
+// (npe nodes per element: npe * npe slots per element, slot = npe * i + j for node pair (i, j))
+__global__ void k_build_offsets(int n_elems, int npe, const int *conn, int n_blocks, const BlockDev *blk,
                                 int *off, int *missing) {
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (t >= 16 * (size_t)n_elems) return;
-  const int e = (int)(t >> 4), slot = (int)(t & 15);
-  const int rn = conn[4 * e + (slot >> 2)], cn = conn[4 * e + (slot & 3)];
+  const int n2 = npe * npe;
+  if (t >= n2 * (size_t)n_elems) return;
+  const size_t e = t / n2;
+  const int slot = (int)(t - e * n2);
+  const int rn = conn[npe * e + slot / npe], cn = conn[npe * e + slot % npe];
   int found = -1;
   for (int b = 0; b < n_blocks && found < 0; b++) {
     const int rr = blk[b].row_map ? blk[b].row_map[rn] : (rn < blk[b].nrows ? rn : -1);

@@ -4,7 +4,7 @@
 // items of k_assemble9 (assemble9_kernels.cuh): one thread block per element, every function
 // below is the job of ONE thread for one node / tying point / Gauss point / table entry /
 // element column.  Host-callable as well: tests/host_emul.cpp steps the same functions on the
-// CPU against the oracle (oracle/shell_oracle_q9.c).
+// CPU against the reference-derived fixtures (tests/golden/quad9.npz).
 //
 // Strain order as the reference (TACSShellElementModel.h:33-77, TACSShellConstitutive.h:125):
 //   0,1,2 membrane (e11, e22, 2e12)   3,4,5 bending   6,7 transverse shear (2e23, 2e13)   8 drill

@@ -72,6 +72,17 @@ int a2ds_synchronize(a2ds_ctx *ctx);
  * elem_comp[e] selects the component record below. */
 int a2ds_set_mesh(a2ds_ctx *ctx, int n_nodes, int n_owned, int n_elems, const int *conn,
                   const int *elem_comp);
+/* The same for elements of order x order nodes.  order 2 = a2ds_set_mesh.  order 3: 9-node
+ * shells (TACSQuad9Shell = TACSShellElement<TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3>,
+ * TACSLinearizedRotation, TACSShellLinearModel>, src/elements/shell/TACSShellElementDefs.h:16-18);
+ * conn[9 e + 3 j + i] in the tensor order of TACSShellQuadBasis<3>::getNodePoint
+ * (TACSShellElementQuadBasis.h:147-150).  A 9-node mesh supports the residual and the tangent
+ * matrix of the linear strain model (a2ds_assemble_res, a2ds_assemble_jacobian with gamma = 0,
+ * a2ds_assemble_mat_type(A2DS_STIFFNESS_MATRIX)) with atomic scatter, on natural-order or
+ * caller-supplied patterns, plus everything that works on nodes and blocks (boundary
+ * conditions, halo exchange, matrix algebra, mat-vec); the other assembly entry points fail. */
+int a2ds_set_mesh_order(a2ds_ctx *ctx, int order, int n_nodes, int n_owned, int n_elems,
+                        const int *conn, const int *elem_comp);
 
 /* TACSAssembler::setNodes (src/TACSAssembler.cpp:912): X[3 n + k], all local nodes */
 int a2ds_set_nodes(a2ds_ctx *ctx, const double *X);

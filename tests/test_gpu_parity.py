@@ -840,3 +840,85 @@ def test_device_built_pattern_is_bit_identical(a2ds, orc):
         r2, c2 = asm.mat_pattern(m2)
         assert np.array_equal(r2, rowp) and np.array_equal(c2, cols)
         asm.close()
+
+
+# ---- 9-node shells (TACSQuad9Shell): k_assemble9 against the order-3 oracle ---------------------
+@pytest.mark.parametrize("transform", [0, 1])
+@pytest.mark.parametrize("T,t_offset", [(0.0, 0.0), (10.0, 0.3)])
+def test_quad9_element_level_vs_oracle(a2ds, orc, transform, T, t_offset):
+    from helpers import random_elements9
+    n = 48
+    X, q = random_elements9(n, seed=300 + transform)
+    Cs, eth = a2ds.iso_shell_tables(t_offset=t_offset)
+    axis = np.array([0.3, 1.0, 0.2])
+    conn = np.arange(9 * n, dtype=np.int32).reshape(n, 9)   # every element has its own 9 nodes
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, 9 * n, order=3)
+    asm.set_nodes(X.reshape(-1, 3))
+    asm.set_components(Cs[None], eth[None], temperature=[T], elem_class=[0], transform=transform,
+                       ref_axis=axis)
+    asm.set_state(q.reshape(-1, 6))
+    kmat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(kmat)
+    res = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
+    K = asm.mat_values(kmat)
+    comp = orc.make_comp(0, Cs, eth, (0, 0, 0), T, transform, axis)
+    worst = [0.0, 0.0]
+    for e in range(n):
+        r_o, k_o = orc.jacobian(comp, X[e].ravel(), q[e].ravel(), order=3)
+        worst[0] = max(worst[0], relmax(res[conn[e]].ravel(), r_o))
+        blocks = np.zeros((54, 54))
+        for i in range(9):
+            for j in range(9):
+                kk = rowp[conn[e, i]] + int(np.searchsorted(cols[rowp[conn[e, i]]:rowp[conn[e, i] + 1]], conn[e, j]))
+                blocks[6 * i:6 * i + 6, 6 * j:6 * j + 6] = K[kk]
+        worst[1] = max(worst[1], relmax(blocks, k_o))
+    assert worst[0] < RES_TOL and worst[1] < MAT_TOL, worst
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["plate", "cylinder"])
+def test_quad9_assembly_vs_oracle(a2ds, orc, name):
+    """assembled 9-node meshes with prescribed boundary values: pattern bit-exact, the three
+    entry points (assembleRes, assembleJacobian, assembleMatType(K)) against oracle9_assemble"""
+    if name == "plate":
+        conn, X, bcn = a2ds.meshes.plate9(9, 7, bump=2e-2)
+    else:
+        conn, X, bcn = a2ds.meshes.cylinder9(12, 5)
+    n = len(X)
+    u = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)
+    u[:, 3:] *= 10.0
+    Cs, eth = a2ds.iso_shell_tables()
+    bc_vars = np.full(len(bcn), 63, dtype=np.int32); bc_vars[::2] = 0b000111
+    bc_vals = np.zeros((len(bcn), 6)); bc_vals[:, 0] = -1e-5
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n, order=3)
+    asm.set_nodes(X)
+    asm.set_components(Cs[None], eth[None])
+    asm.set_bcs(bcn, bc_vars, bc_vals)
+    asm.set_state(u)
+    kmat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(kmat)
+    rowp_o, cols_o = orc.pattern(n, conn, order=3)
+    assert np.array_equal(rowp, rowp_o) and np.array_equal(cols, cols_o)
+    comp = orc.make_comp(0, Cs, eth)
+    ec = np.zeros(len(conn), dtype=np.int32)
+    r_o, k_o = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals, order=3)
+    r0_o, _ = orc.assemble(0, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals, order=3)
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL
+    assert relmax(asm.assembleRes(), r0_o) < RES_TOL
+    asm.assembleMatType(a2ds.STIFFNESS_MATRIX, kmat)
+    assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL
+    asm.assembleJacobian(2.5, 0.0, 0.0, kmat)   # alpha scales the tangent, not the BC rows
+    _, k25_o = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals, alpha=2.5,
+                            order=3)
+    assert relmax(asm.mat_values(kmat), k25_o) < MAT_TOL
+    # the entry points 9-node meshes do not provide fail loudly
+    gmat = asm.create_mat()
+    with pytest.raises(RuntimeError):
+        asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gmat)
+    with pytest.raises(RuntimeError):
+        asm.assembleAll(kmat, gmat)
+    asm.close()

@@ -1,0 +1,67 @@
+"""9-node shells (TACSQuad9Shell) on one GPU: residual + tangent of an n x n plate of 9-node
+elements (same node count as a 2n x 2n plate of 4-node elements), device resident.
+python tools/quad9_bench.py [n=500] [steps=5] -> one JSON line"""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+a2ds = importlib.import_module("a2d-shells_b200")
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    conn, X, bcn = a2ds.meshes.plate9(n, n, bump=1e-3)
+    nn = len(X)
+    Cs, eth = a2ds.iso_shell_tables()
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, nn, order=3)
+    asm.set_nodes(X)
+    asm.set_components(Cs[None], eth[None])
+    asm.set_bcs(bcn, 63)
+    asm.set_state(a2ds.meshes.seeded_state(np.arange(nn), 1e-5))
+    kmat = asm.create_mat()
+    for _ in range(3):
+        asm.assembleJacobian(1.0, 0.0, 0.0, kmat, download=False)
+    asm.synchronize()
+    asm.region_begin()
+    for _ in range(steps):
+        asm.assembleJacobian(1.0, 0.0, 0.0, kmat, download=False)
+    ms = asm.region_end() / steps
+    kms = asm.last_kernel_ms()
+    out = {"workload": f"plate {n}x{n} 9-node MITC shells (TACSQuad9Shell), residual + tangent into BCSR6",
+           "elements": len(conn), "nodes": nn, "blocks": int(asm.mat_nnz(kmat)),
+           "ms_per_step": ms, "kernel_ms": kms, "elements_per_s": len(conn) / (ms * 1e-3),
+           "nodes_per_s": nn / (ms * 1e-3)}
+    # sampled parity against the order-3 oracle on the elements around a few nodes (outside the timing)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py as orc
+        res = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
+        rng = np.random.default_rng(1)
+        sample = rng.choice(len(conn), size=64, replace=False)
+        # rows of nodes interior to an element (its centre node 4) get contributions of that element only
+        comp = orc.make_comp(0, Cs, eth)
+        u = a2ds.meshes.seeded_state(np.arange(nn), 1e-5)
+        worst = 0.0
+        bc = set(int(b) for b in bcn)
+        for e in sample:
+            r_o, _ = orc.jacobian(comp, X[conn[e]].ravel(), u[conn[e]].ravel(), order=3)
+            c = int(conn[e, 4])
+            if c in bc:
+                continue
+            worst = max(worst, np.abs(res[c] - r_o[24:30]).max() / np.abs(r_o).max())
+        out["parity_res_centre_nodes_max_rel"] = worst
+    except Exception as ex:  # noqa: BLE001
+        out["parity_error"] = str(ex)
+    asm.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
