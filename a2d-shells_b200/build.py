@@ -9,6 +9,7 @@ SRCS = [os.path.join(HERE, "csrc", "a2ds.cu"), os.path.join(HERE, "csrc", "mesh_
         os.path.join(HERE, "csrc", "partition.cpp")]
 DEPS = SRCS + [os.path.join(HERE, "csrc", "mitc4_math.h"), os.path.join(HERE, "csrc", "mitc4_tying.h"),
                os.path.join(HERE, "csrc", "assemble_kernels.cuh"),
+               os.path.join(HERE, "csrc", "mitc9_math.h"), os.path.join(HERE, "csrc", "assemble9_kernels.cuh"),
                os.path.join(HERE, "csrc", "aux_kernels.cuh"),
                os.path.join(HERE, "..", "include", "a2ds.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

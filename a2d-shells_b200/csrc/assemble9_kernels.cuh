@@ -5,72 +5,100 @@
 // (src/TACSAssembler.cpp:4000-4242) with TACSShellElement::addResidual / addJacobian inside
 // (src/elements/shell/TACSShellElement.h:303-672).
 //
-// One thread block of 7 warps per element, elements drawn from a counter.  The element math
-// (mitc9_math.h) runs as block-level phases over shared memory: 9 node frames, 28 tying points +
-// 9 Gauss-point frames, the derivative tables (28 x 54 tying, 9 x 54 drill), then per row of
-// three Gauss points the 3 x 54 columns of B and w det C B.  The tangent K = sum B^T (w det C B)
-// is contracted on the FP64 tensor path (mma.m8n8k4): warp w owns the 8 rows 8 w .. 8 w + 7 of
-// the 54 x 54 (padded to 56) element matrix and accumulates the tiles on and right of the
-// diagonal (28 of 49, the matrix is symmetric); the accumulators are added to the BCSR blocks
-// straight from registers, mirrored for the off-diagonal tiles — there is no staged element matrix.
+// One thread block per element in flight, elements drawn from a counter.  The element math
+// (mitc9_math.h) runs as block-level phases over shared memory.  Warp 7 is the PRODUCER: it
+// works one element ahead and fills the geometry record of the next element (gather, 9 node
+// frames with the reference's rounding, 28 tying points, 9 Gauss-point frames, strains and
+// stresses of the state) while warps 0..6, the CONSUMERS, turn the current record into the
+// derivative tables (28 x 54 tying, 9 x 54 drill) and, per row of three Gauss points, the
+// 3 x 54 columns of B and w det C B.  The tangent K = sum B^T (w det C B) is contracted on the
+// FP64 tensor path (mma.m8n8k4): consumer warp w owns the 8 rows 8 w .. 8 w + 7 of the 54 x 54
+// (padded to 56) element matrix and accumulates the tiles on and right of the diagonal (28 of
+// 49, the matrix is symmetric); the accumulators are added to the BCSR blocks straight from
+// registers, mirrored for the off-diagonal tiles — there is no staged element matrix.  The two
+// groups meet at one block barrier per element; the consumers synchronise among themselves on
+// a named barrier.
 #ifndef A2DS_ASSEMBLE9_KERNELS_CUH
 #define A2DS_ASSEMBLE9_KERNELS_CUH
 
 #include "mitc9_math.h"
 
-static const int Q9_THREADS = 224;   // 7 warps: one per 8-row tile of the 56 x 56 padded matrix
+static const int Q9_CONSUMERS = 224; // 7 warps: one per 8-row tile of the 56 x 56 padded matrix
+static const int Q9_THREADS = 256;   // + the producer warp
 static const int Q9_QB = 3;          // Gauss points per contraction batch (one eta row)
+#ifndef A2DS_Q9_MINB
+#define A2DS_Q9_MINB 2   // thread blocks per SM the register budget is sized for
+#endif
 
-struct Elem9Block {
-  a2ds::Elem9 E;
-  double B2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];    // B / CB of the other points of the batch
-  double CB2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];
+struct Meta9 {
+  int elem;       // element of the record, -1: the list is exhausted
+  int comp;
   int nodes[9];
   int off[81];
-  int elem;
+};
+struct Elem9Block {
+  a2ds::Elem9 E[2];   // record of the element being contracted / being prepared
+  Meta9 M[2];
+  a2ds::Shape9 H;     // shape function tables, filled once per block
+  double B2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];    // B / CB of the other points of the batch
+  double CB2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];
 };
 
+__device__ __forceinline__ void q9_consumer_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(Q9_CONSUMERS) : "memory");
+}
+
 template <bool RES, bool KMAT>
-__global__ void __launch_bounds__(Q9_THREADS, 2) k_assemble9(KParams p) {
+__global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams p) {
   using namespace a2ds;
   extern __shared__ __align__(16) unsigned char smem9[];
   Elem9Block &S = *reinterpret_cast<Elem9Block *>(smem9);
-  Elem9 &E = S.E;
+  const Shape9 &H = S.H;
+  const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // batch slot qq: tables of Gauss point 3 b + qq of the current batch b
-  auto Bq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? E.B : S.B2[qq - 1]; };
-  auto CBq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? E.CB : S.CB2[qq - 1]; };
-  // rows 9..11 and columns 54, 55 of the tables stay zero
+  if (tid < 46) q9_shape_tables(S.H, tid);
+  // rows 9..11 and columns 54, 55 of the B tables stay zero
   for (int i = tid; i < Q9_KROWS * Q9_LD; i += Q9_THREADS) {
-    (&E.B[0][0])[i] = 0.0; (&E.CB[0][0])[i] = 0.0;
+    for (int k = 0; k < 2; k++) { (&S.E[k].B[0][0])[i] = 0.0; (&S.E[k].CB[0][0])[i] = 0.0; }
     for (int qq = 0; qq < Q9_QB - 1; qq++) { (&S.B2[qq][0][0])[i] = 0.0; (&S.CB2[qq][0][0])[i] = 0.0; }
   }
-  for (;;) {
-    if (tid == 0) S.elem = atomicAdd(p.work_counter, 1);
-    __syncthreads();
-    const int idx = S.elem;
-    if (idx >= p.n_list) break;
-    const int e = p.elem_list ? __ldg(&p.elem_list[idx]) : idx;
-    const CompData &c = p.comps[__ldg(&p.elem_comp[e])];
-    if (tid < 9) S.nodes[tid] = __ldg(&p.conn[9 * (size_t)e + tid]);
-    if (KMAT && tid >= 32 && tid < 32 + 81) S.off[tid - 32] = __ldg(&p.Koff[81 * (size_t)e + tid - 32]);
-    __syncthreads();
-    if (tid < 27) E.X[tid] = __ldg(&p.X[3 * (size_t)S.nodes[tid / 3] + tid % 3]);
-    else if (tid >= 32 && tid < 32 + 54) {
-      const int d = tid - 32;
-      E.q[d] = __ldg(&p.u[6 * (size_t)S.nodes[d / 6] + d % 6]);
-    }
-    __syncthreads();
-    if (tid < 9) q9_node(c, E, tid);
-    __syncthreads();
-    if (tid < 28) q9_tying(E, tid);
-    else if (tid >= 32 && tid < 41) q9_qp(c, E, tid - 32);
-    __syncthreads();
-    for (int i = tid; i < Q9_NTY * Q9_NV; i += Q9_THREADS) E.Gt[i / Q9_NV][i % Q9_NV] = q9_gt(E, i / Q9_NV, i % Q9_NV);
-    for (int i = tid; i < Q9_NN * Q9_NV; i += Q9_THREADS) E.Dn[i / Q9_NV][i % Q9_NV] = q9_dn(E, i / Q9_NV, i % Q9_NV);
-    if (RES && tid >= 192 && tid < 201) q9_qp_state(c, E, tid - 192, p.thermal);
-    __syncthreads();
+  __syncthreads();
 
+  // ---- producer: the geometry record of the next element of the list (one warp) ----
+  auto produce = [&](Elem9 &E, Meta9 &M) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(p.work_counter, 1);
+    idx = __shfl_sync(FULL, idx, 0);
+    if (idx >= p.n_list) {
+      if (lane == 0) M.elem = -1;
+      return;
+    }
+    const int e = p.elem_list ? __ldg(&p.elem_list[idx]) : idx;
+    if (lane == 0) { M.elem = e; M.comp = __ldg(&p.elem_comp[e]); }
+    if (lane < 9) M.nodes[lane] = __ldg(&p.conn[9 * (size_t)e + lane]);
+    if (KMAT)
+      for (int k = lane; k < 81; k += 32) M.off[k] = __ldg(&p.Koff[81 * (size_t)e + k]);
+    __syncwarp();
+    const CompData &c = p.comps[M.comp];
+    if (lane < 27) E.X[lane] = __ldg(&p.X[3 * (size_t)M.nodes[lane / 3] + lane % 3]);
+    for (int d = lane; d < Q9_NV; d += 32) E.q[d] = __ldg(&p.u[6 * (size_t)M.nodes[d / 6] + d % 6]);
+    __syncwarp();
+    if (lane < 9) q9_node(c, E, lane);
+    __syncwarp();
+    if (lane < Q9_NTY) q9_tying(E, H, lane);
+    if (lane < 9) q9_qp(c, E, H, lane);
+    __syncwarp();
+    if (RES && lane < 9) q9_qp_state(c, E, H, lane, p.thermal);
+  };
+
+  // ---- consumers: tables, columns of B, contraction, scatter of one record (7 warps) ----
+  auto consume = [&](Elem9 &E, const Meta9 &M) {
+    const CompData &c = p.comps[M.comp];
+    auto Bq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? E.B : S.B2[qq - 1]; };
+    auto CBq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? E.CB : S.CB2[qq - 1]; };
+    for (int i = tid; i < Q9_NTY * Q9_NV; i += Q9_CONSUMERS) E.Gt[i / Q9_NV][i % Q9_NV] = q9_gt(E, H, i / Q9_NV, i % Q9_NV);
+    for (int i = tid; i < Q9_NN * Q9_NV; i += Q9_CONSUMERS) E.Dn[i / Q9_NV][i % Q9_NV] = q9_dn(E, H, i / Q9_NV, i % Q9_NV);
+    q9_consumer_barrier();
     double acc[7][2];
 #pragma unroll
     for (int t = 0; t < 7; t++) acc[t][0] = acc[t][1] = 0.0;
@@ -79,14 +107,14 @@ __global__ void __launch_bounds__(Q9_THREADS, 2) k_assemble9(KParams p) {
       if (tid < Q9_QB * Q9_NV) {
         const int qq = tid / Q9_NV, col = tid - Q9_NV * qq, q = Q9_QB * b + qq;
         double Bk[9], Sk[9];
-        q9_bcol(E, q, col, Bk);
+        q9_bcol(E, H, q, col, Bk);
         q9_stress(c.Cs, Bk, Sk);
         double(*Bt)[Q9_LD] = Bq(qq), (*Ct)[Q9_LD] = CBq(qq);
         const double w = E.qw[q];
 #pragma unroll
         for (int k = 0; k < 9; k++) { Bt[k][col] = Bk[k]; Ct[k][col] = w * Sk[k]; }
       }
-      __syncthreads();
+      q9_consumer_barrier();
       if (KMAT) {
 #pragma unroll
         for (int qq = 0; qq < Q9_QB; qq++) {
@@ -110,10 +138,10 @@ __global__ void __launch_bounds__(Q9_THREADS, 2) k_assemble9(KParams p) {
           for (int k = 0; k < 9; k++) r += Bt[k][tid] * s[k];
         }
       }
-      __syncthreads();
+      q9_consumer_barrier();
     }
     if (RES && tid < Q9_NV)
-      atomicAdd(&p.res[6 * (size_t)S.nodes[tid / 6] + tid % 6], p.res_scale * r);
+      atomicAdd(&p.res[6 * (size_t)M.nodes[tid / 6] + tid % 6], p.res_scale * r);
     if (KMAT) {
       // accumulator (row, col) of tile (warp, tj): rows 8 warp + lane / 4, columns 8 tj + 2 (lane % 4) + i
       const int gr = 8 * warp + (lane >> 2);
@@ -128,13 +156,22 @@ __global__ void __launch_bounds__(Q9_THREADS, 2) k_assemble9(KParams p) {
             if (gc >= Q9_NV) continue;
             const int bc = gc / 6, cc = gc - 6 * bc;
             const double v = p.alpha * acc[tj][i];
-            atomicAdd(p.Kval + 36 * (size_t)S.off[9 * br + bc] + 6 * rr + cc, v);
-            if (tj > warp) atomicAdd(p.Kval + 36 * (size_t)S.off[9 * bc + br] + 6 * cc + rr, v);
+            atomicAdd(p.Kval + 36 * (size_t)M.off[9 * br + bc] + 6 * rr + cc, v);
+            if (tj > warp) atomicAdd(p.Kval + 36 * (size_t)M.off[9 * bc + br] + 6 * cc + rr, v);
           }
         }
       }
     }
-    // S.elem, S.nodes and S.off are rewritten only after the barriers at the top of the next trip
+  };
+
+  int cur = 0;
+  if (warp == 7) produce(S.E[0], S.M[0]);
+  for (;;) {
+    __syncthreads();   // record `cur` is complete, record `cur ^ 1` is free again
+    if (S.M[cur].elem < 0) break;
+    if (warp == 7) produce(S.E[cur ^ 1], S.M[cur ^ 1]);
+    else consume(S.E[cur], S.M[cur]);
+    cur ^= 1;
   }
 }
 

@@ -45,6 +45,16 @@ struct Elem9 {
   double CB[Q9_KROWS][Q9_LD];       // w det C B
 };
 
+// shape function tables of the element class (the same for every element: filled once per
+// thread block): values and parametric derivatives at the 9 Gauss points, the 28 tying points
+// and the 9 node points, node index 3 j + i
+struct Shape9 {
+  double Nq[9][9], Nxq[9][9], Neq[9][9];
+  double Nt[Q9_NTY][9], Nxt[Q9_NTY][9], Net[Q9_NTY][9];
+  double Nxn[9][9], Nen[9][9];
+  int tfield[Q9_NTY];
+};
+
 // quadratic Lagrange functions on {-1, 0, 1} (TacsLagrangeLobattoShapeFuncDerivative<3>, :96-104)
 A2DS_HD void q9_lag(double u, double N[3], double dN[3]) {
   N[0] = -0.5 * u * (1.0 - u); N[1] = (1.0 - u) * (1.0 + u); N[2] = 0.5 * (1.0 + u) * u;
@@ -89,6 +99,25 @@ A2DS_HD void q9_shape(const double pt[2], double N[9], double Nx[9], double Ne[9
       Nx[3 * j + i] = da[i] * nb[j];
       Ne[3 * j + i] = na[i] * db[j];
     }
+}
+// table rows of point p: 0..8 Gauss points, 9..36 tying points, 37..45 node points
+A2DS_HD void q9_shape_tables(Shape9 &H, int p) {
+  double pt[2], N[9], Nx[9], Ne[9];
+  if (p < 9) {
+    pt[0] = q9_gauss3(p % 3); pt[1] = q9_gauss3(p / 3);
+    q9_shape(pt, N, Nx, Ne);
+    for (int n = 0; n < 9; n++) { H.Nq[p][n] = N[n]; H.Nxq[p][n] = Nx[n]; H.Neq[p][n] = Ne[n]; }
+  } else if (p < 9 + Q9_NTY) {
+    const int t = p - 9;
+    H.tfield[t] = q9_ty_point(t, pt);
+    q9_shape(pt, N, Nx, Ne);
+    for (int n = 0; n < 9; n++) { H.Nt[t][n] = N[n]; H.Nxt[t][n] = Nx[n]; H.Net[t][n] = Ne[n]; }
+  } else {
+    const int m = p - 9 - Q9_NTY;
+    pt[0] = -1.0 + (m % 3); pt[1] = -1.0 + (m / 3);
+    q9_shape(pt, N, Nx, Ne);
+    for (int n = 0; n < 9; n++) { H.Nxn[m][n] = Nx[n]; H.Nen[m][n] = Ne[n]; }
+  }
 }
 A2DS_HD void q9_interp3(const double w[9], const double *v, int ld, double f[3]) {
   f[0] = f[1] = f[2] = 0.0;
@@ -196,10 +225,9 @@ A2DS_HD void q9_node(const CompData &c, Elem9 &E, int n) {
 
 // ---- tying point t: frame vectors and the tying strain of the state ---------------------------
 // TACSShellLinearModel::computeTyingStrain (TACSShellElementModel.h:33-77)
-A2DS_HD void q9_tying(Elem9 &E, int t) {
-  double pt[2], N[9], Nx[9], Ne[9];
-  const int field = q9_ty_point(t, pt);
-  q9_shape(pt, N, Nx, Ne);
+A2DS_HD void q9_tying(Elem9 &E, const Shape9 &H, int t) {
+  const double *N = H.Nt[t], *Nx = H.Nxt[t], *Ne = H.Net[t];
+  const int field = H.tfield[t];
   double Xxi[3], Xeta[3], n0[3], Uxi[3], Ueta[3], d0[3];
   q9_interp3(Nx, E.X, 3, Xxi);
   q9_interp3(Ne, E.X, 3, Xeta);
@@ -219,10 +247,8 @@ A2DS_HD void q9_tying(Elem9 &E, int t) {
 
 // ---- Gauss point q: frame, Xd^-1 T, the through-thickness term, weight * det -------------------
 // TACSShellElement.h:514-534, TacsShellComputeDispGrad (TACSShellUtilities.h:369-393)
-A2DS_HD void q9_qp(const CompData &c, Elem9 &E, int q) {
-  const double pt[2] = {q9_gauss3(q % 3), q9_gauss3(q / 3)};
-  double N[9], Nx[9], Ne[9];
-  q9_shape(pt, N, Nx, Ne);
+A2DS_HD void q9_qp(const CompData &c, Elem9 &E, const Shape9 &H, int q) {
+  const double *N = H.Nq[q], *Nx = H.Nxq[q], *Ne = H.Neq[q];
   double Xxi[3], Xeta[3], n0[3], nxi[3], neta[3];
   q9_interp3(Nx, E.X, 3, Xxi);
   q9_interp3(Ne, E.X, 3, Xeta);
@@ -297,10 +323,8 @@ A2DS_HD void q9_stress(const double Cs[22], const double e[9], double s[9]) {
 
 // ---- Gauss point q: strains of the state and the weighted stresses ----------------------------
 // TACSShellElement::addResidual, TACSShellElement.h:314-373 (thermal: :549-574)
-A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, int q, double thermal) {
-  const double pt[2] = {q9_gauss3(q % 3), q9_gauss3(q / 3)};
-  double N[9], Nx[9], Ne[9];
-  q9_shape(pt, N, Nx, Ne);
+A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, const Shape9 &H, int q, double thermal) {
+  const double *N = H.Nq[q], *Nx = H.Nxq[q], *Ne = H.Neq[q];
   double e[9], g[5];
   q9_interp_tying(q, E.ety, 1, g);
   q9_membrane_shear(E.qA[q], g, e);
@@ -330,13 +354,10 @@ A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, int q, double thermal) {
 
 // ---- table entries ----------------------------------------------------------------------------
 // Gt[t][dof] = d(tying strain t)/d(dof), dof = 6 m + k (k < 3 displacement, k >= 3 rotation)
-A2DS_HD double q9_gt(const Elem9 &E, int t, int dof) {
-  double pt[2], na[3], nb[3], da[3], db[3];
-  const int field = q9_ty_point(t, pt);
-  q9_lag(pt[0], na, da);
-  q9_lag(pt[1], nb, db);
-  const int m = dof / 6, k = dof % 6, i = m % 3, j = m / 3;
-  const double N = na[i] * nb[j], Nx = da[i] * nb[j], Ne = na[i] * db[j];
+A2DS_HD double q9_gt(const Elem9 &E, const Shape9 &H, int t, int dof) {
+  const int field = H.tfield[t];
+  const int m = dof / 6, k = dof % 6;
+  const double N = H.Nt[t][m], Nx = H.Nxt[t][m], Ne = H.Net[t][m];
   if (k < 3) {
     if (field == 0) return Nx * E.tXxi[t][k];
     if (field == 1) return Ne * E.tXeta[t][k];
@@ -351,25 +372,16 @@ A2DS_HD double q9_gt(const Elem9 &E, int t, int dof) {
   return 0.5 * N * (f[c1] * v[c2] - f[c2] * v[c1]);
 }
 // Dn[n][dof] = d(drill strain at node n)/d(dof)
-A2DS_HD double q9_dn(const Elem9 &E, int n, int dof) {
+A2DS_HD double q9_dn(const Elem9 &E, const Shape9 &H, int n, int dof) {
   const int m = dof / 6, k = dof % 6;
   if (k >= 3) return m == n ? -E.t2n[3 * n + k - 3] : 0.0;
-  const double pt[2] = {-1.0 + (n % 3), -1.0 + (n / 3)};
-  double na[3], nb[3], da[3], db[3];
-  q9_lag(pt[0], na, da);
-  q9_lag(pt[1], nb, db);
-  const int i = m % 3, j = m / 3;
-  return da[i] * nb[j] * E.a1[3 * n + k] + na[i] * db[j] * E.a2[3 * n + k];
+  return H.Nxn[n][m] * E.a1[3 * n + k] + H.Nen[n][m] * E.a2[3 * n + k];
 }
 
 // ---- column `dof` of B at Gauss point q (9 strain rows) ----------------------------------------
-A2DS_HD void q9_bcol(const Elem9 &E, int q, int dof, double Bk[9]) {
-  const double pt[2] = {q9_gauss3(q % 3), q9_gauss3(q / 3)};
-  double na[3], nb[3], da[3], db[3];
-  q9_lag(pt[0], na, da);
-  q9_lag(pt[1], nb, db);
-  const int m = dof / 6, k = dof % 6, i = m % 3, j = m / 3;
-  const double N = na[i] * nb[j], Nx = da[i] * nb[j], Ne = na[i] * db[j];
+A2DS_HD void q9_bcol(const Elem9 &E, const Shape9 &H, int q, int dof, double Bk[9]) {
+  const int m = dof / 6, k = dof % 6;
+  const double N = H.Nq[q][m], Nx = H.Nxq[q][m], Ne = H.Neq[q][m];
   double g[5];
   q9_interp_tying(q, &E.Gt[0][dof], Q9_LD, g);
   q9_membrane_shear(E.qA[q], g, Bk);
@@ -393,11 +405,8 @@ A2DS_HD void q9_bcol(const Elem9 &E, int q, int dof, double Bk[9]) {
   Bk[3] = w0 * v0;
   Bk[4] = w1 * v1;
   Bk[5] = w1 * v0 + w0 * v1;
-  double N9[9];
-  for (int jj = 0; jj < 3; jj++)
-    for (int ii = 0; ii < 3; ii++) N9[3 * jj + ii] = na[ii] * nb[jj];
   double d = 0.0;
-  for (int n = 0; n < 9; n++) d += N9[n] * E.Dn[n][dof];
+  for (int n = 0; n < 9; n++) d += H.Nq[q][n] * E.Dn[n][dof];
   Bk[8] = d;
 }
 

@@ -244,20 +244,22 @@ extern "C" int emul_element9(const double *Cs, const double *eth, double tempera
   memset(&E, 0, sizeof(E));
   memcpy(E.X, X, sizeof(E.X));
   memcpy(E.q, q, sizeof(E.q));
+  static Shape9 H;
+  for (int pnt = 0; pnt < 46; pnt++) q9_shape_tables(H, pnt);
   for (int n = 0; n < 9; n++) q9_node(c, E, n);
-  for (int t = 0; t < 28; t++) q9_tying(E, t);
-  for (int qp = 0; qp < 9; qp++) q9_qp(c, E, qp);
+  for (int t = 0; t < 28; t++) q9_tying(E, H, t);
+  for (int qp = 0; qp < 9; qp++) q9_qp(c, E, H, qp);
   for (int t = 0; t < 28; t++)
-    for (int d = 0; d < 54; d++) E.Gt[t][d] = q9_gt(E, t, d);
+    for (int d = 0; d < 54; d++) E.Gt[t][d] = q9_gt(E, H, t, d);
   for (int n = 0; n < 9; n++)
-    for (int d = 0; d < 54; d++) E.Dn[n][d] = q9_dn(E, n, d);
-  for (int qp = 0; qp < 9; qp++) q9_qp_state(c, E, qp, 1.0);
+    for (int d = 0; d < 54; d++) E.Dn[n][d] = q9_dn(E, H, n, d);
+  for (int qp = 0; qp < 9; qp++) q9_qp_state(c, E, H, qp, 1.0);
   memset(res, 0, 54 * sizeof(double));
   memset(K, 0, 54 * 54 * sizeof(double));
   for (int qp = 0; qp < 9; qp++) {
     for (int d = 0; d < 54; d++) {
       double Bk[9], Sk[9];
-      q9_bcol(E, qp, d, Bk);
+      q9_bcol(E, H, qp, d, Bk);
       q9_stress(c.Cs, Bk, Sk);
       for (int k = 0; k < 9; k++) { E.B[k][d] = Bk[k]; E.CB[k][d] = E.qw[qp] * Sk[k]; }
     }

@@ -60,6 +60,30 @@ def main():
     except Exception as ex:  # noqa: BLE001
         out["parity_error"] = str(ex)
     asm.close()
+    # the unmodified reference beside it (oracle/_ref): assembleJacobian of TACSQuad9Shell on a
+    # bounded sample of the same mesh family, threaded as the reference allows
+    try:
+        import refdrv
+        if refdrv.available():
+            nr = min(n, 120)
+            conn_r, X_r, bcn_r = a2ds.meshes.plate9(nr, nr, bump=1e-3)
+            ra = refdrv.RefAssembler(conn_r, X_r, np.zeros(len(conn_r), dtype=np.int32),
+                                     refdrv.iso_props(kind=2)[None], bcn_r, [list(range(6))] * len(bcn_r),
+                                     [[0.0] * 6] * len(bcn_r), nodes_per_elem=9)
+            ur = np.zeros((len(X_r), 6))
+            ur[ra.new_nodes] = a2ds.meshes.seeded_state(np.arange(len(X_r)), 1e-5)
+            ra.set_state(ur)
+            km = ra.mat_create(1)
+            threads = min(16, os.cpu_count() or 1)
+            ra.set_threads(threads)
+            ra.time(1, km)
+            t = float(np.median([ra.time(1, km) for _ in range(3)]))
+            ra.close()
+            out["cpu_reference"] = {"elements_per_s": len(conn_r) / t, "cores": threads, "kind": "reference",
+                                    "sample": f"plate {nr}x{nr} 9-node elements, assembleJacobian into TACSSchurMat, "
+                                              f"median of 3, {threads} pthreads"}
+    except Exception as ex:  # noqa: BLE001
+        out["cpu_reference_error"] = str(ex)
     print(json.dumps(out))
 
 
