@@ -1443,9 +1443,9 @@ static int launch_mass(a2ds_ctx *c, KParams &p) {
 }
 
 // 9-node elements: one thread block per element (assemble9_kernels.cuh)
-template <bool RES, bool KMAT>
+template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_nine(a2ds_ctx *c, KParams &p) {
-  auto kern = k_assemble9<RES, KMAT>;
+  auto kern = k_assemble9<RES, KMAT, GMAT, NL>;
   static int per_sm_dev[MAX_DEVICES] = {0};   // function attributes are device state
   int &per_sm = per_sm_dev[c->device];
   const size_t smem = (sizeof(Elem9Block) + 15) & ~size_t(15);
@@ -1456,8 +1456,8 @@ static int launch_nine(a2ds_ctx *c, KParams &p) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q9_THREADS, smem));
     if (per_sm == 0) return fail("k_assemble9 does not fit on an SM");
     if (getenv("A2DS_VERBOSE"))
-      fprintf(stderr, "[a2ds] k_assemble9<%d,%d>: %zu B shared per block, %d blocks/SM\n", (int)RES,
-              (int)KMAT, smem, per_sm);
+      fprintf(stderr, "[a2ds] k_assemble9<%d,%d,%d,%d>: %zu B shared per block, %d blocks/SM\n", (int)RES,
+              (int)KMAT, (int)GMAT, (int)NL, smem, per_sm);
   }
   if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, (1 + MAX_ZERO_ROUNDS) * sizeof(int)));
   p.work_counter = c->work_counter;
@@ -1472,15 +1472,22 @@ static int launch_nine(a2ds_ctx *c, KParams &p) {
 // element kernels of one class list (p.elem_list / p.n_list set) for the outputs in `what`
 static int launch_class(a2ds_ctx *c, KParams &p, int cls, int what) {
   if (c->npe == 9) {
-    // TACSQuad9Shell: residual and tangent of the linear strain model (any 22-entry section)
-    if (cls & 1) return fail("assemble: the nonlinear strain model is not available for 9-node elements");
-    switch (what) {
-      case 0: return 0;
-      case 1: return launch_nine<true, false>(c, p);
-      case 2: return launch_nine<false, true>(c, p);
-      case 3: return launch_nine<true, true>(c, p);
-      default: return fail("assemble: 9-node elements provide the residual and the tangent matrix only");
+    // TACSQuad9Shell / TACSQuad9NonlinearShell (any 22-entry section).  The geometric stiffness
+    // is the linear-in-state term for both classes, as for the 4-node elements below.
+    int rc = 0;
+    if (cls & 1) {
+      if (what & 1 || what & 2)
+        rc = (what & 3) == 1 ? launch_nine<true, false, false, true>(c, p)
+           : (what & 3) == 2 ? launch_nine<false, true, false, true>(c, p)
+                             : launch_nine<true, true, false, true>(c, p);
+    } else {
+      if (what & 1 || what & 2)
+        rc = (what & 3) == 1 ? launch_nine<true, false, false, false>(c, p)
+           : (what & 3) == 2 ? launch_nine<false, true, false, false>(c, p)
+                             : launch_nine<true, true, false, false>(c, p);
     }
+    if (!rc && (what & 4)) rc = launch_nine<false, false, true, false>(c, p);
+    return rc;
   }
   const bool cpl = cls >= 2;
   int rc = 0;
@@ -1669,8 +1676,9 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   const int kmat = rq.kmat, gmat = rq.gmat, mmat = rq.mmat;
   // inertial residual M * uddot (TACSShellElement.h:410-447) once second derivatives are set
   const bool MRES = RES && c->udd != nullptr;
-  if (c->npe != 4 && (MM || MRES || GM || c->scatter_mode != A2DS_SCATTER_ATOMIC))
-    return fail("assemble: 9-node elements provide the residual and the tangent matrix (atomic scatter) only");
+  if (c->npe != 4 && (MM || MRES || c->scatter_mode != A2DS_SCATTER_ATOMIC))
+    return fail("assemble: 9-node elements provide the residual, the tangent and the geometric stiffness "
+                "(atomic scatter); no mass terms");
   if (KM && check_mat(c, kmat)) return 1;
   if (GM && check_mat(c, gmat)) return 1;
   if (MM && check_mat(c, mmat)) return 1;

@@ -1,9 +1,12 @@
-// assemble9_kernels.cuh — k_assemble9<RES, KMAT>: residual and tangent of the 9-node MITC shell
-// (TACSQuad9Shell, linear strain model) assembled into the same 6 x 6 BCSR matrices and node
-// vectors as the 4-node path.  Replaces, for that element class, the element loop of
-// TACSAssembler::assembleRes / assembleJacobian / assembleMatType(STIFFNESS)
-// (src/TACSAssembler.cpp:4000-4242) with TACSShellElement::addResidual / addJacobian inside
-// (src/elements/shell/TACSShellElement.h:303-672).
+// assemble9_kernels.cuh — k_assemble9<RES, KMAT, GMAT, NL>: residual, tangent and geometric
+// stiffness of the 9-node MITC shells (TACSQuad9Shell, NL: TACSQuad9NonlinearShell) assembled
+// into the same 6 x 6 BCSR matrices and node vectors as the 4-node path.  Replaces, for these
+// element classes, the element loop of TACSAssembler::assembleRes / assembleJacobian /
+// assembleMatType(STIFFNESS, GEOMETRIC_STIFFNESS) (src/TACSAssembler.cpp:4000-4242) with
+// TACSShellElement::addResidual / addJacobian / getMatType inside
+// (src/elements/shell/TACSShellElement.h:303-771).  The geometric stiffness is the exact
+// linear-in-(state, temperature) part of the nonlinear tangent, G = L^T C B1(q) + B1(q)^T C L +
+// sum_i sigma_i d2e_i, where the reference takes a central difference of that tangent (:705-751).
 //
 // One thread block per element in flight, elements drawn from a counter.  The element math
 // (mitc9_math.h) runs as block-level phases over shared memory.  Warp 7 is the PRODUCER: it
@@ -40,16 +43,35 @@ struct Elem9Block {
   a2ds::Elem9 E[2];   // record of the element being contracted / being prepared
   Meta9 M[2];
   a2ds::Shape9 H;     // shape function tables, filled once per block
+  a2ds::Tab9 T;       // derivative tables of the element being contracted (ends with B, CB)
   double B2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];    // B / CB of the other points of the batch
   double CB2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];
+  // Once the last batch is contracted the tables are dead and hold the element matrix on its
+  // way out: T.B .. CB2 (4032 doubles, contiguous) the 54 x 54 contraction result, T.Gt .. T.Gt1
+  // (3136 doubles) the 54 x 54 geometric term, both in BCSR block order (k9_at).
 };
+static_assert(offsetof(Elem9Block, B2) == offsetof(Elem9Block, T) + offsetof(a2ds::Tab9, CB) +
+                                              sizeof(double) * a2ds::Q9_KROWS * a2ds::Q9_LD,
+              "T.B, T.CB, B2, CB2 must be contiguous");
+static_assert(offsetof(a2ds::Tab9, Gt1) == offsetof(a2ds::Tab9, Gt) + sizeof(double) * a2ds::Q9_NTY * a2ds::Q9_LD,
+              "T.Gt, T.Gt1 must be contiguous");
+// entry (r, c) of the 54 x 54 element matrix in the order the 81 BCSR blocks want it
+__device__ __forceinline__ int k9_at(int r, int c) {
+  const int br = r / 6, bc = c / 6;
+  return 36 * (9 * br + bc) + 6 * (r - 6 * br) + (c - 6 * bc);
+}
 
 __device__ __forceinline__ void q9_consumer_barrier() {
   asm volatile("bar.sync 1, %0;" ::"n"(Q9_CONSUMERS) : "memory");
 }
 
-template <bool RES, bool KMAT>
+// KMAT and GMAT are separate instantiations (one w det C B table): <.., 1, 0, NL> tangent
+// (alpha K into Kval through Koff), <0, 0, 1, 0> geometric stiffness (gscale G into Gval through Goff)
+template <bool RES, bool KMAT, bool GMAT, bool NL>
 __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams p) {
+  static_assert(!(KMAT && GMAT), "tangent and geometric stiffness are separate launches");
+  constexpr bool STATE = RES || GMAT || NL;   // strains / stresses of the state are needed
+  constexpr bool BIL = GMAT || NL;            // bilinear strain terms are needed
   using namespace a2ds;
   extern __shared__ __align__(16) unsigned char smem9[];
   Elem9Block &S = *reinterpret_cast<Elem9Block *>(smem9);
@@ -59,7 +81,7 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
   if (tid < 46) q9_shape_tables(S.H, tid);
   // rows 9..11 and columns 54, 55 of the B tables stay zero
   for (int i = tid; i < Q9_KROWS * Q9_LD; i += Q9_THREADS) {
-    for (int k = 0; k < 2; k++) { (&S.E[k].B[0][0])[i] = 0.0; (&S.E[k].CB[0][0])[i] = 0.0; }
+    (&S.T.B[0][0])[i] = 0.0; (&S.T.CB[0][0])[i] = 0.0;
     for (int qq = 0; qq < Q9_QB - 1; qq++) { (&S.B2[qq][0][0])[i] = 0.0; (&S.CB2[qq][0][0])[i] = 0.0; }
   }
   __syncthreads();
@@ -76,8 +98,10 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
     const int e = p.elem_list ? __ldg(&p.elem_list[idx]) : idx;
     if (lane == 0) { M.elem = e; M.comp = __ldg(&p.elem_comp[e]); }
     if (lane < 9) M.nodes[lane] = __ldg(&p.conn[9 * (size_t)e + lane]);
-    if (KMAT)
-      for (int k = lane; k < 81; k += 32) M.off[k] = __ldg(&p.Koff[81 * (size_t)e + k]);
+    if (KMAT || GMAT) {
+      const int *off = GMAT ? p.Goff : p.Koff;
+      for (int k = lane; k < 81; k += 32) M.off[k] = __ldg(&off[81 * (size_t)e + k]);
+    }
     __syncwarp();
     const CompData &c = p.comps[M.comp];
     if (lane < 27) E.X[lane] = __ldg(&p.X[3 * (size_t)M.nodes[lane / 3] + lane % 3]);
@@ -85,19 +109,27 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
     __syncwarp();
     if (lane < 9) q9_node(c, E, lane);
     __syncwarp();
-    if (lane < Q9_NTY) q9_tying(E, H, lane);
-    if (lane < 9) q9_qp(c, E, H, lane);
+    if (lane < Q9_NTY) q9_tying(E, H, lane, NL);
+    if (lane < 9) q9_qp(c, E, H, lane, BIL);
     __syncwarp();
-    if (RES && lane < 9) q9_qp_state(c, E, H, lane, p.thermal);
+    if (STATE && lane < 9) q9_qp_state(c, E, H, lane, p.thermal, NL, BIL);
+    if (BIL) {
+      __syncwarp();
+      if (lane < Q9_NTY) q9_sigt(E, H, lane);
+    }
   };
 
   // ---- consumers: tables, columns of B, contraction, scatter of one record (7 warps) ----
-  auto consume = [&](Elem9 &E, const Meta9 &M) {
+  auto consume = [&](const Elem9 &E, const Meta9 &M) {
     const CompData &c = p.comps[M.comp];
-    auto Bq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? E.B : S.B2[qq - 1]; };
-    auto CBq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? E.CB : S.CB2[qq - 1]; };
-    for (int i = tid; i < Q9_NTY * Q9_NV; i += Q9_CONSUMERS) E.Gt[i / Q9_NV][i % Q9_NV] = q9_gt(E, H, i / Q9_NV, i % Q9_NV);
-    for (int i = tid; i < Q9_NN * Q9_NV; i += Q9_CONSUMERS) E.Dn[i / Q9_NV][i % Q9_NV] = q9_dn(E, H, i / Q9_NV, i % Q9_NV);
+    Tab9 &Tb = S.T;
+    auto Bq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? Tb.B : S.B2[qq - 1]; };
+    auto CBq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? Tb.CB : S.CB2[qq - 1]; };
+    for (int i = tid; i < Q9_NTY * Q9_NV; i += Q9_CONSUMERS) {
+      Tb.Gt[i / Q9_NV][i % Q9_NV] = q9_gt(E, H, i / Q9_NV, i % Q9_NV);
+      if (BIL) Tb.Gt1[i / Q9_NV][i % Q9_NV] = q9_gt1(E, H, i / Q9_NV, i % Q9_NV);
+    }
+    for (int i = tid; i < Q9_NN * Q9_NV; i += Q9_CONSUMERS) Tb.Dn[i / Q9_NV][i % Q9_NV] = q9_dn(E, H, i / Q9_NV, i % Q9_NV);
     q9_consumer_barrier();
     double acc[7][2];
 #pragma unroll
@@ -106,16 +138,22 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
     for (int b = 0; b < 3; b++) {
       if (tid < Q9_QB * Q9_NV) {
         const int qq = tid / Q9_NV, col = tid - Q9_NV * qq, q = Q9_QB * b + qq;
-        double Bk[9], Sk[9];
-        q9_bcol(E, H, q, col, Bk);
-        q9_stress(c.Cs, Bk, Sk);
+        double Bk[9], B1k[9], Sk[9];
+        q9_bcol(E, Tb, H, q, col, Bk, BIL ? B1k : nullptr);
+        if (NL) {   // B of the nonlinear model = L + Bil(q, .)
+#pragma unroll
+          for (int k = 0; k < 9; k++) Bk[k] += B1k[k];
+        }
+        q9_stress(c.Cs, GMAT ? B1k : Bk, Sk);
         double(*Bt)[Q9_LD] = Bq(qq), (*Ct)[Q9_LD] = CBq(qq);
         const double w = E.qw[q];
 #pragma unroll
         for (int k = 0; k < 9; k++) { Bt[k][col] = Bk[k]; Ct[k][col] = w * Sk[k]; }
       }
       q9_consumer_barrier();
-      if (KMAT) {
+      if (KMAT || GMAT) {
+        // K = B^T (w det C B): symmetric, tiles on and right of the diagonal;
+        // Z = L^T (w det C B1): all 49 tiles, G = Z + Z^T is formed by the scatter
 #pragma unroll
         for (int qq = 0; qq < Q9_QB; qq++) {
           const double(*Bt)[Q9_LD] = Bq(qq), (*Ct)[Q9_LD] = CBq(qq);
@@ -125,7 +163,7 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
             const double a = Bt[kr][8 * warp + (lane >> 2)];
 #pragma unroll
             for (int tj = 0; tj < 7; tj++)
-              if (tj >= warp) dmma884(acc[tj], a, Ct[kr][8 * tj + (lane >> 2)]);
+              if (GMAT || tj >= warp) dmma884(acc[tj], a, Ct[kr][8 * tj + (lane >> 2)]);
           }
         }
       }
@@ -142,24 +180,53 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
     }
     if (RES && tid < Q9_NV)
       atomicAdd(&p.res[6 * (size_t)M.nodes[tid / 6] + tid % 6], p.res_scale * r);
-    if (KMAT) {
-      // accumulator (row, col) of tile (warp, tj): rows 8 warp + lane / 4, columns 8 tj + 2 (lane % 4) + i
+    if (KMAT || GMAT) {
+      double *vals = GMAT ? p.Gval : p.Kval;
+      const double scale = GMAT ? p.gscale : p.alpha;
+      // the tables are dead (barrier at the end of the last batch): stage the accumulators in
+      // block order — accumulator (row, col) of tile (warp, tj): rows 8 warp + lane / 4, columns
+      // 8 tj + 2 (lane % 4) + i; K: off-diagonal tiles mirrored — and the geometric term beside it
+      double *Ke = &Tb.B[0][0], *Kg = &Tb.Gt[0][0];
       const int gr = 8 * warp + (lane >> 2);
       if (gr < Q9_NV) {
-        const int br = gr / 6, rr = gr - 6 * br;
 #pragma unroll
         for (int tj = 0; tj < 7; tj++) {
-          if (tj < warp) continue;
+          if (!GMAT && tj < warp) continue;
 #pragma unroll
           for (int i = 0; i < 2; i++) {
             const int gc = 8 * tj + 2 * (lane & 3) + i;
             if (gc >= Q9_NV) continue;
-            const int bc = gc / 6, cc = gc - 6 * bc;
-            const double v = p.alpha * acc[tj][i];
-            atomicAdd(p.Kval + 36 * (size_t)M.off[9 * br + bc] + 6 * rr + cc, v);
-            if (tj > warp) atomicAdd(p.Kval + 36 * (size_t)M.off[9 * bc + br] + 6 * cc + rr, v);
+            Ke[k9_at(gr, gc)] = acc[tj][i];
+            if (!GMAT && tj > warp) Ke[k9_at(gc, gr)] = acc[tj][i];
           }
         }
+      }
+      // geometric term of the 81 node pairs (four 3 x 3 quadrants each): all of it for G, the
+      // stress term of the nonlinear tangent
+      if (BIL) {
+        for (int item = tid; item < 4 * 81; item += Q9_CONSUMERS) {
+          const int pair = item >> 2, ha = (item >> 1) & 1, hb = item & 1;
+          double o[9];
+          q9_geo_quadrant(E, H, pair / 9, pair % 9, ha, hb, o);
+          double *dst = Kg + 36 * pair + 18 * ha + 3 * hb;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) dst[6 * i + j] = o[3 * i + j];
+        }
+      }
+      q9_consumer_barrier();
+      // 81 blocks x 36 entries leave as coalesced REDs: consecutive threads, consecutive doubles
+      // of a block.  G = Z + Z^T + geometric term: the transposed entry is read from the tile.
+      for (int idx = tid; idx < 81 * 36; idx += Q9_CONSUMERS) {
+        const int blk = idx / 36, ent = idx - 36 * blk;
+        double v = Ke[idx];
+        if (GMAT) {
+          const int br = blk / 9, bc = blk - 9 * br, rr = ent / 6, cc = ent - 6 * rr;
+          v += Ke[36 * (9 * bc + br) + 6 * cc + rr];
+        }
+        if (BIL) v += Kg[idx];
+        atomicAdd(vals + 36 * (size_t)M.off[blk] + ent, scale * v);
       }
     }
   };

@@ -27,7 +27,7 @@ namespace a2ds {
 
 static const int Q9_NN = 9, Q9_NV = 54, Q9_NTY = 28, Q9_LD = 56, Q9_KROWS = 12;
 
-// element record in shared memory (one per thread block)
+// geometry + state record of one element in shared memory (written by the producer warp)
 struct Elem9 {
   double X[27], q[54];
   double fn[27];                    // node normals (TacsShellComputeNodeNormals)
@@ -35,14 +35,23 @@ struct Elem9 {
   double a1[27], a2[27], t2n[27];   // drill derivative coefficients per node, node normal axis
   double etn[9];                    // drill strain of the state at the nodes
   double tXxi[28][3], tXeta[28][3], tn0[28][3];   // tying-point frames
+  double tUxi[28][3], tUeta[28][3], td0[28][3];   // the same of the state: u,xi  u,eta  director
   double ety[28];                   // tying strains of the state
   double qT[9][9], qA[9][9], qZ[9][9];            // Gauss point: T, Xd^-1 T, -Xd^-1 Xdz Xd^-1 T
   double qw[9];                     // quadrature weight * det(Xd)
+  double qP[9][9];                  // T T^T (the natural transform's frame is not orthogonal, see q9_transform)
   double sq[9][9];                  // w det C (e - T e_th) at the Gauss points
+  double qU0[9][6], qU1[9][6];      // columns 0, 1 of u0x, u1x of the state, [2 i + j]
+  double shat[9][5];                // sq pulled back to the tying components (g11 g22 g12 g23 g13)
+  double sigt[28];                  // ... and summed onto the tying points
+};
+// derivative tables and the strain-displacement tables of the Gauss point being contracted
+struct Tab9 {
   double Gt[Q9_NTY][Q9_LD];         // d(tying strain t) / d(dof)
+  double Gt1[Q9_NTY][Q9_LD];        // bilinear tying form with the state: Bil_t(q, 1_dof)
   double Dn[Q9_NN][Q9_LD];          // d(drill strain at node n) / d(dof)
   double B[Q9_KROWS][Q9_LD];        // B of the current Gauss point (rows 9..11, columns 54, 55 zero)
-  double CB[Q9_KROWS][Q9_LD];       // w det C B
+  double CB[Q9_KROWS][Q9_LD];       // w det C B (tangent) or w det C B1 (geometric stiffness)
 };
 
 // shape function tables of the element class (the same for every element: filled once per
@@ -225,7 +234,7 @@ A2DS_HD void q9_node(const CompData &c, Elem9 &E, int n) {
 
 // ---- tying point t: frame vectors and the tying strain of the state ---------------------------
 // TACSShellLinearModel::computeTyingStrain (TACSShellElementModel.h:33-77)
-A2DS_HD void q9_tying(Elem9 &E, const Shape9 &H, int t) {
+A2DS_HD void q9_tying(Elem9 &E, const Shape9 &H, int t, bool nonlinear = false) {
   const double *N = H.Nt[t], *Nx = H.Nxt[t], *Ne = H.Net[t];
   const int field = H.tfield[t];
   double Xxi[3], Xeta[3], n0[3], Uxi[3], Ueta[3], d0[3];
@@ -235,19 +244,29 @@ A2DS_HD void q9_tying(Elem9 &E, const Shape9 &H, int t) {
   q9_interp3(Nx, E.q, 6, Uxi);
   q9_interp3(Ne, E.q, 6, Ueta);
   q9_interp3(N, E.dr, 3, d0);
-  for (int k = 0; k < 3; k++) { E.tXxi[t][k] = Xxi[k]; E.tXeta[t][k] = Xeta[k]; E.tn0[t][k] = n0[k]; }
+  for (int k = 0; k < 3; k++) {
+    E.tXxi[t][k] = Xxi[k]; E.tXeta[t][k] = Xeta[k]; E.tn0[t][k] = n0[k];
+    E.tUxi[t][k] = Uxi[k]; E.tUeta[t][k] = Ueta[k]; E.td0[t][k] = d0[k];
+  }
   double e;
   if (field == 0) e = dot(Uxi, Xxi);
   else if (field == 1) e = dot(Ueta, Xeta);
   else if (field == 2) e = 0.5 * (dot(Uxi, Xeta) + dot(Ueta, Xxi));
   else if (field == 3) e = 0.5 * (dot(Xeta, d0) + dot(n0, Ueta));
   else e = 0.5 * (dot(Xxi, d0) + dot(n0, Uxi));
+  if (nonlinear) {   // + 1/2 Bil_t(q, q), TACSShellNonlinearModel::computeTyingStrain (:644-700)
+    if (field == 0) e += 0.5 * dot(Uxi, Uxi);
+    else if (field == 1) e += 0.5 * dot(Ueta, Ueta);
+    else if (field == 2) e += 0.5 * dot(Uxi, Ueta);
+    else if (field == 3) e += 0.5 * dot(d0, Ueta);
+    else e += 0.5 * dot(d0, Uxi);
+  }
   E.ety[t] = e;
 }
 
 // ---- Gauss point q: frame, Xd^-1 T, the through-thickness term, weight * det -------------------
 // TACSShellElement.h:514-534, TacsShellComputeDispGrad (TACSShellUtilities.h:369-393)
-A2DS_HD void q9_qp(const CompData &c, Elem9 &E, const Shape9 &H, int q) {
+A2DS_HD void q9_qp(const CompData &c, Elem9 &E, const Shape9 &H, int q, bool bil = true) {
   const double *N = H.Nq[q], *Nx = H.Nxq[q], *Ne = H.Neq[q];
   double Xxi[3], Xeta[3], n0[3], nxi[3], neta[3];
   q9_interp3(Nx, E.X, 3, Xxi);
@@ -277,6 +296,10 @@ A2DS_HD void q9_qp(const CompData &c, Elem9 &E, const Shape9 &H, int q) {
       E.qZ[q][3 * i + j] = -(P[3 * i] * A[j] + P[3 * i + 1] * A[3 + j] + P[3 * i + 2] * A[6 + j]);
     }
   E.qw[q] = det * (q9_wt3(q % 3) * q9_wt3(q / 3));
+  if (bil)
+  for (int k = 0; k < 3; k++)
+    for (int l = 0; l < 3; l++)
+      E.qP[q][3 * k + l] = T[3 * k] * T[3 * l] + T[3 * k + 1] * T[3 * l + 1] + T[3 * k + 2] * T[3 * l + 2];
 }
 
 // the 5 interpolated tying components (g11, g22, g12, g23, g13) at Gauss point q of a set of 28
@@ -322,8 +345,12 @@ A2DS_HD void q9_stress(const double Cs[22], const double e[9], double s[9]) {
 }
 
 // ---- Gauss point q: strains of the state and the weighted stresses ----------------------------
-// TACSShellElement::addResidual, TACSShellElement.h:314-373 (thermal: :549-574)
-A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, const Shape9 &H, int q, double thermal) {
+// TACSShellElement::addResidual, TACSShellElement.h:314-373 (thermal: :549-574); nonlinear
+// model: TACSShellNonlinearModel::evalStrain (TACSShellElementModel.h:1112-1130).  Also the
+// state's u0x / u1x columns and the stresses pulled back to the tying components, which the
+// bilinear strain terms (geometric stiffness, nonlinear tangent) use.
+A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, const Shape9 &H, int q, double thermal,
+                         bool nonlinear = false, bool bil = true) {
   const double *N = H.Nq[q], *Nx = H.Nxq[q], *Ne = H.Neq[q];
   double e[9], g[5];
   q9_interp_tying(q, E.ety, 1, g);
@@ -335,41 +362,98 @@ A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, const Shape9 &H, int q, do
   q9_interp3(Nx, E.dr, 3, d0xi);
   q9_interp3(Ne, E.dr, 3, d0eta);
   const double *T = E.qT[q], *A = E.qA[q], *Z = E.qZ[q];
-  double u1x[2][2];   // rows / columns 0, 1 of T^T (u1d A + u0d Z)
+  double u0x[3][2], u1x[3][2];   // columns 0, 1 of T^T (u0d A) and T^T (u1d A + u0d Z)
   for (int j = 0; j < 2; j++) {
-    double v[3];
-    for (int k = 0; k < 3; k++)
-      v[k] = d0xi[k] * A[j] + d0eta[k] * A[3 + j] + u0xi[k] * Z[j] + u0eta[k] * Z[3 + j] + d0[k] * Z[6 + j];
-    for (int i = 0; i < 2; i++) u1x[i][j] = T[i] * v[0] + T[3 + i] * v[1] + T[6 + i] * v[2];
+    double v0[3], v1[3];
+    for (int k = 0; k < 3; k++) {
+      v0[k] = u0xi[k] * A[j] + u0eta[k] * A[3 + j] + d0[k] * A[6 + j];
+      v1[k] = d0xi[k] * A[j] + d0eta[k] * A[3 + j] + u0xi[k] * Z[j] + u0eta[k] * Z[3 + j] + d0[k] * Z[6 + j];
+    }
+    for (int i = 0; i < 3; i++) {
+      u0x[i][j] = T[i] * v0[0] + T[3 + i] * v0[1] + T[6 + i] * v0[2];
+      u1x[i][j] = T[i] * v1[0] + T[3 + i] * v1[1] + T[6 + i] * v1[2];
+      if (bil) {
+        E.qU0[q][2 * i + j] = u0x[i][j];
+        E.qU1[q][2 * i + j] = u1x[i][j];
+      }
+    }
   }
   e[3] = u1x[0][0]; e[4] = u1x[1][1]; e[5] = u1x[0][1] + u1x[1][0];
+  if (nonlinear) {
+    for (int i = 0; i < 3; i++) {
+      e[3] += u0x[i][0] * u1x[i][0];
+      e[4] += u0x[i][1] * u1x[i][1];
+      e[5] += u0x[i][0] * u1x[i][1] + u1x[i][0] * u0x[i][1];
+    }
+  }
   double et = 0.0;
   for (int n = 0; n < 9; n++) et += N[n] * E.etn[n];
   e[8] = et;
   for (int k = 0; k < 9; k++) e[k] -= thermal * c.temperature * c.eth[k];
   double s[9];
   q9_stress(c.Cs, e, s);
-  for (int k = 0; k < 9; k++) E.sq[q][k] = E.qw[q] * s[k];
+  for (int k = 0; k < 9; k++) { s[k] *= E.qw[q]; E.sq[q][k] = s[k]; }
+  if (!bil) return;
+  // P = A Se A^T with Se = [[s0 s2 s7] [s2 s1 s6] [s7 s6 0]]: sum_i s_i e_i = sum P_mn gty_mn
+  const double Se[9] = {s[0], s[2], s[7], s[2], s[1], s[6], s[7], s[6], 0.0};
+  double W[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) W[3 * i + j] = A[3 * i] * Se[j] + A[3 * i + 1] * Se[3 + j] + A[3 * i + 2] * Se[6 + j];
+  auto P = [&](int m, int n) { return W[3 * m] * A[3 * n] + W[3 * m + 1] * A[3 * n + 1] + W[3 * m + 2] * A[3 * n + 2]; };
+  E.shat[q][0] = P(0, 0); E.shat[q][1] = P(1, 1); E.shat[q][2] = 2.0 * P(0, 1);
+  E.shat[q][3] = 2.0 * P(1, 2); E.shat[q][4] = 2.0 * P(0, 2);
+}
+
+// weight of tying point t in the interpolation at Gauss point q (transpose of q9_interp_tying)
+A2DS_HD double q9_ty_weight(int q, int t) {
+  const int a = q % 3, b = q / 3;
+  double ra[2], rb[2];
+  q9_red(q9_gauss3(a), ra);
+  q9_red(q9_gauss3(b), rb);
+  if (t < 6) return (t / 2 == b) ? ra[t % 2] : 0.0;
+  if (t < 12) { const int k = t - 6; return (k % 3 == a) ? rb[k / 3] : 0.0; }
+  if (t < 16) { const int k = t - 12; return ra[k % 2] * rb[k / 2]; }
+  if (t < 22) { const int k = t - 16; return (k % 3 == a) ? rb[k / 3] : 0.0; }
+  const int k = t - 22;
+  return (k / 2 == b) ? ra[k % 2] : 0.0;
+}
+// tying-level stress of tying point t: sum over the Gauss points of weight * pulled-back stress
+A2DS_HD void q9_sigt(Elem9 &E, const Shape9 &H, int t) {
+  const int field = H.tfield[t];
+  double s = 0.0;
+  for (int q = 0; q < 9; q++) s += q9_ty_weight(q, t) * E.shat[q][field];
+  E.sigt[t] = s;
 }
 
 // ---- table entries ----------------------------------------------------------------------------
-// Gt[t][dof] = d(tying strain t)/d(dof), dof = 6 m + k (k < 3 displacement, k >= 3 rotation)
-A2DS_HD double q9_gt(const Elem9 &E, const Shape9 &H, int t, int dof) {
+// d(tying strain t)/d(dof) for the frame (Fxi, Feta, Fn): with the geometry frame (X,xi  X,eta
+// n0) this is Gt, the linear tying rows; with the state's frame (u,xi  u,eta  d0) it is the
+// bilinear form Bil_t(q, 1_dof) of the nonlinear tying strains
+// (TACSShellNonlinearModel::computeTyingStrainDeriv, TACSShellElementModel.h:1033-1109) —
+// the two have the same structure.  dof = 6 m + k (k < 3 displacement, k >= 3 rotation)
+A2DS_HD double q9_gt_frame(const Elem9 &E, const Shape9 &H, const double (*Fxi)[3], const double (*Feta)[3],
+                           const double (*Fn)[3], int t, int dof) {
   const int field = H.tfield[t];
   const int m = dof / 6, k = dof % 6;
   const double N = H.Nt[t][m], Nx = H.Nxt[t][m], Ne = H.Net[t][m];
   if (k < 3) {
-    if (field == 0) return Nx * E.tXxi[t][k];
-    if (field == 1) return Ne * E.tXeta[t][k];
-    if (field == 2) return 0.5 * (Nx * E.tXeta[t][k] + Ne * E.tXxi[t][k]);
-    if (field == 3) return 0.5 * Ne * E.tn0[t][k];
-    return 0.5 * Nx * E.tn0[t][k];
+    if (field == 0) return Nx * Fxi[t][k];
+    if (field == 1) return Ne * Feta[t][k];
+    if (field == 2) return 0.5 * (Nx * Feta[t][k] + Ne * Fxi[t][k]);
+    if (field == 3) return 0.5 * Ne * Fn[t][k];
+    return 0.5 * Nx * Fn[t][k];
   }
   if (field < 3) return 0.0;
   // X,a . (theta x fn) = theta . (fn x X,a)
-  const double *v = field == 3 ? E.tXeta[t] : E.tXxi[t], *f = &E.fn[3 * m];
+  const double *v = field == 3 ? Feta[t] : Fxi[t], *f = &E.fn[3 * m];
   const int c = k - 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
   return 0.5 * N * (f[c1] * v[c2] - f[c2] * v[c1]);
+}
+A2DS_HD double q9_gt(const Elem9 &E, const Shape9 &H, int t, int dof) {
+  return q9_gt_frame(E, H, E.tXxi, E.tXeta, E.tn0, t, dof);
+}
+A2DS_HD double q9_gt1(const Elem9 &E, const Shape9 &H, int t, int dof) {
+  return q9_gt_frame(E, H, E.tUxi, E.tUeta, E.td0, t, dof);
 }
 // Dn[n][dof] = d(drill strain at node n)/d(dof)
 A2DS_HD double q9_dn(const Elem9 &E, const Shape9 &H, int n, int dof) {
@@ -378,36 +462,128 @@ A2DS_HD double q9_dn(const Elem9 &E, const Shape9 &H, int n, int dof) {
   return H.Nxn[n][m] * E.a1[3 * n + k] + H.Nen[n][m] * E.a2[3 * n + k];
 }
 
-// ---- column `dof` of B at Gauss point q (9 strain rows) ----------------------------------------
-A2DS_HD void q9_bcol(const Elem9 &E, const Shape9 &H, int q, int dof, double Bk[9]) {
+// ---- column `dof` at Gauss point q: Bk = d(strain)/d(dof) of the linear model (9 rows) and,
+// when B1k is given, B1k = Bil(q, 1_dof), the state-dependent part of the nonlinear model's B
+// (evalStrainDeriv, TACSShellElementModel.h:1172-1211; its drill row is zero) ---------------------
+// The unit fields of a dof are rank one: u0x(1_dof)_ij = v_i alpha_j, u1x(1_dof)_ij = v_i beta_j
+// with v_i = t_i[k] (displacement) or t_i . (e_c x fn_m) (rotation).
+A2DS_HD void q9_bcol(const Elem9 &E, const Tab9 &Tb, const Shape9 &H, int q, int dof, double Bk[9],
+                     double *B1k = nullptr) {
   const int m = dof / 6, k = dof % 6;
   const double N = H.Nq[q][m], Nx = H.Nxq[q][m], Ne = H.Neq[q][m];
   double g[5];
-  q9_interp_tying(q, &E.Gt[0][dof], Q9_LD, g);
+  q9_interp_tying(q, &Tb.Gt[0][dof], Q9_LD, g);
   q9_membrane_shear(E.qA[q], g, Bk);
   const double *T = E.qT[q], *A = E.qA[q], *Z = E.qZ[q];
-  // u1x_ij = t_i . (u1d a_j + u0d z_j): displacement dofs enter through u0d = [u,xi | u,eta | d],
-  // rotation dofs through the director d_m = theta_m x fn_m in u0d and u1d = [d,xi | d,eta | 0]
-  double w0, w1, v0, v1;   // coefficient of column j = 0, 1 and the vector component dotted with t_i
+  double al0, al1, be0, be1, v[3];
   if (k < 3) {
-    w0 = Nx * Z[0] + Ne * Z[3];
-    w1 = Nx * Z[1] + Ne * Z[4];
-    v0 = T[3 * k]; v1 = T[3 * k + 1];         // t_0[k], t_1[k]
+    al0 = Nx * A[0] + Ne * A[3];
+    al1 = Nx * A[1] + Ne * A[4];
+    be0 = Nx * Z[0] + Ne * Z[3];
+    be1 = Nx * Z[1] + Ne * Z[4];
+    v[0] = T[3 * k]; v[1] = T[3 * k + 1]; v[2] = T[3 * k + 2];
   } else {
-    w0 = Nx * A[0] + Ne * A[3] + N * Z[6];
-    w1 = Nx * A[1] + Ne * A[4] + N * Z[7];
+    al0 = N * A[6];
+    al1 = N * A[7];
+    be0 = Nx * A[0] + Ne * A[3] + N * Z[6];
+    be1 = Nx * A[1] + Ne * A[4] + N * Z[7];
     const double *f = &E.fn[3 * m];
     const int c = k - 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
     // t_i . (theta x fn) = theta . (fn x t_i)
-    v0 = f[c1] * T[3 * c2] - f[c2] * T[3 * c1];
-    v1 = f[c1] * T[3 * c2 + 1] - f[c2] * T[3 * c1 + 1];
+    for (int i = 0; i < 3; i++) v[i] = f[c1] * T[3 * c2 + i] - f[c2] * T[3 * c1 + i];
   }
-  Bk[3] = w0 * v0;
-  Bk[4] = w1 * v1;
-  Bk[5] = w1 * v0 + w0 * v1;
+  Bk[3] = be0 * v[0];
+  Bk[4] = be1 * v[1];
+  Bk[5] = be1 * v[0] + be0 * v[1];
   double d = 0.0;
-  for (int n = 0; n < 9; n++) d += H.Nq[q][n] * E.Dn[n][dof];
+  for (int n = 0; n < 9; n++) d += H.Nq[q][n] * Tb.Dn[n][dof];
   Bk[8] = d;
+  if (B1k) {
+    q9_interp_tying(q, &Tb.Gt1[0][dof], Q9_LD, g);
+    q9_membrane_shear(E.qA[q], g, B1k);
+    const double *U0 = E.qU0[q], *U1 = E.qU1[q];
+    double p0 = 0.0, p1 = 0.0, r0 = 0.0, r1 = 0.0;
+    for (int i = 0; i < 3; i++) {
+      p0 += v[i] * U0[2 * i]; p1 += v[i] * U0[2 * i + 1];
+      r0 += v[i] * U1[2 * i]; r1 += v[i] * U1[2 * i + 1];
+    }
+    B1k[3] = al0 * r0 + be0 * p0;
+    B1k[4] = al1 * r1 + be1 * p1;
+    B1k[5] = al0 * r1 + be0 * p1 + be1 * p0 + al1 * r0;
+    B1k[8] = 0.0;
+  }
+}
+
+// ---- geometric term of node pair (ma, mb): sum_i s_i d2(e_i)/d(dof_a) d(dof_b) ------------------
+// (the second derivatives of the nonlinear strains, TACSShellElementModel.h:1033-1109, 1172-1211,
+// contracted with the weighted stresses E.sq).  With the rank-one unit fields of q9_bcol every
+// bilinear form is a scalar times v_a . v_b, and v_a . v_b is an entry of P = T T^T
+// (displacement dofs) or of P applied to the director derivatives d_c = e_c x fn (rotation dofs);
+// the tying forms use Cartesian dot products directly (P = I).  So the 6 x 6 block is
+//   [ M_uu         M_ut D_b       ]      M_hh' = sum_q coef_q(h, h') P_q + (tying part) I,
+//   [ D_a^T M_tu   D_a^T M_tt D_b ]      D[k][c] = (e_c x fn)[k]
+// One work item = one 3 x 3 quadrant (ha, hb) of the block: out[9] row major, rows = the
+// three dofs of kind ha (0 displacement, 1 rotation) of node ma.
+A2DS_HD void q9_geo_quadrant(const Elem9 &E, const Shape9 &H, int ma, int mb, int ha, int hb, double out[9]) {
+  double M[9];
+  for (int k = 0; k < 9; k++) M[k] = 0.0;
+  // tying part: g11, g22, g12 couple displacements; g23, g13 couple a rotation with a displacement
+  if (!(ha == 1 && hb == 1)) {
+    double c = 0.0;
+    for (int t = 0; t < Q9_NTY; t++) {
+      const int field = H.tfield[t];
+      const double s = E.sigt[t];
+      if (ha == 0 && hb == 0) {
+        if (field == 0) c += s * H.Nxt[t][ma] * H.Nxt[t][mb];
+        else if (field == 1) c += s * H.Net[t][ma] * H.Net[t][mb];
+        else if (field == 2) c += s * 0.5 * (H.Nxt[t][ma] * H.Net[t][mb] + H.Net[t][ma] * H.Nxt[t][mb]);
+      } else {
+        // the rotation node carries N, the displacement node the derivative
+        const int mr = ha == 1 ? ma : mb, md = ha == 1 ? mb : ma;
+        if (field == 3) c += s * 0.5 * H.Nt[t][mr] * H.Net[t][md];
+        else if (field == 4) c += s * 0.5 * H.Nt[t][mr] * H.Nxt[t][md];
+      }
+    }
+    M[0] = M[4] = M[8] = c;
+  }
+  // bending part
+  for (int q = 0; q < 9; q++) {
+    const double *A = E.qA[q], *Z = E.qZ[q], *P = E.qP[q];
+    const double s3 = E.sq[q][3], s4 = E.sq[q][4], s5 = E.sq[q][5];
+    const double Na = H.Nq[q][ma], Nxa = H.Nxq[q][ma], Nea = H.Neq[q][ma];
+    const double Nb = H.Nq[q][mb], Nxb = H.Nxq[q][mb], Neb = H.Neq[q][mb];
+    const double ua0 = Nxa * A[0] + Nea * A[3], ua1 = Nxa * A[1] + Nea * A[4];
+    const double ub0 = Nxb * A[0] + Neb * A[3], ub1 = Nxb * A[1] + Neb * A[4];
+    double ala0, ala1, bea0, bea1, alb0, alb1, beb0, beb1;
+    if (ha == 0) { ala0 = ua0; ala1 = ua1; bea0 = Nxa * Z[0] + Nea * Z[3]; bea1 = Nxa * Z[1] + Nea * Z[4]; }
+    else { ala0 = Na * A[6]; ala1 = Na * A[7]; bea0 = ua0 + Na * Z[6]; bea1 = ua1 + Na * Z[7]; }
+    if (hb == 0) { alb0 = ub0; alb1 = ub1; beb0 = Nxb * Z[0] + Neb * Z[3]; beb1 = Nxb * Z[1] + Neb * Z[4]; }
+    else { alb0 = Nb * A[6]; alb1 = Nb * A[7]; beb0 = ub0 + Nb * Z[6]; beb1 = ub1 + Nb * Z[7]; }
+    const double cf = s3 * (ala0 * beb0 + alb0 * bea0) + s4 * (ala1 * beb1 + alb1 * bea1) +
+                      s5 * (alb0 * bea1 + beb0 * ala1 + ala0 * beb1 + bea0 * alb1);
+    for (int k = 0; k < 9; k++) M[k] += cf * P[k];
+  }
+  // D[k][c] = (e_c x f)[k] = eps_{k c l} f_l
+  const double *fa = &E.fn[3 * ma], *fb = &E.fn[3 * mb];
+  const double Da[9] = {0.0, fa[2], -fa[1], -fa[2], 0.0, fa[0], fa[1], -fa[0], 0.0};
+  const double Db[9] = {0.0, fb[2], -fb[1], -fb[2], 0.0, fb[0], fb[1], -fb[0], 0.0};
+  double R[9];   // M D_b for a rotation column kind, else M
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      R[3 * i + j] = hb == 1 ? M[3 * i] * Db[j] + M[3 * i + 1] * Db[3 + j] + M[3 * i + 2] * Db[6 + j] : M[3 * i + j];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      out[3 * i + j] = ha == 1 ? Da[i] * R[j] + Da[3 + i] * R[3 + j] + Da[6 + i] * R[6 + j] : R[3 * i + j];
+}
+// the whole 6 x 6 block (host emulation): blk[36] row major, rows = dofs of node ma
+A2DS_HD void q9_geo_pair(const Elem9 &E, const Shape9 &H, int ma, int mb, double blk[36]) {
+  for (int ha = 0; ha < 2; ha++)
+    for (int hb = 0; hb < 2; hb++) {
+      double o[9];
+      q9_geo_quadrant(E, H, ma, mb, ha, hb, o);
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) blk[6 * (3 * ha + i) + 3 * hb + j] = o[3 * i + j];
+    }
 }
 
 }  // namespace a2ds

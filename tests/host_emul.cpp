@@ -232,47 +232,75 @@ extern "C" int emul_element_t(const double *Cs, const double *eth, double temper
 
 extern "C" int emul_element9(const double *Cs, const double *eth, double temperature, int transform,
                              const double *axis, const double *X, const double *q, double *res,
-                             double *K) {
+                             double *K, int model, double *G) {
   CompData c;
   memset(&c, 0, sizeof(c));
   memcpy(c.Cs, Cs, sizeof(c.Cs));
   memcpy(c.eth, eth, sizeof(c.eth));
   c.temperature = temperature;
   c.transform = transform;
+  c.model = model;
   memcpy(c.axis, axis, sizeof(c.axis));
+  const bool nl = model == 1;
   static Elem9 E;
+  static Tab9 Tb;
   memset(&E, 0, sizeof(E));
+  memset(&Tb, 0, sizeof(Tb));
   memcpy(E.X, X, sizeof(E.X));
   memcpy(E.q, q, sizeof(E.q));
   static Shape9 H;
   for (int pnt = 0; pnt < 46; pnt++) q9_shape_tables(H, pnt);
   for (int n = 0; n < 9; n++) q9_node(c, E, n);
-  for (int t = 0; t < 28; t++) q9_tying(E, H, t);
+  for (int t = 0; t < 28; t++) q9_tying(E, H, t, nl);
   for (int qp = 0; qp < 9; qp++) q9_qp(c, E, H, qp);
+  for (int qp = 0; qp < 9; qp++) q9_qp_state(c, E, H, qp, 1.0, nl);
+  for (int t = 0; t < 28; t++) q9_sigt(E, H, t);
   for (int t = 0; t < 28; t++)
-    for (int d = 0; d < 54; d++) E.Gt[t][d] = q9_gt(E, H, t, d);
+    for (int d = 0; d < 54; d++) { Tb.Gt[t][d] = q9_gt(E, H, t, d); Tb.Gt1[t][d] = q9_gt1(E, H, t, d); }
   for (int n = 0; n < 9; n++)
-    for (int d = 0; d < 54; d++) E.Dn[n][d] = q9_dn(E, H, n, d);
-  for (int qp = 0; qp < 9; qp++) q9_qp_state(c, E, H, qp, 1.0);
+    for (int d = 0; d < 54; d++) Tb.Dn[n][d] = q9_dn(E, H, n, d);
   memset(res, 0, 54 * sizeof(double));
   memset(K, 0, 54 * 54 * sizeof(double));
+  if (G) memset(G, 0, 54 * 54 * sizeof(double));
+  static double B1[12][56], CB1[12][56];
   for (int qp = 0; qp < 9; qp++) {
     for (int d = 0; d < 54; d++) {
-      double Bk[9], Sk[9];
-      q9_bcol(E, H, qp, d, Bk);
+      double Bk[9], B1k[9], Sk[9];
+      q9_bcol(E, Tb, H, qp, d, Bk, B1k);
+      if (nl)
+        for (int k = 0; k < 9; k++) Bk[k] += B1k[k];
       q9_stress(c.Cs, Bk, Sk);
-      for (int k = 0; k < 9; k++) { E.B[k][d] = Bk[k]; E.CB[k][d] = E.qw[qp] * Sk[k]; }
+      for (int k = 0; k < 9; k++) { Tb.B[k][d] = Bk[k]; Tb.CB[k][d] = E.qw[qp] * Sk[k]; }
+      q9_stress(c.Cs, B1k, Sk);
+      for (int k = 0; k < 9; k++) { B1[k][d] = B1k[k]; CB1[k][d] = E.qw[qp] * Sk[k]; }
     }
     for (int a = 0; a < 54; a++) {
       double r = 0.0;
-      for (int k = 0; k < 9; k++) r += E.B[k][a] * E.sq[qp][k];
+      for (int k = 0; k < 9; k++) r += Tb.B[k][a] * E.sq[qp][k];
       res[a] += r;
       for (int b = 0; b < 54; b++) {
-        double s = 0.0;
-        for (int k = 0; k < 9; k++) s += E.B[k][a] * E.CB[k][b];
+        double s = 0.0, z = 0.0;
+        for (int k = 0; k < 9; k++) {
+          s += Tb.B[k][a] * Tb.CB[k][b];
+          z += Tb.B[k][a] * CB1[k][b] + CB1[k][a] * Tb.B[k][b];
+        }
         K[54 * a + b] += s;
+        if (G) G[54 * a + b] += z;
       }
     }
   }
+  // geometric term of the node pairs: the whole of it for G (stresses of the linear model),
+  // added to the tangent of the nonlinear model
+  if (G || nl)
+    for (int ma = 0; ma < 9; ma++)
+      for (int mb = 0; mb < 9; mb++) {
+        double blk[36];
+        q9_geo_pair(E, H, ma, mb, blk);
+        for (int i = 0; i < 6; i++)
+          for (int j = 0; j < 6; j++) {
+            if (G) G[54 * (6 * ma + i) + 6 * mb + j] += blk[6 * i + j];
+            if (nl) K[54 * (6 * ma + i) + 6 * mb + j] += blk[6 * i + j];
+          }
+      }
   return 0;
 }

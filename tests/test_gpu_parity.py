@@ -843,37 +843,47 @@ def test_device_built_pattern_is_bit_identical(a2ds, orc):
 
 
 # ---- 9-node shells (TACSQuad9Shell): k_assemble9 against the order-3 oracle ---------------------
+@pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("transform", [0, 1])
 @pytest.mark.parametrize("T,t_offset", [(0.0, 0.0), (10.0, 0.3)])
-def test_quad9_element_level_vs_oracle(a2ds, orc, transform, T, t_offset):
+def test_quad9_element_level_vs_oracle(a2ds, orc, kind, transform, T, t_offset):
     from helpers import random_elements9
     n = 48
-    X, q = random_elements9(n, seed=300 + transform)
+    X, q = random_elements9(n, seed=300 + transform + 10 * kind)
     Cs, eth = a2ds.iso_shell_tables(t_offset=t_offset)
     axis = np.array([0.3, 1.0, 0.2])
     conn = np.arange(9 * n, dtype=np.int32).reshape(n, 9)   # every element has its own 9 nodes
     asm = a2ds.Assembler(0)
     asm.set_mesh(conn, 9 * n, order=3)
     asm.set_nodes(X.reshape(-1, 3))
-    asm.set_components(Cs[None], eth[None], temperature=[T], elem_class=[0], transform=transform,
+    asm.set_components(Cs[None], eth[None], temperature=[T], elem_class=[kind], transform=transform,
                        ref_axis=axis)
     asm.set_state(q.reshape(-1, 6))
-    kmat = asm.create_mat()
+    kmat = asm.create_mat(); gmat = asm.create_mat()
     rowp, cols = asm.mat_pattern(kmat)
     res = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
     K = asm.mat_values(kmat)
-    comp = orc.make_comp(0, Cs, eth, (0, 0, 0), T, transform, axis)
-    worst = [0.0, 0.0]
-    for e in range(n):
-        r_o, k_o = orc.jacobian(comp, X[e].ravel(), q[e].ravel(), order=3)
-        worst[0] = max(worst[0], relmax(res[conn[e]].ravel(), r_o))
-        blocks = np.zeros((54, 54))
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gmat)
+    G = asm.mat_values(gmat)
+    comp = orc.make_comp(kind, Cs, eth, (0, 0, 0), T, transform, axis)
+
+    def blocks_of(A, e):
+        out = np.zeros((54, 54))
         for i in range(9):
             for j in range(9):
                 kk = rowp[conn[e, i]] + int(np.searchsorted(cols[rowp[conn[e, i]]:rowp[conn[e, i] + 1]], conn[e, j]))
-                blocks[6 * i:6 * i + 6, 6 * j:6 * j + 6] = K[kk]
-        worst[1] = max(worst[1], relmax(blocks, k_o))
+                out[6 * i:6 * i + 6, 6 * j:6 * j + 6] = A[kk]
+        return out
+    worst = [0.0, 0.0, 0.0]
+    for e in range(n):
+        r_o, k_o = orc.jacobian(comp, X[e].ravel(), q[e].ravel(), order=3)
+        worst[0] = max(worst[0], relmax(res[conn[e]].ravel(), r_o))
+        worst[1] = max(worst[1], relmax(blocks_of(K, e), k_o))
+        if not (kind == 1 and T != 0.0):   # nonlinear class + temperature: reference quirk, see the oracle
+            g_o = orc.mat_type(comp, 1, X[e].ravel(), q[e].ravel(), order=3)
+            worst[2] = max(worst[2], relmax(blocks_of(G, e), g_o))
     assert worst[0] < RES_TOL and worst[1] < MAT_TOL, worst
+    assert worst[2] < (THERMAL_G_TOL if T != 0.0 else MAT_TOL), worst
     asm.close()
 
 
@@ -915,10 +925,19 @@ def test_quad9_assembly_vs_oracle(a2ds, orc, name):
     _, k25_o = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals, alpha=2.5,
                             order=3)
     assert relmax(asm.mat_values(kmat), k25_o) < MAT_TOL
-    # the entry points 9-node meshes do not provide fail loudly
+    # geometric stiffness, alone and in the fused call (one launch per output group)
     gmat = asm.create_mat()
+    _, g_o = orc.assemble(3, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals, order=3)
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gmat)
+    assert relmax(asm.mat_values(gmat), g_o) < MAT_TOL
+    r = asm.assembleAll(kmat, gmat)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL
+    assert relmax(asm.mat_values(gmat), g_o) < MAT_TOL
+    G = asm.mat_values(gmat)
+    # the entry points 9-node meshes do not provide fail loudly
     with pytest.raises(RuntimeError):
-        asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gmat)
+        asm.assembleMatType(a2ds.MASS_MATRIX, gmat)
     with pytest.raises(RuntimeError):
-        asm.assembleAll(kmat, gmat)
+        asm.assembleJacobian(1.0, 0.0, 2.0, kmat)
     asm.close()

@@ -147,10 +147,20 @@ def test_quad9_kernel_math_against_golden(emul, tr, ci):
     ax = g["axis"] / np.linalg.norm(g["axis"])
     for e in range(g["X"].shape[0]):
         res = np.zeros(54); K = np.zeros(54 * 54)
+        G = np.zeros(54 * 54)
         emul.emul_element9(p(g[key + "_Cs"]), p(g[key + "_eth"]), C.c_double(T), C.c_int(tr), p(ax),
-                           p(g["X"][e]), p(g["q"][e]), p(res), p(K))
+                           p(g["X"][e]), p(g["q"][e]), p(res), p(K), C.c_int(0), p(G))
         assert relmax(res, g[key + "_res"][e]) < 1e-12
         assert relmax(K.reshape(54, 54), g[key + "_K"][e]) < 1e-10
+        # geometric stiffness: analytic here, a central difference in the reference (noise 1e-12
+        # without, ~1e-7 with a temperature)
+        assert relmax(G.reshape(54, 54), g[key + "_G"][e]) < (1e-10 if T == 0.0 else 1e-6)
+        # nonlinear strain model (TACSQuad9NonlinearShell): residual and tangent about the state
+        keyn = f"k1_t{tr}_c{ci}"
+        emul.emul_element9(p(g[keyn + "_Cs"]), p(g[keyn + "_eth"]), C.c_double(T), C.c_int(tr), p(ax),
+                           p(g["X"][e]), p(g["q"][e]), p(res), p(K), C.c_int(1), None)
+        assert relmax(res, g[keyn + "_res"][e]) < 1e-12
+        assert relmax(K.reshape(54, 54), g[keyn + "_K"][e]) < 1e-10
 
 
 def test_quad9_kernel_math_against_oracle_many(emul, orc, a2ds):
@@ -167,7 +177,7 @@ def test_quad9_kernel_math_against_oracle_many(emul, orc, a2ds):
             for e in range(len(X)):
                 res = np.zeros(54); K = np.zeros(54 * 54)
                 emul.emul_element9(p(Cs), p(eth), C.c_double(T), C.c_int(tr), p(ax), p(X[e]), p(q[e]),
-                                   p(res), p(K))
+                                   p(res), p(K), C.c_int(0), None)
                 r_o, k_o = orc.jacobian(comp, X[e].ravel(), q[e].ravel(), order=3)
                 worst[0] = max(worst[0], relmax(res, r_o))
                 worst[1] = max(worst[1], relmax(K.reshape(54, 54), k_o))

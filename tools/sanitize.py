@@ -69,11 +69,14 @@ asm.close()
 asm = a2ds.Assembler(0)
 conn9, X9, bc9 = a2ds.meshes.plate9(7, 5, bump=2e-2)
 n9 = len(X9)
-asm.set_mesh(conn9, n9, order=3); asm.set_nodes(X9)
-asm.set_components(Cs2[None], eth2[None], temperature=[4.0]); asm.set_bcs(bc9, 63)
+ec9 = (np.arange(len(conn9)) % 2).astype(np.int32)   # linear and nonlinear class in one mesh
+asm.set_mesh(conn9, n9, elem_comp=ec9, order=3); asm.set_nodes(X9)
+asm.set_components(np.stack([Cs2, Cs2]), np.stack([eth2, eth2]), temperature=[4.0, 4.0], elem_class=[0, 1])
+asm.set_bcs(bc9, 63)
 asm.set_state(a2ds.meshes.seeded_state(np.arange(n9), 1e-4))
-k9 = asm.create_mat()
+k9, g9 = asm.create_mat(), asm.create_mat()
 r9 = asm.assembleJacobian(1.0, 0.0, 0.0, k9); asm.assembleRes(); asm.assembleMatType(0, k9)
-print("quad9", float(np.abs(r9).max()), float(np.abs(asm.mat_values(k9)).max()))
+asm.assembleMatType(1, g9); asm.assembleAll(k9, g9)
+print("quad9", float(np.abs(r9).max()), float(np.abs(asm.mat_values(k9)).max()), float(np.abs(asm.mat_values(g9)).max()))
 asm.close()
 print("SANITIZE_DRIVER_DONE")
