@@ -125,6 +125,19 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
     Tab9 &Tb = S.T;
     auto Bq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? Tb.B : S.B2[qq - 1]; };
     auto CBq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? Tb.CB : S.CB2[qq - 1]; };
+    if (KMAT || GMAT) {
+      // the previous element's matrix went out through the B / CB tables: their padding (rows
+      // 9..11, columns 54, 55), which the contraction reads, has to be zero again
+      double *tab = &Tb.B[0][0];   // T.B, T.CB, B2, CB2: 2 * Q9_QB tables of Q9_KROWS x Q9_LD
+      const int per = (Q9_KROWS - 9) * Q9_LD + 9 * (Q9_LD - Q9_NV);
+      for (int i = tid; i < 2 * Q9_QB * per; i += Q9_CONSUMERS) {
+        const int t = i / per, k = i - per * t;
+        const int at = k < (Q9_KROWS - 9) * Q9_LD ? 9 * Q9_LD + k
+                                                  : Q9_LD * ((k - (Q9_KROWS - 9) * Q9_LD) / (Q9_LD - Q9_NV)) + Q9_NV +
+                                                        (k - (Q9_KROWS - 9) * Q9_LD) % (Q9_LD - Q9_NV);
+        tab[Q9_KROWS * Q9_LD * t + at] = 0.0;
+      }
+    }
     for (int i = tid; i < Q9_NTY * Q9_NV; i += Q9_CONSUMERS) {
       Tb.Gt[i / Q9_NV][i % Q9_NV] = q9_gt(E, H, i / Q9_NV, i % Q9_NV);
       if (BIL) Tb.Gt1[i / Q9_NV][i % Q9_NV] = q9_gt1(E, H, i / Q9_NV, i % Q9_NV);

@@ -40,7 +40,7 @@ struct Shim {
   a2ds_ctx *ctx = nullptr;
   std::map<TACSMat *, int> mats;
   std::vector<TACSElement *> comp_elems;  // one record per distinct element object
-  int n_nodes = 0;
+  int n_nodes = 0, npe = 4;
   std::vector<double> comp_key;   // component tables as last uploaded
   std::vector<double> x_key;      // node coordinates as last uploaded (setNodes after set-up)
 };
@@ -95,18 +95,26 @@ static void shim_upload_components(TACSAssembler *self, Shim &S, bool first) {
       }
       elem_comp[i] = it->second;
     }
-    // connectivity in the assembler's own (local == global on one rank) numbering
-    std::vector<int> conn(4 * (size_t)ne);
+    // connectivity in the assembler's own (local == global on one rank) numbering: a mesh of
+    // 4-node shells or a mesh of 9-node shells (TACSQuad9Shell / TACSQuad9NonlinearShell)
+    const int npe = ne > 0 ? self->elementNodeIndex[1] - self->elementNodeIndex[0] : 4;
+    if (npe != 4 && npe != 9) {
+      fprintf(stderr, "[a2ds shim] %d-node elements are not supported (4- or 9-node shells)\n", npe);
+      abort();
+    }
+    std::vector<int> conn(npe * (size_t)ne);
     for (int i = 0; i < ne; i++) {
       const int start = self->elementNodeIndex[i];
-      if (self->elementNodeIndex[i + 1] - start != 4) {
-        fprintf(stderr, "[a2ds shim] element %d is not a 4-node shell\n", i);
+      if (self->elementNodeIndex[i + 1] - start != npe) {
+        fprintf(stderr, "[a2ds shim] element %d is not a %d-node shell (mixed meshes are not supported)\n", i, npe);
         abort();
       }
-      for (int k = 0; k < 4; k++) conn[4 * i + k] = self->elementTacsNodes[start + k];
+      for (int k = 0; k < npe; k++) conn[npe * (size_t)i + k] = self->elementTacsNodes[start + k];
     }
     S.n_nodes = self->numNodes;
-    CK(a2ds_set_mesh(S.ctx, S.n_nodes, self->numOwnedNodes, ne, conn.data(), elem_comp.data()));
+    S.npe = npe;
+    CK(a2ds_set_mesh_order(S.ctx, npe == 9 ? 3 : 2, S.n_nodes, self->numOwnedNodes, ne, conn.data(),
+                           elem_comp.data()));
     const int *nodes, *vars;
     TacsScalar *vals;
     int nbc = self->bcMap->getBCs(&nodes, &vars, &vals);
@@ -130,13 +138,22 @@ static void shim_upload_components(TACSAssembler *self, Shim &S, bool first) {
   double axis[3] = {1.0, 0.0, 0.0};
   for (int i = 0; i < nc; i++) {
     TACSElement *e = S.comp_elems[i];
-    if (!fill_component<TACSQuad4Shell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i], &cls[i],
-                                        A2DS_QUAD4_SHELL, &transform, axis) &&
-        !fill_component<TACSQuad4NonlinearShell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i],
-                                                 &cls[i], A2DS_QUAD4_NONLINEAR_SHELL, &transform,
-                                                 axis)) {
+    // element class value = strain model (0 linear, 1 nonlinear); the node count comes with the mesh
+    const bool ok =
+        S.npe == 9
+            ? (fill_component<TACSQuad9Shell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i], &cls[i],
+                                              A2DS_QUAD4_SHELL, &transform, axis) ||
+               fill_component<TACSQuad9NonlinearShell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i],
+                                                       &cls[i], A2DS_QUAD4_NONLINEAR_SHELL, &transform, axis))
+            : (fill_component<TACSQuad4Shell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i], &cls[i],
+                                              A2DS_QUAD4_SHELL, &transform, axis) ||
+               fill_component<TACSQuad4NonlinearShell>(e, &Cs[22 * i], &eth[9 * i], &mom[3 * i], &T[i],
+                                                       &cls[i], A2DS_QUAD4_NONLINEAR_SHELL, &transform,
+                                                       axis));
+    if (!ok) {
       fprintf(stderr, "[a2ds shim] element class %s is not supported on the device path "
-                      "(TACSQuad4Shell / TACSQuad4NonlinearShell only); there is no CPU fallback\n",
+                      "(TACSQuad4Shell / TACSQuad4NonlinearShell / TACSQuad9Shell / "
+                      "TACSQuad9NonlinearShell); there is no CPU fallback\n",
               e->getObjectName());
       abort();
     }

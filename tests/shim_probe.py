@@ -13,6 +13,51 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import refdrv  # noqa: E402
 
 a2ds_meshes = importlib.import_module("a2d-shells_b200.meshes")
+if len(sys.argv) > 1 and sys.argv[1] == "quad9":
+    # the same flow with 9-node shells (TACSQuad9Shell): buckling (K and G through
+    # assembleMatType) and one Jacobian assembly; no mass terms for this element on the device
+    conn, X, ends = a2ds_meshes.cylinder9(20, 10)
+    nt = 40
+    bc_vars = [[0, 1, 2, 5]] * len(ends)
+    bc_vals = [[-1e-3 if i >= nt else 0.0, 0.0, 0.0, 0.0] for i in range(len(ends))]
+    ra = refdrv.RefAssembler(conn, X, np.zeros(len(conn), dtype=np.int32), refdrv.iso_props(kind=2)[None],
+                             ends, bc_vars, bc_vals, nodes_per_elem=9)
+    km, gm, am = ra.mat_create(1), ra.mat_create(1), ra.mat_create(1)
+    u = np.zeros((len(X), 6)); u[ra.new_nodes] = a2ds_meshes.seeded_state(np.arange(len(X)), 1e-3)
+    ra.set_state(u)
+    # K and G into the TACSSchurMat blocks at a fixed state (weighted checksums over all four blocks)
+    chk = {}
+    for typ, mat, tag in ((0, km, "k"), (1, gm, "g")):
+        ra.assemble_mat_type(typ, mat)
+        tot, mx = 0.0, 0.0
+        for which in range(4):
+            blk = ra.mat_block(mat, which)
+            if blk is None or blk["A"].size == 0:
+                continue
+            Ab = blk["A"]
+            tot += float((Ab * np.cos(np.arange(Ab.size) + which).reshape(Ab.shape)).sum())
+            mx = max(mx, float(np.abs(Ab).max()))
+        chk[tag + "_chk"] = tot; chk[tag + "_max"] = mx
+    # shift below the lowest eigenvalue: with a shift inside the cluster at 11.7 .. 12 the
+    # shifted operator is nearly singular and the Lanczos result moves with the last bit of G
+    eig, err = ra.buckling(km, gm, am, 0, sigma=10.0, num_eigs=50, max_lanczos=100, u0=None)
+    path = ra.path.copy()
+    chk["path_chk"] = float((path * np.cos(np.arange(path.size)).reshape(path.shape)).sum())
+    chk["path_max"] = float(np.abs(path).max())
+    gblk = ra.mat_block(gm, 0)["A"]
+    chk["gpath_chk"] = float((gblk * np.cos(np.arange(gblk.size)).reshape(gblk.shape)).sum())
+    chk["gpath_max"] = float(np.abs(gblk).max())
+    pm = ra.mat_create(0)
+    u = np.zeros((len(X), 6)); u[ra.new_nodes] = a2ds_meshes.seeded_state(np.arange(len(X)), 1e-5)
+    ra.set_state(u)
+    r = ra.assemble_jacobian(pm)
+    A = ra.mat_block(pm, 0)["A"]
+    w = np.cos(np.arange(A.size)).reshape(A.shape)
+    print("SHIM_PROBE " + json.dumps(dict(eig=eig[:6].tolist(), err=err[:6].tolist(), **chk,
+                                         res_norm=float(np.abs(r).max()), res_sum=float(r.sum()),
+                                         a_max=float(np.abs(A).max()), a_sum=float(A.sum()),
+                                         a_chk=float((A * w).sum()))))
+    sys.exit(0)
 conn, X, ends = a2ds_meshes.cylinder(40, 20)
 bc_vars = [[0, 1, 2, 5]] * len(ends)
 bc_vals = [[-1e-3 if i >= 40 else 0.0, 0.0, 0.0, 0.0] for i in range(len(ends))]

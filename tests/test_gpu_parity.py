@@ -197,22 +197,29 @@ def test_streamed_assembly_vs_oracle(a2ds, orc, name, chunks, monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["plate", "cylinder"])
-def test_assembly_vs_reference_schur_and_parallel(a2ds, ref, name):
+@pytest.mark.parametrize("order", [2, 3])
+def test_assembly_vs_reference_schur_and_parallel(a2ds, ref, name, order):
     """drop-in style: connectivity, nodes, BCs and BOTH matrix patterns are taken from the
-    reference assembler; values must match block for block."""
-    conn, X, bcn = _mesh_case(a2ds, name)
+    reference assembler; values must match block for block.  order 3: TACSQuad9Shell, on a mesh
+    with more elements than resident thread blocks."""
+    if order == 2:
+        conn, X, bcn = _mesh_case(a2ds, name)
+    elif name == "plate":
+        conn, X, bcn = a2ds.meshes.plate9(23, 17, bump=2e-2)
+    else:
+        conn, X, bcn = a2ds.meshes.cylinder9(20, 10)
     n = len(X)
-    props = ref.iso_props()
+    props = ref.iso_props(kind=0 if order == 2 else 2)
     bc_vars = [list(range(6)) if i % 2 else [0, 1, 2] for i in range(len(bcn))]
     bc_vals = [[-1e-5] + [0.0] * (len(v) - 1) for v in bc_vars]
     ra = ref.RefAssembler(conn, X, np.zeros(len(conn), dtype=np.int32), props[None], bcn, bc_vars,
-                          bc_vals)
+                          bc_vals, nodes_per_elem=order * order)
     u = np.zeros((n, 6))
     u[ra.new_nodes] = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)  # keyed on original ids
     ra.set_state(u)
     Cs, eth, _ = ref.con_tables(props)
     asm = a2ds.Assembler(0)
-    asm.set_mesh(ra.conn(), n)
+    asm.set_mesh(ra.conn(), n, order=order)
     asm.set_nodes(ra.nodes())
     asm.set_components(Cs[None], eth[None])
     nodes_b, vars_b, vals_b = ra.bcs()
@@ -891,10 +898,12 @@ def test_quad9_element_level_vs_oracle(a2ds, orc, kind, transform, T, t_offset):
 def test_quad9_assembly_vs_oracle(a2ds, orc, name):
     """assembled 9-node meshes with prescribed boundary values: pattern bit-exact, the three
     entry points (assembleRes, assembleJacobian, assembleMatType(K)) against oracle9_assemble"""
+    # more elements than thread blocks of the persistent grid (2 x 148): every block works
+    # through several elements, so state carried from one element to the next would show
     if name == "plate":
-        conn, X, bcn = a2ds.meshes.plate9(9, 7, bump=2e-2)
+        conn, X, bcn = a2ds.meshes.plate9(31, 24, bump=2e-2)
     else:
-        conn, X, bcn = a2ds.meshes.cylinder9(12, 5)
+        conn, X, bcn = a2ds.meshes.cylinder9(36, 21)
     n = len(X)
     u = a2ds.meshes.seeded_state(np.arange(n), scale=1e-5)
     u[:, 3:] *= 10.0

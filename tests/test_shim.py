@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = os.path.join(ROOT, "tests", "_shim", "libtacs_a2ds_shim.so")
 
 
-def _run(preload):
+def _run(preload, *args):
     env = dict(os.environ)
     env["OPENBLAS_NUM_THREADS"] = "1"
     if preload:
@@ -25,7 +25,7 @@ def _run(preload):
         blas = os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs")
         env["LD_LIBRARY_PATH"] = blas + os.pathsep + env.get("LD_LIBRARY_PATH", "")
         env["LD_PRELOAD"] = SHIM
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shim_probe.py")], env=env,
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shim_probe.py"), *args], env=env,
                          capture_output=True, text=True, timeout=600)
     line = [l for l in out.stdout.splitlines() if l.startswith("SHIM_PROBE ")]
     assert line, out.stdout[-2000:] + out.stderr[-2000:]
@@ -62,3 +62,27 @@ def test_reference_buckling_flow_runs_on_gpu_through_the_shim(ref):
     assert base["at_vs_ad"] < 1e-13 and gpu["at_vs_ad"] < 1e-13
     assert abs(gpu["at_max"] - base["at_max"]) <= 1e-10 * base["at_max"]
     assert abs(gpu["at_chk"] - base["at_chk"]) <= 1e-9 * base["at_max"]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_gpu(), reason="no CUDA device")
+def test_reference_buckling_flow_with_quad9_shells_through_the_shim(ref):
+    """TACSLinearBuckling::solve on a cylinder of TACSQuad9Shell elements: K and G assembled by
+    k_assemble9 inside the unmodified flow, eigenvalues against the reference's own assembly"""
+    if not os.path.exists(SHIM):
+        pytest.skip("shim not built (needs the reference headers)")
+    base, _ = _run(False, "quad9")
+    gpu, log = _run(True, "quad9")
+    assert "[a2ds shim]" in log and "device assembly" in log
+    e0, e1 = np.array(base["eig"])[:4], np.array(gpu["eig"])[:4]   # the converged ones
+    assert np.all(np.array(base["err"])[:4] < 1e-6)
+    assert np.all(np.abs(e1 - e0) <= 1e-8 * np.abs(e0)), (e0, e1)
+    assert abs(gpu["res_norm"] - base["res_norm"]) <= 1e-12 * base["res_norm"]
+    assert abs(gpu["a_max"] - base["a_max"]) <= 1e-10 * base["a_max"]
+    assert abs(gpu["a_chk"] - base["a_chk"]) <= 1e-9 * base["a_max"]
+    # K and G in the four TACSSchurMat blocks at a fixed state, the load path the flow solved
+    # for, and G at that path (weighted checksums over every entry)
+    for tag in ("k", "g", "gpath"):
+        assert abs(gpu[tag + "_max"] - base[tag + "_max"]) <= 1e-10 * base[tag + "_max"]
+        assert abs(gpu[tag + "_chk"] - base[tag + "_chk"]) <= 1e-9 * base[tag + "_max"]
+    assert abs(gpu["path_chk"] - base["path_chk"]) <= 1e-10 * base["path_max"]
