@@ -1436,6 +1436,9 @@ static int launch_mass(a2ds_ctx *c, KParams &p) {
   }
   const int want = ((p.n_list + NB - 1) / NB + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
+  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, (1 + MAX_ZERO_ROUNDS) * sizeof(int)));
+  p.work_counter = c->work_counter;
+  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
   kern<<<grid, wpb * 32, per_warp * wpb, c->stream>>>(p);
   CU(cudaGetLastError());
   c->last_launches++;

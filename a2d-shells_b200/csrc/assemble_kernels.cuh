@@ -1099,8 +1099,13 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 3) k_mass(const KPar
   WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
   const unsigned FULL = 0xffffffffu;
   const int n_groups = (p.n_list + NB - 1) / NB;
-  for (int grp = blockIdx.x * warps_per_block + warp; grp < n_groups;
-       grp += gridDim.x * warps_per_block) {
+  (void)warps_per_block;
+  // batches drawn from the work counter, as in the element kernels (dynamic scheduling)
+  for (;;) {
+    int grp = 0;
+    if (lane == 0) grp = atomicAdd(p.work_counter, 1);
+    grp = __shfl_sync(FULL, grp, 0);
+    if (grp >= n_groups) break;
     const int base = grp * NB, cnt = min(NB, p.n_list - base);
     // lane = 4 j + m: node m of element j
     const int jl = (lane >> 2) & (NB - 1);

@@ -486,6 +486,75 @@ def run_case(args, workload, steps, warmup, dist, world, rank, local_rank, want_
     return res
 
 
+def run_quad9(local_rank, n=500, steps=3, warmup=2, want_parity=True):
+    """extra.quad9_plate: the 9-node shells (TACSQuad9Shell) on this GPU — an n x n
+    plate of 9-node elements (as many nodes as the 2n x 2n plate of 4-node elements of the main
+    line), fused residual + tangent + geometric stiffness, device resident; parity of sampled
+    centre-node rows (one element each) against the order-3 oracle outside the timing."""
+    a2ds = importlib.import_module("a2d-shells_b200")
+    conn, X, bcn = a2ds.meshes.plate9(n, n, bump=1e-3)
+    nn = len(X)
+    Cs, eth = a2ds.iso_shell_tables()
+    asm = a2ds.Assembler(local_rank)
+    asm.set_mesh(conn, nn, order=3)
+    asm.set_nodes(X)
+    asm.set_components(Cs[None], eth[None])
+    asm.set_bcs(bcn, 63)
+    u = a2ds.meshes.seeded_state(np.arange(nn), 1e-5)
+    asm.set_state(u)
+    kmat, gmat = asm.create_mat(), asm.create_mat()
+    out = {"workload": f"plate {n}x{n} 9-node MITC shells (TACSQuad9Shell), fused residual+Kmat+Gmat",
+           "elements": len(conn), "nodes": nn, "unit": "elements/s", "steps": steps, "warmup": warmup}
+    for tag, call in (("res_K", lambda: asm.assembleJacobian(1.0, 0.0, 0.0, kmat, download=False)),
+                      ("res_K_G", lambda: asm.assembleAll(kmat, gmat, download=False))):
+        for _ in range(warmup):
+            call()
+        asm.synchronize()
+        asm.region_begin()
+        for _ in range(steps):
+            call()
+        ms = asm.region_end() / steps
+        out[tag] = {"value": len(conn) / (ms * 1e-3), "ms_per_step": ms}
+    out["value"] = out["res_K_G"]["value"]
+    out["ms_per_step"] = out["res_K_G"]["ms_per_step"]
+    if want_parity:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle_py as orc
+            res = asm.assembleAll(kmat, gmat)
+            rowp, cols = asm.mat_pattern(kmat)
+            comp = orc.make_comp(0, Cs, eth)
+            rng = np.random.default_rng(7)
+            bc = set(int(b) for b in bcn)
+            elems = [int(e) for e in rng.choice(len(conn), size=96, replace=False)
+                     if int(conn[e, 4]) not in bc][:64]
+            centres = np.array([conn[e, 4] for e in elems], dtype=np.int32)
+            krows = asm.mat_rows(kmat, centres, rowp)
+            grows = asm.mat_rows(gmat, centres, rowp)
+            worst = {"res": 0.0, "K": 0.0, "G": 0.0}
+            for e, c, kr, gr in zip(elems, centres, krows, grows):
+                Xe, ue = X[conn[e]].ravel(), u[conn[e]].ravel()
+                r_o, k_o = orc.jacobian(comp, Xe, ue, order=3)
+                g_o = orc.mat_type(comp, 1, Xe, ue, order=3)
+                # the centre node couples to the element's own 9 nodes only: its block row is
+                # row block 4 of the element matrices, columns in ascending node order
+                order = np.argsort(conn[e])
+                assert np.array_equal(cols[rowp[c]:rowp[c + 1]], conn[e][order])
+                for name, ours, ref in (("K", kr, k_o), ("G", gr, g_o)):
+                    blk = np.stack([ref[24:30, 6 * j:6 * j + 6] for j in order])
+                    worst[name] = max(worst[name], float(np.abs(ours - blk).max() / np.abs(ref).max()))
+                worst["res"] = max(worst["res"], float(np.abs(res[c] - r_o[24:30]).max() / np.abs(r_o).max()))
+            tol = {"res": 1e-12, "K": 1e-10, "G": 1e-10}
+            out["parity"] = {"rows": len(elems), "max_rel": worst, "tol": tol,
+                             "ok": bool(all(worst[k] < tol[k] for k in tol)),
+                             "against": "order-3 plain-C oracle (oracle/shell_oracle_q9.c) on the element "
+                                        "around each sampled centre node"}
+        except Exception as e:   # a broken checker must not look like a pass
+            out["parity"] = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+    asm.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -555,6 +624,15 @@ def main():
                 "scaling": "strong", "elements_per_gpu": x["n_elems"], "parity": x["parity"]}
         except Exception as e:
             extra["strong_cyl16m"] = {"error": f"{type(e).__name__}: {e}"}
+        # the 9-node shells on rank 0's GPU (one GPU, no halo)
+        if rank == 0:
+            try:
+                with c_stdout_to_stderr():
+                    extra["quad9_plate"] = run_quad9(local_rank, want_parity=not args.no_parity)
+            except Exception as e:
+                extra["quad9_plate"] = {"error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            dist.barrier()
 
     if rank == 0:
         peaks, which = measured_peaks()
