@@ -152,6 +152,7 @@ struct a2ds_ctx {
   // two vectors, grown on demand, so that a Krylov loop does not allocate per call
   double *scratch_x = nullptr, *scratch_y = nullptr;
   size_t scratch_nx = 0, scratch_ny = 0;
+  void *shape9_dev = nullptr;    // shape function tables of the 9-node element (k_mass9)
   int *work_counter = nullptr;   // [0] batch counter, [1..] zero_done rounds; zeroed before every k_assemble launch
   // matrices the next k_assemble_t launch has to zero itself (in-kernel zeroing)
   double *pz_K = nullptr, *pz_G = nullptr;
@@ -273,7 +274,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   free_lists(c);
   cudaFree(c->conn); cudaFree(c->elem_comp); cudaFree(c->X); cudaFree(c->u); cudaFree(c->res);
   cudaFree(c->udd);
-  cudaFree(c->scratch_x); cudaFree(c->scratch_y); cudaFree(c->zplan_dev);
+  cudaFree(c->scratch_x); cudaFree(c->scratch_y); cudaFree(c->zplan_dev); cudaFree(c->shape9_dev);
   cudaFree(c->nat_d_rowp); cudaFree(c->nat_d_cols);
   cudaFree(c->comps); cudaFree(c->bc_nodes); cudaFree(c->bc_vars); cudaFree(c->bc_vals);
   cudaFree(c->send_nodes); cudaFree(c->recv_nodes); cudaFree(c->send_buf); cudaFree(c->recv_buf);
@@ -1418,9 +1419,36 @@ static int launch_elem(a2ds_ctx *c, KParams &p, bool coupled) {
   return launch_one_t<RES, KMAT, GMAT, NL>(c, p);
 }
 
+// mass kernel of the 9-node shells (assemble9_kernels.cuh): one warp per element
+template <bool RES, bool MAT>
+static int launch_mass9(a2ds_ctx *c, KParams &p) {
+  if (!c->shape9_dev) {
+    CU(cudaMalloc((void **)&c->shape9_dev, sizeof(a2ds::Shape9)));
+    k_shape9_tables<<<1, 64, 0, c->stream>>>((a2ds::Shape9 *)c->shape9_dev);
+    CU(cudaGetLastError());
+  }
+  auto kern = k_mass9<RES, MAT>;
+  const int wpb = 4;
+  const size_t smem = wpb * sizeof(Mass9Warp);
+  static bool attr_set[MAX_DEVICES] = {false};
+  if (!attr_set[c->device]) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[c->device] = true;
+  }
+  if (!c->work_counter) CU(cudaMalloc((void **)&c->work_counter, (1 + MAX_ZERO_ROUNDS) * sizeof(int)));
+  p.work_counter = c->work_counter;
+  CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  const int grid = std::max(1, std::min((p.n_list + wpb - 1) / wpb, c->n_sm * 4));
+  kern<<<grid, wpb * 32, smem, c->stream>>>(p, (const a2ds::Shape9 *)c->shape9_dev);
+  CU(cudaGetLastError());
+  c->last_launches++;
+  return 0;
+}
+
 // launch the mass kernel over one element list
 template <bool RES, bool MAT>
 static int launch_mass(a2ds_ctx *c, KParams &p) {
+  if (c->npe == 9) return launch_mass9<RES, MAT>(c, p);
   const size_t per_warp = (offsetof(WarpScratch, E2) + 15) & ~size_t(15);
   p.scratch_bytes = (int)per_warp;
   auto kern = k_mass<RES, MAT>;
@@ -1679,9 +1707,8 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   const int kmat = rq.kmat, gmat = rq.gmat, mmat = rq.mmat;
   // inertial residual M * uddot (TACSShellElement.h:410-447) once second derivatives are set
   const bool MRES = RES && c->udd != nullptr;
-  if (c->npe != 4 && (MM || MRES || c->scatter_mode != A2DS_SCATTER_ATOMIC))
-    return fail("assemble: 9-node elements provide the residual, the tangent and the geometric stiffness "
-                "(atomic scatter); no mass terms");
+  if (c->npe != 4 && c->scatter_mode != A2DS_SCATTER_ATOMIC)
+    return fail("assemble: 9-node elements are assembled with the atomic scatter only");
   if (KM && check_mat(c, kmat)) return 1;
   if (GM && check_mat(c, gmat)) return 1;
   if (MM && check_mat(c, mmat)) return 1;

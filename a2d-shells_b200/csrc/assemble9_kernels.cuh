@@ -255,4 +255,71 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
   }
 }
 
+
+// ---- mass path of the 9-node shells: gamma M into a matrix and / or the inertial residual M u'' ----
+// (TACS_MASS_MATRIX, the gamma term of assembleJacobian, TACSShellElement.h:410-447, 614-648).
+// One warp per element: node normals, w det of the 9 Gauss points, then the 81 node-pair blocks
+// (a scalar per pair times fixed 3 x 3 patterns, q9_mass_pair); p.u holds the second time
+// derivatives (as for k_mass), p.alpha the scale of the matrix.
+struct Mass9Warp {
+  a2ds::Elem9 E;
+  int nodes[9];
+  int off[81];
+};
+template <bool RES, bool MAT>
+__global__ void __launch_bounds__(128) k_mass9(KParams p, const a2ds::Shape9 *Hg) {
+  using namespace a2ds;
+  extern __shared__ __align__(16) unsigned char smem9m[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Mass9Warp &W = reinterpret_cast<Mass9Warp *>(smem9m)[warp];
+  const Shape9 &H = *Hg;
+  const unsigned FULL = 0xffffffffu;
+  for (;;) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(p.work_counter, 1);
+    idx = __shfl_sync(FULL, idx, 0);
+    if (idx >= p.n_list) break;
+    const int e = p.elem_list ? __ldg(&p.elem_list[idx]) : idx;
+    const CompData &c = p.comps[__ldg(&p.elem_comp[e])];
+    if (lane < 9) W.nodes[lane] = __ldg(&p.conn[9 * (size_t)e + lane]);
+    if (MAT)
+      for (int k = lane; k < 81; k += 32) W.off[k] = __ldg(&p.Koff[81 * (size_t)e + k]);
+    __syncwarp();
+    if (lane < 27) W.E.X[lane] = __ldg(&p.X[3 * (size_t)W.nodes[lane / 3] + lane % 3]);
+    if (RES)
+      for (int d = lane; d < Q9_NV; d += 32) W.E.q[d] = __ldg(&p.u[6 * (size_t)W.nodes[d / 6] + d % 6]);
+    __syncwarp();
+    if (lane < 9) q9_node_normal(W.E, lane);
+    __syncwarp();
+    if (lane < 9) q9_qp_det(W.E, H, lane);
+    __syncwarp();
+    for (int pair = lane; pair < 81; pair += 32) {
+      const int ma = pair / 9, mb = pair - 9 * ma;
+      double blk[36];
+      q9_mass_pair(c, W.E, H, ma, mb, blk);
+      if (MAT) {
+        double *dst = p.Kval + 36 * (size_t)W.off[pair];
+#pragma unroll
+        for (int k = 0; k < 36; k++)
+          if (blk[k] != 0.0) atomicAdd(dst + k, p.alpha * blk[k]);
+      }
+      if (RES) {
+        double *r = &p.res[6 * (size_t)W.nodes[ma]];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < 6; j++) s += blk[6 * i + j] * W.E.q[6 * mb + j];
+          atomicAdd(r + i, p.res_scale * s);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+// fills the shape tables once per device (k_mass9 reads them from global memory)
+__global__ void k_shape9_tables(a2ds::Shape9 *H) {
+  if (threadIdx.x < 46) a2ds::q9_shape_tables(*H, threadIdx.x);
+}
+
 #endif

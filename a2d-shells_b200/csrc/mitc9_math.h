@@ -586,5 +586,44 @@ A2DS_HD void q9_geo_pair(const Elem9 &E, const Shape9 &H, int ma, int mb, double
     }
 }
 
+// ---- mass path: M_e = sum_q w det N_a N_b [[m0 I, m1 D_b], [m1 D_a^T, m2 D_a^T D_b]] --------
+// (TACSShellElement.h:410-447, 614-648 with TACSLinearizedRotation: the director rate is
+// d'' = theta'' x fn, TACSDirector.h:232-262).  Needs only the node normals and w det of the
+// Gauss points; blk[36] row major, rows = dofs of node ma.
+A2DS_HD void q9_mass_pair(const CompData &c, const Elem9 &E, const Shape9 &H, int ma, int mb, double blk[36]) {
+  double cf = 0.0;
+  for (int q = 0; q < 9; q++) cf += E.qw[q] * H.Nq[q][ma] * H.Nq[q][mb];
+  const double *fa = &E.fn[3 * ma], *fb = &E.fn[3 * mb];
+  const double Da[9] = {0.0, fa[2], -fa[1], -fa[2], 0.0, fa[0], fa[1], -fa[0], 0.0};
+  const double Db[9] = {0.0, fb[2], -fb[1], -fb[2], 0.0, fb[0], fb[1], -fb[0], 0.0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      blk[6 * i + j] = (i == j) ? cf * c.mom[0] : 0.0;
+      blk[6 * i + 3 + j] = cf * c.mom[1] * Db[3 * i + j];
+      blk[6 * (3 + i) + j] = cf * c.mom[1] * Da[3 * j + i];
+      blk[6 * (3 + i) + 3 + j] = cf * c.mom[2] * (Da[i] * Db[j] + Da[3 + i] * Db[3 + j] + Da[6 + i] * Db[6 + j]);
+    }
+}
+// node normal only (first part of q9_node) and w det of Gauss point q only (part of q9_qp)
+A2DS_HD void q9_node_normal(Elem9 &E, int n) {
+  const double pt[2] = {-1.0 + (n % 3), -1.0 + (n / 3)};
+  double Xxi[3], Xeta[3], fn[3];
+  q9_grad_strict(pt, E.X, 3, Xxi, Xeta);
+  scross(Xxi, Xeta, fn);
+  const double nrm = sqrt(sdot(fn, fn));
+  if (nrm != 0.0) {
+    const double inv = 1.0 / nrm;
+    fn[0] = A2DS_MUL(fn[0], inv); fn[1] = A2DS_MUL(fn[1], inv); fn[2] = A2DS_MUL(fn[2], inv);
+  }
+  for (int k = 0; k < 3; k++) E.fn[3 * n + k] = fn[k];
+}
+A2DS_HD void q9_qp_det(Elem9 &E, const Shape9 &H, int q) {
+  double Xxi[3], Xeta[3], n0[3], Xi[9];
+  q9_interp3(H.Nxq[q], E.X, 3, Xxi);
+  q9_interp3(H.Neq[q], E.X, 3, Xeta);
+  q9_interp3(H.Nq[q], E.fn, 3, n0);
+  E.qw[q] = q9_frame_inverse(Xxi, Xeta, n0, Xi) * (q9_wt3(q % 3) * q9_wt3(q / 3));
+}
+
 }  // namespace a2ds
 #endif

@@ -76,13 +76,13 @@ int a2ds_set_mesh(a2ds_ctx *ctx, int n_nodes, int n_owned, int n_elems, const in
  * shells (TACSQuad9Shell = TACSShellElement<TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3>,
  * TACSLinearizedRotation, TACSShellLinearModel>, src/elements/shell/TACSShellElementDefs.h:16-18);
  * conn[9 e + 3 j + i] in the tensor order of TACSShellQuadBasis<3>::getNodePoint
- * (TACSShellElementQuadBasis.h:147-150).  A 9-node mesh supports the residual, the tangent and
- * the geometric stiffness of both strain models (a2ds_assemble_res, a2ds_assemble_jacobian with
- * gamma = 0, a2ds_assemble_mat_type(A2DS_STIFFNESS_MATRIX | A2DS_GEOMETRIC_STIFFNESS_MATRIX),
- * a2ds_assemble_all, a2ds_assemble_mat_combo of those; TACSQuad9NonlinearShell = elem_class 1)
- * with atomic scatter, on natural-order or caller-supplied patterns, plus everything that works
- * on nodes and blocks (boundary conditions, halo exchange, matrix algebra, mat-vec); mass terms,
- * the coloured scatter modes and the matrix-free product fail for it. */
+ * (TACSShellElementQuadBasis.h:147-150).  A 9-node mesh supports every assembly entry point of
+ * both strain models (TACSQuad9NonlinearShell = elem_class 1): a2ds_assemble_res,
+ * a2ds_assemble_jacobian (alpha, gamma, second time derivatives), a2ds_assemble_mat_type
+ * (stiffness, geometric stiffness, mass), a2ds_assemble_all, a2ds_assemble_mat_combo — with the
+ * atomic scatter, on natural-order or caller-supplied patterns — plus everything that works on
+ * nodes and blocks (boundary conditions, halo exchange, matrix algebra, mat-vec); the coloured
+ * scatter modes and the matrix-free product fail for it. */
 int a2ds_set_mesh_order(a2ds_ctx *ctx, int order, int n_nodes, int n_owned, int n_elems,
                         const int *conn, const int *elem_comp);
 

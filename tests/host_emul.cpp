@@ -304,3 +304,25 @@ extern "C" int emul_element9(const double *Cs, const double *eth, double tempera
       }
   return 0;
 }
+
+// mass matrix of the 9-node element through q9_mass_pair (the work items of k_mass9)
+extern "C" int emul_mass9(const double *mom, const double *X, double *M) {
+  CompData c;
+  memset(&c, 0, sizeof(c));
+  memcpy(c.mom, mom, sizeof(c.mom));
+  static Elem9 E;
+  static Shape9 H;
+  memset(&E, 0, sizeof(E));
+  memcpy(E.X, X, sizeof(E.X));
+  for (int pnt = 0; pnt < 46; pnt++) q9_shape_tables(H, pnt);
+  for (int n = 0; n < 9; n++) q9_node_normal(E, n);
+  for (int q = 0; q < 9; q++) q9_qp_det(E, H, q);
+  for (int ma = 0; ma < 9; ma++)
+    for (int mb = 0; mb < 9; mb++) {
+      double blk[36];
+      q9_mass_pair(c, E, H, ma, mb, blk);
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) M[54 * (6 * ma + i) + 6 * mb + j] = blk[6 * i + j];
+    }
+  return 0;
+}

@@ -944,9 +944,70 @@ def test_quad9_assembly_vs_oracle(a2ds, orc, name):
     assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL
     assert relmax(asm.mat_values(gmat), g_o) < MAT_TOL
     G = asm.mat_values(gmat)
-    # the entry points 9-node meshes do not provide fail loudly
+    # what 9-node meshes do not provide fails loudly
+    asm.set_scatter_mode(a2ds.SCATTER_COLORED)
     with pytest.raises(RuntimeError):
-        asm.assembleMatType(a2ds.MASS_MATRIX, gmat)
+        asm.assembleMatType(a2ds.STIFFNESS_MATRIX, gmat)
+    asm.set_scatter_mode(a2ds.SCATTER_ATOMIC)
     with pytest.raises(RuntimeError):
-        asm.assembleJacobian(1.0, 0.0, 2.0, kmat)
+        asm.addJacobianVecProduct(1.0, 1.0, u, np.zeros((n, 6)))
+    asm.close()
+
+
+def test_quad9_mixed_classes_mass_and_combo_vs_oracle(a2ds, orc):
+    """one 9-node mesh with 24 components — own sections (coupled B block, As[1]), a mix of
+    TACSQuad9Shell and TACSQuad9NonlinearShell — through every assembly entry point: fused
+    res + K + G, the mass matrix, the gamma / uddot terms, assembleMatCombo"""
+    conn, X, bcn = a2ds.meshes.cylinder9(24, 14)
+    n = len(X); ne = len(conn)
+    rng = np.random.default_rng(9)
+    ncomp = 24
+    Cs = np.zeros((ncomp, 22)); eth = np.zeros((ncomp, 9)); mom = np.zeros((ncomp, 3))
+    for c in range(ncomp):
+        t = rng.uniform(0.005, 0.02); off = rng.uniform(-0.4, 0.4)
+        base, e = a2ds.iso_shell_tables(E=72e9 * rng.uniform(0.5, 2), nu=rng.uniform(0.2, 0.4), t=t,
+                                        t_offset=off)
+        base[7] *= 1.0 + 0.1 * rng.uniform()
+        base[19] = 0.05 * base[18] * rng.uniform(-1, 1)
+        Cs[c] = base; eth[c] = e; mom[c] = a2ds.iso_mass_moments(2700.0, t, off)
+    cls = (rng.uniform(size=ncomp) < 0.4).astype(np.int32)
+    elem_comp = rng.integers(0, ncomp, ne).astype(np.int32)
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-4)
+    udd = a2ds.meshes.seeded_state(np.arange(n) + 77, 1.0)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n, elem_comp=elem_comp, order=3); asm.set_nodes(X)
+    asm.set_components(Cs, eth, elem_class=cls)
+    asm.set_mass_moments(mom)
+    bc_vars = np.full(len(bcn), 63, dtype=np.int32); bc_vals = np.zeros((len(bcn), 6))
+    asm.set_bcs(bcn, bc_vars, bc_vals); asm.set_state(u)
+    k = asm.create_mat(); g = asm.create_mat(); m = asm.create_mat()
+    rowp, cols = asm.mat_pattern(k)
+    comps = [orc.make_comp(int(cls[c]), Cs[c], eth[c], mom[c]) for c in range(ncomp)]
+    oargs = (conn, elem_comp, comps, X, u, rowp, cols, bcn, bc_vars, bc_vals)
+    r_o, k_o = orc.assemble(1, *oargs, order=3)
+    _, g_o = orc.assemble(3, *oargs, order=3)
+    _, m_o = orc.assemble(4, *oargs, order=3)
+    r = asm.assembleAll(k, g)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(k), k_o) < MAT_TOL
+    assert relmax(asm.mat_values(g), g_o) < MAT_TOL
+    asm.assembleMatType(a2ds.MASS_MATRIX, m)
+    assert relmax(asm.mat_values(m), m_o) < 1e-13
+    # gamma term and inertial residual
+    asm.set_state_rates(None, udd)
+    r = asm.assembleJacobian(0.7, 0.0, 3.0, k)
+    r_o2, j_o = orc.assemble(1, *oargs, alpha=0.7, gamma=3.0, udd=udd, order=3)
+    assert relmax(r, r_o2) < RES_TOL and relmax(asm.mat_values(k), j_o) < MAT_TOL
+    r0_o, _ = orc.assemble(0, *oargs, udd=udd, order=3)
+    assert relmax(asm.assembleRes(), r0_o) < RES_TOL
+    asm.set_state_rates(None, None)
+    # A = K - 2 G + 5 M with the boundary conditions applied once
+    asm.assembleMatCombo([a2ds.STIFFNESS_MATRIX, a2ds.GEOMETRIC_STIFFNESS_MATRIX, a2ds.MASS_MATRIX],
+                         [1.0, -2.0, 5.0], k)
+    _, k2_o = orc.assemble(2, *oargs, order=3)
+    combo = k2_o - 2.0 * g_o + 5.0 * m_o
+    for b, nd in enumerate(bcn):   # BC rows: zero, 1 on the diagonal entry (applied once)
+        for j in range(rowp[nd], rowp[nd + 1]):
+            combo[j] = np.eye(6) if cols[j] == nd else 0.0
+    assert relmax(asm.mat_values(k), combo) < MAT_TOL
     asm.close()

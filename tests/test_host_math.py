@@ -182,3 +182,19 @@ def test_quad9_kernel_math_against_oracle_many(emul, orc, a2ds):
                 worst[0] = max(worst[0], relmax(res, r_o))
                 worst[1] = max(worst[1], relmax(K.reshape(54, 54), k_o))
     assert worst[0] < 1e-12 and worst[1] < 1e-10, worst
+
+
+def test_quad9_mass_math_against_oracle(emul, orc):
+    """q9_mass_pair (the work items of k_mass9) against the order-3 oracle's TACS_MASS_MATRIX,
+    with a non-zero first mass moment"""
+    from helpers import random_elements9
+    import ctypes as C
+    X, _ = random_elements9(20, seed=3)
+    mom = np.array([27.18, 0.011, 2.3e-4])
+    p = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
+    comp = orc.make_comp(0, np.ones(22), np.zeros(9), mom)
+    for e in range(len(X)):
+        M = np.zeros(54 * 54)
+        emul.emul_mass9(p(mom), p(X[e]), p(M))
+        m_o = orc.mat_type(comp, 2, X[e].ravel(), np.zeros(54), order=3)
+        assert relmax(M.reshape(54, 54), m_o) < 1e-13
