@@ -44,14 +44,14 @@ struct Elem9Block {
   Meta9 M[2];
   a2ds::Shape9 H;     // shape function tables, filled once per block
   a2ds::Tab9 T;       // derivative tables of the element being contracted (ends with B, CB)
-  double B2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];    // B / CB of the other points of the batch
-  double CB2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LD];
+  double B2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LDB];    // B / CB of the other points of the batch
+  double CB2[Q9_QB - 1][a2ds::Q9_KROWS][a2ds::Q9_LDB];
   // Once the last batch is contracted the tables are dead and hold the element matrix on its
-  // way out: T.B .. CB2 (4032 doubles, contiguous) the 54 x 54 contraction result, T.Gt .. T.Gt1
+  // way out: T.B .. CB2 (4896 doubles, contiguous) the 54 x 54 contraction result, T.Gt .. T.Gt1
   // (3136 doubles) the 54 x 54 geometric term, both in BCSR block order (k9_at).
 };
 static_assert(offsetof(Elem9Block, B2) == offsetof(Elem9Block, T) + offsetof(a2ds::Tab9, CB) +
-                                              sizeof(double) * a2ds::Q9_KROWS * a2ds::Q9_LD,
+                                              sizeof(double) * a2ds::Q9_KROWS * a2ds::Q9_LDB,
               "T.B, T.CB, B2, CB2 must be contiguous");
 static_assert(offsetof(a2ds::Tab9, Gt1) == offsetof(a2ds::Tab9, Gt) + sizeof(double) * a2ds::Q9_NTY * a2ds::Q9_LD,
               "T.Gt, T.Gt1 must be contiguous");
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 46) q9_shape_tables(S.H, tid);
   // rows 9..11 and columns 54, 55 of the B tables stay zero
-  for (int i = tid; i < Q9_KROWS * Q9_LD; i += Q9_THREADS) {
+  for (int i = tid; i < Q9_KROWS * Q9_LDB; i += Q9_THREADS) {
     (&S.T.B[0][0])[i] = 0.0; (&S.T.CB[0][0])[i] = 0.0;
     for (int qq = 0; qq < Q9_QB - 1; qq++) { (&S.B2[qq][0][0])[i] = 0.0; (&S.CB2[qq][0][0])[i] = 0.0; }
   }
@@ -123,19 +123,19 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
   auto consume = [&](const Elem9 &E, const Meta9 &M) {
     const CompData &c = p.comps[M.comp];
     Tab9 &Tb = S.T;
-    auto Bq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? Tb.B : S.B2[qq - 1]; };
-    auto CBq = [&](int qq) -> double(*)[Q9_LD] { return qq == 0 ? Tb.CB : S.CB2[qq - 1]; };
+    auto Bq = [&](int qq) -> double(*)[Q9_LDB] { return qq == 0 ? Tb.B : S.B2[qq - 1]; };
+    auto CBq = [&](int qq) -> double(*)[Q9_LDB] { return qq == 0 ? Tb.CB : S.CB2[qq - 1]; };
     if (KMAT || GMAT) {
       // the previous element's matrix went out through the B / CB tables: their padding (rows
       // 9..11, columns 54, 55), which the contraction reads, has to be zero again
-      double *tab = &Tb.B[0][0];   // T.B, T.CB, B2, CB2: 2 * Q9_QB tables of Q9_KROWS x Q9_LD
-      const int per = (Q9_KROWS - 9) * Q9_LD + 9 * (Q9_LD - Q9_NV);
+      double *tab = &Tb.B[0][0];   // T.B, T.CB, B2, CB2: 2 * Q9_QB tables of Q9_KROWS x Q9_LDB
+      const int per = (Q9_KROWS - 9) * Q9_LDB + 9 * (Q9_LDB - Q9_NV);
       for (int i = tid; i < 2 * Q9_QB * per; i += Q9_CONSUMERS) {
         const int t = i / per, k = i - per * t;
-        const int at = k < (Q9_KROWS - 9) * Q9_LD ? 9 * Q9_LD + k
-                                                  : Q9_LD * ((k - (Q9_KROWS - 9) * Q9_LD) / (Q9_LD - Q9_NV)) + Q9_NV +
-                                                        (k - (Q9_KROWS - 9) * Q9_LD) % (Q9_LD - Q9_NV);
-        tab[Q9_KROWS * Q9_LD * t + at] = 0.0;
+        const int at = k < (Q9_KROWS - 9) * Q9_LDB ? 9 * Q9_LDB + k
+                                                   : Q9_LDB * ((k - (Q9_KROWS - 9) * Q9_LDB) / (Q9_LDB - Q9_NV)) + Q9_NV +
+                                                         (k - (Q9_KROWS - 9) * Q9_LDB) % (Q9_LDB - Q9_NV);
+        tab[Q9_KROWS * Q9_LDB * t + at] = 0.0;
       }
     }
     for (int i = tid; i < Q9_NTY * Q9_NV; i += Q9_CONSUMERS) {
@@ -158,32 +158,36 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
           for (int k = 0; k < 9; k++) Bk[k] += B1k[k];
         }
         q9_stress(c.Cs, GMAT ? B1k : Bk, Sk);
-        double(*Bt)[Q9_LD] = Bq(qq), (*Ct)[Q9_LD] = CBq(qq);
+        double(*Bt)[Q9_LDB] = Bq(qq), (*Ct)[Q9_LDB] = CBq(qq);
         const double w = E.qw[q];
 #pragma unroll
         for (int k = 0; k < 9; k++) { Bt[k][col] = Bk[k]; Ct[k][col] = w * Sk[k]; }
       }
       q9_consumer_barrier();
       if (KMAT || GMAT) {
-        // K = B^T (w det C B): symmetric, tiles on and right of the diagonal;
-        // Z = L^T (w det C B1): all 49 tiles, G = Z + Z^T is formed by the scatter
+        // K = B^T (w det C B) is symmetric: warp w contracts the four tiles (w, (w + d) mod 7),
+        // d = 0..3 — every unordered tile pair exactly once, the same work for every warp;
+        // Z = L^T (w det C B1): all 49 tiles (d = 0..6), G = Z + Z^T is formed by the scatter
 #pragma unroll
         for (int qq = 0; qq < Q9_QB; qq++) {
-          const double(*Bt)[Q9_LD] = Bq(qq), (*Ct)[Q9_LD] = CBq(qq);
+          const double(*Bt)[Q9_LDB] = Bq(qq), (*Ct)[Q9_LDB] = CBq(qq);
 #pragma unroll
           for (int ks = 0; ks < 3; ks++) {
             const int kr = 4 * ks + (lane & 3);
             const double a = Bt[kr][8 * warp + (lane >> 2)];
 #pragma unroll
-            for (int tj = 0; tj < 7; tj++)
-              if (GMAT || tj >= warp) dmma884(acc[tj], a, Ct[kr][8 * tj + (lane >> 2)]);
+            for (int d = 0; d < (GMAT ? 7 : 4); d++) {
+              int tj = warp + d;
+              if (tj >= 7) tj -= 7;
+              dmma884(acc[d], a, Ct[kr][8 * tj + (lane >> 2)]);
+            }
           }
         }
       }
       if (RES && tid < Q9_NV) {
 #pragma unroll
         for (int qq = 0; qq < Q9_QB; qq++) {
-          const double(*Bt)[Q9_LD] = Bq(qq);
+          const double(*Bt)[Q9_LDB] = Bq(qq);
           const double *s = E.sq[Q9_QB * b + qq];
 #pragma unroll
           for (int k = 0; k < 9; k++) r += Bt[k][tid] * s[k];
@@ -203,14 +207,15 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
       const int gr = 8 * warp + (lane >> 2);
       if (gr < Q9_NV) {
 #pragma unroll
-        for (int tj = 0; tj < 7; tj++) {
-          if (!GMAT && tj < warp) continue;
+        for (int d = 0; d < (GMAT ? 7 : 4); d++) {
+          int tj = warp + d;
+          if (tj >= 7) tj -= 7;
 #pragma unroll
           for (int i = 0; i < 2; i++) {
             const int gc = 8 * tj + 2 * (lane & 3) + i;
             if (gc >= Q9_NV) continue;
-            Ke[k9_at(gr, gc)] = acc[tj][i];
-            if (!GMAT && tj > warp) Ke[k9_at(gc, gr)] = acc[tj][i];
+            Ke[k9_at(gr, gc)] = acc[d][i];
+            if (!GMAT && d > 0) Ke[k9_at(gc, gr)] = acc[d][i];   // the mirrored tile of the symmetric K
           }
         }
       }
@@ -249,8 +254,15 @@ __global__ void __launch_bounds__(Q9_THREADS, A2DS_Q9_MINB) k_assemble9(KParams 
   for (;;) {
     __syncthreads();   // record `cur` is complete, record `cur ^ 1` is free again
     if (S.M[cur].elem < 0) break;
+#if defined(A2DS_Q9_TIMING_NO_CONSUME)   // timing experiments only: results are wrong
+    if (warp == 7) produce(S.E[cur ^ 1], S.M[cur ^ 1]);
+#elif defined(A2DS_Q9_TIMING_NO_PRODUCE)
+    if (warp == 7) { if (lane == 0) S.M[cur ^ 1].elem = (int)atomicAdd(p.work_counter, 1) < p.n_list ? 0 : -1; }
+    else consume(S.E[cur], S.M[cur]);
+#else
     if (warp == 7) produce(S.E[cur ^ 1], S.M[cur ^ 1]);
     else consume(S.E[cur], S.M[cur]);
+#endif
     cur ^= 1;
   }
 }

@@ -577,7 +577,11 @@ __device__ __forceinline__ void stage_tiles_t(double *E, const double (&acc)[6][
     }
 }
 // scatter of the staged blocks: as scatter_matrix, on the block-major tile
-__device__ __forceinline__ void scatter_matrix_t(const double *E, double *vals, int off16, int lane) {
+#ifndef A2DS_OFF_LDS
+#define A2DS_OFF_LDS 0   // 1: block offsets of the scatter by broadcast LDS.128 from the gathered table instead of shuffles
+#endif
+__device__ __forceinline__ void scatter_matrix_t(const double *E, double *vals, int off16, int lane,
+                                                 const int *offrow = nullptr) {
   const unsigned FULL = 0xffffffffu;
   const int tb = lane >> 2;
 #pragma unroll
@@ -589,12 +593,22 @@ __device__ __forceinline__ void scatter_matrix_t(const double *E, double *vals, 
       v0[k] = E[ET_R * (b >> 2) + ET_C * (b & 3) + lane];
     }
     const double v1 = E[ET_R * (2 * half + (tb >> 2)) + ET_C * (tb & 3) + 32 + (lane & 3)];
+#if A2DS_OFF_LDS
+    const int4 oa = *reinterpret_cast<const int4 *>(offrow + 8 * half);
+    const int4 ob = *reinterpret_cast<const int4 *>(offrow + 8 * half + 4);
+    const int offs[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+    const int offt = offrow[8 * half + tb];
+    (void)FULL; (void)off16;
+#pragma unroll
+    for (int k = 0; k < 8; k++) atomicAdd(vals + 36 * (size_t)offs[k] + lane, v0[k]);
+#else
     const int offt = __shfl_sync(FULL, off16, 8 * half + tb);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int off = __shfl_sync(FULL, off16, 8 * half + k);
       atomicAdd(vals + 36 * (size_t)off + lane, v0[k]);
     }
+#endif
     atomicAdd(vals + 36 * (size_t)offt + 32 + (lane & 3), v1);
   }
 }
@@ -1020,7 +1034,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
           }
           if (lane < 24) atomicAdd(&p.jvp_y[6 * (size_t)node + lane % 6], p.jvp_scale * y);
         } else {
-          scatter_matrix_t(ws.E, p.Kval, rb.koff[j][lane & 15], lane);
+          scatter_matrix_t(ws.E, p.Kval, rb.koff[j][lane & 15], lane, rb.koff[j]);
         }
       }
       if (GMAT) {
@@ -1058,7 +1072,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
         }
         __syncwarp();
         if (j + 1 < cnt) prologue(j + 1);   // H and the tying stresses are free from here on
-        scatter_matrix_t(ws.E, p.Gval, goffb[j][lane & 15], lane);
+        scatter_matrix_t(ws.E, p.Gval, goffb[j][lane & 15], lane, goffb[j]);
       }
       if (!GMAT && !KMAT && j + 1 < cnt) prologue(j + 1);
       __syncwarp();

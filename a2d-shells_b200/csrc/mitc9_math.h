@@ -26,6 +26,9 @@
 namespace a2ds {
 
 static const int Q9_NN = 9, Q9_NV = 54, Q9_NTY = 28, Q9_LD = 56, Q9_KROWS = 12;
+// leading dimension of the B / CB tables: 68 = 4 (mod 16) puts the four strain rows a DMMA
+// fragment load touches (lane & 3) into disjoint bank groups for the 8 columns (lane >> 2)
+static const int Q9_LDB = 68;
 
 // geometry + state record of one element in shared memory (written by the producer warp)
 struct Elem9 {
@@ -50,8 +53,8 @@ struct Tab9 {
   double Gt[Q9_NTY][Q9_LD];         // d(tying strain t) / d(dof)
   double Gt1[Q9_NTY][Q9_LD];        // bilinear tying form with the state: Bil_t(q, 1_dof)
   double Dn[Q9_NN][Q9_LD];          // d(drill strain at node n) / d(dof)
-  double B[Q9_KROWS][Q9_LD];        // B of the current Gauss point (rows 9..11, columns 54, 55 zero)
-  double CB[Q9_KROWS][Q9_LD];       // w det C B (tangent) or w det C B1 (geometric stiffness)
+  double B[Q9_KROWS][Q9_LDB];       // B of the current Gauss point (rows 9..11, columns 54.. zero)
+  double CB[Q9_KROWS][Q9_LDB];      // w det C B (tangent) or w det C B1 (geometric stiffness)
 };
 
 // shape function tables of the element class (the same for every element: filled once per
@@ -102,7 +105,9 @@ A2DS_HD void q9_shape(const double pt[2], double N[9], double Nx[9], double Ne[9
   double na[3], nb[3], da[3], db[3];
   q9_lag(pt[0], na, da);
   q9_lag(pt[1], nb, db);
+  #pragma unroll
   for (int j = 0; j < 3; j++)
+    #pragma unroll
     for (int i = 0; i < 3; i++) {
       N[3 * j + i] = na[i] * nb[j];
       Nx[3 * j + i] = da[i] * nb[j];
@@ -115,22 +120,27 @@ A2DS_HD void q9_shape_tables(Shape9 &H, int p) {
   if (p < 9) {
     pt[0] = q9_gauss3(p % 3); pt[1] = q9_gauss3(p / 3);
     q9_shape(pt, N, Nx, Ne);
+    #pragma unroll
     for (int n = 0; n < 9; n++) { H.Nq[p][n] = N[n]; H.Nxq[p][n] = Nx[n]; H.Neq[p][n] = Ne[n]; }
   } else if (p < 9 + Q9_NTY) {
     const int t = p - 9;
     H.tfield[t] = q9_ty_point(t, pt);
     q9_shape(pt, N, Nx, Ne);
+    #pragma unroll
     for (int n = 0; n < 9; n++) { H.Nt[t][n] = N[n]; H.Nxt[t][n] = Nx[n]; H.Net[t][n] = Ne[n]; }
   } else {
     const int m = p - 9 - Q9_NTY;
     pt[0] = -1.0 + (m % 3); pt[1] = -1.0 + (m / 3);
     q9_shape(pt, N, Nx, Ne);
+    #pragma unroll
     for (int n = 0; n < 9; n++) { H.Nxn[m][n] = Nx[n]; H.Nen[m][n] = Ne[n]; }
   }
 }
 A2DS_HD void q9_interp3(const double w[9], const double *v, int ld, double f[3]) {
   f[0] = f[1] = f[2] = 0.0;
+  #pragma unroll
   for (int n = 0; n < 9; n++)
+    #pragma unroll
     for (int k = 0; k < 3; k++) f[k] += w[n] * v[ld * n + k];
 }
 
@@ -176,7 +186,9 @@ A2DS_HD double q9_frame_inverse(const double a[3], const double b[3], const doub
   return det;
 }
 A2DS_HD void q9_matmul_strict(const double A[9], const double B[9], double C[9]) {
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++)
       C[3 * i + j] = A2DS_ADD(A2DS_ADD(A2DS_MUL(A[3 * i], B[j]), A2DS_MUL(A[3 * i + 1], B[3 + j])),
                               A2DS_MUL(A[3 * i + 2], B[6 + j]));
@@ -186,10 +198,14 @@ A2DS_HD void q9_grad_strict(const double pt[2], const double *v, int ld, double 
   double na[3], nb[3], da[3], db[3];
   q9_lag(pt[0], na, da);
   q9_lag(pt[1], nb, db);
+  #pragma unroll
   for (int k = 0; k < 3; k++) gxi[k] = geta[k] = 0.0;
+  #pragma unroll
   for (int j = 0; j < 3; j++)
+    #pragma unroll
     for (int i = 0; i < 3; i++) {
       const double wx = A2DS_MUL(da[i], nb[j]), we = A2DS_MUL(na[i], db[j]);
+      #pragma unroll
       for (int k = 0; k < 3; k++) {
         gxi[k] = A2DS_ADD(gxi[k], A2DS_MUL(wx, v[ld * (3 * j + i) + k]));
         geta[k] = A2DS_ADD(geta[k], A2DS_MUL(we, v[ld * (3 * j + i) + k]));
@@ -223,6 +239,7 @@ A2DS_HD void q9_node(const CompData &c, Elem9 &E, int n) {
   E.etn[n] = drill_strain_state(T, S, uxi, ueta, th);
   double w[3];
   cross(t1, t2, w);
+  #pragma unroll
   for (int k = 0; k < 3; k++) {
     E.fn[3 * n + k] = fn[k];
     E.a1[3 * n + k] = 0.5 * (S[0] * t2[k] - S[1] * t1[k]);
@@ -244,6 +261,7 @@ A2DS_HD void q9_tying(Elem9 &E, const Shape9 &H, int t, bool nonlinear = false) 
   q9_interp3(Nx, E.q, 6, Uxi);
   q9_interp3(Ne, E.q, 6, Ueta);
   q9_interp3(N, E.dr, 3, d0);
+  #pragma unroll
   for (int k = 0; k < 3; k++) {
     E.tXxi[t][k] = Xxi[k]; E.tXeta[t][k] = Xeta[k]; E.tn0[t][k] = n0[k];
     E.tUxi[t][k] = Uxi[k]; E.tUeta[t][k] = Ueta[k]; E.td0[t][k] = d0[k];
@@ -281,15 +299,20 @@ A2DS_HD void q9_qp(const CompData &c, Elem9 &E, const Shape9 &H, int q, bool bil
   const double T[9] = {t1[0], t2[0], nn[0], t1[1], t2[1], nn[1], t1[2], t2[2], nn[2]};
   // A = Xd^-1 T;  Z = -(Xd^-1 Xdz) A with Xdz = [n,xi | n,eta | 0]
   double A[9], P[9];
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++)
       A[3 * i + j] = Xi[3 * i] * T[j] + Xi[3 * i + 1] * T[3 + j] + Xi[3 * i + 2] * T[6 + j];
+  #pragma unroll
   for (int i = 0; i < 3; i++) {
     P[3 * i] = Xi[3 * i] * nxi[0] + Xi[3 * i + 1] * nxi[1] + Xi[3 * i + 2] * nxi[2];
     P[3 * i + 1] = Xi[3 * i] * neta[0] + Xi[3 * i + 1] * neta[1] + Xi[3 * i + 2] * neta[2];
     P[3 * i + 2] = 0.0;
   }
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++) {
       E.qT[q][3 * i + j] = T[3 * i + j];
       E.qA[q][3 * i + j] = A[3 * i + j];
@@ -297,7 +320,9 @@ A2DS_HD void q9_qp(const CompData &c, Elem9 &E, const Shape9 &H, int q, bool bil
     }
   E.qw[q] = det * (q9_wt3(q % 3) * q9_wt3(q / 3));
   if (bil)
+  #pragma unroll
   for (int k = 0; k < 3; k++)
+    #pragma unroll
     for (int l = 0; l < 3; l++)
       E.qP[q][3 * k + l] = T[3 * k] * T[3 * l] + T[3 * k + 1] * T[3 * l + 1] + T[3 * k + 2] * T[3 * l + 2];
 }
@@ -321,7 +346,9 @@ A2DS_HD void q9_membrane_shear(const double A[9], const double g[5], double e[9]
   // gty = [[g11 g12 g13] [g12 g22 g23] [g13 g23 0]]
   const double G[9] = {g[0], g[2], g[4], g[2], g[1], g[3], g[4], g[3], 0.0};
   double W[9];
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++) W[3 * i + j] = G[3 * i] * A[j] + G[3 * i + 1] * A[3 + j] + G[3 * i + 2] * A[6 + j];
   const double e00 = A[0] * W[0] + A[3] * W[3] + A[6] * W[6];
   const double e01 = A[0] * W[1] + A[3] * W[4] + A[6] * W[7];
@@ -363,12 +390,15 @@ A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, const Shape9 &H, int q, do
   q9_interp3(Ne, E.dr, 3, d0eta);
   const double *T = E.qT[q], *A = E.qA[q], *Z = E.qZ[q];
   double u0x[3][2], u1x[3][2];   // columns 0, 1 of T^T (u0d A) and T^T (u1d A + u0d Z)
+  #pragma unroll
   for (int j = 0; j < 2; j++) {
     double v0[3], v1[3];
+    #pragma unroll
     for (int k = 0; k < 3; k++) {
       v0[k] = u0xi[k] * A[j] + u0eta[k] * A[3 + j] + d0[k] * A[6 + j];
       v1[k] = d0xi[k] * A[j] + d0eta[k] * A[3 + j] + u0xi[k] * Z[j] + u0eta[k] * Z[3 + j] + d0[k] * Z[6 + j];
     }
+    #pragma unroll
     for (int i = 0; i < 3; i++) {
       u0x[i][j] = T[i] * v0[0] + T[3 + i] * v0[1] + T[6 + i] * v0[2];
       u1x[i][j] = T[i] * v1[0] + T[3 + i] * v1[1] + T[6 + i] * v1[2];
@@ -380,6 +410,7 @@ A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, const Shape9 &H, int q, do
   }
   e[3] = u1x[0][0]; e[4] = u1x[1][1]; e[5] = u1x[0][1] + u1x[1][0];
   if (nonlinear) {
+    #pragma unroll
     for (int i = 0; i < 3; i++) {
       e[3] += u0x[i][0] * u1x[i][0];
       e[4] += u0x[i][1] * u1x[i][1];
@@ -387,17 +418,22 @@ A2DS_HD void q9_qp_state(const CompData &c, Elem9 &E, const Shape9 &H, int q, do
     }
   }
   double et = 0.0;
+  #pragma unroll
   for (int n = 0; n < 9; n++) et += N[n] * E.etn[n];
   e[8] = et;
+  #pragma unroll
   for (int k = 0; k < 9; k++) e[k] -= thermal * c.temperature * c.eth[k];
   double s[9];
   q9_stress(c.Cs, e, s);
+  #pragma unroll
   for (int k = 0; k < 9; k++) { s[k] *= E.qw[q]; E.sq[q][k] = s[k]; }
   if (!bil) return;
   // P = A Se A^T with Se = [[s0 s2 s7] [s2 s1 s6] [s7 s6 0]]: sum_i s_i e_i = sum P_mn gty_mn
   const double Se[9] = {s[0], s[2], s[7], s[2], s[1], s[6], s[7], s[6], 0.0};
   double W[9];
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++) W[3 * i + j] = A[3 * i] * Se[j] + A[3 * i + 1] * Se[3 + j] + A[3 * i + 2] * Se[6 + j];
   auto P = [&](int m, int n) { return W[3 * m] * A[3 * n] + W[3 * m + 1] * A[3 * n + 1] + W[3 * m + 2] * A[3 * n + 2]; };
   E.shat[q][0] = P(0, 0); E.shat[q][1] = P(1, 1); E.shat[q][2] = 2.0 * P(0, 1);
@@ -421,6 +457,7 @@ A2DS_HD double q9_ty_weight(int q, int t) {
 A2DS_HD void q9_sigt(Elem9 &E, const Shape9 &H, int t) {
   const int field = H.tfield[t];
   double s = 0.0;
+  #pragma unroll
   for (int q = 0; q < 9; q++) s += q9_ty_weight(q, t) * E.shat[q][field];
   E.sigt[t] = s;
 }
@@ -490,12 +527,14 @@ A2DS_HD void q9_bcol(const Elem9 &E, const Tab9 &Tb, const Shape9 &H, int q, int
     const double *f = &E.fn[3 * m];
     const int c = k - 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
     // t_i . (theta x fn) = theta . (fn x t_i)
+    #pragma unroll
     for (int i = 0; i < 3; i++) v[i] = f[c1] * T[3 * c2 + i] - f[c2] * T[3 * c1 + i];
   }
   Bk[3] = be0 * v[0];
   Bk[4] = be1 * v[1];
   Bk[5] = be1 * v[0] + be0 * v[1];
   double d = 0.0;
+  #pragma unroll
   for (int n = 0; n < 9; n++) d += H.Nq[q][n] * Tb.Dn[n][dof];
   Bk[8] = d;
   if (B1k) {
@@ -503,6 +542,7 @@ A2DS_HD void q9_bcol(const Elem9 &E, const Tab9 &Tb, const Shape9 &H, int q, int
     q9_membrane_shear(E.qA[q], g, B1k);
     const double *U0 = E.qU0[q], *U1 = E.qU1[q];
     double p0 = 0.0, p1 = 0.0, r0 = 0.0, r1 = 0.0;
+    #pragma unroll
     for (int i = 0; i < 3; i++) {
       p0 += v[i] * U0[2 * i]; p1 += v[i] * U0[2 * i + 1];
       r0 += v[i] * U1[2 * i]; r1 += v[i] * U1[2 * i + 1];
@@ -526,6 +566,7 @@ A2DS_HD void q9_bcol(const Elem9 &E, const Tab9 &Tb, const Shape9 &H, int q, int
 // three dofs of kind ha (0 displacement, 1 rotation) of node ma.
 A2DS_HD void q9_geo_quadrant(const Elem9 &E, const Shape9 &H, int ma, int mb, int ha, int hb, double out[9]) {
   double M[9];
+  #pragma unroll
   for (int k = 0; k < 9; k++) M[k] = 0.0;
   // tying part: g11, g22, g12 couple displacements; g23, g13 couple a rotation with a displacement
   if (!(ha == 1 && hb == 1)) {
@@ -561,6 +602,7 @@ A2DS_HD void q9_geo_quadrant(const Elem9 &E, const Shape9 &H, int ma, int mb, in
     else { alb0 = Nb * A[6]; alb1 = Nb * A[7]; beb0 = ub0 + Nb * Z[6]; beb1 = ub1 + Nb * Z[7]; }
     const double cf = s3 * (ala0 * beb0 + alb0 * bea0) + s4 * (ala1 * beb1 + alb1 * bea1) +
                       s5 * (alb0 * bea1 + beb0 * ala1 + ala0 * beb1 + bea0 * alb1);
+    #pragma unroll
     for (int k = 0; k < 9; k++) M[k] += cf * P[k];
   }
   // D[k][c] = (e_c x f)[k] = eps_{k c l} f_l
@@ -568,20 +610,28 @@ A2DS_HD void q9_geo_quadrant(const Elem9 &E, const Shape9 &H, int ma, int mb, in
   const double Da[9] = {0.0, fa[2], -fa[1], -fa[2], 0.0, fa[0], fa[1], -fa[0], 0.0};
   const double Db[9] = {0.0, fb[2], -fb[1], -fb[2], 0.0, fb[0], fb[1], -fb[0], 0.0};
   double R[9];   // M D_b for a rotation column kind, else M
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++)
       R[3 * i + j] = hb == 1 ? M[3 * i] * Db[j] + M[3 * i + 1] * Db[3 + j] + M[3 * i + 2] * Db[6 + j] : M[3 * i + j];
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++)
       out[3 * i + j] = ha == 1 ? Da[i] * R[j] + Da[3 + i] * R[3 + j] + Da[6 + i] * R[6 + j] : R[3 * i + j];
 }
 // the whole 6 x 6 block (host emulation): blk[36] row major, rows = dofs of node ma
 A2DS_HD void q9_geo_pair(const Elem9 &E, const Shape9 &H, int ma, int mb, double blk[36]) {
+  #pragma unroll
   for (int ha = 0; ha < 2; ha++)
+    #pragma unroll
     for (int hb = 0; hb < 2; hb++) {
       double o[9];
       q9_geo_quadrant(E, H, ma, mb, ha, hb, o);
+      #pragma unroll
       for (int i = 0; i < 3; i++)
+        #pragma unroll
         for (int j = 0; j < 3; j++) blk[6 * (3 * ha + i) + 3 * hb + j] = o[3 * i + j];
     }
 }
@@ -592,11 +642,14 @@ A2DS_HD void q9_geo_pair(const Elem9 &E, const Shape9 &H, int ma, int mb, double
 // Gauss points; blk[36] row major, rows = dofs of node ma.
 A2DS_HD void q9_mass_pair(const CompData &c, const Elem9 &E, const Shape9 &H, int ma, int mb, double blk[36]) {
   double cf = 0.0;
+  #pragma unroll
   for (int q = 0; q < 9; q++) cf += E.qw[q] * H.Nq[q][ma] * H.Nq[q][mb];
   const double *fa = &E.fn[3 * ma], *fb = &E.fn[3 * mb];
   const double Da[9] = {0.0, fa[2], -fa[1], -fa[2], 0.0, fa[0], fa[1], -fa[0], 0.0};
   const double Db[9] = {0.0, fb[2], -fb[1], -fb[2], 0.0, fb[0], fb[1], -fb[0], 0.0};
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++) {
       blk[6 * i + j] = (i == j) ? cf * c.mom[0] : 0.0;
       blk[6 * i + 3 + j] = cf * c.mom[1] * Db[3 * i + j];
@@ -615,6 +668,7 @@ A2DS_HD void q9_node_normal(Elem9 &E, int n) {
     const double inv = 1.0 / nrm;
     fn[0] = A2DS_MUL(fn[0], inv); fn[1] = A2DS_MUL(fn[1], inv); fn[2] = A2DS_MUL(fn[2], inv);
   }
+  #pragma unroll
   for (int k = 0; k < 3; k++) E.fn[3 * n + k] = fn[k];
 }
 A2DS_HD void q9_qp_det(Elem9 &E, const Shape9 &H, int q) {
