@@ -1700,6 +1700,8 @@ static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int w
 static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("assemble: mesh or nodes not set");
+  if (c->npe != 4 && c->scatter_mode != A2DS_SCATTER_ATOMIC)
+    return fail("assemble: 9-node elements are assembled with the atomic scatter only");
   if (build_lists(c)) return 1;
   const int what = rq.what & 7;
   const bool RES = rq.what & 1, KM = (rq.what & 2) != 0, GM = (rq.what & 4) != 0,
@@ -1707,8 +1709,6 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   const int kmat = rq.kmat, gmat = rq.gmat, mmat = rq.mmat;
   // inertial residual M * uddot (TACSShellElement.h:410-447) once second derivatives are set
   const bool MRES = RES && c->udd != nullptr;
-  if (c->npe != 4 && c->scatter_mode != A2DS_SCATTER_ATOMIC)
-    return fail("assemble: 9-node elements are assembled with the atomic scatter only");
   if (KM && check_mat(c, kmat)) return 1;
   if (GM && check_mat(c, gmat)) return 1;
   if (MM && check_mat(c, mmat)) return 1;

@@ -169,7 +169,11 @@ def _cpu_reference_rate(nx, reps, threads=None, warmup=0, aggregate=False):
     u = np.zeros((n, 6))
     u[ra.new_nodes] = a2ds.meshes.seeded_state(np.arange(n), 1e-5)
     ra.set_state(u)
-    km = ra.mat_create(1); gm = ra.mat_create(1)   # TACSSchurMat, as the shipped examples
+    # TACSSchurMat as the shipped examples use (mechBuckling.cpp:118-120), created with the local
+    # nodes in natural order: the default AMD pass over the interior block is set-up, not
+    # assembly, and takes ~5 minutes at 1 M nodes (16 s at 160 k) — the assembly path and its
+    # measured rate are the same (oracle/ref_driver.cpp, refdrv_mat_create kind 2)
+    km = ra.mat_create(2); gm = ra.mat_create(2)
     ra.set_threads(threads)
     for _ in range(warmup):
         ra.time(1, km); ra.time(3, gm)
@@ -182,7 +186,7 @@ def _cpu_reference_rate(nx, reps, threads=None, warmup=0, aggregate=False):
     how = f"{reps} timed passes after {warmup} warm-up" if aggregate else f"median of {reps}"
     return dict(value=len(conn) / t, unit="elements/s", cores=threads, kind="reference",
                 sample=f"plate {nx}x{nx} ({len(conn)} elements), {how}: "
-                       f"assembleJacobian(res+K)+assembleMatType(G) into TACSSchurMat, "
+                       f"assembleJacobian(res+K)+assembleMatType(G) into TACSSchurMat (natural order), "
                        f"{threads} pthreads on {cores} host cores",
                 seconds_per_pass=t, n_elems=len(conn))
 

@@ -346,10 +346,14 @@ int refdrv_set_temperature(void *h, double T) {
 int refdrv_mat_create(void *h, int kind) {
   RefCtx *c = (RefCtx *)h;
   RefMat m;
-  m.kind = kind;
+  m.kind = kind == 2 ? 1 : kind;   /* both Schur flavours */
   m.blk[0] = m.blk[1] = m.blk[2] = m.blk[3] = NULL;
-  if (kind == 1) {
-    TACSSchurMat *s = c->assembler->createSchurMat();
+  if (kind == 1 || kind == 2) {
+    /* 1: as the shipped examples call it (TACS_AMD_ORDER, mechBuckling.cpp:118-120); 2: the same
+       matrix class with the local nodes left in their natural order — no AMD pass over the
+       interior block, which at 1 M nodes takes minutes and is set-up, not assembly */
+    TACSSchurMat *s = kind == 1 ? c->assembler->createSchurMat()
+                                : c->assembler->createSchurMat(TACSAssembler::NATURAL_ORDER);
     s->incref();
     s->getBCSRMat(&m.blk[0], &m.blk[1], &m.blk[2], &m.blk[3]);
     m.mat = s;

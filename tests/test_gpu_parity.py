@@ -1011,3 +1011,33 @@ def test_quad9_mixed_classes_mass_and_combo_vs_oracle(a2ds, orc):
             combo[j] = np.eye(6) if cols[j] == nd else 0.0
     assert relmax(asm.mat_values(k), combo) < MAT_TOL
     asm.close()
+
+
+def test_quad9_empty_and_single_element(a2ds, orc):
+    """edge cases of the 9-node path: no elements, and one element (a single thread block,
+    the producer's look-ahead finds the list exhausted immediately)"""
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(np.zeros((0, 9), dtype=np.int32), 5, order=3)
+    asm.set_nodes(np.zeros((5, 3)))
+    Cs, eth = a2ds.iso_shell_tables()
+    asm.set_components(Cs[None], eth[None])
+    asm.set_state(np.zeros((5, 6)))
+    k = asm.create_mat()
+    assert asm.mat_nnz(k) == 0
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, k)
+    assert not r.any()
+    asm.close()
+    from helpers import random_elements9
+    X, q = random_elements9(1, seed=12)
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(np.arange(9, dtype=np.int32)[None], 9, order=3)
+    asm.set_nodes(X[0]); asm.set_components(Cs[None], eth[None]); asm.set_state(q[0])
+    k = asm.create_mat(); g = asm.create_mat()
+    r = asm.assembleAll(k, g)
+    comp = orc.make_comp(0, Cs, eth)
+    r_o, k_o = orc.jacobian(comp, X[0].ravel(), q[0].ravel(), order=3)
+    g_o = orc.mat_type(comp, 1, X[0].ravel(), q[0].ravel(), order=3)
+    K = asm.mat_values(k).reshape(9, 9, 6, 6).transpose(0, 2, 1, 3).reshape(54, 54)
+    G = asm.mat_values(g).reshape(9, 9, 6, 6).transpose(0, 2, 1, 3).reshape(54, 54)
+    assert relmax(r.ravel(), r_o) < RES_TOL and relmax(K, k_o) < MAT_TOL and relmax(G, g_o) < MAT_TOL
+    asm.close()

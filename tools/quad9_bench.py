@@ -83,7 +83,7 @@ def main():
             ur = np.zeros((len(X_r), 6))
             ur[ra.new_nodes] = a2ds.meshes.seeded_state(np.arange(len(X_r)), 1e-5)
             ra.set_state(ur)
-            km = ra.mat_create(1)
+            km = ra.mat_create(2)
             threads = min(16, os.cpu_count() or 1)
             ra.set_threads(threads)
             ra.time(1, km)
