@@ -578,7 +578,7 @@ __device__ __forceinline__ void stage_tiles_t(double *E, const double (&acc)[6][
 }
 // scatter of the staged blocks: as scatter_matrix, on the block-major tile
 #ifndef A2DS_OFF_LDS
-#define A2DS_OFF_LDS 0   // 1: block offsets of the scatter by broadcast LDS.128 from the gathered table instead of shuffles
+#define A2DS_OFF_LDS 1   // block offsets of the scatter by broadcast LDS.128 from the gathered table (0: by shuffles; measured +0.3 ... 1 %)
 #endif
 __device__ __forceinline__ void scatter_matrix_t(const double *E, double *vals, int off16, int lane,
                                                  const int *offrow = nullptr) {
