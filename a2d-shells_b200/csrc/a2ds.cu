@@ -126,6 +126,11 @@ struct a2ds_ctx {
   // residual rows go back (on d2h_stream) as soon as the last range that adds to them is done
   static const int MAX_CHUNKS = 16, ROWS_PER_CHUNK = 4;   // residual row chunks are finer than the ranges
   cudaStream_t d2h_stream = nullptr;
+  // ... and the matrices are zeroed row range by row range on zero_stream, ahead of the element
+  // range that needs them, next to the kernel of the range before (natural-order matrices)
+  cudaStream_t zero_stream = nullptr;
+  cudaEvent_t ev_zero_go = nullptr, ev_z[MAX_CHUNKS + 1] = {};
+  bool stream_zero = true;       // A2DS_STREAM_ZERO=0: zero the matrices in front of the first range
   cudaEvent_t ev_up[MAX_CHUNKS] = {}, ev_row[MAX_CHUNKS * ROWS_PER_CHUNK] = {};
   int stream_chunks = 8;         // A2DS_STREAM_CHUNKS (1: off)
   int stream_min_elems = 200000; // A2DS_STREAM_MIN_ELEMS: smaller meshes are not worth the launch tails
@@ -233,6 +238,10 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->zero_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_zero_go, cudaEventDisableTiming));
+  for (cudaEvent_t &e : c->ev_z) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (const char *env = getenv("A2DS_STREAM_ZERO")) c->stream_zero = atoi(env) != 0;
   for (int k = 0; k < a2ds_ctx::MAX_CHUNKS; k++) CU(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming));
   for (cudaEvent_t &e : c->ev_row) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (const char *env = getenv("A2DS_STREAM_CHUNKS"))
@@ -268,6 +277,7 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->d2h_stream);
+  cudaStreamSynchronize(c->zero_stream);
   cudaStreamSynchronize(c->stream);
   for (auto &m : c->mats)
     for (void *p : m.owned) cudaFree(p);
@@ -284,6 +294,9 @@ extern "C" int a2ds_destroy(a2ds_ctx *c) {
   cudaEventDestroy(c->ev_state); cudaEventDestroy(c->ev_used);
   for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_row) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_z) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_zero_go);
+  cudaStreamDestroy(c->zero_stream);
   cudaStreamDestroy(c->d2h_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
@@ -297,6 +310,7 @@ extern "C" int a2ds_synchronize(a2ds_ctx *c) {
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->copy_stream));
   CU(cudaStreamSynchronize(c->d2h_stream));
+  CU(cudaStreamSynchronize(c->zero_stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
   A2DS_CATCH(a2ds_synchronize)
@@ -1605,7 +1619,7 @@ static void build_stream_plan(a2ds_ctx *c, bool ghost_last, StreamPlan &pl) {
 struct AsmReq;
 // the element launches, the residual halo, its boundary conditions and its way back of a
 // streamed assembly (see a2ds_ctx::d2h_stream); the outputs are zeroed already
-static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int what);
+static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int what, bool zero_mats);
 
 // One assembly request.  what: bit 0 residual, bit 1 tangent, bit 2 geometric stiffness,
 // bit 3 mass matrix (into mmat, which may be the tangent matrix: gamma term of the Jacobian).
@@ -1629,7 +1643,7 @@ static int apply_mat_bcs(a2ds_ctx *c, int mat) {
 }
 
 
-static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int what) {
+static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int what, bool zero_mats) {
   const bool RES = what & 1;
   const bool ghost_last = c->halo_pending;
   StreamPlan &pl = c->splan[ghost_last ? 1 : 0];
@@ -1663,10 +1677,37 @@ static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int w
     return 0;
   };
   const KParams base = p;
+  if (zero_mats) {
+    // all zeroing is queued now, in the order the element ranges need it: block rows up to the
+    // highest node of range `at` are clean once ev_z[at] has fired; it runs next to the kernels
+    // of the first ranges instead of in front of them
+    CU(cudaEventRecord(c->ev_zero_go, c->stream));   // after everything that still reads the matrices
+    CU(cudaStreamWaitEvent(c->zero_stream, c->ev_zero_go, 0));
+    int zeroed = 0;
+    auto zero_rows = [&](int hi) -> int {
+      if (hi <= zeroed) return 0;
+      for (int mid : {(what & 2) ? rq.kmat : -1, (what & 4) ? rq.gmat : -1}) {
+        if (mid < 0) continue;
+        MatrixRec &m = c->mats[mid];
+        const int *rowp = m.h_rowp[0]->data();
+        const size_t b0 = (size_t)rowp[zeroed], b1 = (size_t)rowp[hi];
+        if (b1 > b0) CU(cudaMemsetAsync(m.A + 36 * b0, 0, (b1 - b0) * 36 * sizeof(double), c->zero_stream));
+      }
+      zeroed = hi;
+      return 0;
+    };
+    for (int at = 0; at < C; at++) {
+      if (zero_rows(std::min(c->n_nodes, pl.max_node[pl.order[at]] + 1))) return 1;
+      CU(cudaEventRecord(c->ev_z[at], c->zero_stream));
+    }
+    if (zero_rows(c->n_nodes)) return 1;   // rows no element adds to
+    CU(cudaEventRecord(c->ev_z[C], c->zero_stream));
+  }
   for (int at = 0; at < C; at++) {
     const int k = pl.order[at];
     const int e0 = pl.e0[k], e1 = pl.e0[k + 1];
     const bool ghost = pl.max_node[k] >= c->n_owned;
+    if (zero_mats) CU(cudaStreamWaitEvent(c->stream, c->ev_z[at], 0));
     if (pending) {
       // rows this range reads: up to its highest node, or everything that is coming
       const int need = (ghost && !halo_done) ? c->up_rows : std::min(pl.max_node[k] + 1, c->up_rows);
@@ -1688,6 +1729,7 @@ static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int w
     }
     if (finish_rows(at)) return 1;
   }
+  if (zero_mats) CU(cudaStreamWaitEvent(c->stream, c->ev_z[C], 0));
   if (pending && waited < c->up_chunks - 1) CU(cudaStreamWaitEvent(c->stream, c->ev_state, 0));
   c->state_pending = false;
   if (!halo_done && halo_exchange(c, c->u, false)) return 1;
@@ -1715,6 +1757,20 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   if (KM && GM && kmat == gmat && what == 7)
     return fail("assemble: tangent and geometric matrices must differ");
   c->pz_K = c->pz_G = nullptr;
+  // streamed: one class, natural element order, atomic scatter, host I/O in the step
+  int only_cls = -1, n_nonempty = 0;
+  for (int cls = 0; cls < 4; cls++)
+    if (c->list_len[cls][0] > 0) { n_nonempty++; only_cls = cls; }
+  const bool streamed = c->npe == 4 && A2DS_ZWAIT == 0 && c->stream_chunks > 1 && rq.zero && rq.finish &&
+                        c->n_colors == 1 && n_nonempty == 1 &&
+                        c->list_dev[only_cls][0] == nullptr && c->n_elems >= c->stream_min_elems &&
+                        !MM && !MRES && what != 0 &&
+                        ((c->state_pending && c->up_chunks > 1) || (rq.res_host && RES));
+  // ... and then natural-order matrices (block rows in node order, host row pointer at hand)
+  // are zeroed range by range next to the kernels instead of in front of them
+  auto natural = [&](int mat) { return c->mats[mat].n_blocks == 1 && c->mats[mat].shared_hash != nullptr; };
+  const bool zero_streamed = streamed && c->stream_zero && (KM || GM) && (!KM || natural(kmat)) &&
+                             (!GM || natural(gmat));
   if (rq.zero) {
     c->last_launches = 0;
     CU(cudaEventRecord(c->ev0, c->stream));
@@ -1732,7 +1788,7 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     if (ikz) {
       if (KM) { c->pz_K = c->mats[kmat].A; c->pz_nK = c->mats[kmat].total; }
       if (GM) { c->pz_G = c->mats[gmat].A; c->pz_nG = c->mats[gmat].total; }
-    } else {
+    } else if (!zero_streamed) {
       if (KM) CU(cudaMemsetAsync(c->mats[kmat].A, 0, c->mats[kmat].total * 36 * sizeof(double), c->stream));
       if (GM) CU(cudaMemsetAsync(c->mats[gmat].A, 0, c->mats[gmat].total * 36 * sizeof(double), c->stream));
     }
@@ -1740,15 +1796,6 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
       CU(cudaMemsetAsync(c->mats[mmat].A, 0, c->mats[mmat].total * 36 * sizeof(double), c->stream));
     c->last_launches += (RES ? 1 : 0) + (ikz ? 0 : (KM ? 1 : 0) + (GM ? 1 : 0)) + (MM && !(KM && mmat == kmat) ? 1 : 0);
   }
-
-  // streamed: one class, natural element order, atomic scatter, host I/O in the step
-  int only_cls = -1, n_nonempty = 0;
-  for (int cls = 0; cls < 4; cls++)
-    if (c->list_len[cls][0] > 0) { n_nonempty++; only_cls = cls; }
-  const bool streamed = c->npe == 4 && c->stream_chunks > 1 && rq.zero && rq.finish && c->n_colors == 1 && n_nonempty == 1 &&
-                        c->list_dev[only_cls][0] == nullptr && c->n_elems >= c->stream_min_elems &&
-                        !MM && !MRES && what != 0 && !c->pz_K && !c->pz_G &&
-                        ((c->state_pending && c->up_chunks > 1) || (rq.res_host && RES));
 
   KParams p;
   memset(&p, 0, sizeof(p));
@@ -1760,7 +1807,7 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
 
   CU(cudaEventRecord(c->evk0, c->stream));
   if (streamed) {
-    if (run_streamed(c, rq, p, only_cls, what)) return 1;
+    if (run_streamed(c, rq, p, only_cls, what, zero_streamed)) return 1;
   } else {
     if (state_wait(c)) return 1;  // the upload overlapped the zeroing above
     for (int col = 0; col < c->n_colors; col++) {
