@@ -131,6 +131,7 @@ struct a2ds_ctx {
   cudaStream_t zero_stream = nullptr;
   cudaEvent_t ev_zero_go = nullptr, ev_z[MAX_CHUNKS + 1] = {};
   bool stream_zero = true;       // A2DS_STREAM_ZERO=0: zero the matrices in front of the first range
+  bool stream_resident = false;  // A2DS_STREAM_RESIDENT=1: steps without host I/O take the element ranges too (for the zeroing)
   cudaEvent_t ev_up[MAX_CHUNKS] = {}, ev_row[MAX_CHUNKS * ROWS_PER_CHUNK] = {};
   int stream_chunks = 8;         // A2DS_STREAM_CHUNKS (1: off)
   int stream_min_elems = 200000; // A2DS_STREAM_MIN_ELEMS: smaller meshes are not worth the launch tails
@@ -250,6 +251,7 @@ extern "C" int a2ds_create(int device, a2ds_ctx **out) {
   CU(cudaEventCreateWithFlags(&c->ev_zero_go, cudaEventDisableTiming));
   for (cudaEvent_t &e : c->ev_z) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (const char *env = getenv("A2DS_STREAM_ZERO")) c->stream_zero = atoi(env) != 0;
+  if (const char *env = getenv("A2DS_STREAM_RESIDENT")) c->stream_resident = atoi(env) != 0;
   for (int k = 0; k < a2ds_ctx::MAX_CHUNKS; k++) CU(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming));
   for (cudaEvent_t &e : c->ev_row) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (const char *env = getenv("A2DS_STREAM_CHUNKS"))
@@ -1767,16 +1769,18 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   int only_cls = -1, n_nonempty = 0;
   for (int cls = 0; cls < 4; cls++)
     if (c->list_len[cls][0] > 0) { n_nonempty++; only_cls = cls; }
+  // ... and then natural-order matrices (block rows in node order, host row pointer at hand)
+  // are zeroed range by range next to the kernels instead of in front of them; with
+  // stream_resident a step without host I/O is split as well when it has such matrices to zero
+  auto natural = [&](int mat) { return c->mats[mat].n_blocks == 1 && c->mats[mat].shared_hash != nullptr; };
+  const bool zero_natural = c->stream_zero && (KM || GM) && (!KM || natural(kmat)) && (!GM || natural(gmat));
   const bool streamed = c->npe == 4 && A2DS_ZWAIT == 0 && c->stream_chunks > 1 && rq.zero && rq.finish &&
                         c->n_colors == 1 && n_nonempty == 1 &&
                         c->list_dev[only_cls][0] == nullptr && c->n_elems >= c->stream_min_elems &&
                         !MM && !MRES && what != 0 &&
-                        ((c->state_pending && c->up_chunks > 1) || (rq.res_host && RES));
-  // ... and then natural-order matrices (block rows in node order, host row pointer at hand)
-  // are zeroed range by range next to the kernels instead of in front of them
-  auto natural = [&](int mat) { return c->mats[mat].n_blocks == 1 && c->mats[mat].shared_hash != nullptr; };
-  const bool zero_streamed = streamed && c->stream_zero && (KM || GM) && (!KM || natural(kmat)) &&
-                             (!GM || natural(gmat));
+                        ((c->state_pending && c->up_chunks > 1) || (rq.res_host && RES) ||
+                         (c->stream_resident && zero_natural));
+  const bool zero_streamed = streamed && zero_natural;
   if (rq.zero) {
     c->last_launches = 0;
     CU(cudaEventRecord(c->ev0, c->stream));

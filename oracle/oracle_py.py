@@ -148,3 +148,43 @@ def assemble(op, conn, elem_comp, comps, X, u, rowp, cols, bc_nodes=None, bc_var
                                      _p(np.ascontiguousarray(cols, dtype=np.int32)), _p(res), _p(A))
     assert miss == 0, "element block missing from the pattern"
     return res, A
+
+
+def pattern_dep(n_nodes, conn, dep_ptr, dep_conn, order=2):
+    """pattern of a mesh with dependent nodes (connectivity entries -(d + 1))"""
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, order * order)
+    dp = np.ascontiguousarray(dep_ptr, dtype=np.int32); dc = np.ascontiguousarray(dep_conn, dtype=np.int32)
+    rowp = np.zeros(n_nodes + 1, dtype=np.int32)
+    f = _fn("pattern_dep", order)
+    nnz = f(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(dp), _p(dc), _p(rowp), None)
+    cols = np.zeros(nnz, dtype=np.int32)
+    f(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(dp), _p(dc), _p(rowp), _p(cols))
+    return rowp, cols
+
+
+def assemble_dep(op, conn, elem_comp, comps, X, u, dep, rowp, cols, bc_nodes=None, bc_vars=None,
+                 bc_vals=None, alpha=1.0, gamma=0.0, udd=None, order=2):
+    """assemble() on a mesh with dependent nodes, dep = (dep_ptr, dep_conn, dep_weights);
+    X, u, udd and the residual have one row per independent node"""
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, order * order)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 6)
+    n = X.shape[0]
+    dp = np.ascontiguousarray(dep[0], dtype=np.int32); dc = np.ascontiguousarray(dep[1], dtype=np.int32)
+    dw = np.ascontiguousarray(dep[2], dtype=np.float64)
+    arr = (Comp * len(comps))(*comps)
+    ec = np.ascontiguousarray(elem_comp, dtype=np.int32)
+    nb = 0 if bc_nodes is None else len(bc_nodes)
+    bn = np.ascontiguousarray(bc_nodes if nb else np.zeros(0), dtype=np.int32)
+    bv = np.ascontiguousarray(bc_vars if nb else np.zeros(0), dtype=np.int32)
+    bx = np.ascontiguousarray(bc_vals if nb else np.zeros(0), dtype=np.float64)
+    res = np.zeros((n, 6)) if op <= 1 else None
+    A = np.zeros((len(cols), 6, 6)) if op >= 1 else None
+    udd = None if udd is None else np.ascontiguousarray(udd, dtype=np.float64).reshape(-1, 6)
+    miss = _fn("assemble_dep", order)(
+        C.c_int(op), C.c_double(alpha), C.c_double(gamma), C.c_int(n), C.c_int(conn.shape[0]),
+        _p(conn), _p(ec), arr, _p(X), _p(u), _p(udd), C.c_int(len(dp) - 1), _p(dp), _p(dc), _p(dw),
+        C.c_int(nb), _p(bn), _p(bv), _p(bx), _p(np.ascontiguousarray(rowp, dtype=np.int32)),
+        _p(np.ascontiguousarray(cols, dtype=np.int32)), _p(res), _p(A))
+    assert miss == 0, "element block missing from the pattern"
+    return res, A

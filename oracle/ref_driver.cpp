@@ -208,6 +208,17 @@ void *refdrv_create_n(int nodes_per_elem, int n_nodes, int n_elems, const int *c
                       const int *elem_comp, const double *X, int n_bc, const int *bc_nodes,
                       const int *bc_ptr, const int *bc_vars, const double *bc_vals, int n_comp,
                       const double *comp_props, int transform_kind, const double *axis);
+/* dependent nodes for the NEXT refdrv_create / refdrv_create_n call
+   (TACSCreator::setDependentNodes, src/TACSCreator.h:65-67): connectivity entries -(d + 1) */
+static std::vector<int> g_dep_ptr, g_dep_conn;
+static std::vector<double> g_dep_w;
+int refdrv_next_dependent_nodes(int n_dep, const int *dep_ptr, const int *dep_conn,
+                                const double *dep_w) {
+  g_dep_ptr.assign(dep_ptr, dep_ptr + n_dep + 1);
+  g_dep_conn.assign(dep_conn, dep_conn + dep_ptr[n_dep]);
+  g_dep_w.assign(dep_w, dep_w + dep_ptr[n_dep]);
+  return 0;
+}
 void *refdrv_create(int n_nodes, int n_elems, const int *conn, const int *elem_comp,
                     const double *X, int n_bc, const int *bc_nodes, const int *bc_ptr,
                     const int *bc_vars, const double *bc_vals, int n_comp,
@@ -237,6 +248,11 @@ void *refdrv_create_n(int nodes_per_elem, int n_nodes, int n_elems, const int *c
   for (int i = 0; i <= n_elems; i++) ptr[i] = nodes_per_elem * i;
   c->creator->setGlobalConnectivity(n_nodes, n_elems, ptr.data(), conn, elem_comp);
   c->creator->setBoundaryConditions(n_bc, bc_nodes, bc_ptr, bc_vars, bc_vals);
+  if (g_dep_ptr.size() > 1) {
+    c->creator->setDependentNodes((int)g_dep_ptr.size() - 1, g_dep_ptr.data(), g_dep_conn.data(),
+                                  g_dep_w.data());
+    g_dep_ptr.clear(); g_dep_conn.clear(); g_dep_w.clear();
+  }
   c->creator->setNodes(X);
 
   TACSShellTransform *tr = make_transform(transform_kind, axis);
@@ -283,6 +299,20 @@ int refdrv_get_conn(void *h, int *conn) {
   c->assembler->getElementConnectivity(&ptr, &cn);
   memcpy(conn, cn, (size_t)ptr[c->n_elems] * sizeof(int));
   return 0;
+}
+
+/* dependent nodes as the assembler holds them (reference numbering); returns their number */
+int refdrv_get_dep(void *h, int *ptr, int *conn, double *w) {
+  RefCtx *c = (RefCtx *)h;
+  TACSBVecDepNodes *d = c->assembler->getBVecDepNodes();
+  if (!d) return 0;
+  const int *dp, *dc;
+  const double *dw;
+  int nd = d->getDepNodes(&dp, &dc, &dw);
+  if (ptr) memcpy(ptr, dp, (nd + 1) * sizeof(int));
+  if (conn) memcpy(conn, dc, dp[nd] * sizeof(int));
+  if (w) memcpy(w, dw, dp[nd] * sizeof(double));
+  return nd;
 }
 
 int refdrv_get_nodes(void *h, double *X) {

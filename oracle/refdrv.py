@@ -109,8 +109,15 @@ class RefAssembler:
     """Reference TACSAssembler built through TACSCreator for a quad mesh."""
 
     def __init__(self, conn, X, elem_comp, comp_props, bc_nodes=None, bc_vars=None, bc_vals=None,
-                 transform=0, axis=(1.0, 0.0, 0.0), nodes_per_elem=4):
+                 transform=0, axis=(1.0, 0.0, 0.0), nodes_per_elem=4, dep=None):
+        """dep = (dep_ptr, dep_conn, dep_weights): dependent nodes (TACSCreator::setDependentNodes);
+        connectivity entries -(d + 1) refer to dependent node d"""
         L = lib()
+        if dep is not None:
+            dp = np.ascontiguousarray(dep[0], dtype=np.int32)
+            dc = np.ascontiguousarray(dep[1], dtype=np.int32)
+            dw = np.ascontiguousarray(dep[2], dtype=np.float64)
+            L.refdrv_next_dependent_nodes(C.c_int(len(dp) - 1), _p(dp), _p(dc), _p(dw))
         L.refdrv_create_n.restype = C.c_void_p
         self.nodes_per_elem = nodes_per_elem   # 9: TACSQuad9Shell components (props[0] = 2, 3)
         conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, nodes_per_elem)
@@ -145,6 +152,17 @@ class RefAssembler:
         c = np.zeros((self.n_elems, self.nodes_per_elem), dtype=np.int32)
         lib().refdrv_get_conn(self.h, _p(c))
         return c
+
+    def dep(self):
+        """(dep_ptr, dep_conn, dep_weights) in the reference's numbering, or None"""
+        nd = lib().refdrv_get_dep(self.h, None, None, None)
+        if nd == 0:
+            return None
+        ptr = np.zeros(nd + 1, dtype=np.int32)
+        lib().refdrv_get_dep(self.h, _p(ptr), None, None)
+        cn = np.zeros(ptr[-1], dtype=np.int32); w = np.zeros(ptr[-1])
+        lib().refdrv_get_dep(self.h, _p(ptr), _p(cn), _p(w))
+        return ptr, cn, w
 
     def nodes(self):
         X = np.zeros((self.n_nodes, 3))

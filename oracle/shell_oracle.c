@@ -37,6 +37,8 @@
 #define oracle_pattern oracle9_pattern
 #define oracle_assemble oracle9_assemble
 #define oracle_assemble_dyn oracle9_assemble_dyn
+#define oracle_pattern_dep oracle9_pattern_dep
+#define oracle_assemble_dep oracle9_assemble_dep
 #endif
 #include "shell_oracle.h"
 
@@ -881,5 +883,175 @@ int oracle_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_e
             if (bc_vars[b] & (1 << ii)) a[7 * ii] = 1.0;
       }
     }
+  return missing;
+}
+
+/* ---- dependent nodes --------------------------------------------------------
+   A connectivity entry -(d + 1) refers to dependent node d, whose values are the weighted sum
+   of the independent nodes dep_conn[dep_ptr[d] .. dep_ptr[d + 1]) (TACSAssembler::setDependentNodes,
+   src/TACSAssembler.cpp:716-775). */
+
+/* independent nodes of an element with their weights: the varp / vars / weights arrays of
+   TACSAssembler::addMatValues (src/TACSAssembler.h:485-505) */
+static int expand_nodes(const int *nd, const int *dep_ptr, const int *dep_conn,
+                        const double *dep_w, int *varp, int *vars, double *weights) {
+  int k = 0;
+  varp[0] = 0;
+  for (int i = 0; i < NN; i++) {
+    if (nd[i] >= 0) {
+      weights[k] = 1.0; vars[k] = nd[i]; k++;
+    } else {
+      int dep = -nd[i] - 1;
+      for (int j = dep_ptr[dep]; j < dep_ptr[dep + 1]; j++, k++) {
+        weights[k] = dep_w[j]; vars[k] = dep_conn[j];
+      }
+    }
+    varp[i + 1] = k;
+  }
+  return k;
+}
+
+/* TACSAssembler::computeLocalNodeToNodeCSR with dependent nodes (src/TACSAssembler.cpp:1839-1935:
+   every independent node behind an element couples to every other one), sorted and unique */
+int oracle_pattern_dep(int n_nodes, int n_elems, const int *conn, const int *dep_ptr,
+                       const int *dep_conn, int *rowp, int *cols) {
+  /* independent nodes behind every element (nodeCount of the reference, :1858-1875) */
+  int *eptr = (int *)malloc(sizeof(int) * ((size_t)n_elems + 1));
+  eptr[0] = 0;
+  for (int e = 0; e < n_elems; e++) {
+    int n = 0;
+    for (int i = 0; i < NN; i++) {
+      int v = conn[NN * e + i];
+      n += v >= 0 ? 1 : dep_ptr[-v] - dep_ptr[-v - 1];
+    }
+    eptr[e + 1] = eptr[e] + n;
+  }
+  int *vars = (int *)malloc(sizeof(int) * (size_t)(eptr[n_elems] > 0 ? eptr[n_elems] : 1));
+  for (int e = 0, k = 0; e < n_elems; e++)
+    for (int i = 0; i < NN; i++) {
+      int v = conn[NN * e + i];
+      if (v >= 0) vars[k++] = v;
+      else for (int j = dep_ptr[-v - 1]; j < dep_ptr[-v]; j++) vars[k++] = dep_conn[j];
+    }
+  int *cnt = (int *)calloc((size_t)n_nodes + 1, sizeof(int));
+  for (int e = 0; e < n_elems; e++)
+    for (int a = eptr[e]; a < eptr[e + 1]; a++) cnt[vars[a] + 1] += eptr[e + 1] - eptr[e];
+  for (int i = 0; i < n_nodes; i++) cnt[i + 1] += cnt[i];
+  int *tmp = (int *)malloc(sizeof(int) * (size_t)(cnt[n_nodes] > 0 ? cnt[n_nodes] : 1));
+  int *fill = (int *)malloc(sizeof(int) * (size_t)(n_nodes > 0 ? n_nodes : 1));
+  for (int i = 0; i < n_nodes; i++) fill[i] = cnt[i];
+  for (int e = 0; e < n_elems; e++)
+    for (int a = eptr[e]; a < eptr[e + 1]; a++)
+      for (int b = eptr[e]; b < eptr[e + 1]; b++) tmp[fill[vars[a]]++] = vars[b];
+  int nnz = 0;
+  rowp[0] = 0;
+  for (int r = 0; r < n_nodes; r++) {
+    int len = cnt[r + 1] - cnt[r];
+    int *row = &tmp[cnt[r]];
+    qsort(row, len, sizeof(int), cmp_int);
+    int last = -1;
+    for (int k = 0; k < len; k++)
+      if (k == 0 || row[k] != last) {
+        if (cols) cols[nnz] = row[k];
+        nnz++;
+        last = row[k];
+      }
+    rowp[r + 1] = nnz;
+  }
+  free(cnt); free(tmp); free(fill); free(eptr); free(vars);
+  return nnz;
+}
+
+/* oracle_assemble_dyn on a mesh with dependent nodes.  Gather: the values of a dependent node
+   are the weighted sum of its independent nodes, accumulated from zero in list order
+   (TACSBVec::endDistributeValues, src/bpmat/TACSBVec.cpp:930-975; node locations the same way
+   through TACSAssembler::setNodes).  Residual: element rows of a dependent node are summed in
+   the dependent slot first and distributed with the weights afterwards (TACSBVec::setValues with
+   TACS_ADD_VALUES, then beginSetValues, :855-885).  Matrix: W^T K_e W block by block
+   (TACSAssembler::addMatValues -> addWeightValues, src/TACSAssembler.h:485-510,
+   BCSRMat::addRowWeightValues).  X, u, udd, res have n_nodes rows (independent nodes). */
+int oracle_assemble_dep(int op, double alpha, double gamma, int n_nodes, int n_elems,
+                        const int *conn, const int *elem_comp, const oracle_comp_t *comps,
+                        const double *X, const double *u, const double *udd, int n_dep,
+                        const int *dep_ptr, const int *dep_conn, const double *dep_w, int n_bc,
+                        const int *bc_nodes, const int *bc_vars, const double *bc_vals,
+                        const int *rowp, const int *cols, double *res, double *A) {
+  int missing = 0, max_dep = 1;
+  for (int d = 0; d < n_dep; d++)
+    if (dep_ptr[d + 1] - dep_ptr[d] > max_dep) max_dep = dep_ptr[d + 1] - dep_ptr[d];
+  const int cap = NN * max_dep;
+  int *varp = (int *)malloc(sizeof(int) * (NN + 1)), *vars = (int *)malloc(sizeof(int) * cap);
+  double *w = (double *)malloc(sizeof(double) * cap);
+  /* dependent rows of X, u, udd and of the residual */
+  double *Xd = (double *)calloc((size_t)3 * (n_dep + 1), sizeof(double));
+  double *ud = (double *)calloc((size_t)6 * (n_dep + 1), sizeof(double));
+  double *uddd = (double *)calloc((size_t)6 * (n_dep + 1), sizeof(double));
+  double *rd = (double *)calloc((size_t)6 * (n_dep + 1), sizeof(double));
+  for (int d = 0; d < n_dep; d++)
+    for (int j = dep_ptr[d]; j < dep_ptr[d + 1]; j++) {
+      for (int k = 0; k < 3; k++) Xd[3 * d + k] += dep_w[j] * X[3 * (size_t)dep_conn[j] + k];
+      for (int k = 0; k < 6; k++) ud[6 * d + k] += dep_w[j] * u[6 * (size_t)dep_conn[j] + k];
+      if (udd) for (int k = 0; k < 6; k++) uddd[6 * d + k] += dep_w[j] * udd[6 * (size_t)dep_conn[j] + k];
+    }
+  if (res) memset(res, 0, sizeof(double) * 6 * (size_t)n_nodes);
+  if (A) memset(A, 0, sizeof(double) * 36 * (size_t)rowp[n_nodes]);
+  for (int e = 0; e < n_elems; e++) {
+    const int *nd = &conn[NN * e];
+    const oracle_comp_t *c = &comps[elem_comp ? elem_comp[e] : 0];
+    double Xe[3 * NN], qe[NV], qdde[NV], re[NV], me[NV * NV];
+    for (int i = 0; i < NN; i++) {
+      const double *xs = nd[i] >= 0 ? &X[3 * (size_t)nd[i]] : &Xd[3 * (-nd[i] - 1)];
+      const double *us = nd[i] >= 0 ? &u[6 * (size_t)nd[i]] : &ud[6 * (-nd[i] - 1)];
+      memcpy(&Xe[3 * i], xs, 3 * sizeof(double));
+      memcpy(&qe[6 * i], us, 6 * sizeof(double));
+      if (udd) memcpy(&qdde[6 * i], nd[i] >= 0 ? &udd[6 * (size_t)nd[i]] : &uddd[6 * (-nd[i] - 1)], 6 * sizeof(double));
+      else memset(&qdde[6 * i], 0, 6 * sizeof(double));
+    }
+    if (op == 0) { oracle_residual(c, Xe, qe, re); if (udd) inertia(c, 0.0, Xe, qdde, re, NULL); }
+    else if (op == 1) oracle_jacobian_dyn(c, alpha, gamma, Xe, qe, qdde, re, me);
+    else oracle_mat_type(c, op - 2, Xe, qe, me);
+    if (res && op <= 1)
+      for (int i = 0; i < NN; i++) {
+        double *dst = nd[i] >= 0 ? &res[6 * (size_t)nd[i]] : &rd[6 * (-nd[i] - 1)];
+        for (int k = 0; k < 6; k++) dst[k] += re[6 * i + k];
+      }
+    if (A && op >= 1) {
+      expand_nodes(nd, dep_ptr, dep_conn, dep_w, varp, vars, w);
+      for (int i = 0; i < NN; i++)
+        for (int ii = varp[i]; ii < varp[i + 1]; ii++)
+          for (int j = 0; j < NN; j++)
+            for (int jj = varp[j]; jj < varp[j + 1]; jj++) {
+              int k = find_col(rowp, cols, vars[ii], vars[jj]);
+              if (k < 0) { missing++; continue; }
+              double *a = &A[36 * (size_t)k];
+              const double ww = w[ii] * w[jj];
+              for (int r = 0; r < 6; r++)
+                for (int cc = 0; cc < 6; cc++) a[6 * r + cc] += ww * me[NV * (6 * i + r) + 6 * j + cc];
+            }
+    }
+  }
+  if (res && op <= 1)
+    for (int d = 0; d < n_dep; d++)
+      for (int j = dep_ptr[d]; j < dep_ptr[d + 1]; j++)
+        for (int k = 0; k < 6; k++) res[6 * (size_t)dep_conn[j] + k] += dep_w[j] * rd[6 * d + k];
+  if (res && op <= 1)
+    for (int b = 0; b < n_bc; b++)
+      for (int k = 0; k < 6; k++)
+        if (bc_vars[b] & (1 << k))
+          res[6 * (size_t)bc_nodes[b] + k] = u[6 * (size_t)bc_nodes[b] + k] - bc_vals[6 * b + k];
+  if (A && op >= 1)
+    for (int b = 0; b < n_bc; b++) {
+      int row = bc_nodes[b];
+      for (int j = rowp[row]; j < rowp[row + 1]; j++) {
+        double *a = &A[36 * (size_t)j];
+        for (int ii = 0; ii < 6; ii++)
+          if (bc_vars[b] & (1 << ii))
+            for (int jj = 0; jj < 6; jj++) a[6 * ii + jj] = 0.0;
+        if (cols[j] == row)
+          for (int ii = 0; ii < 6; ii++)
+            if (bc_vars[b] & (1 << ii)) a[7 * ii] = 1.0;
+      }
+    }
+  free(varp); free(vars); free(w); free(Xd); free(ud); free(uddd); free(rd);
   return missing;
 }

@@ -103,6 +103,28 @@ int oracle9_assemble_dyn(int op, double alpha, double gamma, int n_nodes, int n_
                          const int *bc_nodes, const int *bc_vars, const double *bc_vals,
                          const int *rowp, const int *cols, double *res, double *A);
 
+/* Meshes with dependent nodes (TACSAssembler::setDependentNodes, src/TACSAssembler.cpp:716-775):
+   a connectivity entry -(d + 1) is dependent node d = sum_j dep_w[j] * node dep_conn[j],
+   j in dep_ptr[d] .. dep_ptr[d + 1].  Pattern over the independent nodes behind every element
+   (computeLocalNodeToNodeCSR :1850-1935), assembly with the weights (TACSBVec.cpp:855-885,
+   :930-975; TACSAssembler.h:485-510).  Vectors have n_nodes (independent) rows. */
+int oracle_pattern_dep(int n_nodes, int n_elems, const int *conn, const int *dep_ptr,
+                       const int *dep_conn, int *rowp, int *cols);
+int oracle_assemble_dep(int op, double alpha, double gamma, int n_nodes, int n_elems,
+                        const int *conn, const int *elem_comp, const oracle_comp_t *comps,
+                        const double *X, const double *u, const double *udd, int n_dep,
+                        const int *dep_ptr, const int *dep_conn, const double *dep_w, int n_bc,
+                        const int *bc_nodes, const int *bc_vars, const double *bc_vals,
+                        const int *rowp, const int *cols, double *res, double *A);
+int oracle9_pattern_dep(int n_nodes, int n_elems, const int *conn, const int *dep_ptr,
+                        const int *dep_conn, int *rowp, int *cols);
+int oracle9_assemble_dep(int op, double alpha, double gamma, int n_nodes, int n_elems,
+                         const int *conn, const int *elem_comp, const oracle_comp_t *comps,
+                         const double *X, const double *u, const double *udd, int n_dep,
+                         const int *dep_ptr, const int *dep_conn, const double *dep_w, int n_bc,
+                         const int *bc_nodes, const int *bc_vars, const double *bc_vals,
+                         const int *rowp, const int *cols, double *res, double *A);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,8 @@ of the reference itself on seeded inputs:
   plate.npz, cylinder.npz : small assembled meshes (reference numbering): pattern,
                  res, K, G of assembleJacobian / assembleMatType, with BCs
   quad9.npz    : the 9-node element (TACSQuad9Shell): random elements and a small assembled plate
+  dep.npz      : a small curved panel with DEPENDENT nodes (TACSCreator::setDependentNodes), both
+                 element classes: pattern, res, K, G, M and the dynamic Jacobian, reference numbering
   buckling.npz : lowest 6 buckling eigenvalues of a 40x20 cylinder
   bdf.npz      : what the reference's TACSMeshLoader reads from the decks in this
                  directory (mixed.bdf: hand-written, every card family and field format;
@@ -27,7 +29,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import refdrv  # noqa: E402
-from helpers import random_elements, random_elements9  # noqa: E402
+from helpers import random_elements, random_elements9, with_dependent_nodes  # noqa: E402
 
 a2ds = importlib.import_module("a2d-shells_b200")
 AXIS = np.array([0.3, 1.0, 0.2])
@@ -127,6 +129,44 @@ def mesh(name):
     ra.close()
 
 
+def dep():
+    """dependent nodes through the reference's own path (TACSAssembler.h:469-510, TACSBVec.cpp:855-975)"""
+    conn, X, bcn = a2ds.meshes.plate(6, 5, bump=0.05)
+    conn2, Xi, bc2, dp = with_dependent_nodes(conn, X, bcn, 3, seed=1)
+    n = len(Xi)
+    out = {}
+    for kind in (0, 1):
+        p = refdrv.iso_props(kind=kind, t_offset=0.25)
+        Cs, eth, mom = refdrv.con_tables(p)
+        bc_vars = [list(range(6)) if i % 2 else [0, 1, 2] for i in range(len(bc2))]
+        bc_vals = [[-1e-5] + [0.0] * (len(v) - 1) for v in bc_vars]
+        ra = refdrv.RefAssembler(conn2, Xi, np.zeros(len(conn2), dtype=np.int32), p[None], bc2, bc_vars,
+                                 bc_vals, dep=dp)
+        u = a2ds.meshes.seeded_state(np.arange(n), 1e-4)
+        udd = a2ds.meshes.seeded_state(np.arange(n) + 1000, 1.0)
+        ra.set_state(u, None, udd)
+        m = ra.mat_create(0)
+        ra.assemble_mat_type(2, m)
+        blk = ra.mat_block(m, 0)
+        res_dyn = ra.assemble_jacobian(m, alpha=1.0, gamma=3.0)
+        J = ra.mat_block(m, 0)["A"]
+        ra.assemble_mat_type(1, m)
+        G = ra.mat_block(m, 0)["A"]
+        ra.set_state(u)
+        res = ra.assemble_jacobian(m)
+        K = ra.mat_block(m, 0)["A"]
+        nodes_b, vars_b, vals_b = ra.bcs()
+        dr = ra.dep()
+        if kind == 0:
+            out.update(conn=ra.conn(), X=ra.nodes(), u=u, udd=udd, bc_nodes=nodes_b, bc_vars=vars_b,
+                       bc_vals=vals_b, rowp=blk["rowp"], cols=blk["cols"], dep_ptr=dr[0], dep_conn=dr[1],
+                       dep_w=dr[2], Cs=Cs, eth=eth, mom=mom)
+        out.update({"M%d" % kind: blk["A"], "J%d" % kind: J, "res_dyn%d" % kind: res_dyn,
+                    "G%d" % kind: G, "K%d" % kind: K, "res%d" % kind: res})
+        ra.close()
+    np.savez_compressed(os.path.join(HERE, "dep.npz"), **out)
+
+
 def bdf():
     out = {}
     rng = np.random.default_rng(7)
@@ -179,9 +219,9 @@ def buckling():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["elements", "plate", "cylinder", "buckling", "bdf", "quad9"]
+    which = sys.argv[1:] or ["elements", "plate", "cylinder", "buckling", "bdf", "quad9", "dep"]
     for w in which:   # e.g. `python make_golden.py bdf` regenerates only bdf.npz
         {"elements": elements, "plate": lambda: mesh("plate"), "cylinder": lambda: mesh("cylinder"),
-         "buckling": buckling, "bdf": bdf, "quad9": quad9}[w]()
+         "buckling": buckling, "bdf": bdf, "quad9": quad9, "dep": dep}[w]()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -97,3 +97,46 @@ def bcsr_matvec(A, rowp, cols, x):
     y = np.zeros((n, 6))
     np.add.at(y, rows, np.einsum("kij,kj->ki", A, x[cols]))
     return y
+
+
+def with_dependent_nodes(conn, X, bc_nodes, n_dep, seed=0, npe=4):
+    """Turn n_dep nodes of a mesh into DEPENDENT nodes (TACSAssembler::setDependentNodes): each
+    is replaced by a weighted mean of the other nodes of its elements (up to 8 of them), the
+    remaining nodes are renumbered compactly.  Returns (conn with -(d + 1) entries, X of the
+    independent nodes, their BC node list, (dep_ptr, dep_conn, dep_weights))."""
+    rng = np.random.default_rng(seed)
+    conn = np.asarray(conn).reshape(-1, npe)
+    n = len(X)
+    banned = set(int(b) for b in bc_nodes)
+    chosen, nbrs_of = [], {}
+    node_elems = [[] for _ in range(n)]
+    for e, nd in enumerate(conn):
+        for v in nd:
+            node_elems[int(v)].append(e)
+    for v in rng.permutation(n):
+        v = int(v)
+        if len(chosen) == n_dep:
+            break
+        if v in banned:
+            continue
+        nb = sorted(set(int(w) for e in node_elems[v] for w in conn[e]) - {v})
+        if any(w in nbrs_of for w in nb):      # a dependent node never depends on another one
+            continue
+        pick = nb     # the whole patch around the node: its weighted mean stays close to the node
+        chosen.append(v); nbrs_of[v] = pick
+        banned.update(nb); banned.add(v)
+    assert len(chosen) == n_dep, "mesh too small for that many dependent nodes"
+    keep = np.ones(n, bool); keep[chosen] = False
+    new = -np.ones(n, dtype=np.int64); new[keep] = np.arange(keep.sum())
+    for d, v in enumerate(chosen):
+        new[v] = -(d + 1)
+    dep_ptr = [0]; dep_conn = []; dep_w = []
+    for v in chosen:
+        w = rng.uniform(0.8, 1.2, len(nbrs_of[v])); w /= w.sum()
+        dep_conn += [int(new[x]) for x in nbrs_of[v]]; dep_w += list(w)
+        dep_ptr.append(len(dep_conn))
+    conn2 = new[conn].astype(np.int32)
+    bc2 = new[np.asarray(bc_nodes, dtype=np.int64)].astype(np.int32)
+    assert (bc2 >= 0).all() and min(dep_conn) >= 0
+    return (conn2, np.ascontiguousarray(X[keep]), bc2,
+            (np.array(dep_ptr, np.int32), np.array(dep_conn, np.int32), np.array(dep_w)))

@@ -215,3 +215,67 @@ def test_quad9_oracle_against_reference_live(orc, ref):
                 m_ref = ref.element(p, 4, Xe, qe, transform=tr, axis=axis)[1]
                 assert np.abs(m_ref).max() > 0
                 assert relmax(orc.mat_type(comp, 2, Xe, qe, order=3), m_ref) < 1e-13
+
+
+def test_dependent_nodes_against_golden(orc):
+    """mesh with dependent nodes (TACSAssembler::setDependentNodes): pattern bit-exact, res / K /
+    G / M / dynamic Jacobian of both element classes against the reference's outputs (dep.npz)"""
+    g = np.load(os.path.join(GOLD, "dep.npz"))
+    conn, X, u, udd = g["conn"], g["X"], g["u"], g["udd"]
+    assert (conn < 0).any()
+    dep = (g["dep_ptr"], g["dep_conn"], g["dep_w"])
+    rowp, cols = orc.pattern_dep(len(X), conn, dep[0], dep[1])
+    assert rowp.tobytes() == g["rowp"].tobytes() and cols.tobytes() == g["cols"].tobytes()
+    ec = np.zeros(len(conn), dtype=np.int32)
+    for kind in (0, 1):
+        comp = orc.make_comp(kind, g["Cs"], g["eth"], g["mom"])
+        args = (conn, ec, [comp], X, u, dep, rowp, cols, g["bc_nodes"], g["bc_vars"], g["bc_vals"])
+        r, K = orc.assemble_dep(1, *args)
+        assert relmax(r, g["res%d" % kind]) < 1e-13 and relmax(K, g["K%d" % kind]) < 1e-13
+        _, G = orc.assemble_dep(3, *args)
+        assert relmax(G, g["G%d" % kind]) < 1e-10
+        _, M = orc.assemble_dep(4, *args)
+        assert relmax(M, g["M%d" % kind]) < 1e-13
+        r, J = orc.assemble_dep(1, *args, alpha=1.0, gamma=3.0, udd=udd)
+        assert relmax(r, g["res_dyn%d" % kind]) < 1e-13 and relmax(J, g["J%d" % kind]) < 1e-13
+
+
+def test_dependent_nodes_against_reference_live(orc, ref):
+    """the same on another mesh / seed against the unmodified reference run here; without
+    dependent nodes the dep entry points reduce to the plain ones"""
+    import importlib
+    from helpers import with_dependent_nodes
+    a2ds = importlib.import_module("a2d-shells_b200")
+    conn, X, bcn = a2ds.meshes.cylinder(10, 6)
+    conn2, Xi, bc2, dp = with_dependent_nodes(conn, X, bcn, 5, seed=4)
+    n = len(Xi)
+    p = ref.iso_props(kind=1, t_offset=0.1)
+    Cs, eth, mom = ref.con_tables(p)
+    ra = ref.RefAssembler(conn2, Xi, np.zeros(len(conn2), dtype=np.int32), p[None], bc2,
+                          [list(range(6))] * len(bc2), [[0.0] * 6] * len(bc2), dep=dp)
+    try:
+        conn_r, X_r, dep_r = ra.conn(), ra.nodes(), ra.dep()
+        nodes_b, vars_b, vals_b = ra.bcs()
+        u = a2ds.meshes.seeded_state(np.arange(n), 1e-4)
+        ra.set_state(u)
+        m = ra.mat_create(0)
+        r_ref = ra.assemble_jacobian(m)
+        blk = ra.mat_block(m, 0)
+    finally:
+        ra.close()
+    rowp, cols = orc.pattern_dep(n, conn_r, dep_r[0], dep_r[1])
+    assert np.array_equal(rowp, blk["rowp"]) and np.array_equal(cols, blk["cols"])
+    comp = orc.make_comp(1, Cs, eth, mom)
+    ec = np.zeros(len(conn_r), dtype=np.int32)
+    r, K = orc.assemble_dep(1, conn_r, ec, [comp], X_r, u, dep_r, rowp, cols, nodes_b, vars_b, vals_b)
+    assert relmax(r, r_ref) < 1e-13 and relmax(K, blk["A"]) < 1e-13
+    # no dependent nodes: identical to the plain entry points
+    none = (np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    rp0, cl0 = orc.pattern(len(X), conn)
+    rp1, cl1 = orc.pattern_dep(len(X), conn, none[0], none[1])
+    assert np.array_equal(rp0, rp1) and np.array_equal(cl0, cl1)
+    uu = a2ds.meshes.seeded_state(np.arange(len(X)), 1e-4)
+    ec = np.zeros(len(conn), dtype=np.int32)
+    ra_, Ka = orc.assemble(1, conn, ec, [comp], X, uu, rp0, cl0)
+    rb_, Kb = orc.assemble_dep(1, conn, ec, [comp], X, uu, none, rp0, cl0)
+    assert np.array_equal(ra_, rb_) and np.array_equal(Ka, Kb)
