@@ -20,7 +20,7 @@ SCATTER_ATOMIC_COLOR_ORDER = 2
 # every symbol include/a2ds.h declares (tests check the library exports them all)
 SYMBOLS = [
     "a2ds_last_error", "a2ds_version", "a2ds_create", "a2ds_destroy", "a2ds_synchronize",
-    "a2ds_set_mesh", "a2ds_set_mesh_order", "a2ds_set_nodes", "a2ds_set_components", "a2ds_set_state",
+    "a2ds_set_mesh", "a2ds_set_mesh_order", "a2ds_set_dependent_nodes", "a2ds_set_nodes", "a2ds_set_components", "a2ds_set_state",
     "a2ds_set_state_dev", "a2ds_set_bcs", "a2ds_set_scatter_mode", "a2ds_mat_create",
     "a2ds_mat_create_natural", "a2ds_mat_pattern", "a2ds_mat_nnz", "a2ds_mat_zero",
     "a2ds_mat_download", "a2ds_mat_values_dev", "a2ds_mat_download_rows", "a2ds_assemble_res", "a2ds_assemble_jacobian",
@@ -385,6 +385,17 @@ class Assembler:
             self._chk(self.L.a2ds_set_mesh_order(self.ctx, C.c_int(order), C.c_int(self.n_nodes),
                                                  C.c_int(self.n_owned), C.c_int(self.n_elems),
                                                  _p(conn), _p(ec)))
+
+    def set_dependent_nodes(self, dep_ptr, dep_conn, dep_weights):
+        """TACSAssembler::setDependentNodes: dependent node d = sum_j w[j] * node dep_conn[j] over
+        dep_ptr[d] .. dep_ptr[d + 1]; the connectivity of the FOLLOWING set_mesh refers to it as
+        -(d + 1).  (None, None, None) withdraws the declaration."""
+        if dep_ptr is None:
+            self._chk(self.L.a2ds_set_dependent_nodes(self.ctx, C.c_int(0), None, None, None))
+            return
+        dp, dc, dw = _i32(dep_ptr), _i32(dep_conn), _f64(dep_weights)
+        assert len(dc) == len(dw) == dp[-1]
+        self._chk(self.L.a2ds_set_dependent_nodes(self.ctx, C.c_int(len(dp) - 1), _p(dp), _p(dc), _p(dw)))
 
     def set_nodes(self, X):
         X = _f64(X).reshape(-1, 3)

@@ -94,6 +94,11 @@ struct MatrixRec {
   std::vector<const int *> d_rowp, d_cols;       // device copy, per block
   unsigned long long pattern_hash = 0;           // fingerprint of (rowp, cols), 0 = not computed
   unsigned long long *shared_hash = nullptr;     // natural-order matrices of one mesh share it
+  // dependent nodes: n_fold scratch blocks behind the `total` blocks of the matrix take the
+  // element blocks of node pairs with a dependent node; k_dep_fold distributes them (W^T K_e W)
+  int n_fold = 0;
+  int *fold_ptr = nullptr, *fold_tgt = nullptr;
+  double *fold_w = nullptr;
   // matrix halo (ParallelMat flavour): blocks of ghost rows sent to / received from peers
   bool has_halo = false;
   std::vector<int> halo_peers, halo_send_ptr, halo_recv_ptr;
@@ -144,6 +149,16 @@ struct a2ds_ctx {
   int n_nodes = 0, n_owned = 0, n_elems = 0, n_comp = 0, n_bc = 0;
   int npe = 4;   // nodes per element: 4 (MITC4, every entry point) or 9 (MITC9, see a2ds_set_mesh_order)
   bool mesh_set = false;
+  // dependent nodes (a2ds_set_dependent_nodes; TACSAssembler::setDependentNodes): the spec is
+  // kept on the host and applied by the next a2ds_set_mesh; dependent node d of the current mesh
+  // is row n_nodes + d of X / u / res / udd, and h_conn refers to it by that row
+  std::vector<int> h_dep_ptr, h_dep_conn;
+  std::vector<double> h_dep_w;
+  int n_dep = 0;
+  int *dep_ptr = nullptr, *dep_conn = nullptr;
+  double *dep_w = nullptr;
+  std::vector<int> h_dep_slots;   // e * npe^2 + slot of every element node pair with a dependent node
+  size_t n_ext() const { return (size_t)n_nodes + (size_t)n_dep; }
   int *conn = nullptr, *elem_comp = nullptr;
   std::vector<int> h_conn, h_elem_comp, h_class;
   // natural-order pattern of the current mesh, built by the first a2ds_mat_create_natural
@@ -326,6 +341,40 @@ extern "C" int a2ds_synchronize(a2ds_ctx *c) {
   A2DS_CATCH(a2ds_synchronize)
 }
 
+// Dependent nodes (TACSAssembler::setDependentNodes, src/TACSAssembler.cpp:716-775): the spec is
+// stored and applied by the following a2ds_set_mesh calls (n_dep = 0 withdraws it), as the
+// reference wants it set before initialize().
+extern "C" int a2ds_set_dependent_nodes(a2ds_ctx *c, int n_dep, const int *dep_ptr, const int *dep_conn,
+                                        const double *dep_weights) {
+  A2DS_TRY
+  if (n_dep < 0) return fail("a2ds_set_dependent_nodes: negative count");
+  if (n_dep == 0) {
+    c->h_dep_ptr.clear(); c->h_dep_conn.clear(); c->h_dep_w.clear();
+    return 0;
+  }
+  if (!dep_ptr || !dep_conn || !dep_weights || dep_ptr[0] != 0)
+    return fail("a2ds_set_dependent_nodes: dep_ptr must start at 0 and all three arrays be given");
+  for (int d = 0; d < n_dep; d++)
+    if (dep_ptr[d + 1] < dep_ptr[d]) return fail("a2ds_set_dependent_nodes: dep_ptr is not monotone");
+  for (int j = 0; j < dep_ptr[n_dep]; j++)
+    if (dep_conn[j] < 0)
+      return fail("a2ds_set_dependent_nodes: a dependent node must refer to independent nodes only");
+  c->h_dep_ptr.assign(dep_ptr, dep_ptr + n_dep + 1);
+  c->h_dep_conn.assign(dep_conn, dep_conn + dep_ptr[n_dep]);
+  c->h_dep_w.assign(dep_weights, dep_weights + dep_ptr[n_dep]);
+  return 0;
+  A2DS_CATCH(a2ds_set_dependent_nodes)
+}
+
+// rows of the dependent nodes of a node vector with nc values per node (see k_dep_gather)
+static int dep_gather(a2ds_ctx *c, double *v, int nc) {
+  if (!c->n_dep) return 0;
+  k_dep_gather<<<(c->n_dep * nc + 127) / 128, 128, 0, c->stream>>>(c->n_dep, nc, c->n_nodes, c->dep_ptr,
+                                                                   c->dep_conn, c->dep_w, v);
+  c->last_launches++;
+  return 0;
+}
+
 extern "C" int a2ds_set_mesh(a2ds_ctx *c, int n_nodes, int n_owned, int n_elems, const int *conn,
                              const int *elem_comp) {
   return a2ds_set_mesh_order(c, 2, n_nodes, n_owned, n_elems, conn, elem_comp);
@@ -338,10 +387,15 @@ extern "C" int a2ds_set_mesh_order(a2ds_ctx *c, int order, int n_nodes, int n_ow
   if (order != 2 && order != 3) return fail("a2ds_set_mesh_order: order must be 2 (4 nodes) or 3 (9 nodes)");
   if (n_owned > n_nodes || n_nodes < 0 || n_elems < 0) return fail("a2ds_set_mesh: bad sizes");
   const int npe = order * order;
+  const int n_dep = c->h_dep_ptr.empty() ? 0 : (int)c->h_dep_ptr.size() - 1;
   for (size_t i = 0; i < npe * (size_t)n_elems; i++)
-    if (conn[i] < 0 || conn[i] >= n_nodes)
-      return fail("a2ds_set_mesh: connectivity refers to a node outside [0, n_nodes) "
-                  "(dependent nodes are not supported)");
+    if (conn[i] < -n_dep || conn[i] >= n_nodes)
+      return fail(n_dep ? "a2ds_set_mesh: connectivity refers to a node outside [0, n_nodes) or to a "
+                          "dependent node that was not declared"
+                        : "a2ds_set_mesh: connectivity refers to a node outside [0, n_nodes) "
+                          "(negative entries need a2ds_set_dependent_nodes first)");
+  for (int v : c->h_dep_conn)
+    if (v >= n_nodes) return fail("a2ds_set_mesh: a dependent node refers to a node outside [0, n_nodes)");
   if (c->mesh_set) {
     // a second mesh on the same context: nothing sized for the old one may survive — the
     // matrices (offset tables of 16 * old n_elems), the halo lists and the BC arrays
@@ -358,12 +412,30 @@ extern "C" int a2ds_set_mesh_order(a2ds_ctx *c, int order, int n_nodes, int n_ow
   }
   c->n_nodes = n_nodes; c->n_owned = n_owned; c->n_elems = n_elems; c->npe = npe;
   c->h_conn.assign(conn, conn + npe * (size_t)n_elems);
+  c->n_dep = n_dep;
+  c->h_dep_slots.clear();
+  if (n_dep) {
+    // dependent node d = connectivity entry -(d + 1) -> row n_nodes + d behind the local rows
+    for (size_t e = 0; e < (size_t)n_elems; e++) {
+      int *nd = &c->h_conn[npe * e];
+      bool any = false;
+      for (int i = 0; i < npe; i++)
+        if (nd[i] < 0) { nd[i] = n_nodes + (-nd[i] - 1); any = true; }
+      if (!any) continue;
+      for (int slot = 0; slot < npe * npe; slot++)
+        if (nd[slot / npe] >= n_nodes || nd[slot % npe] >= n_nodes)
+          c->h_dep_slots.push_back((int)(e * npe * npe) + slot);
+    }
+    if (upload(&c->dep_ptr, c->h_dep_ptr.data(), c->h_dep_ptr.size(), c->stream)) return 1;
+    if (upload(&c->dep_conn, c->h_dep_conn.data(), c->h_dep_conn.size(), c->stream)) return 1;
+    if (upload(&c->dep_w, c->h_dep_w.data(), c->h_dep_w.size(), c->stream)) return 1;
+  }
   c->nat_ready = false;
   cudaFree(c->nat_d_rowp); cudaFree(c->nat_d_cols);
   c->nat_d_rowp = c->nat_d_cols = nullptr; c->nat_hash = 0;
   if (elem_comp) c->h_elem_comp.assign(elem_comp, elem_comp + n_elems);
   else c->h_elem_comp.assign(n_elems, 0);
-  if (upload(&c->conn, conn, npe * (size_t)n_elems, c->stream)) return 1;
+  if (upload(&c->conn, c->h_conn.data(), npe * (size_t)n_elems, c->stream)) return 1;
   if (upload(&c->elem_comp, c->h_elem_comp.data(), (size_t)n_elems, c->stream)) return 1;
   CU(cudaStreamSynchronize(c->copy_stream));
   c->state_pending = false;
@@ -371,11 +443,13 @@ extern "C" int a2ds_set_mesh_order(a2ds_ctx *c, int order, int n_nodes, int n_ow
   cudaFree(c->X); cudaFree(c->u); cudaFree(c->res); cudaFree(c->udd);
   c->udd = nullptr;
   c->X = c->u = c->res = nullptr;
-  CU(cudaMalloc((void **)&c->X, 3 * (size_t)n_nodes * sizeof(double)));
-  CU(cudaMalloc((void **)&c->u, 6 * (size_t)n_nodes * sizeof(double)));
-  CU(cudaMalloc((void **)&c->res, 6 * (size_t)n_nodes * sizeof(double)));
-  CU(cudaMemsetAsync(c->u, 0, 6 * (size_t)n_nodes * sizeof(double), c->stream));
-  CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)n_nodes * sizeof(double), c->stream));
+  const size_t n_ext = std::max<size_t>(c->n_ext(), 1);   // dependent rows behind the local ones
+  CU(cudaMalloc((void **)&c->X, 3 * n_ext * sizeof(double)));
+  CU(cudaMalloc((void **)&c->u, 6 * n_ext * sizeof(double)));
+  CU(cudaMalloc((void **)&c->res, 6 * n_ext * sizeof(double)));
+  CU(cudaMemsetAsync(c->X, 0, 3 * n_ext * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->u, 0, 6 * n_ext * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->res, 0, 6 * n_ext * sizeof(double), c->stream));
   free_lists(c);
   c->mesh_set = true;
   return 0;
@@ -388,6 +462,8 @@ extern "C" int a2ds_set_nodes(a2ds_ctx *c, const double *X) {
   if (!c->X) return fail("a2ds_set_nodes: call a2ds_set_mesh first");
   CU(cudaMemcpyAsync(c->X, X, 3 * (size_t)c->n_nodes * sizeof(double), cudaMemcpyHostToDevice,
                      c->stream));
+  // locations of the dependent nodes (TACSAssembler::setNodes distributes xptVec the same way)
+  if (dep_gather(c, c->X, 3)) return 1;
   CU(cudaStreamSynchronize(c->stream));
   return 0;
   A2DS_CATCH(a2ds_set_nodes)
@@ -473,8 +549,8 @@ extern "C" int a2ds_set_state_rates(a2ds_ctx *c, int n_given, const double *udot
   if (n_given != c->n_nodes && n_given != c->n_owned)
     return fail("a2ds_set_state_rates: n_given must be n_nodes or n_owned");
   if (!c->udd) {
-    CU(cudaMalloc((void **)&c->udd, std::max<size_t>(6 * (size_t)c->n_nodes * sizeof(double), 8)));
-    CU(cudaMemsetAsync(c->udd, 0, 6 * (size_t)c->n_nodes * sizeof(double), c->stream));
+    CU(cudaMalloc((void **)&c->udd, std::max<size_t>(6 * c->n_ext() * sizeof(double), 8)));
+    CU(cudaMemsetAsync(c->udd, 0, 6 * c->n_ext() * sizeof(double), c->stream));
   }
   CU(cudaMemcpyAsync(c->udd, uddot, 6 * (size_t)n_given * sizeof(double), cudaMemcpyHostToDevice,
                      c->stream));
@@ -590,6 +666,8 @@ static void color_elements(int nn, int ne, const int *conn, std::vector<int> &co
 static int build_lists(a2ds_ctx *c) {
   if (c->lists_ready) return 0;
   if (c->n_comp == 0) return fail("assemble: a2ds_set_components has not been called");
+  if (c->n_dep && c->scatter_mode != A2DS_SCATTER_ATOMIC)
+    return fail("assemble: meshes with dependent nodes are assembled with the atomic scatter only");
   for (int e = 0; e < c->n_elems; e++)
     if (c->h_elem_comp[e] < 0 || c->h_elem_comp[e] >= c->n_comp)
       return fail("assemble: element component index out of range");
@@ -626,6 +704,83 @@ static int build_lists(a2ds_ctx *c) {
     }
   }
   c->lists_ready = true;
+  return 0;
+}
+
+// ---- dependent nodes: the fold plan of a matrix -------------------------------------------
+// One BCSR block of a matrix as the host sees it (mirror of BlockDev)
+struct HostBlock {
+  const int *rowp, *cols, *row_map, *col_map;
+  long long base;
+  int nrows;
+};
+// block offset of node pair (rn, cn): the search of k_build_offsets on the host
+static long long host_find_block(const std::vector<HostBlock> &hb, int rn, int cn) {
+  for (const HostBlock &b : hb) {
+    const int rr = b.row_map ? b.row_map[rn] : (rn < b.nrows ? rn : -1);
+    const int cc = b.col_map ? b.col_map[cn] : cn;
+    if (rr < 0 || rr >= b.nrows || cc < 0) continue;
+    const int *lo = b.cols + b.rowp[rr], *hi = b.cols + b.rowp[rr + 1];
+    const int *it = std::lower_bound(lo, hi, cc);
+    if (it != hi && *it == cc) return b.base + (it - b.cols);
+  }
+  return -1;
+}
+// Every element node pair with a dependent node gets a scratch block behind the matrix
+// (m.total + s, through the offset table) and the list of (independent row, independent column)
+// blocks it is distributed to with the product of the weights: the varp / vars / weights
+// expansion of TACSAssembler::addMatValues (src/TACSAssembler.h:485-510) done once per matrix.
+static int build_dep_fold(a2ds_ctx *c, const std::vector<HostBlock> &hb, MatrixRec &m, const char *who) {
+  const int ns = (int)c->h_dep_slots.size();
+  if (!ns) return 0;
+  const int npe = c->npe, n2 = npe * npe, nn = c->n_nodes;
+  std::vector<int> fptr(1, 0), ftgt;
+  std::vector<double> fw;
+  auto expand = [&](int node, std::vector<std::pair<int, double>> &out) {
+    out.clear();
+    if (node < nn) { out.emplace_back(node, 1.0); return; }
+    const int d = node - nn;
+    for (int j = c->h_dep_ptr[d]; j < c->h_dep_ptr[d + 1]; j++) out.emplace_back(c->h_dep_conn[j], c->h_dep_w[j]);
+  };
+  std::vector<std::pair<int, double>> ri, cj;
+  long long missing = 0;
+  for (int s = 0; s < ns; s++) {
+    const int pos = c->h_dep_slots[s], e = pos / n2, slot = pos - e * n2;
+    expand(c->h_conn[npe * (size_t)e + slot / npe], ri);
+    expand(c->h_conn[npe * (size_t)e + slot % npe], cj);
+    for (auto &a : ri)
+      for (auto &b : cj) {
+        const long long k = host_find_block(hb, a.first, b.first);
+        if (k < 0) { missing++; continue; }
+        ftgt.push_back((int)k); fw.push_back(a.second * b.second);
+      }
+    fptr.push_back((int)ftgt.size());
+  }
+  if (missing)
+    return fail(std::string(who) + ": the pattern misses " + std::to_string(missing) +
+                " blocks between the independent nodes of dependent nodes");
+  int *d_pos = nullptr;
+  if (upload(&d_pos, c->h_dep_slots.data(), (size_t)ns, c->stream)) return 1;
+  if (upload(&m.fold_ptr, fptr.data(), fptr.size(), c->stream)) return 1;
+  if (upload(&m.fold_tgt, ftgt.data(), ftgt.size(), c->stream)) return 1;
+  if (upload(&m.fold_w, fw.data(), fw.size(), c->stream)) return 1;
+  m.owned.push_back(m.fold_ptr);
+  if (m.fold_tgt) m.owned.push_back(m.fold_tgt);
+  if (m.fold_w) m.owned.push_back(m.fold_w);
+  k_dep_patch_offsets<<<(ns + 255) / 256, 256, 0, c->stream>>>(ns, d_pos, (int)m.total, m.off);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_pos);
+  m.n_fold = ns;
+  return 0;
+}
+// distribute and clear the scratch blocks of a matrix an element pass has added to
+static int dep_fold(a2ds_ctx *c, MatrixRec &m) {
+  if (!m.n_fold) return 0;
+  const size_t nt = 36 * (size_t)m.n_fold;
+  k_dep_fold<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(m.n_fold, m.total, m.fold_ptr, m.fold_tgt,
+                                                                 m.fold_w, m.A);
+  c->last_launches++;
   return 0;
 }
 
@@ -681,9 +836,11 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   if (total >= (1ll << 31)) return fail("a2ds_mat_create: more than 2^31 blocks on one GPU");
   tm.lap("mat_create: pattern upload");
   m.total = total;
-  CU(cudaMalloc((void **)&m.A, std::max<long long>(total, 1) * 36 * sizeof(double)));
+  const long long n_scratch = (long long)c->h_dep_slots.size();   // fold scratch of the dependent nodes
+  if (total + n_scratch >= (1ll << 31)) return fail("a2ds_mat_create: more than 2^31 blocks on one GPU");
+  CU(cudaMalloc((void **)&m.A, std::max<long long>(total + n_scratch, 1) * 36 * sizeof(double)));
   m.owned.push_back(m.A);
-  CU(cudaMemsetAsync(m.A, 0, total * 36 * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(m.A, 0, (total + n_scratch) * 36 * sizeof(double), c->stream));
   CU(cudaMalloc((void **)&m.blk_dev, n_blocks * sizeof(BlockDev)));
   m.owned.push_back(m.blk_dev);
   CU(cudaMemcpyAsync(m.blk_dev, hb.data(), n_blocks * sizeof(BlockDev), cudaMemcpyHostToDevice,
@@ -696,7 +853,7 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
   if (c->n_elems > 0) {
     const size_t nt = c->npe * c->npe * (size_t)c->n_elems;
     k_build_offsets<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(
-        c->n_elems, c->npe, c->conn, n_blocks, m.blk_dev, m.off, d_missing);
+        c->n_elems, c->npe, c->conn, n_blocks, m.blk_dev, m.off, d_missing, c->n_nodes);
     CU(cudaGetLastError());
   }
   int missing = 0;
@@ -708,6 +865,16 @@ extern "C" int a2ds_mat_create(a2ds_ctx *c, int n_blocks, const int *nrows,
     for (void *p : m.owned) cudaFree(p);
     return fail("a2ds_mat_create: " + std::to_string(missing) +
                 " element blocks have no entry in the supplied non-zero pattern");
+  }
+  if (n_scratch) {
+    std::vector<HostBlock> hh(n_blocks);
+    for (int b = 0; b < n_blocks; b++)
+      hh[b] = HostBlock{m.h_rowp[b]->data(), m.h_cols[b]->data(), row_map ? row_map[b] : nullptr,
+                        col_map ? col_map[b] : nullptr, m.base[b], nrows[b]};
+    if (build_dep_fold(c, hh, m, "a2ds_mat_create")) {
+      for (void *p : m.owned) cudaFree(p);
+      return 1;
+    }
   }
   c->mats.push_back(std::move(m));
   tm.lap("mat_create: record");
@@ -741,6 +908,8 @@ static int check_mat(a2ds_ctx *c, int mat, int block = 0) {
 // node -> nodes of its elements (4 per incidence), then sort + unique per row.  The rows are
 // independent once the incidences are bucketed: the sort / unique pass runs on all host cores
 // (two sweeps: count the distinct columns of every row, then write them at their offsets).
+static void sort_unique_rows(int nn, const std::vector<int> &ptr, std::vector<int> &tmp,
+                             std::vector<int> &rowp, std::vector<int> &cols);
 static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &rowp,
                            std::vector<int> &cols, int npe = 4) {
   std::vector<int> ptr(nn + 1, 0);
@@ -759,6 +928,14 @@ static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &ro
       for (int j = 0; j < npe; j++) tmp[fill[r]++] = conn[npe * (size_t)e + j];
     }
   fill.clear(); fill.shrink_to_fit();
+  sort_unique_rows(nn, ptr, tmp, rowp, cols);
+  return 0;
+}
+
+// rows of candidate columns (bucket r = tmp[ptr[r] .. ptr[r + 1])) -> sorted, distinct CSR
+// (TacsSortAndUniquifyCSR, src/utils/TacsUtilities.cpp:280)
+static void sort_unique_rows(int nn, const std::vector<int> &ptr, std::vector<int> &tmp,
+                             std::vector<int> &rowp, std::vector<int> &cols) {
   rowp.assign(nn + 1, 0);
   const int nt = (int)std::max(1u, std::min(16u, nn < (1 << 16) ? 1u : std::thread::hardware_concurrency()));
   auto sweep = [&](bool write) {
@@ -783,6 +960,37 @@ static int natural_pattern(int nn, int ne, const int *conn, std::vector<int> &ro
   for (int r = 0; r < nn; r++) rowp[r + 1] += rowp[r];
   cols.assign((size_t)rowp[nn], 0);
   sweep(true);
+}
+
+// the same with dependent nodes: every independent node behind an element couples to every
+// other one (TACSAssembler::computeLocalNodeToNodeCSR, src/TACSAssembler.cpp:1850-1935)
+static int natural_pattern_dep(a2ds_ctx *c, std::vector<int> &rowp, std::vector<int> &cols) {
+  const int nn = c->n_nodes, ne = c->n_elems, npe = c->npe;
+  std::vector<int> eptr(ne + 1, 0), vars;
+  for (int e = 0; e < ne; e++) {
+    for (int i = 0; i < npe; i++) {
+      const int v = c->h_conn[npe * (size_t)e + i];
+      if (v < nn) vars.push_back(v);
+      else vars.insert(vars.end(), c->h_dep_conn.begin() + c->h_dep_ptr[v - nn],
+                       c->h_dep_conn.begin() + c->h_dep_ptr[v - nn + 1]);
+    }
+    if (vars.size() > 0x7fffffffull) return fail("pattern too large");
+    eptr[e + 1] = (int)vars.size();
+  }
+  std::vector<long long> cnt(nn + 1, 0);
+  for (int e = 0; e < ne; e++)
+    for (int a = eptr[e]; a < eptr[e + 1]; a++) cnt[vars[a] + 1] += eptr[e + 1] - eptr[e];
+  std::vector<int> ptr(nn + 1, 0);
+  for (int i = 0; i < nn; i++) {
+    cnt[i + 1] += cnt[i];
+    if (cnt[i + 1] > 0x7fffffffll) return fail("pattern too large");
+    ptr[i + 1] = (int)cnt[i + 1];
+  }
+  std::vector<int> tmp(ptr[nn]), fill(ptr.begin(), ptr.end() - 1);
+  for (int e = 0; e < ne; e++)
+    for (int a = eptr[e]; a < eptr[e + 1]; a++)
+      for (int b = eptr[e]; b < eptr[e + 1]; b++) tmp[fill[vars[a]]++] = vars[b];
+  sort_unique_rows(nn, ptr, tmp, rowp, cols);
   return 0;
 }
 
@@ -864,11 +1072,13 @@ extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   StageTimer tm;
   if (!c->nat_ready) {
     static const bool host_only = getenv("A2DS_HOST_PATTERN") && atoi(getenv("A2DS_HOST_PATTERN")) != 0;
-    int rc = (host_only || c->npe != 4) ? 2 : natural_pattern_device(c);   // 9-node meshes: host sweep
+    // 9-node meshes and meshes with dependent nodes: host sweep
+    int rc = (host_only || c->npe != 4 || c->n_dep) ? 2 : natural_pattern_device(c);
     if (rc == 1) return 1;
     if (rc == 2) {   // very high valence somewhere (or asked for): host sort / unique sweep
       auto hr = std::make_shared<std::vector<int>>(), hc = std::make_shared<std::vector<int>>();
-      if (natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), *hr, *hc, c->npe)) return 1;
+      if (c->n_dep ? natural_pattern_dep(c, *hr, *hc)
+                   : natural_pattern(c->n_nodes, c->n_elems, c->h_conn.data(), *hr, *hc, c->npe)) return 1;
       c->nat_rowp = hr; c->nat_cols = hc;
       if (upload(&c->nat_d_rowp, hr->data(), hr->size(), c->stream)) return 1;
       if (upload(&c->nat_d_cols, hc->data(), hc->size(), c->stream)) return 1;
@@ -887,9 +1097,11 @@ extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   BlockDev hb;
   hb.rowp = c->nat_d_rowp; hb.cols = c->nat_d_cols; hb.row_map = nullptr; hb.col_map = nullptr;
   hb.base = 0; hb.nrows = c->n_nodes; hb.ident = 1;
-  CU(cudaMalloc((void **)&m.A, std::max<long long>(nnz, 1) * 36 * sizeof(double)));
+  const long long n_scratch = (long long)c->h_dep_slots.size();   // fold scratch of the dependent nodes
+  if (nnz + n_scratch >= (1ll << 31)) return fail("a2ds_mat_create_natural: more than 2^31 blocks on one GPU");
+  CU(cudaMalloc((void **)&m.A, std::max<long long>(nnz + n_scratch, 1) * 36 * sizeof(double)));
   m.owned.push_back(m.A);
-  CU(cudaMemsetAsync(m.A, 0, nnz * 36 * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(m.A, 0, (nnz + n_scratch) * 36 * sizeof(double), c->stream));
   CU(cudaMalloc((void **)&m.blk_dev, sizeof(BlockDev)));
   m.owned.push_back(m.blk_dev);
   CU(cudaMemcpyAsync(m.blk_dev, &hb, sizeof(BlockDev), cudaMemcpyHostToDevice, c->stream));
@@ -901,7 +1113,7 @@ extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   if (c->n_elems > 0) {
     const size_t nt = c->npe * c->npe * (size_t)c->n_elems;
     k_build_offsets<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(c->n_elems, c->npe, c->conn, 1,
-                                                                        m.blk_dev, m.off, d_missing);
+                                                                        m.blk_dev, m.off, d_missing, c->n_nodes);
     CU(cudaGetLastError());
   }
   int missing = 0;
@@ -912,6 +1124,13 @@ extern "C" int a2ds_mat_create_natural(a2ds_ctx *c, int *mat) {
   if (missing) {
     for (void *p : m.owned) cudaFree(p);
     return fail("a2ds_mat_create_natural: the pattern misses " + std::to_string(missing) + " element blocks");
+  }
+  if (n_scratch) {
+    std::vector<HostBlock> hh(1, HostBlock{c->nat_rowp->data(), c->nat_cols->data(), nullptr, nullptr, 0, c->n_nodes});
+    if (build_dep_fold(c, hh, m, "a2ds_mat_create_natural")) {
+      for (void *p : m.owned) cudaFree(p);
+      return 1;
+    }
   }
   m.shared_hash = &c->nat_hash;
   c->mats.push_back(std::move(m));
@@ -1752,6 +1971,8 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   if (!c->mesh_set) return fail("assemble: mesh or nodes not set");
   if (c->npe != 4 && c->scatter_mode != A2DS_SCATTER_ATOMIC)
     return fail("assemble: 9-node elements are assembled with the atomic scatter only");
+  if (c->n_dep && c->scatter_mode != A2DS_SCATTER_ATOMIC)
+    return fail("assemble: meshes with dependent nodes are assembled with the atomic scatter only");
   if (build_lists(c)) return 1;
   const int what = rq.what & 7;
   const bool RES = rq.what & 1, KM = (rq.what & 2) != 0, GM = (rq.what & 4) != 0,
@@ -1775,7 +1996,7 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   auto natural = [&](int mat) { return c->mats[mat].n_blocks == 1 && c->mats[mat].shared_hash != nullptr; };
   const bool zero_natural = c->stream_zero && (KM || GM) && (!KM || natural(kmat)) && (!GM || natural(gmat));
   const bool streamed = c->npe == 4 && A2DS_ZWAIT == 0 && c->stream_chunks > 1 && rq.zero && rq.finish &&
-                        c->n_colors == 1 && n_nonempty == 1 &&
+                        c->n_colors == 1 && n_nonempty == 1 && c->n_dep == 0 &&
                         c->list_dev[only_cls][0] == nullptr && c->n_elems >= c->stream_min_elems &&
                         !MM && !MRES && what != 0 &&
                         ((c->state_pending && c->up_chunks > 1) || (rq.res_host && RES) ||
@@ -1784,7 +2005,7 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   if (rq.zero) {
     c->last_launches = 0;
     CU(cudaEventRecord(c->ev0, c->stream));
-    if (RES) CU(cudaMemsetAsync(c->res, 0, 6 * (size_t)c->n_nodes * sizeof(double), c->stream));
+    if (RES) CU(cudaMemsetAsync(c->res, 0, 6 * c->n_ext() * sizeof(double), c->stream));
     // the tangent / geometric matrices are zeroed by the first element kernel itself when
     // that is k_assemble_t in a single launch per class (atomic scatter); otherwise here
     static const bool ikz_env = !(getenv("A2DS_INKERNEL_ZERO") && atoi(getenv("A2DS_INKERNEL_ZERO")) == 0);
@@ -1820,6 +2041,8 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     if (run_streamed(c, rq, p, only_cls, what, zero_streamed)) return 1;
   } else {
     if (state_wait(c)) return 1;  // the upload overlapped the zeroing above
+    // state (and accelerations) of the dependent nodes: TACSBVec::endDistributeValues
+    if (c->n_dep && (dep_gather(c, c->u, 6) || (c->udd && dep_gather(c, c->udd, 6)))) return 1;
     for (int col = 0; col < c->n_colors; col++) {
       for (int cls = 0; cls < 4; cls++) {
         p.n_list = c->list_len[cls][col];
@@ -1841,6 +2064,18 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     }
   }
   if (!streamed) CU(cudaEventRecord(c->evk1, c->stream));
+  if (c->n_dep) {
+    // what the elements added to dependent rows / node pairs goes to the independent nodes with
+    // the weights (TACSBVec::beginSetValues, TACSAssembler::addMatValues); the scratch is cleared
+    if (RES) {
+      k_dep_scatter<<<(c->n_dep * 6 + 127) / 128, 128, 0, c->stream>>>(c->n_dep, 6, c->n_nodes, c->dep_ptr,
+                                                                      c->dep_conn, c->dep_w, c->res);
+      c->last_launches++;
+    }
+    if (KM && dep_fold(c, c->mats[kmat])) return 1;
+    if (GM && !(KM && gmat == kmat) && dep_fold(c, c->mats[gmat])) return 1;
+    if (MM && !(KM && mmat == kmat) && !(GM && mmat == gmat) && dep_fold(c, c->mats[mmat])) return 1;
+  }
   if (!rq.finish) return 0;
   // ghost residual contributions -> owners (TACSBVec::beginSetValues/endSetValues, ADD)
   if (!streamed) {
@@ -1948,6 +2183,8 @@ extern "C" int a2ds_add_jacobian_vec_product_dev(a2ds_ctx *c, double scale, doub
   CU(cudaSetDevice(c->device));
   if (!c->mesh_set) return fail("addJacobianVecProduct: mesh or nodes not set");
   if (c->npe != 4) return fail("addJacobianVecProduct: 4-node elements only");
+  if (c->n_dep) return fail("addJacobianVecProduct: not available on meshes with dependent nodes "
+                            "(assemble the tangent and use a2ds_mat_mult)");
   if (((uintptr_t)x_dev & 15) || ((uintptr_t)y_dev & 7))
     return fail("addJacobianVecProduct: x must be 16-byte aligned (rows are fetched with 16-byte cp.async)");
   if (build_lists(c)) return 1;

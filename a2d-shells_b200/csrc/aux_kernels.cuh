@@ -16,14 +16,17 @@ struct BlockDev {
 // element -> block offset table; replaces TACSSchurMat::addValues' findIndex +
 // BCSRMat::addRowValues' bsearch (TACSSchurMat.cpp:453-531, BCSRMat.cpp:1778-1827)
 // (npe nodes per element: npe * npe slots per element, slot = npe * i + j for node pair (i, j))
+// Node ids >= n_indep are dependent nodes (rows behind the independent ones): their slots are
+// left at -1 here and pointed at the matrix's fold scratch afterwards (k_dep_patch_offsets).
 __global__ void k_build_offsets(int n_elems, int npe, const int *conn, int n_blocks, const BlockDev *blk,
-                                int *off, int *missing) {
+                                int *off, int *missing, int n_indep) {
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const int n2 = npe * npe;
   if (t >= n2 * (size_t)n_elems) return;
   const size_t e = t / n2;
   const int slot = (int)(t - e * n2);
   const int rn = conn[npe * e + slot / npe], cn = conn[npe * e + slot % npe];
+  if (rn >= n_indep || cn >= n_indep) { off[t] = -1; return; }
   int found = -1;
   for (int b = 0; b < n_blocks && found < 0; b++) {
     const int rr = blk[b].row_map ? blk[b].row_map[rn] : (rn < blk[b].nrows ? rn : -1);
@@ -38,6 +41,57 @@ __global__ void k_build_offsets(int n_elems, int npe, const int *conn, int n_blo
   }
   off[t] = found;
   if (found < 0) atomicAdd(missing, 1);
+}
+
+// ---- dependent nodes ---------------------------------------------------------------------------
+// A dependent node d is the weighted sum of the independent nodes conn[ptr[d] .. ptr[d + 1])
+// (TACSAssembler::setDependentNodes, src/TACSAssembler.cpp:716-775).  On the device it is one
+// more row behind the n_indep local rows of X / u / res, so that the element kernels gather
+// and scatter it like any node; the kernels here fill those rows before the element pass and
+// distribute what the elements added to them afterwards.
+//
+// v[n_indep + d] = sum_j w_j v[conn_j], accumulated from zero in list order
+// (TACSBVec::endDistributeValues, src/bpmat/TACSBVec.cpp:930-975)
+__global__ void k_dep_gather(int n_dep, int nc, int n_indep, const int *ptr, const int *conn,
+                             const double *w, double *v) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_dep * nc) return;
+  const int d = t / nc, k = t - d * nc;
+  double z = 0.0;
+  for (int j = ptr[d]; j < ptr[d + 1]; j++) z += w[j] * v[(size_t)nc * conn[j] + k];
+  v[(size_t)nc * (n_indep + d) + k] = z;
+}
+// v[conn_j] += w_j v[n_indep + d], then the dependent row is cleared
+// (TACSBVec::beginSetValues with TACS_ADD_VALUES / endSetValues, TACSBVec.cpp:855-910)
+__global__ void k_dep_scatter(int n_dep, int nc, int n_indep, const int *ptr, const int *conn,
+                              const double *w, double *v) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_dep * nc) return;
+  const int d = t / nc, k = t - d * nc;
+  const double z = v[(size_t)nc * (n_indep + d) + k];
+  v[(size_t)nc * (n_indep + d) + k] = 0.0;
+  for (int j = ptr[d]; j < ptr[d + 1]; j++) atomicAdd(&v[(size_t)nc * conn[j] + k], w[j] * z);
+}
+// element -> block offsets of the node pairs with a dependent node: fold slot s lives in block
+// base + s of the value array (behind the matrix proper)
+__global__ void k_dep_patch_offsets(int n_slots, const int *slot_pos, int base, int *off) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_slots) off[slot_pos[s]] = base + s;
+}
+// W^T K_e W (TACSAssembler::addMatValues -> addWeightValues, src/TACSAssembler.h:485-510): the
+// element block a kernel added to fold slot s goes to every (independent row, independent
+// column) pair behind it with the product of the two weights; the slot is cleared for the next
+// assembly.  The target list is built on the host when the matrix is created.
+__global__ void k_dep_fold(int n_slots, long long base, const int *fptr, const int *ftgt,
+                           const double *fw, double *A) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= 36 * (size_t)n_slots) return;
+  const int s = (int)(t / 36), k = (int)(t - 36 * (size_t)s);
+  double *src = A + 36 * (size_t)(base + s) + k;
+  const double v = *src;
+  *src = 0.0;
+  if (v == 0.0) return;
+  for (int j = fptr[s]; j < fptr[s + 1]; j++) atomicAdd(&A[36 * (size_t)ftgt[j] + k], fw[j] * v);
 }
 
 // ---- non-zero pattern of the natural-order matrix on the device -------------------------------

@@ -31,6 +31,11 @@ class DeviceAssembler {
     check(a2ds_set_mesh(ctx_, n_nodes, n_owned, n_elems, conn, elem_comp), "a2ds_set_mesh");
     n_nodes_ = n_nodes; n_owned_ = n_owned;
   }
+  // TACSAssembler::setDependentNodes — before setMesh, as the reference wants it before
+  // initialize(); the connectivity then refers to dependent node d as -(d + 1)
+  void setDependentNodes(int n_dep, const int *dep_ptr, const int *dep_conn, const double *dep_weights) {
+    check(a2ds_set_dependent_nodes(ctx_, n_dep, dep_ptr, dep_conn, dep_weights), "a2ds_set_dependent_nodes");
+  }
   void setNodes(const double *X) { check(a2ds_set_nodes(ctx_, X), "a2ds_set_nodes"); }
   void setComponents(int n_comp, const double *Cs, const double *eth, const double *temperature,
                      const int *elem_class, int transform, const double *ref_axis) {

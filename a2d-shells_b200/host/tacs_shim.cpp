@@ -113,6 +113,14 @@ static void shim_upload_components(TACSAssembler *self, Shim &S, bool first) {
     }
     S.n_nodes = self->numNodes;
     S.npe = npe;
+    if (self->numDependentNodes > 0) {
+      // dependent nodes (TACSAssembler::setDependentNodes): elementTacsNodes refers to them as
+      // -(d + 1), which is what a2ds_set_mesh expects once the weights are declared
+      const int *dp = nullptr, *dc = nullptr;
+      const double *dw = nullptr;
+      const int nd = self->depNodes->getDepNodes(&dp, &dc, &dw);
+      CK(a2ds_set_dependent_nodes(S.ctx, nd, dp, dc, dw));
+    }
     CK(a2ds_set_mesh_order(S.ctx, npe == 9 ? 3 : 2, S.n_nodes, self->numOwnedNodes, ne, conn.data(),
                            elem_comp.data()));
     const int *nodes, *vars;
@@ -181,10 +189,6 @@ static Shim &shim_get(TACSAssembler *self) {
   if (first) {
     if (self->mpiSize != 1) {
       fprintf(stderr, "[a2ds shim] multi-rank assemblers are not supported by the shim\n");
-      abort();
-    }
-    if (self->numDependentNodes != 0) {
-      fprintf(stderr, "[a2ds shim] dependent nodes are not supported\n");
       abort();
     }
     const char *dev = getenv("A2DS_DEVICE");

@@ -86,6 +86,24 @@ int a2ds_set_mesh(a2ds_ctx *ctx, int n_nodes, int n_owned, int n_elems, const in
 int a2ds_set_mesh_order(a2ds_ctx *ctx, int order, int n_nodes, int n_owned, int n_elems,
                         const int *conn, const int *elem_comp);
 
+/* TACSAssembler::setDependentNodes (src/TACSAssembler.cpp:716-775).  Dependent node d is the
+ * weighted sum  sum_j dep_weights[j] * node dep_conn[j],  j in dep_ptr[d] .. dep_ptr[d + 1]
+ * (local independent nodes), and appears in the connectivity as the entry -(d + 1), exactly as
+ * in the reference's elementTacsNodes.  Like the reference (before initialize()) the call comes
+ * BEFORE a2ds_set_mesh / a2ds_set_mesh_order, which apply it; n_dep = 0 withdraws it.  Replaces
+ * the dependent-node branches of TACSBVec::endDistributeValues / beginSetValues
+ * (src/bpmat/TACSBVec.cpp:930-975, :855-885: values of a dependent node gathered from, residual
+ * rows distributed to its independent nodes), TACSAssembler::addMatValues ->
+ * addWeightValues (src/TACSAssembler.h:469-510: W^T K_e W) and computeLocalNodeToNodeCSR
+ * (src/TACSAssembler.cpp:1850-1935: the pattern couples all independent nodes behind an
+ * element).  On the device a dependent node is one more row behind the local rows of X / u /
+ * res, the element kernels are unchanged; node pairs with a dependent node go to scratch blocks
+ * behind the matrix and are distributed by a fold kernel whose target list is built with the
+ * matrix.  Vectors at the boundary keep n_nodes rows.  Atomic scatter only; the matrix-free
+ * product and the streamed assembly are not available on such meshes. */
+int a2ds_set_dependent_nodes(a2ds_ctx *ctx, int n_dep, const int *dep_ptr, const int *dep_conn,
+                             const double *dep_weights);
+
 /* TACSAssembler::setNodes (src/TACSAssembler.cpp:912): X[3 n + k], all local nodes */
 int a2ds_set_nodes(a2ds_ctx *ctx, const double *X);
 

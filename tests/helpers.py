@@ -117,7 +117,7 @@ def with_dependent_nodes(conn, X, bc_nodes, n_dep, seed=0, npe=4):
         v = int(v)
         if len(chosen) == n_dep:
             break
-        if v in banned:
+        if v in banned or len(node_elems[v]) < 4:   # interior corner nodes: the patch surrounds them
             continue
         nb = sorted(set(int(w) for e in node_elems[v] for w in conn[e]) - {v})
         if any(w in nbrs_of for w in nb):      # a dependent node never depends on another one

@@ -58,6 +58,45 @@ if len(sys.argv) > 1 and sys.argv[1] == "quad9":
                                          a_max=float(np.abs(A).max()), a_sum=float(A.sum()),
                                          a_chk=float((A * w).sum()))))
     sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "dep":
+    # a cylinder with DEPENDENT nodes (TACSCreator::setDependentNodes): K and G into the four
+    # TACSSchurMat blocks, the buckling flow, and a Jacobian into a TACSParallelMat
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import with_dependent_nodes
+    conn, X, ends = a2ds_meshes.cylinder(40, 20)
+    conn2, Xi, ends2, dep = with_dependent_nodes(conn, X, ends, 30, seed=3)
+    bc_vars = [[0, 1, 2, 5]] * len(ends2)
+    bc_vals = [[-1e-3 if i >= 40 else 0.0, 0.0, 0.0, 0.0] for i in range(len(ends2))]
+    ra = refdrv.RefAssembler(conn2, Xi, np.zeros(len(conn2), dtype=np.int32), refdrv.iso_props()[None],
+                             ends2, bc_vars, bc_vals, dep=dep)
+    n = len(Xi)
+    km, gm, am = ra.mat_create(1), ra.mat_create(1), ra.mat_create(1)
+    u = np.zeros((n, 6)); u[ra.new_nodes] = a2ds_meshes.seeded_state(np.arange(n), 1e-3)
+    ra.set_state(u)
+    chk = {}
+    for typ, mat, tag in ((0, km, "k"), (1, gm, "g")):
+        ra.assemble_mat_type(typ, mat)
+        tot, mx = 0.0, 0.0
+        for which in range(4):
+            blk = ra.mat_block(mat, which)
+            if blk is None or blk["A"].size == 0:
+                continue
+            Ab = blk["A"]
+            tot += float((Ab * np.cos(np.arange(Ab.size) + which).reshape(Ab.shape)).sum())
+            mx = max(mx, float(np.abs(Ab).max()))
+        chk[tag + "_chk"] = tot; chk[tag + "_max"] = mx
+    eig, err = ra.buckling(km, gm, am, 0, sigma=12.0, num_eigs=50, max_lanczos=100, u0=None)
+    pm = ra.mat_create(0)
+    u = np.zeros((n, 6)); u[ra.new_nodes] = a2ds_meshes.seeded_state(np.arange(n), 1e-5)
+    ra.set_state(u)
+    r = ra.assemble_jacobian(pm)
+    A = ra.mat_block(pm, 0)["A"]
+    w = np.cos(np.arange(A.size)).reshape(A.shape)
+    print("SHIM_PROBE " + json.dumps(dict(eig=eig[:6].tolist(), err=err[:6].tolist(), **chk,
+                                         res_norm=float(np.abs(r).max()),
+                                         res_chk=float((r * w.ravel()[:r.size].reshape(r.shape)).sum()),
+                                         a_max=float(np.abs(A).max()), a_chk=float((A * w).sum()))))
+    sys.exit(0)
 conn, X, ends = a2ds_meshes.cylinder(40, 20)
 bc_vars = [[0, 1, 2, 5]] * len(ends)
 bc_vals = [[-1e-3 if i >= 40 else 0.0, 0.0, 0.0, 0.0] for i in range(len(ends))]

@@ -1041,3 +1041,158 @@ def test_quad9_empty_and_single_element(a2ds, orc):
     G = asm.mat_values(g).reshape(9, 9, 6, 6).transpose(0, 2, 1, 3).reshape(54, 54)
     assert relmax(r.ravel(), r_o) < RES_TOL and relmax(K, k_o) < MAT_TOL and relmax(G, g_o) < MAT_TOL
     asm.close()
+
+
+# ---- dependent nodes (TACSAssembler::setDependentNodes) --------------------------------------
+def _dep_case(a2ds, orc, order, n_dep, seed):
+    """curved mesh with n_dep dependent nodes, 6 components of both element classes (with and
+    without membrane-bending coupling, so both 4-node kernel families run), BCs with prescribed
+    values; returns the assembler and the oracle's argument tuple"""
+    from helpers import with_dependent_nodes
+    if order == 2:
+        conn, X, bcn = a2ds.meshes.cylinder(37, 23)
+    else:
+        conn, X, bcn = a2ds.meshes.plate9(19, 14, bump=2e-2)
+    npe = order * order
+    conn2, Xi, bc2, dep = with_dependent_nodes(conn, X, bcn, n_dep, seed=seed, npe=npe)
+    n = len(Xi); ne = len(conn2)
+    rng = np.random.default_rng(seed)
+    ncomp = 6
+    Cs = np.zeros((ncomp, 22)); eth = np.zeros((ncomp, 9)); mom = np.zeros((ncomp, 3))
+    for c in range(ncomp):
+        t = rng.uniform(0.005, 0.02); off = 0.0 if c % 2 == 0 else rng.uniform(-0.4, 0.4)
+        Cs[c], eth[c] = a2ds.iso_shell_tables(t=t, t_offset=off)
+        mom[c] = a2ds.iso_mass_moments(rng.uniform(1e3, 8e3), t, off)
+    cls = np.array([0, 0, 1, 1, 0, 1], dtype=np.int32)
+    elem_comp = rng.integers(0, ncomp, ne).astype(np.int32)
+    u = a2ds.meshes.seeded_state(np.arange(n), 1e-5)
+    udd = a2ds.meshes.seeded_state(np.arange(n) + 4242, 1.0)
+    bc_vars = np.full(len(bc2), 63, dtype=np.int32); bc_vars[::2] = 0b000111
+    bc_vals = np.zeros((len(bc2), 6)); bc_vals[:, 0] = -1e-5
+    asm = a2ds.Assembler(0)
+    asm.set_dependent_nodes(*dep)
+    asm.set_mesh(conn2, n, elem_comp=elem_comp, order=order); asm.set_nodes(Xi)
+    asm.set_components(Cs, eth, elem_class=cls); asm.set_mass_moments(mom)
+    asm.set_bcs(bc2, bc_vars, bc_vals); asm.set_state(u)
+    comps = [orc.make_comp(int(cls[c]), Cs[c], eth[c], mom[c]) for c in range(ncomp)]
+    rowp, cols = orc.pattern_dep(n, conn2, dep[0], dep[1], order=order)
+    oargs = (conn2, elem_comp, comps, Xi, u, dep, rowp, cols, bc2, bc_vars, bc_vals)
+    return asm, oargs, udd
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_dependent_nodes_vs_oracle(a2ds, orc, order):
+    """a mesh with dependent nodes through every assembly entry point: the values of a dependent
+    node are gathered from its independent nodes, its residual rows and the element blocks of
+    its node pairs distributed with the weights (TACSBVec.cpp:855-975, TACSAssembler.h:469-510);
+    pattern bit-exact (computeLocalNodeToNodeCSR with dependent nodes)"""
+    asm, oargs, udd = _dep_case(a2ds, orc, order, 40 if order == 2 else 12, seed=5)
+    rowp_o, cols_o = oargs[6], oargs[7]
+    kw = dict(order=order)
+    kmat = asm.create_mat(); gmat = asm.create_mat()
+    rowp, cols = asm.mat_pattern(kmat)
+    assert np.array_equal(rowp, rowp_o) and np.array_equal(cols, cols_o)
+    r_o, k_o = orc.assemble_dep(1, *oargs, **kw)
+    _, g_o = orc.assemble_dep(3, *oargs, **kw)
+    _, m_o = orc.assemble_dep(4, *oargs, **kw)
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, kmat)
+    assert relmax(r, r_o) < RES_TOL and relmax(asm.mat_values(kmat), k_o) < MAT_TOL
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, gmat)
+    assert relmax(asm.mat_values(gmat), g_o) < MAT_TOL
+    asm.assembleMatType(a2ds.MASS_MATRIX, gmat)
+    assert relmax(asm.mat_values(gmat), m_o) < 1e-13
+    r = asm.assembleAll(kmat, gmat)    # twice: the fold scratch must come back clean
+    r = asm.assembleAll(kmat, gmat)
+    assert relmax(r, r_o) < RES_TOL
+    assert relmax(asm.mat_values(kmat), k_o) < MAT_TOL and relmax(asm.mat_values(gmat), g_o) < MAT_TOL
+    r0_o, _ = orc.assemble_dep(0, *oargs, **kw)
+    assert relmax(asm.assembleRes(), r0_o) < RES_TOL
+    # dynamic terms: accelerations of the dependent nodes are gathered as well
+    asm.set_state_rates(None, udd)
+    r = asm.assembleJacobian(0.7, 0.0, 2.5, kmat)
+    r_o2, j_o = orc.assemble_dep(1, *oargs, alpha=0.7, gamma=2.5, udd=udd, **kw)
+    assert relmax(r, r_o2) < RES_TOL and relmax(asm.mat_values(kmat), j_o) < MAT_TOL
+    asm.set_state_rates(None, None)
+    # assembleMatCombo: K - 3.5 G + 120 M, folded after every pass, BCs once
+    asm.assembleMatCombo([a2ds.STIFFNESS_MATRIX, a2ds.GEOMETRIC_STIFFNESS_MATRIX, a2ds.MASS_MATRIX],
+                         [1.0, -3.5, 120.0], kmat)
+    parts = [orc.assemble_dep(op, *oargs[:8], None, None, None, **kw)[1] for op in (2, 3, 4)]
+    A_o = parts[0] - 3.5 * parts[1] + 120.0 * parts[2]
+    for nd, bv in zip(oargs[8], oargs[9]):
+        for j in range(rowp[nd], rowp[nd + 1]):
+            for k in range(6):
+                if bv & (1 << k):
+                    A_o[j, k, :] = 0.0
+                    if cols[j] == nd:
+                        A_o[j, k, k] = 1.0
+    assert relmax(asm.mat_values(kmat), A_o) < MAT_TOL
+    # a caller-supplied pattern (a2ds_mat_create) takes the same fold plan
+    pm = asm.create_mat_from_pattern([dict(nrows=len(rowp) - 1, rowp=rowp, cols=cols)])
+    asm.assembleMatType(a2ds.STIFFNESS_MATRIX, pm)
+    asm.assembleMatType(a2ds.STIFFNESS_MATRIX, kmat)
+    assert np.array_equal(asm.mat_pattern(pm)[1], cols)
+    assert relmax(asm.mat_values(pm), asm.mat_values(kmat)) < 1e-14
+    # ... and one that lacks the couplings between the independent nodes is refused
+    rp_plain = np.arange(len(rowp), dtype=np.int32); cl_plain = np.arange(len(rowp) - 1, dtype=np.int32)
+    with pytest.raises(RuntimeError):
+        asm.create_mat_from_pattern([dict(nrows=len(rowp) - 1, rowp=rp_plain, cols=cl_plain)])
+    # what such meshes do not provide fails loudly
+    asm.set_scatter_mode(a2ds.SCATTER_COLORED)
+    with pytest.raises(RuntimeError):
+        asm.assembleMatType(a2ds.STIFFNESS_MATRIX, kmat)
+    asm.set_scatter_mode(a2ds.SCATTER_ATOMIC)
+    if order == 2:
+        with pytest.raises(RuntimeError, match="dependent"):
+            asm.addJacobianVecProduct(1.0, 1.0, oargs[4], np.zeros_like(oargs[4]))
+    asm.close()
+
+
+def test_dependent_nodes_against_reference_golden(a2ds):
+    """the reference's own outputs on a panel with dependent nodes (tests/golden/dep.npz, written
+    by the unmodified reference through TACSCreator::setDependentNodes), both element classes"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dep.npz"))
+    n = len(g["X"])
+    for kind in (0, 1):
+        asm = a2ds.Assembler(0)
+        asm.set_dependent_nodes(g["dep_ptr"], g["dep_conn"], g["dep_w"])
+        asm.set_mesh(g["conn"], n); asm.set_nodes(g["X"])
+        asm.set_components(g["Cs"][None], g["eth"][None], elem_class=[kind])
+        asm.set_mass_moments(g["mom"][None])
+        asm.set_bcs(g["bc_nodes"], g["bc_vars"], g["bc_vals"]); asm.set_state(g["u"])
+        mat = asm.create_mat()
+        rowp, cols = asm.mat_pattern(mat)
+        assert rowp.tobytes() == g["rowp"].tobytes() and cols.tobytes() == g["cols"].tobytes()
+        r = asm.assembleJacobian(1.0, 0.0, 0.0, mat)
+        assert relmax(r, g["res%d" % kind]) < RES_TOL
+        assert relmax(asm.mat_values(mat), g["K%d" % kind]) < MAT_TOL
+        asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, mat)
+        assert relmax(asm.mat_values(mat), g["G%d" % kind]) < MAT_TOL
+        asm.assembleMatType(a2ds.MASS_MATRIX, mat)
+        assert relmax(asm.mat_values(mat), g["M%d" % kind]) < 1e-13
+        asm.set_state_rates(None, g["udd"])
+        r = asm.assembleJacobian(1.0, 0.0, 3.0, mat)
+        assert relmax(r, g["res_dyn%d" % kind]) < RES_TOL
+        assert relmax(asm.mat_values(mat), g["J%d" % kind]) < MAT_TOL
+        asm.close()
+
+
+def test_dependent_nodes_declaration_errors(a2ds):
+    """undeclared or inconsistent dependent nodes are refused at a2ds_set_mesh"""
+    conn, X, _ = a2ds.meshes.plate(4, 4)
+    bad = conn.copy(); bad[3, 2] = -1
+    asm = a2ds.Assembler(0)
+    with pytest.raises(RuntimeError, match="a2ds_set_dependent_nodes"):
+        asm.set_mesh(bad, len(X))
+    asm.set_dependent_nodes([0, 2], [0, len(X) + 5], [0.5, 0.5])     # refers to a node that is not there
+    with pytest.raises(RuntimeError):
+        asm.set_mesh(bad, len(X))
+    asm.set_dependent_nodes([0, 2], [0, 1], [0.5, 0.5])
+    bad[3, 2] = -2                                                    # only one dependent node declared
+    with pytest.raises(RuntimeError):
+        asm.set_mesh(bad, len(X))
+    with pytest.raises(RuntimeError):
+        asm.set_dependent_nodes([0, 2], [0, -1], [0.5, 0.5])          # dependent on a dependent node
+    asm.set_dependent_nodes(None, None, None)                        # withdrawn: plain meshes again
+    asm.set_mesh(conn, len(X))
+    asm.close()

@@ -86,3 +86,24 @@ def test_reference_buckling_flow_with_quad9_shells_through_the_shim(ref):
         assert abs(gpu[tag + "_max"] - base[tag + "_max"]) <= 1e-10 * base[tag + "_max"]
         assert abs(gpu[tag + "_chk"] - base[tag + "_chk"]) <= 1e-9 * base[tag + "_max"]
     assert abs(gpu["path_chk"] - base["path_chk"]) <= 1e-10 * base["path_max"]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_gpu(), reason="no CUDA device")
+def test_reference_flow_with_dependent_nodes_through_the_shim(ref):
+    """a reference assembler WITH dependent nodes (TACSCreator::setDependentNodes): the shim hands
+    them to a2ds_set_dependent_nodes; K and G in the TACSSchurMat blocks, the Jacobian in a
+    TACSParallelMat, the residual and the buckling eigenvalues against the reference's own path"""
+    if not os.path.exists(SHIM):
+        pytest.skip("shim not built (needs the reference headers)")
+    base, _ = _run(False, "dep")
+    gpu, log = _run(True, "dep")
+    assert "[a2ds shim]" in log and "device assembly" in log
+    e0, e1 = np.array(base["eig"])[:4], np.array(gpu["eig"])[:4]
+    assert np.all(np.array(base["err"])[:4] < 1e-6)
+    assert np.all(np.abs(e1 - e0) <= 1e-8 * np.abs(e0)), (e0, e1)
+    assert abs(gpu["res_norm"] - base["res_norm"]) <= 1e-12 * base["res_norm"]
+    assert abs(gpu["res_chk"] - base["res_chk"]) <= 1e-11 * base["res_norm"]
+    for tag in ("a", "k", "g"):
+        assert abs(gpu[tag + "_max"] - base[tag + "_max"]) <= 1e-10 * base[tag + "_max"]
+        assert abs(gpu[tag + "_chk"] - base[tag + "_chk"]) <= 1e-9 * base[tag + "_max"]

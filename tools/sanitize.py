@@ -79,4 +79,30 @@ r9 = asm.assembleJacobian(1.0, 0.0, 0.0, k9); asm.assembleRes(); asm.assembleMat
 asm.assembleMatType(1, g9); asm.assembleAll(k9, g9)
 print("quad9", float(np.abs(r9).max()), float(np.abs(asm.mat_values(k9)).max()), float(np.abs(asm.mat_values(g9)).max()))
 asm.close()
+# dependent nodes: two interior nodes of a plate replaced by the weighted mean of the 8 nodes
+# around them (k_dep_gather / k_dep_scatter / k_dep_fold, scratch blocks behind the matrix)
+os.environ["A2DS_STREAM_CHUNKS"] = "1"
+asm = a2ds.Assembler(0)
+connd, Xd, bcd = a2ds.meshes.plate(8, 6, bump=2e-2)
+nd_ = len(Xd)
+picks = [2 * 9 + 2, 3 * 9 + 5]
+keep = np.ones(nd_, bool); keep[picks] = False
+new = -np.ones(nd_, dtype=np.int64); new[keep] = np.arange(keep.sum())
+dp, dc, dw = [0], [], []
+for d, v in enumerate(picks):
+    nb = sorted(set(int(w) for e in connd if v in e for w in e) - {v})
+    dc += [int(new[w]) for w in nb]; dw += [1.0 / len(nb)] * len(nb); dp.append(len(dc))
+    new[v] = -(d + 1)
+asm.set_dependent_nodes(dp, dc, dw)
+asm.set_mesh(new[connd].astype(np.int32), int(keep.sum()), elem_comp=(np.arange(len(connd)) % 2).astype(np.int32))
+asm.set_nodes(Xd[keep])
+asm.set_components(np.stack([Cs2, Cs]), np.stack([eth2, eth]), elem_class=[1, 0])   # both kernel families
+asm.set_mass_moments(np.tile(a2ds.iso_mass_moments(2700.0, 0.01, 0.2), (2, 1)))
+asm.set_bcs(new[bcd].astype(np.int32), 63)
+asm.set_state(a2ds.meshes.seeded_state(np.arange(int(keep.sum())), 1e-4))
+kd, gd = asm.create_mat(), asm.create_mat()
+rd = asm.assembleAll(kd, gd); asm.assembleJacobian(1.0, 0.0, 2.0, kd); asm.assembleRes()
+asm.assembleMatCombo([0, 1, 2], [1.0, 0.5, -3.0], gd)
+print("dependent nodes", float(np.abs(rd).max()), float(np.abs(asm.mat_values(kd)).max()))
+asm.close()
 print("SANITIZE_DRIVER_DONE")
