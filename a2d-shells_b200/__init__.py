@@ -8,7 +8,7 @@ structured meshes the benchmark runs on.  There is no CPU path: importing works
 anywhere, creating an `Assembler` needs the library and a B200.
 """
 from . import meshes  # noqa: F401
-from .capi import (Assembler, Mesh, Partition, partition_rcb, halo_from_distribute, A2dsError, host_pattern, host_color_elements, lib_path, load_library, SCATTER_ATOMIC,  # noqa: F401
+from .capi import (Assembler, Mesh, Partition, partition_rcb, halo_from_distribute, A2dsError, host_pattern, host_color_elements, host_color_elements_hashed, lib_path, load_library, SCATTER_ATOMIC,  # noqa: F401
                    SCATTER_COLORED, SCATTER_ATOMIC_COLOR_ORDER, STIFFNESS_MATRIX, GEOMETRIC_STIFFNESS_MATRIX, MASS_MATRIX,
                    QUAD4_SHELL, QUAD4_NONLINEAR_SHELL, TRANSFORM_NATURAL, TRANSFORM_REF_AXIS)
 from .constitutive import iso_shell_tables, iso_mass_moments  # noqa: F401

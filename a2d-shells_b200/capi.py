@@ -28,6 +28,7 @@ SYMBOLS = [
     "a2ds_comm_unique_id", "a2ds_comm_init", "a2ds_set_halo", "a2ds_halo_forward",
     "a2ds_halo_from_distribute",
     "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
+    "a2ds_host_color_elements_hashed", "a2ds_get_element_colors",
     "a2ds_last_kernel_ms", "a2ds_region_begin", "a2ds_region_end",
     "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
     "a2ds_add_jacobian_vec_product", "a2ds_add_jacobian_vec_product_dev",
@@ -121,6 +122,18 @@ def host_color_elements(n_nodes, conn):
     nc = C.c_int()
     if L.a2ds_host_color_elements(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(color),
                                   C.byref(nc)):
+        raise A2dsError(L.a2ds_last_error().decode())
+    return color, nc.value
+
+
+def host_color_elements_hashed(n_nodes, conn):
+    """the device's colouring rule (hashed-priority greedy) stepped on the host"""
+    L = load_library()
+    conn = _i32(conn).reshape(-1, 4)
+    color = np.zeros(conn.shape[0], dtype=np.int32)
+    nc = C.c_int()
+    if L.a2ds_host_color_elements_hashed(C.c_int(n_nodes), C.c_int(conn.shape[0]), _p(conn), _p(color),
+                                         C.byref(nc)):
         raise A2dsError(L.a2ds_last_error().decode())
     return color, nc.value
 
@@ -448,6 +461,13 @@ class Assembler:
 
     def set_scatter_mode(self, mode):
         self._chk(self.L.a2ds_set_scatter_mode(self.ctx, C.c_int(mode)))
+
+    def element_colors(self):
+        """element colours of the coloured scatter modes, computed on the device"""
+        color = np.zeros(self.n_elems, dtype=np.int32)
+        nc = C.c_int()
+        self._chk(self.L.a2ds_get_element_colors(self.ctx, _p(color), C.byref(nc)))
+        return color, nc.value
 
     # -- matrices -----------------------------------------------------------------
     def create_mat(self):

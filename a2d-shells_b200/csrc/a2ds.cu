@@ -663,6 +663,107 @@ static void color_elements(int nn, int ne, const int *conn, std::vector<int> &co
   }
 }
 
+// The colouring rule of the device (aux_kernels.cuh, k_color_round) stepped sequentially:
+// greedy in decreasing order of color_key.  Bit-identical to the device's result.
+static void color_elements_hashed(int nn, int ne, const int *conn, std::vector<int> &color,
+                                  int &n_colors) {
+  std::vector<int> ptr(nn + 1, 0);
+  for (size_t i = 0; i < 4 * (size_t)ne; i++) ptr[conn[i] + 1]++;
+  for (int i = 0; i < nn; i++) ptr[i + 1] += ptr[i];
+  std::vector<int> adj(ptr[nn]), fill(ptr.begin(), ptr.end() - 1);
+  for (int e = 0; e < ne; e++)
+    for (int i = 0; i < 4; i++) adj[fill[conn[4 * e + i]]++] = e;
+  std::vector<unsigned long long> order(ne);
+  for (int e = 0; e < ne; e++) order[e] = color_key(e);
+  std::sort(order.begin(), order.end(), std::greater<unsigned long long>());
+  color.assign(ne, -1);
+  n_colors = 0;
+  std::vector<int> mark;
+  for (int s = 0; s < ne; s++) {
+    const int e = (int)(order[s] & 0xffffffffu);
+    for (int i = 0; i < 4; i++) {
+      const int n = conn[4 * e + i];
+      for (int k = ptr[n]; k < ptr[n + 1]; k++) {
+        const int o = adj[k];
+        if (color[o] >= 0) {
+          if (color[o] >= (int)mark.size()) mark.resize(color[o] + 1, -1);
+          mark[color[o]] = e;
+        }
+      }
+    }
+    int col = 0;
+    while (col < (int)mark.size() && mark[col] == e) col++;
+    color[e] = col;
+    n_colors = std::max(n_colors, col + 1);
+  }
+}
+
+// Element colours of the context's mesh, computed on the device (k_pat_count / k_pat_fill give
+// the elements around every node, k_color_round sweeps until nothing is left); the host copy is
+// one download.  The reference has no counterpart: its element loop is sequential per thread
+// and adds under a mutex (src/TACSAssembler.cpp:4561-4576).
+static int color_elements_device(a2ds_ctx *c, std::vector<int> &color, int &n_colors) {
+  const int nn = c->n_nodes, ne = c->n_elems;
+  const size_t n4 = 4 * (size_t)ne;
+  color.assign(ne, 0);
+  n_colors = ne ? 1 : 0;
+  if (!ne) return 0;
+  int *deg = nullptr, *ptr = nullptr, *adj = nullptr, *col = nullptr, *left = nullptr;
+  void *tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(deg); cudaFree(ptr); cudaFree(adj); cudaFree(col); cudaFree(left); cudaFree(tmp); };
+  CU(cudaMalloc((void **)&deg, ((size_t)nn + 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&ptr, ((size_t)nn + 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&adj, n4 * sizeof(int)));
+  CU(cudaMalloc((void **)&col, (size_t)ne * sizeof(int)));
+  CU(cudaMalloc((void **)&left, sizeof(int)));
+  CU(cudaMemsetAsync(deg, 0, ((size_t)nn + 1) * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(col, 0xff, (size_t)ne * sizeof(int), c->stream));
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, ptr, nn + 1, c->stream);
+  CU(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+  const unsigned g4 = (unsigned)((n4 + 255) / 256), ge = (unsigned)((ne + 255) / 256);
+  k_pat_count<<<g4, 256, 0, c->stream>>>(n4, c->conn, deg);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, ptr, nn + 1, c->stream);
+  CU(cudaMemsetAsync(deg, 0, ((size_t)nn + 1) * sizeof(int), c->stream));   // reused as the fill cursor
+  k_pat_fill<<<g4, 256, 0, c->stream>>>(n4, c->conn, ptr, deg, adj);
+  int remaining = ne, rounds = 0;
+  while (remaining > 0) {
+    CU(cudaMemsetAsync(left, 0, sizeof(int), c->stream));
+    k_color_round<<<ge, 256, 0, c->stream>>>(ne, c->conn, ptr, adj, col, left);
+    int now = 0;
+    CU(cudaMemcpyAsync(&now, left, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (now >= remaining && ++rounds > 4) {   // cannot happen: the highest key always colours itself
+      cleanup();
+      return fail("element colouring on the device made no progress");
+    }
+    if (now < remaining) rounds = 0;
+    remaining = now;
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(color.data(), col, (size_t)ne * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cleanup();
+  for (int e = 0; e < ne; e++) n_colors = std::max(n_colors, color[e] + 1);
+  return 0;
+}
+
+// colours of the context's mesh, whichever way they are made (A2DS_HOST_COLORING=1: the host
+// pass of the same rule; =2: the natural-order greedy pass of a2ds_host_color_elements)
+static int mesh_colors(a2ds_ctx *c, std::vector<int> &color, int &n_colors) {
+  static const int host_rule = getenv("A2DS_HOST_COLORING") ? atoi(getenv("A2DS_HOST_COLORING")) : 0;
+  if (c->npe != 4) return fail("element colouring: 4-node meshes only");
+  if (host_rule == 2) {   // natural-order greedy: sequential by nature, fewest colours on structured meshes
+    color_elements(c->n_nodes, c->n_elems, c->h_conn.data(), color, n_colors);
+    return 0;
+  }
+  if (host_rule) {
+    color_elements_hashed(c->n_nodes, c->n_elems, c->h_conn.data(), color, n_colors);
+    return 0;
+  }
+  return color_elements_device(c, color, n_colors);
+}
+
 static int build_lists(a2ds_ctx *c) {
   if (c->lists_ready) return 0;
   if (c->n_comp == 0) return fail("assemble: a2ds_set_components has not been called");
@@ -673,8 +774,11 @@ static int build_lists(a2ds_ctx *c) {
       return fail("assemble: element component index out of range");
   std::vector<int> color;
   int ncol = 1;
-  if (c->scatter_mode != A2DS_SCATTER_ATOMIC)
-    color_elements(c->n_nodes, c->n_elems, c->h_conn.data(), color, ncol);
+  if (c->scatter_mode != A2DS_SCATTER_ATOMIC) {
+    StageTimer tm;
+    if (mesh_colors(c, color, ncol)) return 1;
+    tm.lap("element colouring");
+  }
   // colour order in ONE launch: the lists of the colours are concatenated, so that elements
   // in flight together rarely share a node (fewer RED collisions in L2), without the launch
   // boundaries (and the reproducibility) of the coloured mode
@@ -705,6 +809,19 @@ static int build_lists(a2ds_ctx *c) {
   }
   c->lists_ready = true;
   return 0;
+}
+
+extern "C" int a2ds_get_element_colors(a2ds_ctx *c, int *color, int *n_colors) {
+  A2DS_TRY
+  if (!c->mesh_set) return fail("a2ds_get_element_colors: call a2ds_set_mesh first");
+  CU(cudaSetDevice(c->device));
+  std::vector<int> col;
+  int nc = 0;
+  if (mesh_colors(c, col, nc)) return 1;
+  if (color && !col.empty()) memcpy(color, col.data(), col.size() * sizeof(int));
+  if (n_colors) *n_colors = nc;
+  return 0;
+  A2DS_CATCH(a2ds_get_element_colors)
 }
 
 // ---- dependent nodes: the fold plan of a matrix -------------------------------------------
@@ -1016,6 +1133,18 @@ extern "C" int a2ds_host_color_elements(int n_nodes, int n_elems, const int *con
   *n_colors = nc;
   return 0;
   A2DS_CATCH(a2ds_host_color_elements)
+}
+
+extern "C" int a2ds_host_color_elements_hashed(int n_nodes, int n_elems, const int *conn, int *color,
+                                               int *n_colors) {
+  A2DS_TRY
+  std::vector<int> col;
+  int nc = 0;
+  color_elements_hashed(n_nodes, n_elems, conn, col, nc);
+  if (!col.empty()) memcpy(color, col.data(), col.size() * sizeof(int));
+  *n_colors = nc;
+  return 0;
+  A2DS_CATCH(a2ds_host_color_elements_hashed)
 }
 
 // natural-order pattern built on the device (aux_kernels.cuh, k_pat_*); the host copy is one

@@ -3,6 +3,11 @@
 // HBM-bound matrix algebra of the buckling flow (copy / axpy, 6x6 BCSR mat-vec).
 #ifndef A2DS_AUX_KERNELS_CUH
 #define A2DS_AUX_KERNELS_CUH
+#ifdef __CUDACC__
+#define A2DS_COLOR_HD __host__ __device__ __forceinline__
+#else
+#define A2DS_COLOR_HD inline
+#endif
 
 #include <cuda_runtime.h>
 
@@ -93,6 +98,51 @@ __global__ void k_dep_fold(int n_slots, long long base, const int *fptr, const i
   if (v == 0.0) return;
   for (int j = fptr[s]; j < fptr[s + 1]; j++) atomicAdd(&A[36 * (size_t)ftgt[j] + k], fw[j] * v);
 }
+
+// ---- element colouring on the device --------------------------------------------------------
+// Elements sharing a node get different colours (A2DS_SCATTER_COLORED: one launch per colour,
+// every block / residual row receives at most one contribution per launch).  Rule: greedy in the
+// order of a hashed priority (color_key, ties impossible: the element index is its low word) —
+// an element takes the smallest colour none of its higher-priority neighbours holds.  On the
+// device that is a Jones-Plassmann sweep: per round every uncoloured element whose uncoloured
+// neighbours all have a lower key colours itself; two adjacent elements are never coloured in
+// the same round, and the result does not depend on the timing — it is the colouring the
+// sequential greedy pass in decreasing key order produces (color_elements_hashed on the host,
+// bit-identical).  O(log n) rounds instead of the n-long dependency chain of natural order.
+A2DS_COLOR_HD unsigned long long color_key(int e) {
+  unsigned h = (unsigned)e + 0x9e3779b9u;
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return ((unsigned long long)h << 32) | (unsigned)e;
+}
+#ifdef __CUDACC__
+__global__ void k_color_round(int ne, const int *conn, const int *ptr, const int *adj, int *color,
+                              int *left) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne || __ldcg(&color[e]) >= 0) return;
+  const unsigned long long key = color_key(e);
+  int nodes[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) nodes[i] = conn[4 * (size_t)e + i];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    for (int k = ptr[nodes[i]]; k < ptr[nodes[i] + 1]; k++) {
+      const int o = adj[k];
+      if (o != e && __ldcg(&color[o]) < 0 && color_key(o) > key) { atomicAdd(left, 1); return; }
+    }
+  // every neighbour still uncoloured has a lower key and waits for this element: the colours
+  // read below are final
+  for (int base = 0;; base += 64) {
+    unsigned long long used = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      for (int k = ptr[nodes[i]]; k < ptr[nodes[i] + 1]; k++) {
+        const int co = __ldcg(&color[adj[k]]) - base;
+        if (co >= 0 && co < 64) used |= 1ull << co;
+      }
+    if (~used) { color[e] = base + __ffsll((long long)~used) - 1; return; }
+  }
+}
+#endif
 
 // ---- non-zero pattern of the natural-order matrix on the device -------------------------------
 // TACSAssembler::computeLocalNodeToNodeCSR + TacsSortAndUniquifyCSR (src/TACSAssembler.cpp:1839,

@@ -291,6 +291,15 @@ int a2ds_host_pattern(int n_nodes, int n_elems, const int *conn, int *rowp, int 
  * elements sharing a node never share a colour. */
 int a2ds_host_color_elements(int n_nodes, int n_elems, const int *conn, int *color,
                              int *n_colors);
+/* The colouring rule the device uses (k_color_round, csrc/aux_kernels.cuh): greedy in the order of
+ * a hashed element priority — a Jones-Plassmann sweep, O(log n) rounds on the device — stepped
+ * sequentially on the host; bit-identical to a2ds_get_element_colors. */
+int a2ds_host_color_elements_hashed(int n_nodes, int n_elems, const int *conn, int *color,
+                                    int *n_colors);
+/* Element colours of the context's mesh as A2DS_SCATTER_COLORED / _COLOR_ORDER use them, computed
+ * on the device (4-node meshes; color may be NULL to obtain only *n_colors).  The reference has
+ * no counterpart (its threaded element loop adds under a mutex, src/TACSAssembler.cpp:4561-4576). */
+int a2ds_get_element_colors(a2ds_ctx *ctx, int *color, int *n_colors);
 
 /* ---- partition (host only) ---------------------------------------------------------
  * One rank's part of an element-wise partitioned global mesh and its ghost-exchange plan,

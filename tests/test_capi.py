@@ -85,6 +85,29 @@ def test_structured_plate_needs_four_colors(a2ds):
     assert nc == 4
 
 
+def _fan(m):
+    """m quads around one hub node (a valence-m junction): every pair of them shares the hub"""
+    conn = np.array([[0, 1 + 2 * k, 2 + 2 * k, 1 + (2 * k + 2) % (2 * m)] for k in range(m)], dtype=np.int32)
+    return conn, 2 * m + 1
+
+
+def test_hashed_coloring_is_valid(a2ds):
+    """the device's colouring rule stepped on the host: valid on structured and unstructured
+    meshes, and on a fan that needs more colours than a machine word holds"""
+    cases = [(c, len(X)) for c, X, _ in (a2ds.meshes.plate(11, 7), a2ds.meshes.cylinder(9, 4),
+                                         a2ds.meshes.cubed_sphere(6, shuffle_seed=3))]
+    cases.append(_fan(70))
+    for conn, n in cases:
+        color, nc = a2ds.host_color_elements_hashed(n, conn)
+        assert color.min() == 0 and color.max() == nc - 1
+        for c in range(nc):
+            nodes = conn[color == c].ravel()
+            assert len(nodes) == len(np.unique(nodes))
+    assert nc == 70   # the fan: all elements pairwise adjacent
+    conn, X, _ = a2ds.meshes.plate(40, 40)
+    assert a2ds.host_color_elements_hashed(len(X), conn)[1] <= 9
+
+
 def test_seeded_state_is_partition_independent(a2ds):
     ids = np.arange(1000)
     u = a2ds.meshes.seeded_state(ids, 1e-5)

@@ -267,6 +267,26 @@ def test_deterministic_mode_is_bit_reproducible(a2ds):
     assert outs[0] == outs[1] == outs[2]
 
 
+def test_device_colouring_matches_host_rule(a2ds):
+    """element colours computed on the device (k_color_round) are valid and bit-identical to the
+    sequential pass of the same rule on the host; structured, unstructured / shuffled, and a
+    valence-70 fan (more colours than one 64-bit mask)"""
+    fan = np.array([[0, 1 + 2 * k, 2 + 2 * k, 1 + (2 * k + 2) % 140] for k in range(70)], dtype=np.int32)
+    cases = [(c, len(X)) for c, X, _ in (a2ds.meshes.plate(301, 203), a2ds.meshes.cylinder(64, 40),
+                                         a2ds.meshes.cubed_sphere(12, shuffle_seed=5))]
+    cases.append((fan, 141))
+    for conn, n in cases:
+        asm = a2ds.Assembler(0)
+        asm.set_mesh(conn, n)
+        color, nc = asm.element_colors()
+        asm.close()
+        ref, nref = a2ds.host_color_elements_hashed(n, conn)
+        assert nc == nref and color.tobytes() == ref.tobytes()
+        for c in range(nc):
+            nodes = conn[color == c].ravel()
+            assert len(nodes) == len(np.unique(nodes))
+
+
 def test_properties_at_size(a2ds):
     """size-independent properties on a mesh far beyond what the oracle can check:
     K symmetric (before BCs), K u = r for the linear element, G linear in u."""
