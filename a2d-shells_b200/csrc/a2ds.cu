@@ -680,7 +680,7 @@ static void color_elements_hashed(int nn, int ne, const int *conn, std::vector<i
   n_colors = 0;
   std::vector<int> mark;
   for (int s = 0; s < ne; s++) {
-    const int e = (int)(order[s] & 0xffffffffu);
+    const int e = color_key_elem(order[s]);
     for (int i = 0; i < 4; i++) {
       const int n = conn[4 * e + i];
       for (int k = ptr[n]; k < ptr[n + 1]; k++) {

@@ -46,18 +46,8 @@ struct KParams {
   const struct ZeroPlan *zplan;
 };
 
-// A2DS_DMMA_FREE=1 drops the `volatile`: the instruction has no side effects, and without it the
-// scheduler may move other work between two DMMAs (ptxas puts a NOP between back-to-back ones)
-#ifndef A2DS_DMMA_FREE
-#define A2DS_DMMA_FREE 0
-#endif
-#if A2DS_DMMA_FREE
-#define A2DS_DMMA_ASM asm
-#else
-#define A2DS_DMMA_ASM asm volatile
-#endif
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  A2DS_DMMA_ASM("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
