@@ -17,6 +17,17 @@
 #include "mitc4_tying.h"
 
 using namespace a2ds;
+// work description of the zeroing a launch of k_assemble_t does on the side (see the comment in
+// front of A2DS_ZWAIT below)
+struct ZeroPlan {
+  double2 *zK, *zG;        // arrays to zero (null: none)
+  long long nK, nG;        // lengths in double2 units
+  int cK, cG;              // chunk of one warp in one round (double2 units, whole blocks)
+  float inv_round;         // 1 / (blocks per round)
+  int rounds, ahead;       // number of rounds; rounds zeroed before the first batch
+  int *done;               // per round: number of warps that have zeroed it
+};
+
 struct KParams {
   const int *elem_list;  // elements to process (NULL: 0..n_list-1)
   int n_list;
@@ -44,7 +55,14 @@ struct KParams {
   // zeroing of the output matrices inside k_assemble_t (cooperative launch; null: the caller
   // zeroed them): see ZeroPlan
   const struct ZeroPlan *zplan;
+  // A2DS_ZWAIT == 2 (double buffering): the plan by value, zval.rounds == 0: nothing to zero
+  ZeroPlan zval;
 };
+#if !defined(A2DS_ZWAIT) || A2DS_ZWAIT == 2
+#define A2DS_ZP(p) ((p).zval)
+#else
+#define A2DS_ZP(p) (*(p).zplan)
+#endif
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -491,14 +509,6 @@ __device__ __forceinline__ int et_at(int bi, int rr, int bj, int cc) {
 // The zeros are still in L2 when the REDs arrive: nothing is read from DRAM and every block is
 // written to DRAM once.  No __threadfence(), no call: either one, merely present in the
 // kernel, costs every variant 15-17 % (measured; profiles/README.md).
-struct ZeroPlan {
-  double2 *zK, *zG;        // arrays to zero (null: none)
-  long long nK, nG;        // lengths in double2 units
-  int cK, cG;              // chunk of one warp in one round (double2 units, whole blocks)
-  float inv_round;         // 1 / (blocks per round)
-  int rounds, ahead;       // number of rounds; rounds zeroed before the first batch
-  int *done;               // per round: number of warps that have zeroed it
-};
 #ifndef A2DS_MB_T
 #define A2DS_MB_T 2
 #endif
@@ -509,8 +519,13 @@ struct ZeroPlan {
 #define A2DS_ELEM_SYNC 0
 #endif
 #ifndef A2DS_ZWAIT
-#define A2DS_ZWAIT 0   // 1: zeroing of the output matrices inside k_assemble_t (see ZeroPlan).  Built
-#endif                 // and measured, not faster than the memsets it replaces (profiles/README.md): off
+#define A2DS_ZWAIT 2   // 1: zeroing of the output matrices inside k_assemble_t with the round protocol of
+#endif                 // ZeroPlan.  Built and measured, not faster than the memsets it replaces
+                       // (profiles/README.md).  2 (default): double buffering — the kernel zeroes the
+                       // SPARE value array of each matrix (the one the next assembly will add into) with
+                       // bulk copies spread over the lanes; nothing in the launch depends on them, so
+                       // there is no fence, no counter and no wait: rounds are only the way the work is
+                       // spread over the trips.  0: memsets in front of the kernel.
 struct BatchTmp {   // node-phase outputs only the Gauss-point phase reads; overlaid on the staging
   double dr[12], etn[4], pad_[4];   // tile E, which is only live inside the per-element loop
 };                  // 20 doubles = 4 (mod 16)
@@ -632,6 +647,29 @@ __device__ __forceinline__ void zero_chunk(double2 *zb, long long n2, int c2, in
     dst += n; bytes -= n;
   }
 }
+#if A2DS_ZWAIT == 2
+// the same chunk with the bulk copies spread over the lanes (segment i of ZERO_SRC_BYTES by lane
+// i mod 32): one predicated instruction per lane instead of a loop in lane 0.  Bulk async-groups
+// are per thread: every lane commits, and waits for, its own copies.  (An L2 evict_first hint on
+// the copies changes nothing: measured.)
+__device__ __forceinline__ void zero_chunk_lanes(double2 *zb, long long n2, int c2, int r, int gw, int n_gw,
+                                                 unsigned src, int lane) {
+  if (!zb) return;
+  const long long s0 = ((long long)r * n_gw + gw) * c2;
+  const long long left = n2 - s0;
+  const int bytes = 16 * (left < c2 ? (left > 0 ? (int)left : 0) : c2);
+  unsigned char *dst = reinterpret_cast<unsigned char *>(zb + s0);
+  for (int o = lane * ZERO_SRC_BYTES; o < bytes; o += 32 * ZERO_SRC_BYTES) {
+    const int n = bytes - o > ZERO_SRC_BYTES ? ZERO_SRC_BYTES : bytes - o;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + o), "r"(src), "r"(n) : "memory");
+  }
+}
+__device__ __forceinline__ void zero_round(const ZeroPlan &z, int r, int gw, int n_gw, unsigned src, int lane) {
+  zero_chunk_lanes(z.zK, z.nK, z.cK, r, gw, n_gw, src, lane);
+  zero_chunk_lanes(z.zG, z.nG, z.cG, r, gw, n_gw, src, lane);
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+#else
 __device__ __forceinline__ void zero_round(const ZeroPlan &z, int r, int gw, int n_gw, unsigned src, int lane) {
   if (lane == 0) {
     zero_chunk(z.zK, z.nK, z.cK, r, gw, n_gw, src);
@@ -639,6 +677,7 @@ __device__ __forceinline__ void zero_round(const ZeroPlan &z, int r, int gw, int
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 }
+#endif
 // round r of this warp is zeroed: wait for the bulk copies, then count it (release)
 __device__ __forceinline__ void zero_publish(int *done, int r, int lane) {
   if (lane == 0) {
@@ -760,18 +799,25 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
 
 #if A2DS_ZWAIT
   // zeroing of the output matrices by rounds (see ZeroPlan)
-  const bool zon = p.zplan != nullptr;
+#if A2DS_ZWAIT == 2
+  const bool zon = (KMAT || GMAT) && p.zval.rounds > 0;
+#else
+  const bool zon = (KMAT || GMAT) && p.zplan != nullptr;
+#endif
   const int gw = blockIdx.x * (blockDim.x >> 5) + warp, n_gw = gridDim.x * (blockDim.x >> 5);
   int zr = 0;        // rounds this warp has zeroed (the last one possibly not yet published)
   int zknown = -1;   // highest round known complete on all warps
   bool zpend = false;
+#if A2DS_ZWAIT == 1
   if (zon) {
-    const ZeroPlan z = *p.zplan;
+    const ZeroPlan &z = A2DS_ZP(p);
     for (; zr < z.rounds && zr < z.ahead; zr++) {
       zero_round(z, zr, gw, n_gw, zsrc, lane);
       zero_publish(z.done, zr, lane);
     }
   }
+#endif
+  (void)zknown; (void)zpend;
 #endif
 
   auto batch_ids = [&](int grp_, int &e_out, int &nd_out) {
@@ -845,9 +891,13 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
     const int base = grp * NB;
     const int cnt = grp < n_groups ? min(NB, p.n_list - base) : 0;
 #if A2DS_ZWAIT
-    if (zon && zr < p.zplan->rounds) {   // issued here, published after the batched phases
-      zero_round(*p.zplan, zr, gw, n_gw, zsrc, lane);
+    if (zon && zr < A2DS_ZP(p).rounds) {   // issued here, published after the batched phases
+      zero_round(A2DS_ZP(p), zr, gw, n_gw, zsrc, lane);
+#if A2DS_ZWAIT == 1
       zpend = true;
+#else
+      zr++;   // spare array: nobody waits for it inside this launch
+#endif
     }
 #endif
     int e_nxt = -1, nd_nxt = 0;
@@ -877,10 +927,10 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       issue_gather(buf ? ws.raw0 : ws.raw1, ws.goff[buf ^ 1], e_nxt, nd_nxt);
     e_cur = e_nxt; nd_cur = nd_nxt;
     __syncwarp();
-#if A2DS_ZWAIT
+#if A2DS_ZWAIT == 1
     if (zon) {
-      const int n_zr = p.zplan->rounds;
-      int *zdone = p.zplan->done;
+      const int n_zr = A2DS_ZP(p).rounds;
+      int *zdone = A2DS_ZP(p).done;
       if (zpend) { zero_publish(zdone, zr, lane); zr++; zpend = false; }
       // the round the highest block offset of this batch falls into must be complete (rounded
       // up: one round early costs nothing, one round late is a race)
@@ -895,14 +945,14 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mxw = max(mxw, __shfl_xor_sync(FULL, mxw, o));
-      const int rneed = min(n_zr - 1, (int)((float)mxw * p.zplan->inv_round) + 1);
+      const int rneed = min(n_zr - 1, (int)((float)mxw * A2DS_ZP(p).inv_round) + 1);
       while (rneed > zknown) {
         int v = 0;
         if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(zdone + rneed) : "memory");
         v = __shfl_sync(FULL, v, 0);
         if (v >= n_gw) { zknown = rneed; break; }
         if (zr < n_zr) {   // zero ahead instead of idling
-          zero_round(*p.zplan, zr, gw, n_gw, zsrc, lane);
+          zero_round(A2DS_ZP(p), zr, gw, n_gw, zsrc, lane);
           zero_publish(zdone, zr, lane);
           zr++;
         }
@@ -1089,12 +1139,18 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MB_T) k_assembl
 #if A2DS_ZWAIT
   // rounds this warp has not reached yet (short lists, warps without a batch)
   if (zon) {
-    const ZeroPlan z = *p.zplan;
+    const ZeroPlan &z = A2DS_ZP(p);
+#if A2DS_ZWAIT == 1
     if (zpend) { zero_publish(z.done, zr, lane); zr++; }
     for (; zr < z.rounds; zr++) {
       zero_round(z, zr, gw, n_gw, zsrc, lane);
       zero_publish(z.done, zr, lane);
     }
+#else
+    for (; zr < z.rounds; zr++) zero_round(z, zr, gw, n_gw, zsrc, lane);
+    // the bulk copies read bs.zero_src: they must have completed before the block retires
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
   }
 #endif
 }

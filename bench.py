@@ -6,7 +6,9 @@
 One "step" is one pass of the hot path over the whole (per-rank) mesh: the fused
 residual + tangent stiffness + geometric stiffness assembly of every MITC4 element
 into two device-resident BCSR matrices and the residual vector, including the
-zeroing of the outputs, the boundary-condition kernels and, for N > 1, the NCCL ghost
+zeroing of the outputs (done by the element kernel itself for the value arrays the NEXT step
+adds into — the matrices are double buffered —, one zeroing per step all the same), the
+boundary-condition kernels and, for N > 1, the NCCL ghost
 exchanges (forward for the state, reverse-add for the residual).
 
 Workload (N = 1): BASELINE.json configs[1], flat plate 1000 x 1000 MITC4 quads, seeded
@@ -671,9 +673,17 @@ def main():
                                                   if args.workload == "wingbox" else
                                                   f"{world} row slabs, first-touch ownership"),
                 "l2": f"outputs (2 x {n_elems * 2592 / 1e9:.1f} GB BCSR) and inputs exceed the 126 MB L2 every step",
-                "scatter": args.scatter},
+                "scatter": args.scatter,
+                "zeroing": ("matrices double buffered on the device: the element kernel zeroes the spare value "
+                            "array of K and G for the next step while it adds into the current one, the step "
+                            "swaps instead of zeroing (A2DS_DOUBLE_BUFFER=0: two memsets in front of the kernel)"
+                            if os.environ.get("A2DS_DOUBLE_BUFFER", "1") != "0" else "memsets in front of the kernel")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm,
+                         # the same algorithmic bytes over the whole step (zeroing, BC kernels, halo)
+                         "frac_of_step": alg_bytes * n_elems / (r["ms_step"] * 1e-3) / 1e9 / hbm,
+                         "kernel_includes": "the zeroing of the spare value arrays (5184 B/element of extra DRAM "
+                                            "writes) that used to be two memsets outside the kernel",
                          "traffic": cnt["dram_bytes_per_elem"] * n_elems if quote else None,
                          "traffic_source": (cnt.get("report") if quote else
                                             "no capture of this kernel build / workload (profiles/kernel_counters.json)"),

@@ -178,6 +178,13 @@ int a2ds_mat_zero(a2ds_ctx *ctx, int mat);
  * reference solver" path: BCSRMat::getArrays) / borrow the device pointer */
 int a2ds_mat_download(a2ds_ctx *ctx, int mat, int block, double *A);
 int a2ds_mat_values_dev(a2ds_ctx *ctx, int mat, int block, double **A_dev);
+/* NOTE: the borrowed pointer is valid until the next a2ds_assemble_* call that zeroes this matrix:
+ * matrices that take part in assembleJacobian / assembleMatType(G) / a2ds_assemble_all are double
+ * buffered on the device (the element kernel zeroes the value array the NEXT assembly will add
+ * into, and that assembly swaps the two arrays instead of zeroing: TACSMat::zeroEntries without a
+ * pass over the matrix); ask again after each assembly.  Every other entry point (download, copy,
+ * axpy, mult, apply_bcs) follows the swap.  A2DS_DOUBLE_BUFFER=0 switches it off; it is also
+ * skipped for a matrix whose second array would take the last 15 % of the GPU's memory. */
 /* the blocks of the listed block rows only, row after row (36 doubles per block): spot checks
  * of matrices too large to copy back (a row loop over BCSRMat::getArrays, BCSRMat.cpp:2312) */
 int a2ds_mat_download_rows(a2ds_ctx *ctx, int mat, int block, int n_rows, const int *rows,

@@ -196,6 +196,60 @@ def test_streamed_assembly_vs_oracle(a2ds, orc, name, chunks, monkeypatch):
     asm.close()
 
 
+@pytest.mark.parametrize("dbuf", ["1", "0"])
+def test_double_buffered_matrices_vs_oracle(a2ds, orc, dbuf, monkeypatch):
+    """matrices are double buffered on the device: the element kernel zeroes the spare value array
+    for the next assembly, which swaps instead of zeroing (run_assembly, csrc/a2ds.cu).  A sequence
+    of assemblies with changing states, entry points and matrix roles must give the oracle's
+    values every time — a block of the spare array left unzeroed, or a stale array after a swap,
+    shows up as a wrong entry; the same sequence with A2DS_DOUBLE_BUFFER=0 (memsets) as control."""
+    monkeypatch.setenv("A2DS_DOUBLE_BUFFER", dbuf)
+    conn, X, bcn = a2ds.meshes.cylinder(61, 37)      # 2257 elements: not a multiple of the batch
+    n = len(X)
+    Cs, eth = a2ds.iso_shell_tables()
+    asm = a2ds.Assembler(0)
+    asm.set_mesh(conn, n); asm.set_nodes(X); asm.set_components(Cs[None], eth[None])
+    asm.set_bcs(bcn, 63)
+    a = asm.create_mat(); b = asm.create_mat()
+    rowp, cols = asm.mat_pattern(a)
+    comp = orc.make_comp(0, Cs, eth)
+    ec = np.zeros(len(conn), dtype=np.int32)
+    bc_vars = np.full(len(bcn), 63, dtype=np.int32); bc_vals = np.zeros((len(bcn), 6))
+    states = [a2ds.meshes.seeded_state(np.arange(n) + 17 * k, scale=(k + 1) * 1e-5) for k in range(3)]
+    want = []
+    for u in states:
+        r_o, k_o = orc.assemble(1, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals)
+        _, g_o = orc.assemble(3, conn, ec, [comp], X, u, rowp, cols, bcn, bc_vars, bc_vals)
+        want.append((r_o, k_o, g_o))
+    def check(mat, ref_vals):
+        assert relmax(asm.mat_values(mat), ref_vals) < MAT_TOL
+    for it in range(7):                               # odd and even numbers of swaps per matrix
+        s = it % 3
+        asm.set_state(states[s])
+        r = asm.assembleAll(a, b)
+        assert relmax(r, want[s][0]) < RES_TOL
+        check(a, want[s][1]); check(b, want[s][2])
+    # roles exchanged, single-matrix entry points in between (K alone takes the memset path)
+    asm.set_state(states[1])
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, a); check(a, want[1][2])
+    asm.assembleMatType(a2ds.STIFFNESS_MATRIX, b); check(b, want[1][1])
+    asm.set_state(states[2])
+    r = asm.assembleJacobian(1.0, 0.0, 0.0, a, False); check(a, want[2][1])
+    asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, b); check(b, want[2][2])
+    asm.set_state(states[0])
+    asm.assembleMatType(a2ds.STIFFNESS_MATRIX, a); check(a, want[0][1])
+    r = asm.assembleAll(b, a)
+    assert relmax(r, want[0][0]) < RES_TOL
+    check(b, want[0][1]); check(a, want[0][2])
+    # device-side consumers follow the swap: y = K x through the SpMV against the host product
+    import torch
+    x = torch.randn(n, 6, dtype=torch.float64, device="cuda"); y = torch.zeros_like(x)
+    asm.mat_mult_dev(b, x.data_ptr(), y.data_ptr())
+    yh = bcsr_matvec(want[0][1].reshape(-1, 6, 6), rowp, cols, x.cpu().numpy())
+    assert relmax(y.cpu().numpy(), yh) < 1e-10
+    asm.close()
+
+
 @pytest.mark.parametrize("name", ["plate", "cylinder"])
 @pytest.mark.parametrize("order", [2, 3])
 def test_assembly_vs_reference_schur_and_parallel(a2ds, ref, name, order):

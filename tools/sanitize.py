@@ -48,6 +48,8 @@ blocks = [dict(nrows=n2, rowp=rowp, cols=cols, row_map=ident, col_map=ident, ide
 pk = asm.create_mat_from_pattern(blocks); pg = asm.create_mat_from_pattern(blocks)
 r2 = asm.assembleAll(pk, pg)
 asm.assembleJacobian(1.0, 0.0, 0.0, pk); asm.assembleMatType(1, pg)
+for _ in range(3):   # double-buffered matrices: swap with the spare array the previous kernel zeroed
+    r2 = asm.assembleAll(pk, pg)
 y2 = asm.addJacobianVecProduct(1.0, 1.0, np.ones((n2, 6)), np.zeros((n2, 6)))
 print("two-block", float(np.abs(r2).max()), float(np.abs(asm.mat_values(pk)).max()), float(np.abs(y2).max()))
 asm.close()
