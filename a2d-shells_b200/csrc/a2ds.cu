@@ -1406,15 +1406,12 @@ extern "C" int a2ds_mat_axpy(a2ds_ctx *c, double alpha, int x, int y) {
   A2DS_CATCH(a2ds_mat_axpy)
 }
 
+static int apply_mat_bcs(a2ds_ctx *c, int mat0, int mat1, int mat2);
 extern "C" int a2ds_mat_apply_bcs(a2ds_ctx *c, int mat) {
   A2DS_TRY
   if (check_mat(c, mat)) return 1;
   CU(cudaSetDevice(c->device));
-  if (!c->n_bc) return 0;
-  MatrixRec &m = c->mats[mat];
-  const int nt = c->n_bc * m.n_blocks;
-  k_mat_bcs<<<(nt + 127) / 128, 128, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars, m.n_blocks,
-                                                     m.blk_dev, m.A);
+  if (apply_mat_bcs(c, mat, -1, -1)) return 1;
   CU(cudaGetLastError());
   return 0;
   A2DS_CATCH(a2ds_mat_apply_bcs)
@@ -2007,12 +2004,21 @@ struct AsmReq {
   double *res_host = nullptr;
 };
 
-static int apply_mat_bcs(a2ds_ctx *c, int mat) {
+// boundary conditions of up to three matrices in one launch (-1: none)
+static int apply_mat_bcs(a2ds_ctx *c, int mat0, int mat1, int mat2) {
   if (!c->n_bc) return 0;
-  MatrixRec &m = c->mats[mat];
-  const int nt = c->n_bc * m.n_blocks;
-  k_mat_bcs<<<(nt + 127) / 128, 128, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars, m.n_blocks,
-                                                     m.blk_dev, m.A);
+  BcMats M;
+  int nm = 0, max_blocks = 0;
+  for (int mat : {mat0, mat1, mat2}) {
+    if (mat < 0) continue;
+    MatrixRec &m = c->mats[mat];
+    M.blk[nm] = m.blk_dev; M.A[nm] = m.A; M.n_blocks[nm] = m.n_blocks;
+    max_blocks = std::max(max_blocks, m.n_blocks);
+    nm++;
+  }
+  if (!nm) return 0;
+  const long long nt = 32ll * c->n_bc * max_blocks;
+  k_mat_bcs<<<dim3((unsigned)((nt + 127) / 128), nm), 128, 0, c->stream>>>(c->n_bc, c->bc_nodes, c->bc_vars, M);
   c->last_launches++;
   return 0;
 }
@@ -2295,9 +2301,8 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
   if (GM && !(KM && gmat == kmat) && mat_halo_reverse(c, c->mats[gmat])) return 1;
   if (MM && !(KM && mmat == kmat) && !(GM && mmat == gmat) && mat_halo_reverse(c, c->mats[mmat]))
     return 1;
-  if (KM && apply_mat_bcs(c, kmat)) return 1;
-  if (GM && !(KM && gmat == kmat) && apply_mat_bcs(c, gmat)) return 1;
-  if (MM && !(KM && mmat == kmat) && !(GM && mmat == gmat) && apply_mat_bcs(c, mmat)) return 1;
+  if (apply_mat_bcs(c, KM ? kmat : -1, (GM && !(KM && gmat == kmat)) ? gmat : -1,
+                    (MM && !(KM && mmat == kmat) && !(GM && mmat == gmat)) ? mmat : -1)) return 1;
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, c->stream));
   if (rq.res_host) {

@@ -232,24 +232,33 @@ __global__ void k_vec_copy_bcs(int n_bc, const int *nodes, const int *vars, cons
 // matrix BC rows: zero the constrained DOF rows of every block in the block row, 1.0 on
 // the diagonal entry of the diagonal block (BCSRMat::zeroRow, BCSRMat.cpp:2005-2030;
 // columns untouched, as the reference)
-__global__ void k_mat_bcs(int n_bc, const int *nodes, const int *vars, int n_blocks,
-                          const BlockDev *blk, double *A) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per (BC node, BCSR block): the lanes sweep the 36 entries of every block of the row
+// (coalesced); blockIdx.y selects the matrix, so the tangent and the geometric stiffness of a
+// fused assembly share one launch.
+struct BcMats {
+  const BlockDev *blk[3];
+  double *A[3];
+  int n_blocks[3];
+};
+__global__ void k_mat_bcs(int n_bc, const int *nodes, const int *vars, BcMats M) {
+  const int im = blockIdx.y;
+  const int n_blocks = M.n_blocks[im];
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n_bc * n_blocks) return;
   const int b = t / n_blocks, ib = t - b * n_blocks;
-  const BlockDev B = blk[ib];
+  const BlockDev B = M.blk[im][ib];
+  double *A = M.A[im];
   const int n = nodes[b], mask = vars[b];
   const int row = B.row_map ? B.row_map[n] : n;
   if (row < 0 || row >= B.nrows) return;
   const int diag_col = B.col_map ? B.col_map[n] : n;
   for (int j = B.rowp[row]; j < B.rowp[row + 1]; j++) {
     double *a = &A[36 * (size_t)(B.base + j)];
-    for (int ii = 0; ii < 6; ii++)
-      if (mask & (1 << ii))
-        for (int jj = 0; jj < 6; jj++) a[6 * ii + jj] = 0.0;
-    if (B.ident && B.cols[j] == diag_col)
-      for (int ii = 0; ii < 6; ii++)
-        if (mask & (1 << ii)) a[7 * ii] = 1.0;
+    const bool diag = B.ident && B.cols[j] == diag_col;
+    for (int e = lane; e < 36; e += 32) {
+      const int ii = e / 6, jj = e - 6 * ii;
+      if (mask & (1 << ii)) a[e] = (diag && ii == jj) ? 1.0 : 0.0;
+    }
   }
 }
 
