@@ -28,7 +28,7 @@ SYMBOLS = [
     "a2ds_comm_unique_id", "a2ds_comm_init", "a2ds_set_halo", "a2ds_halo_forward",
     "a2ds_halo_from_distribute",
     "a2ds_last_timing", "a2ds_host_pattern", "a2ds_host_color_elements",
-    "a2ds_host_color_elements_hashed", "a2ds_get_element_colors",
+    "a2ds_host_color_elements_hashed", "a2ds_get_element_colors", "a2ds_set_double_buffer",
     "a2ds_last_kernel_ms", "a2ds_region_begin", "a2ds_region_end",
     "a2ds_mat_copy", "a2ds_mat_axpy", "a2ds_mat_apply_bcs", "a2ds_mat_mult_dev", "a2ds_mat_mult",
     "a2ds_add_jacobian_vec_product", "a2ds_add_jacobian_vec_product_dev",
@@ -461,6 +461,10 @@ class Assembler:
 
     def set_scatter_mode(self, mode):
         self._chk(self.L.a2ds_set_scatter_mode(self.ctx, C.c_int(mode)))
+
+    def set_double_buffer(self, on):
+        """matrices double buffered on the device (default on); off frees the spare value arrays"""
+        self._chk(self.L.a2ds_set_double_buffer(self.ctx, C.c_int(1 if on else 0)))
 
     def element_colors(self):
         """element colours of the coloured scatter modes, computed on the device"""

@@ -628,6 +628,26 @@ extern "C" int a2ds_set_bcs(a2ds_ctx *c, int n_bc, const int *nodes, const int *
   A2DS_CATCH(a2ds_set_bcs)
 }
 
+extern "C" int a2ds_set_double_buffer(a2ds_ctx *c, int on) {
+  A2DS_TRY
+  CU(cudaSetDevice(c->device));
+  c->double_buffer = on != 0;
+  if (!on) {
+    // give the spare value arrays back (after whatever still zeroes them)
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto &m : c->mats) {
+      if (!m.spare) continue;
+      auto it = std::find(m.owned.begin(), m.owned.end(), (void *)m.spare);
+      if (it != m.owned.end()) m.owned.erase(it);
+      CU(cudaFree(m.spare));
+      m.spare = nullptr; m.spare_clean = false;
+    }
+  }
+  for (auto &m : c->mats) m.spare_refused = false;
+  return 0;
+  A2DS_CATCH(a2ds_set_double_buffer)
+}
+
 extern "C" int a2ds_set_scatter_mode(a2ds_ctx *c, int mode) {
   A2DS_TRY
   if (mode != A2DS_SCATTER_ATOMIC && mode != A2DS_SCATTER_COLORED &&

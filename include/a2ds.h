@@ -185,6 +185,8 @@ int a2ds_mat_values_dev(a2ds_ctx *ctx, int mat, int block, double **A_dev);
  * pass over the matrix); ask again after each assembly.  Every other entry point (download, copy,
  * axpy, mult, apply_bcs) follows the swap.  A2DS_DOUBLE_BUFFER=0 switches it off; it is also
  * skipped for a matrix whose second array would take the last 15 % of the GPU's memory. */
+/* the same switch at run time; on = 0 also frees the second value arrays (one matrix size each) */
+int a2ds_set_double_buffer(a2ds_ctx *ctx, int on);
 /* the blocks of the listed block rows only, row after row (36 doubles per block): spot checks
  * of matrices too large to copy back (a row loop over BCSRMat::getArrays, BCSRMat.cpp:2312) */
 int a2ds_mat_download_rows(a2ds_ctx *ctx, int mat, int block, int n_rows, const int *rows,

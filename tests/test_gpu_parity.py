@@ -229,6 +229,12 @@ def test_double_buffered_matrices_vs_oracle(a2ds, orc, dbuf, monkeypatch):
         r = asm.assembleAll(a, b)
         assert relmax(r, want[s][0]) < RES_TOL
         check(a, want[s][1]); check(b, want[s][2])
+    # switched off at run time (spare arrays freed) and on again (allocated anew)
+    asm.set_double_buffer(False)
+    r = asm.assembleAll(a, b); check(a, want[0][1]); check(b, want[0][2])
+    asm.set_double_buffer(dbuf == "1")
+    for _ in range(2):
+        r = asm.assembleAll(a, b); check(a, want[0][1]); check(b, want[0][2])
     # roles exchanged, single-matrix entry points in between (K alone takes the memset path)
     asm.set_state(states[1])
     asm.assembleMatType(a2ds.GEOMETRIC_STIFFNESS_MATRIX, a); check(a, want[1][2])
