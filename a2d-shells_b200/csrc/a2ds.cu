@@ -1696,6 +1696,24 @@ extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
 
 // ---- assembly ------------------------------------------------------------------
 static const int MAX_ZERO_ROUNDS = 4096;   // rounds of the in-kernel zeroing (see ZeroPlan)
+// double buffering: the share of the spare value arrays (c->pz_*) the launch about to be made
+// zeroes on the side, about one round per trip of a warp; by value in the kernel parameters
+static void spare_zero_plan(a2ds_ctx *c, KParams &p, int n_gw, int n_groups) {
+  p.zval.rounds = 0;
+  if (A2DS_ZWAIT != 2 || !(c->pz_K || c->pz_G)) return;
+  const int rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / std::max(1, n_gw)));
+  ZeroPlan zp;
+  memset(&zp, 0, sizeof(zp));
+  zp.zK = (double2 *)c->pz_K; zp.nK = 18ll * c->pz_nK;
+  zp.zG = (double2 *)c->pz_G; zp.nG = 18ll * c->pz_nG;
+  const long long per_round = (long long)rounds * n_gw;
+  zp.cK = 18 * (int)std::max<long long>(1, (c->pz_nK + per_round - 1) / per_round);   // whole blocks (18 double2)
+  zp.cG = 18 * (int)std::max<long long>(1, (c->pz_nG + per_round - 1) / per_round);
+  zp.rounds = rounds;
+  p.zval = zp;
+  c->pz_K = c->pz_G = nullptr;
+}
+
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 static int launch_one(a2ds_ctx *c, KParams &p) {
   const size_t raw = (GMAT || NL) ? sizeof(WarpScratch) : offsetof(WarpScratch, E2);
@@ -1732,6 +1750,7 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
   p.zplan = nullptr;
+  spare_zero_plan(c, p, grid * wpb, n_groups);
   CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
   kern<<<grid, wpb * 32, smem, c->stream>>>(p);
   CU(cudaGetLastError());
@@ -1773,9 +1792,9 @@ static int launch_one_t(a2ds_ctx *c, KParams &p) {
   const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
   p.zplan = nullptr;
-  p.zval.rounds = 0;
+  spare_zero_plan(c, p, grid * wpb, n_groups);
   int rounds = 0;
-  if (c->pz_K || c->pz_G) {
+  if (A2DS_ZWAIT == 1 && (c->pz_K || c->pz_G)) {
     // in-kernel zeroing by rounds (see ZeroPlan): about one round per trip of a warp
     static const int ahead = getenv("A2DS_ZERO_AHEAD") ? atoi(getenv("A2DS_ZERO_AHEAD")) : 3;
     const int n_gw = grid * wpb;
@@ -1793,16 +1812,9 @@ static int launch_one_t(a2ds_ctx *c, KParams &p) {
     zp.inv_round = (float)(1.0 / bpr) * (1.0f + 1e-6f);
     zp.rounds = rounds; zp.ahead = std::max(1, ahead);
     zp.done = c->work_counter + 1;
-    if (A2DS_ZWAIT == 2) {
-      // spare arrays: the plan travels with the kernel parameters, and there are no completion
-      // counters (nothing waits for a spare array)
-      p.zval = zp;
-      rounds = 0;
-    } else {
-      if (!c->zplan_dev) CU(cudaMalloc((void **)&c->zplan_dev, sizeof(ZeroPlan)));
-      CU(cudaMemcpyAsync(c->zplan_dev, &zp, sizeof(ZeroPlan), cudaMemcpyHostToDevice, c->stream));
-      p.zplan = c->zplan_dev;
-    }
+    if (!c->zplan_dev) CU(cudaMalloc((void **)&c->zplan_dev, sizeof(ZeroPlan)));
+    CU(cudaMemcpyAsync(c->zplan_dev, &zp, sizeof(ZeroPlan), cudaMemcpyHostToDevice, c->stream));
+    p.zplan = c->zplan_dev;
     c->pz_K = c->pz_G = nullptr;
   }
   CU(cudaMemsetAsync(c->work_counter, 0, (1 + rounds) * sizeof(int), c->stream));
@@ -2211,7 +2223,7 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     // loses more to the extra writes than the memset costs (measured: 2.59 -> 2.74 ms at 1 M
     // elements; residual + tangent 3.04 -> 2.85, geometric 4.27 -> 4.06, all three 5.76 -> 5.34)
     const bool dbuf = A2DS_ZWAIT == 2 && c->double_buffer && !first_form && c->npe == 4 && c->n_colors == 1 &&
-                      (KM || GM) && !MM && c->n_dep == 0 && first_cls >= 0 && first_cls < 2 &&
+                      (KM || GM) && !MM && c->n_dep == 0 && first_cls >= 0 &&
                       !(KM && GM && kmat == gmat) && (what == 3 || what == 4 || what == 7);
     if (dbuf) {
       auto prepare = [&](int mat, double *&sp, long long &spn, bool &clean) -> int {

@@ -17,8 +17,16 @@
 #include "mitc4_tying.h"
 
 using namespace a2ds;
-// work description of the zeroing a launch of k_assemble_t does on the side (see the comment in
-// front of A2DS_ZWAIT below)
+#ifndef A2DS_ZWAIT
+#define A2DS_ZWAIT 2   // 1: zeroing of the output matrices inside k_assemble_t with the round protocol of
+#endif                 // ZeroPlan.  Built and measured, not faster than the memsets it replaces
+                       // (profiles/README.md).  2 (default): double buffering — the kernel zeroes the
+                       // SPARE value array of each matrix (the one the next assembly will add into) with
+                       // bulk copies spread over the lanes; nothing in the launch depends on them, so
+                       // there is no fence, no counter and no wait: rounds are only the way the work is
+                       // spread over the trips.  0: memsets in front of the kernel.
+// work description of the zeroing a launch of an element kernel does on the side (see "zeroing
+// of the output matrices" below)
 struct ZeroPlan {
   double2 *zK, *zG;        // arrays to zero (null: none)
   long long nK, nG;        // lengths in double2 units
@@ -58,7 +66,7 @@ struct KParams {
   // A2DS_ZWAIT == 2 (double buffering): the plan by value, zval.rounds == 0: nothing to zero
   ZeroPlan zval;
 };
-#if !defined(A2DS_ZWAIT) || A2DS_ZWAIT == 2
+#if A2DS_ZWAIT == 2
 #define A2DS_ZP(p) ((p).zval)
 #else
 #define A2DS_ZP(p) (*(p).zplan)
@@ -253,11 +261,30 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+#if A2DS_ZWAIT == 2
+__device__ __forceinline__ void zero_round(const ZeroPlan &z, int r, int gw, int n_gw, unsigned src, int lane);
+#endif
+
 template <bool RES, bool KMAT, bool GMAT, bool NL>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT, NL))
     k_assemble(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#if A2DS_ZWAIT == 2
+  // double buffering (see k_assemble_t): the spare value arrays of the matrices are zeroed on
+  // the side, one round per trip, from a zeroed 1 KB buffer
+  __shared__ alignas(16) double zero_src1[128];
+  const bool zon = (KMAT || GMAT) && p.zval.rounds > 0;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp, n_gw = gridDim.x * (blockDim.x >> 5);
+  int zr = 0;
+  unsigned zsrc = 0;
+  if (KMAT || GMAT) {
+    if (threadIdx.x < 128) zero_src1[threadIdx.x] = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    zsrc = (unsigned)__cvta_generic_to_shared(zero_src1);
+    __syncthreads();
+  }
+#endif
   WarpScratch &ws = *reinterpret_cast<WarpScratch *>(smem_raw + (size_t)warp * p.scratch_bytes);
   ElemWork &wk = ws.work;
   // full scratch + asynchronous prefetch of the next batch
@@ -330,6 +357,9 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     if (lane == 0) drawn = atomicAdd(p.work_counter, 1);
     const int base = grp * NB;
     const int cnt = min(NB, p.n_list - base);
+#if A2DS_ZWAIT == 2
+    if (zon && zr < p.zval.rounds) { zero_round(p.zval, zr, gw, n_gw, zsrc, lane); zr++; }
+#endif
     // ids of the NEXT batch: requested now, consumed after the geometry phases
     int e_nxt = -1, nd_nxt = 0;
     if (PF) batch_ids(grp_nxt, e_nxt, nd_nxt);
@@ -471,6 +501,12 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, A2DS_MIN_BLOCKS(GMAT
     if (PF) { grp = grp_nxt; grp_nxt = drawn; }
     else { grp = drawn; batch_ids(grp, e_cur, nd_cur); }
   }
+#if A2DS_ZWAIT == 2
+  if (zon) {   // rounds this warp has not reached; the copies read zero_src1 until they complete
+    for (; zr < p.zval.rounds; zr++) zero_round(p.zval, zr, gw, n_gw, zsrc, lane);
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+#endif
 }
 
 
@@ -518,14 +554,6 @@ __device__ __forceinline__ int et_at(int bi, int rr, int bj, int cc) {
 #ifndef A2DS_ELEM_SYNC
 #define A2DS_ELEM_SYNC 0
 #endif
-#ifndef A2DS_ZWAIT
-#define A2DS_ZWAIT 2   // 1: zeroing of the output matrices inside k_assemble_t with the round protocol of
-#endif                 // ZeroPlan.  Built and measured, not faster than the memsets it replaces
-                       // (profiles/README.md).  2 (default): double buffering — the kernel zeroes the
-                       // SPARE value array of each matrix (the one the next assembly will add into) with
-                       // bulk copies spread over the lanes; nothing in the launch depends on them, so
-                       // there is no fence, no counter and no wait: rounds are only the way the work is
-                       // spread over the trips.  0: memsets in front of the kernel.
 struct BatchTmp {   // node-phase outputs only the Gauss-point phase reads; overlaid on the staging
   double dr[12], etn[4], pad_[4];   // tile E, which is only live inside the per-element loop
 };                  // 20 doubles = 4 (mod 16)
