@@ -58,6 +58,9 @@ class DeviceAssembler {
     check(a2ds_set_mass_moments(ctx_, n_comp, moments), "a2ds_set_mass_moments");
   }
   void haloForward() { check(a2ds_halo_forward(ctx_), "a2ds_halo_forward"); }
+  // matrices double buffered on the device (default on: no zeroEntries pass per assembly, one more
+  // value array per matrix); off frees the second arrays
+  void setDoubleBuffer(bool on) { check(a2ds_set_double_buffer(ctx_, on ? 1 : 0), "a2ds_set_double_buffer"); }
   // multi-GPU, one process per GPU: this rank's part of an element-wise partitioned global
   // mesh (node ownership and numbering as TACSCreator::createTACS) and its ghost-exchange
   // plan, then a2ds_set_mesh + a2ds_set_halo.  Returns local -> global node numbers.

@@ -193,6 +193,9 @@ static Shim &shim_get(TACSAssembler *self) {
     }
     const char *dev = getenv("A2DS_DEVICE");
     CK(a2ds_create(dev ? atoi(dev) : 0, &S.ctx));
+    // K and G go back to the host matrices after every assembly (shim_copy_back, PCIe bound):
+    // the second value arrays of the double-buffered matrices would only cost memory here
+    if (!getenv("A2DS_DOUBLE_BUFFER")) CK(a2ds_set_double_buffer(S.ctx, 0));
     fprintf(stderr, "[a2ds shim] %s: TACSAssembler %p -> device assembly (%d elements, %d nodes)\n",
             a2ds_version(), (void *)self, self->numElements, self->numNodes);
   }
