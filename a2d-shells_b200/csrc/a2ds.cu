@@ -1698,10 +1698,24 @@ extern "C" int a2ds_halo_forward(a2ds_ctx *c) {
 static const int MAX_ZERO_ROUNDS = 4096;   // rounds of the in-kernel zeroing (see ZeroPlan)
 // double buffering: the share of the spare value arrays (c->pz_*) the launch about to be made
 // zeroes on the side, about one round per trip of a warp; by value in the kernel parameters
-static void spare_zero_plan(a2ds_ctx *c, KParams &p, int n_gw, int n_groups) {
+static int spare_zero_plan(a2ds_ctx *c, KParams &p, int n_gw, int n_groups) {
   p.zval.rounds = 0;
-  if (A2DS_ZWAIT != 2 || !(c->pz_K || c->pz_G)) return;
-  const int rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / std::max(1, n_gw)));
+  if (A2DS_ZWAIT != 2 || !(c->pz_K || c->pz_G)) return 0;
+  n_gw = std::max(1, n_gw);
+  int rounds = std::max(1, std::min(MAX_ZERO_ROUNDS, n_groups / n_gw));
+  // a warp's chunk of one round stays below 256 MB (32-bit byte counts in the kernel): a short
+  // launch in front of a large matrix takes more rounds (done at the end of the kernel), and
+  // beyond MAX_ZERO_ROUNDS the array is zeroed by a memset after all
+  const long long max_blocks = (256ll << 20) / 288;
+  const long long need = (std::max(c->pz_K ? c->pz_nK : 0, c->pz_G ? c->pz_nG : 0) + max_blocks * n_gw - 1) /
+                         (max_blocks * n_gw);
+  if (need > MAX_ZERO_ROUNDS) {
+    if (c->pz_K) CU(cudaMemsetAsync(c->pz_K, 0, c->pz_nK * 36 * sizeof(double), c->stream));
+    if (c->pz_G) CU(cudaMemsetAsync(c->pz_G, 0, c->pz_nG * 36 * sizeof(double), c->stream));
+    c->pz_K = c->pz_G = nullptr;
+    return 0;
+  }
+  rounds = std::max(rounds, (int)need);
   ZeroPlan zp;
   memset(&zp, 0, sizeof(zp));
   zp.zK = (double2 *)c->pz_K; zp.nK = 18ll * c->pz_nK;
@@ -1712,6 +1726,7 @@ static void spare_zero_plan(a2ds_ctx *c, KParams &p, int n_gw, int n_groups) {
   zp.rounds = rounds;
   p.zval = zp;
   c->pz_K = c->pz_G = nullptr;
+  return 0;
 }
 
 template <bool RES, bool KMAT, bool GMAT, bool NL>
@@ -1750,7 +1765,7 @@ static int launch_one(a2ds_ctx *c, KParams &p) {
   const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
   p.zplan = nullptr;
-  spare_zero_plan(c, p, grid * wpb, n_groups);
+  if (spare_zero_plan(c, p, grid * wpb, n_groups)) return 1;
   CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
   kern<<<grid, wpb * 32, smem, c->stream>>>(p);
   CU(cudaGetLastError());
@@ -1792,7 +1807,7 @@ static int launch_one_t(a2ds_ctx *c, KParams &p) {
   const int want = (n_groups + wpb - 1) / wpb;
   const int grid = std::max(1, std::min(want, c->n_sm * per_sm));
   p.zplan = nullptr;
-  spare_zero_plan(c, p, grid * wpb, n_groups);
+  if (spare_zero_plan(c, p, grid * wpb, n_groups)) return 1;
   int rounds = 0;
   if (A2DS_ZWAIT == 1 && (c->pz_K || c->pz_G)) {
     // in-kernel zeroing by rounds (see ZeroPlan): about one round per trip of a warp
@@ -2019,6 +2034,19 @@ static void build_stream_plan(a2ds_ctx *c, bool ghost_last, StreamPlan &pl) {
   pl.ready = true;
 }
 
+// double buffering: the share of the spare arrays the next element launch zeroes, in proportion
+// to the elements it processes (`upto_elems` of `all_elems` done once it has run)
+static void spare_share(a2ds_ctx *c, long long upto_elems, long long all_elems) {
+  const bool last = upto_elems >= all_elems;
+  auto share = [&](double *sp, long long n, long long &done, double *&pz, long long &pzn) {
+    if (!sp) return;
+    const long long upto = last ? n : std::min(n, (long long)((double)n * (double)upto_elems / (double)all_elems));
+    if (upto > done) { pz = sp + 36 * done; pzn = upto - done; done = upto; }
+  };
+  share(c->sp_K, c->sp_nK, c->sp_doneK, c->pz_K, c->pz_nK);
+  share(c->sp_G, c->sp_nG, c->sp_doneG, c->pz_G, c->pz_nG);
+}
+
 struct AsmReq;
 // the element launches, the residual halo, its boundary conditions and its way back of a
 // streamed assembly (see a2ds_ctx::d2h_stream); the outputs are zeroed already
@@ -2142,14 +2170,7 @@ static int run_streamed(a2ds_ctx *c, const AsmReq &rq, KParams p, int cls, int w
       if (base.Goff) p.Goff = base.Goff + 16 * (size_t)e0;
       // this range's share of the spare arrays (double buffering), in proportion to its elements
       elems_done += e1 - e0;
-      const bool last = elems_done >= c->n_elems;
-      auto share = [&](double *sp, long long n, long long &done, double *&pz, long long &pzn) {
-        if (!sp) return;
-        const long long upto = last ? n : std::min(n, (long long)((double)n * (double)elems_done / (double)c->n_elems));
-        if (upto > done) { pz = sp + 36 * done; pzn = upto - done; done = upto; }
-      };
-      share(c->sp_K, c->sp_nK, c->sp_doneK, c->pz_K, c->pz_nK);
-      share(c->sp_G, c->sp_nG, c->sp_doneG, c->pz_G, c->pz_nG);
+      spare_share(c, elems_done, c->n_elems);
       if (launch_class(c, p, cls, what)) return 1;
     }
     if (finish_rows(at)) return 1;
@@ -2251,10 +2272,6 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
       if (KM && prepare(kmat, c->sp_K, c->sp_nK, clean_K)) return 1;
       if (GM && prepare(gmat, c->sp_G, c->sp_nG, clean_G)) return 1;
       c->sp_doneK = c->sp_doneG = 0;
-      if (!streamed) {
-        c->pz_K = c->sp_K; c->pz_nK = c->sp_nK;
-        c->pz_G = c->sp_G; c->pz_nG = c->sp_nG;
-      }
     }
     const bool set_K = KM && !clean_K, set_G = GM && !clean_G;
     if (zero_streamed && !set_K && !set_G) zero_streamed = false;
@@ -2285,11 +2302,14 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     if (state_wait(c)) return 1;  // the upload overlapped the zeroing above
     // state (and accelerations) of the dependent nodes: TACSBVec::endDistributeValues
     if (c->n_dep && (dep_gather(c, c->u, 6) || (c->udd && dep_gather(c, c->udd, 6)))) return 1;
+    long long elems_done = 0;
     for (int col = 0; col < c->n_colors; col++) {
       for (int cls = 0; cls < 4; cls++) {
         p.n_list = c->list_len[cls][col];
         p.elem_list = c->list_dev[cls][col];
         if (p.n_list == 0) continue;
+        elems_done += p.n_list;
+        spare_share(c, elems_done, c->n_elems);   // double buffering: every class launch its share
         if (launch_class(c, p, cls, what)) return 1;
         if (MM || MRES) {
           // mass path: same element lists (and colours), both element classes alike
@@ -2305,6 +2325,13 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
       }
     }
   }
+  // double buffering: whatever part of a spare array no launch took (should not happen: the
+  // element lists cover the mesh) is zeroed here, never left stale
+  if (c->sp_K && c->sp_doneK < c->sp_nK)
+    CU(cudaMemsetAsync(c->sp_K + 36 * c->sp_doneK, 0, (c->sp_nK - c->sp_doneK) * 36 * sizeof(double), c->stream));
+  if (c->sp_G && c->sp_doneG < c->sp_nG)
+    CU(cudaMemsetAsync(c->sp_G + 36 * c->sp_doneG, 0, (c->sp_nG - c->sp_doneG) * 36 * sizeof(double), c->stream));
+  c->sp_K = c->sp_G = nullptr;
   if (!streamed) CU(cudaEventRecord(c->evk1, c->stream));
   if (c->n_dep) {
     // what the elements added to dependent rows / node pairs goes to the independent nodes with
