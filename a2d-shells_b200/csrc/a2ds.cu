@@ -2243,7 +2243,10 @@ static int run_assembly(a2ds_ctx *c, const AsmReq &rq) {
     // (what == 2): that kernel is already bound by the read-modify-write traffic of its REDs and
     // loses more to the extra writes than the memset costs (measured: 2.59 -> 2.74 ms at 1 M
     // elements; residual + tangent 3.04 -> 2.85, geometric 4.27 -> 4.06, all three 5.76 -> 5.34)
-    const bool dbuf = A2DS_ZWAIT == 2 && c->double_buffer && !first_form && c->npe == 4 && c->n_colors == 1 &&
+    // (one launch per colour: only with the geometric stiffness in the pass — residual + tangent
+    // in colour-sized launches loses to the extra writes like the tangent alone, 3.76 -> 4.00 ms)
+    const bool dbuf = A2DS_ZWAIT == 2 && c->double_buffer && !first_form && c->npe == 4 &&
+                      (c->n_colors == 1 || (what & 4)) &&
                       (KM || GM) && !MM && c->n_dep == 0 && first_cls >= 0 &&
                       !(KM && GM && kmat == gmat) && (what == 3 || what == 4 || what == 7);
     if (dbuf) {
