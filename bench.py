@@ -197,6 +197,23 @@ PLATE_WORKLOAD = ("flat plate {nx}x{ny} MITC4 quads (BASELINE configs[1] per GPU
                   "residual+Kmat+Gmat, linear elastic iso shell")
 
 
+def arm_config(args, world, workload, n_elems):
+    """`config` of the JSON line — the workload and how our arm runs it; the reference arm carries
+    the identical object (it is timed on OUR arm's configuration), its own run details sit in
+    `reference_run` / `cpu_baseline`"""
+    return {
+        "workload": workload,
+        "elements_per_gpu": n_elems,
+        "partition": (f"{world} parts by recursive coordinate bisection, first-touch ownership"
+                      if args.workload == "wingbox" else f"{world} row slabs, first-touch ownership"),
+        "l2": f"outputs (2 x {n_elems * 2592 / 1e9:.1f} GB BCSR) and inputs exceed the 126 MB L2 every step",
+        "scatter": args.scatter,
+        "zeroing": ("matrices double buffered on the device: the element kernel zeroes the spare value "
+                    "array of K and G for the next step while it adds into the current one, the step "
+                    "swaps instead of zeroing (A2DS_DOUBLE_BUFFER=0: two memsets in front of the kernel)"
+                    if os.environ.get("A2DS_DOUBLE_BUFFER", "1") != "0" else "memsets in front of the kernel")}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the unmodified
     sources compiled into oracle/_ref), same metric and workload as our arm: one step = one
@@ -221,11 +238,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_pass"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": PLATE_WORKLOAD.format(nx=args.nx, ny=args.nx * args.gpus),
-                   "elements_per_gpu": r["n_elems"],
-                   "elements_per_step": r["n_elems"],
-                   "timed_passes": n_pass,
-                   "sample": r["sample"]},
+        "config": arm_config(args, args.gpus, PLATE_WORKLOAD.format(nx=args.nx, ny=args.nx * args.gpus),
+                             args.nx * args.nx),
+        "reference_run": {"elements_per_step": r["n_elems"], "timed_passes": n_pass, "sample": r["sample"]},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "elements/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -667,17 +682,7 @@ def main():
             "scaling": "strong" if r["strong"] else "weak",
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": r["wl"],
-                "elements_per_gpu": n_elems, "partition": (f"{world} parts by recursive coordinate bisection, first-touch ownership"
-                                                  if args.workload == "wingbox" else
-                                                  f"{world} row slabs, first-touch ownership"),
-                "l2": f"outputs (2 x {n_elems * 2592 / 1e9:.1f} GB BCSR) and inputs exceed the 126 MB L2 every step",
-                "scatter": args.scatter,
-                "zeroing": ("matrices double buffered on the device: the element kernel zeroes the spare value "
-                            "array of K and G for the next step while it adds into the current one, the step "
-                            "swaps instead of zeroing (A2DS_DOUBLE_BUFFER=0: two memsets in front of the kernel)"
-                            if os.environ.get("A2DS_DOUBLE_BUFFER", "1") != "0" else "memsets in front of the kernel")},
+            "config": arm_config(args, world, r["wl"], n_elems),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm,
                          # the same algorithmic bytes over the whole step (zeroing, BC kernels, halo)

@@ -24,7 +24,14 @@ def test_reference_arm_prints_one_json_line(ref):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "elements/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
-    assert "flat plate 1000x1000" in d["config"]["workload"] and "24x24" in d["config"]["sample"]
+    assert "flat plate 1000x1000" in d["config"]["workload"] and "24x24" in d["reference_run"]["sample"]
+    # the reference arm is timed on OUR arm's configuration: the same `config` object
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    ours = bench.arm_config(argparse.Namespace(workload="plate", scatter="atomic"), 1, d["config"]["workload"],
+                            1000 * 1000)
+    assert d["config"] == ours
     assert d["steps"] == 2 and d["warmup"] == 1
 
 
